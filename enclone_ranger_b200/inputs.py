@@ -1,0 +1,164 @@
+"""Host-side containers for the flattened join input (include/enclone_join_b200.h: ejb_input).
+
+JoinInput is numpy-backed so that tests can build micro-cases by hand; it mirrors, field for field,
+what the Rust shim (rust/enclone_join_b200) flattens from info[] / exact_clonotypes[] / to_bc /
+refdata before calling ejb_join.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._abi import EjbInput, SynthConfig, SynthSummary, load_synth
+
+_FIELDS = {
+    # name: (dtype, count attribute or None)
+    "row_nchains": np.int32, "row_len": np.int32, "row_tig_off": np.int64, "row_has_del": np.uint8,
+    "row_vs": np.int32, "row_js": np.int32, "row_cdr3_off": np.int64, "row_cdr3_len": np.int32,
+    "row_exact": np.int32, "row_exact_col": np.int32, "tig_bytes": np.uint8, "cdr3_bytes": np.uint8,
+    "ex_chain_off": np.int64, "ex_cell_off": np.int64,
+    "ch_left": np.uint8, "ch_c_ref": np.int32, "ch_v_ref": np.int32, "ch_u_ref": np.int32,
+    "ch_fr1_start": np.int32, "ch_cdr1_start": np.int32, "ch_fr2_start": np.int32,
+    "ch_cdr2_start": np.int32, "ch_fr3_start": np.int32, "ch_hcomp": np.int32,
+    "ch_amino_off": np.int64, "ch_amino_len": np.int32, "amino_bytes": np.uint8,
+    "cell_donor": np.int32, "cell_barcode": np.uint32,
+    "seg_off": np.int64, "seg_bytes": np.uint8, "ref_off": np.int64, "ref_bytes": np.uint8,
+    "ref_name_id": np.int32,
+}
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+_CT = {np.int32: C.c_int32, np.int64: C.c_int64, np.uint8: C.c_uint8, np.uint32: C.c_uint32}
+
+
+class JoinInput:
+    """Owns numpy arrays for every ejb_input field; `.c` is the matching C struct."""
+
+    def __init__(self, **arrays):
+        self.a = {}
+        for name, dt in _FIELDS.items():
+            v = np.ascontiguousarray(np.asarray(arrays.get(name, []), dtype=dt))
+            if v.size == 0:
+                v = np.zeros(1, dtype=dt)[:0].copy()
+            self.a[name] = v
+        a = self.a
+        self.n_rows = int(a["row_nchains"].size)
+        self.n_exacts = max(0, int(a["ex_chain_off"].size) - 1)
+        self.n_chains = int(a["ch_left"].size)
+        self.n_cells = int(a["cell_barcode"].size)
+        self.n_segs = max(0, int(a["seg_off"].size) - 1)
+        self.n_refs = max(0, int(a["ref_off"].size) - 1)
+        # keep 1-element backing stores alive for empty arrays so that pointers are non-NULL
+        self._keep = {n: (v if v.size else np.zeros(1, dtype=v.dtype)) for n, v in a.items()}
+        c = EjbInput()
+        for name, dt in _FIELDS.items():
+            setattr(c, name, _ptr(self._keep[name], _CT[dt]))
+        c.n_rows, c.n_exacts, c.n_chains = self.n_rows, self.n_exacts, self.n_chains
+        c.n_cells, c.n_segs, c.n_refs = self.n_cells, self.n_segs, self.n_refs
+        c.n_tig_bytes = int(a["tig_bytes"].size)
+        c.n_cdr3_bytes = int(a["cdr3_bytes"].size)
+        c.n_amino_bytes = int(a["amino_bytes"].size)
+        self.c = c
+
+    def c_ptr(self):
+        return C.pointer(self.c)
+
+    @staticmethod
+    def from_c(cin, copy=True):
+        """Build a JoinInput from an ejb_input struct (e.g. the synthetic generator's)."""
+        def arr(ptr, n, dt):
+            if n == 0:
+                return np.zeros(0, dtype=dt)
+            v = np.ctypeslib.as_array(ptr, shape=(n,))
+            return v.copy() if copy else v
+        N, E, CH, X, S, R = cin.n_rows, cin.n_exacts, cin.n_chains, cin.n_cells, cin.n_segs, cin.n_refs
+        sizes = {
+            "row_nchains": N, "row_len": 2 * N, "row_tig_off": 2 * N, "row_has_del": 2 * N, "row_vs": 2 * N,
+            "row_js": 2 * N, "row_cdr3_off": 2 * N, "row_cdr3_len": 2 * N, "row_exact": N,
+            "row_exact_col": 2 * N, "tig_bytes": cin.n_tig_bytes, "cdr3_bytes": cin.n_cdr3_bytes,
+            "ex_chain_off": E + 1, "ex_cell_off": E + 1, "ch_left": CH, "ch_c_ref": CH, "ch_v_ref": CH,
+            "ch_u_ref": CH, "ch_fr1_start": CH, "ch_cdr1_start": CH, "ch_fr2_start": CH,
+            "ch_cdr2_start": CH, "ch_fr3_start": CH, "ch_hcomp": CH, "ch_amino_off": CH,
+            "ch_amino_len": CH, "amino_bytes": cin.n_amino_bytes, "cell_donor": X, "cell_barcode": X,
+            "seg_off": S + 1, "seg_bytes": 0, "ref_off": R + 1, "ref_bytes": 0, "ref_name_id": R,
+        }
+        out = {}
+        for name, dt in _FIELDS.items():
+            if name in ("seg_bytes", "ref_bytes"):
+                continue
+            out[name] = arr(getattr(cin, name), sizes[name], dt)
+        out["seg_bytes"] = arr(cin.seg_bytes, int(out["seg_off"][-1]) if S else 0, np.uint8)
+        out["ref_bytes"] = arr(cin.ref_bytes, int(out["ref_off"][-1]) if R else 0, np.uint8)
+        return JoinInput(**out)
+
+    def take_rows(self, idx):
+        """A new JoinInput with only rows `idx` (in that order); other tables are kept whole."""
+        idx = np.asarray(idx, dtype=np.int64)
+        two = np.stack([2 * idx, 2 * idx + 1], axis=1).reshape(-1)
+        b = dict(self.a)
+        for n in ("row_nchains", "row_exact"):
+            b[n] = self.a[n][idx]
+        for n in ("row_len", "row_tig_off", "row_has_del", "row_vs", "row_js", "row_cdr3_off",
+                  "row_cdr3_len", "row_exact_col"):
+            b[n] = self.a[n][two]
+        return JoinInput(**b)
+
+    def nbytes(self):
+        return int(sum(v.nbytes for v in self.a.values()))
+
+
+class Repertoire:
+    """A synthetic repertoire produced by csrc/synth.cpp (owns the native buffers)."""
+
+    def __init__(self, handle, lib):
+        self._h, self._lib = handle, lib
+        self.c_ptr = lib.ejb_synth_input(handle)
+        self.c = self.c_ptr.contents
+        s = SynthSummary()
+        lib.ejb_synth_get_summary(handle, C.byref(s))
+        self.summary = s.as_dict()
+
+    def row_clone(self):
+        return np.ctypeslib.as_array(self._lib.ejb_synth_row_clone(self._h), shape=(self.c.n_rows,)).copy()
+
+    def to_join_input(self):
+        return JoinInput.from_c(self.c)
+
+    def close(self):
+        if self._h:
+            self._lib.ejb_synth_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def synth_config(config=0, **overrides):
+    lib = load_synth()
+    cfg = SynthConfig()
+    lib.ejb_synth_preset(int(config), C.byref(cfg))
+    for k, v in overrides.items():
+        if v is None:
+            continue
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def generate(config=0, **overrides):
+    """Generate BASELINE.json config `config` (0..4); keyword overrides e.g. n_cells=..., seed=..."""
+    lib = load_synth()
+    cfg = synth_config(config, **overrides)
+    h = C.c_void_p()
+    rc = lib.ejb_synth_generate(C.byref(cfg), C.byref(h))
+    if rc != 0:
+        raise RuntimeError(f"ejb_synth_generate failed: {rc}")
+    rep = Repertoire(h, lib)
+    rep.config = cfg
+    return rep

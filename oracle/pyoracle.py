@@ -1,0 +1,78 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes front-end of oracle/liboracle.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from enclone_ranger_b200._abi import OracleResult, load_oracle  # noqa: E402
+
+
+def _np(ptr, n, dt):
+    if n == 0:
+        return np.zeros(0, dtype=dt)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
+
+def run(params, c_input_ptr, threads=0):
+    """Run the CPU restatement of join_exacts.  Returns a dict of numpy arrays + counters."""
+    L = load_oracle()
+    r = OracleResult()
+    rc = L.oracle_join(C.byref(params), c_input_ptr, int(threads), C.byref(r))
+    if rc != 0:
+        msg = r.error.decode()
+        raise RuntimeError(f"oracle_join failed ({rc}): {msg}")
+    E, N = r.n_edges, r.n_rows
+    out = dict(
+        edge_k1=_np(r.edge_k1, E, np.int32), edge_k2=_np(r.edge_k2, E, np.int32),
+        edge_cd=_np(r.edge_cd, E, np.int32), edge_nrefs=_np(r.edge_nrefs, E, np.int32),
+        edge_shares=_np(r.edge_shares, 2 * E, np.int32).reshape(-1, 2),
+        edge_indeps=_np(r.edge_indeps, 2 * E, np.int32).reshape(-1, 2),
+        edge_k=_np(r.edge_k, E, np.int32), edge_d=_np(r.edge_d, E, np.int32), edge_n=_np(r.edge_n, E, np.int32),
+        edge_p1=_np(r.edge_p1, E, np.float64), edge_mult=_np(r.edge_mult, E, np.float64),
+        edge_score=_np(r.edge_score, E, np.float64), edge_err=_np(r.edge_err, E, np.uint8),
+        eq_x=_np(r.eq_x, N, np.int32), eq_y=_np(r.eq_y, N, np.int32), eq_z=_np(r.eq_z, N, np.int32),
+        labels=_np(r.labels, N, np.int32),
+        n_buckets=r.n_buckets, pairs_lens=r.pairs_lens, pairs_scored=r.pairs_scored,
+        join_one_calls=r.join_one_calls, pot_found=r.pot_found, two_cell_deleted=r.two_cell_deleted,
+        joins=r.joins, errors=r.errors, seconds_join=r.seconds_join, threads=r.threads,
+    )
+    L.oracle_result_free(C.byref(r))
+    return out
+
+
+def p1(k, d, n):
+    L = load_oracle()
+    v = C.c_double()
+    rc = L.oracle_p1(int(k), int(d), int(n), C.byref(v))
+    if rc != 0:
+        raise ValueError("out of range")
+    return v.value
+
+
+def sr_entry(n, k):
+    L = load_oracle()
+    hi, lo = C.c_double(), C.c_double()
+    L.oracle_sr_entry(int(n), int(k), C.byref(hi), C.byref(lo))
+    return hi.value, lo.value
+
+
+def dd_ops(a, b):
+    L = load_oracle()
+    out = (C.c_double * 8)()
+    L.oracle_dd_ops(a[0], a[1], b[0], b[1], out)
+    return [(out[2 * i], out[2 * i + 1]) for i in range(4)]
+
+
+def equiv_replay(n, a, b):
+    L = load_oracle()
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    b = np.ascontiguousarray(b, dtype=np.int32)
+    x = np.zeros(n, np.int32); y = np.zeros(n, np.int32); z = np.zeros(n, np.int32)
+    p = lambda v: v.ctypes.data_as(C.POINTER(C.c_int32))
+    L.oracle_equiv_replay(n, p(a), p(b), len(a), p(x), p(y), p(z))
+    return x, y, z
