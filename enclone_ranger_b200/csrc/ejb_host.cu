@@ -1,0 +1,1188 @@
+// ejb_host.cu — host orchestration and C ABI of the B200 clonotype join.
+//
+// Replaces, behind include/enclone_join_b200.h, the reference path
+//   join_exacts (enclone/src/join.rs:31-590) -> join_core (join_core.rs:11-51) ->
+//   join_one (enclone_core/src/join_one.rs:66-887) -> finish_join (join2.rs:36-87).
+// There is no CPU fallback: every entry point fails with EJB_ERR_NO_DEVICE / EJB_ERR_CUDA when the
+// device path cannot run.  See DESIGN.md for the round scheduler and the forest argument.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/enclone_join_b200.h"
+#include "ejb_device.cuh"
+#include "equiv.hpp"
+
+using namespace ejb;
+
+namespace {
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap && p) return cudaSuccess;
+        release();
+        size_t want = std::max<size_t>(bytes, 256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Unit {  // a run of row blocks of one sub-bucket, processed against all columns to its right
+    int32_t sub, rb0, rb1;
+};
+
+}  // namespace
+
+struct ejb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int shard_rank = 0, shard_world = 1;
+    unsigned long long cand_cap = 1ull << 26;
+    unsigned long long pair_budget = 1ull << 32;
+    uint32_t p1_cap = 1u << 22;
+    bool have_input = false, have_run = false;
+
+    // persistent
+    DevBuf d_sr, d_p1_keys, d_p1_vals, d_p1_new, d_ctr, d_err;
+    unsigned long long p1_count = 0;
+    Counters* h_ctr = nullptr;  // pinned
+
+    // uploaded input
+    ejb_params params;
+    DevIn din;
+    std::vector<DevBuf> in_bufs;
+    int64_t h2d_bytes = 0;
+    double ms_h2d = 0;
+
+    // derived (per run)
+    DevBuf d_head, d_scan, d_keys, d_keys2, d_vals, d_vals2, d_cubtmp, d_subhead, d_subincl, d_subinfo;
+    DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_m_flags, d_m_vs, d_m_js, d_m_tot, d_m_exact, d_m_chain;
+    DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
+    DevBuf d_tasks, d_cand, d_slow, d_slowslot, d_surv, d_pass, d_roots, d_forest;
+    DevBuf d_qofrow, d_deg, d_tuples, d_keep, d_first, d_labels, d_fkeys, d_fkeys2, d_fidx, d_fidx2, d_nout;
+    DevBuf d_o_k1, d_o_k2, d_o_cd, d_o_nrefs, d_o_sh, d_o_in, d_o_k, d_o_d, d_o_n, d_o_p1, d_o_mult, d_o_score, d_o_err;
+    std::vector<SubBucket> subs;
+    int64_t n_active = 0, n_pos = 0, n_blocks = 0, n_final = 0;
+    unsigned long long forest_cap = 0;
+    ejb_stats stats;
+
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    cudaEvent_t ev() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
+};
+
+namespace {
+
+int fail(ejb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(c, _e == cudaErrorMemoryAllocation ? EJB_ERR_OOM : EJB_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                        cudaGetErrorString(_e));                                                         \
+    } while (0)
+
+inline unsigned int nblk(int64_t n, int t) { return (unsigned int)std::max<int64_t>(1, (n + t - 1) / t); }
+
+// start.rs:50-99 with the product's dd arithmetic; triangular layout, row n at n(n+1)/2
+void build_sr_table(std::vector<dd_t>& s, int n_max) {
+    s.assign((size_t)(n_max + 1) * (n_max + 2) / 2, dd_make(0.0));
+    auto at = [&](int n, int k) -> dd_t& { return s[(size_t)n * (n + 1) / 2 + k]; };
+    at(0, 0) = dd_make(1.0);
+    std::vector<dd_t> z, n2n1(n_max + 1, dd_make(0.0)), k1k(n_max, dd_make(0.0)), njn(n_max + 1, dd_make(0.0));
+    for (int n = 2; n <= n_max; n++) n2n1[n] = dd_div(dd_make((double)(n - 2)), dd_make((double)(n - 1)));
+    for (int k = 1; k < n_max; k++) k1k[k] = dd_div(dd_make((double)(k - 1)), dd_make((double)k));
+    for (int n = 1; n <= n_max; n++) {
+        dd_t p = dd_make(1.0);
+        for (int j = 1; j <= n; j++) p = dd_mul(p, dd_div(dd_make((double)j), dd_make((double)n)));
+        njn[n] = p;
+    }
+    for (int n = 1; n <= n_max; n++) {
+        at(n, 0) = dd_make(0.0);
+        for (int k = 1; k + 1 < n; k++) z[k - 1] = dd_mul(z[k - 1], k1k[k]);
+        if (n >= 2) z.push_back(dd_powi(n2n1[n], n - 1));
+        for (int k = 1; k < n; k++) at(n, k) = dd_add(at(n - 1, k), dd_mul(at(n - 1, k - 1), z[k - 1]));
+        at(n, n) = njn[n];
+    }
+}
+
+const std::vector<dd_t>& sr_table_host() {
+    static std::vector<dd_t> t;
+    static std::once_flag once;
+    std::call_once(once, [] { build_sr_table(t, SR_NMAX); });
+    return t;
+}
+
+template <class T>
+int upload_array(ejb_ctx* c, const T* src, int64_t n, const T** dst) {
+    c->in_bufs.emplace_back();
+    DevBuf& b = c->in_bufs.back();
+    const size_t bytes = (size_t)std::max<int64_t>(n, 1) * sizeof(T);
+    CK(b.ensure(bytes + 16));
+    if (n > 0) {
+        if (!src) return fail(c, EJB_ERR_INVALID, "null input array with %lld elements", (long long)n);
+        CK(cudaMemcpyAsync(b.p, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+        c->h2d_bytes += (int64_t)n * sizeof(T);
+    }
+    *dst = b.as<const T>();
+    return EJB_OK;
+}
+
+int check_params(ejb_ctx* c, const ejb_params* p) {
+    if (p->unsupported_modes != 0)
+        return fail(c, EJB_ERR_UNSUPPORTED,
+                    "join mode mask 0x%x requested; only the enclone_ranger default join is implemented "
+                    "(bcjoin/basic/basic_h/basicx/join_full_diff/old_mult/force/super_comp_filt are rejected)",
+                    p->unsupported_modes);
+    if (p->ref_v_trim < 0 || p->ref_j_trim < 0 || p->max_degradation < 0) return fail(c, EJB_ERR_INVALID, "negative heuristic");
+    return EJB_OK;
+}
+
+DevParams make_dev_params(const ejb_params& p) {
+    DevParams P;
+    P.is_bcr = p.is_bcr;
+    P.mix_donors = p.mix_donors;
+    P.easy = p.easy;
+    P.old_light = p.old_light;
+    P.max_score = p.max_score;
+    P.cdr3_mult = p.cdr3_mult;
+    P.cdr3_ident_thr = 1.0 - p.join_cdr3_ident / 100.0;  // join_one.rs:231, evaluated once in f64
+    P.fwr1_cdr12_delta = p.fwr1_cdr12_delta;
+    P.max_cdr3_diffs = p.max_cdr3_diffs;
+    P.auto_share = p.auto_share;
+    P.comp_filt = p.comp_filt;
+    P.comp_filt_bound = p.comp_filt_bound;
+    P.max_diffs = p.max_diffs;
+    P.max_degradation = p.max_degradation;
+    P.ref_v_trim = p.ref_v_trim;
+    P.ref_j_trim = p.ref_j_trim;
+    return P;
+}
+
+int sync_counters(ejb_ctx* c) {
+    CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EJB_OK;
+}
+#define CTR_FIELD(f) (reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_ctr.p) + offsetof(Counters, f)))
+cudaError_t zero_counter(ejb_ctx* c, size_t off) {
+    return cudaMemsetAsync(reinterpret_cast<char*>(c->d_ctr.p) + off, 0, sizeof(unsigned long long), c->stream);
+}
+
+template <int W1>
+void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks) {
+    k_stage1<W1><<<(unsigned int)n_ctas, S1_THREADS, 0, c->stream>>>(c->d_subs.as<SubBucket>(), tasks, n_tasks, c->d_cdr3w.as<uint32_t>(),
+                                                                      c->d_labq.as<int32_t>(), c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(),
+                                                                      c->cand_cap, c->d_ctr.as<Counters>());
+}
+
+// stage-1 for sub-buckets whose CDR3s exceed the fast path: every not-yet-connected pair is a candidate
+__global__ void k_stage1_nofilter(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, int n_tasks,
+                                  const int32_t* __restrict__ labq, uint2* __restrict__ cand, unsigned long long cand_cap, Counters* ctr) {
+    const int64_t cta = blockIdx.x;
+    int lo = 0, hi = n_tasks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tasks[mid].cta0 <= cta) lo = mid; else hi = mid - 1;
+    }
+    const RowTask t = tasks[lo];
+    const SubBucket sb = subs[t.sub];
+    const int nb = (sb.n + TILE - 1) / TILE;
+    const int cb_first = t.rb + (int)(cta - t.cta0) * S1_STRIP;
+    unsigned long long ev = 0;
+    for (int cb = cb_first; cb < nb && cb < cb_first + S1_STRIP; cb++) {
+        for (int idx = threadIdx.x; idx < TILE * TILE; idx += blockDim.x) {
+            const int r = t.rb * TILE + (idx >> 7), cc = cb * TILE + (idx & 127);
+            if (r >= sb.n || cc >= sb.n || r >= cc) continue;
+            ev++;
+            const uint32_t q1 = (uint32_t)(sb.q0 + r), q2 = (uint32_t)(sb.q0 + cc);
+            if (labq[q1] == labq[q2]) continue;
+            const unsigned long long o = atomicAdd(&ctr->n_cand, 1ull);
+            if (o < cand_cap) cand[o] = make_uint2(q1, q2); else ctr->overflow = 1ull;
+        }
+    }
+    if (ev) atomicAdd(&ctr->pairs_eval, ev);
+}
+
+struct RoundTimes {
+    cudaEvent_t e0, e1, e2, e3;
+};
+
+S2Ctx make_s2ctx(ejb_ctx* c, int tuple_mode) {
+    S2Ctx X;
+    X.in = c->din;
+    X.P = make_dev_params(c->params);
+    X.subs = c->d_subs.as<SubBucket>();
+    X.M.row = c->d_m_row.as<int32_t>();
+    X.M.sub = c->d_m_sub.as<int32_t>();
+    X.M.flags = c->d_m_flags.as<uint32_t>();
+    X.M.vs = c->d_m_vs.as<int2>();
+    X.M.js = c->d_m_js.as<int2>();
+    X.M.tot = c->d_m_tot.as<int32_t>();
+    X.M.exact = c->d_m_exact.as<int32_t>();
+    X.M.chain = c->d_m_chain.as<int2>();
+    X.cdr3w = c->d_cdr3w.as<uint32_t>();
+    X.rowstore = c->d_rowstore.as<uint4>();
+    X.donor_mask = c->d_donor.as<unsigned long long>();
+    X.bc_sorted = c->d_bckeys2.as<uint64_t>();
+    X.powtab = c->d_powtab.as<double>();
+    X.pow_off = c->d_powoff.as<int32_t>();
+    X.p1.keys = c->d_p1_keys.as<unsigned long long>();
+    X.p1.vals = c->d_p1_vals.as<double>();
+    X.p1.newslots = c->d_p1_new.as<uint32_t>();
+    X.p1.cap_mask = c->p1_cap - 1;
+    X.ctr = c->d_ctr.as<Counters>();
+    X.surv = c->d_surv.as<Survivor>();
+    X.surv_cap = c->cand_cap;
+    X.slow = c->d_slow.as<uint2>();
+    X.slow_slot = c->d_slowslot.as<uint32_t>();
+    X.slow_cap = c->cand_cap;
+    X.tuple_mode = tuple_mode;
+    return X;
+}
+
+// stage 2 on the candidate list currently in `cand` (count on the device): 2a -> slow -> p1 -> 2b
+int run_stage2(ejb_ctx* c, const uint2* cand, const uint32_t* cand_slot, const unsigned long long* n_cand_dev, int tuple_mode) {
+    S2Ctx X = make_s2ctx(c, tuple_mode);
+    const int grid = c->sm_count * 8;
+    CK(zero_counter(c, offsetof(Counters, n_slow)));
+    CK(zero_counter(c, offsetof(Counters, n_surv)));
+    CK(zero_counter(c, offsetof(Counters, n_newkeys)));
+    k_stage2a<<<grid, 256, 0, c->stream>>>(X, cand, cand_slot, n_cand_dev, c->cand_cap);
+    k_stage2_slow<<<grid, 256, 0, c->stream>>>(X, CTR_FIELD(n_slow));
+    k_p1<<<grid, 256, 0, c->stream>>>(X.p1, c->d_sr.as<dd_t>(), CTR_FIELD(n_newkeys));
+    k_stage2b<<<grid, 256, 0, c->stream>>>(X, CTR_FIELD(n_surv), c->d_pass.as<unsigned long long>(), c->cand_cap, c->d_tuples.as<EdgeTuple>());
+    c->stats.kernel_launches += 4;
+    CK(cudaGetLastError());
+    return EJB_OK;
+}
+
+int p1_cache_clear(ejb_ctx* c) {
+    CK(cudaMemsetAsync(c->d_p1_keys.p, 0xff, (size_t)c->p1_cap * 8, c->stream));
+    c->p1_count = 0;
+    return EJB_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int ejb_abi_version(void) { return EJB_ABI_VERSION; }
+
+void ejb_params_default(ejb_params* p, int is_bcr) {
+    memset(p, 0, sizeof(*p));
+    p->is_bcr = is_bcr ? 1 : 0;
+    p->max_score = 100000.0;
+    p->cdr3_mult = 5.0;
+    p->mult_pow = 80.0;
+    p->join_cdr3_ident = 85.0;
+    p->fwr1_cdr12_delta = 20.0;
+    p->max_cdr3_diffs = 1000;
+    p->cdr3_normal_len = 42;
+    p->auto_share = 15;
+    p->comp_filt = 8;
+    p->comp_filt_bound = 80;
+    p->max_diffs = 1000000;
+    p->max_degradation = 2;
+    p->ref_v_trim = 15;
+    p->ref_j_trim = 15;
+}
+
+const char* ejb_last_error(const ejb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int ejb_create(ejb_ctx** out, const int* device_ids, int n_devices) {
+    if (!out) return EJB_ERR_INVALID;
+    *out = nullptr;
+    if (n_devices != 1) return EJB_ERR_UNSUPPORTED;  // one context drives one GPU; ranks/processes shard buckets (ejb_set_shard)
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return EJB_ERR_NO_DEVICE;
+    const int dev = device_ids ? device_ids[0] : 0;
+    if (dev < 0 || dev >= count) return EJB_ERR_NO_DEVICE;
+    ejb_ctx* c = new ejb_ctx();
+    c->device = dev;
+    if (cudaSetDevice(dev) != cudaSuccess) {
+        delete c;
+        return EJB_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, dev);
+    c->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("EJB_CAND_CAP")) c->cand_cap = std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
+    if (const char* e = getenv("EJB_PAIR_BUDGET")) c->pair_budget = std::max<unsigned long long>(1ull << 16, strtoull(e, nullptr, 10));
+    auto bail = [&](int code) {
+        std::string m = c->err;
+        delete c;
+        (void)m;
+        return code;
+    };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(EJB_ERR_CUDA);
+    if (cudaMallocHost(&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(EJB_ERR_OOM);
+    const std::vector<dd_t>& sr = sr_table_host();
+    if (c->d_sr.ensure(sr.size() * sizeof(dd_t)) != cudaSuccess) return bail(EJB_ERR_OOM);
+    cudaMemcpyAsync(c->d_sr.p, sr.data(), sr.size() * sizeof(dd_t), cudaMemcpyHostToDevice, c->stream);
+    if (c->d_p1_keys.ensure((size_t)c->p1_cap * 8) != cudaSuccess || c->d_p1_vals.ensure((size_t)c->p1_cap * 8) != cudaSuccess ||
+        c->d_p1_new.ensure((size_t)c->p1_cap * 4) != cudaSuccess || c->d_ctr.ensure(sizeof(Counters)) != cudaSuccess ||
+        c->d_err.ensure(64) != cudaSuccess)
+        return bail(EJB_ERR_OOM);
+    cudaMemsetAsync(c->d_p1_keys.p, 0xff, (size_t)c->p1_cap * 8, c->stream);
+    cudaMemsetAsync(c->d_ctr.p, 0, sizeof(Counters), c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(EJB_ERR_CUDA);
+    memset(&c->stats, 0, sizeof(c->stats));
+    *out = c;
+    return EJB_OK;
+}
+
+void ejb_destroy(ejb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    c->in_bufs.clear();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// Multi-GPU: this context only joins the sub-buckets it owns (LPT by pair count over `world`
+// owners, identical on every rank); the caller gathers the per-rank edge lists.
+int ejb_set_shard(ejb_ctx* c, int rank, int world) {
+    if (!c || world < 1 || rank < 0 || rank >= world) return EJB_ERR_INVALID;
+    c->shard_rank = rank;
+    c->shard_world = world;
+    return EJB_OK;
+}
+
+int ejb_set_capacity(ejb_ctx* c, unsigned long long cand_cap, unsigned long long pair_budget) {
+    if (!c) return EJB_ERR_INVALID;
+    if (cand_cap) c->cand_cap = std::max<unsigned long long>(1024, cand_cap);
+    if (pair_budget) c->pair_budget = std::max<unsigned long long>(1ull << 14, pair_budget);
+    return EJB_OK;
+}
+
+int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
+    if (!c || !p || !in) return EJB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    c->have_input = c->have_run = false;
+    int rc = check_params(c, p);
+    if (rc) return rc;
+    if (in->n_rows < 0 || in->n_rows >= (1ll << 28)) return fail(c, EJB_ERR_INVALID, "n_rows out of range (need 0 <= n < 2^28)");
+    if (in->n_exacts < 0 || in->n_chains < 0 || in->n_cells < 0 || in->n_segs < 0 || in->n_refs < 0) return fail(c, EJB_ERR_INVALID, "negative count");
+    if (in->n_rows > 0 && (in->n_exacts == 0 || in->n_segs == 0)) return fail(c, EJB_ERR_INVALID, "rows without exacts/segs");
+    c->params = *p;
+    const double t0 = now_ms();
+    c->in_bufs.clear();
+    c->in_bufs.reserve(64);
+    c->h2d_bytes = 0;
+    DevIn& d = c->din;
+    memset(&d, 0, sizeof(d));
+    d.n_rows = in->n_rows; d.n_exacts = in->n_exacts; d.n_chains = in->n_chains; d.n_cells = in->n_cells;
+    d.n_segs = in->n_segs; d.n_refs = in->n_refs;
+    d.n_tig_bytes = in->n_tig_bytes; d.n_cdr3_bytes = in->n_cdr3_bytes; d.n_amino_bytes = in->n_amino_bytes;
+    const int64_t N = in->n_rows;
+    // host-side: seg / ref byte totals need the last offset
+    if (in->n_segs > 0 && !in->seg_off) return fail(c, EJB_ERR_INVALID, "seg_off is null");
+    if (in->n_refs > 0 && !in->ref_off) return fail(c, EJB_ERR_INVALID, "ref_off is null");
+    d.n_seg_bytes = in->n_segs > 0 ? in->seg_off[in->n_segs] : 0;
+    d.n_ref_bytes = in->n_refs > 0 ? in->ref_off[in->n_refs] : 0;
+    if (d.n_seg_bytes < 0 || d.n_ref_bytes < 0) return fail(c, EJB_ERR_INVALID, "negative seg/ref byte count");
+    // content-canonical seg ids: DnaString equality is by content (join_one.rs:331)
+    std::vector<int32_t> canon((size_t)std::max<int64_t>(in->n_segs, 1), 0);
+    {
+        std::map<std::string, int> ids;
+        for (int64_t s = 0; s < in->n_segs; s++) {
+            const int64_t a = in->seg_off[s], b = in->seg_off[s + 1];
+            if (a < 0 || b < a || b > d.n_seg_bytes) return fail(c, EJB_ERR_INVALID, "seg_off not monotone");
+            std::string key((const char*)in->seg_bytes + a, (size_t)(b - a));
+            for (auto& ch : key) {  // 2-bit content: non-ACGT -> A, case-insensitive
+                switch (ch) {
+                    case 'C': case 'c': ch = 'C'; break;
+                    case 'G': case 'g': ch = 'G'; break;
+                    case 'T': case 't': ch = 'T'; break;
+                    default: ch = 'A';
+                }
+            }
+            auto it = ids.find(key);
+            if (it == ids.end()) it = ids.emplace(std::move(key), (int)ids.size()).first;
+            canon[s] = it->second;
+        }
+    }
+#define UP(field, n) if ((rc = upload_array(c, in->field, (n), &d.field)) != EJB_OK) return rc
+    UP(row_nchains, N); UP(row_len, 2 * N); UP(row_tig_off, 2 * N); UP(row_has_del, 2 * N); UP(row_vs, 2 * N); UP(row_js, 2 * N);
+    UP(row_cdr3_off, 2 * N); UP(row_cdr3_len, 2 * N); UP(row_exact, N); UP(row_exact_col, 2 * N);
+    UP(tig_bytes, in->n_tig_bytes); UP(cdr3_bytes, in->n_cdr3_bytes);
+    UP(ex_chain_off, in->n_exacts + 1); UP(ex_cell_off, in->n_exacts + 1);
+    UP(ch_left, in->n_chains); UP(ch_c_ref, in->n_chains); UP(ch_v_ref, in->n_chains); UP(ch_u_ref, in->n_chains);
+    UP(ch_hcomp, in->n_chains); UP(ch_amino_off, in->n_chains); UP(ch_amino_len, in->n_chains);
+    UP(amino_bytes, in->n_amino_bytes); UP(cell_donor, in->n_cells); UP(cell_barcode, in->n_cells);
+    UP(seg_off, in->n_segs + 1); UP(seg_bytes, d.n_seg_bytes); UP(ref_off, in->n_refs + 1); UP(ref_bytes, d.n_ref_bytes);
+    UP(ref_name_id, in->n_refs);
+#undef UP
+    if ((rc = upload_array(c, in->ch_fr1_start, in->n_chains, &d.ch_fr1)) != EJB_OK) return rc;
+    if ((rc = upload_array(c, in->ch_cdr1_start, in->n_chains, &d.ch_cdr1)) != EJB_OK) return rc;
+    if ((rc = upload_array(c, in->ch_fr2_start, in->n_chains, &d.ch_fr2)) != EJB_OK) return rc;
+    if ((rc = upload_array(c, in->ch_cdr2_start, in->n_chains, &d.ch_cdr2)) != EJB_OK) return rc;
+    if ((rc = upload_array(c, in->ch_fr3_start, in->n_chains, &d.ch_fr3)) != EJB_OK) return rc;
+    if ((rc = upload_array(c, canon.data(), in->n_segs, &d.seg_canon)) != EJB_OK) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    c->ms_h2d = now_ms() - t0;
+    c->have_input = true;
+    return EJB_OK;
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// ejb_run
+// ================================================================================================
+namespace {
+
+int cub_sort_pairs64(ejb_ctx* c, const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, int64_t n) {
+    size_t tmp = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, (int)n, 0, 64, c->stream));
+    CK(c->d_cubtmp.ensure(tmp));
+    CK(cub::DeviceRadixSort::SortPairs(c->d_cubtmp.p, tmp, kin, kout, vin, vout, (int)n, 0, 64, c->stream));
+    return EJB_OK;
+}
+int cub_sort_keys64(ejb_ctx* c, const uint64_t* kin, uint64_t* kout, int64_t n) {
+    size_t tmp = 0;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, kin, kout, (int)n, 0, 64, c->stream));
+    CK(c->d_cubtmp.ensure(tmp));
+    CK(cub::DeviceRadixSort::SortKeys(c->d_cubtmp.p, tmp, kin, kout, (int)n, 0, 64, c->stream));
+    return EJB_OK;
+}
+int cub_incl_sum(ejb_ctx* c, const int32_t* in, int32_t* out, int64_t n) {
+    size_t tmp = 0;
+    CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, in, out, (int)n, c->stream));
+    CK(c->d_cubtmp.ensure(tmp));
+    CK(cub::DeviceScan::InclusiveSum(c->d_cubtmp.p, tmp, in, out, (int)n, c->stream));
+    return EJB_OK;
+}
+
+// One scheduler round: stage 1 over `units`, stage 2, forest update.  Returns 1 when the
+// candidate buffer overflowed (nothing committed; the caller splits the round and retries).
+int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes>& times) {
+    const std::vector<SubBucket>& subs = c->subs;
+    // ---- tasks grouped by W1 ----
+    std::vector<RowTask> tasks[MAXW1 + 1];
+    int64_t nctas[MAXW1 + 1] = {0};
+    for (const Unit& u : units) {
+        const SubBucket& sb = subs[u.sub];
+        const int nb = (sb.n + TILE - 1) / TILE;
+        for (int rb = u.rb0; rb < u.rb1; rb++) {
+            RowTask t;
+            t.sub = u.sub;
+            t.rb = rb;
+            t.cta0 = nctas[sb.W1];
+            tasks[sb.W1].push_back(t);
+            nctas[sb.W1] += (nb - rb + S1_STRIP - 1) / S1_STRIP;
+        }
+    }
+    size_t total_tasks = 0;
+    for (auto& v : tasks) total_tasks += v.size();
+    CK(c->d_tasks.ensure(total_tasks * sizeof(RowTask)));
+    RoundTimes rt;
+    rt.e0 = c->ev(); rt.e1 = c->ev(); rt.e2 = c->ev(); rt.e3 = c->ev();
+    CK(zero_counter(c, offsetof(Counters, n_cand)));
+    CK(zero_counter(c, offsetof(Counters, n_pass)));
+    CK(zero_counter(c, offsetof(Counters, overflow)));
+    CK(cudaEventRecord(rt.e0, c->stream));
+    size_t off = 0;
+    for (int w = 0; w <= MAXW1; w++) {
+        if (tasks[w].empty()) continue;
+        RowTask* dt = c->d_tasks.as<RowTask>() + off;
+        CK(cudaMemcpyAsync(dt, tasks[w].data(), tasks[w].size() * sizeof(RowTask), cudaMemcpyHostToDevice, c->stream));
+        const int nt = (int)tasks[w].size();
+        switch (w) {
+            case 0:
+                k_stage1_nofilter<<<(unsigned int)nctas[0], 256, 0, c->stream>>>(c->d_subs.as<SubBucket>(), dt, nt, c->d_labq.as<int32_t>(),
+                                                                                c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr.as<Counters>());
+                break;
+            case 1: launch_stage1_w<1>(c, nctas[1], dt, nt); break;
+            case 2: launch_stage1_w<2>(c, nctas[2], dt, nt); break;
+            case 3: launch_stage1_w<3>(c, nctas[3], dt, nt); break;
+            case 4: launch_stage1_w<4>(c, nctas[4], dt, nt); break;
+            case 5: launch_stage1_w<5>(c, nctas[5], dt, nt); break;
+            case 6: launch_stage1_w<6>(c, nctas[6], dt, nt); break;
+        }
+        c->stats.kernel_launches++;
+        off += tasks[w].size();
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(rt.e1, c->stream));
+    int rc = run_stage2(c, c->d_cand.as<uint2>(), nullptr, CTR_FIELD(n_cand), 0);
+    if (rc) return rc;
+    CK(cudaEventRecord(rt.e2, c->stream));
+    // first Borůvka iteration is launched speculatively; its result is only used when nothing overflowed
+    const int grid = c->sm_count * 8;
+    CK(zero_counter(c, offsetof(Counters, n_alive)));
+    k_fill_u64<<<nblk(c->din.n_rows, 256), 256, 0, c->stream>>>(c->d_best.as<unsigned long long>(), c->din.n_rows, ~0ull);
+    k_bor_min<<<grid, 256, 0, c->stream>>>(c->d_pass.as<unsigned long long>(), CTR_FIELD(n_pass), c->cand_cap, c->d_parent.as<int32_t>(),
+                                          c->d_best.as<unsigned long long>(), 0, c->d_roots.as<int2>(), c->d_ctr.as<Counters>());
+    c->stats.kernel_launches += 2;
+    rc = sync_counters(c);
+    if (rc) return rc;
+    const Counters& h = *c->h_ctr;
+    if (h.overflow || h.n_cand > c->cand_cap || h.n_surv > c->cand_cap || h.n_pass > c->cand_cap || h.n_slow > c->cand_cap) {
+        c->ev_used -= 4;
+        return 1;
+    }
+    if (h.n_newkeys > c->p1_cap / 2) return fail(c, EJB_ERR_OOM, "p1 cache overflow (%llu new keys in one round)", h.n_newkeys);
+    if (h.n_errflag_range) return fail(c, EJB_ERR_RANGE, "k = indeps + 2*shares exceeds the Stirling table (k > 3000); the reference panics here (join_one.rs:30)");
+    if (h.n_errflag_panic) return fail(c, EJB_ERR_INVALID, "input on which the reference panics (J range longer than a contig, seg shorter than ref trim, or inconsistent feature starts)");
+    c->p1_count += h.n_newkeys;
+    c->stats.p1_unique += (int64_t)h.n_newkeys;
+    c->stats.stage1_candidates += (int64_t)h.n_cand;
+    c->stats.stage2_survivors += (int64_t)h.n_surv;
+    c->stats.pass_edges += (int64_t)h.n_pass;
+    if (h.n_pass > 0) {
+        int iter = 0;
+        unsigned long long alive = h.n_alive;
+        while (alive > 0) {
+            if (iter >= 60) return fail(c, EJB_ERR_CUDA, "forest did not converge");
+            k_bor_hook<<<grid, 256, 0, c->stream>>>(c->d_pass.as<unsigned long long>(), CTR_FIELD(n_pass), c->cand_cap, c->d_parent.as<int32_t>(),
+                                                   c->d_best.as<unsigned long long>(), iter, c->d_roots.as<int2>(),
+                                                   c->d_forest.as<unsigned long long>(), c->forest_cap, c->d_ctr.as<Counters>());
+            k_bor_compress<<<grid, 256, 0, c->stream>>>(CTR_FIELD(n_pass), c->cand_cap, c->d_parent.as<int32_t>(), c->d_roots.as<int2>());
+            iter++;
+            CK(zero_counter(c, offsetof(Counters, n_alive)));
+            k_bor_min<<<grid, 256, 0, c->stream>>>(c->d_pass.as<unsigned long long>(), CTR_FIELD(n_pass), c->cand_cap, c->d_parent.as<int32_t>(),
+                                                  c->d_best.as<unsigned long long>(), iter, c->d_roots.as<int2>(), c->d_ctr.as<Counters>());
+            c->stats.kernel_launches += 3;
+            rc = sync_counters(c);
+            if (rc) return rc;
+            if (c->h_ctr->overflow) return fail(c, EJB_ERR_CUDA, "forest buffer overflow");
+            alive = c->h_ctr->n_alive;
+        }
+        k_flatten<<<nblk(c->n_pos, 256), 256, 0, c->stream>>>(c->d_parent.as<int32_t>(), c->d_m_row.as<int32_t>(), c->n_pos, c->d_labq.as<int32_t>());
+        k_block_labels<<<nblk(c->n_blocks * 32, 256), 256, 0, c->stream>>>(c->d_subs.as<SubBucket>(), (int)subs.size(), c->d_labq.as<int32_t>(),
+                                                                          c->d_blklab.as<int32_t>(), c->d_blksub.as<int32_t>(), (int)c->n_blocks);
+        c->stats.kernel_launches += 2;
+    }
+    CK(cudaEventRecord(rt.e3, c->stream));
+    times.push_back(rt);
+    c->stats.rounds++;
+    return EJB_OK;
+}
+
+// runs `units` as one round; on overflow splits and recurses (each part commits before the next)
+int run_units(ejb_ctx* c, std::vector<Unit> units, std::vector<RoundTimes>& times, int depth) {
+    if (units.empty()) return EJB_OK;
+    int rc = run_round(c, units, times);
+    if (rc != 1) return rc;
+    if (depth > 40) return fail(c, EJB_ERR_OOM, "candidate buffer too small even for a single row block; raise EJB_CAND_CAP");
+    if (units.size() > 1) {
+        const size_t h = units.size() / 2;
+        std::vector<Unit> a(units.begin(), units.begin() + h), b(units.begin() + h, units.end());
+        rc = run_units(c, a, times, depth + 1);
+        if (rc) return rc;
+        return run_units(c, b, times, depth + 1);
+    }
+    Unit u = units[0];
+    if (u.rb1 - u.rb0 <= 1)
+        return fail(c, EJB_ERR_OOM, "candidate buffer (%llu) too small for one 128-row block of a %d-row sub-bucket; raise EJB_CAND_CAP", c->cand_cap,
+                    c->subs[u.sub].n);
+    const int mid = (u.rb0 + u.rb1) / 2;
+    Unit a = u, b = u;
+    a.rb1 = mid;
+    b.rb0 = mid;
+    rc = run_units(c, {a}, times, depth + 1);
+    if (rc) return rc;
+    return run_units(c, {b}, times, depth + 1);
+}
+
+}  // namespace
+
+extern "C" int ejb_run(ejb_ctx* c) {
+    if (!c) return EJB_ERR_INVALID;
+    if (!c->have_input) return fail(c, EJB_ERR_INVALID, "ejb_run without ejb_upload");
+    CK(cudaSetDevice(c->device));
+    c->have_run = false;
+    const double t_wall0 = now_ms();
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->ev_used = 0;
+    const DevIn& din = c->din;
+    const int64_t N = din.n_rows;
+    cudaStream_t st = c->stream;
+    cudaEvent_t ev_start = c->ev(), ev_packed = c->ev(), ev_rounds = c->ev(), ev_end = c->ev();
+    CK(cudaEventRecord(ev_start, st));
+    CK(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(Counters), st));
+    CK(cudaMemsetAsync(c->d_err.p, 0, 64, st));
+    if (c->p1_count > c->p1_cap / 4) {
+        int rc = p1_cache_clear(c);
+        if (rc) return rc;
+    }
+    c->subs.clear();
+    c->n_active = c->n_pos = c->n_blocks = c->n_final = 0;
+    std::vector<RoundTimes> times;
+
+    if (N > 0) {
+        // ---- bucket scan + sub-bucket sort (join.rs:68-88) ----
+        CK(c->d_head.ensure((size_t)N * 4));
+        CK(c->d_scan.ensure((size_t)N * 4));
+        CK(c->d_keys.ensure((size_t)N * 8));
+        CK(c->d_keys2.ensure((size_t)N * 8));
+        CK(c->d_vals.ensure((size_t)N * 4));
+        CK(c->d_vals2.ensure((size_t)N * 4));
+        k_heads<<<nblk(N, 256), 256, 0, st>>>(din, c->d_head.as<int32_t>(), c->d_err.as<unsigned int>());
+        const int64_t tmax = std::max({din.n_exacts, din.n_chains, din.n_cells, din.n_segs, din.n_refs});
+        k_validate_tables<<<nblk(tmax, 256), 256, 0, st>>>(din, c->d_err.as<unsigned int>());
+        int rc = cub_incl_sum(c, c->d_head.as<int32_t>(), c->d_scan.as<int32_t>(), N);
+        if (rc) return rc;
+        unsigned long long* d_nactive = reinterpret_cast<unsigned long long*>(c->d_err.as<char>() + 8);
+        k_keys<<<nblk(N, 256), 256, 0, st>>>(din, c->d_scan.as<int32_t>(), c->d_keys.as<uint64_t>(), c->d_vals.as<uint32_t>(), d_nactive);
+        c->stats.kernel_launches += 4;
+        rc = cub_sort_pairs64(c, c->d_keys.as<uint64_t>(), c->d_keys2.as<uint64_t>(), c->d_vals.as<uint32_t>(), c->d_vals2.as<uint32_t>(), N);
+        if (rc) return rc;
+        struct { unsigned int err; unsigned int pad; unsigned long long n_active; } hdr;
+        int32_t n_buckets = 0;
+        CK(cudaMemcpyAsync(&hdr, c->d_err.p, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&n_buckets, c->d_scan.as<int32_t>() + (N - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (hdr.err) return fail(c, EJB_ERR_INVALID, "input validation failed (mask 0x%x: 1 nchains, 2 exact id, 4 tig offsets, 8 cdr3 offsets, 16 seg ids, 32 exact_cols, 64/128 exact tables, 256 ref ids, 512 amino, 1024 donor id >= 64, 2048 seg_off, 4096 ref_off)", hdr.err);
+        c->stats.n_buckets = n_buckets;
+        c->n_active = (int64_t)hdr.n_active;
+    }
+    const int64_t NA = c->n_active;
+    const uint64_t* keys_sorted = c->d_keys2.as<uint64_t>();
+    const uint32_t* row_of = c->d_vals2.as<uint32_t>();
+    int n_subs = 0;
+    if (NA > 0) {
+        CK(c->d_subhead.ensure((size_t)NA * 4));
+        CK(c->d_subincl.ensure((size_t)NA * 4));
+        k_subheads<<<nblk(NA, 256), 256, 0, st>>>(keys_sorted, NA, c->d_subhead.as<int32_t>());
+        int rc = cub_incl_sum(c, c->d_subhead.as<int32_t>(), c->d_subincl.as<int32_t>(), NA);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&n_subs, c->d_subincl.as<int32_t>() + (NA - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(c->d_subinfo.ensure((size_t)n_subs * sizeof(SubInfo)));
+        k_subinfo<<<nblk(NA, 256), 256, 0, st>>>(din, keys_sorted, row_of, c->d_subhead.as<int32_t>(), c->d_subincl.as<int32_t>(), NA, c->d_subinfo.as<SubInfo>());
+        c->stats.kernel_launches += 2;
+        std::vector<SubInfo> si((size_t)n_subs);
+        CK(cudaMemcpyAsync(si.data(), c->d_subinfo.p, (size_t)n_subs * sizeof(SubInfo), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        c->stats.d2h_bytes += (int64_t)n_subs * sizeof(SubInfo);
+
+        // ---- sub-bucket table, offsets, thresholds ----
+        const DevParams P = make_dev_params(c->params);
+        std::vector<SubBucket>& subs = c->subs;
+        subs.resize(n_subs);
+        int64_t q = 0, s1 = 0, rs = 0, blk = 0;
+        int64_t bucket_rows = 0;
+        uint64_t cur_bucket = ~0ull;
+        int max_cdr3 = 0;
+        for (int s = 0; s < n_subs; s++) {
+            SubBucket& sb = subs[s];
+            sb.j0 = si[s].q0;
+            sb.n = (int32_t)(((s + 1 < n_subs) ? si[s + 1].q0 : NA) - si[s].q0);
+            sb.npad = (sb.n + 3) & ~3;
+            sb.ch = (int32_t)((si[s].key >> 16) & 0xffff);
+            sb.cl = (int32_t)(si[s].key & 0xffff);
+            sb.Lh = si[s].Lh;
+            sb.Ll = si[s].Ll;
+            const int T = sb.ch + sb.cl;
+            const int w1 = (T + 31) / 32;
+            sb.W1 = (w1 >= 1 && w1 <= MAXW1) ? w1 : 0;
+            const int w4h = (sb.Lh + 127) / 128, w4l = (sb.Ll + 127) / 128;
+            sb.W4h = (w4h >= 1 && w4h <= MAXW4) ? w4h : 0;
+            sb.W4l = (w4l >= 1 && w4l <= MAXW4) ? w4l : 0;
+            sb.rec_u4 = 3 * (sb.W4h + sb.W4l);
+            sb.q0 = q;
+            sb.s1_off = s1;
+            sb.rs_off = rs;
+            sb.blk0 = (int32_t)blk;
+            sb.n3 = 3 * (sb.Lh + sb.Ll);
+            sb.owner = 0;
+            // stage-1 threshold: a superset of join_one.rs:231 and :286-290 (stage 2 re-tests exactly)
+            int maxcd = T;
+            if (P.is_bcr) {
+                maxcd = 0;
+                for (int cd = T; cd >= 0; cd--)
+                    if (!((double)cd / (double)T > P.cdr3_ident_thr)) { maxcd = cd; break; }
+                if (T == 0) maxcd = 0;
+                if (P.max_cdr3_diffs < 1000) maxcd = (int)std::min<long long>(maxcd, P.max_cdr3_diffs);
+            } else {
+                maxcd = 0;  // TCR: cd > 0 rejects
+            }
+            sb.maxcd = maxcd;
+            max_cdr3 = std::max({max_cdr3, sb.ch, sb.cl});
+            q += sb.npad;
+            s1 += (int64_t)2 * sb.W1 * sb.npad;
+            rs += (int64_t)sb.n * sb.rec_u4;
+            blk += (sb.n + TILE - 1) / TILE;
+            c->stats.pairs_scored += (int64_t)sb.n * (sb.n - 1) / 2;
+            const uint64_t b = si[s].key >> 32;
+            if (b != cur_bucket) {
+                c->stats.pairs_lens += bucket_rows * (bucket_rows - 1) / 2;
+                bucket_rows = 0;
+                cur_bucket = b;
+            }
+            bucket_rows += sb.n;
+        }
+        c->stats.pairs_lens += bucket_rows * (bucket_rows - 1) / 2;
+        c->stats.n_subbuckets = n_subs;
+        c->n_pos = q;
+        c->n_blocks = blk;
+        if (q >= (1ll << 31)) return fail(c, EJB_ERR_INVALID, "too many packed rows");
+
+        // ---- multi-GPU ownership: LPT by pair count ----
+        if (c->shard_world > 1) {
+            std::vector<int> order(n_subs);
+            for (int s = 0; s < n_subs; s++) order[s] = s;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return subs[a].n > subs[b].n; });
+            std::vector<double> load(c->shard_world, 0.0);
+            for (int s : order) {
+                int best = 0;
+                for (int r = 1; r < c->shard_world; r++)
+                    if (load[r] < load[best]) best = r;
+                subs[s].owner = best;
+                load[best] += (double)subs[s].n * (subs[s].n - 1) / 2 + 64.0 * subs[s].n;
+            }
+        }
+
+        // ---- pow table: mult_pow ^ (cdr3_normal_len * cd / n), join_one.rs:531-539 ----
+        std::vector<int32_t> pow_off((size_t)max_cdr3 + 2, 0);
+        std::vector<char> len_used((size_t)max_cdr3 + 1, 0);
+        for (auto& sb : subs) len_used[sb.ch] = len_used[sb.cl] = 1;
+        std::vector<double> powtab;
+        for (int n = 0; n <= max_cdr3; n++) {
+            pow_off[n] = (int32_t)powtab.size();
+            if (!len_used[n]) continue;
+            for (int cd = 0; cd <= n; cd++)
+                powtab.push_back(std::pow(c->params.mult_pow, (double)c->params.cdr3_normal_len * (double)cd / (double)n));
+        }
+        if (powtab.empty()) powtab.push_back(1.0);
+        CK(c->d_powtab.ensure(powtab.size() * 8));
+        CK(c->d_powoff.ensure(pow_off.size() * 4));
+        CK(cudaMemcpyAsync(c->d_powtab.p, powtab.data(), powtab.size() * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->d_powoff.p, pow_off.data(), pow_off.size() * 4, cudaMemcpyHostToDevice, st));
+
+        // ---- device arrays ----
+        CK(c->d_subs.ensure((size_t)n_subs * sizeof(SubBucket)));
+        CK(cudaMemcpyAsync(c->d_subs.p, subs.data(), (size_t)n_subs * sizeof(SubBucket), cudaMemcpyHostToDevice, st));
+        std::vector<int32_t> blk_sub((size_t)blk);
+        for (int s = 0; s < n_subs; s++)
+            for (int b = 0; b < (subs[s].n + TILE - 1) / TILE; b++) blk_sub[subs[s].blk0 + b] = s;
+        CK(c->d_blksub.ensure((size_t)std::max<int64_t>(blk, 1) * 4));
+        CK(cudaMemcpyAsync(c->d_blksub.p, blk_sub.data(), (size_t)blk * 4, cudaMemcpyHostToDevice, st));
+        CK(c->d_cdr3w.ensure((size_t)(s1 + 4) * 4));
+        CK(c->d_rowstore.ensure((size_t)(rs + 1) * 16));
+        const size_t np = (size_t)c->n_pos + 4;
+        CK(c->d_m_row.ensure(np * 4)); CK(c->d_m_sub.ensure(np * 4)); CK(c->d_m_flags.ensure(np * 4)); CK(c->d_m_vs.ensure(np * 8));
+        CK(c->d_m_js.ensure(np * 8)); CK(c->d_m_tot.ensure(np * 4)); CK(c->d_m_exact.ensure(np * 4)); CK(c->d_m_chain.ensure(np * 8));
+        CK(c->d_labq.ensure(np * 4)); CK(c->d_blklab.ensure((size_t)std::max<int64_t>(blk, 1) * 4));
+        CK(cudaMemsetAsync(c->d_m_row.p, 0xff, np * 4, st));   // -1 = padding position
+        CK(cudaMemsetAsync(c->d_labq.p, 0xff, np * 4, st));
+        CK(cudaMemsetAsync(c->d_cdr3w.p, 0, (size_t)(s1 + 4) * 4, st));
+        RowMeta M;
+        M.row = c->d_m_row.as<int32_t>(); M.sub = c->d_m_sub.as<int32_t>(); M.flags = c->d_m_flags.as<uint32_t>();
+        M.vs = c->d_m_vs.as<int2>(); M.js = c->d_m_js.as<int2>(); M.tot = c->d_m_tot.as<int32_t>();
+        M.exact = c->d_m_exact.as<int32_t>(); M.chain = c->d_m_chain.as<int2>();
+        k_pack_rows<<<nblk(NA * 32, 256), 256, 0, st>>>(din, P, c->d_subs.as<SubBucket>(), c->d_subincl.as<int32_t>(), row_of, NA, c->d_cdr3w.as<uint32_t>(),
+                                                       c->d_rowstore.as<uint4>(), M);
+        c->stats.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    // ---- per exact: donor masks + sorted barcode lists ----
+    CK(c->d_donor.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 8));
+    CK(c->d_bckeys.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
+    CK(c->d_bckeys2.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
+    if (din.n_exacts > 0) {
+        k_exact_prep<<<nblk(din.n_exacts, 256), 256, 0, st>>>(din, c->d_donor.as<unsigned long long>(), c->d_bckeys.as<uint64_t>());
+        c->stats.kernel_launches++;
+        if (din.n_cells > 0) {
+            int rc = cub_sort_keys64(c, c->d_bckeys.as<uint64_t>(), c->d_bckeys2.as<uint64_t>(), din.n_cells);
+            if (rc) return rc;
+        }
+    }
+    // ---- union-find state, work buffers ----
+    CK(c->d_parent.ensure((size_t)std::max<int64_t>(N, 1) * 4));
+    CK(c->d_best.ensure((size_t)std::max<int64_t>(N, 1) * 8));
+    if (N > 0) k_iota<<<nblk(N, 256), 256, 0, st>>>(c->d_parent.as<int32_t>(), N);
+    if (c->n_pos > 0) {
+        k_flatten<<<nblk(c->n_pos, 256), 256, 0, st>>>(c->d_parent.as<int32_t>(), c->d_m_row.as<int32_t>(), c->n_pos, c->d_labq.as<int32_t>());
+        k_block_labels<<<nblk(c->n_blocks * 32, 256), 256, 0, st>>>(c->d_subs.as<SubBucket>(), n_subs, c->d_labq.as<int32_t>(), c->d_blklab.as<int32_t>(),
+                                                                   c->d_blksub.as<int32_t>(), (int)c->n_blocks);
+        c->stats.kernel_launches += 3;
+    }
+    const unsigned long long cap = c->cand_cap;
+    c->forest_cap = (unsigned long long)std::max<int64_t>(N, 1);
+    CK(c->d_cand.ensure(cap * 8)); CK(c->d_slow.ensure(cap * 8)); CK(c->d_slowslot.ensure(cap * 4));
+    CK(c->d_surv.ensure(cap * sizeof(Survivor))); CK(c->d_pass.ensure(cap * 8)); CK(c->d_roots.ensure(cap * 8));
+    CK(c->d_forest.ensure(c->forest_cap * 8));
+    CK(c->d_tuples.ensure(std::max<unsigned long long>(c->forest_cap, 1) * sizeof(EdgeTuple)));
+    CK(cudaEventRecord(ev_packed, st));
+
+    // ---- round scheduler ----
+    {
+        const std::vector<SubBucket>& subs = c->subs;
+        std::vector<int> next_rb(subs.size(), 0), grow(subs.size(), 1), live;
+        for (int s = 0; s < (int)subs.size(); s++)
+            if (subs[s].n >= 2 && subs[s].owner == c->shard_rank) live.push_back(s);
+        while (!live.empty()) {
+            std::vector<Unit> units;
+            unsigned long long pairs = 0;
+            std::vector<int> still;
+            for (int s : live) {
+                const SubBucket& sb = subs[s];
+                const int nb = (sb.n + TILE - 1) / TILE;
+                int g = std::min(grow[s], nb - next_rb[s]);
+                // pairs of rows [rb0*128, ...) x everything to the right
+                auto unit_pairs = [&](int rb0, int rb1) {
+                    const long long r0 = (long long)rb0 * TILE, r1 = std::min<long long>(sb.n, (long long)rb1 * TILE);
+                    const long long rows = r1 - r0;
+                    return (unsigned long long)(rows * (sb.n - r1) + rows * (rows - 1) / 2);
+                };
+                while (g > 1 && unit_pairs(next_rb[s], next_rb[s] + g) > c->pair_budget / 2) g /= 2;
+                const unsigned long long up = unit_pairs(next_rb[s], next_rb[s] + g);
+                if (!units.empty() && pairs + up > c->pair_budget) {
+                    still.push_back(s);
+                    continue;
+                }
+                Unit u;
+                u.sub = s;
+                u.rb0 = next_rb[s];
+                u.rb1 = next_rb[s] + g;
+                units.push_back(u);
+                pairs += up;
+                next_rb[s] += g;
+                // row-block group sizes 1,1,2,4,8,...: the first blocks connect most of a clone, later
+                // ones are mostly skipped by the class test
+                grow[s] = (next_rb[s] <= 1) ? 1 : std::min(next_rb[s], 1 << 14);
+                if (next_rb[s] < nb) still.push_back(s);
+            }
+            live.swap(still);
+            int rc = run_units(c, units, times, 0);
+            if (rc) return rc;
+        }
+    }
+    CK(cudaEventRecord(ev_rounds, st));
+
+    // ---- finalize: tuples of the forest edges, two-cell filter, clonotype_id unions, labels, ordering ----
+    int rc = sync_counters(c);
+    if (rc) return rc;
+    const int64_t NF = (int64_t)c->h_ctr->n_forest;
+    c->stats.forest_edges = NF;
+    c->stats.pairs_evaluated = (int64_t)c->h_ctr->pairs_eval;
+    CK(c->d_keep.ensure((size_t)std::max<int64_t>(NF, 1)));
+    CK(c->d_labels.ensure((size_t)std::max<int64_t>(N, 1) * 4));
+    CK(c->d_nout.ensure(64));
+    CK(cudaMemsetAsync(c->d_nout.p, 0, 64, st));
+    if (NF > 0) {
+        CK(c->d_qofrow.ensure((size_t)N * 4));
+        CK(c->d_deg.ensure((size_t)N * 4));
+        CK(cudaMemsetAsync(c->d_deg.p, 0, (size_t)N * 4, st));
+        k_q_of_row<<<nblk(c->n_pos, 256), 256, 0, st>>>(c->d_m_row.as<int32_t>(), c->n_pos, c->d_qofrow.as<int32_t>());
+        // the (q1,q2) list of ALL forest edges is needed for degrees; tuples are computed in chunks of cand_cap
+        DevBuf d_pairs_all;
+        CK(d_pairs_all.ensure((size_t)NF * 8));
+        k_forest_pairs<<<nblk(NF, 256), 256, 0, st>>>(c->d_forest.as<unsigned long long>(), NF, c->d_qofrow.as<int32_t>(), d_pairs_all.as<uint2>(),
+                                                     c->d_deg.as<int32_t>());
+        c->stats.kernel_launches += 2;
+        DevBuf d_slots;
+        const int64_t chunk = (int64_t)std::min<unsigned long long>(cap, (unsigned long long)NF);
+        CK(d_slots.ensure((size_t)chunk * 4));
+        DevBuf d_cnt;
+        CK(d_cnt.ensure(16));
+        for (int64_t o = 0; o < NF; o += chunk) {
+            const int64_t m = std::min<int64_t>(chunk, NF - o);
+            const unsigned long long mm = (unsigned long long)m;
+            CK(cudaMemcpyAsync(d_cnt.p, &mm, 8, cudaMemcpyHostToDevice, st));
+            k_iota<<<nblk(m, 256), 256, 0, st>>>(d_slots.as<int32_t>(), m, (int32_t)o);  // output slots o..o+m-1
+            rc = run_stage2(c, d_pairs_all.as<uint2>() + o, d_slots.as<uint32_t>(), d_cnt.as<unsigned long long>(), 1);
+            if (rc) return rc;
+            rc = sync_counters(c);
+            if (rc) return rc;
+            if (c->h_ctr->overflow) return fail(c, EJB_ERR_CUDA, "finalize overflow");
+            c->p1_count += c->h_ctr->n_newkeys;
+        }
+        k_two_cell<<<nblk(NF, 256), 256, 0, st>>>(din, make_dev_params(c->params), c->d_forest.as<unsigned long long>(), NF, c->d_deg.as<int32_t>(),
+                                                 c->d_tuples.as<EdgeTuple>(), c->d_parent.as<int32_t>(), c->d_keep.as<uint8_t>(), c->d_ctr.as<Counters>());
+        c->stats.kernel_launches++;
+        CK(c->d_fkeys.ensure((size_t)NF * 8)); CK(c->d_fkeys2.ensure((size_t)NF * 8));
+        CK(c->d_fidx.ensure((size_t)NF * 4)); CK(c->d_fidx2.ensure((size_t)NF * 4));
+        k_final_keys<<<nblk(NF, 256), 256, 0, st>>>(c->d_forest.as<unsigned long long>(), c->d_keep.as<uint8_t>(), NF, c->d_fkeys.as<unsigned long long>(),
+                                                   c->d_fidx.as<uint32_t>(), c->d_nout.as<unsigned long long>());
+        unsigned long long nfinal = 0;
+        CK(cudaMemcpyAsync(&nfinal, c->d_nout.p, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        c->n_final = (int64_t)nfinal;
+        if (nfinal > 0) {
+            rc = cub_sort_pairs64(c, c->d_fkeys.as<uint64_t>(), c->d_fkeys2.as<uint64_t>(), c->d_fidx.as<uint32_t>(), c->d_fidx2.as<uint32_t>(), (int64_t)nfinal);
+            if (rc) return rc;
+            const size_t nf = (size_t)nfinal;
+            CK(c->d_o_k1.ensure(nf * 4)); CK(c->d_o_k2.ensure(nf * 4)); CK(c->d_o_cd.ensure(nf * 4)); CK(c->d_o_nrefs.ensure(nf * 4));
+            CK(c->d_o_sh.ensure(nf * 8)); CK(c->d_o_in.ensure(nf * 8)); CK(c->d_o_k.ensure(nf * 4)); CK(c->d_o_d.ensure(nf * 4));
+            CK(c->d_o_n.ensure(nf * 4)); CK(c->d_o_p1.ensure(nf * 8)); CK(c->d_o_mult.ensure(nf * 8)); CK(c->d_o_score.ensure(nf * 8));
+            CK(c->d_o_err.ensure(nf));
+            FinalOut fo;
+            fo.k1 = c->d_o_k1.as<int32_t>(); fo.k2 = c->d_o_k2.as<int32_t>(); fo.cd = c->d_o_cd.as<int32_t>(); fo.nrefs = c->d_o_nrefs.as<int32_t>();
+            fo.shares = c->d_o_sh.as<int32_t>(); fo.indeps = c->d_o_in.as<int32_t>(); fo.k = c->d_o_k.as<int32_t>(); fo.d = c->d_o_d.as<int32_t>();
+            fo.n = c->d_o_n.as<int32_t>(); fo.p1 = c->d_o_p1.as<double>(); fo.mult = c->d_o_mult.as<double>(); fo.score = c->d_o_score.as<double>();
+            fo.err = c->d_o_err.as<uint8_t>();
+            k_final_gather<<<nblk((int64_t)nfinal, 256), 256, 0, st>>>(c->d_fkeys2.as<unsigned long long>(), c->d_fidx2.as<uint32_t>(), (int64_t)nfinal,
+                                                                      c->d_tuples.as<EdgeTuple>(), fo, c->d_ctr.as<Counters>());
+        }
+        c->stats.kernel_launches += 3;
+        CK(cudaStreamSynchronize(st));
+    }
+    if (N > 0) {
+        // join2.rs:69-84 + canonical labels
+        CK(c->d_first.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 4));
+        k_fill_i32<<<nblk(din.n_exacts, 256), 256, 0, st>>>(c->d_first.as<int32_t>(), din.n_exacts, 0x7fffffff);
+        k_exact_first<<<nblk(N, 256), 256, 0, st>>>(din, c->d_first.as<int32_t>());
+        k_exact_union<<<nblk(N, 256), 256, 0, st>>>(din, c->d_first.as<int32_t>(), c->d_parent.as<int32_t>());
+        k_labels<<<nblk(N, 256), 256, 0, st>>>(c->d_parent.as<int32_t>(), N, c->d_labels.as<int32_t>());
+        c->stats.kernel_launches += 4;
+    }
+    CK(cudaEventRecord(ev_end, st));
+    rc = sync_counters(c);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    c->stats.two_cell_deleted = (int64_t)c->h_ctr->n_two_cell;
+    c->stats.joins = c->n_final;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_start, ev_packed); c->stats.ms_pack = ms;
+    cudaEventElapsedTime(&ms, ev_rounds, ev_end); c->stats.ms_finalize = ms;
+    cudaEventElapsedTime(&ms, ev_start, ev_end); c->stats.ms_device_total = ms;
+    for (auto& t : times) {
+        cudaEventElapsedTime(&ms, t.e0, t.e1); c->stats.ms_stage1 += ms;
+        cudaEventElapsedTime(&ms, t.e1, t.e2); c->stats.ms_stage2 += ms;
+        cudaEventElapsedTime(&ms, t.e2, t.e3); c->stats.ms_forest += ms;
+    }
+    c->stats.ms_h2d = c->ms_h2d;
+    c->stats.h2d_bytes = c->h2d_bytes;
+    c->stats.ms_total = now_ms() - t_wall0;
+    c->have_run = true;
+    return EJB_OK;
+}
+
+namespace {
+struct ResultOwner {
+    std::vector<int32_t> k1, k2, cd, nrefs, sh, in, k, d, n, labels, x, y, z;
+    std::vector<double> p1, mult, score;
+    std::vector<uint8_t> err;
+};
+}  // namespace
+
+extern "C" {
+
+int ejb_download(ejb_ctx* c, ejb_result* out) {
+    if (!c || !out) return EJB_ERR_INVALID;
+    if (!c->have_run) return fail(c, EJB_ERR_INVALID, "ejb_download without ejb_run");
+    CK(cudaSetDevice(c->device));
+    memset(out, 0, sizeof(*out));
+    const double t0 = now_ms();
+    ResultOwner* R = new ResultOwner();
+    const int64_t E = c->n_final, N = c->din.n_rows;
+    cudaStream_t st = c->stream;
+    auto get = [&](auto& vec, const DevBuf& b, size_t n) -> cudaError_t {
+        vec.resize(std::max<size_t>(n, 1));
+        if (n == 0) return cudaSuccess;
+        c->stats.d2h_bytes += (int64_t)(n * sizeof(vec[0]));
+        return cudaMemcpyAsync(vec.data(), b.p, n * sizeof(vec[0]), cudaMemcpyDeviceToHost, st);
+    };
+    cudaError_t e = cudaSuccess;
+    if (E > 0) {
+        if ((e = get(R->k1, c->d_o_k1, E)) || (e = get(R->k2, c->d_o_k2, E)) || (e = get(R->cd, c->d_o_cd, E)) || (e = get(R->nrefs, c->d_o_nrefs, E)) ||
+            (e = get(R->sh, c->d_o_sh, 2 * E)) || (e = get(R->in, c->d_o_in, 2 * E)) || (e = get(R->k, c->d_o_k, E)) || (e = get(R->d, c->d_o_d, E)) ||
+            (e = get(R->n, c->d_o_n, E)) || (e = get(R->p1, c->d_o_p1, E)) || (e = get(R->mult, c->d_o_mult, E)) || (e = get(R->score, c->d_o_score, E)) ||
+            (e = get(R->err, c->d_o_err, E))) {
+            delete R;
+            return fail(c, EJB_ERR_CUDA, "download: %s", cudaGetErrorString(e));
+        }
+    } else {
+        R->k1.resize(1); R->k2.resize(1); R->cd.resize(1); R->nrefs.resize(1); R->sh.resize(2); R->in.resize(2); R->k.resize(1); R->d.resize(1);
+        R->n.resize(1); R->p1.resize(1); R->mult.resize(1); R->score.resize(1); R->err.resize(1);
+    }
+    std::vector<int32_t> row_exact;
+    if ((e = get(R->labels, c->d_labels, N))) {
+        delete R;
+        return fail(c, EJB_ERR_CUDA, "download: %s", cudaGetErrorString(e));
+    }
+    row_exact.resize((size_t)std::max<int64_t>(N, 1));
+    if (N > 0) {
+        e = cudaMemcpyAsync(row_exact.data(), c->din.row_exact, (size_t)N * 4, cudaMemcpyDeviceToHost, st);
+        if (e) { delete R; return fail(c, EJB_ERR_CUDA, "download: %s", cudaGetErrorString(e)); }
+    }
+    e = cudaStreamSynchronize(st);
+    if (e) { delete R; return fail(c, EJB_ERR_CUDA, "download: %s", cudaGetErrorString(e)); }
+    c->stats.ms_d2h = now_ms() - t0;
+    // replay into the reference's EquivRel (join2.rs:45-54, 69-84) so that x/y/z match from_raw
+    const double t1 = now_ms();
+    if (c->shard_world == 1) {
+        ejbhost::EquivRel eq((int32_t)N);
+        for (int64_t i = 0; i < E; i++) eq.join(R->k1[(size_t)i], R->k2[(size_t)i]);
+        ejbhost::finish_join_merge(eq, row_exact.data(), N);
+        R->x = eq.x; R->y = eq.y; R->z = eq.z;
+    }
+    if (R->x.empty()) { R->x.resize(1); R->y.resize(1); R->z.resize(1); }
+    c->stats.ms_replay = now_ms() - t1;
+    int64_t errors = 0;
+    for (int64_t i = 0; i < E; i++) errors += R->err[(size_t)i];
+    c->stats.errors = errors;
+    out->n_edges = E;
+    out->edge_k1 = R->k1.data(); out->edge_k2 = R->k2.data(); out->edge_cd = R->cd.data(); out->edge_nrefs = R->nrefs.data();
+    out->edge_shares = R->sh.data(); out->edge_indeps = R->in.data(); out->edge_k = R->k.data(); out->edge_d = R->d.data(); out->edge_n = R->n.data();
+    out->edge_p1 = R->p1.data(); out->edge_mult = R->mult.data(); out->edge_score = R->score.data(); out->edge_err = R->err.data();
+    out->n_rows = N;
+    out->labels = R->labels.data();
+    out->eq_x = R->x.data(); out->eq_y = R->y.data(); out->eq_z = R->z.data();
+    out->stats = c->stats;
+    out->opaque = R;
+    return EJB_OK;
+}
+
+void ejb_result_free(ejb_ctx* c, ejb_result* out) {
+    (void)c;
+    if (!out) return;
+    delete reinterpret_cast<ResultOwner*>(out->opaque);
+    memset(out, 0, sizeof(*out));
+}
+
+int ejb_join(ejb_ctx* c, const ejb_params* p, const ejb_input* in, ejb_result* out) {
+    const double t0 = now_ms();
+    int rc = ejb_upload(c, p, in);
+    if (rc) return rc;
+    rc = ejb_run(c);
+    if (rc) return rc;
+    rc = ejb_download(c, out);
+    if (rc) return rc;
+    out->stats.ms_total = now_ms() - t0;
+    c->stats.ms_total = out->stats.ms_total;
+    return EJB_OK;
+}
+
+int ejb_last_stats(const ejb_ctx* c, ejb_stats* out) {
+    if (!c || !out) return EJB_ERR_INVALID;
+    *out = c->stats;
+    return EJB_OK;
+}
+
+int ejb_p1_batch(ejb_ctx* c, const int32_t* k, const int32_t* d, const int32_t* n, int64_t count, double* p1_out) {
+    if (!c || count < 0) return EJB_ERR_INVALID;
+    if (count == 0) return EJB_OK;
+    CK(cudaSetDevice(c->device));
+    for (int64_t i = 0; i < count; i++)
+        if (k[i] < 0 || k[i] > SR_NMAX || d[i] < 0 || d[i] > k[i] || n[i] < 1) return fail(c, EJB_ERR_RANGE, "p1 triple %lld out of range", (long long)i);
+    DevBuf dk, dd_, dn, dout;
+    CK(dk.ensure(count * 4)); CK(dd_.ensure(count * 4)); CK(dn.ensure(count * 4)); CK(dout.ensure(count * 8));
+    CK(cudaMemcpyAsync(dk.p, k, count * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(dd_.p, d, count * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(dn.p, n, count * 4, cudaMemcpyHostToDevice, c->stream));
+    k_p1_batch<<<nblk(count * 32, 128), 128, 0, c->stream>>>(c->d_sr.as<dd_t>(), dk.as<int32_t>(), dd_.as<int32_t>(), dn.as<int32_t>(), count, dout.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(p1_out, dout.p, count * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EJB_OK;
+}
+
+int ejb_measure_peaks(ejb_ctx* c, double* popc_per_s, double* lop3_per_s, double* sm_clock_mhz) {
+    if (!c) return EJB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const int blocks = c->sm_count * 8, threads = 256, iters = 1 << 14;
+    DevBuf out;
+    CK(out.ensure((size_t)blocks * threads * 4));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    double best_popc = 0, best_lop = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(a, c->stream));
+        k_peak_popc<<<blocks, threads, 0, c->stream>>>(out.as<uint32_t>(), iters);
+        CK(cudaEventRecord(b, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0) best_popc = std::max(best_popc, (double)blocks * threads * iters * 8.0 / (ms * 1e-3));
+        CK(cudaEventRecord(a, c->stream));
+        k_peak_lop3<<<blocks, threads, 0, c->stream>>>(out.as<uint32_t>(), iters);
+        CK(cudaEventRecord(b, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0) best_lop = std::max(best_lop, (double)blocks * threads * iters * 8.0 / (ms * 1e-3));
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    if (popc_per_s) *popc_per_s = best_popc;
+    if (lop3_per_s) *lop3_per_s = best_lop;
+    if (sm_clock_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+        *sm_clock_mhz = khz / 1000.0;
+    }
+    return EJB_OK;
+}
+
+// host-side EquivRel replay for callers that merge per-rank edge lists (multi-GPU)
+int ejb_equiv_replay(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64_t n_edges, const int32_t* row_exact, int32_t* x, int32_t* y, int32_t* z,
+                     int32_t* labels) {
+    if (n_rows < 0 || n_edges < 0) return EJB_ERR_INVALID;
+    ejbhost::EquivRel eq(n_rows);
+    for (int64_t i = 0; i < n_edges; i++) {
+        if (k1[i] < 0 || k1[i] >= n_rows || k2[i] < 0 || k2[i] >= n_rows) return EJB_ERR_INVALID;
+        eq.join(k1[i], k2[i]);
+    }
+    if (row_exact) ejbhost::finish_join_merge(eq, row_exact, n_rows);
+    if (x) memcpy(x, eq.x.data(), (size_t)n_rows * 4);
+    if (y) memcpy(y, eq.y.data(), (size_t)n_rows * 4);
+    if (z) memcpy(z, eq.z.data(), (size_t)n_rows * 4);
+    if (labels) {
+        std::vector<int32_t> mn((size_t)std::max(n_rows, 1), 0x7fffffff);
+        for (int32_t i = 0; i < n_rows; i++) mn[eq.y[i]] = std::min(mn[eq.y[i]], i);
+        for (int32_t i = 0; i < n_rows; i++) labels[i] = mn[eq.y[i]];
+    }
+    return EJB_OK;
+}
+
+}  // extern "C"

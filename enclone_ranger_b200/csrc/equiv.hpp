@@ -1,0 +1,51 @@
+// equiv.hpp — host-side mirror of the reference's union-find OUTPUT TYPE (product code).
+//
+// join_exacts returns an `EquivRel` (equiv/src/lib.rs:34-138) whose internal state — class ids
+// y[], circular orbit lists x[], sizes z[] — is observable downstream (filter_umi.rs:45-51,
+// disintegrate.rs:106-121).  It depends on the ORDER of the join() calls, so the library replays
+// the device-computed edges sequentially, exactly like finish_join (join2.rs:45-54, 69-84), and
+// hands x/y/z back for EquivRel::from_raw (equiv/src/lib.rs:57).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <utility>
+#include <vector>
+
+namespace ejbhost {
+
+struct EquivRel {
+    std::vector<int32_t> x, y, z;
+    explicit EquivRel(int32_t n) : x((size_t)n), y((size_t)n), z((size_t)n, 1) {
+        for (int32_t i = 0; i < n; i++) x[(size_t)i] = y[(size_t)i] = i;
+    }
+    int32_t class_id(int32_t a) const { return y[(size_t)a]; }
+    int32_t orbit_size(int32_t a) const { return z[(size_t)y[(size_t)a]]; }
+    // relabels the smaller orbit; on a tie b's orbit takes a's class id (equiv/src/lib.rs:64-93)
+    void join(int32_t a, int32_t b) {
+        if (y[(size_t)a] == y[(size_t)b]) return;
+        if (orbit_size(a) < orbit_size(b)) std::swap(a, b);
+        const int32_t total = orbit_size(a) + orbit_size(b);
+        std::swap(x[(size_t)a], x[(size_t)b]);
+        const int32_t cls = y[(size_t)a];
+        for (int32_t n = x[(size_t)a]; y[(size_t)n] != cls; n = x[(size_t)n]) y[(size_t)n] = cls;
+        z[(size_t)y[(size_t)b]] = total;
+    }
+};
+
+// join2.rs:69-84: sort (clonotype_id, class id) and join consecutive entries of one clonotype_id;
+// note that the joined values are CLASS IDS used as element ids (join2.rs:81).
+inline void finish_join_merge(EquivRel& eq, const int32_t* row_exact, int64_t n_rows) {
+    std::vector<std::pair<int64_t, int32_t>> ox;
+    ox.reserve((size_t)n_rows);
+    for (int64_t i = 0; i < n_rows; i++) ox.emplace_back((int64_t)row_exact[i], eq.class_id((int32_t)i));
+    std::sort(ox.begin(), ox.end());
+    size_t i = 0;
+    while (i < ox.size()) {
+        size_t j = i + 1;
+        while (j < ox.size() && ox[j].first == ox[i].first) j++;
+        for (size_t k = i; k + 1 < j; k++) eq.join(ox[k].second, ox[k + 1].second);
+        i = j;
+    }
+}
+
+}  // namespace ejbhost

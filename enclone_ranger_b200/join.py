@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference's join interface on top of the C ABI.
+
+    reference                                   here
+    ---------                                   ----
+    join_exacts(to_bc, refdata, ctl,            join_exacts(ctx, params, inp) -> (EquivRel, JoinResult)
+                exact_clonotypes, info,             inp    : JoinInput / Repertoire (the flattened
+                &mut join_info, &mut raw_joins,              info[] / exact_clonotypes[] / to_bc / refdata)
+                sr, dref) -> EquivRel               params : EjbParams (the join knobs of `ctl`)
+    (enclone/src/join.rs:31-41)                     result.raw_joins == what the reference appends to raw_joins
+
+The product path is the CUDA library only: constructing a JoinContext fails when
+libenclone_join_b200.so is missing or no B200 is visible.  Nothing here imports oracle/.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import EjbResult, EjbStats
+
+
+class JoinError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ejb error {code}: {msg}")
+        self.code = code
+
+
+class EquivRel:
+    """The reference's union-find as raw x/y/z vectors (equiv/src/lib.rs:34-138), read-only view
+    with the accessors downstream code uses (class_id, orbit_reps, orbit, orbit_size, norbits)."""
+
+    def __init__(self, x, y, z):
+        self.x, self.y, self.z = x, y, z
+
+    def class_id(self, a):
+        return int(self.y[a])
+
+    def orbit_size(self, a):
+        return int(self.z[self.y[a]])
+
+    def orbit_reps(self):
+        return np.nonzero(self.y == np.arange(len(self.y), dtype=self.y.dtype))[0].astype(np.int32)
+
+    def norbits(self):
+        return int(len(self.orbit_reps()))
+
+    def orbit(self, a):
+        o = [int(a)]
+        b = int(self.x[a])
+        while b != a:
+            o.append(b)
+            b = int(self.x[b])
+        return o
+
+
+class JoinResult:
+    def __init__(self, r):
+        E, N = r.n_edges, r.n_rows
+
+        def arr(p, n, dt):
+            if n == 0:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(p, shape=(n,)).copy()
+
+        self.edge_k1 = arr(r.edge_k1, E, np.int32)
+        self.edge_k2 = arr(r.edge_k2, E, np.int32)
+        self.edge_cd = arr(r.edge_cd, E, np.int32)
+        self.edge_nrefs = arr(r.edge_nrefs, E, np.int32)
+        self.edge_shares = arr(r.edge_shares, 2 * E, np.int32).reshape(-1, 2)
+        self.edge_indeps = arr(r.edge_indeps, 2 * E, np.int32).reshape(-1, 2)
+        self.edge_k = arr(r.edge_k, E, np.int32)
+        self.edge_d = arr(r.edge_d, E, np.int32)
+        self.edge_n = arr(r.edge_n, E, np.int32)
+        self.edge_p1 = arr(r.edge_p1, E, np.float64)
+        self.edge_mult = arr(r.edge_mult, E, np.float64)
+        self.edge_score = arr(r.edge_score, E, np.float64)
+        self.edge_err = arr(r.edge_err, E, np.uint8)
+        self.labels = arr(r.labels, N, np.int32)
+        self.eq_x = arr(r.eq_x, N, np.int32)
+        self.eq_y = arr(r.eq_y, N, np.int32)
+        self.eq_z = arr(r.eq_z, N, np.int32)
+        self.stats = r.stats.as_dict()
+
+    @property
+    def raw_joins(self):
+        return np.stack([self.edge_k1, self.edge_k2], axis=1)
+
+    def equiv(self):
+        return EquivRel(self.eq_x, self.eq_y, self.eq_z)
+
+
+def _c_input(inp):
+    if hasattr(inp, "c_ptr") and callable(inp.c_ptr):
+        return inp.c_ptr()
+    if hasattr(inp, "c_ptr"):
+        return inp.c_ptr
+    return inp
+
+
+class JoinContext:
+    """Owns one ejb_ctx (one GPU).  `rank`/`world` shard buckets across processes (one per GPU)."""
+
+    def __init__(self, device=0, rank=0, world=1, cand_cap=0, pair_budget=0):
+        self.L = _abi.load_join()
+        self.h = C.c_void_p()
+        dev = (C.c_int * 1)(int(device))
+        rc = self.L.ejb_create(C.byref(self.h), dev, 1)
+        if rc != 0:
+            raise JoinError(rc, "ejb_create failed (no CUDA device? there is no CPU fallback)")
+        self.L.ejb_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self.L.ejb_set_capacity.argtypes = [C.c_void_p, C.c_ulonglong, C.c_ulonglong]
+        if world > 1:
+            self._ck(self.L.ejb_set_shard(self.h, int(rank), int(world)))
+        if cand_cap or pair_budget:
+            self._ck(self.L.ejb_set_capacity(self.h, int(cand_cap), int(pair_budget)))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise JoinError(rc, self.L.ejb_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.L.ejb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- the drop-in call ---
+    def join(self, params, inp):
+        r = EjbResult()
+        self._ck(self.L.ejb_join(self.h, C.byref(params), _c_input(inp), C.byref(r)))
+        out = JoinResult(r)
+        self.L.ejb_result_free(self.h, C.byref(r))
+        return out
+
+    # --- the same in three steps (device-resident timing) ---
+    def upload(self, params, inp):
+        self._ck(self.L.ejb_upload(self.h, C.byref(params), _c_input(inp)))
+
+    def run(self):
+        self._ck(self.L.ejb_run(self.h))
+        s = EjbStats()
+        self.L.ejb_last_stats(self.h, C.byref(s))
+        return s.as_dict()
+
+    def download(self):
+        r = EjbResult()
+        self._ck(self.L.ejb_download(self.h, C.byref(r)))
+        out = JoinResult(r)
+        self.L.ejb_result_free(self.h, C.byref(r))
+        return out
+
+    def p1_batch(self, k, d, n):
+        k = np.ascontiguousarray(k, dtype=np.int32)
+        d = np.ascontiguousarray(d, dtype=np.int32)
+        n = np.ascontiguousarray(n, dtype=np.int32)
+        out = np.zeros(len(k), dtype=np.float64)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        self._ck(self.L.ejb_p1_batch(self.h, ip(k), ip(d), ip(n), len(k), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def measure_peaks(self):
+        a, b, m = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.L.ejb_measure_peaks(self.h, C.byref(a), C.byref(b), C.byref(m)))
+        return {"popc_per_s": a.value, "lop3_per_s": b.value, "sm_clock_mhz": m.value}
+
+
+def join_exacts(ctx, params, inp):
+    """Drop-in for enclone::join::join_exacts: returns (EquivRel, JoinResult)."""
+    res = ctx.join(params, inp)
+    return res.equiv(), res
+
+
+def equiv_replay(n_rows, k1, k2, row_exact=None):
+    """Replay an ordered edge list into the reference's EquivRel (host code in the library)."""
+    L = _abi.load_join()
+    k1 = np.ascontiguousarray(k1, dtype=np.int32)
+    k2 = np.ascontiguousarray(k2, dtype=np.int32)
+    x = np.zeros(n_rows, np.int32); y = np.zeros(n_rows, np.int32); z = np.zeros(n_rows, np.int32)
+    lab = np.zeros(n_rows, np.int32)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    re = None
+    if row_exact is not None:
+        row_exact = np.ascontiguousarray(row_exact, dtype=np.int32)
+        re = ip(row_exact)
+    L.ejb_equiv_replay.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64,
+                                   C.POINTER(C.c_int32)] + [C.POINTER(C.c_int32)] * 4
+    rc = L.ejb_equiv_replay(int(n_rows), ip(k1), ip(k2), len(k1), re, ip(x), ip(y), ip(z), ip(lab))
+    if rc != 0:
+        raise JoinError(rc, "ejb_equiv_replay")
+    return EquivRel(x, y, z), lab

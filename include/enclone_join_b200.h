@@ -254,6 +254,24 @@ int ejb_p1_batch(ejb_ctx* ctx, const int32_t* k, const int32_t* d, const int32_t
  * in 32-bit lane-operations per second; used as the roofline denominator (SURVEY §8 d).     */
 int ejb_measure_peaks(ejb_ctx* ctx, double* popc_per_s, double* lop3_per_s, double* sm_clock_mhz);
 
+/* Multi-GPU: buckets are independent units (join.rs:70-88), so ranks shard them with no collective
+ * on the data path.  After ejb_set_shard(ctx, rank, world) the context joins only the sub-buckets it
+ * owns (longest-processing-time assignment by pair count, identical on every rank) and
+ * ejb_download returns only their edges (labels/eq_* then describe the local edges only); the
+ * caller concatenates the per-rank edge lists, sorts them by (k1, k2) and calls ejb_equiv_replay. */
+int ejb_set_shard(ejb_ctx* ctx, int rank, int world);
+
+/* Work-buffer sizing: cand_cap = capacity (entries) of the candidate / survivor / pass-edge
+ * buffers; pair_budget = upper bound on the pairs one scheduler round evaluates.  0 keeps the
+ * current value.  Defaults: 2^26 and 2^32 (env EJB_CAND_CAP / EJB_PAIR_BUDGET).                */
+int ejb_set_capacity(ejb_ctx* ctx, unsigned long long cand_cap, unsigned long long pair_budget);
+
+/* Host-side replay of an ordered edge list into the reference's EquivRel (join2.rs:45-54) followed,
+ * when row_exact != NULL, by the clonotype_id merge (join2.rs:69-84).  Any of x/y/z/labels may be
+ * NULL.  Pure host code (the EquivRel state is order-dependent and therefore sequential).       */
+int ejb_equiv_replay(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64_t n_edges,
+                     const int32_t* row_exact, int32_t* x, int32_t* y, int32_t* z, int32_t* labels);
+
 int ejb_abi_version(void);
 
 #ifdef __cplusplus
