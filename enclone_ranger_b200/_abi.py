@@ -115,6 +115,7 @@ class EjbStats(C.Structure):
         ("pairs_scored", C.c_int64),
         ("pairs_evaluated", C.c_int64),
         ("stage1_candidates", C.c_int64),
+        ("stage2_slow", C.c_int64),
         ("stage2_survivors", C.c_int64),
         ("pass_edges", C.c_int64),
         ("forest_edges", C.c_int64),

@@ -21,7 +21,10 @@
 #include <vector>
 
 #include "../../include/enclone_join_b200.h"
-#include "ejb_device.cuh"
+#include "ejb_forest.cuh"
+#include "ejb_pack.cuh"
+#include "ejb_stage1.cuh"
+#include "ejb_stage2.cuh"
 #include "equiv.hpp"
 
 using namespace ejb;
@@ -88,7 +91,7 @@ struct ejb_ctx {
 
     // derived (per run)
     DevBuf d_head, d_scan, d_keys, d_keys2, d_vals, d_vals2, d_cubtmp, d_subhead, d_subincl, d_subinfo;
-    DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_m_flags, d_m_vs, d_m_js, d_m_tot, d_m_exact, d_m_chain;
+    DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_aux;
     DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
     DevBuf d_tasks, d_cand, d_slow, d_slowslot, d_surv, d_pass, d_roots, d_forest;
     DevBuf d_qofrow, d_deg, d_tuples, d_keep, d_first, d_labels, d_fkeys, d_fkeys2, d_fidx, d_fidx2, d_nout;
@@ -261,17 +264,11 @@ S2Ctx make_s2ctx(ejb_ctx* c, int tuple_mode) {
     X.in = c->din;
     X.P = make_dev_params(c->params);
     X.subs = c->d_subs.as<SubBucket>();
-    X.M.row = c->d_m_row.as<int32_t>();
-    X.M.sub = c->d_m_sub.as<int32_t>();
-    X.M.flags = c->d_m_flags.as<uint32_t>();
-    X.M.vs = c->d_m_vs.as<int2>();
-    X.M.js = c->d_m_js.as<int2>();
-    X.M.tot = c->d_m_tot.as<int32_t>();
-    X.M.exact = c->d_m_exact.as<int32_t>();
-    X.M.chain = c->d_m_chain.as<int2>();
+    X.aux = c->d_aux.as<int32_t>();
+    X.rowq = c->d_m_row.as<int32_t>();
+    X.subq = c->d_m_sub.as<int32_t>();
     X.cdr3w = c->d_cdr3w.as<uint32_t>();
     X.rowstore = c->d_rowstore.as<uint4>();
-    X.donor_mask = c->d_donor.as<unsigned long long>();
     X.bc_sorted = c->d_bckeys2.as<uint64_t>();
     X.powtab = c->d_powtab.as<double>();
     X.pow_off = c->d_powoff.as<int32_t>();
@@ -583,6 +580,7 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
     c->p1_count += h.n_newkeys;
     c->stats.p1_unique += (int64_t)h.n_newkeys;
     c->stats.stage1_candidates += (int64_t)h.n_cand;
+    c->stats.stage2_slow += (int64_t)h.n_slow;
     c->stats.stage2_survivors += (int64_t)h.n_surv;
     c->stats.pass_edges += (int64_t)h.n_pass;
     if (h.n_pass > 0) {
@@ -706,6 +704,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
         CK(cudaMemcpyAsync(&n_subs, c->d_subincl.as<int32_t>() + (NA - 1), 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(c->d_subinfo.ensure((size_t)n_subs * sizeof(SubInfo)));
+        CK(cudaMemsetAsync(c->d_subinfo.p, 0, (size_t)n_subs * sizeof(SubInfo), st));
         k_subinfo<<<nblk(NA, 256), 256, 0, st>>>(din, keys_sorted, row_of, c->d_subhead.as<int32_t>(), c->d_subincl.as<int32_t>(), NA, c->d_subinfo.as<SubInfo>());
         c->stats.kernel_launches += 2;
         std::vector<SubInfo> si((size_t)n_subs);
@@ -723,8 +722,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
         int max_cdr3 = 0;
         for (int s = 0; s < n_subs; s++) {
             SubBucket& sb = subs[s];
-            sb.j0 = si[s].q0;
-            sb.n = (int32_t)(((s + 1 < n_subs) ? si[s + 1].q0 : NA) - si[s].q0);
+            sb.j0 = si[s].j0;
+            sb.n = (int32_t)(((s + 1 < n_subs) ? si[s + 1].j0 : NA) - si[s].j0);
             sb.npad = (sb.n + 3) & ~3;
             sb.ch = (int32_t)((si[s].key >> 16) & 0xffff);
             sb.cl = (int32_t)(si[s].key & 0xffff);
@@ -736,7 +735,9 @@ extern "C" int ejb_run(ejb_ctx* c) {
             const int w4h = (sb.Lh + 127) / 128, w4l = (sb.Ll + 127) / 128;
             sb.W4h = (w4h >= 1 && w4h <= MAXW4) ? w4h : 0;
             sb.W4l = (w4l >= 1 && w4l <= MAXW4) ? w4l : 0;
-            sb.rec_u4 = 3 * (sb.W4h + sb.W4l);
+            sb.gap = si[s].gap & 3;
+            sb.rec_u4 = rec_planes(sb.gap & 1) * sb.W4h + rec_planes(sb.gap & 2) * sb.W4l;
+            sb.pad = 0;
             sb.q0 = q;
             sb.s1_off = s1;
             sb.rs_off = rs;
@@ -818,32 +819,26 @@ extern "C" int ejb_run(ejb_ctx* c) {
         CK(c->d_cdr3w.ensure((size_t)(s1 + 4) * 4));
         CK(c->d_rowstore.ensure((size_t)(rs + 1) * 16));
         const size_t np = (size_t)c->n_pos + 4;
-        CK(c->d_m_row.ensure(np * 4)); CK(c->d_m_sub.ensure(np * 4)); CK(c->d_m_flags.ensure(np * 4)); CK(c->d_m_vs.ensure(np * 8));
-        CK(c->d_m_js.ensure(np * 8)); CK(c->d_m_tot.ensure(np * 4)); CK(c->d_m_exact.ensure(np * 4)); CK(c->d_m_chain.ensure(np * 8));
+        CK(c->d_m_row.ensure(np * 4)); CK(c->d_m_sub.ensure(np * 4)); CK(c->d_aux.ensure(np * AUX_INTS * 4));
         CK(c->d_labq.ensure(np * 4)); CK(c->d_blklab.ensure((size_t)std::max<int64_t>(blk, 1) * 4));
         CK(cudaMemsetAsync(c->d_m_row.p, 0xff, np * 4, st));   // -1 = padding position
         CK(cudaMemsetAsync(c->d_labq.p, 0xff, np * 4, st));
         CK(cudaMemsetAsync(c->d_cdr3w.p, 0, (size_t)(s1 + 4) * 4, st));
-        RowMeta M;
-        M.row = c->d_m_row.as<int32_t>(); M.sub = c->d_m_sub.as<int32_t>(); M.flags = c->d_m_flags.as<uint32_t>();
-        M.vs = c->d_m_vs.as<int2>(); M.js = c->d_m_js.as<int2>(); M.tot = c->d_m_tot.as<int32_t>();
-        M.exact = c->d_m_exact.as<int32_t>(); M.chain = c->d_m_chain.as<int2>();
-        k_pack_rows<<<nblk(NA * 32, 256), 256, 0, st>>>(din, P, c->d_subs.as<SubBucket>(), c->d_subincl.as<int32_t>(), row_of, NA, c->d_cdr3w.as<uint32_t>(),
-                                                       c->d_rowstore.as<uint4>(), M);
+        // per exact: donor masks + sorted barcode lists (the bucketer copies the masks into the row records)
+        CK(c->d_donor.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 8));
+        CK(c->d_bckeys.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
+        CK(c->d_bckeys2.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
+        k_exact_prep<<<nblk(din.n_exacts, 256), 256, 0, st>>>(din, c->d_donor.as<unsigned long long>(), c->d_bckeys.as<uint64_t>());
+        if (din.n_cells > 0) {
+            int rc2 = cub_sort_keys64(c, c->d_bckeys.as<uint64_t>(), c->d_bckeys2.as<uint64_t>(), din.n_cells);
+            if (rc2) return rc2;
+        }
+        k_pack_rows<<<nblk(NA * 32, 256), 256, 0, st>>>(din, P, c->d_subs.as<SubBucket>(), c->d_subincl.as<int32_t>(), row_of, NA,
+                                                       c->d_donor.as<unsigned long long>(), c->d_cdr3w.as<uint32_t>(), c->d_rowstore.as<uint4>(),
+                                                       c->d_aux.as<int32_t>(), c->d_m_row.as<int32_t>(), c->d_m_sub.as<int32_t>());
+        c->stats.kernel_launches += 2;
         c->stats.kernel_launches++;
         CK(cudaGetLastError());
-    }
-    // ---- per exact: donor masks + sorted barcode lists ----
-    CK(c->d_donor.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 8));
-    CK(c->d_bckeys.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
-    CK(c->d_bckeys2.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
-    if (din.n_exacts > 0) {
-        k_exact_prep<<<nblk(din.n_exacts, 256), 256, 0, st>>>(din, c->d_donor.as<unsigned long long>(), c->d_bckeys.as<uint64_t>());
-        c->stats.kernel_launches++;
-        if (din.n_cells > 0) {
-            int rc = cub_sort_keys64(c, c->d_bckeys.as<uint64_t>(), c->d_bckeys2.as<uint64_t>(), din.n_cells);
-            if (rc) return rc;
-        }
     }
     // ---- union-find state, work buffers ----
     CK(c->d_parent.ensure((size_t)std::max<int64_t>(N, 1) * 4));

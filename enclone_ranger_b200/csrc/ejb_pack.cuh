@@ -1,0 +1,287 @@
+// ejb_pack.cuh — bucket scan (join.rs:68-88) and the bucketer that packs rows into HBM.
+#pragma once
+#include "ejb_types.cuh"
+
+namespace ejb {
+
+// ------------------------------------------------------------------------------------------------
+// Bucket scan (join.rs:68-88): head flag = lens vector differs from the previous row's.
+// Also validates per-row offsets / ids (error bits OR-ed into *err).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_heads(DevIn in, int32_t* head, unsigned int* err) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= in.n_rows) return;
+    const int nc = in.row_nchains[k];
+    unsigned int e = 0;
+    if (nc < 1 || nc > 4) e |= 1;
+    if (in.row_exact[k] < 0 || in.row_exact[k] >= in.n_exacts) e |= 2;
+    for (int m = 0; m < 2 && m < nc; m++) {
+        const int64_t i = 2 * k + m;
+        const int L = in.row_len[i];
+        if (L < 0 || in.row_tig_off[i] < 0 || in.row_tig_off[i] + L > in.n_tig_bytes) e |= 4;
+        const int c = in.row_cdr3_len[i];
+        if (c < 0 || c > 65535 || in.row_cdr3_off[i] < 0 || in.row_cdr3_off[i] + c > in.n_cdr3_bytes) e |= 8;
+        if (in.row_vs[i] < 0 || in.row_vs[i] >= in.n_segs || in.row_js[i] < 0 || in.row_js[i] >= in.n_segs) e |= 16;
+        if (e == 0) {
+            const int ex = in.row_exact[k];
+            const int64_t nch = in.ex_chain_off[ex + 1] - in.ex_chain_off[ex];
+            if (in.row_exact_col[i] < 0 || in.row_exact_col[i] >= nch) e |= 32;
+        }
+    }
+    if (e) atomicOr(err, e);
+    int h = 1;
+    if (k > 0) {
+        h = 0;
+        if (in.row_nchains[k - 1] != nc) h = 1;
+        for (int m = 0; m < 2 && m < nc && !h; m++)
+            if (in.row_len[2 * k + m] != in.row_len[2 * (k - 1) + m]) h = 1;
+        // lens vectors longer than 2 (improper rows) never join; compare only what is stored
+    }
+    head[k] = h;
+}
+
+// validates exact / chain / cell / seg / ref tables
+__global__ void k_validate_tables(DevIn in, unsigned int* err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int e = 0;
+    if (i < in.n_exacts) {
+        if (in.ex_chain_off[i] < 0 || in.ex_chain_off[i + 1] < in.ex_chain_off[i] || in.ex_chain_off[i + 1] > in.n_chains) e |= 64;
+        if (in.ex_cell_off[i] < 0 || in.ex_cell_off[i + 1] < in.ex_cell_off[i] || in.ex_cell_off[i + 1] > in.n_cells) e |= 128;
+    }
+    if (i < in.n_chains) {
+        if (in.ch_v_ref[i] < 0 || in.ch_v_ref[i] >= in.n_refs) e |= 256;
+        if (in.ch_u_ref[i] < -1 || in.ch_u_ref[i] >= in.n_refs) e |= 256;
+        if (in.ch_amino_off[i] != -1 && (in.ch_amino_off[i] < 0 || in.ch_amino_len[i] < 0 || in.ch_amino_off[i] + in.ch_amino_len[i] > in.n_amino_bytes)) e |= 512;
+    }
+    if (i < in.n_cells) {
+        if (in.cell_donor[i] < -1 || in.cell_donor[i] >= 64) e |= 1024;  // donor sets are 64-bit masks
+    }
+    if (i < in.n_segs) {
+        if (in.seg_off[i] < 0 || in.seg_off[i + 1] < in.seg_off[i] || in.seg_off[i + 1] > in.n_seg_bytes) e |= 2048;
+    }
+    if (i < in.n_refs) {
+        if (in.ref_off[i] < 0 || in.ref_off[i + 1] < in.ref_off[i] || in.ref_off[i + 1] > in.n_ref_bytes) e |= 4096;
+    }
+    if (e) atomicOr(err, e);
+}
+
+// sort key of a row: (bucket id, heavy CDR3 len, light CDR3 len); rows that can never join
+// (lens.len() != 2, join_one.rs:83-96) get the maximal key and fall off the end.
+__global__ void k_keys(DevIn in, const int32_t* bucket_incl, uint64_t* keys, uint32_t* vals, unsigned long long* n_active) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t key = ~0ull;
+    bool act = false;
+    if (k < in.n_rows && in.row_nchains[k] == 2) {
+        const uint64_t b = (uint64_t)(bucket_incl[k] - 1);
+        key = (b << 32) | ((uint64_t)in.row_cdr3_len[2 * k] << 16) | (uint64_t)in.row_cdr3_len[2 * k + 1];
+        act = true;
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, act);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_active, (unsigned long long)__popc(m));
+    if (k < in.n_rows) {
+        keys[k] = key;
+        vals[k] = (uint32_t)k;
+    }
+}
+
+__global__ void k_subheads(const uint64_t* keys, int64_t n_active, int32_t* head) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_active) return;
+    head[q] = (q == 0 || keys[q] != keys[q - 1]) ? 1 : 0;
+}
+
+struct SubInfo {
+    int64_t j0;
+    uint64_t key;
+    int32_t Lh, Ll;
+    int32_t gap, pad;   // gap: OR over the sub-bucket's rows of has_del (bit 0 heavy, bit 1 light)
+};
+__global__ void k_subinfo(DevIn in, const uint64_t* keys, const uint32_t* row_of, const int32_t* head, const int32_t* sub_incl,
+                          int64_t n_active, SubInfo* out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_active) return;
+    const int s = sub_incl[j] - 1;
+    const int64_t k = row_of[j];
+    if (head[j]) {
+        out[s].j0 = j;
+        out[s].key = keys[j];
+        out[s].Lh = in.row_len[2 * k];
+        out[s].Ll = in.row_len[2 * k + 1];
+    }
+    const int g = (in.row_has_del[2 * k] ? 1 : 0) | (in.row_has_del[2 * k + 1] ? 2 : 0);
+    if (g) atomicOr(&out[s].gap, g);
+}
+
+// per exact: donor set as a 64-bit mask (join_one.rs:301-315) and sort keys for the barcode lists
+__global__ void k_exact_prep(DevIn in, unsigned long long* donor_mask, uint64_t* bc_keys) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= in.n_exacts) return;
+    unsigned long long m = 0;
+    for (int64_t j = in.ex_cell_off[e]; j < in.ex_cell_off[e + 1]; j++) {
+        const int d = in.cell_donor[j];
+        if (d >= 0) m |= 1ull << d;
+        bc_keys[j] = ((uint64_t)e << 32) | (uint64_t)in.cell_barcode[j];
+    }
+    donor_mask[e] = m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The bucketer: one warp per packed row.  Writes
+//   * CDR3 planes (heavy ++ light concatenated), layout [plane*W1 + w][npad] per sub-bucket
+//   * the row record (layout in ejb_types.cuh): contig planes, own-reference planes in contig
+//     coordinates, compare mask, reference-difference bitmap d, optional gap plane
+//   * the aux record (AUX_INTS ints) and rowq / subq
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__ subs, const int32_t* __restrict__ sub_incl,
+                            const uint32_t* __restrict__ row_of, int64_t n_active, const unsigned long long* __restrict__ donor_mask,
+                            uint32_t* __restrict__ cdr3w, uint4* __restrict__ rowstore, int32_t* __restrict__ aux, int32_t* __restrict__ rowq,
+                            int32_t* __restrict__ subq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= n_active) return;
+    const int s = sub_incl[j] - 1;
+    const SubBucket sb = subs[s];
+    const int64_t k = row_of[j];
+    const int64_t li = j - sb.j0;
+    const int64_t q = sb.q0 + li;
+    uint32_t flags = 0;
+    int tot = 0;
+
+    // ---- CDR3 planes ----
+    {
+        const uint8_t* c0 = in.cdr3_bytes + in.row_cdr3_off[2 * k];
+        const uint8_t* c1 = in.cdr3_bytes + in.row_cdr3_off[2 * k + 1];
+        const int T = sb.ch + sb.cl;
+        const int nw = (T + 31) / 32;
+        bool irr = false;
+        for (int w = 0; w < nw; w++) {
+            const int p = w * 32 + lane;
+            int code = 0;
+            if (p < T) {
+                const uint8_t b = (p < sb.ch) ? c0[p] : c1[p - sb.ch];
+                if (!is_acgt(b)) irr = true;
+                code = base2bit(b);
+            }
+            const uint32_t lo = __ballot_sync(0xffffffffu, code & 1);
+            const uint32_t hi = __ballot_sync(0xffffffffu, code & 2);
+            if (sb.W1 > 0 && lane == 0) {
+                cdr3w[sb.s1_off + (int64_t)(w)*sb.npad + li] = lo;
+                cdr3w[sb.s1_off + (int64_t)(sb.W1 + w) * sb.npad + li] = hi;
+            }
+        }
+        if (__any_sync(0xffffffffu, irr)) flags |= F_CDR3_IRREG;
+    }
+
+    // ---- contig planes, reference planes, compare mask, difference bitmap ----
+    uint32_t* rec32 = reinterpret_cast<uint32_t*>(rowstore + sb.rs_off + li * (int64_t)sb.rec_u4);
+    int base_u4 = 0;
+    for (int m = 0; m < 2; m++) {
+        const int L = (m == 0) ? sb.Lh : sb.Ll;
+        const int W4 = (m == 0) ? sb.W4h : sb.W4l;
+        const int gapbit = (sb.gap >> m) & 1;
+        const bool hasdel = in.row_has_del[2 * k + m] != 0;
+        const uint8_t* tig = in.tig_bytes + in.row_tig_off[2 * k + m];
+        const int sv = in.row_vs[2 * k + m], sj = in.row_js[2 * k + m];
+        const uint8_t* vseg = in.seg_bytes + in.seg_off[sv];
+        const uint8_t* jseg = in.seg_bytes + in.seg_off[sj];
+        const long long vlen = in.seg_off[sv + 1] - in.seg_off[sv];
+        const long long jlen = in.seg_off[sj + 1] - in.seg_off[sj];
+        const long long vr = vlen - P.ref_v_trim, jr = jlen - P.ref_j_trim;  // compared ranges
+        if (vr < 0 || jr < 0 || jr > L) flags |= F_PANIC;   // usize underflow / index panic in the reference
+        if (vr > L) flags |= F_SLOWGEOM;                    // "ugly bailout" join_one.rs:371-373
+        if (vr + jr > L) flags |= F_SLOWGEOM;               // V and J ranges overlap: positions counted twice
+        if (hasdel) flags |= (m == 0) ? F_HASDEL_H : F_HASDEL_L;
+        bool odd = false;
+        const int nw = (L + 31) / 32;
+        for (int w = 0; w < 4 * W4; w++) {
+            uint32_t lo = 0, hi = 0, dm = 0, gp = 0, rlo = 0, rhi = 0, cm = 0;
+            if (w < nw) {
+                const int p = w * 32 + lane;
+                int code = 0, dbit = 0, gbit = 0, rcode = 0, cbit = 0;
+                if (p < L) {
+                    const uint8_t b = tig[p];
+                    if (b == '-' && hasdel) gbit = 1;
+                    else if (!is_acgt(b)) odd = true;
+                    code = base2bit(b);
+                    if (p < vr) {
+                        cbit = 1;
+                        rcode = base2bit(vseg[p]);
+                    } else if (p >= L - jr) {
+                        // counted from the contig end: tig[L-1-pp] vs J[|J|-1-pp]   (join_one.rs:388-391)
+                        const long long pp = (long long)L - 1 - p;
+                        cbit = 1;
+                        rcode = base2bit(jseg[jlen - 1 - pp]);
+                    }
+                    dbit = cbit && (b != bit2base(rcode));
+                }
+                lo = __ballot_sync(0xffffffffu, code & 1);
+                hi = __ballot_sync(0xffffffffu, code & 2);
+                dm = __ballot_sync(0xffffffffu, dbit);
+                gp = __ballot_sync(0xffffffffu, gbit);
+                rlo = __ballot_sync(0xffffffffu, rcode & 1);
+                rhi = __ballot_sync(0xffffffffu, rcode & 2);
+                cm = __ballot_sync(0xffffffffu, cbit);
+                tot += __popc(dm);
+            }
+            if (lane == 0) {
+                rec32[(base_u4 + 0 * W4) * 4 + w] = lo;
+                rec32[(base_u4 + 1 * W4) * 4 + w] = hi;
+                rec32[(base_u4 + 2 * W4) * 4 + w] = dm;
+                if (gapbit) rec32[(base_u4 + 3 * W4) * 4 + w] = gp;
+                rec32[(base_u4 + (3 + gapbit) * W4) * 4 + w] = rlo;
+                rec32[(base_u4 + (4 + gapbit) * W4) * 4 + w] = rhi;
+                rec32[(base_u4 + (5 + gapbit) * W4) * 4 + w] = cm;
+            }
+        }
+        if (W4 == 0) {  // contig longer than the fast path: the byte-exact path handles it
+            for (int p = lane; p < L; p += 32)
+                if (!is_acgt(tig[p]) && !(tig[p] == '-' && hasdel)) odd = true;
+        }
+        if (__any_sync(0xffffffffu, odd)) flags |= (m == 0) ? F_ODDBYTE_H : F_ODDBYTE_L;
+        base_u4 += rec_planes(gapbit) * W4;
+    }
+    if (lane == 0) {
+        rowq[q] = (int32_t)k;
+        subq[q] = s;
+        const int ex = in.row_exact[k];
+        const int64_t c0 = in.ex_chain_off[ex], nch = in.ex_chain_off[ex + 1] - c0;
+        const int ch = (int)(c0 + in.row_exact_col[2 * k]), cl = (int)(c0 + in.row_exact_col[2 * k + 1]);
+        if (nch >= 2 && nch <= 3) flags |= B_NCH_OK;
+        if (nch == 2) flags |= B_NCH2;
+        if (nch >= 2 && in.ch_left[c0] != in.ch_left[c0 + 1]) flags |= B_JUN_LEFT;
+        if (in.ch_left[ch]) flags |= B_LEFT_H;
+        if (in.ch_left[cl]) flags |= B_LEFT_L;
+        if (in.ch_amino_off[ch] == -1) flags |= B_AMINO_TIG_H;
+        const int64_t x0 = in.ex_cell_off[ex], ncells = in.ex_cell_off[ex + 1] - x0;
+        const unsigned long long dmask = donor_mask[ex];
+        int32_t* a = aux + q * AUX_INTS;
+        a[AX_FLAGS] = (int32_t)flags;
+        a[AX_VSH] = in.seg_canon[in.row_vs[2 * k]];
+        a[AX_VSL] = in.seg_canon[in.row_vs[2 * k + 1]];
+        a[AX_JSH] = in.seg_canon[in.row_js[2 * k]];
+        a[AX_JSL] = in.seg_canon[in.row_js[2 * k + 1]];
+        a[AX_TOT] = tot;
+        a[AX_EXACT] = ex;
+        a[AX_NCELLS] = (int32_t)ncells;
+        a[AX_DONLO] = (int32_t)(uint32_t)(dmask & 0xffffffffull);
+        a[AX_DONHI] = (int32_t)(uint32_t)(dmask >> 32);
+        a[AX_CREFH] = in.ch_c_ref[ch];
+        a[AX_CREFL] = in.ch_c_ref[cl];
+        a[AX_HCOMP] = in.ch_hcomp[ch];
+        a[AX_VREFH] = in.ch_v_ref[ch];
+        a[AX_VREFL] = in.ch_v_ref[cl];
+        a[AX_BC0] = ncells > 0 ? (int32_t)in.cell_barcode[x0] : -1;
+        a[AX_VNAMEH] = in.ref_name_id[in.ch_v_ref[ch]];
+        a[AX_VNAMEL] = in.ref_name_id[in.ch_v_ref[cl]];
+        a[AX_FR1] = in.ch_fr1[ch];
+        a[AX_CDR1] = in.ch_cdr1[ch];
+        a[AX_FR2] = in.ch_fr2[ch];
+        a[AX_CDR2] = in.ch_cdr2[ch];
+        a[AX_FR3] = in.ch_fr3[ch];
+        a[AX_CHH] = ch;
+        a[AX_CHL] = cl;
+        a[AX_PAD1] = a[AX_PAD2] = a[AX_PAD3] = 0;
+    }
+}
+
+}  // namespace ejb

@@ -1,0 +1,217 @@
+// ejb_stage1.cuh — CDR3 Hamming pre-filter over all pairs of a sub-bucket (TMA-staged tiles).
+#pragma once
+#include "ejb_types.cuh"
+
+namespace ejb {
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1: all pairs of a sub-bucket, tiled 128 x 128.  One CTA = one row block x a strip of up to
+// S1_STRIP column blocks.  Row/column CDR3 planes + class labels are staged in shared memory by TMA
+// bulk copies (double-buffered columns); each thread keeps an 8-row fragment in registers and walks
+// 8 columns per tile.  Distance = popc of (lo^lo')|(hi^hi') per 32 bases, words pre-reduced with a
+// carry-save adder so that 3 words cost 2 popc.  A pair becomes a candidate iff
+// cd <= maxcd  &&  class labels differ (join_core.rs:32 — a pair already connected by
+// lexicographically smaller joins can never be in pot).
+// ------------------------------------------------------------------------------------------------
+struct RowTask {       // one row block of one sub-bucket
+    int32_t sub;
+    int32_t rb;
+    int64_t cta0;      // first CTA of this task inside the round
+};
+
+template <int W1>
+__device__ __forceinline__ int cdr3_dist(const uint32_t* rl, const uint32_t* rh, const uint32_t* cl, const uint32_t* chh) {
+    uint32_t x[W1];
+#pragma unroll
+    for (int w = 0; w < W1; w++) x[w] = (rl[w] ^ cl[w]) | (rh[w] ^ chh[w]);
+    if (W1 == 1) return __popc(x[0]);
+    if (W1 == 2) return __popc(x[0]) + __popc(x[1]);
+    uint32_t s = x[0] ^ x[1] ^ x[2];
+    uint32_t c = (x[0] & x[1]) | (x[2] & (x[0] ^ x[1]));
+    if (W1 == 3) return __popc(s) + 2 * __popc(c);
+    if (W1 == 4) return __popc(s) + __popc(x[3]) + 2 * __popc(c);
+    if (W1 == 5) {
+        uint32_t s2 = s ^ x[3] ^ x[4];
+        uint32_t c2 = (s & x[3]) | (x[4] & (s ^ x[3]));
+        return __popc(s2) + 2 * (__popc(c) + __popc(c2));
+    }
+    // W1 == 6
+    uint32_t s3 = x[3] ^ x[4] ^ x[5];
+    uint32_t c3 = (x[3] & x[4]) | (x[5] & (x[3] ^ x[4]));
+    return __popc(s) + __popc(s3) + 2 * (__popc(c) + __popc(c3));
+}
+
+template <int W1>
+__global__ void __launch_bounds__(S1_THREADS) k_stage1(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, int n_tasks,
+                                                       const uint32_t* __restrict__ cdr3w, const int32_t* __restrict__ labq,
+                                                       const int32_t* __restrict__ blk_lab, uint2* __restrict__ cand,
+                                                       unsigned long long cand_cap, Counters* __restrict__ ctr) {
+    constexpr int NP = 2 * W1;           // plane-words per row
+    constexpr int SLOT = (NP + 1) * TILE; // words per staged tile (planes + labels)
+    __shared__ __align__(16) uint32_t s_row[SLOT];
+    __shared__ __align__(16) uint32_t s_col[2][SLOT];
+    __shared__ __align__(8) uint64_t s_bar[3];
+    __shared__ uint16_t s_hits[TILE * TILE / 2];
+    __shared__ unsigned int s_nhits;
+    __shared__ unsigned long long s_base;
+    __shared__ int s_cbs[S1_STRIP];
+    __shared__ int s_ncb;
+
+    // ---- locate the task: binary search on cta0 ----
+    const int64_t cta = blockIdx.x;
+    int lo = 0, hi = n_tasks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tasks[mid].cta0 <= cta) lo = mid; else hi = mid - 1;
+    }
+    const RowTask t = tasks[lo];
+    const SubBucket sb = subs[t.sub];
+    if (sb.W1 != W1) return;  // launched once per W1; other widths are handled by their own launch
+    const int nb = (sb.n + TILE - 1) / TILE;
+    const int rb = t.rb;
+    const int cb_first = rb + (int)(cta - t.cta0) * S1_STRIP;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+
+    // class-skip at block level: both blocks uniformly in one class
+    if (tid == 0) {
+        int n = 0;
+        const int lr = blk_lab[sb.blk0 + rb];
+        for (int c = cb_first; c < nb && c < cb_first + S1_STRIP; c++) {
+            const int lc = blk_lab[sb.blk0 + c];
+            if (lr >= 0 && lr == lc) continue;
+            s_cbs[n++] = c;
+        }
+        s_ncb = n;
+        s_nhits = 0;
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar[2], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int ncb = s_ncb;
+    if (ncb == 0) return;
+
+    const uint32_t* base = cdr3w + sb.s1_off;
+    auto issue = [&](uint32_t* dst, int blk, uint64_t* bar) {
+        // rows [blk*128, min(n, blk*128+128)) of every plane-word + labels, 16-byte granules
+        const int r0 = blk * TILE;
+        const int cnt = min(TILE, sb.npad - r0);  // npad is a multiple of 4
+        const uint32_t bytes = (uint32_t)cnt * 4u;
+        mbar_expect_tx(bar, bytes * (NP + 1));
+#pragma unroll
+        for (int pw = 0; pw < NP; pw++) tma_load_1d(dst + pw * TILE, base + (int64_t)pw * sb.npad + r0, bytes, bar);
+        tma_load_1d(dst + NP * TILE, labq + sb.q0 + r0, bytes, bar);   // q0 is a multiple of 4
+    };
+    if (tid == 0) {
+        issue(s_row, rb, &s_bar[2]);
+        issue(s_col[0], s_cbs[0], &s_bar[0]);
+        if (ncb > 1) issue(s_col[1], s_cbs[1], &s_bar[1]);
+    }
+
+    // ---- row fragment -> registers ----
+    mbar_wait(&s_bar[2], 0);
+    uint32_t rl[8][W1], rh[8][W1];
+    int rlab[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int r = i * 16 + ty;
+#pragma unroll
+        for (int w = 0; w < W1; w++) {
+            rl[i][w] = s_row[w * TILE + r];
+            rh[i][w] = s_row[(W1 + w) * TILE + r];
+        }
+        rlab[i] = (int)s_row[NP * TILE + r];
+    }
+    const int row_lim = sb.n - rb * TILE;  // valid local rows are < row_lim
+    const int maxcd = sb.maxcd;
+    unsigned long long evaluated = 0;
+
+    for (int it = 0; it < ncb; it++) {
+        const int cb = s_cbs[it];
+        const int buf = it & 1;
+        mbar_wait(&s_bar[buf], (it >> 1) & 1);
+        const uint32_t* sc = s_col[buf];
+        const int col_lim = sb.n - cb * TILE;
+        const bool diag = (cb == rb);
+        const bool full = !diag && row_lim >= TILE && col_lim >= TILE;
+        // two halves of 64 columns: the hit list holds at most 128 x 64 entries
+        for (int half = 0; half < 2; half++) {
+            if (full) {
+#pragma unroll 2
+                for (int j = half * 4; j < half * 4 + 4; j++) {
+                    const int c = j * 16 + tx;
+                    uint32_t cl[W1], chh[W1];
+#pragma unroll
+                    for (int w = 0; w < W1; w++) {
+                        cl[w] = sc[w * TILE + c];
+                        chh[w] = sc[(W1 + w) * TILE + c];
+                    }
+                    const int clab = (int)sc[NP * TILE + c];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
+                        if (cd <= maxcd && rlab[i] != clab) {
+                            const unsigned int h = atomicAdd(&s_nhits, 1u);
+                            s_hits[h] = (uint16_t)(((i * 16 + ty) << 7) | c);
+                        }
+                    }
+                }
+            } else {
+                for (int j = half * 4; j < half * 4 + 4; j++) {
+                    const int c = j * 16 + tx;
+                    uint32_t cl[W1], chh[W1];
+#pragma unroll
+                    for (int w = 0; w < W1; w++) {
+                        cl[w] = sc[w * TILE + c];
+                        chh[w] = sc[(W1 + w) * TILE + c];
+                    }
+                    const int clab = (int)sc[NP * TILE + c];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int r = i * 16 + ty;
+                        const bool valid = r < row_lim && c < col_lim && (!diag || r < c);
+                        const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
+                        if (valid && cd <= maxcd && rlab[i] != clab) {
+                            const unsigned int h = atomicAdd(&s_nhits, 1u);
+                            s_hits[h] = (uint16_t)((r << 7) | c);
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // all hits of this half recorded (and, after half 1, s_col[buf] drained)
+            const unsigned int nh = s_nhits;
+            if (tid == 0) {
+                if (half == 1) {
+                    // prefetch the tile after next into the buffer just drained
+                    if (it + 2 < ncb) issue(s_col[buf], s_cbs[it + 2], &s_bar[buf]);
+                    const int rr = min(TILE, row_lim), cc = min(TILE, col_lim);
+                    evaluated += diag ? (unsigned long long)rr * (rr - 1) / 2 : (unsigned long long)rr * cc;
+                }
+                if (nh) s_base = atomicAdd(&ctr->n_cand, (unsigned long long)nh);
+            }
+            if (nh) {
+                __syncthreads();
+                const unsigned long long b = s_base;
+                const uint32_t q_r0 = (uint32_t)(sb.q0 + (int64_t)rb * TILE), q_c0 = (uint32_t)(sb.q0 + (int64_t)cb * TILE);
+                for (unsigned int h = tid; h < nh; h += S1_THREADS) {
+                    const unsigned long long o = b + h;
+                    if (o < cand_cap) {
+                        const uint16_t v = s_hits[h];
+                        cand[o] = make_uint2(q_r0 + (v >> 7), q_c0 + (v & 127));
+                    } else {
+                        ctr->overflow = 1ull;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) s_nhits = 0;
+                __syncthreads();
+            }
+        }
+    }
+    if (tid == 0) atomicAdd(&ctr->pairs_eval, evaluated);
+}
+
+
+}  // namespace ejb

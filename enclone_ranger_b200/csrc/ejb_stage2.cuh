@@ -1,0 +1,567 @@
+// ejb_stage2.cuh — the exact join_one decision for stage-1 candidates.
+//
+//   k_stage2a      8 lanes per candidate over the packed planes: CDR3 distances, shared / independent
+//                  mutation counts against one or two references, full-length differences, FWR1/CDR1/CDR2
+//                  differences, then the integer tests of join_one.rs:216-323, 434-440, 474-493.
+//   k_stage2_slow  byte-exact warp-per-candidate restatement for the rare rows the planes cannot
+//                  represent (bytes outside ACGT-, overlapping V/J ranges, over-long contigs).
+//   k_stage2b      one thread per survivor: barcode meet, p1 * mult score, JUN_SHARE, score threshold,
+//                  V gene names, FWR1 - CDR12 identity (join_one.rs:451-470, 499-567, 710-854).
+#pragma once
+#include "ejb_p1.cuh"
+#include "ejb_types.cuh"
+
+namespace ejb {
+
+struct S2Ctx {
+    DevIn in;
+    DevParams P;
+    const SubBucket* subs;
+    const int32_t* aux;          // AUX_INTS per packed row
+    const int32_t* rowq;         // canonical row of a packed position
+    const int32_t* subq;         // sub-bucket of a packed position
+    const uint32_t* cdr3w;
+    const uint4* rowstore;
+    const uint64_t* bc_sorted;   // (exact << 32 | barcode), sorted: each exact's barcodes ascending
+    const double* powtab;        // mult_pow ^ (cdr3_normal_len * cd / n), indexed pow_off[n] + cd
+    const int32_t* pow_off;
+    P1Cache p1;
+    Counters* ctr;
+    Survivor* surv;
+    unsigned long long surv_cap;
+    uint2* slow;                 // candidates routed to the byte-exact slow path
+    uint32_t* slow_slot;
+    unsigned long long slow_cap;
+    int tuple_mode;              // 0: filter -> pass edges; 1: write an EdgeTuple per input pair
+};
+
+struct RegionDiffs {
+    int regfast, fd, c1d, c2d;
+};
+
+// Integer tests shared by the fast and the slow path, executed by one lane per candidate.
+// Appends a Survivor (+ requests its p1) unless join_one would already return false.
+__device__ __forceinline__ void s2_integer_tests(const S2Ctx& X, uint32_t q1, uint32_t q2, uint32_t slot, const SubBucket& sb, int cd1, int cd2,
+                                                 long long diffs, int nrefs, int sh0, int in0, int sh1, int in1, RegionDiffs rg, bool pre_ok,
+                                                 bool force_emit) {
+    const DevParams& P = X.P;
+    const int32_t* a1 = X.aux + (size_t)q1 * AUX_INTS;
+    const int32_t* a2 = X.aux + (size_t)q2 * AUX_INTS;
+    const uint32_t f1 = (uint32_t)a1[AX_FLAGS];
+    const int cd = cd1 + cd2;
+    bool ok = pre_ok;
+    // join_one.rs:216-234
+    if (P.is_bcr) {
+        const int total = sb.ch + sb.cl;
+        if ((double)cd / (double)total > P.cdr3_ident_thr) ok = false;
+    }
+    // :238-267
+    if (!P.is_bcr || P.max_diffs < 1000000) {
+        if (diffs > P.max_diffs) ok = false;
+        if (!P.is_bcr && diffs > 5) ok = false;
+    }
+    // :286-290
+    if ((P.max_cdr3_diffs < 1000 || !P.is_bcr) && (cd > P.max_cdr3_diffs || (!P.is_bcr && cd > 0))) ok = false;
+    // :301-323
+    const unsigned long long m1 = ((unsigned long long)(uint32_t)a1[AX_DONHI] << 32) | (uint32_t)a1[AX_DONLO];
+    const unsigned long long m2 = ((unsigned long long)(uint32_t)a2[AX_DONHI] << 32) | (uint32_t)a2[AX_DONLO];
+    if (!P.mix_donors && m1 != 0 && m2 != 0 && m1 != m2) ok = false;
+    const bool err = (m1 != m2) || __popcll(m1) != 1 || __popcll(m2) != 1;
+    // :444-447
+    const int min_sh = (nrefs == 2) ? min(sh0, sh1) : sh0;
+    const int min_in = (nrefs == 2) ? min(in0, in1) : in0;
+    // :474-476
+    if ((double)cd >= P.cdr3_mult * (double)max(1, min_in)) ok = false;
+    // :481-493
+    if (!P.old_light && cd > 0) {
+        if (!(f1 & B_LEFT_H) && a1[AX_CREFH] != -1 && a2[AX_CREFH] != -1 && a1[AX_CREFH] != a2[AX_CREFH]) ok = false;
+        if (!(f1 & B_LEFT_L) && a1[AX_CREFL] != -1 && a2[AX_CREFL] != -1 && a1[AX_CREFL] != a2[AX_CREFL]) ok = false;
+    }
+    if (!ok && !force_emit) return;
+    const int k = min_in + 2 * min_sh;
+    if (k > SR_NMAX) {
+        if (ok) atomicAdd(&X.ctr->n_errflag_range, 1ull);  // the reference panics on sr[x][u]
+        if (!force_emit) return;
+    }
+    const unsigned long long si = atomicAdd(&X.ctr->n_surv, 1ull);
+    if (si >= X.surv_cap) {
+        X.ctr->overflow = 1ull;
+        return;
+    }
+    Survivor s;
+    s.q1 = q1;
+    s.q2 = q2;
+    s.cd1 = (uint16_t)cd1;
+    s.cd2 = (uint16_t)cd2;
+    s.sh0 = sh0;
+    s.in0 = in0;
+    s.sh1 = sh1;
+    s.in1 = in1;
+    s.nrefs = (uint8_t)nrefs;
+    s.err = err ? 1 : 0;
+    s.ok = ok ? 1 : 0;
+    s.regfast = (uint8_t)rg.regfast;
+    s.fd = (uint16_t)rg.fd;
+    s.c1d = (uint16_t)rg.c1d;
+    s.c2d = (uint16_t)rg.c2d;
+    s.pad = 0;
+    s.slot = slot;
+    X.surv[si] = s;
+    if (k <= SR_NMAX) p1_request(X.p1, sb.n3, k, min_sh, X.ctr);
+}
+
+// popc of e[0..3] (positions bit0 .. bit0+127) restricted to [a, b)
+__device__ __forceinline__ int range_popc4(const uint32_t* e, int bit0, int a, int b) {
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const int lo = max(a - (bit0 + 32 * w), 0), hi = min(b - (bit0 + 32 * w), 32);
+        if (hi > lo) {
+            const uint32_t mh = (hi == 32) ? 0xffffffffu : ((1u << hi) - 1u);
+            s += __popc(e[w] & mh & ~((1u << lo) - 1u));
+        }
+    }
+    return s;
+}
+
+__device__ __forceinline__ void ld4(const uint4* p, uint32_t* o) {
+    const uint4 v = __ldg(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+
+// Fast path: 8 lanes per candidate.  Lane g handles uint4 g of every plane (128 positions).
+//   e    = (lo1^lo2)|(hi1^hi2)|(gap1^gap2)   bases differ (t1 != t2)
+//   one reference (the usual case):  A = popc(d1 & d2), B = popc(d1 & d2 & e)
+//        shares = A - B;  indeps = tot1 + tot2 - 2A + 2B                       (join_one.rs:402-419)
+//   two references: x21 = (t2 != r1) on cmp1, x12 = (t1 != r2) on cmp2, then the same counts per reference
+__global__ void __launch_bounds__(256) k_stage2a(S2Ctx X, const uint2* __restrict__ cand, const uint32_t* __restrict__ cand_slot,
+                                                 const unsigned long long* __restrict__ n_cand_p, unsigned long long cand_cap) {
+    const unsigned long long n_cand = min(*n_cand_p, cand_cap);
+    const int lane = threadIdx.x & 31;
+    const int g = lane & 7, gid = lane >> 3;
+    const unsigned int gmask = 0xffu << (8 * gid);
+    const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long base = warp0 * 4; base < n_cand; base += nwarps * 4) {
+        const unsigned long long ci = base + gid;
+        const bool valid = ci < n_cand;
+        uint2 pr = make_uint2(0, 0);
+        if (valid) pr = cand[ci];
+        const uint32_t q1 = pr.x, q2 = pr.y;
+        const uint32_t slot = (valid && cand_slot) ? cand_slot[ci] : (uint32_t)ci;
+        const SubBucket sb = X.subs[X.subq[q1]];
+        const uint4* ax1 = reinterpret_cast<const uint4*>(X.aux + (size_t)q1 * AUX_INTS);
+        const uint4* ax2 = reinterpret_cast<const uint4*>(X.aux + (size_t)q2 * AUX_INTS);
+        const uint4 a10 = __ldg(ax1), a11 = __ldg(ax1 + 1), a20 = __ldg(ax2), a21 = __ldg(ax2 + 1);
+        const uint32_t f1 = a10.x, f2 = a20.x;
+        const bool nrefs1 = (a10.y == a20.y && a10.z == a20.z && a10.w == a20.w && a11.x == a21.x);
+        const bool fast = ((f1 | f2) & F_SLOWMASK) == 0 && sb.W1 > 0 && sb.W4h > 0 && sb.W4l > 0;
+        const int tot1 = (int)a11.y, tot2 = (int)a21.y;
+        // FWR1 / CDR1 / CDR2 ranges on the left chain, usable when both rows carry identical features
+        int rF0 = 0, rF1 = 0, rC10 = 0, rC11 = 0, rC20 = 0, rC21 = 0, regfast = 0;
+        {
+            const uint4 a14 = __ldg(ax1 + 4), a15 = __ldg(ax1 + 5), a24 = __ldg(ax2 + 4), a25 = __ldg(ax2 + 5);
+            const int fr1 = (int)a14.z, cdr1 = (int)a14.w, fr2 = (int)a15.x, cdr2 = (int)a15.y, fr3 = (int)a15.z;
+            const bool same = a14.z == a24.z && a14.w == a24.w && a15.x == a25.x && a15.y == a25.y && a15.z == a25.z;
+            const uint32_t need = B_LEFT_H | B_AMINO_TIG_H;
+            const bool stdrow = (f1 & (need | B_LEFT_L)) == need && (f2 & (need | B_LEFT_L)) == need;
+            const int L = sb.Lh;
+            const bool has_f = cdr1 != -1;
+            const bool has_c1 = cdr1 != -1 && fr2 != -1 && cdr1 <= fr2;
+            const bool has_c2 = cdr2 != -1 && fr3 != -1 && cdr2 <= fr3;
+            const bool okf = !has_f || (fr1 >= 0 && fr1 <= cdr1 && cdr1 <= L);
+            const bool okc1 = !has_c1 || (cdr1 >= 0 && fr2 <= L);
+            const bool okc2 = !has_c2 || (cdr2 >= 0 && fr3 <= L);
+            if (same && stdrow && okf && okc1 && okc2) {
+                regfast = 1;
+                if (has_f) { rF0 = fr1; rF1 = cdr1; }
+                if (has_c1) { rC10 = cdr1; rC11 = fr2; }
+                if (has_c2) { rC20 = cdr2; rC21 = fr3; }
+            }
+        }
+        // packed accumulators (every field stays < 65536 after the 8-lane sum)
+        uint32_t pk0 = 0 /* cd1 | cd2<<16 */, pk1 = 0 /* A | B<<16 */, pk2 = 0 /* diffs | fd<<16 */, pk3 = 0 /* c1d | c2d<<16 */;
+        uint32_t n0 = 0 /* A0|B0 */, n1 = 0 /* O0|T01 */, n2 = 0 /* A1|B1 */, n3 = 0 /* O1|T10 */;
+        if (valid && fast) {
+            // CDR3 distances, split at the heavy/light boundary of the concatenated planes
+            if (g < sb.W1) {
+                const uint32_t* b = X.cdr3w + sb.s1_off;
+                const int64_t i1 = q1 - sb.q0, i2 = q2 - sb.q0;
+                const uint32_t x = (b[(int64_t)g * sb.npad + i1] ^ b[(int64_t)g * sb.npad + i2]) |
+                                   (b[(int64_t)(sb.W1 + g) * sb.npad + i1] ^ b[(int64_t)(sb.W1 + g) * sb.npad + i2]);
+                const int lo_bit = g * 32;
+                uint32_t hm;  // bits of this word that belong to the heavy CDR3
+                if (sb.ch >= lo_bit + 32) hm = 0xffffffffu;
+                else if (sb.ch <= lo_bit) hm = 0u;
+                else hm = (1u << (sb.ch - lo_bit)) - 1u;
+                pk0 = (uint32_t)__popc(x & hm) | ((uint32_t)__popc(x & ~hm) << 16);
+            }
+            const uint4* r1 = X.rowstore + sb.rs_off + (int64_t)(q1 - sb.q0) * sb.rec_u4;
+            const uint4* r2 = X.rowstore + sb.rs_off + (int64_t)(q2 - sb.q0) * sb.rec_u4;
+#pragma unroll
+            for (int m = 0; m < 2; m++) {
+                const int W4 = m ? sb.W4l : sb.W4h;
+                const int gapbit = (sb.gap >> m) & 1;
+                const int off = m ? rec_planes(sb.gap & 1) * sb.W4h : 0;
+                if (g < W4) {
+                    uint32_t al[4], ah[4], ad[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bd[4], bg[4] = {0, 0, 0, 0}, e[4];
+                    ld4(r1 + off + g, al); ld4(r1 + off + W4 + g, ah); ld4(r1 + off + 2 * W4 + g, ad);
+                    ld4(r2 + off + g, bl); ld4(r2 + off + W4 + g, bh); ld4(r2 + off + 2 * W4 + g, bd);
+                    if (gapbit) { ld4(r1 + off + 3 * W4 + g, ag); ld4(r2 + off + 3 * W4 + g, bg); }
+                    int A = 0, B = 0, df = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        e[w] = (al[w] ^ bl[w]) | (ah[w] ^ bh[w]) | (ag[w] ^ bg[w]);
+                        const uint32_t both = ad[w] & bd[w];
+                        A += __popc(both);
+                        B += __popc(both & e[w]);
+                        df += __popc(e[w]);
+                    }
+                    pk1 += (uint32_t)A | ((uint32_t)B << 16);
+                    pk2 += (uint32_t)df;
+                    if (m == 0 && regfast) {
+                        pk2 += (uint32_t)range_popc4(e, g * 128, rF0, rF1) << 16;
+                        pk3 += (uint32_t)range_popc4(e, g * 128, rC10, rC11) | ((uint32_t)range_popc4(e, g * 128, rC20, rC21) << 16);
+                    }
+                    if (!nrefs1) {
+                        uint32_t arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
+                        const int ro = off + (3 + gapbit) * W4;
+                        ld4(r1 + ro + g, arl); ld4(r1 + ro + W4 + g, arh); ld4(r1 + ro + 2 * W4 + g, ac);
+                        ld4(r2 + ro + g, brl); ld4(r2 + ro + W4 + g, brh); ld4(r2 + ro + 2 * W4 + g, bc);
+                        int A0 = 0, B0 = 0, O0 = 0, T01 = 0, A1 = 0, B1 = 0, O1 = 0, T10 = 0;
+#pragma unroll
+                        for (int w = 0; w < 4; w++) {
+                            const uint32_t x21 = ((bl[w] ^ arl[w]) | (bh[w] ^ arh[w]) | bg[w]) & ac[w];  // t2 != r1 on k1's ranges
+                            const uint32_t x12 = ((al[w] ^ brl[w]) | (ah[w] ^ brh[w]) | ag[w]) & bc[w];  // t1 != r2 on k2's ranges
+                            const uint32_t d1 = ad[w], d2 = bd[w];
+                            A0 += __popc(d1 & x21); B0 += __popc(d1 & x21 & e[w]); O0 += __popc(d1 ^ x21); T01 += __popc(x21);
+                            A1 += __popc(x12 & d2); B1 += __popc(x12 & d2 & e[w]); O1 += __popc(x12 ^ d2); T10 += __popc(x12);
+                        }
+                        n0 += (uint32_t)A0 | ((uint32_t)B0 << 16);
+                        n1 += (uint32_t)O0 | ((uint32_t)T01 << 16);
+                        n2 += (uint32_t)A1 | ((uint32_t)B1 << 16);
+                        n3 += (uint32_t)O1 | ((uint32_t)T10 << 16);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            pk0 += __shfl_xor_sync(0xffffffffu, pk0, o);
+            pk1 += __shfl_xor_sync(0xffffffffu, pk1, o);
+            pk2 += __shfl_xor_sync(0xffffffffu, pk2, o);
+            pk3 += __shfl_xor_sync(0xffffffffu, pk3, o);
+        }
+        if (valid && fast && !nrefs1) {  // group-uniform branch: shuffle inside the 8-lane group only
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                n0 += __shfl_xor_sync(gmask, n0, o);
+                n1 += __shfl_xor_sync(gmask, n1, o);
+                n2 += __shfl_xor_sync(gmask, n2, o);
+                n3 += __shfl_xor_sync(gmask, n3, o);
+            }
+        }
+        if (valid && g == 0) {
+            if (fast) {
+                const int cd1 = (int)(pk0 & 0xffff), cd2 = (int)(pk0 >> 16);
+                const int diffs = (int)(pk2 & 0xffff);
+                RegionDiffs rg;
+                rg.regfast = regfast;
+                rg.fd = (int)(pk2 >> 16);
+                rg.c1d = (int)(pk3 & 0xffff);
+                rg.c2d = (int)(pk3 >> 16);
+                if (nrefs1) {
+                    const int A = (int)(pk1 & 0xffff), B = (int)(pk1 >> 16);
+                    s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, 1, A - B, tot1 + tot2 - 2 * A + 2 * B, 0, 0, rg, true, X.tuple_mode != 0);
+                } else {
+                    const int A0 = (int)(n0 & 0xffff), B0 = (int)(n0 >> 16), O0 = (int)(n1 & 0xffff), T01 = (int)(n1 >> 16);
+                    const int A1 = (int)(n2 & 0xffff), B1 = (int)(n2 >> 16), O1 = (int)(n3 & 0xffff), T10 = (int)(n3 >> 16);
+                    // join_one.rs:434-440: total[0] = (tot1, T01), total[1] = (T10, tot2)
+                    bool ok = true;
+                    if (abs(tot1 - T10) > X.P.max_degradation) ok = false;
+                    if (abs(T01 - tot2) > X.P.max_degradation) ok = false;
+                    if (ok || X.tuple_mode)
+                        s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, 2, A0 - B0, O0 + 2 * B0, A1 - B1, O1 + 2 * B1, rg, ok, X.tuple_mode != 0);
+                }
+            } else {
+                const unsigned long long si = atomicAdd(&X.ctr->n_slow, 1ull);
+                if (si < X.slow_cap) {
+                    X.slow[si] = pr;
+                    X.slow_slot[si] = slot;
+                } else {
+                    X.ctr->overflow = 1ull;
+                }
+            }
+        }
+    }
+}
+
+// Slow path: one warp per candidate, literal byte-level restatement of join_one.rs:216-440
+// ('N' and other odd bytes, overlapping V/J ranges, the V bail-out, over-long contigs).
+__global__ void __launch_bounds__(256) k_stage2_slow(S2Ctx X, const unsigned long long* __restrict__ n_slow_p) {
+    const unsigned long long n_slow = min(*n_slow_p, X.slow_cap);
+    const int lane = threadIdx.x & 31;
+    const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const DevIn& in = X.in;
+    for (unsigned long long ci = warp0; ci < n_slow; ci += nwarps) {
+        const uint2 pr = X.slow[ci];
+        const uint32_t q1 = pr.x, q2 = pr.y, slot = X.slow_slot[ci];
+        const SubBucket sb = X.subs[X.subq[q1]];
+        const int64_t k1 = X.rowq[q1], k2 = X.rowq[q2];
+        const int32_t* a1 = X.aux + (size_t)q1 * AUX_INTS;
+        const int32_t* a2 = X.aux + (size_t)q2 * AUX_INTS;
+        const uint32_t f1 = (uint32_t)a1[AX_FLAGS], f2 = (uint32_t)a2[AX_FLAGS];
+        if ((f1 | f2) & F_PANIC) {
+            if (lane == 0) atomicAdd(&X.ctr->n_errflag_panic, 1ull);
+            if (!X.tuple_mode) continue;
+        }
+        // CDR3 distances on bytes
+        int cd1 = 0, cd2 = 0;
+        {
+            const uint8_t *a = in.cdr3_bytes + in.row_cdr3_off[2 * k1], *b = in.cdr3_bytes + in.row_cdr3_off[2 * k2];
+            for (int p = lane; p < sb.ch; p += 32) cd1 += (a[p] != b[p]);
+            a = in.cdr3_bytes + in.row_cdr3_off[2 * k1 + 1];
+            b = in.cdr3_bytes + in.row_cdr3_off[2 * k2 + 1];
+            for (int p = lane; p < sb.cl; p += 32) cd2 += (a[p] != b[p]);
+        }
+        // full-length differences (join_one.rs:238-260)
+        int diffs = 0;
+        for (int m = 0; m < 2; m++) {
+            const int L = m ? sb.Ll : sb.Lh;
+            const uint8_t *a = in.tig_bytes + in.row_tig_off[2 * k1 + m], *b = in.tig_bytes + in.row_tig_off[2 * k2 + m];
+            const bool hd = in.row_has_del[2 * k1 + m] || in.row_has_del[2 * k2 + m];
+            if (!hd) {
+                for (int p = lane; p < L; p += 32) diffs += (base2bit(a[p]) != base2bit(b[p]));
+            } else {
+                for (int p = lane; p < L; p += 32) diffs += (a[p] != b[p]);
+            }
+        }
+        const int nrefs = (a1[AX_VSH] == a2[AX_VSH] && a1[AX_VSL] == a2[AX_VSL] && a1[AX_JSH] == a2[AX_JSH] && a1[AX_JSL] == a2[AX_JSL]) ? 1 : 2;
+        int sh[2] = {0, 0}, ind[2] = {0, 0}, tot[2][2] = {{0, 0}, {0, 0}};
+        bool bail = false;
+        for (int u = 0; u < nrefs; u++) {
+            const int64_t k = u ? k2 : k1;
+            for (int m = 0; m < 2; m++) {
+                const int L = m ? sb.Ll : sb.Lh;
+                const uint8_t *t1 = in.tig_bytes + in.row_tig_off[2 * k1 + m], *t2 = in.tig_bytes + in.row_tig_off[2 * k2 + m];
+                for (int si = 0; si < 2; si++) {
+                    const int sg = si ? in.row_js[2 * k + m] : in.row_vs[2 * k + m];
+                    const uint8_t* seg = in.seg_bytes + in.seg_off[sg];
+                    const long long slen = in.seg_off[sg + 1] - in.seg_off[sg];
+                    long long rng = slen - (si ? X.P.ref_j_trim : X.P.ref_v_trim);
+                    if (rng < 0) rng = 0;  // flagged F_PANIC
+                    if (si == 0 && rng > L) {
+                        bail = true;  // p reaches tig.len(): return false (join_one.rs:371-373)
+                        rng = L;
+                    }
+                    if (si == 1 && rng > L) rng = L;  // flagged F_PANIC
+                    for (long long p = lane; p < rng; p += 32) {
+                        uint8_t a, b, r;
+                        if (si == 0) {
+                            a = t1[p];
+                            b = t2[p];
+                            r = bit2base(base2bit(seg[p]));
+                        } else {
+                            a = t1[L - p - 1];
+                            b = t2[L - p - 1];
+                            r = bit2base(base2bit(seg[slen - p - 1]));
+                        }
+                        if (a == b && a != r) sh[u]++;
+                        else if ((a == r && b != r) || (b == r && a != r)) ind[u]++;
+                        else if (a != r && b != r) ind[u] += 2;
+                        if (a != r) tot[u][0]++;
+                        if (b != r) tot[u][1]++;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cd1 += __shfl_xor_sync(0xffffffffu, cd1, o);
+            cd2 += __shfl_xor_sync(0xffffffffu, cd2, o);
+            diffs += __shfl_xor_sync(0xffffffffu, diffs, o);
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                sh[u] += __shfl_xor_sync(0xffffffffu, sh[u], o);
+                ind[u] += __shfl_xor_sync(0xffffffffu, ind[u], o);
+                tot[u][0] += __shfl_xor_sync(0xffffffffu, tot[u][0], o);
+                tot[u][1] += __shfl_xor_sync(0xffffffffu, tot[u][1], o);
+            }
+        }
+        if (lane == 0) {
+            bool ok = !bail && !((f1 | f2) & F_PANIC);
+            if (nrefs == 2) {  // join_one.rs:434-440
+                for (int m = 0; m < 2; m++) {
+                    const long long a = tot[0][m], b = tot[1][m];
+                    if ((a <= b ? b - a : a - b) > X.P.max_degradation) ok = false;
+                }
+            }
+            RegionDiffs rg = {0, 0, 0, 0};
+            if (ok || X.tuple_mode)
+                s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, nrefs, sh[0], ind[0], sh[1], ind[1], rg, ok, X.tuple_mode != 0);
+        }
+    }
+}
+
+// sorted-list intersection of the two exacts' barcodes (vector_utils meet, join_one.rs:451-470)
+__device__ __forceinline__ bool bc_meet(const S2Ctx& X, int e1, int e2) {
+    int64_t i = X.in.ex_cell_off[e1], ie = X.in.ex_cell_off[e1 + 1];
+    int64_t j = X.in.ex_cell_off[e2], je = X.in.ex_cell_off[e2 + 1];
+    while (i < ie && j < je) {
+        const uint32_t a = (uint32_t)X.bc_sorted[i], b = (uint32_t)X.bc_sorted[j];
+        if (a < b) i++;
+        else if (b < a) j++;
+        else return true;
+    }
+    return false;
+}
+
+// Stage 2b: one thread per survivor.  Emits pass edges (filter mode) or EdgeTuples (tuple mode).
+__global__ void __launch_bounds__(256) k_stage2b(S2Ctx X, const unsigned long long* __restrict__ n_surv_p, unsigned long long* __restrict__ pass_w,
+                                                 unsigned long long pass_cap, EdgeTuple* __restrict__ tuples) {
+    const unsigned long long n_surv = min(*n_surv_p, X.surv_cap);
+    const DevIn& in = X.in;
+    const DevParams& P = X.P;
+    for (unsigned long long si = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; si < n_surv;
+         si += (unsigned long long)gridDim.x * blockDim.x) {
+        const Survivor s = X.surv[si];
+        const uint32_t q1 = s.q1, q2 = s.q2;
+        const SubBucket sb = X.subs[X.subq[q1]];
+        const int32_t* a1 = X.aux + (size_t)q1 * AUX_INTS;
+        const int32_t* a2 = X.aux + (size_t)q2 * AUX_INTS;
+        const uint32_t f1 = (uint32_t)a1[AX_FLAGS], f2 = (uint32_t)a2[AX_FLAGS];
+        bool ok = s.ok != 0;
+        const int cd = (int)s.cd1 + (int)s.cd2;
+        const int min_sh = (s.nrefs == 2) ? min(s.sh0, s.sh1) : s.sh0;
+        const int min_in = (s.nrefs == 2) ? min(s.in0, s.in1) : s.in0;
+        // :83-89 exact subclonotypes with 2 or 3 chains only
+        if (!(f1 & B_NCH_OK) || !(f2 & B_NCH_OK)) ok = false;
+        // :451-470 barcode overlap
+        if (ok || X.tuple_mode) {
+            if (a1[AX_NCELLS] == 1 && a2[AX_NCELLS] == 1) {
+                if (a1[AX_BC0] == a2[AX_BC0]) ok = false;
+            } else if (bc_meet(X, a1[AX_EXACT], a2[AX_EXACT])) {
+                ok = false;
+            }
+        }
+        // :499-544
+        const int k = min_in + 2 * min_sh, d = min_sh;
+        double p1 = 0.0;
+        if (k <= SR_NMAX) p1 = p1_lookup(X.p1, sb.n3, k, d); else ok = false;
+        const double mult = __dmul_rn(X.powtab[X.pow_off[sb.ch] + s.cd1], X.powtab[X.pow_off[sb.cl] + s.cd2]);
+        const double score = __dmul_rn(p1, mult);
+        // :548-567 JUN_SHARE
+        bool accept = false;
+        if (P.comp_filt < 1000000 && score > P.max_score && min_sh < P.auto_share && (P.comp_filt_bound == 0 || min_in <= P.comp_filt_bound) &&
+            (f1 & B_NCH2) && (f2 & B_NCH2) && (f1 & B_JUN_LEFT)) {
+            const long long comp = min(a1[AX_HCOMP], a2[AX_HCOMP]);
+            if (comp - cd >= P.comp_filt) accept = true;
+        }
+        // :710-715
+        if (!accept && score > P.max_score && min_sh < P.auto_share) ok = false;
+        // :722-758 V gene names (rare: names differ)
+        if (ok && (a1[AX_VNAMEH] != a2[AX_VNAMEH] || a1[AX_VNAMEL] != a2[AX_VNAMEL])) {
+            for (int i = 0; i < 2 && ok; i++) {
+                if (a1[AX_VNAMEH + i] == a2[AX_VNAMEH + i]) continue;
+                const int va = a1[AX_VREFH + i], vb = a2[AX_VREFH + i];
+                const uint8_t *y1 = in.ref_bytes + in.ref_off[va], *y2 = in.ref_bytes + in.ref_off[vb];
+                const long long l1 = in.ref_off[va + 1] - in.ref_off[va], l2 = in.ref_off[vb + 1] - in.ref_off[vb];
+                const long long nn = min(l1, l2);
+                for (long long m = 0; m < nn; m++)
+                    if (base2bit(y1[m]) != base2bit(y2[m])) {
+                        ok = false;
+                        break;
+                    }
+                const int x1 = a1[AX_CHH + i], x2 = a2[AX_CHH + i];
+                const int ua = in.ch_u_ref[x1], ub = in.ch_u_ref[x2];
+                if (ok && ua != -1 && ub != -1) {
+                    const uint8_t *w1 = in.ref_bytes + in.ref_off[ua], *w2 = in.ref_bytes + in.ref_off[ub];
+                    const long long m1 = in.ref_off[ua + 1] - in.ref_off[ua], m2 = in.ref_off[ub + 1] - in.ref_off[ub];
+                    const long long mm = min(m1, m2);
+                    for (long long m = 0; m < mm; m++)
+                        if (base2bit(w1[m1 - 1 - m]) != base2bit(w2[m2 - 1 - m])) {
+                            ok = false;
+                            break;
+                        }
+                }
+            }
+        }
+        // :766-854 FWR1 identity minus CDR1+2 identity on the left chain
+        if (ok) {
+            long long fwr1_len = 0, cdr1_len = 0, cdr2_len = 0, fwr1_diffs = 0, cdr1_diffs = 0, cdr2_diffs = 0;
+            bool panic = false;
+            if (s.regfast) {
+                // both rows: chain 0 is the only left chain, identical feature starts, seq_del_amino == contig
+                const int fr1 = a1[AX_FR1], cdr1 = a1[AX_CDR1], fr2 = a1[AX_FR2], cdr2 = a1[AX_CDR2], fr3 = a1[AX_FR3];
+                if (cdr1 != -1) { fwr1_len = cdr1 - fr1; fwr1_diffs = s.fd; }
+                if (cdr1 != -1 && fr2 != -1 && cdr1 <= fr2) { cdr1_len = fr2 - cdr1; cdr1_diffs = s.c1d; }
+                if (cdr2 != -1 && fr3 != -1 && cdr2 <= fr3) { cdr2_len = fr3 - cdr2; cdr2_diffs = s.c2d; }
+            } else {
+                const int64_t k1 = X.rowq[q1], k2 = X.rowq[q2];
+                for (int m = 0; m < 2; m++) {
+                    const int x1 = a1[AX_CHH + m], x2 = a2[AX_CHH + m];
+                    if (!in.ch_left[x1]) continue;
+                    const uint8_t *s1, *s2;
+                    long long sl1, sl2;
+                    if (in.ch_amino_off[x1] != -1) { s1 = in.amino_bytes + in.ch_amino_off[x1]; sl1 = in.ch_amino_len[x1]; }
+                    else { s1 = in.tig_bytes + in.row_tig_off[2 * k1 + m]; sl1 = m ? sb.Ll : sb.Lh; }
+                    if (in.ch_amino_off[x2] != -1) { s2 = in.amino_bytes + in.ch_amino_off[x2]; sl2 = in.ch_amino_len[x2]; }
+                    else { s2 = in.tig_bytes + in.row_tig_off[2 * k2 + m]; sl2 = m ? sb.Ll : sb.Lh; }
+                    auto region = [&](long long r1a, long long r1b, long long r2a, long long r2b, long long& rlen, long long& rdiffs) {
+                        const long long len = r1b - r1a;
+                        if (r2b - r2a == len) {
+                            if (len > 0 && (r1a + len > sl1 || r2a + len > sl2 || r1a < 0 || r2a < 0)) { panic = true; return; }
+                            long long df = 0;
+                            for (long long p = 0; p < len; p++) df += (s1[p + r1a] != s2[p + r2a]);
+                            rlen = len;
+                            rdiffs = df;
+                        }
+                    };
+                    const int f1a = in.ch_fr1[x1], c1a = in.ch_cdr1[x1], f2a = in.ch_fr2[x1], c2a = in.ch_cdr2[x1], f3a = in.ch_fr3[x1];
+                    const int f1b = in.ch_fr1[x2], c1b = in.ch_cdr1[x2], f2b = in.ch_fr2[x2], c2b = in.ch_cdr2[x2], f3b = in.ch_fr3[x2];
+                    if (c1a != -1 && c1b != -1) {
+                        if (c1a < f1a || c1b < f1b) panic = true;  // usize underflow in the reference
+                        else region(f1a, c1a, f1b, c1b, fwr1_len, fwr1_diffs);
+                    }
+                    if (c1a != -1 && f2a != -1 && c1b != -1 && f2b != -1 && c1a <= f2a && c1b <= f2b) region(c1a, f2a, c1b, f2b, cdr1_len, cdr1_diffs);
+                    if (c2a != -1 && f3a != -1 && c2b != -1 && f3b != -1 && c2a <= f3a && c2b <= f3b) region(c2a, f3a, c2b, f3b, cdr2_len, cdr2_diffs);
+                }
+            }
+            if (panic) {
+                atomicAdd(&X.ctr->n_errflag_panic, 1ull);
+                ok = false;
+            } else if (fwr1_len > 0 && cdr1_len > 0 && cdr2_len > 0) {
+                const double fwr1_identity = 100.0 * (double)(fwr1_len - fwr1_diffs) / (double)fwr1_len;
+                const long long len = cdr1_len + cdr2_len, df = cdr1_diffs + cdr2_diffs;
+                const double cdr12_identity = 100.0 * (double)(len - df) / (double)len;
+                if (fwr1_identity - cdr12_identity >= P.fwr1_cdr12_delta) ok = false;
+            }
+        }
+        if (X.tuple_mode) {
+            EdgeTuple t;
+            t.cd = cd;
+            t.nrefs = s.nrefs;
+            t.sh0 = s.sh0;
+            t.sh1 = (s.nrefs == 2) ? s.sh1 : 0;
+            t.in0 = s.in0;
+            t.in1 = (s.nrefs == 2) ? s.in1 : 0;
+            t.k = k;
+            t.d = d;
+            t.n = sb.n3;
+            t.err = s.err;
+            t.pass = ok ? 1 : 0;
+            t.pad = 0;
+            t.p1 = p1;
+            t.mult = mult;
+            t.score = score;
+            tuples[s.slot] = t;
+        } else if (ok) {
+            const unsigned long long o = atomicAdd(&X.ctr->n_pass, 1ull);
+            if (o < pass_cap) pass_w[o] = ((unsigned long long)(uint32_t)X.rowq[q1] << 28) | (unsigned long long)(uint32_t)X.rowq[q2];
+            else X.ctr->overflow = 1ull;
+        }
+    }
+}
+
+}  // namespace ejb

@@ -1,0 +1,176 @@
+// ejb_types.cuh — shared device/host types and helpers of the sm_100a clonotype join.
+//
+// Kernel map (reference function each one replaces):
+//   ejb_pack.cuh    k_heads / k_keys / k_subheads / k_subinfo  bucket scan of join_exacts, enclone/src/join.rs:68-88
+//                   k_pack_rows  the "bucketer": 2-bit planes of contigs + their V/J references, compare
+//                                masks, reference-difference bitmaps (the per-ROW half of the per-base
+//                                compares of enclone_core/src/join_one.rs:343-429)
+//   ejb_stage1.cuh  k_stage1<W1> CDR3 Hamming pre-filter, join_one.rs:216-234, 271-290, + the same-class
+//                                skip of enclone/src/join_core.rs:32
+//   ejb_stage2.cuh  k_stage2a / k_stage2_slow  shares / indeps / diffs + integer tests,
+//                                join_one.rs:238-267, 301-440, 474-493, region diffs of :766-854
+//                   k_stage2b    barcode meet, score, JUN_SHARE, V names, FWR1/CDR12, join_one.rs:451-470,
+//                                499-567, 710-854
+//   ejb_p1.cuh      k_p1         p_at_most_m_distinct_in_sample_of_x_from_n_double, join_one.rs:22-43
+//   ejb_forest.cuh  k_bor_*      lexicographic spanning forest == pot of join_core.rs:23-50
+//                   k_two_cell / k_exact_union / k_labels   join.rs:120-178, join2.rs:69-84
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dd.cuh"
+
+namespace ejb {
+
+constexpr int TILE = 128;          // rows / cols of one stage-1 tile
+constexpr int S1_THREADS = 256;
+constexpr int S1_STRIP = 4;        // column tiles per CTA (row fragment stays in registers)
+constexpr int MAXW1 = 6;           // concatenated CDR3 (heavy+light) up to 192 nt on the fast path
+constexpr int MAXW4 = 8;           // contig up to 1024 nt on the stage-2 fast path
+constexpr int SR_NMAX = 3000;      // stirling2_ratio_table_double(3000), start.rs:344
+
+// ---- per-row record `aux`: AUX_INTS int32 per packed row position ----
+enum AuxField {
+    AX_FLAGS = 0, AX_VSH, AX_VSL, AX_JSH, AX_JSL, AX_TOT, AX_EXACT, AX_NCELLS,          // uint4 #0, #1
+    AX_DONLO, AX_DONHI, AX_CREFH, AX_CREFL, AX_HCOMP, AX_VREFH, AX_VREFL, AX_BC0,       // uint4 #2, #3
+    AX_VNAMEH, AX_VNAMEL, AX_FR1, AX_CDR1, AX_FR2, AX_CDR2, AX_FR3, AX_CHH,             // uint4 #4, #5
+    AX_CHL, AX_PAD1, AX_PAD2, AX_PAD3,                                                  // uint4 #6
+    AUX_INTS
+};
+static_assert(AUX_INTS == 28, "aux record is 7 uint4");
+
+enum RowFlags : uint32_t {
+    F_ODDBYTE_H = 1u, F_ODDBYTE_L = 2u,   // contig has a byte outside ACGT ('-' is fine when has_del is set)
+    F_CDR3_IRREG = 4u,                    // a CDR3 byte outside ACGT
+    F_SLOWGEOM = 8u,                      // V/J ranges overlap, or the V range exceeds the contig
+    F_PANIC = 16u,                        // the reference would panic on this row (J range > contig ...)
+    F_HASDEL_H = 32u, F_HASDEL_L = 64u,
+    F_SLOWMASK = F_ODDBYTE_H | F_ODDBYTE_L | F_CDR3_IRREG | F_SLOWGEOM | F_PANIC,
+    // facts about the row's exact subclonotype
+    B_NCH_OK = 1u << 16,      // share.len() in 2..=3           join_one.rs:87
+    B_NCH2 = 1u << 17,        // share.len() == 2               join_one.rs:554
+    B_JUN_LEFT = 1u << 18,    // share[0].left != share[1].left join_one.rs:556
+    B_LEFT_H = 1u << 19,      // left flag of the row's chain 0 / 1
+    B_LEFT_L = 1u << 20,
+    B_AMINO_TIG_H = 1u << 21  // seq_del_amino of chain 0 is the row's contig
+};
+
+struct SubBucket {
+    int64_t j0;       // first position in the dense (sorted) order
+    int64_t q0;       // first packed row position (multiple of 4: sub-buckets are padded to 16 bytes)
+    int64_t s1_off;   // word offset of this sub-bucket's CDR3 planes in cdr3w
+    int64_t rs_off;   // uint4 offset of this sub-bucket's row records in rowstore
+    int32_t n;        // rows
+    int32_t npad;     // n rounded up to a multiple of 4 (16-byte TMA granules)
+    int32_t ch, cl;   // CDR3 nt lengths
+    int32_t Lh, Ll;   // contig lengths
+    int32_t W1;       // words per plane of the concatenated CDR3; 0 => longer than the fast path
+    int32_t W4h, W4l; // uint4 per plane of the heavy / light contig; 0 => longer than the fast path
+    int32_t gap;      // bit m set: chain m of some row has_del => a gap plane is stored for that chain
+    int32_t rec_u4;   // uint4 per row record
+    int32_t maxcd;    // stage-1 threshold on the CDR3 distance (superset of join_one.rs:231,286-290)
+    int32_t blk0;     // first global 128-row block id
+    int32_t n3;       // 3 * (Lh + Ll)  (join_one.rs:499)
+    int32_t owner;    // rank that owns this sub-bucket (multi-GPU sharding)
+    int32_t pad;
+};
+// Row record layout, per chain m (W4 = W4h or W4l uint4 per plane, in this order):
+//   t_lo, t_hi : 2-bit code of the contig base (A,C,G,T = 0..3; '-' = 0 with the gap bit)
+//   d          : cmp & (contig base != own reference base)
+//   [gap]      : '-' positions (only when SubBucket.gap has bit m)
+//   r_lo, r_hi : the row's own V / J reference bases in CONTIG coordinates (V from the start, J from the end)
+//   cmp        : positions join_one compares: p < |V|-ref_v_trim  or  p >= L-(|J|-ref_j_trim)
+__host__ __device__ __forceinline__ int rec_planes(int gapbit) { return 6 + (gapbit ? 1 : 0); }
+
+// Device view of the raw (uploaded) input, same meaning as ejb_input.
+struct DevIn {
+    int64_t n_rows, n_exacts, n_chains, n_cells, n_segs, n_refs;
+    int64_t n_tig_bytes, n_cdr3_bytes, n_amino_bytes, n_seg_bytes, n_ref_bytes;
+    const int32_t *row_nchains, *row_len, *row_vs, *row_js, *row_cdr3_len, *row_exact, *row_exact_col;
+    const int64_t *row_tig_off, *row_cdr3_off;
+    const uint8_t *row_has_del, *tig_bytes, *cdr3_bytes;
+    const int64_t *ex_chain_off, *ex_cell_off;
+    const uint8_t* ch_left;
+    const int32_t *ch_c_ref, *ch_v_ref, *ch_u_ref, *ch_fr1, *ch_cdr1, *ch_fr2, *ch_cdr2, *ch_fr3, *ch_hcomp, *ch_amino_len;
+    const int64_t* ch_amino_off;
+    const uint8_t* amino_bytes;
+    const int32_t* cell_donor;
+    const uint32_t* cell_barcode;
+    const int64_t* seg_off;
+    const uint8_t* seg_bytes;
+    const int32_t* seg_canon;  // content-canonical seg id (host-built)
+    const int64_t* ref_off;
+    const uint8_t* ref_bytes;
+    const int32_t* ref_name_id;
+};
+
+// Flat join knobs on the device.
+struct DevParams {
+    int is_bcr, mix_donors, easy, old_light;
+    double max_score, cdr3_mult, cdr3_ident_thr /* 1.0 - join_cdr3_ident/100.0 */, fwr1_cdr12_delta;
+    long long max_cdr3_diffs, auto_share, comp_filt, comp_filt_bound, max_diffs, max_degradation, ref_v_trim, ref_j_trim;
+};
+
+struct Survivor {       // a candidate that passed the integer tests of stage 2
+    uint32_t q1, q2;
+    uint16_t cd1, cd2;
+    int32_t sh0, in0, sh1, in1;
+    uint8_t nrefs, err, ok, regfast;   // regfast: fd/c1d/c2d below are valid
+    uint16_t fd, c1d, c2d, pad;        // FWR1 / CDR1 / CDR2 nucleotide differences (join_one.rs:766-854)
+    uint32_t slot;                     // output slot (tuple mode)
+};
+
+struct EdgeTuple {      // numeric members of PotentialJoin (defs.rs:870-891)
+    int32_t cd, nrefs, sh0, sh1, in0, in1, k, d, n, err, pass, pad;
+    double p1, mult, score;
+};
+
+struct Counters {       // device-side counters, one instance per context
+    unsigned long long n_cand, n_slow, n_surv, n_pass, n_newkeys, pairs_eval, n_forest, n_alive;
+    unsigned long long n_two_cell, n_errflag_range, n_errflag_panic, overflow, n_slow_total, n_surv_total, n_pass_total;
+    unsigned long long p1_unique;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int base2bit(uint8_t b) {  // debruijn base_to_bits: non-ACGT -> 0
+    switch (b) {
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return 0;
+    }
+}
+__device__ __forceinline__ bool is_acgt(uint8_t b) { return b == 'A' || b == 'C' || b == 'G' || b == 'T'; }
+__device__ __forceinline__ uint8_t bit2base(int x) { return (uint8_t)("ACGT"[x]); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    while (!mbar_try_wait(bar, phase)) {
+    }
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+}  // namespace ejb

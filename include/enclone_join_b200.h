@@ -172,6 +172,7 @@ typedef struct ejb_stats {
     int64_t pairs_scored;       /* sum over sub-buckets of n(n-1)/2  (the BASELINE metric's unit) */
     int64_t pairs_evaluated;    /* pairs whose CDR3 distance was actually computed on the device  */
     int64_t stage1_candidates;  /* pairs passing the CDR3 pre-filter and not already connected    */
+    int64_t stage2_slow;        /* candidates scored by the byte-exact slow path                  */
     int64_t stage2_survivors;   /* candidates passing the integer tests (reach the score)         */
     int64_t pass_edges;         /* candidates for which join_one would return true                */
     int64_t forest_edges;       /* edges of the lexicographic spanning forest (= pot, join.rs:105)*/
