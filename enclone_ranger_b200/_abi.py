@@ -135,6 +135,9 @@ class EjbStats(C.Structure):
         ("ms_finalize", C.c_double),
         ("ms_d2h", C.c_double),
         ("ms_replay", C.c_double),
+        ("ms_stage2a", C.c_double),
+        ("stage1_launches", C.c_int64),
+        ("stage2a_launches", C.c_int64),
         ("ms_device_total", C.c_double),
         ("ms_total", C.c_double),
     ]
@@ -166,41 +169,6 @@ class EjbResult(C.Structure):
         ("eq_z", _i32p),
         ("stats", EjbStats),
         ("opaque", C.c_void_p),
-    ]
-
-
-class OracleResult(C.Structure):
-    _fields_ = [
-        ("n_edges", C.c_int64),
-        ("edge_k1", _i32p),
-        ("edge_k2", _i32p),
-        ("edge_cd", _i32p),
-        ("edge_nrefs", _i32p),
-        ("edge_shares", _i32p),
-        ("edge_indeps", _i32p),
-        ("edge_k", _i32p),
-        ("edge_d", _i32p),
-        ("edge_n", _i32p),
-        ("edge_p1", _f64p),
-        ("edge_mult", _f64p),
-        ("edge_score", _f64p),
-        ("edge_err", _u8p),
-        ("n_rows", C.c_int64),
-        ("eq_x", _i32p),
-        ("eq_y", _i32p),
-        ("eq_z", _i32p),
-        ("labels", _i32p),
-        ("n_buckets", C.c_int64),
-        ("pairs_lens", C.c_int64),
-        ("pairs_scored", C.c_int64),
-        ("join_one_calls", C.c_int64),
-        ("pot_found", C.c_int64),
-        ("two_cell_deleted", C.c_int64),
-        ("joins", C.c_int64),
-        ("errors", C.c_int64),
-        ("seconds_join", C.c_double),
-        ("threads", C.c_int32),
-        ("error", C.c_char * 256),
     ]
 
 
@@ -243,7 +211,6 @@ class SynthSummary(C.Structure):
 
 LIB_JOIN = os.path.join(HERE, "libenclone_join_b200.so")
 LIB_SYNTH = os.path.join(HERE, "libejb_synth.so")
-LIB_ORACLE = os.path.join(ROOT, "oracle", "liboracle.so")
 
 _cache = {}
 
@@ -278,6 +245,8 @@ def load_join():
                 "(`python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
         L = C.CDLL(LIB_JOIN)
         L.ejb_abi_version.restype = C.c_int
+        L.ejb_abi_sizes.argtypes = [_i64p]
+        L.ejb_abi_sizes.restype = None
         L.ejb_params_default.argtypes = [C.POINTER(EjbParams), C.c_int]
         L.ejb_params_default.restype = None
         L.ejb_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]
@@ -304,25 +273,3 @@ def load_join():
         L.ejb_measure_peaks.restype = C.c_int
         _cache["join"] = L
     return _cache["join"]
-
-
-def load_oracle():
-    """Load the CPU oracle (test infrastructure; only tests / smoke / bench baselines call this)."""
-    if "oracle" not in _cache:
-        if not os.path.exists(LIB_ORACLE):
-            raise RuntimeError(f"{LIB_ORACLE} is missing — run `make -C oracle`")
-        L = C.CDLL(LIB_ORACLE)
-        L.oracle_join.argtypes = [C.POINTER(EjbParams), C.POINTER(EjbInput), C.c_int, C.POINTER(OracleResult)]
-        L.oracle_join.restype = C.c_int
-        L.oracle_result_free.argtypes = [C.POINTER(OracleResult)]
-        L.oracle_result_free.restype = None
-        L.oracle_sr_entry.argtypes = [C.c_int, C.c_int, _f64p, _f64p]
-        L.oracle_sr_entry.restype = None
-        L.oracle_p1.argtypes = [C.c_int64, C.c_int64, C.c_int64, _f64p]
-        L.oracle_p1.restype = C.c_int
-        L.oracle_dd_ops.argtypes = [C.c_double] * 4 + [_f64p]
-        L.oracle_dd_ops.restype = None
-        L.oracle_equiv_replay.argtypes = [C.c_int32, _i32p, _i32p, C.c_int64, _i32p, _i32p, _i32p]
-        L.oracle_equiv_replay.restype = None
-        _cache["oracle"] = L
-    return _cache["oracle"]

@@ -101,6 +101,7 @@ struct ejb_ctx {
     unsigned long long forest_cap = 0;
     ejb_stats stats;
 
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> s2a_events;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     cudaEvent_t ev() {
@@ -293,7 +294,12 @@ int run_stage2(ejb_ctx* c, const uint2* cand, const uint32_t* cand_slot, const u
     CK(zero_counter(c, offsetof(Counters, n_slow)));
     CK(zero_counter(c, offsetof(Counters, n_surv)));
     CK(zero_counter(c, offsetof(Counters, n_newkeys)));
+    cudaEvent_t ea = c->ev(), eb = c->ev();
+    CK(cudaEventRecord(ea, c->stream));
     k_stage2a<<<grid, 256, 0, c->stream>>>(X, cand, cand_slot, n_cand_dev, c->cand_cap);
+    CK(cudaEventRecord(eb, c->stream));
+    c->s2a_events.push_back({ea, eb});
+    c->stats.stage2a_launches++;
     k_stage2_slow<<<grid, 256, 0, c->stream>>>(X, CTR_FIELD(n_slow));
     k_p1<<<grid, 256, 0, c->stream>>>(X.p1, c->d_sr.as<dd_t>(), CTR_FIELD(n_newkeys));
     k_stage2b<<<grid, 256, 0, c->stream>>>(X, CTR_FIELD(n_surv), c->d_pass.as<unsigned long long>(), c->cand_cap, c->d_tuples.as<EdgeTuple>());
@@ -316,6 +322,12 @@ int p1_cache_clear(ejb_ctx* c) {
 extern "C" {
 
 int ejb_abi_version(void) { return EJB_ABI_VERSION; }
+void ejb_abi_sizes(int64_t out[4]) {
+    out[0] = sizeof(ejb_params);
+    out[1] = sizeof(ejb_input);
+    out[2] = sizeof(ejb_stats);
+    out[3] = sizeof(ejb_result);
+}
 
 void ejb_params_default(ejb_params* p, int is_bcr) {
     memset(p, 0, sizeof(*p));
@@ -553,6 +565,7 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
             case 6: launch_stage1_w<6>(c, nctas[6], dt, nt); break;
         }
         c->stats.kernel_launches++;
+        c->stats.stage1_launches++;
         off += tasks[w].size();
     }
     CK(cudaGetLastError());
@@ -571,7 +584,6 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
     if (rc) return rc;
     const Counters& h = *c->h_ctr;
     if (h.overflow || h.n_cand > c->cand_cap || h.n_surv > c->cand_cap || h.n_pass > c->cand_cap || h.n_slow > c->cand_cap) {
-        c->ev_used -= 4;
         return 1;
     }
     if (h.n_newkeys > c->p1_cap / 2) return fail(c, EJB_ERR_OOM, "p1 cache overflow (%llu new keys in one round)", h.n_newkeys);
@@ -649,6 +661,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
     const double t_wall0 = now_ms();
     memset(&c->stats, 0, sizeof(c->stats));
     c->ev_used = 0;
+    c->s2a_events.clear();
     const DevIn& din = c->din;
     const int64_t N = din.n_rows;
     cudaStream_t st = c->stream;
@@ -990,6 +1003,9 @@ extern "C" int ejb_run(ejb_ctx* c) {
     cudaEventElapsedTime(&ms, ev_start, ev_packed); c->stats.ms_pack = ms;
     cudaEventElapsedTime(&ms, ev_rounds, ev_end); c->stats.ms_finalize = ms;
     cudaEventElapsedTime(&ms, ev_start, ev_end); c->stats.ms_device_total = ms;
+    for (auto& pe : c->s2a_events) {
+        cudaEventElapsedTime(&ms, pe.first, pe.second); c->stats.ms_stage2a += ms;
+    }
     for (auto& t : times) {
         cudaEventElapsedTime(&ms, t.e0, t.e1); c->stats.ms_stage1 += ms;
         cudaEventElapsedTime(&ms, t.e1, t.e2); c->stats.ms_stage2 += ms;

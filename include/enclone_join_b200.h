@@ -184,6 +184,8 @@ typedef struct ejb_stats {
     int64_t kernel_launches;    /* CUDA kernels launched by this join                             */
     int64_t h2d_bytes, d2h_bytes;
     double ms_h2d, ms_pack, ms_stage1, ms_stage2, ms_forest, ms_finalize, ms_d2h, ms_replay;
+    double ms_stage2a;          /* k_stage2a alone (inside ms_stage2), CUDA events on the launching stream */
+    int64_t stage1_launches, stage2a_launches;
     double ms_device_total;     /* pack .. finalize, CUDA events                                  */
     double ms_total;            /* wall clock of the whole call                                   */
 } ejb_stats;
@@ -274,6 +276,9 @@ int ejb_equiv_replay(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64
                      const int32_t* row_exact, int32_t* x, int32_t* y, int32_t* z, int32_t* labels);
 
 int ejb_abi_version(void);
+/* sizeof(ejb_params), sizeof(ejb_input), sizeof(ejb_stats), sizeof(ejb_result) as the library was
+ * compiled — lets a binding verify its struct mirrors.                                          */
+void ejb_abi_sizes(int64_t out[4]);
 
 #ifdef __cplusplus
 }

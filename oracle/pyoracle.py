@@ -9,7 +9,72 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from enclone_ranger_b200._abi import OracleResult, load_oracle  # noqa: E402
+from enclone_ranger_b200._abi import EjbInput, EjbParams  # noqa: E402  (struct mirrors of the shared C header only)
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+LIB_ORACLE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liboracle.so")
+_cache = {}
+
+
+class OracleResult(C.Structure):
+    _fields_ = [
+        ("n_edges", C.c_int64),
+        ("edge_k1", _i32p),
+        ("edge_k2", _i32p),
+        ("edge_cd", _i32p),
+        ("edge_nrefs", _i32p),
+        ("edge_shares", _i32p),
+        ("edge_indeps", _i32p),
+        ("edge_k", _i32p),
+        ("edge_d", _i32p),
+        ("edge_n", _i32p),
+        ("edge_p1", _f64p),
+        ("edge_mult", _f64p),
+        ("edge_score", _f64p),
+        ("edge_err", _u8p),
+        ("n_rows", C.c_int64),
+        ("eq_x", _i32p),
+        ("eq_y", _i32p),
+        ("eq_z", _i32p),
+        ("labels", _i32p),
+        ("n_buckets", C.c_int64),
+        ("pairs_lens", C.c_int64),
+        ("pairs_scored", C.c_int64),
+        ("join_one_calls", C.c_int64),
+        ("pot_found", C.c_int64),
+        ("two_cell_deleted", C.c_int64),
+        ("joins", C.c_int64),
+        ("errors", C.c_int64),
+        ("seconds_join", C.c_double),
+        ("threads", C.c_int32),
+        ("error", C.c_char * 256),
+    ]
+
+
+
+def load_oracle():
+    """Load the CPU oracle (test infrastructure; only tests / smoke / bench baselines call this)."""
+    if "oracle" not in _cache:
+        if not os.path.exists(LIB_ORACLE):
+            raise RuntimeError(f"{LIB_ORACLE} is missing — run `make -C oracle`")
+        L = C.CDLL(LIB_ORACLE)
+        L.oracle_join.argtypes = [C.POINTER(EjbParams), C.POINTER(EjbInput), C.c_int, C.POINTER(OracleResult)]
+        L.oracle_join.restype = C.c_int
+        L.oracle_result_free.argtypes = [C.POINTER(OracleResult)]
+        L.oracle_result_free.restype = None
+        L.oracle_sr_entry.argtypes = [C.c_int, C.c_int, _f64p, _f64p]
+        L.oracle_sr_entry.restype = None
+        L.oracle_p1.argtypes = [C.c_int64, C.c_int64, C.c_int64, _f64p]
+        L.oracle_p1.restype = C.c_int
+        L.oracle_dd_ops.argtypes = [C.c_double] * 4 + [_f64p]
+        L.oracle_dd_ops.restype = None
+        L.oracle_equiv_replay.argtypes = [C.c_int32, _i32p, _i32p, C.c_int64, _i32p, _i32p, _i32p]
+        L.oracle_equiv_replay.restype = None
+        _cache["oracle"] = L
+    return _cache["oracle"]
+
 
 
 def _np(ptr, n, dt):

@@ -1,0 +1,159 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Integer / index results bit-exact; fp64 p1 / mult / score bit-exact as well (=> within 1e-12 relative)."""
+import numpy as np
+import pytest
+
+import cases
+import enclone_ranger_b200 as E
+from enclone_ranger_b200 import _abi
+from oracle import pyoracle
+from util import assert_same_result, load_golden
+
+pytestmark = pytest.mark.gpu
+CASES = cases.all_cases()
+
+
+@pytest.mark.parametrize("name,params,inp,expected", CASES, ids=[c[0] for c in CASES])
+def test_micro_case_matches_oracle(gpu_ctx, name, params, inp, expected):
+    want = pyoracle.run(params, inp.c_ptr(), threads=1)
+    got = gpu_ctx.join(params, inp)
+    assert_same_result(got, want, name)
+    if expected is not None:
+        assert list(zip(got.edge_k1.tolist(), got.edge_k2.tolist())) == expected
+
+
+@pytest.mark.parametrize("name", ["hs_bcr_vdjrefs7.npz", "synth_bcr_2k.npz", "synth_tcr_20k.npz"])
+def test_golden_fixture(gpu_ctx, name):
+    inp, want, p = load_golden(name)
+    assert_same_result(gpu_ctx.join(p, inp), want, name)
+
+
+@pytest.mark.parametrize("config,cells,seed", [(0, 10000, None), (0, 30000, 3), (1, 40000, None), (2, 150000, None), (3, 30000, None)])
+def test_synthetic_config_matches_oracle(gpu_ctx, config, cells, seed):
+    rep = E.generate(config, n_cells=cells, seed=seed)
+    p = E.default_params(bool(rep.config.is_bcr))
+    want = pyoracle.run(p, rep.c_ptr, threads=0)
+    got = gpu_ctx.join(p, rep)
+    assert_same_result(got, want, f"config {config}")
+    assert got.stats["pairs_scored"] == want["pairs_scored"] and got.stats["pairs_lens"] == want["pairs_lens"]
+    assert got.stats["n_buckets"] == want["n_buckets"] and got.stats["two_cell_deleted"] == want["two_cell_deleted"]
+    assert got.stats["errors"] == want["errors"] and got.stats["joins"] == want["joins"]
+    # the device labels (union-find) agree with the replayed EquivRel
+    assert np.array_equal(got.labels, want["labels"])
+
+
+def test_tiny_work_buffers_force_round_splitting():
+    """A candidate buffer far smaller than one round's candidates: the scheduler must split rounds / row-block
+    groups and still produce the identical forest (the order-dependent part of join_core)."""
+    rep = E.generate(1, n_cells=20000, seed=8)
+    p = E.default_params(True)
+    want = pyoracle.run(p, rep.c_ptr, threads=0)
+    small = E.JoinContext(cand_cap=1 << 15, pair_budget=1 << 18)
+    got = small.join(p, rep)
+    assert got.stats["rounds"] > 20
+    assert_same_result(got, want, "small buffers")
+    small.close()
+
+
+def test_run_is_deterministic_and_idempotent(gpu_ctx):
+    rep = E.generate(3, n_cells=20000, seed=2)
+    p = E.default_params(True)
+    a = gpu_ctx.join(p, rep)
+    b = gpu_ctx.join(p, rep)
+    for f in ("edge_k1", "edge_k2", "edge_score", "labels", "eq_x", "eq_y", "eq_z"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    gpu_ctx.upload(p, rep)
+    gpu_ctx.run()
+    gpu_ctx.run()
+    c = gpu_ctx.download()
+    assert np.array_equal(a.edge_k1, c.edge_k1) and np.array_equal(a.edge_score, c.edge_score)
+
+
+def test_p1_kernel_bit_exact(gpu_ctx):
+    rng = np.random.default_rng(0)
+    k = rng.integers(0, 400, 300)
+    d = (rng.random(300) * (k + 1)).astype(np.int64)
+    n = rng.integers(1500, 3000, 300)
+    k[:4] = [0, 5, 30, 3000]; d[:4] = [0, 0, 3, 40]; n[:4] = [2000, 2000, 2500, 2445]
+    got = gpu_ctx.p1_batch(k, d, n)
+    want = np.array([pyoracle.p1(int(a), int(b), int(c)) for a, b, c in zip(k, d, n)])
+    assert np.array_equal(got, want)
+    assert f"{got[2]:.7f}" == "0.0005953"   # stirling_numbers/src/lib.rs:315
+
+
+def test_sharded_ranks_union_to_the_full_result():
+    """Two 'ranks' (run back to back on one GPU) own disjoint sub-buckets; their edge lists merge to the
+    single-GPU / oracle result."""
+    from enclone_ranger_b200.multi import merge_edge_parts, EDGE_FIELDS
+    rep = E.generate(1, n_cells=30000, seed=17)
+    p = E.default_params(True)
+    want = pyoracle.run(p, rep.c_ptr, threads=0)
+    parts = []
+    for r in range(3):
+        c = E.JoinContext(rank=r, world=3)
+        res = c.join(p, rep)
+        parts.append({f: getattr(res, f) for f in EDGE_FIELDS})
+        c.close()
+    assert all(len(x["edge_k1"]) > 0 for x in parts)
+    merged = merge_edge_parts(parts)
+    assert_same_result(merged, {k: want[k] for k in want if k.startswith("edge_")}, "sharded")
+    eq, lab = E.equiv_replay(rep.c.n_rows, merged["edge_k1"], merged["edge_k2"], rep.to_join_input().a["row_exact"])
+    assert np.array_equal(eq.x, want["eq_x"]) and np.array_equal(eq.y, want["eq_y"]) and np.array_equal(lab, want["labels"])
+
+
+def test_properties_at_scale(gpu_ctx):
+    """Size-independent properties where the oracle is too slow: sorted forest, one bucket per edge,
+    labels == connected components of edges + clonotype_id merge, idempotent under re-run."""
+    rep = E.generate(1, n_cells=300000, seed=1)
+    p = E.default_params(True)
+    res = gpu_ctx.join(p, rep)
+    k1, k2 = res.edge_k1.astype(np.int64), res.edge_k2.astype(np.int64)
+    key = k1 << 32 | k2
+    assert np.all(key[1:] > key[:-1]) and np.all(k1 < k2)
+    inp = rep.to_join_input()
+    lens = inp.a["row_len"].reshape(-1, 2)
+    assert np.array_equal(lens[k1], lens[k2])
+    c3 = inp.a["row_cdr3_len"].reshape(-1, 2)
+    assert np.array_equal(c3[k1], c3[k2])
+    eq, lab = E.equiv_replay(inp.n_rows, res.edge_k1, res.edge_k2, inp.a["row_exact"])
+    assert np.array_equal(lab, res.labels) and np.array_equal(eq.y, res.eq_y)
+    assert eq.norbits() == len(np.unique(res.labels))
+    assert res.stats["forest_edges"] - res.stats["two_cell_deleted"] == len(k1)
+    # every accepted score obeys the reference's threshold logic (join_one.rs:710-715)
+    d = res.edge_d
+    assert np.all((res.edge_score <= 100000.0) | (d >= 15) | (res.edge_cd <= 100))
+
+
+def test_error_behaviour(gpu_ctx):
+    _, p, inp, _ = next(c for c in CASES if c[0] == "base_join")
+    with pytest.raises(E.JoinError) as ei:
+        gpu_ctx.join(E.default_params(True, unsupported_modes=_abi.EJB_MODE_BASIC), inp)
+    assert ei.value.code == _abi.EJB_ERR_UNSUPPORTED
+    bad = E.JoinInput(**{**inp.a, "row_tig_off": inp.a["row_tig_off"] + 10 ** 9})
+    with pytest.raises(E.JoinError) as ei:
+        gpu_ctx.join(p, bad)
+    assert ei.value.code == _abi.EJB_ERR_INVALID
+    # the context stays usable after an error
+    assert len(gpu_ctx.join(p, inp).edge_k1) == 1
+
+
+def test_stirling_range_error(gpu_ctx):
+    w = cases.World()
+    w.vh = cases.rand_seq(w.rng, 2400); w.VH = 2400
+    w.seg_vh = w.b.seg(w.vh); w.ref_vh = w.b.ref(w.vh, 77)
+    h0, l0 = w.heavy(), w.light()
+    shared = list(range(10, 2300, 2))[:1100]
+    w.member(cases.mutate(h0, shared + [3]), l0, feats=False); w.member(cases.mutate(h0, shared + [7]), l0, feats=False)
+    with pytest.raises(E.JoinError) as ei:
+        gpu_ctx.join(E.default_params(True), w.build())
+    assert ei.value.code == _abi.EJB_ERR_RANGE
+
+
+def test_empty_and_ragged_inputs(gpu_ctx):
+    p = E.default_params(True)
+    empty = E.JoinInput()
+    r = gpu_ctx.join(p, empty)
+    assert len(r.edge_k1) == 0 and len(r.labels) == 0
+    _, p, inp, _ = next(c for c in CASES if c[0] == "onesies_never_join")
+    r = gpu_ctx.join(p, inp)
+    assert len(r.edge_k1) == 0 and r.labels.tolist() == [0, 1]
