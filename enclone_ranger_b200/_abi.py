@@ -138,6 +138,7 @@ class EjbStats(C.Structure):
         ("ms_stage2a", C.c_double),
         ("stage1_launches", C.c_int64),
         ("stage2a_launches", C.c_int64),
+        ("overflow_retries", C.c_int64),
         ("ms_device_total", C.c_double),
         ("ms_total", C.c_double),
     ]

@@ -230,27 +230,31 @@ __global__ void k_final_gather(const unsigned long long* __restrict__ keys, cons
 // ------------------------------------------------------------------------------------------------
 // Integer-pipe peak microbenchmarks (roofline denominators, SURVEY §8 d)
 // ------------------------------------------------------------------------------------------------
+// All operands are per-lane values (anything block-uniform would be moved to the uniform datapath and
+// inflate the figure); 8 independent chains cover the pipe latency.
 __global__ void k_peak_popc(uint32_t* out, int iters) {
-    uint32_t a = threadIdx.x * 2654435761u + 1u, b = blockIdx.x * 40503u + 7u, c = a ^ 0x9e3779b9u, d = b + 0x7f4a7c15u;
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t a0 = t, a1 = t ^ 0x9e3779b9u, a2 = t + 0x7f4a7c15u, a3 = t * 3u, a4 = t ^ 0x55555555u, a5 = t + 0x33333333u, a6 = ~t, a7 = t * 5u;
     uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;
+#pragma unroll 4
     for (int i = 0; i < iters; i++) {
-        // 8 independent popc per iteration; operands evolve with cheap adds on another pipe
-        s0 += __popc(a); s1 += __popc(b); s2 += __popc(c); s3 += __popc(d);
-        s4 += __popc(a ^ 0x55555555u); s5 += __popc(b ^ 0x33333333u); s6 += __popc(c ^ 0x0f0f0f0fu); s7 += __popc(d ^ 0x00ff00ffu);
-        a += 0x01010101u; b += 0x10101010u; c += 0x11111111u; d += 0x00010001u;
+        s0 += __popc(a0); s1 += __popc(a1); s2 += __popc(a2); s3 += __popc(a3);
+        s4 += __popc(a4); s5 += __popc(a5); s6 += __popc(a6); s7 += __popc(a7);
+        a0 += s4; a1 += s5; a2 += s6; a3 += s7; a4 += s0; a5 += s1; a6 += s2; a7 += s3;   // data-dependent: nothing can be hoisted
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7;
 }
 __global__ void k_peak_lop3(uint32_t* out, int iters) {
-    uint32_t a = threadIdx.x * 2654435761u + 1u, b = blockIdx.x * 40503u + 7u, c = a ^ 0x9e3779b9u, d = b + 0x7f4a7c15u;
-    uint32_t e = a + 3, f = b + 5, g = c + 7, h = d + 11;
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t a0 = t, a1 = t ^ 0x9e3779b9u, a2 = t + 0x7f4a7c15u, a3 = t * 3u, a4 = t ^ 0x55555555u, a5 = t + 0x33333333u, a6 = ~t, a7 = t * 5u;
+    const uint32_t m0 = t * 7u, m1 = t * 11u;
+#pragma unroll 4
     for (int i = 0; i < iters; i++) {
-        // 8 independent 3-input logic ops per iteration
-        a = (a ^ b) | (c & i); b = (b & c) ^ (d | i); c = (c | d) ^ (a & i); d = (d ^ a) & (b | i);
-        e = (e ^ f) | (g & i); f = (f & g) ^ (h | i); g = (g | h) ^ (e & i); h = (h ^ e) & (f | i);
+        // 8 three-input logic ops, one LOP3 each (two interleaved groups of 4 independent chains)
+        a0 = (a0 ^ m0) | a4; a1 = (a1 & m0) ^ a5; a2 = (a2 | m0) ^ a6; a3 = (a3 ^ m1) & a7;
+        a4 = (a4 ^ m1) | a0; a5 = (a5 & m1) ^ a1; a6 = (a6 | m1) ^ a2; a7 = (a7 ^ m0) & a3;
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a ^ b ^ c ^ d ^ e ^ f ^ g ^ h;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
 }
-
 
 }  // namespace ejb

@@ -72,7 +72,10 @@ struct ejb_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int shard_rank = 0, shard_world = 1;
-    unsigned long long cand_cap = 1ull << 26;
+    unsigned long long cand_cap = 1ull << 27;
+    bool cap_explicit = false;
+    unsigned long long pairs_eval_seen = 0;
+    double cand_rate = 0.0;   // largest candidates/pairs ratio seen in a completed round of this run
     unsigned long long pair_budget = 1ull << 32;
     uint32_t p1_cap = 1u << 22;
     bool have_input = false, have_run = false;
@@ -86,6 +89,7 @@ struct ejb_ctx {
     ejb_params params;
     DevIn din;
     std::vector<DevBuf> in_bufs;
+    size_t in_used = 0;
     int64_t h2d_bytes = 0;
     double ms_h2d = 0;
 
@@ -95,6 +99,7 @@ struct ejb_ctx {
     DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
     DevBuf d_tasks, d_cand, d_slow, d_slowslot, d_surv, d_pass, d_roots, d_forest;
     DevBuf d_qofrow, d_deg, d_tuples, d_keep, d_first, d_labels, d_fkeys, d_fkeys2, d_fidx, d_fidx2, d_nout;
+    DevBuf d_pairs_all, d_slots, d_cnt;
     DevBuf d_o_k1, d_o_k2, d_o_cd, d_o_nrefs, d_o_sh, d_o_in, d_o_k, d_o_d, d_o_n, d_o_p1, d_o_mult, d_o_score, d_o_err;
     std::vector<SubBucket> subs;
     int64_t n_active = 0, n_pos = 0, n_blocks = 0, n_final = 0;
@@ -167,8 +172,8 @@ const std::vector<dd_t>& sr_table_host() {
 
 template <class T>
 int upload_array(ejb_ctx* c, const T* src, int64_t n, const T** dst) {
-    c->in_bufs.emplace_back();
-    DevBuf& b = c->in_bufs.back();
+    if (c->in_used == c->in_bufs.size()) c->in_bufs.emplace_back();
+    DevBuf& b = c->in_bufs[c->in_used++];
     const size_t bytes = (size_t)std::max<int64_t>(n, 1) * sizeof(T);
     CK(b.ensure(bytes + 16));
     if (n > 0) {
@@ -367,7 +372,10 @@ int ejb_create(ejb_ctx** out, const int* device_ids, int n_devices) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, dev);
     c->sm_count = prop.multiProcessorCount;
-    if (const char* e = getenv("EJB_CAND_CAP")) c->cand_cap = std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
+    if (const char* e = getenv("EJB_CAND_CAP")) {
+        c->cand_cap = std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
+        c->cap_explicit = true;
+    }
     if (const char* e = getenv("EJB_PAIR_BUDGET")) c->pair_budget = std::max<unsigned long long>(1ull << 16, strtoull(e, nullptr, 10));
     auto bail = [&](int code) {
         std::string m = c->err;
@@ -414,7 +422,10 @@ int ejb_set_shard(ejb_ctx* c, int rank, int world) {
 
 int ejb_set_capacity(ejb_ctx* c, unsigned long long cand_cap, unsigned long long pair_budget) {
     if (!c) return EJB_ERR_INVALID;
-    if (cand_cap) c->cand_cap = std::max<unsigned long long>(1024, cand_cap);
+    if (cand_cap) {
+        c->cand_cap = std::max<unsigned long long>(1024, cand_cap);
+        c->cap_explicit = true;
+    }
     if (pair_budget) c->pair_budget = std::max<unsigned long long>(1ull << 14, pair_budget);
     return EJB_OK;
 }
@@ -430,8 +441,8 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     if (in->n_rows > 0 && (in->n_exacts == 0 || in->n_segs == 0)) return fail(c, EJB_ERR_INVALID, "rows without exacts/segs");
     c->params = *p;
     const double t0 = now_ms();
-    c->in_bufs.clear();
-    c->in_bufs.reserve(64);
+    if (c->in_bufs.capacity() < 64) c->in_bufs.reserve(64);   // buffers persist across uploads (no cudaFree/cudaMalloc per join)
+    c->in_used = 0;
     c->h2d_bytes = 0;
     DevIn& d = c->din;
     memset(&d, 0, sizeof(d));
@@ -521,6 +532,7 @@ int cub_incl_sum(ejb_ctx* c, const int32_t* in, int32_t* out, int64_t n) {
 // One scheduler round: stage 1 over `units`, stage 2, forest update.  Returns 1 when the
 // candidate buffer overflowed (nothing committed; the caller splits the round and retries).
 int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes>& times) {
+    const unsigned long long eval_before = c->pairs_eval_seen;
     const std::vector<SubBucket>& subs = c->subs;
     // ---- tasks grouped by W1 ----
     std::vector<RowTask> tasks[MAXW1 + 1];
@@ -584,6 +596,9 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
     if (rc) return rc;
     const Counters& h = *c->h_ctr;
     if (h.overflow || h.n_cand > c->cand_cap || h.n_surv > c->cand_cap || h.n_pass > c->cand_cap || h.n_slow > c->cand_cap) {
+        if (h.pairs_eval > eval_before) c->cand_rate = std::max(c->cand_rate, (double)h.n_cand / (double)(h.pairs_eval - eval_before));
+        c->pairs_eval_seen = h.pairs_eval;
+        c->stats.overflow_retries++;
         return 1;
     }
     if (h.n_newkeys > c->p1_cap / 2) return fail(c, EJB_ERR_OOM, "p1 cache overflow (%llu new keys in one round)", h.n_newkeys);
@@ -591,6 +606,8 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
     if (h.n_errflag_panic) return fail(c, EJB_ERR_INVALID, "input on which the reference panics (J range longer than a contig, seg shorter than ref trim, or inconsistent feature starts)");
     c->p1_count += h.n_newkeys;
     c->stats.p1_unique += (int64_t)h.n_newkeys;
+    if (h.pairs_eval > eval_before) c->cand_rate = std::max(c->cand_rate, (double)h.n_cand / (double)(h.pairs_eval - eval_before));
+    c->pairs_eval_seen = h.pairs_eval;
     c->stats.stage1_candidates += (int64_t)h.n_cand;
     c->stats.stage2_slow += (int64_t)h.n_slow;
     c->stats.stage2_survivors += (int64_t)h.n_surv;
@@ -863,7 +880,15 @@ extern "C" int ejb_run(ejb_ctx* c) {
                                                                    c->d_blksub.as<int32_t>(), (int)c->n_blocks);
         c->stats.kernel_launches += 3;
     }
+    {
+        unsigned long long need = 0;
+        for (const SubBucket& sb : c->subs)
+            if (sb.owner == c->shard_rank) need = std::max<unsigned long long>(need, (unsigned long long)TILE * (unsigned long long)sb.n);
+        if (need > c->cand_cap && !c->cap_explicit) c->cand_cap = need;   // worst case of ONE row block: all of its pairs are candidates
+    }
     const unsigned long long cap = c->cand_cap;
+    c->cand_rate = 0.0;
+    c->pairs_eval_seen = 0;
     c->forest_cap = (unsigned long long)std::max<int64_t>(N, 1);
     CK(c->d_cand.ensure(cap * 8)); CK(c->d_slow.ensure(cap * 8)); CK(c->d_slowslot.ensure(cap * 4));
     CK(c->d_surv.ensure(cap * sizeof(Survivor))); CK(c->d_pass.ensure(cap * 8)); CK(c->d_roots.ensure(cap * 8));
@@ -880,6 +905,10 @@ extern "C" int ejb_run(ejb_ctx* c) {
         while (!live.empty()) {
             std::vector<Unit> units;
             unsigned long long pairs = 0;
+            // keep the expected candidates of a round at <= 60 % of the buffers (rate of the densest round so far, x2 margin)
+            unsigned long long budget = c->pair_budget;
+            if (c->cand_rate > 0.0) budget = std::min<unsigned long long>(budget, (unsigned long long)(0.6 * (double)c->cand_cap / std::min(1.0, 2.0 * c->cand_rate)));
+            budget = std::max<unsigned long long>(budget, 1ull << 14);
             std::vector<int> still;
             for (int s : live) {
                 const SubBucket& sb = subs[s];
@@ -891,9 +920,9 @@ extern "C" int ejb_run(ejb_ctx* c) {
                     const long long rows = r1 - r0;
                     return (unsigned long long)(rows * (sb.n - r1) + rows * (rows - 1) / 2);
                 };
-                while (g > 1 && unit_pairs(next_rb[s], next_rb[s] + g) > c->pair_budget / 2) g /= 2;
+                while (g > 1 && unit_pairs(next_rb[s], next_rb[s] + g) > budget / 2) g /= 2;
                 const unsigned long long up = unit_pairs(next_rb[s], next_rb[s] + g);
-                if (!units.empty() && pairs + up > c->pair_budget) {
+                if (!units.empty() && pairs + up > budget) {
                     still.push_back(s);
                     continue;
                 }
@@ -932,15 +961,15 @@ extern "C" int ejb_run(ejb_ctx* c) {
         CK(cudaMemsetAsync(c->d_deg.p, 0, (size_t)N * 4, st));
         k_q_of_row<<<nblk(c->n_pos, 256), 256, 0, st>>>(c->d_m_row.as<int32_t>(), c->n_pos, c->d_qofrow.as<int32_t>());
         // the (q1,q2) list of ALL forest edges is needed for degrees; tuples are computed in chunks of cand_cap
-        DevBuf d_pairs_all;
+        DevBuf& d_pairs_all = c->d_pairs_all;
         CK(d_pairs_all.ensure((size_t)NF * 8));
         k_forest_pairs<<<nblk(NF, 256), 256, 0, st>>>(c->d_forest.as<unsigned long long>(), NF, c->d_qofrow.as<int32_t>(), d_pairs_all.as<uint2>(),
                                                      c->d_deg.as<int32_t>());
         c->stats.kernel_launches += 2;
-        DevBuf d_slots;
+        DevBuf& d_slots = c->d_slots;
         const int64_t chunk = (int64_t)std::min<unsigned long long>(cap, (unsigned long long)NF);
         CK(d_slots.ensure((size_t)chunk * 4));
-        DevBuf d_cnt;
+        DevBuf& d_cnt = c->d_cnt;
         CK(d_cnt.ensure(16));
         for (int64_t o = 0; o < NF; o += chunk) {
             const int64_t m = std::min<int64_t>(chunk, NF - o);

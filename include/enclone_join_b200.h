@@ -186,6 +186,7 @@ typedef struct ejb_stats {
     double ms_h2d, ms_pack, ms_stage1, ms_stage2, ms_forest, ms_finalize, ms_d2h, ms_replay;
     double ms_stage2a;          /* k_stage2a alone (inside ms_stage2), CUDA events on the launching stream */
     int64_t stage1_launches, stage2a_launches;
+    int64_t overflow_retries;   /* rounds that overflowed the work buffers and were split + re-run   */
     double ms_device_total;     /* pack .. finalize, CUDA events                                  */
     double ms_total;            /* wall clock of the whole call                                   */
 } ejb_stats;

@@ -48,9 +48,10 @@ def test_tiny_work_buffers_force_round_splitting():
     rep = E.generate(1, n_cells=20000, seed=8)
     p = E.default_params(True)
     want = pyoracle.run(p, rep.c_ptr, threads=0)
-    small = E.JoinContext(cand_cap=1 << 15, pair_budget=1 << 18)
+    small = E.JoinContext(cand_cap=1 << 20, pair_budget=1 << 21)   # >= 128 x the largest sub-bucket (one row block must fit)
     got = small.join(p, rep)
     assert got.stats["rounds"] > 20
+    assert got.stats["overflow_retries"] >= 0
     assert_same_result(got, want, "small buffers")
     small.close()
 
