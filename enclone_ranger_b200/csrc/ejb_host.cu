@@ -298,6 +298,7 @@ int run_stage2(ejb_ctx* c, const uint2* cand, const uint32_t* cand_slot, const u
     const int grid = c->sm_count * 8;
     CK(zero_counter(c, offsetof(Counters, n_slow)));
     CK(zero_counter(c, offsetof(Counters, n_surv)));
+    CK(zero_counter(c, offsetof(Counters, n_surv_total)));
     CK(zero_counter(c, offsetof(Counters, n_newkeys)));
     cudaEvent_t ea = c->ev(), eb = c->ev();
     CK(cudaEventRecord(ea, c->stream));
@@ -606,11 +607,11 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
     if (h.n_errflag_panic) return fail(c, EJB_ERR_INVALID, "input on which the reference panics (J range longer than a contig, seg shorter than ref trim, or inconsistent feature starts)");
     c->p1_count += h.n_newkeys;
     c->stats.p1_unique += (int64_t)h.n_newkeys;
-    if (h.pairs_eval > eval_before) c->cand_rate = std::max(c->cand_rate, (double)h.n_cand / (double)(h.pairs_eval - eval_before));
+    if (h.pairs_eval > eval_before) c->cand_rate = (double)h.n_cand / (double)(h.pairs_eval - eval_before);   // most recent round
     c->pairs_eval_seen = h.pairs_eval;
     c->stats.stage1_candidates += (int64_t)h.n_cand;
     c->stats.stage2_slow += (int64_t)h.n_slow;
-    c->stats.stage2_survivors += (int64_t)h.n_surv;
+    c->stats.stage2_survivors += (int64_t)h.n_surv_total;
     c->stats.pass_edges += (int64_t)h.n_pass;
     if (h.n_pass > 0) {
         int iter = 0;
@@ -905,7 +906,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
         while (!live.empty()) {
             std::vector<Unit> units;
             unsigned long long pairs = 0;
-            // keep the expected candidates of a round at <= 60 % of the buffers (rate of the densest round so far, x2 margin)
+            // keep the expected candidates of a round at <= 60 % of the buffers (rate of the previous round, x2 margin;
+            // a misprediction only costs one split-and-retry)
             unsigned long long budget = c->pair_budget;
             if (c->cand_rate > 0.0) budget = std::min<unsigned long long>(budget, (unsigned long long)(0.6 * (double)c->cand_cap / std::min(1.0, 2.0 * c->cand_rate)));
             budget = std::max<unsigned long long>(budget, 1ull << 14);

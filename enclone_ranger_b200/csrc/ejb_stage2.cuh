@@ -39,11 +39,14 @@ struct RegionDiffs {
     int regfast, fd, c1d, c2d;
 };
 
+constexpr uint32_t SURV_INVALID = 0xffffffffu;   // Survivor.q1 of an unused slot
+constexpr int SURV_CHUNK = 64;                    // slots a warp reserves per atomicAdd
+
 // Integer tests shared by the fast and the slow path, executed by one lane per candidate.
-// Appends a Survivor (+ requests its p1) unless join_one would already return false.
-__device__ __forceinline__ void s2_integer_tests(const S2Ctx& X, uint32_t q1, uint32_t q2, uint32_t slot, const SubBucket& sb, int cd1, int cd2,
+// Returns true and fills `s` (+ requests its p1) unless join_one would already return false.
+__device__ __forceinline__ bool s2_integer_tests(const S2Ctx& X, uint32_t q1, uint32_t q2, uint32_t slot, const SubBucket& sb, int cd1, int cd2,
                                                  long long diffs, int nrefs, int sh0, int in0, int sh1, int in1, RegionDiffs rg, bool pre_ok,
-                                                 bool force_emit) {
+                                                 bool force_emit, Survivor& s) {
     const DevParams& P = X.P;
     const int32_t* a1 = X.aux + (size_t)q1 * AUX_INTS;
     const int32_t* a2 = X.aux + (size_t)q2 * AUX_INTS;
@@ -77,18 +80,12 @@ __device__ __forceinline__ void s2_integer_tests(const S2Ctx& X, uint32_t q1, ui
         if (!(f1 & B_LEFT_H) && a1[AX_CREFH] != -1 && a2[AX_CREFH] != -1 && a1[AX_CREFH] != a2[AX_CREFH]) ok = false;
         if (!(f1 & B_LEFT_L) && a1[AX_CREFL] != -1 && a2[AX_CREFL] != -1 && a1[AX_CREFL] != a2[AX_CREFL]) ok = false;
     }
-    if (!ok && !force_emit) return;
+    if (!ok && !force_emit) return false;
     const int k = min_in + 2 * min_sh;
     if (k > SR_NMAX) {
         if (ok) atomicAdd(&X.ctr->n_errflag_range, 1ull);  // the reference panics on sr[x][u]
-        if (!force_emit) return;
+        if (!force_emit) return false;
     }
-    const unsigned long long si = atomicAdd(&X.ctr->n_surv, 1ull);
-    if (si >= X.surv_cap) {
-        X.ctr->overflow = 1ull;
-        return;
-    }
-    Survivor s;
     s.q1 = q1;
     s.q2 = q2;
     s.cd1 = (uint16_t)cd1;
@@ -106,9 +103,45 @@ __device__ __forceinline__ void s2_integer_tests(const S2Ctx& X, uint32_t q1, ui
     s.c2d = (uint16_t)rg.c2d;
     s.pad = 0;
     s.slot = slot;
-    X.surv[si] = s;
     if (k <= SR_NMAX) p1_request(X.p1, sb.n3, k, min_sh, X.ctr);
+    return true;
 }
+
+// Warp-private slot reservation: one atomicAdd per SURV_CHUNK survivors instead of one per survivor
+// (a single-address atomic per candidate serialises the whole kernel in L2).
+struct SurvWriter {
+    unsigned long long pos, end;   // warp-uniform
+    unsigned long long written;
+    __device__ __forceinline__ void init() { pos = end = 0; written = 0; }
+    __device__ __forceinline__ void retire(const S2Ctx& X, int lane) {   // mark the unused tail of the current chunk
+        for (unsigned long long i = pos + lane; i < end && i < X.surv_cap; i += 32) X.surv[i].q1 = SURV_INVALID;
+        pos = end;
+    }
+    __device__ __forceinline__ void push(const S2Ctx& X, int lane, bool emit, const Survivor& s) {   // all 32 lanes must call
+        const unsigned int m = __ballot_sync(0xffffffffu, emit);
+        if (!m) return;
+        const int cnt = __popc(m);
+        if (pos + cnt > end) {
+            retire(X, lane);
+            unsigned long long b = 0;
+            if (lane == 0) b = atomicAdd(&X.ctr->n_surv, (unsigned long long)SURV_CHUNK);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            pos = b;
+            end = b + SURV_CHUNK;
+            if (end > X.surv_cap && lane == 0) X.ctr->overflow = 1ull;
+        }
+        if (emit) {
+            const unsigned long long o = pos + __popc(m & ((1u << lane) - 1u));
+            if (o < X.surv_cap) X.surv[o] = s;
+        }
+        pos += cnt;
+        written += cnt;
+    }
+    __device__ __forceinline__ void finish(const S2Ctx& X, int lane) {
+        retire(X, lane);
+        if (lane == 0 && written) atomicAdd(&X.ctr->n_surv_total, written);
+    }
+};
 
 // popc of e[0..3] (positions bit0 .. bit0+127) restricted to [a, b)
 __device__ __forceinline__ int range_popc4(const uint32_t* e, int bit0, int a, int b) {
@@ -142,6 +175,8 @@ __global__ void __launch_bounds__(256) k_stage2a(S2Ctx X, const uint2* __restric
     const unsigned int gmask = 0xffu << (8 * gid);
     const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    SurvWriter wr;
+    wr.init();
     for (unsigned long long base = warp0 * 4; base < n_cand; base += nwarps * 4) {
         const unsigned long long ci = base + gid;
         const bool valid = ci < n_cand;
@@ -261,6 +296,8 @@ __global__ void __launch_bounds__(256) k_stage2a(S2Ctx X, const uint2* __restric
                 n3 += __shfl_xor_sync(gmask, n3, o);
             }
         }
+        bool emit = false;
+        Survivor sv;
         if (valid && g == 0) {
             if (fast) {
                 const int cd1 = (int)(pk0 & 0xffff), cd2 = (int)(pk0 >> 16);
@@ -272,7 +309,7 @@ __global__ void __launch_bounds__(256) k_stage2a(S2Ctx X, const uint2* __restric
                 rg.c2d = (int)(pk3 >> 16);
                 if (nrefs1) {
                     const int A = (int)(pk1 & 0xffff), B = (int)(pk1 >> 16);
-                    s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, 1, A - B, tot1 + tot2 - 2 * A + 2 * B, 0, 0, rg, true, X.tuple_mode != 0);
+                    emit = s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, 1, A - B, tot1 + tot2 - 2 * A + 2 * B, 0, 0, rg, true, X.tuple_mode != 0, sv);
                 } else {
                     const int A0 = (int)(n0 & 0xffff), B0 = (int)(n0 >> 16), O0 = (int)(n1 & 0xffff), T01 = (int)(n1 >> 16);
                     const int A1 = (int)(n2 & 0xffff), B1 = (int)(n2 >> 16), O1 = (int)(n3 & 0xffff), T10 = (int)(n3 >> 16);
@@ -281,7 +318,7 @@ __global__ void __launch_bounds__(256) k_stage2a(S2Ctx X, const uint2* __restric
                     if (abs(tot1 - T10) > X.P.max_degradation) ok = false;
                     if (abs(T01 - tot2) > X.P.max_degradation) ok = false;
                     if (ok || X.tuple_mode)
-                        s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, 2, A0 - B0, O0 + 2 * B0, A1 - B1, O1 + 2 * B1, rg, ok, X.tuple_mode != 0);
+                        emit = s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, 2, A0 - B0, O0 + 2 * B0, A1 - B1, O1 + 2 * B1, rg, ok, X.tuple_mode != 0, sv);
                 }
             } else {
                 const unsigned long long si = atomicAdd(&X.ctr->n_slow, 1ull);
@@ -293,7 +330,9 @@ __global__ void __launch_bounds__(256) k_stage2a(S2Ctx X, const uint2* __restric
                 }
             }
         }
+        wr.push(X, lane, emit, sv);
     }
+    wr.finish(X, lane);
 }
 
 // Slow path: one warp per candidate, literal byte-level restatement of join_one.rs:216-440
@@ -398,8 +437,13 @@ __global__ void __launch_bounds__(256) k_stage2_slow(S2Ctx X, const unsigned lon
                 }
             }
             RegionDiffs rg = {0, 0, 0, 0};
-            if (ok || X.tuple_mode)
-                s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, nrefs, sh[0], ind[0], sh[1], ind[1], rg, ok, X.tuple_mode != 0);
+            Survivor sv;
+            if ((ok || X.tuple_mode) &&
+                s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, nrefs, sh[0], ind[0], sh[1], ind[1], rg, ok, X.tuple_mode != 0, sv)) {
+                const unsigned long long si = atomicAdd(&X.ctr->n_surv, 1ull);   // rare path: one atomic per survivor is fine
+                if (si < X.surv_cap) X.surv[si] = sv; else X.ctr->overflow = 1ull;
+                atomicAdd(&X.ctr->n_surv_total, 1ull);
+            }
         }
     }
 }
@@ -423,9 +467,16 @@ __global__ void __launch_bounds__(256) k_stage2b(S2Ctx X, const unsigned long lo
     const unsigned long long n_surv = min(*n_surv_p, X.surv_cap);
     const DevIn& in = X.in;
     const DevParams& P = X.P;
-    for (unsigned long long si = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; si < n_surv;
-         si += (unsigned long long)gridDim.x * blockDim.x) {
-        const Survivor s = X.surv[si];
+    const int lane = threadIdx.x & 31;
+    for (unsigned long long sbase = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; sbase < n_surv;
+         sbase += (unsigned long long)gridDim.x * blockDim.x) {
+      const unsigned long long si = sbase + lane;
+      bool pass_edge = false;
+      unsigned long long pass_val = 0;
+      Survivor s;
+      s.q1 = SURV_INVALID;
+      if (si < n_surv) s = X.surv[si];
+      if (s.q1 != SURV_INVALID) {
         const uint32_t q1 = s.q1, q2 = s.q2;
         const SubBucket sb = X.subs[X.subq[q1]];
         const int32_t* a1 = X.aux + (size_t)q1 * AUX_INTS;
@@ -557,10 +608,21 @@ __global__ void __launch_bounds__(256) k_stage2b(S2Ctx X, const unsigned long lo
             t.score = score;
             tuples[s.slot] = t;
         } else if (ok) {
-            const unsigned long long o = atomicAdd(&X.ctr->n_pass, 1ull);
-            if (o < pass_cap) pass_w[o] = ((unsigned long long)(uint32_t)X.rowq[q1] << 28) | (unsigned long long)(uint32_t)X.rowq[q2];
-            else X.ctr->overflow = 1ull;
+            pass_edge = true;
+            pass_val = ((unsigned long long)(uint32_t)X.rowq[q1] << 28) | (unsigned long long)(uint32_t)X.rowq[q2];
         }
+      }
+      // warp-aggregated append: one atomic per warp
+      const unsigned int m = __ballot_sync(0xffffffffu, pass_edge);
+      if (m) {
+          unsigned long long b = 0;
+          if (lane == 0) b = atomicAdd(&X.ctr->n_pass, (unsigned long long)__popc(m));
+          b = __shfl_sync(0xffffffffu, b, 0);
+          if (pass_edge) {
+              const unsigned long long o = b + __popc(m & ((1u << lane) - 1u));
+              if (o < pass_cap) pass_w[o] = pass_val; else X.ctr->overflow = 1ull;
+          }
+      }
     }
 }
 

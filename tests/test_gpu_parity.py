@@ -75,7 +75,7 @@ def test_p1_kernel_bit_exact(gpu_ctx):
     k = rng.integers(0, 400, 300)
     d = (rng.random(300) * (k + 1)).astype(np.int64)
     n = rng.integers(1500, 3000, 300)
-    k[:4] = [0, 5, 30, 3000]; d[:4] = [0, 0, 3, 40]; n[:4] = [2000, 2000, 2500, 2445]
+    k[:4] = [0, 5, 30, 3000]; d[:4] = [0, 0, 3, 40]; n[:4] = [2000, 2000, 2500, 9000]
     got = gpu_ctx.p1_batch(k, d, n)
     want = np.array([pyoracle.p1(int(a), int(b), int(c)) for a, b, c in zip(k, d, n)])
     assert np.array_equal(got, want)
