@@ -299,6 +299,7 @@ int run_stage2(ejb_ctx* c, const uint2* cand, const uint32_t* cand_slot, const u
     CK(zero_counter(c, offsetof(Counters, n_slow)));
     CK(zero_counter(c, offsetof(Counters, n_surv)));
     CK(zero_counter(c, offsetof(Counters, n_surv_total)));
+    CK(zero_counter(c, offsetof(Counters, s2_work)));
     CK(zero_counter(c, offsetof(Counters, n_newkeys)));
     cudaEvent_t ea = c->ev(), eb = c->ev();
     CK(cudaEventRecord(ea, c->stream));

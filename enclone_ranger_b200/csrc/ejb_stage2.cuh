@@ -173,13 +173,23 @@ __global__ void __launch_bounds__(256) k_stage2a(S2Ctx X, const uint2* __restric
     const int lane = threadIdx.x & 31;
     const int g = lane & 7, gid = lane >> 3;
     const unsigned int gmask = 0xffu << (8 * gid);
-    const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    // Work distribution: a CTA takes CONTIGUOUS chunks of the candidate list.  Consecutive candidates come
+    // from one stage-1 tile (<= 128 + 64 distinct rows), so their row records are re-read from L1 instead of L2.
+    constexpr unsigned long long S2A_CHUNK = 2048;
+    __shared__ unsigned long long s_chunk;
+    const int wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     SurvWriter wr;
     wr.init();
-    for (unsigned long long base = warp0 * 4; base < n_cand; base += nwarps * 4) {
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_chunk = atomicAdd(&X.ctr->s2_work, S2A_CHUNK);
+      __syncthreads();
+      const unsigned long long c0 = s_chunk;
+      if (c0 >= n_cand) break;
+      const unsigned long long c1 = min(c0 + S2A_CHUNK, n_cand);
+      for (unsigned long long base = c0 + (unsigned long long)wib * 4; base < c1; base += (unsigned long long)nwb * 4) {
         const unsigned long long ci = base + gid;
-        const bool valid = ci < n_cand;
+        const bool valid = ci < c1;
         uint2 pr = make_uint2(0, 0);
         if (valid) pr = cand[ci];
         const uint32_t q1 = pr.x, q2 = pr.y;
@@ -331,6 +341,7 @@ __global__ void __launch_bounds__(256) k_stage2a(S2Ctx X, const uint2* __restric
             }
         }
         wr.push(X, lane, emit, sv);
+      }
     }
     wr.finish(X, lane);
 }

@@ -128,7 +128,7 @@ struct EdgeTuple {      // numeric members of PotentialJoin (defs.rs:870-891)
 struct Counters {       // device-side counters, one instance per context
     unsigned long long n_cand, n_slow, n_surv, n_pass, n_newkeys, pairs_eval, n_forest, n_alive;
     unsigned long long n_two_cell, n_errflag_range, n_errflag_panic, overflow, n_slow_total, n_surv_total, n_pass_total;
-    unsigned long long p1_unique;
+    unsigned long long p1_unique, s2_work;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -48,12 +48,18 @@ def test_tiny_work_buffers_force_round_splitting():
     rep = E.generate(1, n_cells=20000, seed=8)
     p = E.default_params(True)
     want = pyoracle.run(p, rep.c_ptr, threads=0)
-    small = E.JoinContext(cand_cap=1 << 20, pair_budget=1 << 21)   # >= 128 x the largest sub-bucket (one row block must fit)
+    # tiny pair budget: many scheduler rounds (>= 128 x the largest sub-bucket must still fit the buffers)
+    small = E.JoinContext(cand_cap=1 << 22, pair_budget=1 << 20)
     got = small.join(p, rep)
     assert got.stats["rounds"] > 20
-    assert got.stats["overflow_retries"] >= 0
-    assert_same_result(got, want, "small buffers")
+    assert_same_result(got, want, "small budget")
     small.close()
+    # buffers smaller than a round's candidates: overflow -> split -> retry
+    tight = E.JoinContext(cand_cap=1 << 21, pair_budget=1 << 30)
+    got = tight.join(p, rep)
+    assert got.stats["overflow_retries"] > 0
+    assert_same_result(got, want, "overflow retry")
+    tight.close()
 
 
 def test_run_is_deterministic_and_idempotent(gpu_ctx):
