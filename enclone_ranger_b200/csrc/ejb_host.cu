@@ -768,7 +768,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
             sb.W4h = (w4h >= 1 && w4h <= MAXW4) ? w4h : 0;
             sb.W4l = (w4l >= 1 && w4l <= MAXW4) ? w4l : 0;
             sb.gap = si[s].gap & 3;
-            sb.rec_u4 = rec_planes(sb.gap & 1) * sb.W4h + rec_planes(sb.gap & 2) * sb.W4l;
+            sb.rec_u4 = rec_planes(0, sb.gap & 1) * sb.W4h + rec_planes(1, sb.gap & 2) * sb.W4l;
             sb.pad = 0;
             sb.q0 = q;
             sb.s1_off = s1;

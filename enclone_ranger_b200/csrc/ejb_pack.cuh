@@ -175,6 +175,30 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
     // ---- contig planes, reference planes, compare mask, difference bitmap ----
     uint32_t* rec32 = reinterpret_cast<uint32_t*>(rowstore + sb.rs_off + li * (int64_t)sb.rec_u4);
     int base_u4 = 0;
+    // FWR1 / CDR1 / CDR2 ranges of chain 0 (only meaningful when that chain is the left chain; stage 2 checks)
+    int rF0 = 0, rF1 = 0, rC10 = 0, rC11 = 0, rC20 = 0, rC21 = 0;
+    {
+        const int ex0 = in.row_exact[k];
+        const int chh = (int)(in.ex_chain_off[ex0] + in.row_exact_col[2 * k]);
+        const int fr1 = in.ch_fr1[chh], cdr1 = in.ch_cdr1[chh], fr2 = in.ch_fr2[chh], cdr2 = in.ch_cdr2[chh], fr3 = in.ch_fr3[chh];
+        const int L = sb.Lh;
+        const bool has_f = cdr1 != -1;
+        const bool has_c1 = cdr1 != -1 && fr2 != -1 && cdr1 <= fr2;
+        const bool has_c2 = cdr2 != -1 && fr3 != -1 && cdr2 <= fr3;
+        const bool okf = !has_f || (fr1 >= 0 && fr1 <= cdr1 && cdr1 <= L);
+        const bool okc1 = !has_c1 || (cdr1 >= 0 && fr2 <= L);
+        const bool okc2 = !has_c2 || (cdr2 >= 0 && fr3 <= L);
+        // the three ranges must also be pairwise disjoint to share one region-id plane pair
+        bool disj = true;
+        if (has_f && has_c2 && !(cdr1 <= cdr2 || fr3 <= fr1)) disj = false;
+        if (has_c1 && has_c2 && !(fr2 <= cdr2 || fr3 <= cdr1)) disj = false;
+        if (okf && okc1 && okc2 && disj) {
+            flags |= B_REG_OK;
+            if (has_f) { rF0 = fr1; rF1 = cdr1; }
+            if (has_c1) { rC10 = cdr1; rC11 = fr2; }
+            if (has_c2) { rC20 = cdr2; rC21 = fr3; }
+        }
+    }
     for (int m = 0; m < 2; m++) {
         const int L = (m == 0) ? sb.Lh : sb.Ll;
         const int W4 = (m == 0) ? sb.W4h : sb.W4l;
@@ -194,7 +218,7 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
         bool odd = false;
         const int nw = (L + 31) / 32;
         for (int w = 0; w < 4 * W4; w++) {
-            uint32_t lo = 0, hi = 0, dm = 0, gp = 0, rlo = 0, rhi = 0, cm = 0;
+            uint32_t lo = 0, hi = 0, dm = 0, gp = 0, rlo = 0, rhi = 0, cm = 0, glo = 0, ghi = 0;
             if (w < nw) {
                 const int p = w * 32 + lane;
                 int code = 0, dbit = 0, gbit = 0, rcode = 0, cbit = 0;
@@ -214,6 +238,14 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
                     }
                     dbit = cbit && (b != bit2base(rcode));
                 }
+                if (m == 0) {
+                    int rid = 0;
+                    if (p >= rF0 && p < rF1) rid = 1;
+                    else if (p >= rC10 && p < rC11) rid = 2;
+                    else if (p >= rC20 && p < rC21) rid = 3;
+                    glo = __ballot_sync(0xffffffffu, rid & 1);
+                    ghi = __ballot_sync(0xffffffffu, rid & 2);
+                }
                 lo = __ballot_sync(0xffffffffu, code & 1);
                 hi = __ballot_sync(0xffffffffu, code & 2);
                 dm = __ballot_sync(0xffffffffu, dbit);
@@ -228,9 +260,15 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
                 rec32[(base_u4 + 1 * W4) * 4 + w] = hi;
                 rec32[(base_u4 + 2 * W4) * 4 + w] = dm;
                 if (gapbit) rec32[(base_u4 + 3 * W4) * 4 + w] = gp;
-                rec32[(base_u4 + (3 + gapbit) * W4) * 4 + w] = rlo;
-                rec32[(base_u4 + (4 + gapbit) * W4) * 4 + w] = rhi;
-                rec32[(base_u4 + (5 + gapbit) * W4) * 4 + w] = cm;
+                int o = 3 + gapbit;
+                if (m == 0) {
+                    rec32[(base_u4 + o * W4) * 4 + w] = glo;
+                    rec32[(base_u4 + (o + 1) * W4) * 4 + w] = ghi;
+                    o += 2;
+                }
+                rec32[(base_u4 + o * W4) * 4 + w] = rlo;
+                rec32[(base_u4 + (o + 1) * W4) * 4 + w] = rhi;
+                rec32[(base_u4 + (o + 2) * W4) * 4 + w] = cm;
             }
         }
         if (W4 == 0) {  // contig longer than the fast path: the byte-exact path handles it
@@ -238,7 +276,7 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
                 if (!is_acgt(tig[p]) && !(tig[p] == '-' && hasdel)) odd = true;
         }
         if (__any_sync(0xffffffffu, odd)) flags |= (m == 0) ? F_ODDBYTE_H : F_ODDBYTE_L;
-        base_u4 += rec_planes(gapbit) * W4;
+        base_u4 += rec_planes(m, gapbit) * W4;
     }
     if (lane == 0) {
         rowq[q] = (int32_t)k;

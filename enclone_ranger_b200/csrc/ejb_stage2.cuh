@@ -143,40 +143,139 @@ struct SurvWriter {
     }
 };
 
-// popc of e[0..3] (positions bit0 .. bit0+127) restricted to [a, b)
-__device__ __forceinline__ int range_popc4(const uint32_t* e, int bit0, int a, int b) {
-    int s = 0;
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        const int lo = max(a - (bit0 + 32 * w), 0), hi = min(b - (bit0 + 32 * w), 32);
-        if (hi > lo) {
-            const uint32_t mh = (hi == 32) ? 0xffffffffu : ((1u << hi) - 1u);
-            s += __popc(e[w] & mh & ~((1u << lo) - 1u));
-        }
-    }
-    return s;
-}
-
 __device__ __forceinline__ void ld4(const uint4* p, uint32_t* o) {
     const uint4 v = __ldg(p);
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
 }
 
-// Fast path: 8 lanes per candidate.  Lane g handles uint4 g of every plane (128 positions).
-//   e    = (lo1^lo2)|(hi1^hi2)|(gap1^gap2)   bases differ (t1 != t2)
-//   one reference (the usual case):  A = popc(d1 & d2), B = popc(d1 & d2 & e)
-//        shares = A - B;  indeps = tot1 + tot2 - 2A + 2B                       (join_one.rs:402-419)
-//   two references: x21 = (t2 != r1) on cmp1, x12 = (t1 != r2) on cmp2, then the same counts per reference
-__global__ void __launch_bounds__(256) k_stage2a(S2Ctx X, const uint2* __restrict__ cand, const uint32_t* __restrict__ cand_slot,
-                                                 const unsigned long long* __restrict__ n_cand_p, unsigned long long cand_cap) {
-    const unsigned long long n_cand = min(*n_cand_p, cand_cap);
-    const int lane = threadIdx.x & 31;
-    const int g = lane & 7, gid = lane >> 3;
-    const unsigned int gmask = 0xffu << (8 * gid);
-    // Work distribution: a CTA takes CONTIGUOUS chunks of the candidate list.  Consecutive candidates come
-    // from one stage-1 tile (<= 128 + 64 distinct rows), so their row records are re-read from L1 instead of L2.
+// Plane math of ONE candidate by a group of G lanes (G = 4 or 8); lane g handles uint4 g of every plane
+// (128 positions).  Results are packed sums (every field stays < 65536 after the group reduction):
+//   r[0] = cd1 | cd2<<16      CDR3 differences heavy | light
+//   r[1] = A | B<<16          A = popc(d1 & d2), B = popc(d1 & d2 & e); e = bases differ (incl. gaps)
+//   r[2] = diffs | fd<<16     full-length differences | FWR1 differences
+//   r[3] = c1d | c2d<<16      CDR1 | CDR2 differences                       (regions of row 1's planes)
+//   two references only: r[4] = A0|B0, r[5] = O0|T01, r[6] = A1|B1, r[7] = O1|T10
+//     x21 = (t2 != r1) on cmp1, x12 = (t1 != r2) on cmp2;  A0 = popc(d1&x21) ... (join_one.rs:343-429)
+template <int G>
+__device__ __forceinline__ void s2_planes(const S2Ctx& X, const SubBucket& sb, uint32_t q1, uint32_t q2, int g, bool active, bool nrefs1,
+                                          unsigned int gmask, uint32_t* r) {
+    uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+    if (active) {
+        if (g < sb.W1) {
+            const uint32_t* b = X.cdr3w + sb.s1_off;
+            const int64_t i1 = q1 - sb.q0, i2 = q2 - sb.q0;
+            const uint32_t x = (b[(int64_t)g * sb.npad + i1] ^ b[(int64_t)g * sb.npad + i2]) |
+                               (b[(int64_t)(sb.W1 + g) * sb.npad + i1] ^ b[(int64_t)(sb.W1 + g) * sb.npad + i2]);
+            const int lo_bit = g * 32;
+            uint32_t hm;  // bits of this word that belong to the heavy CDR3
+            if (sb.ch >= lo_bit + 32) hm = 0xffffffffu;
+            else if (sb.ch <= lo_bit) hm = 0u;
+            else hm = (1u << (sb.ch - lo_bit)) - 1u;
+            pk0 = (uint32_t)__popc(x & hm) | ((uint32_t)__popc(x & ~hm) << 16);
+        }
+        if (G == 4 && g + 4 < sb.W1) {   // W1 up to 6 with only 4 lanes: lanes 0,1 take words 4,5 as well
+            const int w = g + 4;
+            const uint32_t* b = X.cdr3w + sb.s1_off;
+            const int64_t i1 = q1 - sb.q0, i2 = q2 - sb.q0;
+            const uint32_t x = (b[(int64_t)w * sb.npad + i1] ^ b[(int64_t)w * sb.npad + i2]) |
+                               (b[(int64_t)(sb.W1 + w) * sb.npad + i1] ^ b[(int64_t)(sb.W1 + w) * sb.npad + i2]);
+            const int lo_bit = w * 32;
+            uint32_t hm;
+            if (sb.ch >= lo_bit + 32) hm = 0xffffffffu;
+            else if (sb.ch <= lo_bit) hm = 0u;
+            else hm = (1u << (sb.ch - lo_bit)) - 1u;
+            pk0 += (uint32_t)__popc(x & hm) | ((uint32_t)__popc(x & ~hm) << 16);
+        }
+        const uint4* r1 = X.rowstore + sb.rs_off + (int64_t)(q1 - sb.q0) * sb.rec_u4;
+        const uint4* r2 = X.rowstore + sb.rs_off + (int64_t)(q2 - sb.q0) * sb.rec_u4;
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            const int W4 = m ? sb.W4l : sb.W4h;
+            const int gapbit = (sb.gap >> m) & 1;
+            const int off = m ? rec_planes(0, sb.gap & 1) * sb.W4h : 0;
+            if (g < W4) {
+                uint32_t al[4], ah[4], ad[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bd[4], bg[4] = {0, 0, 0, 0}, e[4];
+                ld4(r1 + off + g, al); ld4(r1 + off + W4 + g, ah); ld4(r1 + off + 2 * W4 + g, ad);
+                ld4(r2 + off + g, bl); ld4(r2 + off + W4 + g, bh); ld4(r2 + off + 2 * W4 + g, bd);
+                if (gapbit) { ld4(r1 + off + 3 * W4 + g, ag); ld4(r2 + off + 3 * W4 + g, bg); }
+                int A = 0, B = 0, df = 0;
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    e[w] = (al[w] ^ bl[w]) | (ah[w] ^ bh[w]) | (ag[w] ^ bg[w]);
+                    const uint32_t both = ad[w] & bd[w];
+                    A += __popc(both);
+                    B += __popc(both & e[w]);
+                    df += __popc(e[w]);
+                }
+                pk1 += (uint32_t)A | ((uint32_t)B << 16);
+                pk2 += (uint32_t)df;
+                if (m == 0) {   // region ids of row 1: 1 = FWR1, 2 = CDR1, 3 = CDR2
+                    uint32_t gl[4], gh[4];
+                    ld4(r1 + off + (3 + gapbit) * W4 + g, gl); ld4(r1 + off + (4 + gapbit) * W4 + g, gh);
+                    int fd = 0, c1 = 0, c2 = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        fd += __popc(e[w] & gl[w] & ~gh[w]);
+                        c1 += __popc(e[w] & ~gl[w] & gh[w]);
+                        c2 += __popc(e[w] & gl[w] & gh[w]);
+                    }
+                    pk2 += (uint32_t)fd << 16;
+                    pk3 += (uint32_t)c1 | ((uint32_t)c2 << 16);
+                }
+                if (!nrefs1) {
+                    uint32_t arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
+                    const int ro = off + (3 + gapbit + (m == 0 ? 2 : 0)) * W4;
+                    ld4(r1 + ro + g, arl); ld4(r1 + ro + W4 + g, arh); ld4(r1 + ro + 2 * W4 + g, ac);
+                    ld4(r2 + ro + g, brl); ld4(r2 + ro + W4 + g, brh); ld4(r2 + ro + 2 * W4 + g, bc);
+                    int A0 = 0, B0 = 0, O0 = 0, T01 = 0, A1 = 0, B1 = 0, O1 = 0, T10 = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        const uint32_t x21 = ((bl[w] ^ arl[w]) | (bh[w] ^ arh[w]) | bg[w]) & ac[w];  // t2 != r1 on k1's ranges
+                        const uint32_t x12 = ((al[w] ^ brl[w]) | (ah[w] ^ brh[w]) | ag[w]) & bc[w];  // t1 != r2 on k2's ranges
+                        const uint32_t d1 = ad[w], d2 = bd[w];
+                        A0 += __popc(d1 & x21); B0 += __popc(d1 & x21 & e[w]); O0 += __popc(d1 ^ x21); T01 += __popc(x21);
+                        A1 += __popc(x12 & d2); B1 += __popc(x12 & d2 & e[w]); O1 += __popc(x12 ^ d2); T10 += __popc(x12);
+                    }
+                    n0 += (uint32_t)A0 | ((uint32_t)B0 << 16);
+                    n1 += (uint32_t)O0 | ((uint32_t)T01 << 16);
+                    n2 += (uint32_t)A1 | ((uint32_t)B1 << 16);
+                    n3 += (uint32_t)O1 | ((uint32_t)T10 << 16);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+        pk0 += __shfl_xor_sync(0xffffffffu, pk0, o);
+        pk1 += __shfl_xor_sync(0xffffffffu, pk1, o);
+        pk2 += __shfl_xor_sync(0xffffffffu, pk2, o);
+        pk3 += __shfl_xor_sync(0xffffffffu, pk3, o);
+    }
+    if (active && !nrefs1) {  // group-uniform branch: shuffle inside the group only
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            n0 += __shfl_xor_sync(gmask, n0, o);
+            n1 += __shfl_xor_sync(gmask, n1, o);
+            n2 += __shfl_xor_sync(gmask, n2, o);
+            n3 += __shfl_xor_sync(gmask, n3, o);
+        }
+    }
+    r[0] = pk0; r[1] = pk1; r[2] = pk2; r[3] = pk3; r[4] = n0; r[5] = n1; r[6] = n2; r[7] = n3;
+}
+
+// Stage 2a.  A warp works on batches of 32 consecutive candidates:
+//   phase 1: the plane math, G lanes per candidate (G = 4 when both contigs fit 4 uint4 = 512 nt, else 8),
+//            packed results to shared memory;
+//   phase 2: one lane per candidate runs the scalar integer tests and emits the survivor.
+// A CTA takes CONTIGUOUS chunks of the candidate list: consecutive candidates come from one stage-1 tile
+// (<= 128 + 64 distinct rows), so their row records are re-read from L1 instead of L2.
+__global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __restrict__ cand, const uint32_t* __restrict__ cand_slot,
+                                                    const unsigned long long* __restrict__ n_cand_p, unsigned long long cand_cap) {
     constexpr unsigned long long S2A_CHUNK = 2048;
     __shared__ unsigned long long s_chunk;
+    __shared__ uint32_t s_res[8][32][9];   // [warp][candidate][8 packed results]; padded row: conflict-free column reads
+    const unsigned long long n_cand = min(*n_cand_p, cand_cap);
+    const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     SurvWriter wr;
     wr.init();
@@ -187,142 +286,82 @@ __global__ void __launch_bounds__(256) k_stage2a(S2Ctx X, const uint2* __restric
       const unsigned long long c0 = s_chunk;
       if (c0 >= n_cand) break;
       const unsigned long long c1 = min(c0 + S2A_CHUNK, n_cand);
-      for (unsigned long long base = c0 + (unsigned long long)wib * 4; base < c1; base += (unsigned long long)nwb * 4) {
-        const unsigned long long ci = base + gid;
+      for (unsigned long long base = c0 + (unsigned long long)wib * 32; base < c1; base += (unsigned long long)nwb * 32) {
+        // ---- my own candidate (phase 2 owner) ----
+        const unsigned long long ci = base + lane;
         const bool valid = ci < c1;
         uint2 pr = make_uint2(0, 0);
         if (valid) pr = cand[ci];
         const uint32_t q1 = pr.x, q2 = pr.y;
-        const uint32_t slot = (valid && cand_slot) ? cand_slot[ci] : (uint32_t)ci;
-        const SubBucket sb = X.subs[X.subq[q1]];
-        const uint4* ax1 = reinterpret_cast<const uint4*>(X.aux + (size_t)q1 * AUX_INTS);
-        const uint4* ax2 = reinterpret_cast<const uint4*>(X.aux + (size_t)q2 * AUX_INTS);
-        const uint4 a10 = __ldg(ax1), a11 = __ldg(ax1 + 1), a20 = __ldg(ax2), a21 = __ldg(ax2 + 1);
+        const int sid = X.subq[q1];
+        const SubBucket sb = X.subs[sid];
+        const int32_t* a1 = X.aux + (size_t)q1 * AUX_INTS;
+        const int32_t* a2 = X.aux + (size_t)q2 * AUX_INTS;
+        const uint4 a10 = __ldg(reinterpret_cast<const uint4*>(a1)), a20 = __ldg(reinterpret_cast<const uint4*>(a2));
         const uint32_t f1 = a10.x, f2 = a20.x;
-        const bool nrefs1 = (a10.y == a20.y && a10.z == a20.z && a10.w == a20.w && a11.x == a21.x);
-        const bool fast = ((f1 | f2) & F_SLOWMASK) == 0 && sb.W1 > 0 && sb.W4h > 0 && sb.W4l > 0;
-        const int tot1 = (int)a11.y, tot2 = (int)a21.y;
-        // FWR1 / CDR1 / CDR2 ranges on the left chain, usable when both rows carry identical features
-        int rF0 = 0, rF1 = 0, rC10 = 0, rC11 = 0, rC20 = 0, rC21 = 0, regfast = 0;
-        {
-            const uint4 a14 = __ldg(ax1 + 4), a15 = __ldg(ax1 + 5), a24 = __ldg(ax2 + 4), a25 = __ldg(ax2 + 5);
-            const int fr1 = (int)a14.z, cdr1 = (int)a14.w, fr2 = (int)a15.x, cdr2 = (int)a15.y, fr3 = (int)a15.z;
-            const bool same = a14.z == a24.z && a14.w == a24.w && a15.x == a25.x && a15.y == a25.y && a15.z == a25.z;
-            const uint32_t need = B_LEFT_H | B_AMINO_TIG_H;
-            const bool stdrow = (f1 & (need | B_LEFT_L)) == need && (f2 & (need | B_LEFT_L)) == need;
-            const int L = sb.Lh;
-            const bool has_f = cdr1 != -1;
-            const bool has_c1 = cdr1 != -1 && fr2 != -1 && cdr1 <= fr2;
-            const bool has_c2 = cdr2 != -1 && fr3 != -1 && cdr2 <= fr3;
-            const bool okf = !has_f || (fr1 >= 0 && fr1 <= cdr1 && cdr1 <= L);
-            const bool okc1 = !has_c1 || (cdr1 >= 0 && fr2 <= L);
-            const bool okc2 = !has_c2 || (cdr2 >= 0 && fr3 <= L);
-            if (same && stdrow && okf && okc1 && okc2) {
-                regfast = 1;
-                if (has_f) { rF0 = fr1; rF1 = cdr1; }
-                if (has_c1) { rC10 = cdr1; rC11 = fr2; }
-                if (has_c2) { rC20 = cdr2; rC21 = fr3; }
+        const bool nrefs1 = (a10.y == a20.y && a10.z == a20.z && a10.w == a20.w && a1[AX_JSL] == a2[AX_JSL]);
+        const bool fast = valid && ((f1 | f2) & F_SLOWMASK) == 0 && sb.W1 > 0 && sb.W4h > 0 && sb.W4l > 0;
+        const bool wide = fast && (sb.W4h > 4 || sb.W4l > 4);
+        // ---- phase 1 ----
+        if (!__any_sync(0xffffffffu, wide)) {
+#pragma unroll 1
+            for (int it = 0; it < 4; it++) {
+                const int src = it * 8 + (lane >> 2);           // candidate (lane index of its owner) this group works on
+                const uint32_t gq1 = __shfl_sync(0xffffffffu, q1, src), gq2 = __shfl_sync(0xffffffffu, q2, src);
+                const int gsid = __shfl_sync(0xffffffffu, sid, src);
+                const bool gfast = __shfl_sync(0xffffffffu, (int)fast, src) != 0, gn1 = __shfl_sync(0xffffffffu, (int)nrefs1, src) != 0;
+                const SubBucket gsb = X.subs[gsid];
+                uint32_t r[8];
+                s2_planes<4>(X, gsb, gq1, gq2, lane & 3, gfast, gn1, 0xfu << (lane & 28), r);
+                if ((lane & 3) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) s_res[wib][src][i] = r[i];
+                }
             }
-        }
-        // packed accumulators (every field stays < 65536 after the 8-lane sum)
-        uint32_t pk0 = 0 /* cd1 | cd2<<16 */, pk1 = 0 /* A | B<<16 */, pk2 = 0 /* diffs | fd<<16 */, pk3 = 0 /* c1d | c2d<<16 */;
-        uint32_t n0 = 0 /* A0|B0 */, n1 = 0 /* O0|T01 */, n2 = 0 /* A1|B1 */, n3 = 0 /* O1|T10 */;
-        if (valid && fast) {
-            // CDR3 distances, split at the heavy/light boundary of the concatenated planes
-            if (g < sb.W1) {
-                const uint32_t* b = X.cdr3w + sb.s1_off;
-                const int64_t i1 = q1 - sb.q0, i2 = q2 - sb.q0;
-                const uint32_t x = (b[(int64_t)g * sb.npad + i1] ^ b[(int64_t)g * sb.npad + i2]) |
-                                   (b[(int64_t)(sb.W1 + g) * sb.npad + i1] ^ b[(int64_t)(sb.W1 + g) * sb.npad + i2]);
-                const int lo_bit = g * 32;
-                uint32_t hm;  // bits of this word that belong to the heavy CDR3
-                if (sb.ch >= lo_bit + 32) hm = 0xffffffffu;
-                else if (sb.ch <= lo_bit) hm = 0u;
-                else hm = (1u << (sb.ch - lo_bit)) - 1u;
-                pk0 = (uint32_t)__popc(x & hm) | ((uint32_t)__popc(x & ~hm) << 16);
-            }
-            const uint4* r1 = X.rowstore + sb.rs_off + (int64_t)(q1 - sb.q0) * sb.rec_u4;
-            const uint4* r2 = X.rowstore + sb.rs_off + (int64_t)(q2 - sb.q0) * sb.rec_u4;
+        } else {
+#pragma unroll 1
+            for (int it = 0; it < 8; it++) {
+                const int src = it * 4 + (lane >> 3);
+                const uint32_t gq1 = __shfl_sync(0xffffffffu, q1, src), gq2 = __shfl_sync(0xffffffffu, q2, src);
+                const int gsid = __shfl_sync(0xffffffffu, sid, src);
+                const bool gfast = __shfl_sync(0xffffffffu, (int)fast, src) != 0, gn1 = __shfl_sync(0xffffffffu, (int)nrefs1, src) != 0;
+                const SubBucket gsb = X.subs[gsid];
+                uint32_t r[8];
+                s2_planes<8>(X, gsb, gq1, gq2, lane & 7, gfast, gn1, 0xffu << (lane & 24), r);
+                if ((lane & 7) == 0) {
 #pragma unroll
-            for (int m = 0; m < 2; m++) {
-                const int W4 = m ? sb.W4l : sb.W4h;
-                const int gapbit = (sb.gap >> m) & 1;
-                const int off = m ? rec_planes(sb.gap & 1) * sb.W4h : 0;
-                if (g < W4) {
-                    uint32_t al[4], ah[4], ad[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bd[4], bg[4] = {0, 0, 0, 0}, e[4];
-                    ld4(r1 + off + g, al); ld4(r1 + off + W4 + g, ah); ld4(r1 + off + 2 * W4 + g, ad);
-                    ld4(r2 + off + g, bl); ld4(r2 + off + W4 + g, bh); ld4(r2 + off + 2 * W4 + g, bd);
-                    if (gapbit) { ld4(r1 + off + 3 * W4 + g, ag); ld4(r2 + off + 3 * W4 + g, bg); }
-                    int A = 0, B = 0, df = 0;
-#pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                        e[w] = (al[w] ^ bl[w]) | (ah[w] ^ bh[w]) | (ag[w] ^ bg[w]);
-                        const uint32_t both = ad[w] & bd[w];
-                        A += __popc(both);
-                        B += __popc(both & e[w]);
-                        df += __popc(e[w]);
-                    }
-                    pk1 += (uint32_t)A | ((uint32_t)B << 16);
-                    pk2 += (uint32_t)df;
-                    if (m == 0 && regfast) {
-                        pk2 += (uint32_t)range_popc4(e, g * 128, rF0, rF1) << 16;
-                        pk3 += (uint32_t)range_popc4(e, g * 128, rC10, rC11) | ((uint32_t)range_popc4(e, g * 128, rC20, rC21) << 16);
-                    }
-                    if (!nrefs1) {
-                        uint32_t arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
-                        const int ro = off + (3 + gapbit) * W4;
-                        ld4(r1 + ro + g, arl); ld4(r1 + ro + W4 + g, arh); ld4(r1 + ro + 2 * W4 + g, ac);
-                        ld4(r2 + ro + g, brl); ld4(r2 + ro + W4 + g, brh); ld4(r2 + ro + 2 * W4 + g, bc);
-                        int A0 = 0, B0 = 0, O0 = 0, T01 = 0, A1 = 0, B1 = 0, O1 = 0, T10 = 0;
-#pragma unroll
-                        for (int w = 0; w < 4; w++) {
-                            const uint32_t x21 = ((bl[w] ^ arl[w]) | (bh[w] ^ arh[w]) | bg[w]) & ac[w];  // t2 != r1 on k1's ranges
-                            const uint32_t x12 = ((al[w] ^ brl[w]) | (ah[w] ^ brh[w]) | ag[w]) & bc[w];  // t1 != r2 on k2's ranges
-                            const uint32_t d1 = ad[w], d2 = bd[w];
-                            A0 += __popc(d1 & x21); B0 += __popc(d1 & x21 & e[w]); O0 += __popc(d1 ^ x21); T01 += __popc(x21);
-                            A1 += __popc(x12 & d2); B1 += __popc(x12 & d2 & e[w]); O1 += __popc(x12 ^ d2); T10 += __popc(x12);
-                        }
-                        n0 += (uint32_t)A0 | ((uint32_t)B0 << 16);
-                        n1 += (uint32_t)O0 | ((uint32_t)T01 << 16);
-                        n2 += (uint32_t)A1 | ((uint32_t)B1 << 16);
-                        n3 += (uint32_t)O1 | ((uint32_t)T10 << 16);
-                    }
+                    for (int i = 0; i < 8; i++) s_res[wib][src][i] = r[i];
                 }
             }
         }
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            pk0 += __shfl_xor_sync(0xffffffffu, pk0, o);
-            pk1 += __shfl_xor_sync(0xffffffffu, pk1, o);
-            pk2 += __shfl_xor_sync(0xffffffffu, pk2, o);
-            pk3 += __shfl_xor_sync(0xffffffffu, pk3, o);
-        }
-        if (valid && fast && !nrefs1) {  // group-uniform branch: shuffle inside the 8-lane group only
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                n0 += __shfl_xor_sync(gmask, n0, o);
-                n1 += __shfl_xor_sync(gmask, n1, o);
-                n2 += __shfl_xor_sync(gmask, n2, o);
-                n3 += __shfl_xor_sync(gmask, n3, o);
-            }
-        }
+        __syncwarp();
+        // ---- phase 2: one lane per candidate ----
         bool emit = false;
         Survivor sv;
-        if (valid && g == 0) {
+        if (valid) {
+            const uint32_t slot = cand_slot ? cand_slot[ci] : (uint32_t)ci;
             if (fast) {
-                const int cd1 = (int)(pk0 & 0xffff), cd2 = (int)(pk0 >> 16);
-                const int diffs = (int)(pk2 & 0xffff);
+                const uint32_t* r = s_res[wib][lane];
+                const int cd1 = (int)(r[0] & 0xffff), cd2 = (int)(r[0] >> 16);
+                const int diffs = (int)(r[2] & 0xffff);
+                const int tot1 = a1[AX_TOT], tot2 = a2[AX_TOT];
+                // region differences are usable when both rows: chain 0 is the only left chain, seq_del_amino is the
+                // contig, well-formed ranges, and identical feature starts
                 RegionDiffs rg;
-                rg.regfast = regfast;
-                rg.fd = (int)(pk2 >> 16);
-                rg.c1d = (int)(pk3 & 0xffff);
-                rg.c2d = (int)(pk3 >> 16);
+                const uint32_t need = B_LEFT_H | B_AMINO_TIG_H | B_REG_OK;
+                const uint4 a14 = __ldg(reinterpret_cast<const uint4*>(a1) + 4), a15 = __ldg(reinterpret_cast<const uint4*>(a1) + 5);
+                const uint4 a24 = __ldg(reinterpret_cast<const uint4*>(a2) + 4), a25 = __ldg(reinterpret_cast<const uint4*>(a2) + 5);
+                const bool same = a14.z == a24.z && a14.w == a24.w && a15.x == a25.x && a15.y == a25.y && a15.z == a25.z;
+                rg.regfast = (same && (f1 & (need | B_LEFT_L)) == need && (f2 & (need | B_LEFT_L)) == need) ? 1 : 0;
+                rg.fd = (int)(r[2] >> 16);
+                rg.c1d = (int)(r[3] & 0xffff);
+                rg.c2d = (int)(r[3] >> 16);
                 if (nrefs1) {
-                    const int A = (int)(pk1 & 0xffff), B = (int)(pk1 >> 16);
+                    const int A = (int)(r[1] & 0xffff), B = (int)(r[1] >> 16);
                     emit = s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, 1, A - B, tot1 + tot2 - 2 * A + 2 * B, 0, 0, rg, true, X.tuple_mode != 0, sv);
                 } else {
-                    const int A0 = (int)(n0 & 0xffff), B0 = (int)(n0 >> 16), O0 = (int)(n1 & 0xffff), T01 = (int)(n1 >> 16);
-                    const int A1 = (int)(n2 & 0xffff), B1 = (int)(n2 >> 16), O1 = (int)(n3 & 0xffff), T10 = (int)(n3 >> 16);
+                    const int A0 = (int)(r[4] & 0xffff), B0 = (int)(r[4] >> 16), O0 = (int)(r[5] & 0xffff), T01 = (int)(r[5] >> 16);
+                    const int A1 = (int)(r[6] & 0xffff), B1 = (int)(r[6] >> 16), O1 = (int)(r[7] & 0xffff), T10 = (int)(r[7] >> 16);
                     // join_one.rs:434-440: total[0] = (tot1, T01), total[1] = (T10, tot2)
                     bool ok = true;
                     if (abs(tot1 - T10) > X.P.max_degradation) ok = false;
@@ -340,6 +379,7 @@ __global__ void __launch_bounds__(256) k_stage2a(S2Ctx X, const uint2* __restric
                 }
             }
         }
+        __syncwarp();   // s_res is rewritten by the next batch
         wr.push(X, lane, emit, sv);
       }
     }

@@ -52,7 +52,8 @@ enum RowFlags : uint32_t {
     B_JUN_LEFT = 1u << 18,    // share[0].left != share[1].left join_one.rs:556
     B_LEFT_H = 1u << 19,      // left flag of the row's chain 0 / 1
     B_LEFT_L = 1u << 20,
-    B_AMINO_TIG_H = 1u << 21  // seq_del_amino of chain 0 is the row's contig
+    B_AMINO_TIG_H = 1u << 21, // seq_del_amino of chain 0 is the row's contig
+    B_REG_OK = 1u << 22       // chain 0's FWR1/CDR1/CDR2 ranges are well formed and inside the contig: the region planes are valid
 };
 
 struct SubBucket {
@@ -78,9 +79,11 @@ struct SubBucket {
 //   t_lo, t_hi : 2-bit code of the contig base (A,C,G,T = 0..3; '-' = 0 with the gap bit)
 //   d          : cmp & (contig base != own reference base)
 //   [gap]      : '-' positions (only when SubBucket.gap has bit m)
+//   [g_lo,g_hi]: chain 0 only — region id of each position: 1 = FWR1 [fr1,cdr1), 2 = CDR1 [cdr1,fr2),
+//                3 = CDR2 [cdr2,fr3), 0 = elsewhere                       (join_one.rs:766-854)
 //   r_lo, r_hi : the row's own V / J reference bases in CONTIG coordinates (V from the start, J from the end)
 //   cmp        : positions join_one compares: p < |V|-ref_v_trim  or  p >= L-(|J|-ref_j_trim)
-__host__ __device__ __forceinline__ int rec_planes(int gapbit) { return 6 + (gapbit ? 1 : 0); }
+__host__ __device__ __forceinline__ int rec_planes(int m, int gapbit) { return 6 + (gapbit ? 1 : 0) + (m == 0 ? 2 : 0); }
 
 // Device view of the raw (uploaded) input, same meaning as ejb_input.
 struct DevIn {
