@@ -149,7 +149,7 @@ def test_stirling_range_error(gpu_ctx):
     w.vh = cases.rand_seq(w.rng, 2400); w.VH = 2400
     w.seg_vh = w.b.seg(w.vh); w.ref_vh = w.b.ref(w.vh, 77)
     h0, l0 = w.heavy(), w.light()
-    shared = list(range(10, 2300, 2))[:1100]
+    shared = list(range(10, 2380))[:1600]   # k = 2 + 2 * 1600 > 3000
     w.member(cases.mutate(h0, shared + [3]), l0, feats=False); w.member(cases.mutate(h0, shared + [7]), l0, feats=False)
     with pytest.raises(E.JoinError) as ei:
         gpu_ctx.join(E.default_params(True), w.build())
