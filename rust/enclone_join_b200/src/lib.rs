@@ -51,10 +51,12 @@ pub mod sys {
 
     #[repr(C)]
     pub struct EjbStats {
-        pub counters: [i64; 19],      // n_buckets .. d2h_bytes (see the header)
-        pub ms: [f64; 10],            // ms_h2d .. ms_total
+        pub counters: [i64; 18],      // n_buckets .. d2h_bytes, in header order
+        pub ms: [f64; 8],             // ms_h2d, ms_pack, ms_stage1, ms_stage2, ms_forest, ms_finalize, ms_d2h, ms_replay
         pub ms_stage2a: f64,
         pub launches: [i64; 3],       // stage1_launches, stage2a_launches, overflow_retries
+        pub ms_device_total: f64,
+        pub ms_total: f64,
     }
 
     #[repr(C)]
