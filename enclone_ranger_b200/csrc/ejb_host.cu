@@ -60,8 +60,8 @@ struct DevBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct Unit {  // a run of row blocks of one sub-bucket, processed against all columns to its right
-    int32_t sub, rb0, rb1;
+struct Unit {  // rows [r0, r1) of one sub-bucket, processed against all columns to their right
+    int32_t sub, r0, r1;
 };
 
 }  // namespace
@@ -84,6 +84,8 @@ struct ejb_ctx {
     DevBuf d_sr, d_p1_keys, d_p1_vals, d_p1_new, d_ctr, d_err;
     unsigned long long p1_count = 0;
     Counters* h_ctr = nullptr;  // pinned
+    char* h_res = nullptr;      // pinned result arena (grow-only); ejb_result arrays point into it
+    size_t h_res_cap = 0;
 
     // uploaded input
     ejb_params params;
@@ -249,8 +251,9 @@ __global__ void k_stage1_nofilter(const SubBucket* __restrict__ subs, const RowT
     unsigned long long ev = 0;
     for (int cb = cb_first; cb < nb && cb < cb_first + S1_STRIP; cb++) {
         for (int idx = threadIdx.x; idx < TILE * TILE; idx += blockDim.x) {
-            const int r = t.rb * TILE + (idx >> 7), cc = cb * TILE + (idx & 127);
-            if (r >= sb.n || cc >= sb.n || r >= cc) continue;
+            const int rl = idx >> 7;
+            const int r = t.rb * TILE + rl, cc = cb * TILE + (idx & 127);
+            if (rl < t.row_lo || rl >= t.row_hi || r >= sb.n || cc >= sb.n || r >= cc) continue;
             ev++;
             const uint32_t q1 = (uint32_t)(sb.q0 + r), q2 = (uint32_t)(sb.q0 + cc);
             if (labq[q1] == labq[q2]) continue;
@@ -408,6 +411,7 @@ void ejb_destroy(ejb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->h_res) cudaFreeHost(c->h_res);
     c->in_bufs.clear();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -542,10 +546,12 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
     for (const Unit& u : units) {
         const SubBucket& sb = subs[u.sub];
         const int nb = (sb.n + TILE - 1) / TILE;
-        for (int rb = u.rb0; rb < u.rb1; rb++) {
+        for (int rb = u.r0 / TILE; rb * TILE < u.r1; rb++) {
             RowTask t;
             t.sub = u.sub;
             t.rb = rb;
+            t.row_lo = std::max(u.r0 - rb * TILE, 0);
+            t.row_hi = std::min(u.r1 - rb * TILE, TILE);
             t.cta0 = nctas[sb.W1];
             tasks[sb.W1].push_back(t);
             nctas[sb.W1] += (nb - rb + S1_STRIP - 1) / S1_STRIP;
@@ -658,13 +664,15 @@ int run_units(ejb_ctx* c, std::vector<Unit> units, std::vector<RoundTimes>& time
         return run_units(c, b, times, depth + 1);
     }
     Unit u = units[0];
-    if (u.rb1 - u.rb0 <= 1)
-        return fail(c, EJB_ERR_OOM, "candidate buffer (%llu) too small for one 128-row block of a %d-row sub-bucket; raise EJB_CAND_CAP", c->cand_cap,
+    if (u.r1 - u.r0 <= 1)
+        return fail(c, EJB_ERR_OOM, "work buffers (%llu entries) too small for one row of a %d-row sub-bucket; raise EJB_CAND_CAP", c->cand_cap,
                     c->subs[u.sub].n);
-    const int mid = (u.rb0 + u.rb1) / 2;
+    // NOTE: a unit may be split by ROWS only.  Splitting a row range by columns and contracting after each part is not
+    // exact: a lighter edge (smaller k1, later column part) could have to evict a heavier edge already in the forest.
+    const int mid = (u.r0 + u.r1) / 2;
     Unit a = u, b = u;
-    a.rb1 = mid;
-    b.rb0 = mid;
+    a.r1 = mid;
+    b.r0 = mid;
     rc = run_units(c, {a}, times, depth + 1);
     if (rc) return rc;
     return run_units(c, {b}, times, depth + 1);
@@ -901,7 +909,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
     // ---- round scheduler ----
     {
         const std::vector<SubBucket>& subs = c->subs;
-        std::vector<int> next_rb(subs.size(), 0), grow(subs.size(), 1), live;
+        std::vector<int> next_row(subs.size(), 0), live;
         for (int s = 0; s < (int)subs.size(); s++)
             if (subs[s].n >= 2 && subs[s].owner == c->shard_rank) live.push_back(s);
         while (!live.empty()) {
@@ -915,31 +923,30 @@ extern "C" int ejb_run(ejb_ctx* c) {
             std::vector<int> still;
             for (int s : live) {
                 const SubBucket& sb = subs[s];
-                const int nb = (sb.n + TILE - 1) / TILE;
-                int g = std::min(grow[s], nb - next_rb[s]);
-                // pairs of rows [rb0*128, ...) x everything to the right
-                auto unit_pairs = [&](int rb0, int rb1) {
-                    const long long r0 = (long long)rb0 * TILE, r1 = std::min<long long>(sb.n, (long long)rb1 * TILE);
+                // pairs of rows [r0, r1) x everything to their right
+                auto unit_pairs = [&](long long r0, long long r1) {
                     const long long rows = r1 - r0;
                     return (unsigned long long)(rows * (sb.n - r1) + rows * (rows - 1) / 2);
                 };
-                while (g > 1 && unit_pairs(next_rb[s], next_rb[s] + g) > budget / 2) g /= 2;
-                const unsigned long long up = unit_pairs(next_rb[s], next_rb[s] + g);
+                // unit sizes: rows [0,8), [8,32), [32,128), then doubling — the first few rows of a clone connect most of
+                // it, so later units are mostly skipped by the class test; a unit never exceeds half the round budget
+                const int r0 = next_row[s];
+                int r1 = (r0 < 8) ? 8 : (r0 < 32) ? 32 : (r0 < TILE) ? TILE : std::min<long long>(2ll * r0, (long long)r0 + (1 << 21));
+                r1 = std::min(r1, sb.n);
+                while (r1 - r0 > 1 && unit_pairs(r0, r1) > budget / 2) r1 = r0 + (r1 - r0) / 2;
+                const unsigned long long up = unit_pairs(r0, r1);
                 if (!units.empty() && pairs + up > budget) {
                     still.push_back(s);
                     continue;
                 }
                 Unit u;
                 u.sub = s;
-                u.rb0 = next_rb[s];
-                u.rb1 = next_rb[s] + g;
+                u.r0 = r0;
+                u.r1 = r1;
                 units.push_back(u);
                 pairs += up;
-                next_rb[s] += g;
-                // row-block group sizes 1,1,2,4,8,...: the first blocks connect most of a clone, later
-                // ones are mostly skipped by the class test
-                grow[s] = (next_rb[s] <= 1) ? 1 : std::min(next_rb[s], 1 << 14);
-                if (next_rb[s] < nb) still.push_back(s);
+                next_row[s] = r1;
+                if (r1 < sb.n - 1) still.push_back(s);   // the last row has no pair to its right
             }
             live.swap(still);
             int rc = run_units(c, units, times, 0);
@@ -1050,14 +1057,6 @@ extern "C" int ejb_run(ejb_ctx* c) {
     return EJB_OK;
 }
 
-namespace {
-struct ResultOwner {
-    std::vector<int32_t> k1, k2, cd, nrefs, sh, in, k, d, n, labels, x, y, z;
-    std::vector<double> p1, mult, score;
-    std::vector<uint8_t> err;
-};
-}  // namespace
-
 extern "C" {
 
 int ejb_download(ejb_ctx* c, ejb_result* out) {
@@ -1066,71 +1065,76 @@ int ejb_download(ejb_ctx* c, ejb_result* out) {
     CK(cudaSetDevice(c->device));
     memset(out, 0, sizeof(*out));
     const double t0 = now_ms();
-    ResultOwner* R = new ResultOwner();
     const int64_t E = c->n_final, N = c->din.n_rows;
     cudaStream_t st = c->stream;
-    auto get = [&](auto& vec, const DevBuf& b, size_t n) -> cudaError_t {
-        vec.resize(std::max<size_t>(n, 1));
-        if (n == 0) return cudaSuccess;
-        c->stats.d2h_bytes += (int64_t)(n * sizeof(vec[0]));
-        return cudaMemcpyAsync(vec.data(), b.p, n * sizeof(vec[0]), cudaMemcpyDeviceToHost, st);
+    // ---- carve the pinned arena: 13 edge arrays + labels + x/y/z + row_exact scratch ----
+    const size_t e1 = (size_t)std::max<int64_t>(E, 1), n1 = (size_t)std::max<int64_t>(N, 1);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t need = 7 * al(e1 * 4) + 2 * al(e1 * 8) + 3 * al(e1 * 8) + al(e1) + 5 * al(n1 * 4) + 4096;
+    if (need > c->h_res_cap) {
+        if (c->h_res) cudaFreeHost(c->h_res);
+        c->h_res = nullptr;
+        c->h_res_cap = 0;
+        const size_t want = need + need / 4;
+        CK(cudaMallocHost(&c->h_res, want));
+        c->h_res_cap = want;
+    }
+    char* p = c->h_res;
+    auto take = [&](size_t bytes) { char* r = p; p += al(bytes); return r; };
+    int32_t* k1 = (int32_t*)take(e1 * 4); int32_t* k2 = (int32_t*)take(e1 * 4); int32_t* cd = (int32_t*)take(e1 * 4);
+    int32_t* nrefs = (int32_t*)take(e1 * 4); int32_t* kk = (int32_t*)take(e1 * 4); int32_t* dd_ = (int32_t*)take(e1 * 4); int32_t* nn = (int32_t*)take(e1 * 4);
+    int32_t* sh = (int32_t*)take(e1 * 8); int32_t* in = (int32_t*)take(e1 * 8);
+    double* p1 = (double*)take(e1 * 8); double* mult = (double*)take(e1 * 8); double* score = (double*)take(e1 * 8);
+    uint8_t* err = (uint8_t*)take(e1);
+    int32_t* labels = (int32_t*)take(n1 * 4); int32_t* ex = (int32_t*)take(n1 * 4); int32_t* ey = (int32_t*)take(n1 * 4); int32_t* ez = (int32_t*)take(n1 * 4);
+    int32_t* row_exact = (int32_t*)take(n1 * 4);
+    auto get = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        if (bytes == 0) return cudaSuccess;
+        c->stats.d2h_bytes += (int64_t)bytes;
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
     };
-    cudaError_t e = cudaSuccess;
     if (E > 0) {
-        if ((e = get(R->k1, c->d_o_k1, E)) || (e = get(R->k2, c->d_o_k2, E)) || (e = get(R->cd, c->d_o_cd, E)) || (e = get(R->nrefs, c->d_o_nrefs, E)) ||
-            (e = get(R->sh, c->d_o_sh, 2 * E)) || (e = get(R->in, c->d_o_in, 2 * E)) || (e = get(R->k, c->d_o_k, E)) || (e = get(R->d, c->d_o_d, E)) ||
-            (e = get(R->n, c->d_o_n, E)) || (e = get(R->p1, c->d_o_p1, E)) || (e = get(R->mult, c->d_o_mult, E)) || (e = get(R->score, c->d_o_score, E)) ||
-            (e = get(R->err, c->d_o_err, E))) {
-            delete R;
-            return fail(c, EJB_ERR_CUDA, "download: %s", cudaGetErrorString(e));
-        }
-    } else {
-        R->k1.resize(1); R->k2.resize(1); R->cd.resize(1); R->nrefs.resize(1); R->sh.resize(2); R->in.resize(2); R->k.resize(1); R->d.resize(1);
-        R->n.resize(1); R->p1.resize(1); R->mult.resize(1); R->score.resize(1); R->err.resize(1);
+        const size_t e = (size_t)E;
+        CK(get(k1, c->d_o_k1.p, e * 4)); CK(get(k2, c->d_o_k2.p, e * 4)); CK(get(cd, c->d_o_cd.p, e * 4)); CK(get(nrefs, c->d_o_nrefs.p, e * 4));
+        CK(get(sh, c->d_o_sh.p, e * 8)); CK(get(in, c->d_o_in.p, e * 8)); CK(get(kk, c->d_o_k.p, e * 4)); CK(get(dd_, c->d_o_d.p, e * 4));
+        CK(get(nn, c->d_o_n.p, e * 4)); CK(get(p1, c->d_o_p1.p, e * 8)); CK(get(mult, c->d_o_mult.p, e * 8)); CK(get(score, c->d_o_score.p, e * 8));
+        CK(get(err, c->d_o_err.p, e));
     }
-    std::vector<int32_t> row_exact;
-    if ((e = get(R->labels, c->d_labels, N))) {
-        delete R;
-        return fail(c, EJB_ERR_CUDA, "download: %s", cudaGetErrorString(e));
-    }
-    row_exact.resize((size_t)std::max<int64_t>(N, 1));
     if (N > 0) {
-        e = cudaMemcpyAsync(row_exact.data(), c->din.row_exact, (size_t)N * 4, cudaMemcpyDeviceToHost, st);
-        if (e) { delete R; return fail(c, EJB_ERR_CUDA, "download: %s", cudaGetErrorString(e)); }
+        CK(get(labels, c->d_labels.p, (size_t)N * 4));
+        CK(get(row_exact, c->din.row_exact, (size_t)N * 4));
     }
-    e = cudaStreamSynchronize(st);
-    if (e) { delete R; return fail(c, EJB_ERR_CUDA, "download: %s", cudaGetErrorString(e)); }
+    CK(cudaStreamSynchronize(st));
     c->stats.ms_d2h = now_ms() - t0;
     // replay into the reference's EquivRel (join2.rs:45-54, 69-84) so that x/y/z match from_raw
     const double t1 = now_ms();
-    if (c->shard_world == 1) {
+    if (c->shard_world == 1 && N > 0) {
         ejbhost::EquivRel eq((int32_t)N);
-        for (int64_t i = 0; i < E; i++) eq.join(R->k1[(size_t)i], R->k2[(size_t)i]);
-        ejbhost::finish_join_merge(eq, row_exact.data(), N);
-        R->x = eq.x; R->y = eq.y; R->z = eq.z;
+        for (int64_t i = 0; i < E; i++) eq.join(k1[i], k2[i]);
+        ejbhost::finish_join_merge(eq, row_exact, N);
+        memcpy(ex, eq.x.data(), (size_t)N * 4);
+        memcpy(ey, eq.y.data(), (size_t)N * 4);
+        memcpy(ez, eq.z.data(), (size_t)N * 4);
     }
-    if (R->x.empty()) { R->x.resize(1); R->y.resize(1); R->z.resize(1); }
     c->stats.ms_replay = now_ms() - t1;
     int64_t errors = 0;
-    for (int64_t i = 0; i < E; i++) errors += R->err[(size_t)i];
+    for (int64_t i = 0; i < E; i++) errors += err[i];
     c->stats.errors = errors;
     out->n_edges = E;
-    out->edge_k1 = R->k1.data(); out->edge_k2 = R->k2.data(); out->edge_cd = R->cd.data(); out->edge_nrefs = R->nrefs.data();
-    out->edge_shares = R->sh.data(); out->edge_indeps = R->in.data(); out->edge_k = R->k.data(); out->edge_d = R->d.data(); out->edge_n = R->n.data();
-    out->edge_p1 = R->p1.data(); out->edge_mult = R->mult.data(); out->edge_score = R->score.data(); out->edge_err = R->err.data();
+    out->edge_k1 = k1; out->edge_k2 = k2; out->edge_cd = cd; out->edge_nrefs = nrefs;
+    out->edge_shares = sh; out->edge_indeps = in; out->edge_k = kk; out->edge_d = dd_; out->edge_n = nn;
+    out->edge_p1 = p1; out->edge_mult = mult; out->edge_score = score; out->edge_err = err;
     out->n_rows = N;
-    out->labels = R->labels.data();
-    out->eq_x = R->x.data(); out->eq_y = R->y.data(); out->eq_z = R->z.data();
+    out->labels = labels;
+    out->eq_x = ex; out->eq_y = ey; out->eq_z = ez;
     out->stats = c->stats;
-    out->opaque = R;
+    out->opaque = nullptr;
     return EJB_OK;
 }
 
 void ejb_result_free(ejb_ctx* c, ejb_result* out) {
-    (void)c;
-    if (!out) return;
-    delete reinterpret_cast<ResultOwner*>(out->opaque);
-    memset(out, 0, sizeof(*out));
+    (void)c;   // the arrays live in the context's pinned arena, reused by the next download
+    if (out) memset(out, 0, sizeof(*out));
 }
 
 int ejb_join(ejb_ctx* c, const ejb_params* p, const ejb_input* in, ejb_result* out) {

@@ -13,10 +13,11 @@ namespace ejb {
 // cd <= maxcd  &&  class labels differ (join_core.rs:32 — a pair already connected by
 // lexicographically smaller joins can never be in pot).
 // ------------------------------------------------------------------------------------------------
-struct RowTask {       // one row block of one sub-bucket
+struct RowTask {       // (part of) one row block of one sub-bucket, against every column block to its right
     int32_t sub;
     int32_t rb;
-    int64_t cta0;      // first CTA of this task inside the round
+    int64_t cta0;      // first CTA of this task inside the launch
+    int32_t row_lo, row_hi;   // local rows [row_lo, row_hi) of the block belong to this round's unit
 };
 
 template <int W1>
@@ -124,7 +125,8 @@ __global__ void __launch_bounds__(S1_THREADS) k_stage1(const SubBucket* __restri
         }
         rlab[i] = (int)s_row[NP * TILE + r];
     }
-    const int row_lim = sb.n - rb * TILE;  // valid local rows are < row_lim
+    const int row_lo = t.row_lo;
+    const int row_lim = min(sb.n - rb * TILE, t.row_hi);  // valid local rows are row_lo <= r < row_lim
     const int maxcd = sb.maxcd;
     unsigned long long evaluated = 0;
 
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(S1_THREADS) k_stage1(const SubBucket* __restri
         const uint32_t* sc = s_col[buf];
         const int col_lim = sb.n - cb * TILE;
         const bool diag = (cb == rb);
-        const bool full = !diag && row_lim >= TILE && col_lim >= TILE;
+        const bool full = !diag && row_lo == 0 && row_lim >= TILE && col_lim >= TILE;
         // two halves of 64 columns: the hit list holds at most 128 x 64 entries
         for (int half = 0; half < 2; half++) {
             if (full) {
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(S1_THREADS) k_stage1(const SubBucket* __restri
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int r = i * 16 + ty;
-                        const bool valid = r < row_lim && c < col_lim && (!diag || r < c);
+                        const bool valid = r >= row_lo && r < row_lim && c < col_lim && (!diag || r < c);
                         const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
                         if (valid && cd <= maxcd && rlab[i] != clab) {
                             const unsigned int h = atomicAdd(&s_nhits, 1u);
@@ -186,8 +188,15 @@ __global__ void __launch_bounds__(S1_THREADS) k_stage1(const SubBucket* __restri
                 if (half == 1) {
                     // prefetch the tile after next into the buffer just drained
                     if (it + 2 < ncb) issue(s_col[buf], s_cbs[it + 2], &s_bar[buf]);
-                    const int rr = min(TILE, row_lim), cc = min(TILE, col_lim);
-                    evaluated += diag ? (unsigned long long)rr * (rr - 1) / 2 : (unsigned long long)rr * cc;
+                    const long long hi = min(TILE, row_lim), lo = row_lo, cc = min(TILE, col_lim), nr = hi - lo;
+                    if (nr > 0) {
+                        if (!diag) evaluated += (unsigned long long)(nr * cc);
+                        else {   // pairs (r, c) with lo <= r < hi, r < c < cc
+                            const long long h2 = min(hi, cc);
+                            const long long n2 = max(h2 - lo, 0ll);
+                            evaluated += (unsigned long long)(n2 * (cc - 1) - (lo + h2 - 1) * n2 / 2);
+                        }
+                    }
                 }
                 if (nh) s_base = atomicAdd(&ctr->n_cand, (unsigned long long)nh);
             }

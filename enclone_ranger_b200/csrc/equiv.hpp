@@ -34,10 +34,16 @@ struct EquivRel {
 
 // join2.rs:69-84: sort (clonotype_id, class id) and join consecutive entries of one clonotype_id;
 // note that the joined values are CLASS IDS used as element ids (join2.rs:81).
+// Only clonotype_ids owning two or more rows can cause a join, so the sort is restricted to those
+// rows (same join sequence as sorting everything: ids ascending, class ids ascending inside an id).
 inline void finish_join_merge(EquivRel& eq, const int32_t* row_exact, int64_t n_rows) {
-    std::vector<std::pair<int64_t, int32_t>> ox;
-    ox.reserve((size_t)n_rows);
-    for (int64_t i = 0; i < n_rows; i++) ox.emplace_back((int64_t)row_exact[i], eq.class_id((int32_t)i));
+    int32_t max_id = -1;
+    for (int64_t i = 0; i < n_rows; i++) max_id = std::max(max_id, row_exact[i]);
+    std::vector<int32_t> cnt((size_t)max_id + 2, 0);
+    for (int64_t i = 0; i < n_rows; i++) cnt[(size_t)row_exact[i]]++;
+    std::vector<std::pair<int32_t, int32_t>> ox;
+    for (int64_t i = 0; i < n_rows; i++)
+        if (cnt[(size_t)row_exact[i]] >= 2) ox.emplace_back(row_exact[i], eq.class_id((int32_t)i));
     std::sort(ox.begin(), ox.end());
     size_t i = 0;
     while (i < ox.size()) {

@@ -21,7 +21,8 @@
  * unwinds across the ABI; ejb_last_error() gives a human-readable message; one
  * ejb_ctx is used from one thread at a time; all input pointers are caller-owned
  * HOST memory (pinned or pageable), read-only for the duration of the call; result
- * arrays are library-owned until ejb_result_free().  Absent Option<usize> values are
+ * arrays live in a pinned arena owned by the context and stay valid until ejb_result_free(),
+ * the next ejb_join / ejb_download on the same context, or ejb_destroy().  Absent Option<usize> values are
  * encoded as EJB_NONE (-1).
  */
 #ifndef ENCLONE_JOIN_B200_H
