@@ -217,59 +217,57 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
         if (hasdel) flags |= (m == 0) ? F_HASDEL_H : F_HASDEL_L;
         bool odd = false;
         const int nw = (L + 31) / 32;
-        for (int w = 0; w < 4 * W4; w++) {
-            uint32_t lo = 0, hi = 0, dm = 0, gp = 0, rlo = 0, rhi = 0, cm = 0, glo = 0, ghi = 0;
-            if (w < nw) {
-                const int p = w * 32 + lane;
-                int code = 0, dbit = 0, gbit = 0, rcode = 0, cbit = 0;
-                if (p < L) {
-                    const uint8_t b = tig[p];
-                    if (b == '-' && hasdel) gbit = 1;
-                    else if (!is_acgt(b)) odd = true;
-                    code = base2bit(b);
-                    if (p < vr) {
-                        cbit = 1;
-                        rcode = base2bit(vseg[p]);
-                    } else if (p >= L - jr) {
-                        // counted from the contig end: tig[L-1-pp] vs J[|J|-1-pp]   (join_one.rs:388-391)
-                        const long long pp = (long long)L - 1 - p;
-                        cbit = 1;
-                        rcode = base2bit(jseg[jlen - 1 - pp]);
-                    }
-                    dbit = cbit && (b != bit2base(rcode));
+        // lane w keeps word w of every plane (4 * W4 <= 32 words), so each plane is written with one coalesced store
+        uint32_t k_lo = 0, k_hi = 0, k_d = 0, k_gap = 0, k_glo = 0, k_ghi = 0, k_rlo = 0, k_rhi = 0, k_cm = 0;
+        for (int w = 0; w < nw && w < 4 * W4; w++) {
+            const int p = w * 32 + lane;
+            int code = 0, dbit = 0, gbit = 0, rcode = 0, cbit = 0, rid = 0;
+            if (p < L) {
+                const uint8_t b = tig[p];
+                if (b == '-' && hasdel) gbit = 1;
+                else if (!is_acgt(b)) odd = true;
+                code = base2bit(b);
+                if (p < vr) {
+                    cbit = 1;
+                    rcode = base2bit(vseg[p]);
+                } else if (p >= L - jr) {
+                    // counted from the contig end: tig[L-1-pp] vs J[|J|-1-pp]   (join_one.rs:388-391)
+                    const long long pp = (long long)L - 1 - p;
+                    cbit = 1;
+                    rcode = base2bit(jseg[jlen - 1 - pp]);
                 }
+                dbit = cbit && (b != bit2base(rcode));
                 if (m == 0) {
-                    int rid = 0;
                     if (p >= rF0 && p < rF1) rid = 1;
                     else if (p >= rC10 && p < rC11) rid = 2;
                     else if (p >= rC20 && p < rC21) rid = 3;
-                    glo = __ballot_sync(0xffffffffu, rid & 1);
-                    ghi = __ballot_sync(0xffffffffu, rid & 2);
                 }
-                lo = __ballot_sync(0xffffffffu, code & 1);
-                hi = __ballot_sync(0xffffffffu, code & 2);
-                dm = __ballot_sync(0xffffffffu, dbit);
-                gp = __ballot_sync(0xffffffffu, gbit);
-                rlo = __ballot_sync(0xffffffffu, rcode & 1);
-                rhi = __ballot_sync(0xffffffffu, rcode & 2);
-                cm = __ballot_sync(0xffffffffu, cbit);
-                tot += __popc(dm);
             }
-            if (lane == 0) {
-                rec32[(base_u4 + 0 * W4) * 4 + w] = lo;
-                rec32[(base_u4 + 1 * W4) * 4 + w] = hi;
-                rec32[(base_u4 + 2 * W4) * 4 + w] = dm;
-                if (gapbit) rec32[(base_u4 + 3 * W4) * 4 + w] = gp;
-                int o = 3 + gapbit;
-                if (m == 0) {
-                    rec32[(base_u4 + o * W4) * 4 + w] = glo;
-                    rec32[(base_u4 + (o + 1) * W4) * 4 + w] = ghi;
-                    o += 2;
-                }
-                rec32[(base_u4 + o * W4) * 4 + w] = rlo;
-                rec32[(base_u4 + (o + 1) * W4) * 4 + w] = rhi;
-                rec32[(base_u4 + (o + 2) * W4) * 4 + w] = cm;
+            const uint32_t lo = __ballot_sync(0xffffffffu, code & 1), hi = __ballot_sync(0xffffffffu, code & 2);
+            const uint32_t dm = __ballot_sync(0xffffffffu, dbit), gp = __ballot_sync(0xffffffffu, gbit);
+            const uint32_t rlo = __ballot_sync(0xffffffffu, rcode & 1), rhi = __ballot_sync(0xffffffffu, rcode & 2);
+            const uint32_t cm = __ballot_sync(0xffffffffu, cbit);
+            const uint32_t glo = __ballot_sync(0xffffffffu, rid & 1), ghi = __ballot_sync(0xffffffffu, rid & 2);
+            tot += __popc(dm);
+            if (lane == w) {
+                k_lo = lo; k_hi = hi; k_d = dm; k_gap = gp; k_glo = glo; k_ghi = ghi; k_rlo = rlo; k_rhi = rhi; k_cm = cm;
             }
+        }
+        if (lane < 4 * W4) {
+            uint32_t* r = rec32 + base_u4 * 4 + lane;
+            const int st = 4 * W4;
+            r[0] = k_lo;
+            r[st] = k_hi;
+            r[2 * st] = k_d;
+            int o = 3;
+            if (gapbit) r[(o++) * st] = k_gap;
+            if (m == 0) {
+                r[(o++) * st] = k_glo;
+                r[(o++) * st] = k_ghi;
+            }
+            r[o * st] = k_rlo;
+            r[(o + 1) * st] = k_rhi;
+            r[(o + 2) * st] = k_cm;
         }
         if (W4 == 0) {  // contig longer than the fast path: the byte-exact path handles it
             for (int p = lane; p < L; p += 32)
@@ -278,6 +276,8 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
         if (__any_sync(0xffffffffu, odd)) flags |= (m == 0) ? F_ODDBYTE_H : F_ODDBYTE_L;
         base_u4 += rec_planes(m, gapbit) * W4;
     }
+    __shared__ __align__(16) int32_t s_aux[8][AUX_INTS];
+    int32_t* const a = s_aux[(threadIdx.x >> 5) & 7];
     if (lane == 0) {
         rowq[q] = (int32_t)k;
         subq[q] = s;
@@ -292,7 +292,6 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
         if (in.ch_amino_off[ch] == -1) flags |= B_AMINO_TIG_H;
         const int64_t x0 = in.ex_cell_off[ex], ncells = in.ex_cell_off[ex + 1] - x0;
         const unsigned long long dmask = donor_mask[ex];
-        int32_t* a = aux + q * AUX_INTS;
         a[AX_FLAGS] = (int32_t)flags;
         a[AX_VSH] = in.seg_canon[in.row_vs[2 * k]];
         a[AX_VSL] = in.seg_canon[in.row_vs[2 * k + 1]];
@@ -320,6 +319,8 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
         a[AX_CHL] = cl;
         a[AX_PAD1] = a[AX_PAD2] = a[AX_PAD3] = 0;
     }
+    __syncwarp();
+    if (lane < AUX_INTS / 4) reinterpret_cast<uint4*>(aux + q * AUX_INTS)[lane] = reinterpret_cast<const uint4*>(a)[lane];
 }
 
 }  // namespace ejb

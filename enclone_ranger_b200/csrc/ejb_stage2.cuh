@@ -158,8 +158,46 @@ __device__ __forceinline__ void ld4(const uint4* p, uint32_t* o) {
 //     x21 = (t2 != r1) on cmp1, x12 = (t1 != r2) on cmp2;  A0 = popc(d1&x21) ... (join_one.rs:343-429)
 template <int G>
 __device__ __forceinline__ void s2_planes(const S2Ctx& X, const SubBucket& sb, uint32_t q1, uint32_t q2, int g, bool active, bool nrefs1,
-                                          unsigned int gmask, uint32_t* r) {
+                                          unsigned int gmask, int tot1, int tot2, uint32_t* r) {
     uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+    // Two references: nearly every such candidate dies on the degradation test (join_one.rs:434-440), which only
+    // needs T01 = popc(t2 != r1 on cmp1) and T10 = popc(t1 != r2 on cmp2) — evaluate that first and stop early.
+    if (active && !nrefs1 && !X.tuple_mode) {
+        uint32_t tt = 0;   // T01 | T10 << 16
+        const uint4* r1 = X.rowstore + sb.rs_off + (int64_t)(q1 - sb.q0) * sb.rec_u4;
+        const uint4* r2 = X.rowstore + sb.rs_off + (int64_t)(q2 - sb.q0) * sb.rec_u4;
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            const int W4 = m ? sb.W4l : sb.W4h;
+            const int gapbit = (sb.gap >> m) & 1;
+            const int off = m ? rec_planes(0, sb.gap & 1) * sb.W4h : 0;
+            if (g < W4) {
+                uint32_t al[4], ah[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bg[4] = {0, 0, 0, 0}, arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
+                ld4(r1 + off + g, al); ld4(r1 + off + W4 + g, ah);
+                ld4(r2 + off + g, bl); ld4(r2 + off + W4 + g, bh);
+                if (gapbit) { ld4(r1 + off + 3 * W4 + g, ag); ld4(r2 + off + 3 * W4 + g, bg); }
+                const int ro = off + (3 + gapbit + (m == 0 ? 2 : 0)) * W4;
+                ld4(r1 + ro + g, arl); ld4(r1 + ro + W4 + g, arh); ld4(r1 + ro + 2 * W4 + g, ac);
+                ld4(r2 + ro + g, brl); ld4(r2 + ro + W4 + g, brh); ld4(r2 + ro + 2 * W4 + g, bc);
+                int T01 = 0, T10 = 0;
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    T01 += __popc(((bl[w] ^ arl[w]) | (bh[w] ^ arh[w]) | bg[w]) & ac[w]);
+                    T10 += __popc(((al[w] ^ brl[w]) | (ah[w] ^ brh[w]) | ag[w]) & bc[w]);
+                }
+                tt += (uint32_t)T01 | ((uint32_t)T10 << 16);
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) tt += __shfl_xor_sync(gmask, tt, o);
+        const int T01 = (int)(tt & 0xffff), T10 = (int)(tt >> 16);
+        if (abs(tot1 - T10) > X.P.max_degradation || abs(T01 - tot2) > X.P.max_degradation) {
+            active = false;          // rejected: phase 2 repeats the test on these totals and drops the candidate
+            n1 = (uint32_t)T01 << 16;
+            n3 = (uint32_t)T10 << 16;
+        }
+    }
+    const bool early_dead = !active && (n1 | n3) != 0;
     if (active) {
         if (g < sb.W1) {
             const uint32_t* b = X.cdr3w + sb.s1_off;
@@ -260,6 +298,7 @@ __device__ __forceinline__ void s2_planes(const S2Ctx& X, const SubBucket& sb, u
             n3 += __shfl_xor_sync(gmask, n3, o);
         }
     }
+    (void)early_dead;
     r[0] = pk0; r[1] = pk1; r[2] = pk2; r[3] = pk3; r[4] = n0; r[5] = n1; r[6] = n2; r[7] = n3;
 }
 
@@ -302,6 +341,7 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
         const bool nrefs1 = (a10.y == a20.y && a10.z == a20.z && a10.w == a20.w && a1[AX_JSL] == a2[AX_JSL]);
         const bool fast = valid && ((f1 | f2) & F_SLOWMASK) == 0 && sb.W1 > 0 && sb.W4h > 0 && sb.W4l > 0;
         const bool wide = fast && (sb.W4h > 4 || sb.W4l > 4);
+        const int tot1 = a1[AX_TOT], tot2 = a2[AX_TOT];
         // ---- phase 1 ----
         if (!__any_sync(0xffffffffu, wide)) {
 #pragma unroll 1
@@ -311,8 +351,9 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
                 const int gsid = __shfl_sync(0xffffffffu, sid, src);
                 const bool gfast = __shfl_sync(0xffffffffu, (int)fast, src) != 0, gn1 = __shfl_sync(0xffffffffu, (int)nrefs1, src) != 0;
                 const SubBucket gsb = X.subs[gsid];
+                const int gt1 = __shfl_sync(0xffffffffu, tot1, src), gt2 = __shfl_sync(0xffffffffu, tot2, src);
                 uint32_t r[8];
-                s2_planes<4>(X, gsb, gq1, gq2, lane & 3, gfast, gn1, 0xfu << (lane & 28), r);
+                s2_planes<4>(X, gsb, gq1, gq2, lane & 3, gfast, gn1, 0xfu << (lane & 28), gt1, gt2, r);
                 if ((lane & 3) == 0) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) s_res[wib][src][i] = r[i];
@@ -326,8 +367,9 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
                 const int gsid = __shfl_sync(0xffffffffu, sid, src);
                 const bool gfast = __shfl_sync(0xffffffffu, (int)fast, src) != 0, gn1 = __shfl_sync(0xffffffffu, (int)nrefs1, src) != 0;
                 const SubBucket gsb = X.subs[gsid];
+                const int gt1 = __shfl_sync(0xffffffffu, tot1, src), gt2 = __shfl_sync(0xffffffffu, tot2, src);
                 uint32_t r[8];
-                s2_planes<8>(X, gsb, gq1, gq2, lane & 7, gfast, gn1, 0xffu << (lane & 24), r);
+                s2_planes<8>(X, gsb, gq1, gq2, lane & 7, gfast, gn1, 0xffu << (lane & 24), gt1, gt2, r);
                 if ((lane & 7) == 0) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) s_res[wib][src][i] = r[i];
@@ -344,7 +386,6 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
                 const uint32_t* r = s_res[wib][lane];
                 const int cd1 = (int)(r[0] & 0xffff), cd2 = (int)(r[0] >> 16);
                 const int diffs = (int)(r[2] & 0xffff);
-                const int tot1 = a1[AX_TOT], tot2 = a2[AX_TOT];
                 // region differences are usable when both rows: chain 0 is the only left chain, seq_del_amino is the
                 // contig, well-formed ranges, and identical feature starts
                 RegionDiffs rg;
