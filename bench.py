@@ -5,8 +5,10 @@
 
 One "step" = one pass of the hot path (bucketer -> pair kernels -> forest -> union-find) over the whole
 synthetic repertoire.  N=1 workload: BASELINE.json configs[1] (1M-cell heavy-tailed human BCR repertoire).
-N>1: the same repertoire, buckets sharded over N ranks by the library (strong scaling), per-rank edge lists
-gathered to rank 0 over NCCL.
+N>1 (weak scaling): the same clone-size law at N x 1M cells (N=8 ~ configs[4]); rank 0 generates the
+repertoire, whole lens-buckets are assigned to ranks by pair count (LPT) and each rank receives, uploads and
+joins only its buckets — no collective on the data path; the per-rank edge lists are gathered GPU-to-GPU to
+rank 0 over NCCL and merged there.
 
   value   pairs/s with inputs resident in HBM (ejb_run), device time from CUDA events on the launching stream
   e2e     pairs/s through ejb_join with HOST (pinned) buffers: H2D + run + D2H + EquivRel replay in the timed region
@@ -157,7 +159,7 @@ def run_reference_arm(args, rank):
     val = pairs / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 popc + f64 score",
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 popc + f64 score",
         "data": "synthetic", "config": {"workload": WORKLOAD, "timed": "CPU restatement of join_exacts (oracle port of the Rust reference; rustc/cargo absent)",
                                           "sample": desc},
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc},
@@ -200,10 +202,33 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from enclone_ranger_b200 import multi
+    base_cells = args.cells if args.cells is not None else 1000000
     t_gen = time.time()
-    rep = E.generate(CONFIG_INDEX, n_cells=args.cells)
-    inp = rep.to_join_input()      # numpy-owned copies (host buffers of the caller)
-    rep.close()
+    full_rows, row_exact_full = 0, None
+    if world == 1:
+        rep = E.generate(CONFIG_INDEX, n_cells=base_cells)
+        inp = rep.to_join_input()      # numpy-owned copies (host buffers of the caller)
+        rep.close()
+        my_rows = None
+        full_rows, row_exact_full = inp.n_rows, inp.a["row_exact"]
+    else:
+        parts = None
+        if rank == 0:
+            rep = E.generate(CONFIG_INDEX, n_cells=base_cells * world)
+            full = rep.to_join_input()
+            rep.close()
+            full_rows, row_exact_full = full.n_rows, full.a["row_exact"].copy()
+            parts = []
+            for rows in multi.partition_buckets(full, world):
+                sub, _ = full.subset_rows(rows)
+                parts.append((sub, rows))
+            del full
+        inp, my_rows = multi.scatter_parts(parts, dev)
+        del parts
+        fr = torch.tensor([full_rows], dtype=torch.int64, device=dev)
+        dist.broadcast(fr, src=0)
+        full_rows = int(fr.item())
     t_gen = time.time() - t_gen
     params = E.default_params(True)
     # pin the caller's host buffers (the e2e contract copies from pinned host memory)
@@ -213,18 +238,18 @@ def main():
         if arr.nbytes >= 1 << 16:
             if int(cudart.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)) == 0:
                 pinned.append(arr)
-    ctx = E.JoinContext(device=local_rank, rank=rank, world=world)
+    ctx = E.JoinContext(device=local_rank)
     peaks = ctx.measure_peaks() if rank == 0 else None
+    rows_dev = torch.from_numpy(my_rows).to(dev) if my_rows is not None else None
 
-    def gather_edges_device(res):
-        """rank-local (k1,k2) -> rank 0 over NCCL, merged by sorting the 64-bit (k1<<32|k2) keys on the device"""
-        key = torch.from_numpy(res.edge_k1.astype(np.int64) << 32 | res.edge_k2.astype(np.int64)).to(dev)
+    def gather_keys(key):
+        """per-rank sorted 64-bit (k1<<32|k2) keys (global row ids) -> rank 0 over NCCL, merged by a device sort"""
         if world == 1:
             return key
         n = torch.tensor([key.numel()], dtype=torch.int64, device=dev)
         sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
         dist.all_gather(sizes, n)
-        sizes = [int(s.item()) for s in sizes]
+        sizes = [int(x.item()) for x in sizes]
         mx = max(max(sizes), 1)
         pad = torch.full((mx,), -1, dtype=torch.int64, device=dev)
         pad[: key.numel()] = key
@@ -232,8 +257,7 @@ def main():
         dist.gather(pad, bufs, dst=0)
         if rank != 0:
             return None
-        allk = torch.cat([bufs[r][: sizes[r]] for r in range(world)])
-        return torch.sort(allk).values
+        return torch.sort(torch.cat([bufs[r][: sizes[r]] for r in range(world)])).values
 
     # ---------------- device-resident arm: value ----------------
     ctx.upload(params, inp)
@@ -241,7 +265,8 @@ def main():
     def step_resident():
         st = ctx.run()
         if world > 1:
-            gather_edges_device(ctx.download())
+            k1, k2 = ctx.device_edges()     # device pointers, no host round trip
+            gather_keys((rows_dev[k1.long()] << 32) | rows_dev[k2.long()])
         return st
 
     for _ in range(args.warmup):
@@ -256,26 +281,28 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3 / args.steps
     clocks = sampler.stop() if sampler else None
-    # per-step time: CUDA-event device time at N=1; at N>1 the slowest rank's wall time per step (run + gather)
+    # per-step time: CUDA-event device time at N=1; at N>1 the slowest rank's wall time per step (run + gather + merge)
     t_local = (sum(dev_ms) / len(dev_ms)) if world == 1 else wall_ms
+    pairs = stats["pairs_scored"]
     if world > 1:
         t = torch.tensor([t_local], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_step = float(t.item())
-        ln = torch.tensor([launches], dtype=torch.int64, device=dev)
+        ln = torch.tensor([launches, pairs], dtype=torch.int64, device=dev)
         dist.all_reduce(ln)
-        launches = int(ln.item())
+        launches, pairs = int(ln[0].item()), int(ln[1].item())
     else:
         t_step = t_local
-    pairs = stats["pairs_scored"]
 
     # ---------------- end-to-end arm: host buffers through ejb_join ----------------
     def step_e2e():
         res = ctx.join(params, inp)
-        merged = gather_edges_device(res)
-        if world > 1 and rank == 0:
-            k = merged.cpu().numpy()
-            E.equiv_replay(inp.n_rows, (k >> 32).astype(np.int32), (k & 0xffffffff).astype(np.int32), inp.a["row_exact"])
+        if world > 1:
+            key = torch.from_numpy(my_rows[res.edge_k1].astype(np.int64) << 32 | my_rows[res.edge_k2].astype(np.int64)).to(dev)
+            merged = gather_keys(key)
+            if rank == 0:   # raw_joins of the whole repertoire + the EquivRel finish_join returns
+                k = merged.cpu().numpy()
+                E.equiv_replay(full_rows, (k >> 32).astype(np.int32), (k & 0xffffffff).astype(np.int32), row_exact_full)
         return res
 
     step_e2e()
@@ -310,13 +337,13 @@ def main():
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             hbm_peak = 6650.0
-        alg_bytes = packed_bytes + 8.0 * stats["joins"] + 4.0 * inp.n_rows
+        alg_bytes = packed_bytes + 8.0 * stats["joins"] + 4.0 * inp.n_rows   # rank 0's share at N > 1
         line = {
             "metric": METRIC, "value": pairs / (t_step / 1e3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 popc + f64 score", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.cells is None else f"DEBUG {args.cells}-cell variant of configs[1]", "cells": int(inp.n_cells), "rows": int(inp.n_rows),
+            "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 popc + f64 score", "data": "synthetic",
+            "config": {"workload": (WORKLOAD if world == 1 else f"configs[1] clone-size law at {world} x 1M cells, lens-buckets partitioned over {world} ranks") if args.cells is None else f"DEBUG {args.cells}-cell-per-GPU variant of configs[1]", "cells": int(base_cells * world), "rows": int(full_rows), "rows_rank0": int(inp.n_rows),
                        "pairs_scored": int(pairs), "pairs_lens_buckets": int(stats["pairs_lens"]), "sub_buckets": int(stats["n_subbuckets"]),
-                       "parallelism": f"bucket-sharded x{world}" if world > 1 else "single GPU",
+                       "parallelism": f"bucket-sharded x{world}, weak scaling (1M cells per GPU)" if world > 1 else "single GPU",
                        "l2": f"inputs ({stats['h2d_bytes'] / 1e6:.0f} MB raw + packed row store) exceed the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the library's launching stream (ejb_stats.ms_device_total)" if world == 1 else "wall clock between device syncs, max over ranks",
                        "wall_ms_per_step": wall_ms, "generate_s": t_gen},

@@ -1150,6 +1150,16 @@ int ejb_join(ejb_ctx* c, const ejb_params* p, const ejb_input* in, ejb_result* o
     return EJB_OK;
 }
 
+int ejb_device_edges(ejb_ctx* c, int64_t* n_edges, const int32_t** d_k1, const int32_t** d_k2, const int32_t** d_labels) {
+    if (!c) return EJB_ERR_INVALID;
+    if (!c->have_run) return fail(c, EJB_ERR_INVALID, "ejb_device_edges without ejb_run");
+    if (n_edges) *n_edges = c->n_final;
+    if (d_k1) *d_k1 = c->n_final > 0 ? c->d_o_k1.as<const int32_t>() : nullptr;
+    if (d_k2) *d_k2 = c->n_final > 0 ? c->d_o_k2.as<const int32_t>() : nullptr;
+    if (d_labels) *d_labels = c->d_labels.as<const int32_t>();
+    return EJB_OK;
+}
+
 int ejb_last_stats(const ejb_ctx* c, ejb_stats* out) {
     if (!c || !out) return EJB_ERR_INVALID;
     *out = c->stats;

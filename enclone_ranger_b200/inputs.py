@@ -105,6 +105,43 @@ class JoinInput:
             b[n] = self.a[n][two]
         return JoinInput(**b)
 
+    def subset_rows(self, idx):
+        """Rows `idx` (ascending) with the exact / chain / cell tables compacted to what those rows reference.
+        Seg and ref tables are kept whole (they are small).  Returns (JoinInput, old exact id of each new exact)."""
+        idx = np.asarray(idx, dtype=np.int64)
+        a = self.a
+        two = np.stack([2 * idx, 2 * idx + 1], axis=1).reshape(-1)
+        b = dict(a)
+        for n in ("row_nchains",):
+            b[n] = a[n][idx]
+        for n in ("row_len", "row_has_del", "row_vs", "row_js", "row_cdr3_len", "row_exact_col"):
+            b[n] = a[n][two]
+        # contig / CDR3 bytes: gather the referenced spans
+        def gather_spans(off, ln, data):
+            ln = ln.astype(np.int64)
+            new_off = np.concatenate([[0], np.cumsum(ln)])[:-1]
+            total = int(ln.sum())
+            src = np.repeat(off - new_off, ln) + np.arange(total, dtype=np.int64)
+            return new_off.astype(np.int64), data[src] if total else data[:0]
+        b["row_tig_off"], b["tig_bytes"] = gather_spans(a["row_tig_off"][two], b["row_len"] * (np.repeat(b["row_nchains"], 2) > np.tile([0, 1], len(idx))), a["tig_bytes"])
+        b["row_cdr3_off"], b["cdr3_bytes"] = gather_spans(a["row_cdr3_off"][two], b["row_cdr3_len"] * (np.repeat(b["row_nchains"], 2) > np.tile([0, 1], len(idx))), a["cdr3_bytes"])
+        # exacts
+        old_ex = a["row_exact"][idx]
+        used, inv = np.unique(old_ex, return_inverse=True)
+        b["row_exact"] = inv.astype(np.int32)
+        def compact(offs, arrays):
+            ln = (offs[used + 1] - offs[used]).astype(np.int64)
+            new_off = np.concatenate([[0], np.cumsum(ln)])
+            total = int(new_off[-1])
+            src = np.repeat(offs[used] - new_off[:-1], ln) + np.arange(total, dtype=np.int64)
+            return new_off.astype(np.int64), {n: a[n][src] for n in arrays}, src
+        b["ex_chain_off"], ch, _ = compact(a["ex_chain_off"], ["ch_left", "ch_c_ref", "ch_v_ref", "ch_u_ref", "ch_fr1_start", "ch_cdr1_start",
+                                                                 "ch_fr2_start", "ch_cdr2_start", "ch_fr3_start", "ch_hcomp", "ch_amino_off", "ch_amino_len"])
+        b.update(ch)
+        b["ex_cell_off"], ce, _ = compact(a["ex_cell_off"], ["cell_donor", "cell_barcode"])
+        b.update(ce)
+        return JoinInput(**b), used
+
     def nbytes(self):
         return int(sum(v.nbytes for v in self.a.values()))
 

@@ -154,6 +154,22 @@ class JoinContext:
         self.L.ejb_result_free(self.h, C.byref(r))
         return out
 
+    def device_edges(self):
+        """(k1, k2) of the last run() as zero-copy torch CUDA tensors (valid until the next run())."""
+        import torch
+        n = C.c_int64()
+        k1, k2 = C.c_void_p(), C.c_void_p()
+        self.L.ejb_device_edges.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
+        self._ck(self.L.ejb_device_edges(self.h, C.byref(n), C.byref(k1), C.byref(k2), None))
+        if n.value == 0:
+            e = torch.zeros(0, dtype=torch.int32, device="cuda")
+            return e, e.clone()
+
+        class _Dev:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, True), "version": 2}
+        return torch.as_tensor(_Dev(k1.value, n.value), device="cuda"), torch.as_tensor(_Dev(k2.value, n.value), device="cuda")
+
     def p1_batch(self, k, d, n):
         k = np.ascontiguousarray(k, dtype=np.int32)
         d = np.ascontiguousarray(d, dtype=np.int32)

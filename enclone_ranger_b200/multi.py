@@ -57,3 +57,87 @@ def gather_edges(local, device=None, group=None, dst=0):
         return None
     parts = [_unpack(bufs[r][: sizes[r]].cpu().numpy()) for r in range(world)]
     return merge_edge_parts(parts)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Host-side bucket partitioning: each rank receives (and uploads) only the rows of the buckets it owns.
+# ------------------------------------------------------------------------------------------------------------
+def bucket_ids(inp):
+    """Bucket id of every row: maximal runs of equal `lens` (enclone/src/join.rs:68-88)."""
+    a = inp.a
+    n = inp.n_rows
+    lens = a["row_len"].reshape(-1, 2)
+    nch = a["row_nchains"]
+    head = np.ones(n, dtype=bool)
+    if n > 1:
+        head[1:] = (lens[1:] != lens[:-1]).any(axis=1) | (nch[1:] != nch[:-1])
+    return np.cumsum(head) - 1
+
+
+def partition_buckets(inp, world):
+    """Longest-processing-time assignment of whole buckets to `world` ranks by pair count.
+    Returns a list of ascending row-index arrays (rows of 1-chain buckets, which never join, are dropped)."""
+    bucket = bucket_ids(inp)
+    nb = int(bucket[-1]) + 1 if inp.n_rows else 0
+    two = inp.a["row_nchains"] == 2
+    c3 = inp.a["row_cdr3_len"].reshape(-1, 2)
+    key = np.stack([bucket[two], c3[two, 0], c3[two, 1]], axis=1)
+    uniq, cnt = np.unique(key, axis=0, return_counts=True)
+    cost = np.zeros(nb, dtype=np.float64)
+    np.add.at(cost, uniq[:, 0], cnt.astype(np.float64) * (cnt - 1) / 2 + 64.0 * cnt)
+    # buckets taken out of their neighbourhood must not fuse with another run of the same lens
+    lens = inp.a["row_len"].reshape(-1, 2)
+    first = np.nonzero(np.diff(np.concatenate([[-1], bucket])))[0]
+    lk = (lens[first, 0].astype(np.int64) << 32) | lens[first, 1].astype(np.int64) | (inp.a["row_nchains"][first].astype(np.int64) << 60)
+    if len(np.unique(lk)) != len(lk):
+        raise ValueError("equal lens occur in several runs (unsorted info); use in-library sharding (ejb_set_shard) instead")
+    order = np.argsort(-cost, kind="stable")
+    load = np.zeros(world)
+    owner = np.full(nb, -1, dtype=np.int64)
+    for b in order:
+        if cost[b] <= 0:
+            continue
+        r = int(np.argmin(load))
+        owner[b] = r
+        load[r] += cost[b]
+    row_owner = owner[bucket]
+    return [np.nonzero(row_owner == r)[0] for r in range(world)]
+
+
+def scatter_parts(parts, device, src=0, group=None):
+    """rank `src` holds `parts` = list (one per rank) of (JoinInput, global_rows); every rank gets its own.
+    Arrays travel as byte tensors over the process group (NCCL: device tensors)."""
+    from .inputs import JoinInput, _FIELDS
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    names = list(_FIELDS.keys()) + ["__rows__"]
+    mine = None
+    for r in range(world):
+        if rank == src:
+            inp, rows = parts[r]
+            arrs = {n: inp.a[n] for n in _FIELDS}
+            arrs["__rows__"] = np.asarray(rows, dtype=np.int64)
+            sizes = torch.tensor([arrs[n].nbytes for n in names], dtype=torch.int64, device=device)
+        else:
+            sizes = torch.zeros(len(names), dtype=torch.int64, device=device)
+        if r == src:
+            if rank == src:
+                mine = {n: arrs[n] for n in names}
+            continue
+        if rank == src:
+            dist.send(sizes, dst=r, group=group)
+            for n in names:
+                if arrs[n].nbytes:
+                    dist.send(torch.from_numpy(np.ascontiguousarray(arrs[n]).view(np.uint8).reshape(-1).copy()).to(device), dst=r, group=group)
+        elif rank == r:
+            dist.recv(sizes, src=src, group=group)
+            mine = {}
+            for n, sz in zip(names, sizes.tolist()):
+                dt = np.int64 if n == "__rows__" else _FIELDS[n]
+                if sz:
+                    t = torch.empty(int(sz), dtype=torch.uint8, device=device)
+                    dist.recv(t, src=src, group=group)
+                    mine[n] = t.cpu().numpy().view(dt).copy()
+                else:
+                    mine[n] = np.zeros(0, dtype=dt)
+    rows = mine.pop("__rows__")
+    return JoinInput(**mine), rows

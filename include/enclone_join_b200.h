@@ -277,6 +277,11 @@ int ejb_set_capacity(ejb_ctx* ctx, unsigned long long cand_cap, unsigned long lo
 int ejb_equiv_replay(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64_t n_edges,
                      const int32_t* row_exact, int32_t* x, int32_t* y, int32_t* z, int32_t* labels);
 
+/* Device-resident result of the last ejb_run (valid until the next ejb_run on this context): final edge
+ * list in raw_joins order and the canonical labels, as DEVICE pointers — lets a multi-GPU caller gather the
+ * per-rank edges GPU-to-GPU (NCCL) without a host round trip.                                       */
+int ejb_device_edges(ejb_ctx* ctx, int64_t* n_edges, const int32_t** d_k1, const int32_t** d_k2, const int32_t** d_labels);
+
 int ejb_abi_version(void);
 /* sizeof(ejb_params), sizeof(ejb_input), sizeof(ejb_stats), sizeof(ejb_result) as the library was
  * compiled — lets a binding verify its struct mirrors.                                          */
