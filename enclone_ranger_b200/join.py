@@ -102,6 +102,7 @@ class JoinContext:
 
     def __init__(self, device=0, rank=0, world=1, cand_cap=0, pair_budget=0):
         self.L = _abi.load_join()
+        self.device = int(device)
         self.h = C.c_void_p()
         dev = (C.c_int * 1)(int(device))
         rc = self.L.ejb_create(C.byref(self.h), dev, 1)
@@ -162,13 +163,14 @@ class JoinContext:
         self.L.ejb_device_edges.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
         self._ck(self.L.ejb_device_edges(self.h, C.byref(n), C.byref(k1), C.byref(k2), None))
         if n.value == 0:
-            e = torch.zeros(0, dtype=torch.int32, device="cuda")
+            e = torch.zeros(0, dtype=torch.int32, device=f"cuda:{self.device}")
             return e, e.clone()
 
         class _Dev:
             def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, True), "version": 2}
-        return torch.as_tensor(_Dev(k1.value, n.value), device="cuda"), torch.as_tensor(_Dev(k2.value, n.value), device="cuda")
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        dev = f"cuda:{self.device}"
+        return torch.as_tensor(_Dev(k1.value, n.value), device=dev), torch.as_tensor(_Dev(k2.value, n.value), device=dev)
 
     def p1_batch(self, k, d, n):
         k = np.ascontiguousarray(k, dtype=np.int32)

@@ -108,6 +108,31 @@ def test_sharded_ranks_union_to_the_full_result():
     assert np.array_equal(eq.x, want["eq_x"]) and np.array_equal(eq.y, want["eq_y"]) and np.array_equal(lab, want["labels"])
 
 
+def test_device_resident_edges_and_host_partitioning(gpu_ctx):
+    """The multi-GPU data path on one GPU: whole buckets partitioned on the host (LPT), each part joined on its own,
+    device-resident (k1,k2) mapped back to global rows, merged -> equals the oracle on the whole input."""
+    import torch
+    from enclone_ranger_b200.multi import partition_buckets
+    rep = E.generate(1, n_cells=30000, seed=23)
+    inp = rep.to_join_input()
+    p = E.default_params(True)
+    want = pyoracle.run(p, inp.c_ptr(), threads=0)
+    keys = []
+    for rows in partition_buckets(inp, 3):
+        sub, _ = inp.subset_rows(rows)
+        gpu_ctx.upload(p, sub)
+        gpu_ctx.run()
+        k1, k2 = gpu_ctx.device_edges()
+        host = gpu_ctx.download()
+        assert np.array_equal(k1.cpu().numpy(), host.edge_k1) and np.array_equal(k2.cpu().numpy(), host.edge_k2)
+        r = torch.from_numpy(rows).to(k1.device)
+        keys.append((r[k1.long()] << 32) | r[k2.long()])
+    k = torch.sort(torch.cat(keys)).values.cpu().numpy()
+    assert np.array_equal((k >> 32).astype(np.int32), want["edge_k1"]) and np.array_equal((k & 0xffffffff).astype(np.int32), want["edge_k2"])
+    eq, lab = E.equiv_replay(inp.n_rows, (k >> 32).astype(np.int32), (k & 0xffffffff).astype(np.int32), inp.a["row_exact"])
+    assert np.array_equal(eq.y, want["eq_y"]) and np.array_equal(lab, want["labels"])
+
+
 def test_properties_at_scale(gpu_ctx):
     """Size-independent properties where the oracle is too slow: sorted forest, one bucket per edge,
     labels == connected components of edges + clonotype_id merge, idempotent under re-run."""
