@@ -219,38 +219,52 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
         const int nw = (L + 31) / 32;
         // lane w keeps word w of every plane (4 * W4 <= 32 words), so each plane is written with one coalesced store
         uint32_t k_lo = 0, k_hi = 0, k_d = 0, k_gap = 0, k_glo = 0, k_ghi = 0, k_rlo = 0, k_rhi = 0, k_cm = 0;
-        for (int w = 0; w < nw && w < 4 * W4; w++) {
-            const int p = w * 32 + lane;
-            int code = 0, dbit = 0, gbit = 0, rcode = 0, cbit = 0, rid = 0;
-            if (p < L) {
-                const uint8_t b = tig[p];
-                if (b == '-' && hasdel) gbit = 1;
-                else if (!is_acgt(b)) odd = true;
-                code = base2bit(b);
-                if (p < vr) {
-                    cbit = 1;
-                    rcode = base2bit(vseg[p]);
-                } else if (p >= L - jr) {
-                    // counted from the contig end: tig[L-1-pp] vs J[|J|-1-pp]   (join_one.rs:388-391)
-                    const long long pp = (long long)L - 1 - p;
-                    cbit = 1;
-                    rcode = base2bit(jseg[jlen - 1 - pp]);
-                }
-                dbit = cbit && (b != bit2base(rcode));
-                if (m == 0) {
-                    if (p >= rF0 && p < rF1) rid = 1;
-                    else if (p >= rC10 && p < rC11) rid = 2;
-                    else if (p >= rC20 && p < rC21) rid = 3;
+        const int nwords = min(nw, 4 * W4);
+        for (int w0 = 0; w0 < nwords; w0 += 8) {
+            // batch the byte loads of 8 words (contig + reference) before the ballots: 16 independent loads in flight
+            uint8_t tb[8], rb[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int p = (w0 + i) * 32 + lane;
+                tb[i] = 0;
+                rb[i] = 0;
+                if (w0 + i < nwords && p < L) {
+                    tb[i] = tig[p];
+                    if (p < vr) rb[i] = vseg[p];
+                    else if (p >= L - jr) rb[i] = jseg[jlen - 1 - ((long long)L - 1 - p)];   // tig[L-1-pp] vs J[|J|-1-pp], join_one.rs:388-391
                 }
             }
-            const uint32_t lo = __ballot_sync(0xffffffffu, code & 1), hi = __ballot_sync(0xffffffffu, code & 2);
-            const uint32_t dm = __ballot_sync(0xffffffffu, dbit), gp = __ballot_sync(0xffffffffu, gbit);
-            const uint32_t rlo = __ballot_sync(0xffffffffu, rcode & 1), rhi = __ballot_sync(0xffffffffu, rcode & 2);
-            const uint32_t cm = __ballot_sync(0xffffffffu, cbit);
-            const uint32_t glo = __ballot_sync(0xffffffffu, rid & 1), ghi = __ballot_sync(0xffffffffu, rid & 2);
-            tot += __popc(dm);
-            if (lane == w) {
-                k_lo = lo; k_hi = hi; k_d = dm; k_gap = gp; k_glo = glo; k_ghi = ghi; k_rlo = rlo; k_rhi = rhi; k_cm = cm;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int w = w0 + i;
+                if (w >= nwords) break;   // warp-uniform
+                const int p = w * 32 + lane;
+                int code = 0, dbit = 0, gbit = 0, rcode = 0, cbit = 0, rid = 0;
+                if (p < L) {
+                    const uint8_t b = tb[i];
+                    if (b == '-' && hasdel) gbit = 1;
+                    else if (!is_acgt(b)) odd = true;
+                    code = base2bit(b);
+                    if (p < vr || p >= L - jr) {
+                        cbit = 1;
+                        rcode = base2bit(rb[i]);
+                    }
+                    dbit = cbit && (b != bit2base(rcode));
+                    if (m == 0) {
+                        if (p >= rF0 && p < rF1) rid = 1;
+                        else if (p >= rC10 && p < rC11) rid = 2;
+                        else if (p >= rC20 && p < rC21) rid = 3;
+                    }
+                }
+                const uint32_t lo = __ballot_sync(0xffffffffu, code & 1), hi = __ballot_sync(0xffffffffu, code & 2);
+                const uint32_t dm = __ballot_sync(0xffffffffu, dbit), gp = __ballot_sync(0xffffffffu, gbit);
+                const uint32_t rlo = __ballot_sync(0xffffffffu, rcode & 1), rhi = __ballot_sync(0xffffffffu, rcode & 2);
+                const uint32_t cm = __ballot_sync(0xffffffffu, cbit);
+                const uint32_t glo = __ballot_sync(0xffffffffu, rid & 1), ghi = __ballot_sync(0xffffffffu, rid & 2);
+                tot += __popc(dm);
+                if (lane == w) {
+                    k_lo = lo; k_hi = hi; k_d = dm; k_gap = gp; k_glo = glo; k_ghi = ghi; k_rlo = rlo; k_rhi = rhi; k_cm = cm;
+                }
             }
         }
         if (lane < 4 * W4) {
