@@ -464,6 +464,7 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     if (d.n_seg_bytes < 0 || d.n_ref_bytes < 0) return fail(c, EJB_ERR_INVALID, "negative seg/ref byte count");
     // content-canonical seg ids: DnaString equality is by content (join_one.rs:331)
     std::vector<int32_t> canon((size_t)std::max<int64_t>(in->n_segs, 1), 0);
+    std::vector<uint8_t> seg_canon_bytes((size_t)std::max<int64_t>(d.n_seg_bytes, 1), 'A');   // DnaString content: upper-case ACGT, anything else -> A
     {
         std::map<std::string, int> ids;
         for (int64_t s = 0; s < in->n_segs; s++) {
@@ -478,6 +479,7 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
                     default: ch = 'A';
                 }
             }
+            memcpy(seg_canon_bytes.data() + a, key.data(), key.size());
             auto it = ids.find(key);
             if (it == ids.end()) it = ids.emplace(std::move(key), (int)ids.size()).first;
             canon[s] = it->second;
@@ -491,7 +493,7 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     UP(ch_left, in->n_chains); UP(ch_c_ref, in->n_chains); UP(ch_v_ref, in->n_chains); UP(ch_u_ref, in->n_chains);
     UP(ch_hcomp, in->n_chains); UP(ch_amino_off, in->n_chains); UP(ch_amino_len, in->n_chains);
     UP(amino_bytes, in->n_amino_bytes); UP(cell_donor, in->n_cells); UP(cell_barcode, in->n_cells);
-    UP(seg_off, in->n_segs + 1); UP(seg_bytes, d.n_seg_bytes); UP(ref_off, in->n_refs + 1); UP(ref_bytes, d.n_ref_bytes);
+    UP(seg_off, in->n_segs + 1); UP(ref_off, in->n_refs + 1); UP(ref_bytes, d.n_ref_bytes);
     UP(ref_name_id, in->n_refs);
 #undef UP
     if ((rc = upload_array(c, in->ch_fr1_start, in->n_chains, &d.ch_fr1)) != EJB_OK) return rc;
@@ -500,6 +502,8 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     if ((rc = upload_array(c, in->ch_cdr2_start, in->n_chains, &d.ch_cdr2)) != EJB_OK) return rc;
     if ((rc = upload_array(c, in->ch_fr3_start, in->n_chains, &d.ch_fr3)) != EJB_OK) return rc;
     if ((rc = upload_array(c, canon.data(), in->n_segs, &d.seg_canon)) != EJB_OK) return rc;
+    if (in->n_segs > 0 && !in->seg_bytes) return fail(c, EJB_ERR_INVALID, "seg_bytes is null");
+    if ((rc = upload_array(c, (const uint8_t*)seg_canon_bytes.data(), d.n_seg_bytes, &d.seg_bytes)) != EJB_OK) return rc;
     CK(cudaStreamSynchronize(c->stream));
     c->ms_h2d = now_ms() - t0;
     c->have_input = true;
@@ -815,6 +819,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
         c->n_pos = q;
         c->n_blocks = blk;
         if (q >= (1ll << 31)) return fail(c, EJB_ERR_INVALID, "too many packed rows");
+        if (rs >= (1ll << 32) || s1 >= (1ll << 32)) return fail(c, EJB_ERR_INVALID, "packed row store exceeds 32-bit indexing (64 GB)");
 
         // ---- multi-GPU ownership: LPT by pair count ----
         if (c->shard_world > 1) {

@@ -159,8 +159,8 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
             int code = 0;
             if (p < T) {
                 const uint8_t b = (p < sb.ch) ? c0[p] : c1[p - sb.ch];
-                if (!is_acgt(b)) irr = true;
-                code = base2bit(b);
+                if (!is_acgt_fast(b)) irr = true;
+                code = (int)base_code(b);
             }
             const uint32_t lo = __ballot_sync(0xffffffffu, code & 1);
             const uint32_t hi = __ballot_sync(0xffffffffu, code & 2);
@@ -217,75 +217,59 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
         if (hasdel) flags |= (m == 0) ? F_HASDEL_H : F_HASDEL_L;
         bool odd = false;
         const int nw = (L + 31) / 32;
-        // lane w keeps word w of every plane (4 * W4 <= 32 words), so each plane is written with one coalesced store
+        const int npl = rec_planes(m, gapbit);
+        // lane w keeps word w of every plane (4 * W4 <= 32 words) and writes them at the end
         uint32_t k_lo = 0, k_hi = 0, k_d = 0, k_gap = 0, k_glo = 0, k_ghi = 0, k_rlo = 0, k_rhi = 0, k_cm = 0;
         const int nwords = min(nw, 4 * W4);
-        for (int w0 = 0; w0 < nwords; w0 += 8) {
-            // batch the byte loads of 8 words (contig + reference) before the ballots: 16 independent loads in flight
-            uint8_t tb[8], rb[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int p = (w0 + i) * 32 + lane;
-                tb[i] = 0;
-                rb[i] = 0;
-                if (w0 + i < nwords && p < L) {
-                    tb[i] = tig[p];
-                    if (p < vr) rb[i] = vseg[p];
-                    else if (p >= L - jr) rb[i] = jseg[jlen - 1 - ((long long)L - 1 - p)];   // tig[L-1-pp] vs J[|J|-1-pp], join_one.rs:388-391
-                }
+        const long long jshift = (long long)jlen - L;   // J index of contig position p: p + jshift  (tig[L-1-pp] vs J[|J|-1-pp], join_one.rs:388-391)
+#pragma unroll 4
+        for (int w = 0; w < nwords; w++) {
+            const int p = w * 32 + lane;
+            uint32_t b = 0, rbyte = 0;
+            bool inr = false;
+            if (p < L) {
+                b = tig[p];
+                if (p < vr) { rbyte = vseg[p]; inr = true; }
+                else if (p >= L - jr) { rbyte = jseg[p + jshift]; inr = true; }
             }
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int w = w0 + i;
-                if (w >= nwords) break;   // warp-uniform
-                const int p = w * 32 + lane;
-                int code = 0, dbit = 0, gbit = 0, rcode = 0, cbit = 0, rid = 0;
-                if (p < L) {
-                    const uint8_t b = tb[i];
-                    if (b == '-' && hasdel) gbit = 1;
-                    else if (!is_acgt(b)) odd = true;
-                    code = base2bit(b);
-                    if (p < vr || p >= L - jr) {
-                        cbit = 1;
-                        rcode = base2bit(rb[i]);
-                    }
-                    dbit = cbit && (b != bit2base(rcode));
-                    if (m == 0) {
-                        if (p >= rF0 && p < rF1) rid = 1;
-                        else if (p >= rC10 && p < rC11) rid = 2;
-                        else if (p >= rC20 && p < rC21) rid = 3;
-                    }
-                }
-                const uint32_t lo = __ballot_sync(0xffffffffu, code & 1), hi = __ballot_sync(0xffffffffu, code & 2);
-                const uint32_t dm = __ballot_sync(0xffffffffu, dbit), gp = __ballot_sync(0xffffffffu, gbit);
-                const uint32_t rlo = __ballot_sync(0xffffffffu, rcode & 1), rhi = __ballot_sync(0xffffffffu, rcode & 2);
-                const uint32_t cm = __ballot_sync(0xffffffffu, cbit);
-                const uint32_t glo = __ballot_sync(0xffffffffu, rid & 1), ghi = __ballot_sync(0xffffffffu, rid & 2);
-                tot += __popc(dm);
-                if (lane == w) {
-                    k_lo = lo; k_hi = hi; k_d = dm; k_gap = gp; k_glo = glo; k_ghi = ghi; k_rlo = rlo; k_rhi = rhi; k_cm = cm;
-                }
+            const bool gapb = (b == '-') && hasdel;
+            if (p < L && !gapb && !is_acgt_fast(b)) odd = true;
+            const uint32_t code = base_code(b), rcode = base_code(rbyte);
+            const bool dbit = inr && (b != rbyte);   // seg bytes are canonical upper-case ACGT (host), '-' never equals them
+            int rid = 0;
+            if (m == 0) {
+                if (p >= rF0 && p < rF1) rid = 1;
+                else if (p >= rC10 && p < rC11) rid = 2;
+                else if (p >= rC20 && p < rC21) rid = 3;
+            }
+            const uint32_t lo = __ballot_sync(0xffffffffu, code & 1), hi = __ballot_sync(0xffffffffu, code & 2);
+            const uint32_t dm = __ballot_sync(0xffffffffu, dbit), gp = __ballot_sync(0xffffffffu, gapb);
+            const uint32_t rlo = __ballot_sync(0xffffffffu, inr && (rcode & 1)), rhi = __ballot_sync(0xffffffffu, inr && (rcode & 2));
+            const uint32_t cm = __ballot_sync(0xffffffffu, inr);
+            const uint32_t glo = __ballot_sync(0xffffffffu, rid & 1), ghi = __ballot_sync(0xffffffffu, rid & 2);
+            tot += __popc(dm);
+            if (lane == w) {
+                k_lo = lo; k_hi = hi; k_d = dm; k_gap = gp; k_glo = glo; k_ghi = ghi; k_rlo = rlo; k_rhi = rhi; k_cm = cm;
             }
         }
         if (lane < 4 * W4) {
-            uint32_t* r = rec32 + base_u4 * 4 + lane;
-            const int st = 4 * W4;
-            r[0] = k_lo;
-            r[st] = k_hi;
-            r[2 * st] = k_d;
-            int o = 3;
-            if (gapbit) r[(o++) * st] = k_gap;
+            // lane-major record: window g = lane / 4, word j = lane % 4 of each plane's uint4
+            uint32_t* r = rec32 + (base_u4 + (lane >> 2) * npl) * 4 + (lane & 3);
+            r[PL_TLO * 4] = k_lo;
+            r[PL_THI * 4] = k_hi;
+            r[PL_D * 4] = k_d;
+            r[PL_RLO * 4] = k_rlo;
+            r[PL_RHI * 4] = k_rhi;
+            r[PL_CMP * 4] = k_cm;
             if (m == 0) {
-                r[(o++) * st] = k_glo;
-                r[(o++) * st] = k_ghi;
+                r[PL_GLO * 4] = k_glo;
+                r[PL_GHI * 4] = k_ghi;
             }
-            r[o * st] = k_rlo;
-            r[(o + 1) * st] = k_rhi;
-            r[(o + 2) * st] = k_cm;
+            if (gapbit) r[gap_plane(m) * 4] = k_gap;
         }
         if (W4 == 0) {  // contig longer than the fast path: the byte-exact path handles it
             for (int p = lane; p < L; p += 32)
-                if (!is_acgt(tig[p]) && !(tig[p] == '-' && hasdel)) odd = true;
+                if (!is_acgt_fast(tig[p]) && !(tig[p] == '-' && hasdel)) odd = true;
         }
         if (__any_sync(0xffffffffu, odd)) flags |= (m == 0) ? F_ODDBYTE_H : F_ODDBYTE_L;
         base_u4 += rec_planes(m, gapbit) * W4;

@@ -43,7 +43,7 @@ __device__ __forceinline__ int cdr3_dist(const uint32_t* rl, const uint32_t* rh,
 }
 
 template <int W1>
-__global__ void __launch_bounds__(S1_THREADS) k_stage1(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, int n_tasks,
+__global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2)) k_stage1(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, int n_tasks,
                                                        const uint32_t* __restrict__ cdr3w, const int32_t* __restrict__ labq,
                                                        const int32_t* __restrict__ blk_lab, uint2* __restrict__ cand,
                                                        unsigned long long cand_cap, Counters* __restrict__ ctr) {

@@ -148,139 +148,143 @@ __device__ __forceinline__ void ld4(const uint4* p, uint32_t* o) {
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
 }
 
-// Plane math of ONE candidate by a group of G lanes (G = 4 or 8); lane g handles uint4 g of every plane
-// (128 positions).  Results are packed sums (every field stays < 65536 after the group reduction):
+// Per-candidate values the owner lane derives once and hands to the group working on it (by shuffle).
+struct CandInfo {
+    uint32_t meta;        // W1 | W4h<<3 | W4l<<7 | gap<<11 | fast<<13 | nrefs1<<14 | ch<<16
+    uint32_t rec1, rec2;  // uint4 index of the two row records in rowstore
+    uint32_t cw1, cw2;    // word index of the two rows in plane 0 / word 0 of cdr3w
+    uint32_t npad;        // row stride of the CDR3 planes
+    int tot1, tot2;
+};
+__device__ __forceinline__ CandInfo shfl_cand(const CandInfo& c, int src) {
+    CandInfo r;
+    r.meta = __shfl_sync(0xffffffffu, c.meta, src);
+    r.rec1 = __shfl_sync(0xffffffffu, c.rec1, src);
+    r.rec2 = __shfl_sync(0xffffffffu, c.rec2, src);
+    r.cw1 = __shfl_sync(0xffffffffu, c.cw1, src);
+    r.cw2 = __shfl_sync(0xffffffffu, c.cw2, src);
+    r.npad = __shfl_sync(0xffffffffu, c.npad, src);
+    r.tot1 = __shfl_sync(0xffffffffu, c.tot1, src);
+    r.tot2 = __shfl_sync(0xffffffffu, c.tot2, src);
+    return r;
+}
+
+// Plane math of ONE candidate by a group of G lanes (G = 4 or 8); lane g handles window g (128 positions) of
+// every plane.  Results are packed sums (every field stays < 65536 after the group reduction):
 //   r[0] = cd1 | cd2<<16      CDR3 differences heavy | light
 //   r[1] = A | B<<16          A = popc(d1 & d2), B = popc(d1 & d2 & e); e = bases differ (incl. gaps)
 //   r[2] = diffs | fd<<16     full-length differences | FWR1 differences
 //   r[3] = c1d | c2d<<16      CDR1 | CDR2 differences                       (regions of row 1's planes)
 //   two references only: r[4] = A0|B0, r[5] = O0|T01, r[6] = A1|B1, r[7] = O1|T10
 //     x21 = (t2 != r1) on cmp1, x12 = (t1 != r2) on cmp2;  A0 = popc(d1&x21) ... (join_one.rs:343-429)
+template <int G, int M>
+__device__ __forceinline__ void s2_chain(const uint4* __restrict__ pa, const uint4* __restrict__ pb, bool gapbit, bool nrefs1, uint32_t& pk1, uint32_t& pk2,
+                                         uint32_t& pk3, uint32_t& n0, uint32_t& n1, uint32_t& n2, uint32_t& n3) {
+    uint32_t al[4], ah[4], ad[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bd[4], bg[4] = {0, 0, 0, 0}, e[4];
+    ld4(pa + PL_TLO, al); ld4(pa + PL_THI, ah); ld4(pa + PL_D, ad);
+    ld4(pb + PL_TLO, bl); ld4(pb + PL_THI, bh); ld4(pb + PL_D, bd);
+    if (gapbit) { ld4(pa + gap_plane(M), ag); ld4(pb + gap_plane(M), bg); }
+    int A = 0, B = 0, df = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        e[w] = (al[w] ^ bl[w]) | (ah[w] ^ bh[w]) | (ag[w] ^ bg[w]);
+        const uint32_t both = ad[w] & bd[w];
+        A += __popc(both);
+        B += __popc(both & e[w]);
+        df += __popc(e[w]);
+    }
+    pk1 += (uint32_t)A | ((uint32_t)B << 16);
+    pk2 += (uint32_t)df;
+    if (M == 0) {   // region ids of row 1: 1 = FWR1, 2 = CDR1, 3 = CDR2
+        uint32_t gl[4], gh[4];
+        ld4(pa + PL_GLO, gl); ld4(pa + PL_GHI, gh);
+        int fd = 0, c1 = 0, c2 = 0;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            fd += __popc(e[w] & gl[w] & ~gh[w]);
+            c1 += __popc(e[w] & ~gl[w] & gh[w]);
+            c2 += __popc(e[w] & gl[w] & gh[w]);
+        }
+        pk2 += (uint32_t)fd << 16;
+        pk3 += (uint32_t)c1 | ((uint32_t)c2 << 16);
+    }
+    if (!nrefs1) {
+        uint32_t arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
+        ld4(pa + PL_RLO, arl); ld4(pa + PL_RHI, arh); ld4(pa + PL_CMP, ac);
+        ld4(pb + PL_RLO, brl); ld4(pb + PL_RHI, brh); ld4(pb + PL_CMP, bc);
+        int A0 = 0, B0 = 0, O0 = 0, T01 = 0, A1 = 0, B1 = 0, O1 = 0, T10 = 0;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const uint32_t x21 = ((bl[w] ^ arl[w]) | (bh[w] ^ arh[w]) | bg[w]) & ac[w];  // t2 != r1 on k1's ranges
+            const uint32_t x12 = ((al[w] ^ brl[w]) | (ah[w] ^ brh[w]) | ag[w]) & bc[w];  // t1 != r2 on k2's ranges
+            const uint32_t d1 = ad[w], d2 = bd[w];
+            A0 += __popc(d1 & x21); B0 += __popc(d1 & x21 & e[w]); O0 += __popc(d1 ^ x21); T01 += __popc(x21);
+            A1 += __popc(x12 & d2); B1 += __popc(x12 & d2 & e[w]); O1 += __popc(x12 ^ d2); T10 += __popc(x12);
+        }
+        n0 += (uint32_t)A0 | ((uint32_t)B0 << 16);
+        n1 += (uint32_t)O0 | ((uint32_t)T01 << 16);
+        n2 += (uint32_t)A1 | ((uint32_t)B1 << 16);
+        n3 += (uint32_t)O1 | ((uint32_t)T10 << 16);
+    }
+}
+
+// T01 | T10<<16 of one chain window: the two totals the degradation test needs (join_one.rs:434-440)
+template <int M>
+__device__ __forceinline__ uint32_t s2_chain_degr(const uint4* __restrict__ pa, const uint4* __restrict__ pb, bool gapbit) {
+    uint32_t al[4], ah[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bg[4] = {0, 0, 0, 0}, arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
+    ld4(pa + PL_TLO, al); ld4(pa + PL_THI, ah); ld4(pb + PL_TLO, bl); ld4(pb + PL_THI, bh);
+    if (gapbit) { ld4(pa + gap_plane(M), ag); ld4(pb + gap_plane(M), bg); }
+    ld4(pa + PL_RLO, arl); ld4(pa + PL_RHI, arh); ld4(pa + PL_CMP, ac);
+    ld4(pb + PL_RLO, brl); ld4(pb + PL_RHI, brh); ld4(pb + PL_CMP, bc);
+    int T01 = 0, T10 = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        T01 += __popc(((bl[w] ^ arl[w]) | (bh[w] ^ arh[w]) | bg[w]) & ac[w]);
+        T10 += __popc(((al[w] ^ brl[w]) | (ah[w] ^ brh[w]) | ag[w]) & bc[w]);
+    }
+    return (uint32_t)T01 | ((uint32_t)T10 << 16);
+}
+
 template <int G>
-__device__ __forceinline__ void s2_planes(const S2Ctx& X, const SubBucket& sb, uint32_t q1, uint32_t q2, int g, bool active, bool nrefs1,
-                                          unsigned int gmask, int tot1, int tot2, uint32_t* r) {
+__device__ __forceinline__ void s2_planes(const S2Ctx& X, const CandInfo& ci, int g, unsigned int gmask, uint32_t* r) {
+    const int W1 = ci.meta & 7, W4h = (ci.meta >> 3) & 15, W4l = (ci.meta >> 7) & 15, gap = (ci.meta >> 11) & 3, ch = ci.meta >> 16;
+    bool active = (ci.meta >> 13) & 1;
+    const bool nrefs1 = (ci.meta >> 14) & 1;
+    const int npl0 = rec_planes(0, gap & 1), npl1 = rec_planes(1, gap & 2);
+    const uint4* pa0 = X.rowstore + ci.rec1 + g * npl0;
+    const uint4* pb0 = X.rowstore + ci.rec2 + g * npl0;
+    const uint4* pa1 = X.rowstore + ci.rec1 + W4h * npl0 + g * npl1;
+    const uint4* pb1 = X.rowstore + ci.rec2 + W4h * npl0 + g * npl1;
     uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
     // Two references: nearly every such candidate dies on the degradation test (join_one.rs:434-440), which only
     // needs T01 = popc(t2 != r1 on cmp1) and T10 = popc(t1 != r2 on cmp2) — evaluate that first and stop early.
     if (active && !nrefs1 && !X.tuple_mode) {
-        uint32_t tt = 0;   // T01 | T10 << 16
-        const uint4* r1 = X.rowstore + sb.rs_off + (int64_t)(q1 - sb.q0) * sb.rec_u4;
-        const uint4* r2 = X.rowstore + sb.rs_off + (int64_t)(q2 - sb.q0) * sb.rec_u4;
-#pragma unroll
-        for (int m = 0; m < 2; m++) {
-            const int W4 = m ? sb.W4l : sb.W4h;
-            const int gapbit = (sb.gap >> m) & 1;
-            const int off = m ? rec_planes(0, sb.gap & 1) * sb.W4h : 0;
-            if (g < W4) {
-                uint32_t al[4], ah[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bg[4] = {0, 0, 0, 0}, arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
-                ld4(r1 + off + g, al); ld4(r1 + off + W4 + g, ah);
-                ld4(r2 + off + g, bl); ld4(r2 + off + W4 + g, bh);
-                if (gapbit) { ld4(r1 + off + 3 * W4 + g, ag); ld4(r2 + off + 3 * W4 + g, bg); }
-                const int ro = off + (3 + gapbit + (m == 0 ? 2 : 0)) * W4;
-                ld4(r1 + ro + g, arl); ld4(r1 + ro + W4 + g, arh); ld4(r1 + ro + 2 * W4 + g, ac);
-                ld4(r2 + ro + g, brl); ld4(r2 + ro + W4 + g, brh); ld4(r2 + ro + 2 * W4 + g, bc);
-                int T01 = 0, T10 = 0;
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    T01 += __popc(((bl[w] ^ arl[w]) | (bh[w] ^ arh[w]) | bg[w]) & ac[w]);
-                    T10 += __popc(((al[w] ^ brl[w]) | (ah[w] ^ brh[w]) | ag[w]) & bc[w]);
-                }
-                tt += (uint32_t)T01 | ((uint32_t)T10 << 16);
-            }
-        }
+        uint32_t tt = 0;
+        if (g < W4h) tt += s2_chain_degr<0>(pa0, pb0, gap & 1);
+        if (g < W4l) tt += s2_chain_degr<1>(pa1, pb1, gap & 2);
 #pragma unroll
         for (int o = 1; o < G; o <<= 1) tt += __shfl_xor_sync(gmask, tt, o);
         const int T01 = (int)(tt & 0xffff), T10 = (int)(tt >> 16);
-        if (abs(tot1 - T10) > X.P.max_degradation || abs(T01 - tot2) > X.P.max_degradation) {
+        if (abs(ci.tot1 - T10) > X.P.max_degradation || abs(T01 - ci.tot2) > X.P.max_degradation) {
             active = false;          // rejected: phase 2 repeats the test on these totals and drops the candidate
             n1 = (uint32_t)T01 << 16;
             n3 = (uint32_t)T10 << 16;
         }
     }
-    const bool early_dead = !active && (n1 | n3) != 0;
     if (active) {
-        if (g < sb.W1) {
-            const uint32_t* b = X.cdr3w + sb.s1_off;
-            const int64_t i1 = q1 - sb.q0, i2 = q2 - sb.q0;
-            const uint32_t x = (b[(int64_t)g * sb.npad + i1] ^ b[(int64_t)g * sb.npad + i2]) |
-                               (b[(int64_t)(sb.W1 + g) * sb.npad + i1] ^ b[(int64_t)(sb.W1 + g) * sb.npad + i2]);
-            const int lo_bit = g * 32;
-            uint32_t hm;  // bits of this word that belong to the heavy CDR3
-            if (sb.ch >= lo_bit + 32) hm = 0xffffffffu;
-            else if (sb.ch <= lo_bit) hm = 0u;
-            else hm = (1u << (sb.ch - lo_bit)) - 1u;
-            pk0 = (uint32_t)__popc(x & hm) | ((uint32_t)__popc(x & ~hm) << 16);
-        }
-        if (G == 4 && g + 4 < sb.W1) {   // W1 up to 6 with only 4 lanes: lanes 0,1 take words 4,5 as well
-            const int w = g + 4;
-            const uint32_t* b = X.cdr3w + sb.s1_off;
-            const int64_t i1 = q1 - sb.q0, i2 = q2 - sb.q0;
-            const uint32_t x = (b[(int64_t)w * sb.npad + i1] ^ b[(int64_t)w * sb.npad + i2]) |
-                               (b[(int64_t)(sb.W1 + w) * sb.npad + i1] ^ b[(int64_t)(sb.W1 + w) * sb.npad + i2]);
+        // CDR3 distances, split at the heavy/light boundary of the concatenated planes
+        for (int w = g; w < W1; w += G) {
+            const uint32_t* b = X.cdr3w;
+            const uint32_t x = (b[ci.cw1 + w * ci.npad] ^ b[ci.cw2 + w * ci.npad]) | (b[ci.cw1 + (W1 + w) * ci.npad] ^ b[ci.cw2 + (W1 + w) * ci.npad]);
             const int lo_bit = w * 32;
-            uint32_t hm;
-            if (sb.ch >= lo_bit + 32) hm = 0xffffffffu;
-            else if (sb.ch <= lo_bit) hm = 0u;
-            else hm = (1u << (sb.ch - lo_bit)) - 1u;
+            uint32_t hm;  // bits of this word that belong to the heavy CDR3
+            if (ch >= lo_bit + 32) hm = 0xffffffffu;
+            else if (ch <= lo_bit) hm = 0u;
+            else hm = (1u << (ch - lo_bit)) - 1u;
             pk0 += (uint32_t)__popc(x & hm) | ((uint32_t)__popc(x & ~hm) << 16);
         }
-        const uint4* r1 = X.rowstore + sb.rs_off + (int64_t)(q1 - sb.q0) * sb.rec_u4;
-        const uint4* r2 = X.rowstore + sb.rs_off + (int64_t)(q2 - sb.q0) * sb.rec_u4;
-#pragma unroll
-        for (int m = 0; m < 2; m++) {
-            const int W4 = m ? sb.W4l : sb.W4h;
-            const int gapbit = (sb.gap >> m) & 1;
-            const int off = m ? rec_planes(0, sb.gap & 1) * sb.W4h : 0;
-            if (g < W4) {
-                uint32_t al[4], ah[4], ad[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bd[4], bg[4] = {0, 0, 0, 0}, e[4];
-                ld4(r1 + off + g, al); ld4(r1 + off + W4 + g, ah); ld4(r1 + off + 2 * W4 + g, ad);
-                ld4(r2 + off + g, bl); ld4(r2 + off + W4 + g, bh); ld4(r2 + off + 2 * W4 + g, bd);
-                if (gapbit) { ld4(r1 + off + 3 * W4 + g, ag); ld4(r2 + off + 3 * W4 + g, bg); }
-                int A = 0, B = 0, df = 0;
-#pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    e[w] = (al[w] ^ bl[w]) | (ah[w] ^ bh[w]) | (ag[w] ^ bg[w]);
-                    const uint32_t both = ad[w] & bd[w];
-                    A += __popc(both);
-                    B += __popc(both & e[w]);
-                    df += __popc(e[w]);
-                }
-                pk1 += (uint32_t)A | ((uint32_t)B << 16);
-                pk2 += (uint32_t)df;
-                if (m == 0) {   // region ids of row 1: 1 = FWR1, 2 = CDR1, 3 = CDR2
-                    uint32_t gl[4], gh[4];
-                    ld4(r1 + off + (3 + gapbit) * W4 + g, gl); ld4(r1 + off + (4 + gapbit) * W4 + g, gh);
-                    int fd = 0, c1 = 0, c2 = 0;
-#pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                        fd += __popc(e[w] & gl[w] & ~gh[w]);
-                        c1 += __popc(e[w] & ~gl[w] & gh[w]);
-                        c2 += __popc(e[w] & gl[w] & gh[w]);
-                    }
-                    pk2 += (uint32_t)fd << 16;
-                    pk3 += (uint32_t)c1 | ((uint32_t)c2 << 16);
-                }
-                if (!nrefs1) {
-                    uint32_t arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
-                    const int ro = off + (3 + gapbit + (m == 0 ? 2 : 0)) * W4;
-                    ld4(r1 + ro + g, arl); ld4(r1 + ro + W4 + g, arh); ld4(r1 + ro + 2 * W4 + g, ac);
-                    ld4(r2 + ro + g, brl); ld4(r2 + ro + W4 + g, brh); ld4(r2 + ro + 2 * W4 + g, bc);
-                    int A0 = 0, B0 = 0, O0 = 0, T01 = 0, A1 = 0, B1 = 0, O1 = 0, T10 = 0;
-#pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                        const uint32_t x21 = ((bl[w] ^ arl[w]) | (bh[w] ^ arh[w]) | bg[w]) & ac[w];  // t2 != r1 on k1's ranges
-                        const uint32_t x12 = ((al[w] ^ brl[w]) | (ah[w] ^ brh[w]) | ag[w]) & bc[w];  // t1 != r2 on k2's ranges
-                        const uint32_t d1 = ad[w], d2 = bd[w];
-                        A0 += __popc(d1 & x21); B0 += __popc(d1 & x21 & e[w]); O0 += __popc(d1 ^ x21); T01 += __popc(x21);
-                        A1 += __popc(x12 & d2); B1 += __popc(x12 & d2 & e[w]); O1 += __popc(x12 ^ d2); T10 += __popc(x12);
-                    }
-                    n0 += (uint32_t)A0 | ((uint32_t)B0 << 16);
-                    n1 += (uint32_t)O0 | ((uint32_t)T01 << 16);
-                    n2 += (uint32_t)A1 | ((uint32_t)B1 << 16);
-                    n3 += (uint32_t)O1 | ((uint32_t)T10 << 16);
-                }
-            }
-        }
+        if (g < W4h) s2_chain<G, 0>(pa0, pb0, gap & 1, nrefs1, pk1, pk2, pk3, n0, n1, n2, n3);
+        if (g < W4l) s2_chain<G, 1>(pa1, pb1, gap & 2, nrefs1, pk1, pk2, pk3, n0, n1, n2, n3);
     }
 #pragma unroll
     for (int o = 1; o < G; o <<= 1) {
@@ -298,7 +302,6 @@ __device__ __forceinline__ void s2_planes(const S2Ctx& X, const SubBucket& sb, u
             n3 += __shfl_xor_sync(gmask, n3, o);
         }
     }
-    (void)early_dead;
     r[0] = pk0; r[1] = pk1; r[2] = pk2; r[3] = pk3; r[4] = n0; r[5] = n1; r[6] = n2; r[7] = n3;
 }
 
@@ -342,18 +345,24 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
         const bool fast = valid && ((f1 | f2) & F_SLOWMASK) == 0 && sb.W1 > 0 && sb.W4h > 0 && sb.W4l > 0;
         const bool wide = fast && (sb.W4h > 4 || sb.W4l > 4);
         const int tot1 = a1[AX_TOT], tot2 = a2[AX_TOT];
+        CandInfo me;
+        me.meta = (uint32_t)sb.W1 | ((uint32_t)sb.W4h << 3) | ((uint32_t)sb.W4l << 7) | ((uint32_t)sb.gap << 11) | ((uint32_t)fast << 13) |
+                  ((uint32_t)nrefs1 << 14) | ((uint32_t)sb.ch << 16);
+        me.rec1 = (uint32_t)(sb.rs_off + (int64_t)(q1 - sb.q0) * sb.rec_u4);
+        me.rec2 = (uint32_t)(sb.rs_off + (int64_t)(q2 - sb.q0) * sb.rec_u4);
+        me.cw1 = (uint32_t)(sb.s1_off + (q1 - sb.q0));
+        me.cw2 = (uint32_t)(sb.s1_off + (q2 - sb.q0));
+        me.npad = (uint32_t)sb.npad;
+        me.tot1 = tot1;
+        me.tot2 = tot2;
         // ---- phase 1 ----
         if (!__any_sync(0xffffffffu, wide)) {
 #pragma unroll 1
             for (int it = 0; it < 4; it++) {
                 const int src = it * 8 + (lane >> 2);           // candidate (lane index of its owner) this group works on
-                const uint32_t gq1 = __shfl_sync(0xffffffffu, q1, src), gq2 = __shfl_sync(0xffffffffu, q2, src);
-                const int gsid = __shfl_sync(0xffffffffu, sid, src);
-                const bool gfast = __shfl_sync(0xffffffffu, (int)fast, src) != 0, gn1 = __shfl_sync(0xffffffffu, (int)nrefs1, src) != 0;
-                const SubBucket gsb = X.subs[gsid];
-                const int gt1 = __shfl_sync(0xffffffffu, tot1, src), gt2 = __shfl_sync(0xffffffffu, tot2, src);
+                const CandInfo gc = shfl_cand(me, src);
                 uint32_t r[8];
-                s2_planes<4>(X, gsb, gq1, gq2, lane & 3, gfast, gn1, 0xfu << (lane & 28), gt1, gt2, r);
+                s2_planes<4>(X, gc, lane & 3, 0xfu << (lane & 28), r);
                 if ((lane & 3) == 0) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) s_res[wib][src][i] = r[i];
@@ -363,13 +372,9 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
 #pragma unroll 1
             for (int it = 0; it < 8; it++) {
                 const int src = it * 4 + (lane >> 3);
-                const uint32_t gq1 = __shfl_sync(0xffffffffu, q1, src), gq2 = __shfl_sync(0xffffffffu, q2, src);
-                const int gsid = __shfl_sync(0xffffffffu, sid, src);
-                const bool gfast = __shfl_sync(0xffffffffu, (int)fast, src) != 0, gn1 = __shfl_sync(0xffffffffu, (int)nrefs1, src) != 0;
-                const SubBucket gsb = X.subs[gsid];
-                const int gt1 = __shfl_sync(0xffffffffu, tot1, src), gt2 = __shfl_sync(0xffffffffu, tot2, src);
+                const CandInfo gc = shfl_cand(me, src);
                 uint32_t r[8];
-                s2_planes<8>(X, gsb, gq1, gq2, lane & 7, gfast, gn1, 0xffu << (lane & 24), gt1, gt2, r);
+                s2_planes<8>(X, gc, lane & 7, 0xffu << (lane & 24), r);
                 if ((lane & 7) == 0) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) s_res[wib][src][i] = r[i];

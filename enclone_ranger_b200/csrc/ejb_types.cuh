@@ -24,7 +24,7 @@ namespace ejb {
 
 constexpr int TILE = 128;          // rows / cols of one stage-1 tile
 constexpr int S1_THREADS = 256;
-constexpr int S1_STRIP = 8;        // column tiles per CTA (row fragment stays in registers)
+constexpr int S1_STRIP = 4;        // column tiles per CTA (row fragment stays in registers)
 constexpr int MAXW1 = 6;           // concatenated CDR3 (heavy+light) up to 192 nt on the fast path
 constexpr int MAXW4 = 8;           // contig up to 1024 nt on the stage-2 fast path
 constexpr int SR_NMAX = 3000;      // stirling2_ratio_table_double(3000), start.rs:344
@@ -75,15 +75,21 @@ struct SubBucket {
     int32_t owner;    // rank that owns this sub-bucket (multi-GPU sharding)
     int32_t pad;
 };
-// Row record layout, per chain m (W4 = W4h or W4l uint4 per plane, in this order):
-//   t_lo, t_hi : 2-bit code of the contig base (A,C,G,T = 0..3; '-' = 0 with the gap bit)
-//   d          : cmp & (contig base != own reference base)
-//   [gap]      : '-' positions (only when SubBucket.gap has bit m)
-//   [g_lo,g_hi]: chain 0 only — region id of each position: 1 = FWR1 [fr1,cdr1), 2 = CDR1 [cdr1,fr2),
-//                3 = CDR2 [cdr2,fr3), 0 = elsewhere                       (join_one.rs:766-854)
-//   r_lo, r_hi : the row's own V / J reference bases in CONTIG coordinates (V from the start, J from the end)
-//   cmp        : positions join_one compares: p < |V|-ref_v_trim  or  p >= L-(|J|-ref_j_trim)
+// Row record layout.  Per chain m the record is LANE-MAJOR: for each uint4 index g (128 positions) the planes
+// of that window are contiguous, so a lane reads all its planes at compile-time offsets from one base pointer:
+//     chain m, window g, plane pl  ->  uint4 index  off_m + g * rec_planes(m, gap_m) + pl
+//   PL_TLO, PL_THI : 2-bit code of the contig base ((byte >> 1) & 3: A,C,T,G = 0,1,2,3; '-' carries the gap bit)
+//   PL_D           : cmp & (contig base != own reference base)
+//   PL_RLO, PL_RHI : the row's own V / J reference bases in CONTIG coordinates (V from the start, J from the end)
+//   PL_CMP         : positions join_one compares: p < |V|-ref_v_trim  or  p >= L-(|J|-ref_j_trim)
+//   chain 0 only   PL_GLO, PL_GHI: region id of each position: 1 = FWR1 [fr1,cdr1), 2 = CDR1 [cdr1,fr2),
+//                  3 = CDR2 [cdr2,fr3), 0 = elsewhere                       (join_one.rs:766-854)
+//   [gap]          : '-' positions, last plane, only when SubBucket.gap has bit m
+enum Plane { PL_TLO = 0, PL_THI = 1, PL_D = 2, PL_RLO = 3, PL_RHI = 4, PL_CMP = 5, PL_GLO = 6, PL_GHI = 7 };
 __host__ __device__ __forceinline__ int rec_planes(int m, int gapbit) { return 6 + (gapbit ? 1 : 0) + (m == 0 ? 2 : 0); }
+__host__ __device__ __forceinline__ int gap_plane(int m) { return m == 0 ? 8 : 6; }
+__device__ __forceinline__ uint32_t base_code(uint32_t byte) { return (byte >> 1) & 3u; }   // A,C,T,G -> 0,1,2,3
+__device__ __forceinline__ bool is_acgt_fast(uint32_t b) { return (b & 0xe0u) == 0x40u && ((0x0010008au >> (b & 31u)) & 1u); }
 
 // Device view of the raw (uploaded) input, same meaning as ejb_input.
 struct DevIn {
