@@ -776,9 +776,9 @@ extern "C" int ejb_run(ejb_ctx* c) {
             const int T = sb.ch + sb.cl;
             const int w1 = (T + 31) / 32;
             sb.W1 = (w1 >= 1 && w1 <= MAXW1) ? w1 : 0;
-            const int w4h = (sb.Lh + 127) / 128, w4l = (sb.Ll + 127) / 128;
-            sb.W4h = (w4h >= 1 && w4h <= MAXW4) ? w4h : 0;
-            sb.W4l = (w4l >= 1 && w4l <= MAXW4) ? w4l : 0;
+            // uint4 per plane: 4 up to 512 nt (compile-time stride on the common path), 8 up to 1024 nt, else byte path only
+            sb.W4h = (sb.Lh >= 1 && sb.Lh <= 512) ? 4 : (sb.Lh <= 128 * MAXW4 && sb.Lh >= 1) ? MAXW4 : 0;
+            sb.W4l = (sb.Ll >= 1 && sb.Ll <= 512) ? 4 : (sb.Ll <= 128 * MAXW4 && sb.Ll >= 1) ? MAXW4 : 0;
             sb.gap = si[s].gap & 3;
             sb.rec_u4 = rec_planes(0, sb.gap & 1) * sb.W4h + rec_planes(1, sb.gap & 2) * sb.W4l;
             sb.pad = 0;

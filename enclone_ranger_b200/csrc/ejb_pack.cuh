@@ -253,19 +253,20 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
             }
         }
         if (lane < 4 * W4) {
-            // lane-major record: window g = lane / 4, word j = lane % 4 of each plane's uint4
-            uint32_t* r = rec32 + (base_u4 + (lane >> 2) * npl) * 4 + (lane & 3);
-            r[PL_TLO * 4] = k_lo;
-            r[PL_THI * 4] = k_hi;
-            r[PL_D * 4] = k_d;
-            r[PL_RLO * 4] = k_rlo;
-            r[PL_RHI * 4] = k_rhi;
-            r[PL_CMP * 4] = k_cm;
+            // plane-major record: one coalesced store per plane
+            uint32_t* r = rec32 + base_u4 * 4 + lane;
+            const int st = 4 * W4;
+            r[PL_TLO * st] = k_lo;
+            r[PL_THI * st] = k_hi;
+            r[PL_D * st] = k_d;
+            r[PL_RLO * st] = k_rlo;
+            r[PL_RHI * st] = k_rhi;
+            r[PL_CMP * st] = k_cm;
             if (m == 0) {
-                r[PL_GLO * 4] = k_glo;
-                r[PL_GHI * 4] = k_ghi;
+                r[PL_GLO * st] = k_glo;
+                r[PL_GHI * st] = k_ghi;
             }
-            if (gapbit) r[gap_plane(m) * 4] = k_gap;
+            if (gapbit) r[gap_plane(m) * st] = k_gap;
         }
         if (W4 == 0) {  // contig longer than the fast path: the byte-exact path handles it
             for (int p = lane; p < L; p += 32)

@@ -177,13 +177,15 @@ __device__ __forceinline__ CandInfo shfl_cand(const CandInfo& c, int src) {
 //   r[3] = c1d | c2d<<16      CDR1 | CDR2 differences                       (regions of row 1's planes)
 //   two references only: r[4] = A0|B0, r[5] = O0|T01, r[6] = A1|B1, r[7] = O1|T10
 //     x21 = (t2 != r1) on cmp1, x12 = (t1 != r2) on cmp2;  A0 = popc(d1&x21) ... (join_one.rs:343-429)
-template <int G, int M>
-__device__ __forceinline__ void s2_chain(const uint4* __restrict__ pa, const uint4* __restrict__ pb, bool gapbit, bool nrefs1, uint32_t& pk1, uint32_t& pk2,
-                                         uint32_t& pk3, uint32_t& n0, uint32_t& n1, uint32_t& n2, uint32_t& n3) {
+// WS = plane stride in uint4 when known at compile time (4), 0 = runtime stride `st`
+template <int WS, int M>
+__device__ __forceinline__ void s2_chain(const uint4* __restrict__ pa, const uint4* __restrict__ pb, int st, bool gapbit, bool nrefs1, uint32_t& pk1,
+                                         uint32_t& pk2, uint32_t& pk3, uint32_t& n0, uint32_t& n1, uint32_t& n2, uint32_t& n3) {
+    const int S = WS ? WS : st;
     uint32_t al[4], ah[4], ad[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bd[4], bg[4] = {0, 0, 0, 0}, e[4];
-    ld4(pa + PL_TLO, al); ld4(pa + PL_THI, ah); ld4(pa + PL_D, ad);
-    ld4(pb + PL_TLO, bl); ld4(pb + PL_THI, bh); ld4(pb + PL_D, bd);
-    if (gapbit) { ld4(pa + gap_plane(M), ag); ld4(pb + gap_plane(M), bg); }
+    ld4(pa + PL_TLO * S, al); ld4(pa + PL_THI * S, ah); ld4(pa + PL_D * S, ad);
+    ld4(pb + PL_TLO * S, bl); ld4(pb + PL_THI * S, bh); ld4(pb + PL_D * S, bd);
+    if (gapbit) { ld4(pa + gap_plane(M) * S, ag); ld4(pb + gap_plane(M) * S, bg); }
     int A = 0, B = 0, df = 0;
 #pragma unroll
     for (int w = 0; w < 4; w++) {
@@ -197,7 +199,7 @@ __device__ __forceinline__ void s2_chain(const uint4* __restrict__ pa, const uin
     pk2 += (uint32_t)df;
     if (M == 0) {   // region ids of row 1: 1 = FWR1, 2 = CDR1, 3 = CDR2
         uint32_t gl[4], gh[4];
-        ld4(pa + PL_GLO, gl); ld4(pa + PL_GHI, gh);
+        ld4(pa + PL_GLO * S, gl); ld4(pa + PL_GHI * S, gh);
         int fd = 0, c1 = 0, c2 = 0;
 #pragma unroll
         for (int w = 0; w < 4; w++) {
@@ -210,8 +212,8 @@ __device__ __forceinline__ void s2_chain(const uint4* __restrict__ pa, const uin
     }
     if (!nrefs1) {
         uint32_t arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
-        ld4(pa + PL_RLO, arl); ld4(pa + PL_RHI, arh); ld4(pa + PL_CMP, ac);
-        ld4(pb + PL_RLO, brl); ld4(pb + PL_RHI, brh); ld4(pb + PL_CMP, bc);
+        ld4(pa + PL_RLO * S, arl); ld4(pa + PL_RHI * S, arh); ld4(pa + PL_CMP * S, ac);
+        ld4(pb + PL_RLO * S, brl); ld4(pb + PL_RHI * S, brh); ld4(pb + PL_CMP * S, bc);
         int A0 = 0, B0 = 0, O0 = 0, T01 = 0, A1 = 0, B1 = 0, O1 = 0, T10 = 0;
 #pragma unroll
         for (int w = 0; w < 4; w++) {
@@ -229,13 +231,14 @@ __device__ __forceinline__ void s2_chain(const uint4* __restrict__ pa, const uin
 }
 
 // T01 | T10<<16 of one chain window: the two totals the degradation test needs (join_one.rs:434-440)
-template <int M>
-__device__ __forceinline__ uint32_t s2_chain_degr(const uint4* __restrict__ pa, const uint4* __restrict__ pb, bool gapbit) {
+template <int WS, int M>
+__device__ __forceinline__ uint32_t s2_chain_degr(const uint4* __restrict__ pa, const uint4* __restrict__ pb, int st, bool gapbit) {
+    const int S = WS ? WS : st;
     uint32_t al[4], ah[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bg[4] = {0, 0, 0, 0}, arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
-    ld4(pa + PL_TLO, al); ld4(pa + PL_THI, ah); ld4(pb + PL_TLO, bl); ld4(pb + PL_THI, bh);
-    if (gapbit) { ld4(pa + gap_plane(M), ag); ld4(pb + gap_plane(M), bg); }
-    ld4(pa + PL_RLO, arl); ld4(pa + PL_RHI, arh); ld4(pa + PL_CMP, ac);
-    ld4(pb + PL_RLO, brl); ld4(pb + PL_RHI, brh); ld4(pb + PL_CMP, bc);
+    ld4(pa + PL_TLO * S, al); ld4(pa + PL_THI * S, ah); ld4(pb + PL_TLO * S, bl); ld4(pb + PL_THI * S, bh);
+    if (gapbit) { ld4(pa + gap_plane(M) * S, ag); ld4(pb + gap_plane(M) * S, bg); }
+    ld4(pa + PL_RLO * S, arl); ld4(pa + PL_RHI * S, arh); ld4(pa + PL_CMP * S, ac);
+    ld4(pb + PL_RLO * S, brl); ld4(pb + PL_RHI * S, brh); ld4(pb + PL_CMP * S, bc);
     int T01 = 0, T10 = 0;
 #pragma unroll
     for (int w = 0; w < 4; w++) {
@@ -250,18 +253,19 @@ __device__ __forceinline__ void s2_planes(const S2Ctx& X, const CandInfo& ci, in
     const int W1 = ci.meta & 7, W4h = (ci.meta >> 3) & 15, W4l = (ci.meta >> 7) & 15, gap = (ci.meta >> 11) & 3, ch = ci.meta >> 16;
     bool active = (ci.meta >> 13) & 1;
     const bool nrefs1 = (ci.meta >> 14) & 1;
-    const int npl0 = rec_planes(0, gap & 1), npl1 = rec_planes(1, gap & 2);
-    const uint4* pa0 = X.rowstore + ci.rec1 + g * npl0;
-    const uint4* pb0 = X.rowstore + ci.rec2 + g * npl0;
-    const uint4* pa1 = X.rowstore + ci.rec1 + W4h * npl0 + g * npl1;
-    const uint4* pb1 = X.rowstore + ci.rec2 + W4h * npl0 + g * npl1;
+    constexpr int WS = (G == 4) ? 4 : 0;   // the 4-lane path only runs when both chains have W4 == 4
+    const int off1 = W4h * rec_planes(0, gap & 1);
+    const uint4* pa0 = X.rowstore + ci.rec1 + g;
+    const uint4* pb0 = X.rowstore + ci.rec2 + g;
+    const uint4* pa1 = pa0 + off1;
+    const uint4* pb1 = pb0 + off1;
     uint32_t pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;
     // Two references: nearly every such candidate dies on the degradation test (join_one.rs:434-440), which only
     // needs T01 = popc(t2 != r1 on cmp1) and T10 = popc(t1 != r2 on cmp2) — evaluate that first and stop early.
     if (active && !nrefs1 && !X.tuple_mode) {
         uint32_t tt = 0;
-        if (g < W4h) tt += s2_chain_degr<0>(pa0, pb0, gap & 1);
-        if (g < W4l) tt += s2_chain_degr<1>(pa1, pb1, gap & 2);
+        if (g < W4h) tt += s2_chain_degr<WS, 0>(pa0, pb0, W4h, gap & 1);
+        if (g < W4l) tt += s2_chain_degr<WS, 1>(pa1, pb1, W4l, gap & 2);
 #pragma unroll
         for (int o = 1; o < G; o <<= 1) tt += __shfl_xor_sync(gmask, tt, o);
         const int T01 = (int)(tt & 0xffff), T10 = (int)(tt >> 16);
@@ -283,8 +287,8 @@ __device__ __forceinline__ void s2_planes(const S2Ctx& X, const CandInfo& ci, in
             else hm = (1u << (ch - lo_bit)) - 1u;
             pk0 += (uint32_t)__popc(x & hm) | ((uint32_t)__popc(x & ~hm) << 16);
         }
-        if (g < W4h) s2_chain<G, 0>(pa0, pb0, gap & 1, nrefs1, pk1, pk2, pk3, n0, n1, n2, n3);
-        if (g < W4l) s2_chain<G, 1>(pa1, pb1, gap & 2, nrefs1, pk1, pk2, pk3, n0, n1, n2, n3);
+        if (g < W4h) s2_chain<WS, 0>(pa0, pb0, W4h, gap & 1, nrefs1, pk1, pk2, pk3, n0, n1, n2, n3);
+        if (g < W4l) s2_chain<WS, 1>(pa1, pb1, W4l, gap & 2, nrefs1, pk1, pk2, pk3, n0, n1, n2, n3);
     }
 #pragma unroll
     for (int o = 1; o < G; o <<= 1) {

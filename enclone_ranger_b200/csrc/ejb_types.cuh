@@ -75,9 +75,9 @@ struct SubBucket {
     int32_t owner;    // rank that owns this sub-bucket (multi-GPU sharding)
     int32_t pad;
 };
-// Row record layout.  Per chain m the record is LANE-MAJOR: for each uint4 index g (128 positions) the planes
-// of that window are contiguous, so a lane reads all its planes at compile-time offsets from one base pointer:
-//     chain m, window g, plane pl  ->  uint4 index  off_m + g * rec_planes(m, gap_m) + pl
+// Row record layout.  Per chain m the record is PLANE-MAJOR with a fixed plane order; W4 (uint4 per plane) is 4
+// for contigs up to 512 nt and 8 up to 1024 nt, so that the common case has a compile-time plane stride:
+//     chain m, plane pl, window g (128 positions)  ->  uint4 index  off_m + pl * W4_m + g
 //   PL_TLO, PL_THI : 2-bit code of the contig base ((byte >> 1) & 3: A,C,T,G = 0,1,2,3; '-' carries the gap bit)
 //   PL_D           : cmp & (contig base != own reference base)
 //   PL_RLO, PL_RHI : the row's own V / J reference bases in CONTIG coordinates (V from the start, J from the end)
