@@ -104,6 +104,9 @@ class EjbInput(C.Structure):
         ("ref_off", _i64p),
         ("ref_bytes", _u8p),
         ("ref_name_id", _i32p),
+        ("row_tig2_off", _i64p),
+        ("tig2_words", _u32p),
+        ("n_tig2_words", C.c_int64),
     ]
 
 

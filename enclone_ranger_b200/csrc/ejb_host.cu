@@ -455,6 +455,7 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     d.n_rows = in->n_rows; d.n_exacts = in->n_exacts; d.n_chains = in->n_chains; d.n_cells = in->n_cells;
     d.n_segs = in->n_segs; d.n_refs = in->n_refs;
     d.n_tig_bytes = in->n_tig_bytes; d.n_cdr3_bytes = in->n_cdr3_bytes; d.n_amino_bytes = in->n_amino_bytes;
+    d.n_tig2_words = in->row_tig2_off ? in->n_tig2_words : 0;
     const int64_t N = in->n_rows;
     // host-side: seg / ref byte totals need the last offset
     if (in->n_segs > 0 && !in->seg_off) return fail(c, EJB_ERR_INVALID, "seg_off is null");
@@ -501,6 +502,10 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     if ((rc = upload_array(c, in->ch_fr2_start, in->n_chains, &d.ch_fr2)) != EJB_OK) return rc;
     if ((rc = upload_array(c, in->ch_cdr2_start, in->n_chains, &d.ch_cdr2)) != EJB_OK) return rc;
     if ((rc = upload_array(c, in->ch_fr3_start, in->n_chains, &d.ch_fr3)) != EJB_OK) return rc;
+    if (in->row_tig2_off) {
+        if ((rc = upload_array(c, in->row_tig2_off, 2 * N, &d.row_tig2_off)) != EJB_OK) return rc;
+        if ((rc = upload_array(c, in->tig2_words, in->n_tig2_words, &d.tig2_words)) != EJB_OK) return rc;
+    }
     if ((rc = upload_array(c, canon.data(), in->n_segs, &d.seg_canon)) != EJB_OK) return rc;
     if (in->n_segs > 0 && !in->seg_bytes) return fail(c, EJB_ERR_INVALID, "seg_bytes is null");
     if ((rc = upload_array(c, (const uint8_t*)seg_canon_bytes.data(), d.n_seg_bytes, &d.seg_bytes)) != EJB_OK) return rc;
@@ -731,7 +736,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
         CK(cudaMemcpyAsync(&hdr, c->d_err.p, 16, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&n_buckets, c->d_scan.as<int32_t>() + (N - 1), 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (hdr.err) return fail(c, EJB_ERR_INVALID, "input validation failed (mask 0x%x: 1 nchains, 2 exact id, 4 tig offsets, 8 cdr3 offsets, 16 seg ids, 32 exact_cols, 64/128 exact tables, 256 ref ids, 512 amino, 1024 donor id >= 64, 2048 seg_off, 4096 ref_off)", hdr.err);
+        if (hdr.err) return fail(c, EJB_ERR_INVALID, "input validation failed (mask 0x%x: 1 nchains, 2 exact id, 4 tig offsets, 8 cdr3 offsets, 16 seg ids, 32 exact_cols, 64/128 exact tables, 256 ref ids, 512 amino, 1024 donor id >= 64, 2048 seg_off, 4096 ref_off, 8192 packed contig)", hdr.err);
         c->stats.n_buckets = n_buckets;
         c->n_active = (int64_t)hdr.n_active;
     }

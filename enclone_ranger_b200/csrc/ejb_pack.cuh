@@ -18,7 +18,10 @@ __global__ void k_heads(DevIn in, int32_t* head, unsigned int* err) {
     for (int m = 0; m < 2 && m < nc; m++) {
         const int64_t i = 2 * k + m;
         const int L = in.row_len[i];
-        if (L < 0 || in.row_tig_off[i] < 0 || in.row_tig_off[i] + L > in.n_tig_bytes) e |= 4;
+        const int64_t o2 = in.row_tig2_off ? in.row_tig2_off[i] : -1;
+        if (o2 >= 0) {   // 2-bit packed contig: pure ACGT by contract, never a has_del row
+            if (L < 0 || o2 + (L + 15) / 16 > in.n_tig2_words || in.row_has_del[i]) e |= 8192;
+        } else if (L < 0 || in.row_tig_off[i] < 0 || in.row_tig_off[i] + L > in.n_tig_bytes) e |= 4;
         const int c = in.row_cdr3_len[i];
         if (c < 0 || c > 65535 || in.row_cdr3_off[i] < 0 || in.row_cdr3_off[i] + c > in.n_cdr3_bytes) e |= 8;
         if (in.row_vs[i] < 0 || in.row_vs[i] >= in.n_segs || in.row_js[i] < 0 || in.row_js[i] >= in.n_segs) e |= 16;
@@ -204,7 +207,10 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
         const int W4 = (m == 0) ? sb.W4h : sb.W4l;
         const int gapbit = (sb.gap >> m) & 1;
         const bool hasdel = in.row_has_del[2 * k + m] != 0;
-        const uint8_t* tig = in.tig_bytes + in.row_tig_off[2 * k + m];
+        const int64_t off2 = in.row_tig2_off ? in.row_tig2_off[2 * k + m] : -1;
+        const bool packed = off2 >= 0;
+        const uint8_t* tig = in.tig_bytes + (packed ? 0 : in.row_tig_off[2 * k + m]);
+        const uint32_t* tig2 = in.tig2_words + (packed ? off2 : 0);
         const int sv = in.row_vs[2 * k + m], sj = in.row_js[2 * k + m];
         const uint8_t* vseg = in.seg_bytes + in.seg_off[sv];
         const uint8_t* jseg = in.seg_bytes + in.seg_off[sj];
@@ -225,17 +231,24 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
 #pragma unroll 4
         for (int w = 0; w < nwords; w++) {
             const int p = w * 32 + lane;
-            uint32_t b = 0, rbyte = 0;
+            uint32_t b = 'A', rbyte = 0, code = 0;
             bool inr = false;
             if (p < L) {
-                b = tig[p];
+                if (packed) {
+                    const uint32_t c2 = (tig2[p >> 4] >> (2 * (p & 15))) & 3u;   // A,C,G,T = 0..3
+                    code = c2 ^ (c2 >> 1);                                      // -> internal A,C,T,G = 0,1,2,3
+                } else {
+                    b = tig[p];
+                    code = base_code(b);
+                }
                 if (p < vr) { rbyte = vseg[p]; inr = true; }
                 else if (p >= L - jr) { rbyte = jseg[p + jshift]; inr = true; }
             }
             const bool gapb = (b == '-') && hasdel;
             if (p < L && !gapb && !is_acgt_fast(b)) odd = true;
-            const uint32_t code = base_code(b), rcode = base_code(rbyte);
-            const bool dbit = inr && (b != rbyte);   // seg bytes are canonical upper-case ACGT (host), '-' never equals them
+            const uint32_t rcode = base_code(rbyte);
+            // seg bytes are canonical upper-case ACGT (host); '-' and odd bytes never equal them
+            const bool dbit = inr && (packed ? (code != rcode) : (b != rbyte));
             int rid = 0;
             if (m == 0) {
                 if (p >= rF0 && p < rF1) rid = 1;
@@ -268,7 +281,7 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
             }
             if (gapbit) r[gap_plane(m) * st] = k_gap;
         }
-        if (W4 == 0) {  // contig longer than the fast path: the byte-exact path handles it
+        if (W4 == 0 && !packed) {  // contig longer than the fast path: the byte-exact path handles it
             for (int p = lane; p < L; p += 32)
                 if (!is_acgt_fast(tig[p]) && !(tig[p] == '-' && hasdel)) odd = true;
         }

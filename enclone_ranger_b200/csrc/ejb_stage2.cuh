@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(256) k_stage2_slow(S2Ctx X, const unsigned lon
         int diffs = 0;
         for (int m = 0; m < 2; m++) {
             const int L = m ? sb.Ll : sb.Lh;
-            const uint8_t *a = in.tig_bytes + in.row_tig_off[2 * k1 + m], *b = in.tig_bytes + in.row_tig_off[2 * k2 + m];
+            const TigRef a = tig_ref(in, k1, m), b = tig_ref(in, k2, m);
             const bool hd = in.row_has_del[2 * k1 + m] || in.row_has_del[2 * k2 + m];
             if (!hd) {
                 for (int p = lane; p < L; p += 32) diffs += (base2bit(a[p]) != base2bit(b[p]));
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(256) k_stage2_slow(S2Ctx X, const unsigned lon
             const int64_t k = u ? k2 : k1;
             for (int m = 0; m < 2; m++) {
                 const int L = m ? sb.Ll : sb.Lh;
-                const uint8_t *t1 = in.tig_bytes + in.row_tig_off[2 * k1 + m], *t2 = in.tig_bytes + in.row_tig_off[2 * k2 + m];
+                const TigRef t1 = tig_ref(in, k1, m), t2 = tig_ref(in, k2, m);
                 for (int si = 0; si < 2; si++) {
                     const int sg = si ? in.row_js[2 * k + m] : in.row_vs[2 * k + m];
                     const uint8_t* seg = in.seg_bytes + in.seg_off[sg];
@@ -654,12 +654,12 @@ __global__ void __launch_bounds__(256) k_stage2b(S2Ctx X, const unsigned long lo
                 for (int m = 0; m < 2; m++) {
                     const int x1 = a1[AX_CHH + m], x2 = a2[AX_CHH + m];
                     if (!in.ch_left[x1]) continue;
-                    const uint8_t *s1, *s2;
+                    TigRef s1, s2;
                     long long sl1, sl2;
-                    if (in.ch_amino_off[x1] != -1) { s1 = in.amino_bytes + in.ch_amino_off[x1]; sl1 = in.ch_amino_len[x1]; }
-                    else { s1 = in.tig_bytes + in.row_tig_off[2 * k1 + m]; sl1 = m ? sb.Ll : sb.Lh; }
-                    if (in.ch_amino_off[x2] != -1) { s2 = in.amino_bytes + in.ch_amino_off[x2]; sl2 = in.ch_amino_len[x2]; }
-                    else { s2 = in.tig_bytes + in.row_tig_off[2 * k2 + m]; sl2 = m ? sb.Ll : sb.Lh; }
+                    if (in.ch_amino_off[x1] != -1) { s1.b = in.amino_bytes + in.ch_amino_off[x1]; s1.w = nullptr; sl1 = in.ch_amino_len[x1]; }
+                    else { s1 = tig_ref(in, k1, m); sl1 = m ? sb.Ll : sb.Lh; }
+                    if (in.ch_amino_off[x2] != -1) { s2.b = in.amino_bytes + in.ch_amino_off[x2]; s2.w = nullptr; sl2 = in.ch_amino_len[x2]; }
+                    else { s2 = tig_ref(in, k2, m); sl2 = m ? sb.Ll : sb.Lh; }
                     auto region = [&](long long r1a, long long r1b, long long r2a, long long r2b, long long& rlen, long long& rdiffs) {
                         const long long len = r1b - r1a;
                         if (r2b - r2a == len) {

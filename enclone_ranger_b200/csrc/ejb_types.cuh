@@ -111,6 +111,9 @@ struct DevIn {
     const int64_t* ref_off;
     const uint8_t* ref_bytes;
     const int32_t* ref_name_id;
+    const int64_t* row_tig2_off;   // optional 2-bit packed contigs (NULL: all ASCII)
+    const uint32_t* tig2_words;
+    int64_t n_tig2_words;
 };
 
 // Flat join knobs on the device.
@@ -153,6 +156,27 @@ __device__ __forceinline__ int base2bit(uint8_t b) {  // debruijn base_to_bits: 
 }
 __device__ __forceinline__ bool is_acgt(uint8_t b) { return b == 'A' || b == 'C' || b == 'G' || b == 'T'; }
 __device__ __forceinline__ uint8_t bit2base(int x) { return (uint8_t)("ACGT"[x]); }
+
+// A contig that is either ASCII bytes or 2-bit packed words (16 bases per word, A,C,G,T = 0..3); the byte-exact
+// paths read it through this view.
+struct TigRef {
+    const uint8_t* b;
+    const uint32_t* w;
+    __device__ __forceinline__ uint8_t operator[](long long p) const {
+        if (b) return b[p];
+        const uint32_t x = w[p >> 4];
+        return (uint8_t)("ACGT"[(x >> (2 * (int)(p & 15))) & 3u]);
+    }
+};
+__device__ __forceinline__ TigRef tig_ref(const DevIn& in, int64_t k, int m) {
+    TigRef r;
+    r.b = nullptr;
+    r.w = nullptr;
+    const int64_t o2 = in.row_tig2_off ? in.row_tig2_off[2 * k + m] : -1;
+    if (o2 >= 0) r.w = in.tig2_words + o2;
+    else r.b = in.tig_bytes + in.row_tig_off[2 * k + m];
+    return r;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

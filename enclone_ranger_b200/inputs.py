@@ -23,6 +23,8 @@ _FIELDS = {
     "cell_donor": np.int32, "cell_barcode": np.uint32,
     "seg_off": np.int64, "seg_bytes": np.uint8, "ref_off": np.int64, "ref_bytes": np.uint8,
     "ref_name_id": np.int32,
+    # optional 2-bit packed contigs
+    "row_tig2_off": np.int64, "tig2_words": np.uint32,
 }
 
 
@@ -57,6 +59,9 @@ class JoinInput:
             setattr(c, name, _ptr(self._keep[name], _CT[dt]))
         c.n_rows, c.n_exacts, c.n_chains = self.n_rows, self.n_exacts, self.n_chains
         c.n_cells, c.n_segs, c.n_refs = self.n_cells, self.n_segs, self.n_refs
+        c.n_tig2_words = int(a["tig2_words"].size)
+        if a["row_tig2_off"].size == 0:
+            c.row_tig2_off = None          # NULL: every contig is ASCII
         c.n_tig_bytes = int(a["tig_bytes"].size)
         c.n_cdr3_bytes = int(a["cdr3_bytes"].size)
         c.n_amino_bytes = int(a["amino_bytes"].size)
@@ -83,6 +88,7 @@ class JoinInput:
             "ch_cdr2_start": CH, "ch_fr3_start": CH, "ch_hcomp": CH, "ch_amino_off": CH,
             "ch_amino_len": CH, "amino_bytes": cin.n_amino_bytes, "cell_donor": X, "cell_barcode": X,
             "seg_off": S + 1, "seg_bytes": 0, "ref_off": R + 1, "ref_bytes": 0, "ref_name_id": R,
+            "row_tig2_off": 2 * N if cin.row_tig2_off else 0, "tig2_words": cin.n_tig2_words,
         }
         out = {}
         for name, dt in _FIELDS.items():
@@ -106,6 +112,7 @@ class JoinInput:
         return JoinInput(**b)
 
     def subset_rows(self, idx):
+        assert self.a["row_tig2_off"].size == 0, "subset the ASCII form, then call to_packed()"
         """Rows `idx` (ascending) with the exact / chain / cell tables compacted to what those rows reference.
         Seg and ref tables are kept whole (they are small).  Returns (JoinInput, old exact id of each new exact)."""
         idx = np.asarray(idx, dtype=np.int64)
@@ -141,6 +148,47 @@ class JoinInput:
         b["ex_cell_off"], ce, _ = compact(a["ex_cell_off"], ["cell_donor", "cell_barcode"])
         b.update(ce)
         return JoinInput(**b), used
+
+    def to_packed(self):
+        """The same input with every eligible contig (pure upper-case ACGT, has_del == 0) supplied 2-bit packed
+        (what the Rust shim sends from info[k].tigsp); the other contigs stay ASCII."""
+        a = self.a
+        n2 = 2 * self.n_rows
+        ln = a["row_len"].astype(np.int64)
+        if a["row_tig2_off"].size:
+            return self
+        valid = np.repeat(a["row_nchains"], 2) > np.tile([0, 1], self.n_rows)
+        ln = np.where(valid, ln, 0)
+        off = a["row_tig_off"]
+        total = int(ln.sum())
+        src = np.repeat(off - (np.cumsum(ln) - ln), ln) + np.arange(total, dtype=np.int64)
+        flat = a["tig_bytes"][src] if total else np.zeros(0, np.uint8)
+        lut = np.full(256, 255, dtype=np.uint8)
+        lut[ord("A")], lut[ord("C")], lut[ord("G")], lut[ord("T")] = 0, 1, 2, 3
+        codes = lut[flat]
+        seg = np.repeat(np.arange(n2), ln)
+        bad = np.zeros(n2, dtype=bool)
+        if total:
+            np.logical_or.at(bad, seg, codes == 255)
+        elig = valid & ~bad & (a["row_has_del"] == 0) & (ln > 0)
+        nw = np.where(elig, (ln + 15) // 16, 0)
+        woff = np.cumsum(nw) - nw
+        words = np.zeros(int(nw.sum()), dtype=np.uint32)
+        keep = elig[seg]
+        pos = (np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(ln) - ln, ln))[keep]
+        widx = woff[seg[keep]] + pos // 16
+        np.bitwise_or.at(words, widx, (codes[keep].astype(np.uint32) << (2 * (pos % 16)).astype(np.uint32)))
+        b = dict(a)
+        b["row_tig2_off"] = np.where(elig, woff, -1).astype(np.int64)
+        b["tig2_words"] = words
+        # ASCII bytes only for the rows that stay ASCII
+        ln_ascii = np.where(elig, 0, ln)
+        new_off = np.cumsum(ln_ascii) - ln_ascii
+        tot2 = int(ln_ascii.sum())
+        src2 = np.repeat(off - new_off, ln_ascii) + np.arange(tot2, dtype=np.int64)
+        b["tig_bytes"] = a["tig_bytes"][src2] if tot2 else np.zeros(0, np.uint8)
+        b["row_tig_off"] = np.where(elig, -1, new_off).astype(np.int64)
+        return JoinInput(**b)
 
     def nbytes(self):
         return int(sum(v.nbytes for v in self.a.values()))

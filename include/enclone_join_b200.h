@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define EJB_ABI_VERSION 1
+#define EJB_ABI_VERSION 2
 #define EJB_NONE (-1)
 
 typedef enum ejb_status {
@@ -163,6 +163,16 @@ typedef struct ejb_input {
     const uint8_t* ref_bytes;     /* ASCII ACGT                                                   */
     const int32_t* ref_name_id;   /* [n_refs] interned id of refdata.name[r] with any "*..." suffix
                                      removed (TextUtils::before("*"), join_one.rs:727-732)        */
+
+    /* ---- optional: 2-bit packed contigs (the role of info[k].tigsp, defs.rs:744) ----
+     * A row-chain whose contig is pure upper-case ACGT and has_del == 0 may be supplied packed instead of
+     * as ASCII: row_tig2_off[2*k+m] >= 0 is the index of its first word in tig2_words (16 bases per
+     * uint32_t, base i in bits [2i%32, 2i%32+2) of word i/16, A,C,G,T = 0,1,2,3); row_tig_off is then
+     * ignored for that row-chain.  row_tig2_off == NULL or an entry == EJB_NONE means ASCII.
+     * A quarter of the bytes to copy to the device.                                              */
+    const int64_t* row_tig2_off;  /* [2*n_rows] or NULL                                           */
+    const uint32_t* tig2_words;
+    int64_t n_tig2_words;
 } ejb_input;
 
 /* Counters and timings of one join (all optional diagnostics). */

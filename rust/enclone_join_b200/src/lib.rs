@@ -47,6 +47,7 @@ pub mod sys {
         pub n_cells: i64, pub cell_donor: *const i32, pub cell_barcode: *const u32,
         pub n_segs: i64, pub seg_off: *const i64, pub seg_bytes: *const u8,
         pub n_refs: i64, pub ref_off: *const i64, pub ref_bytes: *const u8, pub ref_name_id: *const i32,
+        pub row_tig2_off: *const i64, pub tig2_words: *const u32, pub n_tig2_words: i64,
     }
 
     #[repr(C)]
@@ -128,6 +129,8 @@ pub fn join_exacts(
     let (mut row_cdr3_off, mut row_cdr3_len) = (vec![0i64; 2 * n], vec![0i32; 2 * n]);
     let mut row_exact_col = vec![0i32; 2 * n];
     let (mut tig_bytes, mut cdr3_bytes) = (Vec::<u8>::new(), Vec::<u8>::new());
+    let mut row_tig2_off = vec![-1i64; 2 * n];
+    let mut tig2_words = Vec::<u32>::new();   // 2-bit packed contigs (from tigsp) for rows without indel marks
     let mut segs: HashMap<Vec<u8>, i32> = HashMap::new();   // DnaString content -> seg id (join_one.rs:331 compares content)
     let (mut seg_off, mut seg_bytes) = (vec![0i64], Vec::<u8>::new());
     let mut seg_id = |s: &debruijn::dna_string::DnaString| -> i32 {
@@ -145,8 +148,22 @@ pub fn join_exacts(
         for m in 0..x.lens.len().min(2) {
             let i = 2 * k + m;
             row_len[i] = x.lens[m] as i32;
-            row_tig_off[i] = tig_bytes.len() as i64;
-            tig_bytes.extend_from_slice(&x.tigs[m]);
+            if !x.has_del[m] && x.tigs[m].iter().all(|b| matches!(b, b'A' | b'C' | b'G' | b'T')) {
+                // tigsp[m] holds the same bases 2-bit packed (info.rs:64); re-pack 16 per u32, base i at bits 2*(i%16)
+                row_tig2_off[i] = tig2_words.len() as i64;
+                row_tig_off[i] = -1;
+                let sp = &x.tigsp[m];
+                for w in 0..(sp.len() + 15) / 16 {
+                    let mut v = 0u32;
+                    for j in 0..16.min(sp.len() - 16 * w) {
+                        v |= (sp.get(16 * w + j) as u32) << (2 * j);
+                    }
+                    tig2_words.push(v);
+                }
+            } else {
+                row_tig_off[i] = tig_bytes.len() as i64;
+                tig_bytes.extend_from_slice(&x.tigs[m]);
+            }
             row_has_del[i] = x.has_del[m] as u8;
             row_vs[i] = seg_id(&x.vs[m]);
             row_js[i] = seg_id(&x.js[m]);
@@ -220,6 +237,7 @@ pub fn join_exacts(
         n_cells: cell_donor.len() as i64, cell_donor: cell_donor.as_ptr(), cell_barcode: cell_barcode.as_ptr(),
         n_segs: (seg_off.len() - 1) as i64, seg_off: seg_off.as_ptr(), seg_bytes: seg_bytes.as_ptr(),
         n_refs: refdata.refs.len() as i64, ref_off: ref_off.as_ptr(), ref_bytes: ref_bytes.as_ptr(), ref_name_id: ref_name_id.as_ptr(),
+        row_tig2_off: row_tig2_off.as_ptr(), tig2_words: tig2_words.as_ptr(), n_tig2_words: tig2_words.len() as i64,
     };
 
     // ---- call the library; errors become panics, like the reference's own invariant failures ----

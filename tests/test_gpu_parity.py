@@ -42,6 +42,26 @@ def test_synthetic_config_matches_oracle(gpu_ctx, config, cells, seed):
     assert np.array_equal(got.labels, want["labels"])
 
 
+@pytest.mark.parametrize("name,params,inp,expected", CASES, ids=[c[0] for c in CASES])
+def test_micro_case_packed_contigs(gpu_ctx, name, params, inp, expected):
+    """Same cases with every eligible contig supplied 2-bit packed (the tigsp path of the ABI)."""
+    want = pyoracle.run(params, inp.c_ptr(), threads=1)
+    assert_same_result(gpu_ctx.join(params, inp.to_packed()), want, name + " (packed)")
+
+
+@pytest.mark.parametrize("config,cells", [(0, 20000), (1, 40000), (2, 100000)])
+def test_synthetic_packed_contigs(gpu_ctx, config, cells):
+    rep = E.generate(config, n_cells=cells, seed=77)
+    p = E.default_params(bool(rep.config.is_bcr))
+    inp = rep.to_join_input()
+    pk = inp.to_packed()
+    assert pk.a["tig_bytes"].size < inp.a["tig_bytes"].size // 10
+    want = pyoracle.run(p, inp.c_ptr(), threads=0)
+    got = gpu_ctx.join(p, pk)
+    assert_same_result(got, want, f"config {config} packed")
+    assert got.stats["h2d_bytes"] < 0.6 * gpu_ctx.join(p, inp).stats["h2d_bytes"]
+
+
 def test_tiny_work_buffers_force_round_splitting():
     """A candidate buffer far smaller than one round's candidates: the scheduler must split rounds / row-block
     groups and still produce the identical forest (the order-dependent part of join_core)."""
