@@ -99,6 +99,8 @@ struct ejb_ctx {
     DevBuf d_head, d_scan, d_keys, d_keys2, d_vals, d_vals2, d_cubtmp, d_subhead, d_subincl, d_subinfo;
     DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_aux;
     DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
+    DevBuf d_unitcand;
+    std::vector<unsigned long long> h_unitcand;   // candidates each unit of the last round produced (valid even when it overflowed)
     DevBuf d_tasks, d_cand, d_slow, d_slowslot, d_surv, d_pass, d_roots, d_forest;
     DevBuf d_qofrow, d_deg, d_tuples, d_keep, d_first, d_labels, d_fkeys, d_fkeys2, d_fidx, d_fidx2, d_nout;
     DevBuf d_pairs_all, d_slots, d_cnt;
@@ -232,12 +234,13 @@ template <int W1>
 void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks) {
     k_stage1<W1><<<(unsigned int)n_ctas, S1_THREADS, 0, c->stream>>>(c->d_subs.as<SubBucket>(), tasks, n_tasks, c->d_cdr3w.as<uint32_t>(),
                                                                       c->d_labq.as<int32_t>(), c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(),
-                                                                      c->cand_cap, c->d_ctr.as<Counters>());
+                                                                      c->cand_cap, c->d_ctr.as<Counters>(), c->d_unitcand.as<unsigned long long>());
 }
 
 // stage-1 for sub-buckets whose CDR3s exceed the fast path: every not-yet-connected pair is a candidate
 __global__ void k_stage1_nofilter(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, int n_tasks,
-                                  const int32_t* __restrict__ labq, uint2* __restrict__ cand, unsigned long long cand_cap, Counters* ctr) {
+                                  const int32_t* __restrict__ labq, uint2* __restrict__ cand, unsigned long long cand_cap, Counters* ctr,
+                                  unsigned long long* __restrict__ unit_cand) {
     const int64_t cta = blockIdx.x;
     int lo = 0, hi = n_tasks - 1;
     while (lo < hi) {
@@ -258,6 +261,7 @@ __global__ void k_stage1_nofilter(const SubBucket* __restrict__ subs, const RowT
             const uint32_t q1 = (uint32_t)(sb.q0 + r), q2 = (uint32_t)(sb.q0 + cc);
             if (labq[q1] == labq[q2]) continue;
             const unsigned long long o = atomicAdd(&ctr->n_cand, 1ull);
+            atomicAdd(&unit_cand[t.unit], 1ull);
             if (o < cand_cap) cand[o] = make_uint2(q1, q2); else ctr->overflow = 1ull;
         }
     }
@@ -549,14 +553,20 @@ int cub_incl_sum(ejb_ctx* c, const int32_t* in, int32_t* out, int64_t n) {
 int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes>& times) {
     const unsigned long long eval_before = c->pairs_eval_seen;
     const std::vector<SubBucket>& subs = c->subs;
+    CK(c->d_unitcand.ensure(units.size() * 8 + 8));
+    CK(cudaMemsetAsync(c->d_unitcand.p, 0, units.size() * 8, c->stream));
+    c->h_unitcand.assign(units.size(), 0);
     // ---- tasks grouped by W1 ----
     std::vector<RowTask> tasks[MAXW1 + 1];
     int64_t nctas[MAXW1 + 1] = {0};
-    for (const Unit& u : units) {
+    for (size_t ui = 0; ui < units.size(); ui++) {
+        const Unit& u = units[ui];
         const SubBucket& sb = subs[u.sub];
         const int nb = (sb.n + TILE - 1) / TILE;
         for (int rb = u.r0 / TILE; rb * TILE < u.r1; rb++) {
             RowTask t;
+            t.unit = (int32_t)ui;
+            t.pad = 0;
             t.sub = u.sub;
             t.rb = rb;
             t.row_lo = std::max(u.r0 - rb * TILE, 0);
@@ -584,7 +594,7 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
         switch (w) {
             case 0:
                 k_stage1_nofilter<<<(unsigned int)nctas[0], 256, 0, c->stream>>>(c->d_subs.as<SubBucket>(), dt, nt, c->d_labq.as<int32_t>(),
-                                                                                c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr.as<Counters>());
+                                                                                c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr.as<Counters>(), c->d_unitcand.as<unsigned long long>());
                 break;
             case 1: launch_stage1_w<1>(c, nctas[1], dt, nt); break;
             case 2: launch_stage1_w<2>(c, nctas[2], dt, nt); break;
@@ -609,6 +619,7 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
     k_bor_min<<<grid, 256, 0, c->stream>>>(c->d_pass.as<unsigned long long>(), CTR_FIELD(n_pass), c->cand_cap, c->d_parent.as<int32_t>(),
                                           c->d_best.as<unsigned long long>(), 0, c->d_roots.as<int2>(), c->d_ctr.as<Counters>());
     c->stats.kernel_launches += 2;
+    CK(cudaMemcpyAsync(c->h_unitcand.data(), c->d_unitcand.p, units.size() * 8, cudaMemcpyDeviceToHost, c->stream));
     rc = sync_counters(c);
     if (rc) return rc;
     const Counters& h = *c->h_ctr;
@@ -657,34 +668,6 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
     times.push_back(rt);
     c->stats.rounds++;
     return EJB_OK;
-}
-
-// runs `units` as one round; on overflow splits and recurses (each part commits before the next)
-int run_units(ejb_ctx* c, std::vector<Unit> units, std::vector<RoundTimes>& times, int depth) {
-    if (units.empty()) return EJB_OK;
-    int rc = run_round(c, units, times);
-    if (rc != 1) return rc;
-    if (depth > 40) return fail(c, EJB_ERR_OOM, "candidate buffer too small even for a single row block; raise EJB_CAND_CAP");
-    if (units.size() > 1) {
-        const size_t h = units.size() / 2;
-        std::vector<Unit> a(units.begin(), units.begin() + h), b(units.begin() + h, units.end());
-        rc = run_units(c, a, times, depth + 1);
-        if (rc) return rc;
-        return run_units(c, b, times, depth + 1);
-    }
-    Unit u = units[0];
-    if (u.r1 - u.r0 <= 1)
-        return fail(c, EJB_ERR_OOM, "work buffers (%llu entries) too small for one row of a %d-row sub-bucket; raise EJB_CAND_CAP", c->cand_cap,
-                    c->subs[u.sub].n);
-    // NOTE: a unit may be split by ROWS only.  Splitting a row range by columns and contracting after each part is not
-    // exact: a lighter edge (smaller k1, later column part) could have to evict a heavier edge already in the forest.
-    const int mid = (u.r0 + u.r1) / 2;
-    Unit a = u, b = u;
-    a.r1 = mid;
-    b.r0 = mid;
-    rc = run_units(c, {a}, times, depth + 1);
-    if (rc) return rc;
-    return run_units(c, {b}, times, depth + 1);
 }
 
 }  // namespace
@@ -919,33 +902,37 @@ extern "C" int ejb_run(ejb_ctx* c) {
     // ---- round scheduler ----
     {
         const std::vector<SubBucket>& subs = c->subs;
+        // Units: rows [r0, r1) of a sub-bucket against every column to their right, in row order.  A unit may only be
+        // split by ROWS (splitting by columns and contracting after each part is not exact: a lighter edge from a later
+        // column part could have to evict a heavier edge already in the forest).  Unit sizes adapt to the measured
+        // candidates per row of the sub-bucket's previous unit: thin while a dense clone is being connected (its pairs are
+        // not yet skipped by the class test), growing 4x per round once the rows ahead are mostly connected.
         std::vector<int> next_row(subs.size(), 0), live;
+        std::vector<double> rho(subs.size(), -1.0);   // candidates per row of the last unit, < 0 = unknown
         for (int s = 0; s < (int)subs.size(); s++)
             if (subs[s].n >= 2 && subs[s].owner == c->shard_rank) live.push_back(s);
+        const double target_unit = std::max(4096.0, (double)c->cand_cap / 64.0);   // candidates one unit should produce
+        int stalls = 0;
         while (!live.empty()) {
             std::vector<Unit> units;
             unsigned long long pairs = 0;
-            // keep the expected candidates of a round at <= 60 % of the buffers (rate of the previous round, x2 margin;
-            // a misprediction only costs one split-and-retry)
-            unsigned long long budget = c->pair_budget;
-            if (c->cand_rate > 0.0) budget = std::min<unsigned long long>(budget, (unsigned long long)(0.6 * (double)c->cand_cap / std::min(1.0, 2.0 * c->cand_rate)));
-            budget = std::max<unsigned long long>(budget, 1ull << 14);
+            double expect = 0.0;   // expected candidates of this round
+            const unsigned long long budget = std::max<unsigned long long>(c->pair_budget, 1ull << 14);
             std::vector<int> still;
             for (int s : live) {
                 const SubBucket& sb = subs[s];
-                // pairs of rows [r0, r1) x everything to their right
                 auto unit_pairs = [&](long long r0, long long r1) {
                     const long long rows = r1 - r0;
                     return (unsigned long long)(rows * (sb.n - r1) + rows * (rows - 1) / 2);
                 };
-                // unit sizes: rows [0,8), [8,32), [32,128), then doubling — the first few rows of a clone connect most of
-                // it, so later units are mostly skipped by the class test; a unit never exceeds half the round budget
                 const int r0 = next_row[s];
-                int r1 = (r0 < 8) ? 8 : (r0 < 32) ? 32 : (r0 < TILE) ? TILE : std::min<long long>(2ll * r0, (long long)r0 + (1 << 21));
-                r1 = std::min(r1, sb.n);
+                long long want = (r0 == 0) ? 8 : std::max<long long>(8, 4ll * r0);            // growth: x4 of the rows done so far
+                if (rho[s] > 0.0) want = std::min<long long>(want, std::max<long long>(1, (long long)(target_unit / rho[s])));
+                int r1 = (int)std::min<long long>((long long)r0 + want, sb.n);
                 while (r1 - r0 > 1 && unit_pairs(r0, r1) > budget / 2) r1 = r0 + (r1 - r0) / 2;
                 const unsigned long long up = unit_pairs(r0, r1);
-                if (!units.empty() && pairs + up > budget) {
+                const double ex = (rho[s] > 0.0 ? rho[s] : std::min<double>(64.0, (double)sb.n)) * (double)(r1 - r0);
+                if (!units.empty() && (pairs + up > budget || expect + ex > 0.5 * (double)c->cand_cap)) {
                     still.push_back(s);
                     continue;
                 }
@@ -955,12 +942,32 @@ extern "C" int ejb_run(ejb_ctx* c) {
                 u.r1 = r1;
                 units.push_back(u);
                 pairs += up;
+                expect += ex;
                 next_row[s] = r1;
                 if (r1 < sb.n - 1) still.push_back(s);   // the last row has no pair to its right
             }
+            int rc = run_round(c, units, times);
+            if (rc != 0 && rc != 1) return rc;
+            // measured density of every unit (also valid for a round that overflowed and was not committed)
+            for (size_t ui = 0; ui < units.size(); ui++)
+                rho[units[ui].sub] = std::max(1e-3, (double)c->h_unitcand[ui] / (double)(units[ui].r1 - units[ui].r0));
+            if (rc == 1) {
+                // nothing was committed: put the units back and re-plan them with the measured densities
+                if (units.size() == 1 && units[0].r1 - units[0].r0 <= 1)
+                    return fail(c, EJB_ERR_OOM, "work buffers (%llu entries) too small for one row of a %d-row sub-bucket; raise EJB_CAND_CAP",
+                                c->cand_cap, subs[units[0].sub].n);
+                if (++stalls > 64) return fail(c, EJB_ERR_OOM, "scheduler cannot fit a round into the work buffers; raise EJB_CAND_CAP");
+                for (const Unit& u : units) {
+                    if (next_row[u.sub] >= subs[u.sub].n - 1 && std::find(still.begin(), still.end(), u.sub) == still.end()) still.push_back(u.sub);
+                    next_row[u.sub] = u.r0;
+                    // make sure the retry is strictly smaller even when the density estimate says otherwise
+                    rho[u.sub] = std::max(rho[u.sub], 2.0 * target_unit / (double)std::max(1, u.r1 - u.r0));
+                }
+                std::sort(still.begin(), still.end());
+            } else {
+                stalls = 0;
+            }
             live.swap(still);
-            int rc = run_units(c, units, times, 0);
-            if (rc) return rc;
         }
     }
     CK(cudaEventRecord(ev_rounds, st));

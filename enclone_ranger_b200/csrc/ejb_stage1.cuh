@@ -18,6 +18,7 @@ struct RowTask {       // (part of) one row block of one sub-bucket, against eve
     int32_t rb;
     int64_t cta0;      // first CTA of this task inside the launch
     int32_t row_lo, row_hi;   // local rows [row_lo, row_hi) of the block belong to this round's unit
+    int32_t unit, pad;        // index of the unit in this round (per-unit candidate counters)
 };
 
 template <int W1>
@@ -46,7 +47,8 @@ template <int W1>
 __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2)) k_stage1(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, int n_tasks,
                                                        const uint32_t* __restrict__ cdr3w, const int32_t* __restrict__ labq,
                                                        const int32_t* __restrict__ blk_lab, uint2* __restrict__ cand,
-                                                       unsigned long long cand_cap, Counters* __restrict__ ctr) {
+                                                       unsigned long long cand_cap, Counters* __restrict__ ctr,
+                                                       unsigned long long* __restrict__ unit_cand) {
     constexpr int NP = 2 * W1;           // plane-words per row
     constexpr int SLOT = (NP + 1) * TILE; // words per staged tile (planes + labels)
     __shared__ __align__(16) uint32_t s_row[SLOT];
@@ -198,7 +200,10 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
                         }
                     }
                 }
-                if (nh) s_base = atomicAdd(&ctr->n_cand, (unsigned long long)nh);
+                if (nh) {
+                    s_base = atomicAdd(&ctr->n_cand, (unsigned long long)nh);
+                    atomicAdd(&unit_cand[t.unit], (unsigned long long)nh);
+                }
             }
             if (nh) {
                 __syncthreads();
