@@ -100,7 +100,9 @@ struct ejb_ctx {
     DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_aux;
     DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
     DevBuf d_unitcand;
-    std::vector<unsigned long long> h_unitcand;   // candidates each unit of the last round produced (valid even when it overflowed)
+    std::vector<unsigned long long> h_unitcand;   // candidates of each task (row range) of the last round, valid even when it overflowed
+    struct TaskMeta { int32_t unit, r0, r1; };
+    std::vector<TaskMeta> task_meta;
     DevBuf d_tasks, d_cand, d_slow, d_slowslot, d_surv, d_pass, d_roots, d_forest;
     DevBuf d_qofrow, d_deg, d_tuples, d_keep, d_first, d_labels, d_fkeys, d_fkeys2, d_fidx, d_fidx2, d_nout;
     DevBuf d_pairs_all, d_slots, d_cnt;
@@ -261,7 +263,7 @@ __global__ void k_stage1_nofilter(const SubBucket* __restrict__ subs, const RowT
             const uint32_t q1 = (uint32_t)(sb.q0 + r), q2 = (uint32_t)(sb.q0 + cc);
             if (labq[q1] == labq[q2]) continue;
             const unsigned long long o = atomicAdd(&ctr->n_cand, 1ull);
-            atomicAdd(&unit_cand[t.unit], 1ull);
+            atomicAdd(&unit_cand[t.tid], 1ull);
             if (o < cand_cap) cand[o] = make_uint2(q1, q2); else ctr->overflow = 1ull;
         }
     }
@@ -553,11 +555,9 @@ int cub_incl_sum(ejb_ctx* c, const int32_t* in, int32_t* out, int64_t n) {
 int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes>& times) {
     const unsigned long long eval_before = c->pairs_eval_seen;
     const std::vector<SubBucket>& subs = c->subs;
-    CK(c->d_unitcand.ensure(units.size() * 8 + 8));
-    CK(cudaMemsetAsync(c->d_unitcand.p, 0, units.size() * 8, c->stream));
-    c->h_unitcand.assign(units.size(), 0);
-    // ---- tasks grouped by W1 ----
+    // ---- tasks grouped by W1; task ids number them in launch order ----
     std::vector<RowTask> tasks[MAXW1 + 1];
+    std::vector<ejb_ctx::TaskMeta> metas[MAXW1 + 1];
     int64_t nctas[MAXW1 + 1] = {0};
     for (size_t ui = 0; ui < units.size(); ui++) {
         const Unit& u = units[ui];
@@ -565,7 +565,7 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
         const int nb = (sb.n + TILE - 1) / TILE;
         for (int rb = u.r0 / TILE; rb * TILE < u.r1; rb++) {
             RowTask t;
-            t.unit = (int32_t)ui;
+            t.tid = 0;
             t.pad = 0;
             t.sub = u.sub;
             t.rb = rb;
@@ -573,12 +573,23 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
             t.row_hi = std::min(u.r1 - rb * TILE, TILE);
             t.cta0 = nctas[sb.W1];
             tasks[sb.W1].push_back(t);
+            metas[sb.W1].push_back({(int32_t)ui, rb * TILE + t.row_lo, rb * TILE + t.row_hi});
             nctas[sb.W1] += (nb - rb + S1_STRIP - 1) / S1_STRIP;
+        }
+    }
+    c->task_meta.clear();
+    for (int w = 0; w <= MAXW1; w++) {
+        for (size_t i = 0; i < tasks[w].size(); i++) {
+            tasks[w][i].tid = (int32_t)c->task_meta.size();
+            c->task_meta.push_back(metas[w][i]);
         }
     }
     size_t total_tasks = 0;
     for (auto& v : tasks) total_tasks += v.size();
     CK(c->d_tasks.ensure(total_tasks * sizeof(RowTask)));
+    CK(c->d_unitcand.ensure(total_tasks * 8 + 8));
+    CK(cudaMemsetAsync(c->d_unitcand.p, 0, total_tasks * 8 + 8, c->stream));
+    c->h_unitcand.assign(total_tasks, 0);
     RoundTimes rt;
     rt.e0 = c->ev(); rt.e1 = c->ev(); rt.e2 = c->ev(); rt.e3 = c->ev();
     CK(zero_counter(c, offsetof(Counters, n_cand)));
@@ -609,7 +620,16 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(rt.e1, c->stream));
-    int rc = run_stage2(c, c->d_cand.as<uint2>(), nullptr, CTR_FIELD(n_cand), 0);
+    // check the candidate count before spending stage 2 on a round that cannot be committed
+    CK(cudaMemcpyAsync(c->h_unitcand.data(), c->d_unitcand.p, total_tasks * 8, cudaMemcpyDeviceToHost, c->stream));
+    int rc = sync_counters(c);
+    if (rc) return rc;
+    if (c->h_ctr->overflow || c->h_ctr->n_cand > c->cand_cap) {
+        c->pairs_eval_seen = c->h_ctr->pairs_eval;
+        c->stats.overflow_retries++;
+        return 1;
+    }
+    rc = run_stage2(c, c->d_cand.as<uint2>(), nullptr, CTR_FIELD(n_cand), 0);
     if (rc) return rc;
     CK(cudaEventRecord(rt.e2, c->stream));
     // first Borůvka iteration is launched speculatively; its result is only used when nothing overflowed
@@ -619,7 +639,6 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
     k_bor_min<<<grid, 256, 0, c->stream>>>(c->d_pass.as<unsigned long long>(), CTR_FIELD(n_pass), c->cand_cap, c->d_parent.as<int32_t>(),
                                           c->d_best.as<unsigned long long>(), 0, c->d_roots.as<int2>(), c->d_ctr.as<Counters>());
     c->stats.kernel_launches += 2;
-    CK(cudaMemcpyAsync(c->h_unitcand.data(), c->d_unitcand.p, units.size() * 8, cudaMemcpyDeviceToHost, c->stream));
     rc = sync_counters(c);
     if (rc) return rc;
     const Counters& h = *c->h_ctr;
@@ -904,19 +923,23 @@ extern "C" int ejb_run(ejb_ctx* c) {
         const std::vector<SubBucket>& subs = c->subs;
         // Units: rows [r0, r1) of a sub-bucket against every column to their right, in row order.  A unit may only be
         // split by ROWS (splitting by columns and contracting after each part is not exact: a lighter edge from a later
-        // column part could have to evict a heavier edge already in the forest).  Unit sizes adapt to the measured
-        // candidates per row of the sub-bucket's previous unit: thin while a dense clone is being connected (its pairs are
-        // not yet skipped by the class test), growing 4x per round once the rows ahead are mostly connected.
+        // column part could have to evict a heavier edge already in the forest).
+        // Sizing: optimistic x4 growth, bounded by the candidate density (per row) of the last row range processed.  When
+        // a round does overflow the candidate buffer (detected right after stage 1, nothing committed), the per-row-range
+        // candidate counts of that attempt are exact upper bounds for the retry, which is planned from them.
+        struct Known { int r0, r1; double cand; };
         std::vector<int> next_row(subs.size(), 0), live;
-        std::vector<double> rho(subs.size(), -1.0);   // candidates per row of the last unit, < 0 = unknown
+        std::vector<double> rho(subs.size(), -1.0);          // candidates per row of the last processed row range
+        std::vector<std::vector<Known>> known(subs.size());  // counted, not yet committed row ranges (ascending)
         for (int s = 0; s < (int)subs.size(); s++)
             if (subs[s].n >= 2 && subs[s].owner == c->shard_rank) live.push_back(s);
-        const double target_unit = std::max(4096.0, (double)c->cand_cap / 64.0);   // candidates one unit should produce
+        const double cap_round = 0.5 * (double)c->cand_cap;                      // expected candidates allowed per round
+        const double target_unit = std::max(4096.0, (double)c->cand_cap / 64.0);   // for ranges that were never counted
         int stalls = 0;
         while (!live.empty()) {
             std::vector<Unit> units;
             unsigned long long pairs = 0;
-            double expect = 0.0;   // expected candidates of this round
+            double expect = 0.0;
             const unsigned long long budget = std::max<unsigned long long>(c->pair_budget, 1ull << 14);
             std::vector<int> still;
             for (int s : live) {
@@ -926,13 +949,43 @@ extern "C" int ejb_run(ejb_ctx* c) {
                     return (unsigned long long)(rows * (sb.n - r1) + rows * (rows - 1) / 2);
                 };
                 const int r0 = next_row[s];
-                long long want = (r0 == 0) ? 8 : std::max<long long>(8, 4ll * r0);            // growth: x4 of the rows done so far
-                if (rho[s] > 0.0) want = std::min<long long>(want, std::max<long long>(1, (long long)(target_unit / rho[s])));
-                int r1 = (int)std::min<long long>((long long)r0 + want, sb.n);
+                int r1;
+                double ex = 0.0;
+                std::vector<Known>& kn = known[s];
+                while (!kn.empty() && kn.front().r1 <= r0) kn.erase(kn.begin());
+                if (!kn.empty() && kn.front().r0 <= r0) {
+                    // counted rows: take as many consecutive ranges as fit, at least a piece of the first
+                    const double room = std::max(cap_round - expect, 0.0);
+                    r1 = r0;
+                    size_t i = 0;
+                    while (i < kn.size() && kn[i].r0 <= r1) {
+                        const double per_row = kn[i].cand / (double)std::max(1, kn[i].r1 - kn[i].r0);
+                        const double c_i = per_row * (double)(kn[i].r1 - r1);
+                        if (ex + c_i <= room) {
+                            ex += c_i;
+                            r1 = kn[i].r1;
+                            i++;
+                        } else {
+                            const int rows = (int)((room - ex) / std::max(per_row, 1e-9));
+                            if (rows > 0) { r1 += rows; ex += per_row * rows; }
+                            break;
+                        }
+                    }
+                    if (r1 == r0) {
+                        if (!units.empty()) { still.push_back(s); continue; }   // no room left in this round
+                        r1 = r0 + 1;                                             // a single row must always be tried
+                        ex = kn.front().cand / (double)std::max(1, kn.front().r1 - kn.front().r0);
+                    }
+                } else {
+                    long long want = (r0 == 0) ? 8 : std::max<long long>(8, 4ll * r0);
+                    if (rho[s] > 0.0) want = std::min<long long>(want, std::max<long long>(1, (long long)(target_unit / rho[s])));
+                    r1 = (int)std::min<long long>((long long)r0 + want, sb.n);
+                    ex = (rho[s] > 0.0 ? rho[s] : std::min<double>(64.0, (double)sb.n)) * (double)(r1 - r0);
+                }
+                r1 = std::min(r1, sb.n);
                 while (r1 - r0 > 1 && unit_pairs(r0, r1) > budget / 2) r1 = r0 + (r1 - r0) / 2;
                 const unsigned long long up = unit_pairs(r0, r1);
-                const double ex = (rho[s] > 0.0 ? rho[s] : std::min<double>(64.0, (double)sb.n)) * (double)(r1 - r0);
-                if (!units.empty() && (pairs + up > budget || expect + ex > 0.5 * (double)c->cand_cap)) {
+                if (!units.empty() && (pairs + up > budget || expect + ex > cap_round)) {
                     still.push_back(s);
                     continue;
                 }
@@ -948,24 +1001,30 @@ extern "C" int ejb_run(ejb_ctx* c) {
             }
             int rc = run_round(c, units, times);
             if (rc != 0 && rc != 1) return rc;
-            // measured density of every unit (also valid for a round that overflowed and was not committed)
-            for (size_t ui = 0; ui < units.size(); ui++)
-                rho[units[ui].sub] = std::max(1e-3, (double)c->h_unitcand[ui] / (double)(units[ui].r1 - units[ui].r0));
             if (rc == 1) {
-                // nothing was committed: put the units back and re-plan them with the measured densities
+                // nothing was committed: put the units back; their per-range counts (valid upper bounds) drive the retry
                 if (units.size() == 1 && units[0].r1 - units[0].r0 <= 1)
                     return fail(c, EJB_ERR_OOM, "work buffers (%llu entries) too small for one row of a %d-row sub-bucket; raise EJB_CAND_CAP",
                                 c->cand_cap, subs[units[0].sub].n);
-                if (++stalls > 64) return fail(c, EJB_ERR_OOM, "scheduler cannot fit a round into the work buffers; raise EJB_CAND_CAP");
+                if (++stalls > 256) return fail(c, EJB_ERR_OOM, "scheduler cannot fit a round into the work buffers; raise EJB_CAND_CAP");
                 for (const Unit& u : units) {
-                    if (next_row[u.sub] >= subs[u.sub].n - 1 && std::find(still.begin(), still.end(), u.sub) == still.end()) still.push_back(u.sub);
+                    if (std::find(still.begin(), still.end(), u.sub) == still.end()) still.push_back(u.sub);
                     next_row[u.sub] = u.r0;
-                    // make sure the retry is strictly smaller even when the density estimate says otherwise
-                    rho[u.sub] = std::max(rho[u.sub], 2.0 * target_unit / (double)std::max(1, u.r1 - u.r0));
+                    known[u.sub].clear();
                 }
+                for (size_t t = 0; t < c->task_meta.size(); t++) {
+                    const auto& m = c->task_meta[t];
+                    known[units[m.unit].sub].push_back({m.r0, m.r1, 1.25 * (double)c->h_unitcand[t] + 1.0});
+                }
+                for (const Unit& u : units) std::sort(known[u.sub].begin(), known[u.sub].end(), [](const Known& a, const Known& b) { return a.r0 < b.r0; });
                 std::sort(still.begin(), still.end());
             } else {
                 stalls = 0;
+                // density of the LAST row range of every unit predicts the rows that follow
+                for (size_t t = 0; t < c->task_meta.size(); t++) {
+                    const auto& m = c->task_meta[t];
+                    if (m.r1 == units[m.unit].r1) rho[units[m.unit].sub] = std::max(1e-3, (double)c->h_unitcand[t] / (double)std::max(1, m.r1 - m.r0));
+                }
             }
             live.swap(still);
         }

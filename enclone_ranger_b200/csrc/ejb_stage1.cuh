@@ -18,7 +18,7 @@ struct RowTask {       // (part of) one row block of one sub-bucket, against eve
     int32_t rb;
     int64_t cta0;      // first CTA of this task inside the launch
     int32_t row_lo, row_hi;   // local rows [row_lo, row_hi) of the block belong to this round's unit
-    int32_t unit, pad;        // index of the unit in this round (per-unit candidate counters)
+    int32_t tid, pad;         // task id inside the round (per-task candidate counters)
 };
 
 template <int W1>
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
                 }
                 if (nh) {
                     s_base = atomicAdd(&ctr->n_cand, (unsigned long long)nh);
-                    atomicAdd(&unit_cand[t.unit], (unsigned long long)nh);
+                    atomicAdd(&unit_cand[t.tid], (unsigned long long)nh);
                 }
             }
             if (nh) {
