@@ -298,8 +298,12 @@ def main():
         ln = torch.tensor([launches, pairs], dtype=torch.int64, device=dev)
         dist.all_reduce(ln)
         launches, pairs = int(ln[0].item()), int(ln[1].item())
+        pr = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(pr, torch.tensor([wall_ms, sum(dev_ms) / len(dev_ms), float(stats["pairs_scored"])], dtype=torch.float64, device=dev))
+        per_rank = [{"wall_ms": float(x[0]), "device_ms": float(x[1]), "pairs": int(x[2])} for x in pr]
     else:
         t_step = t_local
+        per_rank = None
 
     # ---------------- end-to-end arm: host buffers through ejb_join ----------------
     def step_e2e():
@@ -353,7 +357,7 @@ def main():
                        "parallelism": f"bucket-sharded x{world}, weak scaling (1M cells per GPU)" if world > 1 else "single GPU",
                        "l2": f"inputs ({stats['h2d_bytes'] / 1e6:.0f} MB raw + packed row store) exceed the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the library's launching stream (ejb_stats.ms_device_total)" if world == 1 else "wall clock between device syncs, max over ranks",
-                       "wall_ms_per_step": wall_ms, "generate_s": t_gen,
+                       "wall_ms_per_step": wall_ms, "generate_s": t_gen, "per_rank": per_rank,
                        "contig_encoding": "ASCII" if args.ascii else f"2-bit packed where eligible ({raw_tig_bytes / 1e6:.0f} MB ASCII -> {inp.a['tig2_words'].nbytes / 1e6:.0f} MB packed + {inp.a['tig_bytes'].nbytes / 1e6:.0f} MB ASCII)"},
             "clocks": clocks,
             "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]),

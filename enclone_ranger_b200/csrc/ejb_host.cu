@@ -955,7 +955,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
                 while (!kn.empty() && kn.front().r1 <= r0) kn.erase(kn.begin());
                 if (!kn.empty() && kn.front().r0 <= r0) {
                     // counted rows: take as many consecutive ranges as fit, at least a piece of the first
-                    const double room = std::max(cap_round - expect, 0.0);
+                    // a thin slice only: once it is committed the clone ahead is largely connected and the counts are stale
+                    const double room = std::min(std::max(cap_round - expect, 0.0), target_unit);
                     r1 = r0;
                     size_t i = 0;
                     while (i < kn.size() && kn[i].r0 <= r1) {
@@ -1020,6 +1021,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
                 std::sort(still.begin(), still.end());
             } else {
                 stalls = 0;
+                for (const Unit& u : units) known[u.sub].clear();   // stale after a commit
                 // density of the LAST row range of every unit predicts the rows that follow
                 for (size_t t = 0; t < c->task_meta.size(); t++) {
                     const auto& m = c->task_meta[t];
