@@ -298,9 +298,11 @@ def main():
         ln = torch.tensor([launches, pairs], dtype=torch.int64, device=dev)
         dist.all_reduce(ln)
         launches, pairs = int(ln[0].item()), int(ln[1].item())
-        pr = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
-        dist.all_gather(pr, torch.tensor([wall_ms, sum(dev_ms) / len(dev_ms), float(stats["pairs_scored"])], dtype=torch.float64, device=dev))
-        per_rank = [{"wall_ms": float(x[0]), "device_ms": float(x[1]), "pairs": int(x[2])} for x in pr]
+        keys = ("pairs_scored", "pairs_evaluated", "stage1_candidates", "stage2_survivors", "pass_edges", "rounds", "overflow_retries",
+                "ms_pack", "ms_stage1", "ms_stage2", "ms_stage2a", "ms_forest", "ms_finalize")
+        pr = [torch.zeros(2 + len(keys), dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(pr, torch.tensor([wall_ms, sum(dev_ms) / len(dev_ms)] + [float(stats[k]) for k in keys], dtype=torch.float64, device=dev))
+        per_rank = [dict({"wall_ms": round(float(x[0]), 2), "device_ms": round(float(x[1]), 2)}, **{k: round(float(v), 2) for k, v in zip(keys, x[2:].tolist())}) for x in pr]
     else:
         t_step = t_local
         per_rank = None
