@@ -62,6 +62,8 @@ struct DevBuf {
 
 struct Unit {  // rows [r0, r1) of one sub-bucket, processed against all columns to their right
     int32_t sub, r0, r1;
+    double allow;      // candidates after which the unit is truncated (at a row-range boundary) once stage 1 has counted them
+    double cand, pass; // measured: candidates of the committed rows, pass edges
 };
 
 }  // namespace
@@ -99,7 +101,8 @@ struct ejb_ctx {
     DevBuf d_head, d_scan, d_keys, d_keys2, d_vals, d_vals2, d_cubtmp, d_subhead, d_subincl, d_subinfo;
     DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_aux;
     DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
-    DevBuf d_unitcand;
+    DevBuf d_unitcand, d_qcut, d_subpass;
+    std::vector<unsigned int> h_subpass;
     std::vector<unsigned long long> h_unitcand;   // candidates of each task (row range) of the last round, valid even when it overflowed
     struct TaskMeta { int32_t unit, r0, r1; };
     std::vector<TaskMeta> task_meta;
@@ -282,6 +285,8 @@ S2Ctx make_s2ctx(ejb_ctx* c, int tuple_mode) {
     X.aux = c->d_aux.as<int32_t>();
     X.rowq = c->d_m_row.as<int32_t>();
     X.subq = c->d_m_sub.as<int32_t>();
+    X.qcut = c->d_qcut.as<int32_t>();
+    X.sub_pass = c->d_subpass.as<unsigned int>();
     X.cdr3w = c->d_cdr3w.as<uint32_t>();
     X.rowstore = c->d_rowstore.as<uint4>();
     X.bc_sorted = c->d_bckeys2.as<uint64_t>();
@@ -552,7 +557,7 @@ int cub_incl_sum(ejb_ctx* c, const int32_t* in, int32_t* out, int64_t n) {
 
 // One scheduler round: stage 1 over `units`, stage 2, forest update.  Returns 1 when the
 // candidate buffer overflowed (nothing committed; the caller splits the round and retries).
-int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes>& times) {
+int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& times) {
     const unsigned long long eval_before = c->pairs_eval_seen;
     const std::vector<SubBucket>& subs = c->subs;
     // ---- tasks grouped by W1; task ids number them in launch order ----
@@ -629,8 +634,34 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
         c->stats.overflow_retries++;
         return 1;
     }
+    // truncate units whose counted candidates exceed their allowance: keep whole row ranges up to (and including) the one
+    // that crosses it; stage 2 ignores candidates of the rows cut away and the scheduler resumes from the cut
+    std::vector<std::pair<int32_t, int32_t>> cuts;   // (sub, packed position limit)
+    {
+        for (Unit& u : units) u.cand = 0.0;
+        std::vector<char> closed(units.size(), 0);
+        for (size_t t = 0; t < c->task_meta.size(); t++) {   // tasks of one unit are consecutive and in row order
+            const auto& m = c->task_meta[t];
+            Unit& u = units[m.unit];
+            if (closed[m.unit]) continue;
+            u.cand += (double)c->h_unitcand[t];
+            if (u.cand > u.allow && m.r1 < u.r1) {
+                u.r1 = m.r1;
+                closed[m.unit] = 1;
+                cuts.emplace_back(u.sub, (int32_t)(subs[u.sub].q0 + m.r1));
+            }
+        }
+        for (auto& ct : cuts) CK(cudaMemcpyAsync(c->d_qcut.as<int32_t>() + ct.first, &ct.second, 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->d_subpass.p, 0, subs.size() * 4, c->stream));
+    }
     rc = run_stage2(c, c->d_cand.as<uint2>(), nullptr, CTR_FIELD(n_cand), 0);
     if (rc) return rc;
+    {
+        static const int32_t kNoCut = 0x7fffffff;
+        for (auto& ct : cuts) CK(cudaMemcpyAsync(c->d_qcut.as<int32_t>() + ct.first, &kNoCut, 4, cudaMemcpyHostToDevice, c->stream));
+        c->h_subpass.resize(subs.size());
+        CK(cudaMemcpyAsync(c->h_subpass.data(), c->d_subpass.p, subs.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
     CK(cudaEventRecord(rt.e2, c->stream));
     // first Borůvka iteration is launched speculatively; its result is only used when nothing overflowed
     const int grid = c->sm_count * 8;
@@ -659,6 +690,7 @@ int run_round(ejb_ctx* c, const std::vector<Unit>& units, std::vector<RoundTimes
     c->stats.stage2_slow += (int64_t)h.n_slow;
     c->stats.stage2_survivors += (int64_t)h.n_surv_total;
     c->stats.pass_edges += (int64_t)h.n_pass;
+    for (Unit& u : units) u.pass = (double)c->h_subpass[(size_t)u.sub];
     if (h.n_pass > 0) {
         int iter = 0;
         unsigned long long alive = h.n_alive;
@@ -861,6 +893,9 @@ extern "C" int ejb_run(ejb_ctx* c) {
         CK(cudaMemcpyAsync(c->d_powoff.p, pow_off.data(), pow_off.size() * 4, cudaMemcpyHostToDevice, st));
 
         // ---- device arrays ----
+        CK(c->d_qcut.ensure((size_t)n_subs * 4 + 4));
+        CK(c->d_subpass.ensure((size_t)n_subs * 4 + 4));
+        CK(cudaMemsetAsync(c->d_qcut.p, 0x7f, (size_t)n_subs * 4, st));   // 0x7f7f7f7f: no cut
         CK(c->d_subs.ensure((size_t)n_subs * sizeof(SubBucket)));
         CK(cudaMemcpyAsync(c->d_subs.p, subs.data(), (size_t)n_subs * sizeof(SubBucket), cudaMemcpyHostToDevice, st));
         std::vector<int32_t> blk_sub((size_t)blk);
@@ -929,12 +964,13 @@ extern "C" int ejb_run(ejb_ctx* c) {
         // candidate counts of that attempt are exact upper bounds for the retry, which is planned from them.
         struct Known { int r0, r1; double cand; };
         std::vector<int> next_row(subs.size(), 0), live;
-        std::vector<double> rho(subs.size(), -1.0);          // candidates per row of the last processed row range
+        std::vector<double> rho(subs.size(), -1.0);          // candidates per row of the last committed row range
+        std::vector<double> prate(subs.size(), 1.0);         // pass edges per candidate of the last committed unit
         std::vector<std::vector<Known>> known(subs.size());  // counted, not yet committed row ranges (ascending)
         for (int s = 0; s < (int)subs.size(); s++)
             if (subs[s].n >= 2 && subs[s].owner == c->shard_rank) live.push_back(s);
         const double cap_round = 0.5 * (double)c->cand_cap;                      // expected candidates allowed per round
-        const double target_unit = std::max(4096.0, (double)c->cand_cap / 64.0);   // for ranges that were never counted
+        const double target_pass = std::max(4096.0, (double)c->cand_cap / 64.0);   // pass edges one unit should not exceed by much
         int stalls = 0;
         while (!live.empty()) {
             std::vector<Unit> units;
@@ -951,12 +987,14 @@ extern "C" int ejb_run(ejb_ctx* c) {
                 const int r0 = next_row[s];
                 int r1;
                 double ex = 0.0;
+                // where the pairs found mostly JOIN, a unit is truncated early (the rows behind it get connected and are then
+                // skipped by the class test); where they mostly fail, every pair has to be scored once anyway
+                const double allow = target_pass / std::max(prate[s], 0.02);
                 std::vector<Known>& kn = known[s];
                 while (!kn.empty() && kn.front().r1 <= r0) kn.erase(kn.begin());
                 if (!kn.empty() && kn.front().r0 <= r0) {
-                    // counted rows: take as many consecutive ranges as fit, at least a piece of the first
-                    // a thin slice only: once it is committed the clone ahead is largely connected and the counts are stale
-                    const double room = std::min(std::max(cap_round - expect, 0.0), target_unit);
+                    // counted rows (after an overflow): take as many consecutive ranges as fit, at least a piece of the first
+                    const double room = std::min(std::max(cap_round - expect, 0.0), allow);
                     r1 = r0;
                     size_t i = 0;
                     while (i < kn.size() && kn[i].r0 <= r1) {
@@ -978,10 +1016,14 @@ extern "C" int ejb_run(ejb_ctx* c) {
                         ex = kn.front().cand / (double)std::max(1, kn.front().r1 - kn.front().r0);
                     }
                 } else {
-                    long long want = (r0 == 0) ? 8 : std::max<long long>(8, 4ll * r0);
-                    if (rho[s] > 0.0) want = std::min<long long>(want, std::max<long long>(1, (long long)(target_unit / rho[s])));
+                    const long long want = (r0 == 0) ? 8 : std::max<long long>(8, 4ll * r0);   // optimistic x4 growth
                     r1 = (int)std::min<long long>((long long)r0 + want, sb.n);
                     ex = (rho[s] > 0.0 ? rho[s] : std::min<double>(64.0, (double)sb.n)) * (double)(r1 - r0);
+                    // capacity: never plan more expected candidates than a round may hold
+                    if (ex > 0.5 * cap_round) {
+                        r1 = r0 + std::max(1, (int)((double)(r1 - r0) * 0.5 * cap_round / ex));
+                        ex = 0.5 * cap_round;
+                    }
                 }
                 r1 = std::min(r1, sb.n);
                 while (r1 - r0 > 1 && unit_pairs(r0, r1) > budget / 2) r1 = r0 + (r1 - r0) / 2;
@@ -994,40 +1036,47 @@ extern "C" int ejb_run(ejb_ctx* c) {
                 u.sub = s;
                 u.r0 = r0;
                 u.r1 = r1;
+                u.allow = allow;
+                u.cand = u.pass = 0.0;
                 units.push_back(u);
                 pairs += up;
                 expect += ex;
-                next_row[s] = r1;
-                if (r1 < sb.n - 1) still.push_back(s);   // the last row has no pair to its right
             }
+            const std::vector<Unit> planned = units;
             int rc = run_round(c, units, times);
             if (rc != 0 && rc != 1) return rc;
             if (rc == 1) {
-                // nothing was committed: put the units back; their per-range counts (valid upper bounds) drive the retry
+                // nothing was committed: the per-range counts (valid upper bounds) drive the retry
                 if (units.size() == 1 && units[0].r1 - units[0].r0 <= 1)
                     return fail(c, EJB_ERR_OOM, "work buffers (%llu entries) too small for one row of a %d-row sub-bucket; raise EJB_CAND_CAP",
                                 c->cand_cap, subs[units[0].sub].n);
                 if (++stalls > 256) return fail(c, EJB_ERR_OOM, "scheduler cannot fit a round into the work buffers; raise EJB_CAND_CAP");
-                for (const Unit& u : units) {
-                    if (std::find(still.begin(), still.end(), u.sub) == still.end()) still.push_back(u.sub);
-                    next_row[u.sub] = u.r0;
+                for (const Unit& u : planned) {
+                    still.push_back(u.sub);
                     known[u.sub].clear();
                 }
                 for (size_t t = 0; t < c->task_meta.size(); t++) {
                     const auto& m = c->task_meta[t];
-                    known[units[m.unit].sub].push_back({m.r0, m.r1, 1.25 * (double)c->h_unitcand[t] + 1.0});
+                    known[planned[m.unit].sub].push_back({m.r0, m.r1, 1.25 * (double)c->h_unitcand[t] + 1.0});
                 }
-                for (const Unit& u : units) std::sort(known[u.sub].begin(), known[u.sub].end(), [](const Known& a, const Known& b) { return a.r0 < b.r0; });
-                std::sort(still.begin(), still.end());
+                for (const Unit& u : planned) std::sort(known[u.sub].begin(), known[u.sub].end(), [](const Known& a, const Known& b) { return a.r0 < b.r0; });
             } else {
                 stalls = 0;
-                for (const Unit& u : units) known[u.sub].clear();   // stale after a commit
-                // density of the LAST row range of every unit predicts the rows that follow
+                for (size_t ui = 0; ui < units.size(); ui++) {
+                    const Unit& u = units[ui];       // u.r1 may have been truncated by run_round
+                    next_row[u.sub] = u.r1;
+                    known[u.sub].clear();            // stale after a commit
+                    if (u.cand > 0.0) prate[u.sub] = std::min(1.0, u.pass / u.cand);
+                    if (u.r1 < subs[u.sub].n - 1) still.push_back(u.sub);   // the last row has no pair to its right
+                }
+                // candidate density of the last committed row range predicts the rows that follow (capacity planning)
                 for (size_t t = 0; t < c->task_meta.size(); t++) {
                     const auto& m = c->task_meta[t];
                     if (m.r1 == units[m.unit].r1) rho[units[m.unit].sub] = std::max(1e-3, (double)c->h_unitcand[t] / (double)std::max(1, m.r1 - m.r0));
                 }
             }
+            std::sort(still.begin(), still.end());
+            still.erase(std::unique(still.begin(), still.end()), still.end());
             live.swap(still);
         }
     }

@@ -20,6 +20,8 @@ struct S2Ctx {
     const int32_t* aux;          // AUX_INTS per packed row
     const int32_t* rowq;         // canonical row of a packed position
     const int32_t* subq;         // sub-bucket of a packed position
+    const int32_t* qcut;         // per sub-bucket: candidates whose first row is at a packed position >= qcut are not part of this round
+    unsigned int* sub_pass;      // per sub-bucket: pass edges found in this round
     const uint32_t* cdr3w;
     const uint4* rowstore;
     const uint64_t* bc_sorted;   // (exact << 32 | barcode), sorted: each exact's barcodes ascending
@@ -335,11 +337,12 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
       for (unsigned long long base = c0 + (unsigned long long)wib * 32; base < c1; base += (unsigned long long)nwb * 32) {
         // ---- my own candidate (phase 2 owner) ----
         const unsigned long long ci = base + lane;
-        const bool valid = ci < c1;
+        bool valid = ci < c1;
         uint2 pr = make_uint2(0, 0);
         if (valid) pr = cand[ci];
         const uint32_t q1 = pr.x, q2 = pr.y;
         const int sid = X.subq[q1];
+        if (valid && !X.tuple_mode && (int)q1 >= X.qcut[sid]) valid = false;   // row truncated from this round's unit after stage 1
         const SubBucket sb = X.subs[sid];
         const int32_t* a1 = X.aux + (size_t)q1 * AUX_INTS;
         const int32_t* a2 = X.aux + (size_t)q2 * AUX_INTS;
@@ -711,6 +714,7 @@ __global__ void __launch_bounds__(256) k_stage2b(S2Ctx X, const unsigned long lo
         } else if (ok) {
             pass_edge = true;
             pass_val = ((unsigned long long)(uint32_t)X.rowq[q1] << 28) | (unsigned long long)(uint32_t)X.rowq[q2];
+            atomicAdd(&X.sub_pass[X.subq[q1]], 1u);
         }
       }
       // warp-aggregated append: one atomic per warp
