@@ -63,6 +63,8 @@ struct DevBuf {
 struct Unit {  // rows [r0, r1) of one sub-bucket, processed against all columns to their right
     int32_t sub, r0, r1;
     double allow;      // candidates after which the unit is truncated (at a row-range boundary) once stage 1 has counted them
+    double strict;     // ... allowance that applies from the first row range whose density jumps above 8x rho_ref
+    double rho_ref;    // candidates per row of the sub-bucket's last committed row range (< 0: unknown)
     double cand, pass; // measured: candidates of the committed rows, pass edges
 };
 
@@ -639,13 +641,18 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     std::vector<std::pair<int32_t, int32_t>> cuts;   // (sub, packed position limit)
     {
         for (Unit& u : units) u.cand = 0.0;
-        std::vector<char> closed(units.size(), 0);
+        std::vector<char> closed(units.size(), 0), jumped(units.size(), 0);
+        std::vector<double> after_jump(units.size(), 0.0);
         for (size_t t = 0; t < c->task_meta.size(); t++) {   // tasks of one unit are consecutive and in row order
             const auto& m = c->task_meta[t];
             Unit& u = units[m.unit];
             if (closed[m.unit]) continue;
-            u.cand += (double)c->h_unitcand[t];
-            if (u.cand > u.allow && m.r1 < u.r1) {
+            const double cnt = (double)c->h_unitcand[t];
+            // a jump in density = a region (typically a clone not connected yet) the pass-rate estimate knows nothing about
+            if (!jumped[m.unit] && (u.rho_ref < 0.0 || cnt / (double)std::max(1, m.r1 - m.r0) > 8.0 * u.rho_ref + 16.0)) jumped[m.unit] = 1;
+            u.cand += cnt;
+            if (jumped[m.unit]) after_jump[m.unit] += cnt;
+            if ((u.cand > u.allow || (jumped[m.unit] && after_jump[m.unit] > u.strict)) && m.r1 < u.r1) {
                 u.r1 = m.r1;
                 closed[m.unit] = 1;
                 cuts.emplace_back(u.sub, (int32_t)(subs[u.sub].q0 + m.r1));
@@ -1037,6 +1044,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
                 u.r0 = r0;
                 u.r1 = r1;
                 u.allow = allow;
+                u.strict = target_pass;
+                u.rho_ref = rho[s];
                 u.cand = u.pass = 0.0;
                 units.push_back(u);
                 pairs += up;

@@ -577,6 +577,7 @@ __global__ void __launch_bounds__(256) k_stage2b(S2Ctx X, const unsigned long lo
       const unsigned long long si = sbase + lane;
       bool pass_edge = false;
       unsigned long long pass_val = 0;
+      int pass_sub = -1;
       Survivor s;
       s.q1 = SURV_INVALID;
       if (si < n_surv) s = X.surv[si];
@@ -714,7 +715,7 @@ __global__ void __launch_bounds__(256) k_stage2b(S2Ctx X, const unsigned long lo
         } else if (ok) {
             pass_edge = true;
             pass_val = ((unsigned long long)(uint32_t)X.rowq[q1] << 28) | (unsigned long long)(uint32_t)X.rowq[q2];
-            atomicAdd(&X.sub_pass[X.subq[q1]], 1u);
+            pass_sub = X.subq[q1];
         }
       }
       // warp-aggregated append: one atomic per warp
@@ -726,6 +727,9 @@ __global__ void __launch_bounds__(256) k_stage2b(S2Ctx X, const unsigned long lo
           if (pass_edge) {
               const unsigned long long o = b + __popc(m & ((1u << lane) - 1u));
               if (o < pass_cap) pass_w[o] = pass_val; else X.ctr->overflow = 1ull;
+              // per-sub-bucket pass counter, aggregated over the lanes of the warp that hit the same sub-bucket
+              const unsigned int same = __match_any_sync(m, pass_sub);
+              if ((same & ((1u << lane) - 1u)) == 0) atomicAdd(&X.sub_pass[pass_sub], (unsigned int)__popc(same));
           }
       }
     }
