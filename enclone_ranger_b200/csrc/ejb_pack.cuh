@@ -128,6 +128,45 @@ __global__ void k_exact_prep(DevIn in, unsigned long long* donor_mask, uint64_t*
     donor_mask[e] = m;
 }
 
+// Per-segment reference planes (internal base code, 2 planes x SEGPL_WORDS words, position 0 = first base of the
+// segment, zero beyond its end): the fast bucketer path slices / shifts them instead of touching segment bytes.
+constexpr int SEGPL_WORDS = 16;   // segments up to 512 nt
+__global__ void k_seg_planes(DevIn in, uint32_t* __restrict__ segpl) {
+    const int lane = threadIdx.x & 31;
+    const int64_t sg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (sg >= in.n_segs) return;
+    const uint8_t* b = in.seg_bytes + in.seg_off[sg];
+    const long long len = in.seg_off[sg + 1] - in.seg_off[sg];
+    for (int w = 0; w < SEGPL_WORDS; w++) {
+        const long long p = (long long)w * 32 + lane;
+        const uint32_t code = p < len ? base_code(b[p]) : 0u;
+        const uint32_t lo = __ballot_sync(0xffffffffu, code & 1), hi = __ballot_sync(0xffffffffu, code & 2);
+        if (lane == 0) {
+            segpl[(sg * 2 + 0) * SEGPL_WORDS + w] = lo;
+            segpl[(sg * 2 + 1) * SEGPL_WORDS + w] = hi;
+        }
+    }
+}
+// even bits of x compressed into the low 16 bits
+__device__ __forceinline__ uint32_t even_bits(uint32_t x) {
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
+    x = (x | (x >> 8)) & 0x0000ffffu;
+    return x;
+}
+// bits [0, n) set (n may be <= 0 or >= 32)
+__device__ __forceinline__ uint32_t mask_lt(long long n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << (int)n) - 1u)); }
+// 32 bits of a SEGPL_WORDS-word plane starting at bit index `idx` (bits outside the plane read as 0)
+__device__ __forceinline__ uint32_t plane_bits(const uint32_t* __restrict__ pl, long long idx) {
+    const long long wi = idx >> 5;   // floor
+    const int sh = (int)(idx & 31);
+    const uint32_t a = (wi >= 0 && wi < SEGPL_WORDS) ? pl[wi] : 0u;
+    const uint32_t b = (wi + 1 >= 0 && wi + 1 < SEGPL_WORDS) ? pl[wi + 1] : 0u;
+    return sh ? ((a >> sh) | (b << (32 - sh))) : a;
+}
+
 // ------------------------------------------------------------------------------------------------
 // The bucketer: one warp per packed row.  Writes
 //   * CDR3 planes (heavy ++ light concatenated), layout [plane*W1 + w][npad] per sub-bucket
@@ -137,8 +176,8 @@ __global__ void k_exact_prep(DevIn in, unsigned long long* donor_mask, uint64_t*
 // ------------------------------------------------------------------------------------------------
 __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__ subs, const int32_t* __restrict__ sub_incl,
                             const uint32_t* __restrict__ row_of, int64_t n_active, const unsigned long long* __restrict__ donor_mask,
-                            uint32_t* __restrict__ cdr3w, uint4* __restrict__ rowstore, int32_t* __restrict__ aux, int32_t* __restrict__ rowq,
-                            int32_t* __restrict__ subq) {
+                            const uint32_t* __restrict__ segpl, uint32_t* __restrict__ cdr3w, uint4* __restrict__ rowstore,
+                            int32_t* __restrict__ aux, int32_t* __restrict__ rowq, int32_t* __restrict__ subq) {
     const int lane = threadIdx.x & 31;
     const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= n_active) return;
@@ -202,6 +241,69 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
             if (has_c2) { rC20 = cdr2; rC21 = fr3; }
         }
     }
+    // ---- fast path: both contigs 2-bit packed, <= 512 nt, segments <= 512 nt.  Lanes 0-15 build the 16 words of every
+    //      plane of chain 0, lanes 16-31 those of chain 1, by de-interleaving the packed words: no per-base work. ----
+    bool fastrow = sb.W4h == 4 && sb.W4l == 4 && in.row_tig2_off != nullptr;
+    if (fastrow) {
+        for (int m = 0; m < 2; m++) {
+            if (in.row_tig2_off[2 * k + m] < 0) fastrow = false;
+            const int sv = in.row_vs[2 * k + m], sj = in.row_js[2 * k + m];
+            if (in.seg_off[sv + 1] - in.seg_off[sv] > 32 * SEGPL_WORDS || in.seg_off[sj + 1] - in.seg_off[sj] > 32 * SEGPL_WORDS) fastrow = false;
+        }
+    }
+    if (fastrow) {
+        const int m = lane >> 4, w = lane & 15;
+        const int L = m ? sb.Ll : sb.Lh;
+        const int gapbit = (sb.gap >> m) & 1;
+        const int sv = in.row_vs[2 * k + m], sj = in.row_js[2 * k + m];
+        const long long vlen = in.seg_off[sv + 1] - in.seg_off[sv], jlen = in.seg_off[sj + 1] - in.seg_off[sj];
+        const long long vr = vlen - P.ref_v_trim, jr = jlen - P.ref_j_trim;
+        uint32_t fl = 0;
+        if (vr < 0 || jr < 0 || jr > L) fl |= F_PANIC;
+        if (vr > L || vr + jr > L) fl |= F_SLOWGEOM;
+        // contig planes from the packed words (A,C,G,T = 0..3 -> internal code lo' = lo ^ hi, hi' = hi)
+        const uint32_t* tw = in.tig2_words + in.row_tig2_off[2 * k + m];
+        const int nw16 = (L + 15) >> 4;
+        const uint32_t x0 = (2 * w < nw16) ? tw[2 * w] : 0u, x1 = (2 * w + 1 < nw16) ? tw[2 * w + 1] : 0u;
+        const uint32_t inl = mask_lt((long long)L - 32 * w);
+        uint32_t lo = even_bits(x0) | (even_bits(x1) << 16), hi = even_bits(x0 >> 1) | (even_bits(x1 >> 1) << 16);
+        lo = (lo ^ hi) & inl;
+        hi &= inl;
+        // compare masks and reference planes in contig coordinates
+        const uint32_t cmv = mask_lt(vr - 32 * w) & inl;
+        const uint32_t cmj = inl & ~mask_lt(((long long)L - jr) - 32 * w) & ~cmv;   // p >= L - jr, V range has priority
+        const uint32_t* vp = segpl + (size_t)sv * 2 * SEGPL_WORDS;
+        const uint32_t* jp = segpl + (size_t)sj * 2 * SEGPL_WORDS;
+        const long long jidx = (long long)32 * w + (jlen - L);   // J index of contig position 32w
+        const uint32_t rlo = (vp[w] & cmv) | (plane_bits(jp, jidx) & cmj);
+        const uint32_t rhi = (vp[SEGPL_WORDS + w] & cmv) | (plane_bits(jp + SEGPL_WORDS, jidx) & cmj);
+        const uint32_t cm = cmv | cmj;
+        const uint32_t dm = cm & ((lo ^ rlo) | (hi ^ rhi));
+        uint32_t* r = rec32 + (m ? rec_planes(0, sb.gap & 1) * sb.W4h * 4 : 0) + w;
+        const int st = 16;   // 4 * W4
+        r[PL_TLO * st] = lo;
+        r[PL_THI * st] = hi;
+        r[PL_D * st] = dm;
+        r[PL_RLO * st] = rlo;
+        r[PL_RHI * st] = rhi;
+        r[PL_CMP * st] = cm;
+        if (m == 0) {
+            auto rng = [&](int a, int b) { return mask_lt((long long)b - 32 * w) & ~mask_lt((long long)a - 32 * w); };
+            const uint32_t mF = rng(rF0, rF1), mC1 = rng(rC10, rC11), mC2 = rng(rC20, rC21);
+            r[PL_GLO * st] = (mF | mC2) & ~mC1;       // region ids 1 (FWR1) and 3 (CDR2) have the low bit
+            r[PL_GHI * st] = (mC1 | mC2) & ~mF;       // ids 2 (CDR1) and 3 (CDR2) have the high bit; first match wins like the scalar path
+        }
+        if (gapbit) r[gap_plane(m) * st] = 0u;
+        int t = __popc(dm);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+            fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+        }
+        tot = t;
+        flags |= fl;
+    }
+    if (!fastrow)
     for (int m = 0; m < 2; m++) {
         const int L = (m == 0) ? sb.Lh : sb.Ll;
         const int W4 = (m == 0) ? sb.W4h : sb.W4l;
