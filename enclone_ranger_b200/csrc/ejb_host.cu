@@ -103,7 +103,7 @@ struct ejb_ctx {
     DevBuf d_head, d_scan, d_keys, d_keys2, d_vals, d_vals2, d_cubtmp, d_subhead, d_subincl, d_subinfo;
     DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_aux;
     DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
-    DevBuf d_unitcand, d_qcut, d_subpass, d_segpl;
+    DevBuf d_unitcand, d_qcut, d_subpass, d_segpl, d_memo;
     std::vector<unsigned int> h_subpass;
     std::vector<unsigned long long> h_unitcand;   // candidates of each task (row range) of the last round, valid even when it overflowed
     struct TaskMeta { int32_t unit, r0, r1; };
@@ -289,6 +289,7 @@ S2Ctx make_s2ctx(ejb_ctx* c, int tuple_mode) {
     X.subq = c->d_m_sub.as<int32_t>();
     X.qcut = c->d_qcut.as<int32_t>();
     X.sub_pass = c->d_subpass.as<unsigned int>();
+    X.memo = c->d_memo.as<int32_t>();
     X.cdr3w = c->d_cdr3w.as<uint32_t>();
     X.rowstore = c->d_rowstore.as<uint4>();
     X.bc_sorted = c->d_bckeys2.as<uint64_t>();
@@ -927,6 +928,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
             int rc2 = cub_sort_keys64(c, c->d_bckeys.as<uint64_t>(), c->d_bckeys2.as<uint64_t>(), din.n_cells);
             if (rc2) return rc2;
         }
+        CK(c->d_memo.ensure(np * 32));
+        CK(cudaMemsetAsync(c->d_memo.p, 0, np * 32, st));
         CK(c->d_segpl.ensure((size_t)std::max<int64_t>(din.n_segs, 1) * 2 * SEGPL_WORDS * 4));
         k_seg_planes<<<nblk(din.n_segs * 32, 256), 256, 0, st>>>(din, c->d_segpl.as<uint32_t>());
         k_pack_rows<<<nblk(NA * 32, 256), 256, 0, st>>>(din, P, c->d_subs.as<SubBucket>(), c->d_subincl.as<int32_t>(), row_of, NA,

@@ -22,6 +22,7 @@ struct S2Ctx {
     const int32_t* subq;         // sub-bucket of a packed position
     const int32_t* qcut;         // per sub-bucket: candidates whose first row is at a packed position >= qcut are not part of this round
     unsigned int* sub_pass;      // per sub-bucket: pass edges found in this round
+    int32_t* memo;               // per packed row, 8 ints: {state, vs_h, vs_l, js_h, js_l, T, -, -} — see memo_lookup()
     const uint32_t* cdr3w;
     const uint4* rowstore;
     const uint64_t* bc_sorted;   // (exact << 32 | barcode), sorted: each exact's barcodes ascending
@@ -148,6 +149,27 @@ struct SurvWriter {
 __device__ __forceinline__ void ld4(const uint4* p, uint32_t* o) {
     const uint4 v = __ldg(p);
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+
+// Write-once per-row memo of T(row, refset) = number of compared positions where the row's contigs differ from ANOTHER
+// row's V/J references (on that reference set's compare ranges).  It depends only on the row and the foreign
+// reference set (all rows of a sub-bucket have equal contig lengths), and it is all the degradation test
+// (join_one.rs:434-440) needs, so a row that keeps meeting the same foreign reference set — an indel row against its
+// whole clone — is rejected without touching the planes again.  state: 0 empty, 1 being written, 2 ready (immutable).
+__device__ __forceinline__ bool memo_lookup(const int32_t* memo, uint32_t q, int vsh, int vsl, int jsh, int jsl, int& T) {
+    const int32_t* m = memo + (size_t)q * 8;
+    if (*reinterpret_cast<const volatile int32_t*>(m) != 2) return false;
+    __threadfence();
+    if (m[1] != vsh || m[2] != vsl || m[3] != jsh || m[4] != jsl) return false;
+    T = m[5];
+    return true;
+}
+__device__ __forceinline__ void memo_store(int32_t* memo, uint32_t q, int vsh, int vsl, int jsh, int jsl, int T) {
+    int32_t* m = memo + (size_t)q * 8;
+    if (atomicCAS(m, 0, 1) != 0) return;   // somebody else owns the slot
+    m[1] = vsh; m[2] = vsl; m[3] = jsh; m[4] = jsl; m[5] = T;
+    __threadfence();
+    *reinterpret_cast<volatile int32_t*>(m) = 2;
 }
 
 // Per-candidate values the owner lane derives once and hands to the group working on it (by shuffle).
@@ -352,8 +374,15 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
         const bool fast = valid && ((f1 | f2) & F_SLOWMASK) == 0 && sb.W1 > 0 && sb.W4h > 0 && sb.W4l > 0;
         const bool wide = fast && (sb.W4h > 4 || sb.W4l > 4);
         const int tot1 = a1[AX_TOT], tot2 = a2[AX_TOT];
+        // phase 0: two references — try the memoised totals first
+        bool memo_dead = false;
+        if (fast && !nrefs1 && !X.tuple_mode) {
+            int T;
+            if (memo_lookup(X.memo, q1, (int)a20.y, (int)a20.z, (int)a20.w, a2[AX_JSL], T) && abs(tot1 - T) > X.P.max_degradation) memo_dead = true;        // T10
+            else if (memo_lookup(X.memo, q2, (int)a10.y, (int)a10.z, (int)a10.w, a1[AX_JSL], T) && abs(T - tot2) > X.P.max_degradation) memo_dead = true;   // T01
+        }
         CandInfo me;
-        me.meta = (uint32_t)sb.W1 | ((uint32_t)sb.W4h << 3) | ((uint32_t)sb.W4l << 7) | ((uint32_t)sb.gap << 11) | ((uint32_t)fast << 13) |
+        me.meta = (uint32_t)sb.W1 | ((uint32_t)sb.W4h << 3) | ((uint32_t)sb.W4l << 7) | ((uint32_t)sb.gap << 11) | ((uint32_t)(fast && !memo_dead) << 13) |
                   ((uint32_t)nrefs1 << 14) | ((uint32_t)sb.ch << 16);
         me.rec1 = (uint32_t)(sb.rs_off + (int64_t)(q1 - sb.q0) * sb.rec_u4);
         me.rec2 = (uint32_t)(sb.rs_off + (int64_t)(q2 - sb.q0) * sb.rec_u4);
@@ -394,7 +423,9 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
         Survivor sv;
         if (valid) {
             const uint32_t slot = cand_slot ? cand_slot[ci] : (uint32_t)ci;
-            if (fast) {
+            if (fast && memo_dead) {
+                // rejected by the degradation test on memoised totals
+            } else if (fast) {
                 const uint32_t* r = s_res[wib][lane];
                 const int cd1 = (int)(r[0] & 0xffff), cd2 = (int)(r[0] >> 16);
                 const int diffs = (int)(r[2] & 0xffff);
@@ -416,6 +447,10 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
                     const int A0 = (int)(r[4] & 0xffff), B0 = (int)(r[4] >> 16), O0 = (int)(r[5] & 0xffff), T01 = (int)(r[5] >> 16);
                     const int A1 = (int)(r[6] & 0xffff), B1 = (int)(r[6] >> 16), O1 = (int)(r[7] & 0xffff), T10 = (int)(r[7] >> 16);
                     // join_one.rs:434-440: total[0] = (tot1, T01), total[1] = (T10, tot2)
+                    if (!X.tuple_mode) {
+                        memo_store(X.memo, q1, (int)a20.y, (int)a20.z, (int)a20.w, a2[AX_JSL], T10);
+                        memo_store(X.memo, q2, (int)a10.y, (int)a10.z, (int)a10.w, a1[AX_JSL], T01);
+                    }
                     bool ok = true;
                     if (abs(tot1 - T10) > X.P.max_degradation) ok = false;
                     if (abs(T01 - tot2) > X.P.max_degradation) ok = false;
