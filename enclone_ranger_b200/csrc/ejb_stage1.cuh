@@ -155,10 +155,15 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
                     const int clab = (int)sc[NP * TILE + c];
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
-                        const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
-                        if (cd <= maxcd && rlab[i] != clab) {
-                            const unsigned int h = atomicAdd(&s_nhits, 1u);
-                            s_hits[h] = (uint16_t)(((i * 16 + ty) << 7) | c);
+                        // class test first (join_core.rs:32): a warp whose 32 pairs are all already connected skips the
+                        // distance entirely — the common case inside a clone once its first rows have been processed
+                        const bool need = rlab[i] != clab;
+                        if (__any_sync(0xffffffffu, need)) {
+                            const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
+                            if (need && cd <= maxcd) {
+                                const unsigned int h = atomicAdd(&s_nhits, 1u);
+                                s_hits[h] = (uint16_t)(((i * 16 + ty) << 7) | c);
+                            }
                         }
                     }
                 }
@@ -175,11 +180,13 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int r = i * 16 + ty;
-                        const bool valid = r >= row_lo && r < row_lim && c < col_lim && (!diag || r < c);
-                        const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
-                        if (valid && cd <= maxcd && rlab[i] != clab) {
-                            const unsigned int h = atomicAdd(&s_nhits, 1u);
-                            s_hits[h] = (uint16_t)((r << 7) | c);
+                        const bool need = r >= row_lo && r < row_lim && c < col_lim && (!diag || r < c) && rlab[i] != clab;
+                        if (__any_sync(0xffffffffu, need)) {
+                            const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
+                            if (need && cd <= maxcd) {
+                                const unsigned int h = atomicAdd(&s_nhits, 1u);
+                                s_hits[h] = (uint16_t)((r << 7) | c);
+                            }
                         }
                     }
                 }
