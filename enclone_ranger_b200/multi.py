@@ -74,17 +74,33 @@ def bucket_ids(inp):
     return np.cumsum(head) - 1
 
 
-def partition_buckets(inp, world):
-    """Longest-processing-time assignment of whole buckets to `world` ranks by pair count.
+def partition_buckets(inp, world, foreign_weight=100.0):
+    """Longest-processing-time assignment of whole buckets to `world` ranks.
+    Cost of a bucket = sum over its sub-buckets (equal CDR3 lengths) of
+        n(n-1)/2                      pairs the CDR3 pre-filter evaluates
+      + foreign_weight * f * n        stage-2 candidates: f rows whose V/J reference set differs from the sub-bucket's
+                                      majority (e.g. indel-edited references) are scored against every clone-mate through
+                                      the two-reference path and never get skipped by the class test
+      + 64 n                          per-row work.
     Returns a list of ascending row-index arrays (rows of 1-chain buckets, which never join, are dropped)."""
     bucket = bucket_ids(inp)
     nb = int(bucket[-1]) + 1 if inp.n_rows else 0
-    two = inp.a["row_nchains"] == 2
+    two = np.nonzero(inp.a["row_nchains"] == 2)[0]
     c3 = inp.a["row_cdr3_len"].reshape(-1, 2)
     key = np.stack([bucket[two], c3[two, 0], c3[two, 1]], axis=1)
-    uniq, cnt = np.unique(key, axis=0, return_counts=True)
+    uniq, sub_of, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    sub_of = sub_of.reshape(-1)
+    # rows off their sub-bucket's majority reference set
+    vs = inp.a["row_vs"].reshape(-1, 2)[two].astype(np.int64)
+    js = inp.a["row_js"].reshape(-1, 2)[two].astype(np.int64)
+    refkey = ((vs[:, 0] * 1000003 + vs[:, 1]) * 1000003 + js[:, 0]) * 1000003 + js[:, 1]
+    pair = np.stack([sub_of.astype(np.int64), refkey], axis=1)
+    pu, pc = np.unique(pair, axis=0, return_counts=True)
+    major = np.zeros(len(uniq), dtype=np.int64)
+    np.maximum.at(major, pu[:, 0], pc)
+    foreign = cnt - major
     cost = np.zeros(nb, dtype=np.float64)
-    np.add.at(cost, uniq[:, 0], cnt.astype(np.float64) * (cnt - 1) / 2 + 64.0 * cnt)
+    np.add.at(cost, uniq[:, 0], cnt.astype(np.float64) * (cnt - 1) / 2 + foreign_weight * foreign.astype(np.float64) * cnt + 64.0 * cnt)
     # buckets taken out of their neighbourhood must not fuse with another run of the same lens
     lens = inp.a["row_len"].reshape(-1, 2)
     first = np.nonzero(np.diff(np.concatenate([[-1], bucket])))[0]
