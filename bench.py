@@ -309,7 +309,7 @@ def main():
 
     # ---------------- end-to-end arm: host buffers through ejb_join ----------------
     def step_e2e():
-        res = ctx.join(params, inp)
+        res = ctx.join(params, inp, copy=False)   # zero-copy views into the library's pinned result arena
         if world > 1:
             key = torch.from_numpy(my_rows[res.edge_k1].astype(np.int64) << 32 | my_rows[res.edge_k2].astype(np.int64)).to(dev)
             merged = gather_keys(key)

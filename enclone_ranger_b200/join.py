@@ -54,13 +54,19 @@ class EquivRel:
 
 
 class JoinResult:
-    def __init__(self, r):
+    """Edges (raw_joins order), their PotentialJoin numerics, labels and the EquivRel vectors.
+
+    With copy=False the arrays are zero-copy views into the context's pinned result arena: valid until the next
+    join()/download() on the same context (the C ABI's ownership rule); call .detach() to keep them longer."""
+
+    def __init__(self, r, copy=True):
         E, N = r.n_edges, r.n_rows
 
         def arr(p, n, dt):
             if n == 0:
                 return np.zeros(0, dtype=dt)
-            return np.ctypeslib.as_array(p, shape=(n,)).copy()
+            v = np.ctypeslib.as_array(p, shape=(n,))
+            return v.copy() if copy else v
 
         self.edge_k1 = arr(r.edge_k1, E, np.int32)
         self.edge_k2 = arr(r.edge_k2, E, np.int32)
@@ -80,6 +86,12 @@ class JoinResult:
         self.eq_y = arr(r.eq_y, N, np.int32)
         self.eq_z = arr(r.eq_z, N, np.int32)
         self.stats = r.stats.as_dict()
+
+    def detach(self):
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, np.ndarray):
+                setattr(self, k, v.copy())
+        return self
 
     @property
     def raw_joins(self):
@@ -131,10 +143,10 @@ class JoinContext:
             pass
 
     # --- the drop-in call ---
-    def join(self, params, inp):
+    def join(self, params, inp, copy=True):
         r = EjbResult()
         self._ck(self.L.ejb_join(self.h, C.byref(params), _c_input(inp), C.byref(r)))
-        out = JoinResult(r)
+        out = JoinResult(r, copy=copy)
         self.L.ejb_result_free(self.h, C.byref(r))
         return out
 
@@ -148,10 +160,10 @@ class JoinContext:
         self.L.ejb_last_stats(self.h, C.byref(s))
         return s.as_dict()
 
-    def download(self):
+    def download(self, copy=True):
         r = EjbResult()
         self._ck(self.L.ejb_download(self.h, C.byref(r)))
-        out = JoinResult(r)
+        out = JoinResult(r, copy=copy)
         self.L.ejb_result_free(self.h, C.byref(r))
         return out
 
