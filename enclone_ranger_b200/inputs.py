@@ -124,12 +124,17 @@ class JoinInput:
         for n in ("row_len", "row_has_del", "row_vs", "row_js", "row_cdr3_len", "row_exact_col"):
             b[n] = a[n][two]
         # contig / CDR3 bytes: gather the referenced spans
-        def gather_spans(off, ln, data):
+        def gather_spans(off, ln, data, chunk=200000):
             ln = ln.astype(np.int64)
             new_off = np.concatenate([[0], np.cumsum(ln)])[:-1]
-            total = int(ln.sum())
-            src = np.repeat(off - new_off, ln) + np.arange(total, dtype=np.int64)
-            return new_off.astype(np.int64), data[src] if total else data[:0]
+            out = []
+            for c0 in range(0, len(ln), chunk):    # bounded temporaries (a per-byte index array can be tens of GB)
+                l, o = ln[c0:c0 + chunk], off[c0:c0 + chunk]
+                t = int(l.sum())
+                if t:
+                    st = np.cumsum(l) - l
+                    out.append(data[np.repeat(o - st, l) + np.arange(t, dtype=np.int64)])
+            return new_off.astype(np.int64), (np.concatenate(out) if out else data[:0])
         b["row_tig_off"], b["tig_bytes"] = gather_spans(a["row_tig_off"][two], b["row_len"] * (np.repeat(b["row_nchains"], 2) > np.tile([0, 1], len(idx))), a["tig_bytes"])
         b["row_cdr3_off"], b["cdr3_bytes"] = gather_spans(a["row_cdr3_off"][two], b["row_cdr3_len"] * (np.repeat(b["row_nchains"], 2) > np.tile([0, 1], len(idx))), a["cdr3_bytes"])
         # exacts
@@ -149,45 +154,94 @@ class JoinInput:
         b.update(ce)
         return JoinInput(**b), used
 
-    def to_packed(self):
+    def to_packed(self, chunk_rows=100000, native=True):
         """The same input with every eligible contig (pure upper-case ACGT, has_del == 0) supplied 2-bit packed
-        (what the Rust shim sends from info[k].tigsp); the other contigs stay ASCII."""
+        (what the Rust shim sends from info[k].tigsp); the other contigs stay ASCII.  Works in row chunks so that the
+        temporaries stay small (a per-base index array of a 10M-cell repertoire would not fit in memory)."""
         a = self.a
-        n2 = 2 * self.n_rows
-        ln = a["row_len"].astype(np.int64)
         if a["row_tig2_off"].size:
             return self
+        n2 = 2 * self.n_rows
+        if native and self.n_rows:
+            try:
+                return self._to_packed_native()
+            except (RuntimeError, AttributeError, OSError):
+                pass   # generator library missing: numpy fallback below
         valid = np.repeat(a["row_nchains"], 2) > np.tile([0, 1], self.n_rows)
-        ln = np.where(valid, ln, 0)
-        off = a["row_tig_off"]
-        total = int(ln.sum())
-        src = np.repeat(off - (np.cumsum(ln) - ln), ln) + np.arange(total, dtype=np.int64)
-        flat = a["tig_bytes"][src] if total else np.zeros(0, np.uint8)
+        ln_all = np.where(valid, a["row_len"].astype(np.int64), 0)
+        off_all = a["row_tig_off"]
         lut = np.full(256, 255, dtype=np.uint8)
         lut[ord("A")], lut[ord("C")], lut[ord("G")], lut[ord("T")] = 0, 1, 2, 3
-        codes = lut[flat]
-        seg = np.repeat(np.arange(n2), ln)
-        bad = np.zeros(n2, dtype=bool)
-        if total:
-            np.logical_or.at(bad, seg, codes == 255)
-        elig = valid & ~bad & (a["row_has_del"] == 0) & (ln > 0)
-        nw = np.where(elig, (ln + 15) // 16, 0)
-        woff = np.cumsum(nw) - nw
-        words = np.zeros(int(nw.sum()), dtype=np.uint32)
-        keep = elig[seg]
-        pos = (np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(ln) - ln, ln))[keep]
-        widx = woff[seg[keep]] + pos // 16
-        np.bitwise_or.at(words, widx, (codes[keep].astype(np.uint32) << (2 * (pos % 16)).astype(np.uint32)))
+        shifts = (2 * np.arange(16, dtype=np.uint32)).astype(np.uint32)
+        tig2_off = np.full(n2, -1, dtype=np.int64)
+        new_tig_off = np.full(n2, -1, dtype=np.int64)
+        word_chunks, byte_chunks = [], []
+        n_words, n_bytes = 0, 0
+        step = 2 * int(chunk_rows)
+        for c0 in range(0, n2, step):
+            c1 = min(n2, c0 + step)
+            ln, off = ln_all[c0:c1], off_all[c0:c1]
+            total = int(ln.sum())
+            if total == 0:
+                continue
+            start = np.cumsum(ln) - ln
+            src = np.repeat(off - start, ln) + np.arange(total, dtype=np.int64)
+            flat = a["tig_bytes"][src]
+            codes = lut[flat]
+            seg = np.repeat(np.arange(c1 - c0), ln)
+            bad = np.zeros(c1 - c0, dtype=bool)
+            bad[np.unique(seg[codes == 255])] = True
+            elig = (ln > 0) & ~bad & (a["row_has_del"][c0:c1] == 0)
+            # packed part: pad every eligible contig to a multiple of 16 bases, then fold 16 codes into one word
+            nw = np.where(elig, (ln + 15) // 16, 0)
+            woff = np.cumsum(nw) - nw
+            tw = int(nw.sum())
+            if tw:
+                padded = np.zeros(tw * 16, dtype=np.uint32)
+                keep = elig[seg]
+                pos = (np.arange(total, dtype=np.int64) - np.repeat(start, ln))[keep]
+                padded[np.repeat(woff * 16, np.where(elig, ln, 0)) + pos] = codes[keep]
+                words = np.bitwise_or.reduce(padded.reshape(-1, 16) << shifts, axis=1).astype(np.uint32)
+                word_chunks.append(words)
+                tig2_off[c0:c1] = np.where(elig, woff + n_words, -1)
+                n_words += tw
+            # ASCII part
+            ln_a = np.where(elig, 0, ln)
+            tb = int(ln_a.sum())
+            if tb:
+                byte_chunks.append(flat[~elig[seg]])
+                aoff = np.cumsum(ln_a) - ln_a
+                new_tig_off[c0:c1] = np.where(~elig & (ln > 0), aoff + n_bytes, -1)
+                n_bytes += tb
         b = dict(a)
-        b["row_tig2_off"] = np.where(elig, woff, -1).astype(np.int64)
-        b["tig2_words"] = words
-        # ASCII bytes only for the rows that stay ASCII
-        ln_ascii = np.where(elig, 0, ln)
-        new_off = np.cumsum(ln_ascii) - ln_ascii
-        tot2 = int(ln_ascii.sum())
-        src2 = np.repeat(off - new_off, ln_ascii) + np.arange(tot2, dtype=np.int64)
-        b["tig_bytes"] = a["tig_bytes"][src2] if tot2 else np.zeros(0, np.uint8)
-        b["row_tig_off"] = np.where(elig, -1, new_off).astype(np.int64)
+        b["row_tig2_off"] = tig2_off
+        b["tig2_words"] = np.concatenate(word_chunks) if word_chunks else np.zeros(0, np.uint32)
+        b["tig_bytes"] = np.concatenate(byte_chunks) if byte_chunks else np.zeros(0, np.uint8)
+        b["row_tig_off"] = new_tig_off
+        return JoinInput(**b)
+
+    def _to_packed_native(self):
+        lib = load_synth()
+        n2 = 2 * self.n_rows
+        t2 = np.zeros(n2, dtype=np.int64)
+        to = np.zeros(n2, dtype=np.int64)
+        words, nbw = C.POINTER(C.c_uint32)(), C.c_int64()
+        byts, nbb = C.POINTER(C.c_uint8)(), C.c_int64()
+        lib.ejb_synth_pack_contigs.argtypes = [C.POINTER(EjbInput), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.POINTER(C.c_uint32)),
+                                               C.POINTER(C.c_int64), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_int64)]
+        lib.ejb_synth_pack_contigs.restype = C.c_int
+        lib.ejb_synth_free_array.argtypes = [C.c_void_p]
+        rc = lib.ejb_synth_pack_contigs(self.c_ptr(), t2.ctypes.data_as(C.POINTER(C.c_int64)), to.ctypes.data_as(C.POINTER(C.c_int64)),
+                                        C.byref(words), C.byref(nbw), C.byref(byts), C.byref(nbb))
+        if rc != 0:
+            raise RuntimeError("ejb_synth_pack_contigs failed")
+        b = dict(self.a)
+        b["row_tig2_off"] = t2
+        b["row_tig_off"] = to
+        b["tig2_words"] = np.ctypeslib.as_array(words, shape=(max(nbw.value, 1),))[: nbw.value].copy()
+        b["tig_bytes"] = np.ctypeslib.as_array(byts, shape=(max(nbb.value, 1),))[: nbb.value].copy()
+        lib.ejb_synth_free_array(words)
+        lib.ejb_synth_free_array(byts)
         return JoinInput(**b)
 
     def nbytes(self):
