@@ -350,6 +350,12 @@ def main():
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             hbm_peak = 6650.0
+        traffic = None   # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
+        try:
+            nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+            traffic = nt[dom]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         alg_bytes = packed_bytes + 8.0 * stats["joins"] + 4.0 * inp.n_rows   # rank 0's share at N > 1
         line = {
             "metric": METRIC, "value": pairs / (t_step / 1e3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -367,7 +373,8 @@ def main():
                     "breakdown_ms": {k: e2e_stats[k] for k in ("ms_h2d", "ms_device_total", "ms_d2h", "ms_replay")}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "popc", "kernel": dom, "achieved": kernels[dom]["achieved_gpopc_s"], "peak": peak_g, "unit": "Gpopc/s",
-                         "frac": kernels[dom]["achieved_gpopc_s"] / peak_g, "traffic": None, "peak_source": "measured in this job (ejb_measure_peaks: dependency-free __popc loop)",
+                         "frac": kernels[dom]["achieved_gpopc_s"] / peak_g, "traffic": traffic,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/ncu_traffic_r1.json (ncu --set full, 1M-cell config[1])", "peak_source": "measured in this job (ejb_measure_peaks: dependency-free __popc loop)",
                          "lop3_peak_gops": peaks["lop3_per_s"] / 1e9, "kernels": kernels,
                          "whole_join": {"popc_per_pair": p1_avg + p2_avg * stats["stage1_candidates"] / max(pairs, 1),
                                         "roofline_pairs_per_s": peaks["popc_per_s"] / (p1_avg + p2_avg * stats["stage1_candidates"] / max(pairs, 1)),
