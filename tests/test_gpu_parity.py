@@ -209,3 +209,19 @@ def test_empty_and_ragged_inputs(gpu_ctx):
     _, p, inp, _ = next(c for c in CASES if c[0] == "onesies_never_join")
     r = gpu_ctx.join(p, inp)
     assert len(r.edge_k1) == 0 and r.labels.tolist() == [0, 1]
+
+
+@pytest.mark.parametrize("block", range(5))
+def test_randomized_differential(gpu_ctx, block):
+    """Random small inputs mixing rare branches of join_one (gaps with and without shifted seq_del_amino, odd bytes,
+    alternative V/J references, gene-name / UTR variants, jittered feature starts, donors, barcode overlaps, parameter
+    variants): CUDA result == oracle, for ASCII and for 2-bit packed contigs."""
+    import fuzz
+    n_edges = 0
+    for seed in range(block * 60, block * 60 + 60):
+        p, inp = fuzz.random_world(seed)
+        want = pyoracle.run(p, inp.c_ptr(), threads=1)
+        assert_same_result(gpu_ctx.join(p, inp), want, f"fuzz seed {seed}")
+        assert_same_result(gpu_ctx.join(p, inp.to_packed()), want, f"fuzz seed {seed} packed")
+        n_edges += len(want["edge_k1"])
+    assert n_edges > 0

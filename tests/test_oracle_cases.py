@@ -124,3 +124,14 @@ def test_forest_equals_sequential_replay():
         a, b = find(k1), find(k2)
         assert a != b                   # forest
         parent[a] = b
+
+
+def test_fuzz_generator_is_sane():
+    """The random worlds used by the GPU differential test exercise joins, two-reference joins and err joins."""
+    import fuzz
+    edges = nrefs2 = errs = 0
+    for seed in range(40):
+        p, inp = fuzz.random_world(seed)
+        r = pyoracle.run(p, inp.c_ptr(), 1)
+        edges += len(r["edge_k1"]); nrefs2 += int((r["edge_nrefs"] == 2).sum()); errs += int(r["edge_err"].sum())
+    assert edges > 50 and nrefs2 > 5 and errs > 5
