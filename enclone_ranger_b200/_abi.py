@@ -247,7 +247,7 @@ def load_join():
             raise RuntimeError(
                 f"{LIB_JOIN} is missing — the CUDA extension must be built "
                 "(`python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
-        L = C.CDLL(os.environ.get("EJB_LIB", LIB_JOIN))   # EJB_LIB: developer override to A/B-test a differently built library
+        L = C.CDLL(LIB_JOIN)
         L.ejb_abi_version.restype = C.c_int
         L.ejb_abi_sizes.argtypes = [_i64p]
         L.ejb_abi_sizes.restype = None

@@ -431,13 +431,7 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
         a[AX_FR3] = in.ch_fr3[ch];
         a[AX_CHH] = ch;
         a[AX_CHL] = cl;
-        a[AX_REC] = (int32_t)(uint32_t)(sb.rs_off + li * (int64_t)sb.rec_u4);
-        a[AX_CW] = (int32_t)(uint32_t)(sb.s1_off + li);
-        a[AX_NPAD] = sb.npad;
-        a[AX_META] = (int32_t)((uint32_t)sb.W1 | ((uint32_t)sb.W4h << 3) | ((uint32_t)sb.W4l << 7) | ((uint32_t)sb.gap << 11) | ((uint32_t)sb.ch << 16));
-        a[AX_META2] = (int32_t)((uint32_t)sb.cl | ((uint32_t)(sb.Lh + sb.Ll) << 16));
-        a[AX_SUB] = s;
-        a[AX_PAD] = 0;
+        a[AX_PAD1] = a[AX_PAD2] = a[AX_PAD3] = 0;
     }
     __syncwarp();
     if (lane < AUX_INTS / 4) reinterpret_cast<uint4*>(aux + q * AUX_INTS)[lane] = reinterpret_cast<const uint4*>(a)[lane];

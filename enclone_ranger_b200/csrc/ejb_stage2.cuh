@@ -47,7 +47,7 @@ constexpr int SURV_CHUNK = 64;                    // slots a warp reserves per a
 
 // Integer tests shared by the fast and the slow path, executed by one lane per candidate.
 // Returns true and fills `s` (+ requests its p1) unless join_one would already return false.
-__device__ __forceinline__ bool s2_integer_tests(const S2Ctx& X, uint32_t q1, uint32_t q2, uint32_t slot, int ch, int cl, int n3, int cd1, int cd2,
+__device__ __forceinline__ bool s2_integer_tests(const S2Ctx& X, uint32_t q1, uint32_t q2, uint32_t slot, const SubBucket& sb, int cd1, int cd2,
                                                  long long diffs, int nrefs, int sh0, int in0, int sh1, int in1, RegionDiffs rg, bool pre_ok,
                                                  bool force_emit, Survivor& s) {
     const DevParams& P = X.P;
@@ -58,7 +58,7 @@ __device__ __forceinline__ bool s2_integer_tests(const S2Ctx& X, uint32_t q1, ui
     bool ok = pre_ok;
     // join_one.rs:216-234
     if (P.is_bcr) {
-        const int total = ch + cl;
+        const int total = sb.ch + sb.cl;
         if ((double)cd / (double)total > P.cdr3_ident_thr) ok = false;
     }
     // :238-267
@@ -106,7 +106,7 @@ __device__ __forceinline__ bool s2_integer_tests(const S2Ctx& X, uint32_t q1, ui
     s.c2d = (uint16_t)rg.c2d;
     s.pad = 0;
     s.slot = slot;
-    if (k <= SR_NMAX) p1_request(X.p1, n3, k, min_sh, X.ctr);
+    if (k <= SR_NMAX) p1_request(X.p1, sb.n3, k, min_sh, X.ctr);
     return true;
 }
 
@@ -339,10 +339,7 @@ __device__ __forceinline__ void s2_planes(const S2Ctx& X, const CandInfo& ci, in
 //   phase 2: one lane per candidate runs the scalar integer tests and emits the survivor.
 // A CTA takes CONTIGUOUS chunks of the candidate list: consecutive candidates come from one stage-1 tile
 // (<= 128 + 64 distinct rows), so their row records are re-read from L1 instead of L2.
-#ifndef S2A_MINBLOCKS
-#define S2A_MINBLOCKS 3
-#endif
-__global__ void __launch_bounds__(256, S2A_MINBLOCKS) k_stage2a(S2Ctx X, const uint2* __restrict__ cand, const uint32_t* __restrict__ cand_slot,
+__global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __restrict__ cand, const uint32_t* __restrict__ cand_slot,
                                                     const unsigned long long* __restrict__ n_cand_p, unsigned long long cand_cap) {
     constexpr unsigned long long S2A_CHUNK = 2048;
     __shared__ unsigned long long s_chunk;
@@ -366,69 +363,57 @@ __global__ void __launch_bounds__(256, S2A_MINBLOCKS) k_stage2a(S2Ctx X, const u
         uint2 pr = make_uint2(0, 0);
         if (valid) pr = cand[ci];
         const uint32_t q1 = pr.x, q2 = pr.y;
+        const int sid = X.subq[q1];
+        if (valid && !X.tuple_mode && (int)q1 >= X.qcut[sid]) valid = false;   // row truncated from this round's unit after stage 1
+        const SubBucket sb = X.subs[sid];
         const int32_t* a1 = X.aux + (size_t)q1 * AUX_INTS;
         const int32_t* a2 = X.aux + (size_t)q2 * AUX_INTS;
         const uint4 a10 = __ldg(reinterpret_cast<const uint4*>(a1)), a20 = __ldg(reinterpret_cast<const uint4*>(a2));
-        const uint4 a11 = __ldg(reinterpret_cast<const uint4*>(a1) + 1), a21 = __ldg(reinterpret_cast<const uint4*>(a2) + 1);
-        const uint4 a16 = __ldg(reinterpret_cast<const uint4*>(a1) + 6), a17 = __ldg(reinterpret_cast<const uint4*>(a1) + 7);
-        const uint4 a26 = __ldg(reinterpret_cast<const uint4*>(a2) + 6);
-        const int sid = (int)a17.z;
-        if (valid && !X.tuple_mode && (int)q1 >= X.qcut[sid]) valid = false;   // row truncated from this round's unit after stage 1
         const uint32_t f1 = a10.x, f2 = a20.x;
-        const uint32_t meta = a17.x;
-        const int W1 = meta & 7, W4h = (meta >> 3) & 15, W4l = (meta >> 7) & 15, ch = meta >> 16, cl = a17.y & 0xffff, n3 = 3 * (int)(a17.y >> 16);
-        const bool nrefs1 = (a10.y == a20.y && a10.z == a20.z && a10.w == a20.w && a11.x == a21.x);
-        const bool fast = valid && ((f1 | f2) & F_SLOWMASK) == 0 && W1 > 0 && W4h > 0 && W4l > 0;
-        const bool wide = fast && (W4h > 4 || W4l > 4);
-        const int tot1 = (int)a11.y, tot2 = (int)a21.y;
+        const bool nrefs1 = (a10.y == a20.y && a10.z == a20.z && a10.w == a20.w && a1[AX_JSL] == a2[AX_JSL]);
+        const bool fast = valid && ((f1 | f2) & F_SLOWMASK) == 0 && sb.W1 > 0 && sb.W4h > 0 && sb.W4l > 0;
+        const bool wide = fast && (sb.W4h > 4 || sb.W4l > 4);
+        const int tot1 = a1[AX_TOT], tot2 = a2[AX_TOT];
         // phase 0: two references — try the memoised totals first
         bool memo_dead = false;
         if (fast && !nrefs1 && !X.tuple_mode) {
             int T;
-            if (memo_lookup(X.memo, q1, (int)a20.y, (int)a20.z, (int)a20.w, (int)a21.x, T) && abs(tot1 - T) > X.P.max_degradation) memo_dead = true;        // T10
-            else if (memo_lookup(X.memo, q2, (int)a10.y, (int)a10.z, (int)a10.w, (int)a11.x, T) && abs(T - tot2) > X.P.max_degradation) memo_dead = true;   // T01
+            if (memo_lookup(X.memo, q1, (int)a20.y, (int)a20.z, (int)a20.w, a2[AX_JSL], T) && abs(tot1 - T) > X.P.max_degradation) memo_dead = true;        // T10
+            else if (memo_lookup(X.memo, q2, (int)a10.y, (int)a10.z, (int)a10.w, a1[AX_JSL], T) && abs(T - tot2) > X.P.max_degradation) memo_dead = true;   // T01
         }
-        const bool live = fast && !memo_dead;
         CandInfo me;
-        me.meta = (meta & ~(7u << 13)) | ((uint32_t)live << 13) | ((uint32_t)nrefs1 << 14);
-        me.rec1 = a16.y;
-        me.rec2 = a26.y;
-        me.cw1 = a16.z;
-        me.cw2 = a26.z;
-        me.npad = a16.w;
+        me.meta = (uint32_t)sb.W1 | ((uint32_t)sb.W4h << 3) | ((uint32_t)sb.W4l << 7) | ((uint32_t)sb.gap << 11) | ((uint32_t)(fast && !memo_dead) << 13) |
+                  ((uint32_t)nrefs1 << 14) | ((uint32_t)sb.ch << 16);
+        me.rec1 = (uint32_t)(sb.rs_off + (int64_t)(q1 - sb.q0) * sb.rec_u4);
+        me.rec2 = (uint32_t)(sb.rs_off + (int64_t)(q2 - sb.q0) * sb.rec_u4);
+        me.cw1 = (uint32_t)(sb.s1_off + (q1 - sb.q0));
+        me.cw2 = (uint32_t)(sb.s1_off + (q2 - sb.q0));
+        me.npad = (uint32_t)sb.npad;
         me.tot1 = tot1;
         me.tot2 = tot2;
-        // ---- phase 1: plane math for the live candidates of the batch only ----
-        const unsigned int livemask = __ballot_sync(0xffffffffu, live);
-        const int nlive = __popc(livemask);
-        if (nlive > 0) {
-            if (!__any_sync(0xffffffffu, wide)) {
+        // ---- phase 1 ----
+        if (!__any_sync(0xffffffffu, wide)) {
 #pragma unroll 1
-                for (int it = 0; it * 8 < nlive; it++) {
-                    const int idx = it * 8 + (lane >> 2);                       // index among the live candidates
-                    const int src = idx < nlive ? (int)__fns(livemask, 0, idx + 1) : 0;   // lane that owns it
-                    CandInfo gc = shfl_cand(me, src);
-                    if (idx >= nlive) gc.meta &= ~(1u << 13);
-                    uint32_t r[8];
-                    s2_planes<4>(X, gc, lane & 3, 0xfu << (lane & 28), r);
-                    if ((lane & 3) == 0 && idx < nlive) {
+            for (int it = 0; it < 4; it++) {
+                const int src = it * 8 + (lane >> 2);           // candidate (lane index of its owner) this group works on
+                const CandInfo gc = shfl_cand(me, src);
+                uint32_t r[8];
+                s2_planes<4>(X, gc, lane & 3, 0xfu << (lane & 28), r);
+                if ((lane & 3) == 0) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) s_res[wib][src][i] = r[i];
-                    }
+                    for (int i = 0; i < 8; i++) s_res[wib][src][i] = r[i];
                 }
-            } else {
+            }
+        } else {
 #pragma unroll 1
-                for (int it = 0; it * 4 < nlive; it++) {
-                    const int idx = it * 4 + (lane >> 3);
-                    const int src = idx < nlive ? (int)__fns(livemask, 0, idx + 1) : 0;
-                    CandInfo gc = shfl_cand(me, src);
-                    if (idx >= nlive) gc.meta &= ~(1u << 13);
-                    uint32_t r[8];
-                    s2_planes<8>(X, gc, lane & 7, 0xffu << (lane & 24), r);
-                    if ((lane & 7) == 0 && idx < nlive) {
+            for (int it = 0; it < 8; it++) {
+                const int src = it * 4 + (lane >> 3);
+                const CandInfo gc = shfl_cand(me, src);
+                uint32_t r[8];
+                s2_planes<8>(X, gc, lane & 7, 0xffu << (lane & 24), r);
+                if ((lane & 7) == 0) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) s_res[wib][src][i] = r[i];
-                    }
+                    for (int i = 0; i < 8; i++) s_res[wib][src][i] = r[i];
                 }
             }
         }
@@ -457,20 +442,20 @@ __global__ void __launch_bounds__(256, S2A_MINBLOCKS) k_stage2a(S2Ctx X, const u
                 rg.c2d = (int)(r[3] >> 16);
                 if (nrefs1) {
                     const int A = (int)(r[1] & 0xffff), B = (int)(r[1] >> 16);
-                    emit = s2_integer_tests(X, q1, q2, slot, ch, cl, n3, cd1, cd2, diffs, 1, A - B, tot1 + tot2 - 2 * A + 2 * B, 0, 0, rg, true, X.tuple_mode != 0, sv);
+                    emit = s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, 1, A - B, tot1 + tot2 - 2 * A + 2 * B, 0, 0, rg, true, X.tuple_mode != 0, sv);
                 } else {
                     const int A0 = (int)(r[4] & 0xffff), B0 = (int)(r[4] >> 16), O0 = (int)(r[5] & 0xffff), T01 = (int)(r[5] >> 16);
                     const int A1 = (int)(r[6] & 0xffff), B1 = (int)(r[6] >> 16), O1 = (int)(r[7] & 0xffff), T10 = (int)(r[7] >> 16);
                     // join_one.rs:434-440: total[0] = (tot1, T01), total[1] = (T10, tot2)
                     if (!X.tuple_mode) {
-                        memo_store(X.memo, q1, (int)a20.y, (int)a20.z, (int)a20.w, (int)a21.x, T10);
-                        memo_store(X.memo, q2, (int)a10.y, (int)a10.z, (int)a10.w, (int)a11.x, T01);
+                        memo_store(X.memo, q1, (int)a20.y, (int)a20.z, (int)a20.w, a2[AX_JSL], T10);
+                        memo_store(X.memo, q2, (int)a10.y, (int)a10.z, (int)a10.w, a1[AX_JSL], T01);
                     }
                     bool ok = true;
                     if (abs(tot1 - T10) > X.P.max_degradation) ok = false;
                     if (abs(T01 - tot2) > X.P.max_degradation) ok = false;
                     if (ok || X.tuple_mode)
-                        emit = s2_integer_tests(X, q1, q2, slot, ch, cl, n3, cd1, cd2, diffs, 2, A0 - B0, O0 + 2 * B0, A1 - B1, O1 + 2 * B1, rg, ok, X.tuple_mode != 0, sv);
+                        emit = s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, 2, A0 - B0, O0 + 2 * B0, A1 - B1, O1 + 2 * B1, rg, ok, X.tuple_mode != 0, sv);
                 }
             } else {
                 const unsigned long long si = atomicAdd(&X.ctr->n_slow, 1ull);
@@ -593,7 +578,7 @@ __global__ void __launch_bounds__(256) k_stage2_slow(S2Ctx X, const unsigned lon
             RegionDiffs rg = {0, 0, 0, 0};
             Survivor sv;
             if ((ok || X.tuple_mode) &&
-                s2_integer_tests(X, q1, q2, slot, sb.ch, sb.cl, sb.n3, cd1, cd2, diffs, nrefs, sh[0], ind[0], sh[1], ind[1], rg, ok, X.tuple_mode != 0, sv)) {
+                s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, nrefs, sh[0], ind[0], sh[1], ind[1], rg, ok, X.tuple_mode != 0, sv)) {
                 const unsigned long long si = atomicAdd(&X.ctr->n_surv, 1ull);   // rare path: one atomic per survivor is fine
                 if (si < X.surv_cap) X.surv[si] = sv; else X.ctr->overflow = 1ull;
                 atomicAdd(&X.ctr->n_surv_total, 1ull);

@@ -34,15 +34,10 @@ enum AuxField {
     AX_FLAGS = 0, AX_VSH, AX_VSL, AX_JSH, AX_JSL, AX_TOT, AX_EXACT, AX_NCELLS,          // uint4 #0, #1
     AX_DONLO, AX_DONHI, AX_CREFH, AX_CREFL, AX_HCOMP, AX_VREFH, AX_VREFL, AX_BC0,       // uint4 #2, #3
     AX_VNAMEH, AX_VNAMEL, AX_FR1, AX_CDR1, AX_FR2, AX_CDR2, AX_FR3, AX_CHH,             // uint4 #4, #5
-    AX_CHL, AX_REC, AX_CW, AX_NPAD,                                                     // uint4 #6
-    AX_META, AX_META2, AX_SUB, AX_PAD,                                                  // uint4 #7
+    AX_CHL, AX_PAD1, AX_PAD2, AX_PAD3,                                                  // uint4 #6
     AUX_INTS
 };
-static_assert(AUX_INTS == 32, "aux record is 8 uint4 (128 bytes)");
-// AX_REC  : uint4 index of the row record in rowstore          AX_CW : word index of the row in plane 0 / word 0 of cdr3w
-// AX_NPAD : row stride of the sub-bucket's CDR3 planes
-// AX_META : W1 | W4h<<3 | W4l<<7 | gap<<11 | ch<<16  (bits 13-15 are free for per-candidate flags)
-// AX_META2: cl | (Lh+Ll)<<16                                    AX_SUB: sub-bucket id
+static_assert(AUX_INTS == 28, "aux record is 7 uint4");
 
 enum RowFlags : uint32_t {
     F_ODDBYTE_H = 1u, F_ODDBYTE_L = 2u,   // contig has a byte outside ACGT ('-' is fine when has_del is set)
