@@ -269,16 +269,23 @@ def main():
     # ---------------- device-resident arm: value ----------------
     ctx.upload(params, inp)
 
+    gather_ms = []
+
     def step_resident():
         st = ctx.run()
         if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             k1, k2 = ctx.device_edges()     # device pointers, no host round trip
             gather_keys((rows_dev[k1.long()] << 32) | rows_dev[k2.long()])
+            e1.record()
+            gather_ms.append((e0, e1))
         return st
 
     for _ in range(args.warmup):
         step_resident()
     barrier()
+    gather_ms.clear()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     dev_ms, wall0, launches, stats = [], time.perf_counter(), 0, None
     for _ in range(args.steps):
@@ -288,8 +295,10 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3 / args.steps
     clocks = sampler.stop() if sampler else None
-    # per-step time: CUDA-event device time at N=1; at N>1 the slowest rank's wall time per step (run + gather + merge)
-    t_local = (sum(dev_ms) / len(dev_ms)) if world == 1 else wall_ms
+    # per-step time on the device clock: the library's CUDA events around the join (its own stream) + at N>1 torch CUDA events
+    # around the edge gather / merge (torch's stream; it starts after the join has completed); max over ranks below
+    g_ms = [a.elapsed_time(b) for a, b in gather_ms]
+    t_local = (sum(dev_ms) + sum(g_ms)) / len(dev_ms)
     pairs = stats["pairs_scored"]
     if world > 1:
         t = torch.tensor([t_local], dtype=torch.float64, device=dev)
@@ -298,11 +307,11 @@ def main():
         ln = torch.tensor([launches, pairs], dtype=torch.int64, device=dev)
         dist.all_reduce(ln)
         launches, pairs = int(ln[0].item()), int(ln[1].item())
-        keys = ("pairs_scored", "pairs_evaluated", "stage1_candidates", "stage2_survivors", "pass_edges", "rounds", "overflow_retries",
+        keys = ("pairs_scored", "pairs_evaluated", "stage1_candidates", "stage1_ref_kills", "stage2_survivors", "pass_edges", "rounds", "overflow_retries",
                 "ms_pack", "ms_stage1", "ms_stage2", "ms_stage2a", "ms_forest", "ms_finalize")
         pr = [torch.zeros(2 + len(keys), dtype=torch.float64, device=dev) for _ in range(world)]
         dist.all_gather(pr, torch.tensor([wall_ms, sum(dev_ms) / len(dev_ms)] + [float(stats[k]) for k in keys], dtype=torch.float64, device=dev))
-        per_rank = [dict({"wall_ms": round(float(x[0]), 2), "device_ms": round(float(x[1]), 2)}, **{k: round(float(v), 2) for k, v in zip(keys, x[2:].tolist())}) for x in pr]
+        per_rank = [dict({"wall_ms": round(float(x[0]), 2), "join_device_ms": round(float(x[1]), 2)}, **{k: round(float(v), 2) for k, v in zip(keys, x[2:].tolist())}) for x in pr]
     else:
         t_step = t_local
         per_rank = None
@@ -364,7 +373,7 @@ def main():
                        "pairs_scored": int(pairs), "pairs_lens_buckets": int(stats["pairs_lens"]), "sub_buckets": int(stats["n_subbuckets"]),
                        "parallelism": f"bucket-sharded x{world}, weak scaling (1M cells per GPU)" if world > 1 else "single GPU",
                        "l2": f"inputs ({stats['h2d_bytes'] / 1e6:.0f} MB raw + packed row store) exceed the 126 MB L2; no flush needed",
-                       "timing": "CUDA events on the library's launching stream (ejb_stats.ms_device_total)" if world == 1 else "wall clock between device syncs, max over ranks",
+                       "timing": "CUDA events on the library's launching stream (ejb_stats.ms_device_total)" if world == 1 else "device clock: CUDA events of the join on the library's stream + CUDA events of the NCCL edge gather and merge on torch's stream, max over ranks",
                        "wall_ms_per_step": wall_ms, "generate_s": t_gen, "per_rank": per_rank,
                        "contig_encoding": "ASCII" if args.ascii else f"2-bit packed where eligible ({raw_tig_bytes / 1e6:.0f} MB ASCII -> {inp.a['tig2_words'].nbytes / 1e6:.0f} MB packed + {inp.a['tig_bytes'].nbytes / 1e6:.0f} MB ASCII)"},
             "clocks": clocks,
@@ -381,7 +390,7 @@ def main():
                                         "frac": (pairs / (t_step / 1e3)) / (peaks["popc_per_s"] / (p1_avg + p2_avg * stats["stage1_candidates"] / max(pairs, 1)))},
                          "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (t_step / 1e3) / 1e9, "peak_gbs": hbm_peak}},
             "stage_ms": {k: stats[k] for k in ("ms_pack", "ms_stage1", "ms_stage2", "ms_stage2a", "ms_forest", "ms_finalize")},
-            "counts": {k: int(stats[k]) for k in ("pairs_evaluated", "stage1_candidates", "stage2_slow", "stage2_survivors", "pass_edges", "forest_edges", "joins", "rounds")},
+            "counts": {k: int(stats[k]) for k in ("pairs_evaluated", "stage1_candidates", "stage1_ref_kills", "stage2_two_ref", "stage2_memo_dead", "stage2_degr_dead", "stage2_slow", "stage2_survivors", "pass_edges", "forest_edges", "joins", "rounds")},
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle   # CPU baseline leg only: the checker timed as a baseline, never on the product path

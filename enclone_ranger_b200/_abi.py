@@ -144,6 +144,10 @@ class EjbStats(C.Structure):
         ("overflow_retries", C.c_int64),
         ("ms_device_total", C.c_double),
         ("ms_total", C.c_double),
+        ("stage1_ref_kills", C.c_int64),
+        ("stage2_two_ref", C.c_int64),
+        ("stage2_memo_dead", C.c_int64),
+        ("stage2_degr_dead", C.c_int64),
     ]
 
     def as_dict(self):

@@ -74,6 +74,12 @@ struct ejb_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    // Large host->device copies are spread over a few copy streams: on this platform one cudaMemcpyAsync from pinned memory
+    // reaches ~40 GB/s at 16 MB and ~55 GB/s at 512 MB, i.e. every copy pays ~0.1 ms of setup that concurrent copies overlap.
+    static constexpr int N_UP = 4;
+    cudaStream_t up_stream[N_UP] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t up_event[N_UP] = {nullptr, nullptr, nullptr, nullptr};
+    int up_next = 0;
     std::string err;
     int shard_rank = 0, shard_world = 1;
     unsigned long long cand_cap = 1ull << 27;
@@ -98,12 +104,15 @@ struct ejb_ctx {
     size_t in_used = 0;
     int64_t h2d_bytes = 0;
     double ms_h2d = 0;
+    int64_t n_canon_segs = 0;   // distinct seg contents (canonical ids are 0 .. n_canon_segs-1)
 
     // derived (per run)
     DevBuf d_head, d_scan, d_keys, d_keys2, d_vals, d_vals2, d_cubtmp, d_subhead, d_subincl, d_subinfo;
     DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_aux;
     DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
-    DevBuf d_unitcand, d_qcut, d_subpass, d_segpl, d_memo;
+    DevBuf d_unitcand, d_qcut, d_subpass, d_segpl, d_memo, d_tagq, d_deadq;
+    bool tags_on = false;      // reference-set tags in use (every canonical seg id < 65535)
+    int s1_mode = S1_RUNI | S1_TAGS;   // stage-1 kernel variant (EJB_S1_MODE, developer knob)
     std::vector<unsigned int> h_subpass;
     std::vector<unsigned long long> h_unitcand;   // candidates of each task (row range) of the last round, valid even when it overflowed
     struct TaskMeta { int32_t unit, r0, r1; };
@@ -189,7 +198,9 @@ int upload_array(ejb_ctx* c, const T* src, int64_t n, const T** dst) {
     CK(b.ensure(bytes + 16));
     if (n > 0) {
         if (!src) return fail(c, EJB_ERR_INVALID, "null input array with %lld elements", (long long)n);
-        CK(cudaMemcpyAsync(b.p, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+        cudaStream_t st = c->stream;
+        if ((size_t)n * sizeof(T) >= (1u << 20)) st = c->up_stream[c->up_next++ % ejb_ctx::N_UP];
+        CK(cudaMemcpyAsync(b.p, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, st));
         c->h2d_bytes += (int64_t)n * sizeof(T);
     }
     *dst = b.as<const T>();
@@ -237,11 +248,21 @@ cudaError_t zero_counter(ejb_ctx* c, size_t off) {
     return cudaMemsetAsync(reinterpret_cast<char*>(c->d_ctr.p) + off, 0, sizeof(unsigned long long), c->stream);
 }
 
+template <int W1, int MODE>
+void launch_stage1_wm(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks) {
+    k_stage1<W1, MODE><<<(unsigned int)n_ctas, S1_THREADS, 0, c->stream>>>(c->d_subs.as<SubBucket>(), tasks, n_tasks, c->d_cdr3w.as<uint32_t>(),
+                                                                            c->d_labq.as<int32_t>(), c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(),
+                                                                            c->cand_cap, c->d_ctr.as<Counters>(), c->d_unitcand.as<unsigned long long>(),
+                                                                            c->d_tagq.as<unsigned long long>(), c->d_deadq.as<unsigned long long>());
+}
 template <int W1>
 void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks) {
-    k_stage1<W1><<<(unsigned int)n_ctas, S1_THREADS, 0, c->stream>>>(c->d_subs.as<SubBucket>(), tasks, n_tasks, c->d_cdr3w.as<uint32_t>(),
-                                                                      c->d_labq.as<int32_t>(), c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(),
-                                                                      c->cand_cap, c->d_ctr.as<Counters>(), c->d_unitcand.as<unsigned long long>());
+    switch (c->s1_mode & (c->tags_on ? 3 : 1)) {
+        case 0: launch_stage1_wm<W1, 0>(c, n_ctas, tasks, n_tasks); break;
+        case 1: launch_stage1_wm<W1, S1_RUNI>(c, n_ctas, tasks, n_tasks); break;
+        case 2: launch_stage1_wm<W1, S1_TAGS>(c, n_ctas, tasks, n_tasks); break;
+        default: launch_stage1_wm<W1, S1_RUNI | S1_TAGS>(c, n_ctas, tasks, n_tasks); break;
+    }
 }
 
 // stage-1 for sub-buckets whose CDR3s exceed the fast path: every not-yet-connected pair is a candidate
@@ -290,6 +311,8 @@ S2Ctx make_s2ctx(ejb_ctx* c, int tuple_mode) {
     X.qcut = c->d_qcut.as<int32_t>();
     X.sub_pass = c->d_subpass.as<unsigned int>();
     X.memo = c->d_memo.as<int32_t>();
+    X.tagq = c->tags_on ? c->d_tagq.as<unsigned long long>() : nullptr;
+    X.deadq = c->tags_on ? c->d_deadq.as<unsigned long long>() : nullptr;
     X.cdr3w = c->d_cdr3w.as<uint32_t>();
     X.rowstore = c->d_rowstore.as<uint4>();
     X.bc_sorted = c->d_bckeys2.as<uint64_t>();
@@ -403,6 +426,10 @@ int ejb_create(ejb_ctx** out, const int* device_ids, int n_devices) {
         return code;
     };
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(EJB_ERR_CUDA);
+    for (int i = 0; i < ejb_ctx::N_UP; i++)
+        if (cudaStreamCreateWithFlags(&c->up_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->up_event[i], cudaEventDisableTiming) != cudaSuccess)
+            return bail(EJB_ERR_CUDA);
     if (cudaMallocHost(&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(EJB_ERR_OOM);
     const std::vector<dd_t>& sr = sr_table_host();
     if (c->d_sr.ensure(sr.size() * sizeof(dd_t)) != cudaSuccess) return bail(EJB_ERR_OOM);
@@ -427,6 +454,10 @@ void ejb_destroy(ejb_ctx* c) {
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     if (c->h_res) cudaFreeHost(c->h_res);
     c->in_bufs.clear();
+    for (int i = 0; i < ejb_ctx::N_UP; i++) {
+        if (c->up_event[i]) cudaEventDestroy(c->up_event[i]);
+        if (c->up_stream[i]) cudaStreamDestroy(c->up_stream[i]);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -499,6 +530,7 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
             if (it == ids.end()) it = ids.emplace(std::move(key), (int)ids.size()).first;
             canon[s] = it->second;
         }
+        c->n_canon_segs = (int64_t)ids.size();
     }
 #define UP(field, n) if ((rc = upload_array(c, in->field, (n), &d.field)) != EJB_OK) return rc
     UP(row_nchains, N); UP(row_len, 2 * N); UP(row_tig_off, 2 * N); UP(row_has_del, 2 * N); UP(row_vs, 2 * N); UP(row_js, 2 * N);
@@ -523,6 +555,10 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     if ((rc = upload_array(c, canon.data(), in->n_segs, &d.seg_canon)) != EJB_OK) return rc;
     if (in->n_segs > 0 && !in->seg_bytes) return fail(c, EJB_ERR_INVALID, "seg_bytes is null");
     if ((rc = upload_array(c, (const uint8_t*)seg_canon_bytes.data(), d.n_seg_bytes, &d.seg_bytes)) != EJB_OK) return rc;
+    for (int i = 0; i < ejb_ctx::N_UP; i++) {   // the join's stream continues after every copy stream
+        CK(cudaEventRecord(c->up_event[i], c->up_stream[i]));
+        CK(cudaStreamWaitEvent(c->stream, c->up_event[i], 0));
+    }
     CK(cudaStreamSynchronize(c->stream));
     c->ms_h2d = now_ms() - t0;
     c->have_input = true;
@@ -744,7 +780,17 @@ extern "C" int ejb_run(ejb_ctx* c) {
     const int64_t N = din.n_rows;
     cudaStream_t st = c->stream;
     cudaEvent_t ev_start = c->ev(), ev_packed = c->ev(), ev_rounds = c->ev(), ev_end = c->ev();
+    // EJB_TRACE=1: finer CUDA events inside the prepare phase, printed to stderr (developer aid)
+    const bool trace = getenv("EJB_TRACE") != nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> tr;
+    auto mark = [&](const char* name) {
+        if (!trace) return;
+        cudaEvent_t e = c->ev();
+        cudaEventRecord(e, st);
+        tr.emplace_back(name, e);
+    };
     CK(cudaEventRecord(ev_start, st));
+    mark("start");
     CK(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(Counters), st));
     CK(cudaMemsetAsync(c->d_err.p, 0, 64, st));
     if (c->p1_count > c->p1_cap / 4) {
@@ -773,6 +819,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
         c->stats.kernel_launches += 4;
         rc = cub_sort_pairs64(c, c->d_keys.as<uint64_t>(), c->d_keys2.as<uint64_t>(), c->d_vals.as<uint32_t>(), c->d_vals2.as<uint32_t>(), N);
         if (rc) return rc;
+        mark("scan+sort");
         struct { unsigned int err; unsigned int pad; unsigned long long n_active; } hdr;
         int32_t n_buckets = 0;
         CK(cudaMemcpyAsync(&hdr, c->d_err.p, 16, cudaMemcpyDeviceToHost, st));
@@ -800,6 +847,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
         c->stats.kernel_launches += 2;
         std::vector<SubInfo> si((size_t)n_subs);
         CK(cudaMemcpyAsync(si.data(), c->d_subinfo.p, (size_t)n_subs * sizeof(SubInfo), cudaMemcpyDeviceToHost, st));
+        mark("subinfo");
         CK(cudaStreamSynchronize(st));
         c->stats.d2h_bytes += (int64_t)n_subs * sizeof(SubInfo);
 
@@ -930,13 +978,24 @@ extern "C" int ejb_run(ejb_ctx* c) {
         }
         CK(c->d_memo.ensure(np * 32));
         CK(cudaMemsetAsync(c->d_memo.p, 0, np * 32, st));
+        c->s1_mode = S1_RUNI | S1_TAGS;
+        if (const char* e = getenv("EJB_S1_MODE")) c->s1_mode = atoi(e) & 3;
+        c->tags_on = c->n_canon_segs < 65535 && !getenv("EJB_NO_TAGS") && (c->s1_mode & S1_TAGS);
+        if (c->tags_on) {
+            CK(c->d_tagq.ensure(np * 8)); CK(c->d_deadq.ensure(np * 8));
+            CK(cudaMemsetAsync(c->d_tagq.p, 0xff, np * 8, st));    // padding positions: never part of a valid pair
+            CK(cudaMemsetAsync(c->d_deadq.p, 0xff, np * 8, st));   // DEAD_NONE
+        }
         CK(c->d_segpl.ensure((size_t)std::max<int64_t>(din.n_segs, 1) * 2 * SEGPL_WORDS * 4));
         k_seg_planes<<<nblk(din.n_segs * 32, 256), 256, 0, st>>>(din, c->d_segpl.as<uint32_t>());
+        mark("tables+memsets+bcsort");
         k_pack_rows<<<nblk(NA * 32, 256), 256, 0, st>>>(din, P, c->d_subs.as<SubBucket>(), c->d_subincl.as<int32_t>(), row_of, NA,
                                                        c->d_donor.as<unsigned long long>(), c->d_segpl.as<uint32_t>(), c->d_cdr3w.as<uint32_t>(), c->d_rowstore.as<uint4>(),
-                                                       c->d_aux.as<int32_t>(), c->d_m_row.as<int32_t>(), c->d_m_sub.as<int32_t>());
+                                                       c->d_aux.as<int32_t>(), c->d_m_row.as<int32_t>(), c->d_m_sub.as<int32_t>(),
+                                                       c->tags_on ? c->d_tagq.as<unsigned long long>() : nullptr);
         c->stats.kernel_launches += 2;
         c->stats.kernel_launches++;
+        mark("pack_rows");
         CK(cudaGetLastError());
     }
     // ---- union-find state, work buffers ----
@@ -984,6 +1043,10 @@ extern "C" int ejb_run(ejb_ctx* c) {
         const double cap_round = 0.5 * (double)c->cand_cap;                      // expected candidates allowed per round
         const double target_pass = std::max(4096.0, (double)c->cand_cap / 64.0);   // pass edges one unit should not exceed by much
         int stalls = 0;
+        // developer knobs for the unit schedule (first unit, growth factor of the rows done so far)
+        long long first_unit = 8, growth = 4;
+        if (const char* e = getenv("EJB_FIRST_UNIT")) first_unit = std::max(1ll, atoll(e));
+        if (const char* e = getenv("EJB_GROWTH")) growth = std::max(1ll, atoll(e));
         while (!live.empty()) {
             std::vector<Unit> units;
             unsigned long long pairs = 0;
@@ -1028,7 +1091,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
                         ex = kn.front().cand / (double)std::max(1, kn.front().r1 - kn.front().r0);
                     }
                 } else {
-                    const long long want = (r0 == 0) ? 8 : std::max<long long>(8, 4ll * r0);   // optimistic x4 growth
+                    const long long want = (r0 == 0) ? first_unit : std::max<long long>(first_unit, growth * r0);   // optimistic growth: rows done so far x growth
                     r1 = (int)std::min<long long>((long long)r0 + want, sb.n);
                     ex = (rho[s] > 0.0 ? rho[s] : std::min<double>(64.0, (double)sb.n)) * (double)(r1 - r0);
                     // capacity: never plan more expected candidates than a round may hold
@@ -1178,6 +1241,10 @@ extern "C" int ejb_run(ejb_ctx* c) {
     if (rc) return rc;
     CK(cudaGetLastError());
     c->stats.two_cell_deleted = (int64_t)c->h_ctr->n_two_cell;
+    c->stats.stage1_ref_kills = (int64_t)c->h_ctr->n_s1_kill;
+    c->stats.stage2_two_ref = (int64_t)c->h_ctr->n_two_ref;
+    c->stats.stage2_memo_dead = (int64_t)c->h_ctr->n_memo_dead;
+    c->stats.stage2_degr_dead = (int64_t)c->h_ctr->n_degr_dead;
     c->stats.joins = c->n_final;
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_start, ev_packed); c->stats.ms_pack = ms;
@@ -1190,6 +1257,21 @@ extern "C" int ejb_run(ejb_ctx* c) {
         cudaEventElapsedTime(&ms, t.e0, t.e1); c->stats.ms_stage1 += ms;
         cudaEventElapsedTime(&ms, t.e1, t.e2); c->stats.ms_stage2 += ms;
         cudaEventElapsedTime(&ms, t.e2, t.e3); c->stats.ms_forest += ms;
+    }
+    if (trace) {
+        fprintf(stderr, "[ejb trace] prepare:");
+        for (size_t i = 1; i < tr.size(); i++) {
+            cudaEventElapsedTime(&ms, tr[i - 1].second, tr[i].second);
+            fprintf(stderr, " %s %.3f ms;", tr[i].first, ms);
+        }
+        fprintf(stderr, " total pack %.3f ms\n", c->stats.ms_pack);
+        for (size_t i = 0; i < times.size(); i++) {
+            float a, b, d;
+            cudaEventElapsedTime(&a, times[i].e0, times[i].e1);
+            cudaEventElapsedTime(&b, times[i].e1, times[i].e2);
+            cudaEventElapsedTime(&d, times[i].e2, times[i].e3);
+            fprintf(stderr, "[ejb trace] round %zu: stage1 %.3f stage2 %.3f forest %.3f ms\n", i, a, b, d);
+        }
     }
     c->stats.ms_h2d = c->ms_h2d;
     c->stats.h2d_bytes = c->h2d_bytes;
@@ -1234,30 +1316,34 @@ int ejb_download(ejb_ctx* c, ejb_result* out) {
         c->stats.d2h_bytes += (int64_t)bytes;
         return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
     };
+    // what the EquivRel replay needs comes first; the PotentialJoin numerics follow while the host replays
+    if (E > 0) {
+        CK(get(k1, c->d_o_k1.p, (size_t)E * 4));
+        CK(get(k2, c->d_o_k2.p, (size_t)E * 4));
+    }
+    if (N > 0) CK(get(row_exact, c->din.row_exact, (size_t)N * 4));
+    cudaEvent_t ev_edges = c->ev();
+    CK(cudaEventRecord(ev_edges, st));
     if (E > 0) {
         const size_t e = (size_t)E;
-        CK(get(k1, c->d_o_k1.p, e * 4)); CK(get(k2, c->d_o_k2.p, e * 4)); CK(get(cd, c->d_o_cd.p, e * 4)); CK(get(nrefs, c->d_o_nrefs.p, e * 4));
+        CK(get(cd, c->d_o_cd.p, e * 4)); CK(get(nrefs, c->d_o_nrefs.p, e * 4));
         CK(get(sh, c->d_o_sh.p, e * 8)); CK(get(in, c->d_o_in.p, e * 8)); CK(get(kk, c->d_o_k.p, e * 4)); CK(get(dd_, c->d_o_d.p, e * 4));
         CK(get(nn, c->d_o_n.p, e * 4)); CK(get(p1, c->d_o_p1.p, e * 8)); CK(get(mult, c->d_o_mult.p, e * 8)); CK(get(score, c->d_o_score.p, e * 8));
         CK(get(err, c->d_o_err.p, e));
     }
-    if (N > 0) {
-        CK(get(labels, c->d_labels.p, (size_t)N * 4));
-        CK(get(row_exact, c->din.row_exact, (size_t)N * 4));
-    }
-    CK(cudaStreamSynchronize(st));
-    c->stats.ms_d2h = now_ms() - t0;
-    // replay into the reference's EquivRel (join2.rs:45-54, 69-84) so that x/y/z match from_raw
+    if (N > 0) CK(get(labels, c->d_labels.p, (size_t)N * 4));
+    CK(cudaEventSynchronize(ev_edges));
+    // replay into the reference's EquivRel (join2.rs:45-54, 69-84) so that x/y/z match from_raw; the state is built in place
+    // in the result arena
     const double t1 = now_ms();
-    if (c->shard_world == 1 && N > 0) {
-        ejbhost::EquivRel eq((int32_t)N);
+    if (N > 0) {   // sharded contexts: the state of the local edges only
+        ejbhost::EquivRel eq((int32_t)N, ex, ey, ez);
         for (int64_t i = 0; i < E; i++) eq.join(k1[i], k2[i]);
         ejbhost::finish_join_merge(eq, row_exact, N);
-        memcpy(ex, eq.x.data(), (size_t)N * 4);
-        memcpy(ey, eq.y.data(), (size_t)N * 4);
-        memcpy(ez, eq.z.data(), (size_t)N * 4);
     }
     c->stats.ms_replay = now_ms() - t1;
+    CK(cudaStreamSynchronize(st));
+    c->stats.ms_d2h = now_ms() - t0 - c->stats.ms_replay;
     int64_t errors = 0;
     for (int64_t i = 0; i < E; i++) errors += err[i];
     c->stats.errors = errors;
@@ -1372,9 +1458,9 @@ int ejb_equiv_replay(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64
         eq.join(k1[i], k2[i]);
     }
     if (row_exact) ejbhost::finish_join_merge(eq, row_exact, n_rows);
-    if (x) memcpy(x, eq.x.data(), (size_t)n_rows * 4);
-    if (y) memcpy(y, eq.y.data(), (size_t)n_rows * 4);
-    if (z) memcpy(z, eq.z.data(), (size_t)n_rows * 4);
+    if (x) memcpy(x, eq.x, (size_t)n_rows * 4);
+    if (y) memcpy(y, eq.y, (size_t)n_rows * 4);
+    if (z) memcpy(z, eq.z, (size_t)n_rows * 4);
     if (labels) {
         std::vector<int32_t> mn((size_t)std::max(n_rows, 1), 0x7fffffff);
         for (int32_t i = 0; i < n_rows; i++) mn[eq.y[i]] = std::min(mn[eq.y[i]], i);

@@ -43,19 +43,29 @@ __device__ __forceinline__ int cdr3_dist(const uint32_t* rl, const uint32_t* rh,
     return __popc(s) + __popc(s3) + 2 * (__popc(c) + __popc(c3));
 }
 
-template <int W1>
+// MODE bits (compile time):
+//   S1_RUNI   one warp vote per column when the thread's 8 rows and the column carry one class label
+//   S1_TAGS   reference-set tags staged next to the labels; after the pair loop of a half tile the hit list is compacted in
+//             place, dropping hits one of whose rows is known (from an earlier round's stage 2a) to fail the degradation test
+//             of join_one.rs:434-440 against the other row's reference set — the decision stage 2a would take from its memo
+constexpr int S1_RUNI = 1, S1_TAGS = 2;
+
+template <int W1, int MODE>
 __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2)) k_stage1(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, int n_tasks,
                                                        const uint32_t* __restrict__ cdr3w, const int32_t* __restrict__ labq,
                                                        const int32_t* __restrict__ blk_lab, uint2* __restrict__ cand,
                                                        unsigned long long cand_cap, Counters* __restrict__ ctr,
-                                                       unsigned long long* __restrict__ unit_cand) {
-    constexpr int NP = 2 * W1;           // plane-words per row
-    constexpr int SLOT = (NP + 1) * TILE; // words per staged tile (planes + labels)
+                                                       unsigned long long* __restrict__ unit_cand,
+                                                       const unsigned long long* __restrict__ tagq, const unsigned long long* __restrict__ deadq) {
+    constexpr bool RUNI = (MODE & S1_RUNI) != 0, TAGS = (MODE & S1_TAGS) != 0;
+    constexpr int NP = 2 * W1;            // plane-words per row
+    constexpr int TAG0 = (NP + 1) * TILE; // word offset of the staged reference-set tags (uint64 x TILE), then the dead tags
+    constexpr int SLOT = (NP + 1 + (TAGS ? 4 : 0)) * TILE;   // words per staged tile (planes + labels [+ tags + dead tags])
     __shared__ __align__(16) uint32_t s_row[SLOT];
     __shared__ __align__(16) uint32_t s_col[2][SLOT];
     __shared__ __align__(8) uint64_t s_bar[3];
     __shared__ uint16_t s_hits[TILE * TILE / 2];
-    __shared__ unsigned int s_nhits;
+    __shared__ unsigned int s_nhits, s_nkeep;
     __shared__ unsigned long long s_base;
     __shared__ int s_cbs[S1_STRIP];
     __shared__ int s_ncb;
@@ -102,10 +112,14 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
         const int r0 = blk * TILE;
         const int cnt = min(TILE, sb.npad - r0);  // npad is a multiple of 4
         const uint32_t bytes = (uint32_t)cnt * 4u;
-        mbar_expect_tx(bar, bytes * (NP + 1));
+        mbar_expect_tx(bar, bytes * (NP + 1 + (TAGS ? 4 : 0)));
 #pragma unroll
         for (int pw = 0; pw < NP; pw++) tma_load_1d(dst + pw * TILE, base + (int64_t)pw * sb.npad + r0, bytes, bar);
         tma_load_1d(dst + NP * TILE, labq + sb.q0 + r0, bytes, bar);   // q0 is a multiple of 4
+        if (TAGS) {
+            tma_load_1d(dst + TAG0, tagq + sb.q0 + r0, bytes * 2, bar);
+            tma_load_1d(dst + TAG0 + 2 * TILE, deadq + sb.q0 + r0, bytes * 2, bar);
+        }
     };
     if (tid == 0) {
         issue(s_row, rb, &s_bar[2]);
@@ -127,10 +141,17 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
         }
         rlab[i] = (int)s_row[NP * TILE + r];
     }
+    // common class label of this thread's 8 rows (-2: mixed): a column whose label equals it needs no per-row test
+    int runi = rlab[0];
+    if (RUNI) {
+#pragma unroll
+        for (int i = 1; i < 8; i++)
+            if (rlab[i] != runi) runi = -2;
+    }
     const int row_lo = t.row_lo;
     const int row_lim = min(sb.n - rb * TILE, t.row_hi);  // valid local rows are row_lo <= r < row_lim
     const int maxcd = sb.maxcd;
-    unsigned long long evaluated = 0;
+    unsigned long long evaluated = 0, killed = 0;   // thread 0 only
 
     for (int it = 0; it < ncb; it++) {
         const int cb = s_cbs[it];
@@ -146,13 +167,14 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
 #pragma unroll 2
                 for (int j = half * 4; j < half * 4 + 4; j++) {
                     const int c = j * 16 + tx;
+                    const int clab = (int)sc[NP * TILE + c];
+                    if (RUNI && __all_sync(0xffffffffu, clab == runi)) continue;   // 16 rows x 16 columns of one class: one vote instead of eight
                     uint32_t cl[W1], chh[W1];
 #pragma unroll
                     for (int w = 0; w < W1; w++) {
                         cl[w] = sc[w * TILE + c];
                         chh[w] = sc[(W1 + w) * TILE + c];
                     }
-                    const int clab = (int)sc[NP * TILE + c];
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         // class test first (join_core.rs:32): a warp whose 32 pairs are all already connected skips the
@@ -170,13 +192,14 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
             } else {
                 for (int j = half * 4; j < half * 4 + 4; j++) {
                     const int c = j * 16 + tx;
+                    const int clab = (int)sc[NP * TILE + c];
+                    if (RUNI && __all_sync(0xffffffffu, clab == runi)) continue;
                     uint32_t cl[W1], chh[W1];
 #pragma unroll
                     for (int w = 0; w < W1; w++) {
                         cl[w] = sc[w * TILE + c];
                         chh[w] = sc[(W1 + w) * TILE + c];
                     }
-                    const int clab = (int)sc[NP * TILE + c];
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int r = i * 16 + ty;
@@ -191,7 +214,34 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
                     }
                 }
             }
-            __syncthreads();  // all hits of this half recorded (and, after half 1, s_col[buf] drained)
+            __syncthreads();  // all hits of this half recorded (and, after half 1, s_col[buf] drained of plane reads)
+            if (TAGS) {
+                const unsigned int nh0 = s_nhits;
+                if (nh0) {   // block-uniform
+                    const unsigned long long* rt = reinterpret_cast<const unsigned long long*>(s_row + TAG0);
+                    const unsigned long long* ct = reinterpret_cast<const unsigned long long*>(sc + TAG0);
+                    if (tid == 0) s_nkeep = 0;
+                    __syncthreads();
+                    for (unsigned int b0 = 0; b0 < nh0; b0 += S1_THREADS) {
+                        const unsigned int h = b0 + tid;
+                        bool keep = false;
+                        uint16_t v = 0;
+                        if (h < nh0) {
+                            v = s_hits[h];
+                            const int r = v >> 7, c = v & 127;
+                            keep = !(rt[TILE + r] == ct[c] || ct[TILE + c] == rt[r]);
+                        }
+                        __syncthreads();   // entries [b0, b0 + 256) are in registers; kept ones land below b0 + 256
+                        if (keep) s_hits[atomicAdd(&s_nkeep, 1u)] = v;
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        killed += nh0 - s_nkeep;
+                        s_nhits = s_nkeep;
+                    }
+                    __syncthreads();
+                }
+            }
             const unsigned int nh = s_nhits;
             if (tid == 0) {
                 if (half == 1) {
@@ -231,7 +281,10 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
             }
         }
     }
-    if (tid == 0) atomicAdd(&ctr->pairs_eval, evaluated);
+    if (tid == 0) {
+        atomicAdd(&ctr->pairs_eval, evaluated);
+        if (killed) atomicAdd(&ctr->n_s1_kill, killed);
+    }
 }
 
 

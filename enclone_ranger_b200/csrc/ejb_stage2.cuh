@@ -23,6 +23,8 @@ struct S2Ctx {
     const int32_t* qcut;         // per sub-bucket: candidates whose first row is at a packed position >= qcut are not part of this round
     unsigned int* sub_pass;      // per sub-bucket: pass edges found in this round
     int32_t* memo;               // per packed row, 8 ints: {state, vs_h, vs_l, js_h, js_l, T, -, -} — see memo_lookup()
+    const unsigned long long* tagq;   // reference-set tag per packed row (nullptr: tags off), see ejb_types.cuh
+    unsigned long long* deadq;        // per packed row: tag of a foreign reference set the row is dead against (read by stage 1)
     const uint32_t* cdr3w;
     const uint4* rowstore;
     const uint64_t* bc_sorted;   // (exact << 32 | barcode), sorted: each exact's barcodes ascending
@@ -164,12 +166,16 @@ __device__ __forceinline__ bool memo_lookup(const int32_t* memo, uint32_t q, int
     T = m[5];
     return true;
 }
-__device__ __forceinline__ void memo_store(int32_t* memo, uint32_t q, int vsh, int vsl, int jsh, int jsl, int T) {
+// `dead` = the totals fail the degradation test for row q against that reference set: the winner of the slot also publishes
+// the fact to stage 1 (deadq[q] = tag of the foreign reference set; written once, consistent with the memo).
+__device__ __forceinline__ void memo_store(int32_t* memo, uint32_t q, int vsh, int vsl, int jsh, int jsl, int T, bool dead,
+                                           unsigned long long* deadq, const unsigned long long* tagq, uint32_t q_other) {
     int32_t* m = memo + (size_t)q * 8;
     if (atomicCAS(m, 0, 1) != 0) return;   // somebody else owns the slot
     m[1] = vsh; m[2] = vsl; m[3] = jsh; m[4] = jsl; m[5] = T;
     __threadfence();
     *reinterpret_cast<volatile int32_t*>(m) = 2;
+    if (dead && deadq) deadq[q] = tagq[q_other];
 }
 
 // Per-candidate values the owner lane derives once and hands to the group working on it (by shuffle).
@@ -349,6 +355,7 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
     const int wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     SurvWriter wr;
     wr.init();
+    unsigned int n_two = 0, n_memo = 0, n_degr = 0;   // diagnostics, per lane; reduced once at the end
     for (;;) {
       __syncthreads();
       if (threadIdx.x == 0) s_chunk = atomicAdd(&X.ctr->s2_work, S2A_CHUNK);
@@ -423,8 +430,10 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
         Survivor sv;
         if (valid) {
             const uint32_t slot = cand_slot ? cand_slot[ci] : (uint32_t)ci;
+            if (fast && !nrefs1 && !X.tuple_mode) n_two++;
             if (fast && memo_dead) {
                 // rejected by the degradation test on memoised totals
+                n_memo++;
             } else if (fast) {
                 const uint32_t* r = s_res[wib][lane];
                 const int cd1 = (int)(r[0] & 0xffff), cd2 = (int)(r[0] >> 16);
@@ -447,13 +456,14 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
                     const int A0 = (int)(r[4] & 0xffff), B0 = (int)(r[4] >> 16), O0 = (int)(r[5] & 0xffff), T01 = (int)(r[5] >> 16);
                     const int A1 = (int)(r[6] & 0xffff), B1 = (int)(r[6] >> 16), O1 = (int)(r[7] & 0xffff), T10 = (int)(r[7] >> 16);
                     // join_one.rs:434-440: total[0] = (tot1, T01), total[1] = (T10, tot2)
+                    const bool dead1 = abs(tot1 - T10) > X.P.max_degradation;   // q1 fails against q2's reference set, whoever carries it
+                    const bool dead2 = abs(T01 - tot2) > X.P.max_degradation;
                     if (!X.tuple_mode) {
-                        memo_store(X.memo, q1, (int)a20.y, (int)a20.z, (int)a20.w, a2[AX_JSL], T10);
-                        memo_store(X.memo, q2, (int)a10.y, (int)a10.z, (int)a10.w, a1[AX_JSL], T01);
+                        memo_store(X.memo, q1, (int)a20.y, (int)a20.z, (int)a20.w, a2[AX_JSL], T10, dead1, X.deadq, X.tagq, q2);
+                        memo_store(X.memo, q2, (int)a10.y, (int)a10.z, (int)a10.w, a1[AX_JSL], T01, dead2, X.deadq, X.tagq, q1);
                     }
-                    bool ok = true;
-                    if (abs(tot1 - T10) > X.P.max_degradation) ok = false;
-                    if (abs(T01 - tot2) > X.P.max_degradation) ok = false;
+                    const bool ok = !dead1 && !dead2;
+                    if (!ok && !X.tuple_mode) n_degr++;
                     if (ok || X.tuple_mode)
                         emit = s2_integer_tests(X, q1, q2, slot, sb, cd1, cd2, diffs, 2, A0 - B0, O0 + 2 * B0, A1 - B1, O1 + 2 * B1, rg, ok, X.tuple_mode != 0, sv);
                 }
@@ -472,6 +482,17 @@ __global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __rest
       }
     }
     wr.finish(X, lane);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_two += __shfl_xor_sync(0xffffffffu, n_two, o);
+        n_memo += __shfl_xor_sync(0xffffffffu, n_memo, o);
+        n_degr += __shfl_xor_sync(0xffffffffu, n_degr, o);
+    }
+    if (lane == 0 && n_two) {
+        atomicAdd(&X.ctr->n_two_ref, (unsigned long long)n_two);
+        if (n_memo) atomicAdd(&X.ctr->n_memo_dead, (unsigned long long)n_memo);
+        if (n_degr) atomicAdd(&X.ctr->n_degr_dead, (unsigned long long)n_degr);
+    }
 }
 
 // Slow path: one warp per candidate, literal byte-level restatement of join_one.rs:216-440

@@ -141,7 +141,22 @@ struct Counters {       // device-side counters, one instance per context
     unsigned long long n_cand, n_slow, n_surv, n_pass, n_newkeys, pairs_eval, n_forest, n_alive;
     unsigned long long n_two_cell, n_errflag_range, n_errflag_panic, overflow, n_slow_total, n_surv_total, n_pass_total;
     unsigned long long p1_unique, s2_work;
+    unsigned long long n_s1_kill;     // stage-1 hits dropped because one row is known dead against the other's reference set
+    unsigned long long n_two_ref;     // stage-2a candidates with two reference sets (filter mode)
+    unsigned long long n_memo_dead;   // ... of which rejected on memoised totals (phase 0)
+    unsigned long long n_degr_dead;   // ... of which rejected by the degradation test on freshly computed totals
 };
+
+// Reference-set tags (stage-1 kill of pairs that are known to fail join_one.rs:434-440).
+//   tagq[q]  = canonical (vs_h, vs_l, js_h, js_l) ids of row q, 16 bits each; TAG_SLOW for rows the plane path cannot score
+//   deadq[q] = tag of a FOREIGN reference set R with |tot_q - T(q, R)| > max_degradation (written by stage 2a), else DEAD_NONE
+// Requires every canonical seg id < 65535 (otherwise the tags are switched off).
+constexpr unsigned long long DEAD_NONE = 0xffffffffffffffffull;
+constexpr unsigned long long TAG_SLOW = 0xfffffffffffffffeull;
+__host__ __device__ __forceinline__ unsigned long long make_ref_tag(int vsh, int vsl, int jsh, int jsl) {
+    return (unsigned long long)(uint32_t)vsh | ((unsigned long long)(uint32_t)vsl << 16) | ((unsigned long long)(uint32_t)jsh << 32) |
+           ((unsigned long long)(uint32_t)jsl << 48);
+}
 
 // ------------------------------------------------------------------------------------------------
 // small helpers

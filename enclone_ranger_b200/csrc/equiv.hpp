@@ -14,21 +14,33 @@
 namespace ejbhost {
 
 struct EquivRel {
-    std::vector<int32_t> x, y, z;
-    explicit EquivRel(int32_t n) : x((size_t)n), y((size_t)n), z((size_t)n, 1) {
-        for (int32_t i = 0; i < n; i++) x[(size_t)i] = y[(size_t)i] = i;
+    // the state lives in caller-provided arrays (the library's pinned result arena): no allocation, no copy-out
+    int32_t *x, *y, *z;
+    std::vector<int32_t> own;   // backing store when constructed without external arrays
+    EquivRel(int32_t n, int32_t* xs, int32_t* ys, int32_t* zs) : x(xs), y(ys), z(zs) { init(n); }
+    explicit EquivRel(int32_t n) : own(3 * (size_t)n) {
+        x = own.data();
+        y = x + n;
+        z = y + n;
+        init(n);
     }
-    int32_t class_id(int32_t a) const { return y[(size_t)a]; }
-    int32_t orbit_size(int32_t a) const { return z[(size_t)y[(size_t)a]]; }
+    void init(int32_t n) {
+        for (int32_t i = 0; i < n; i++) {
+            x[i] = y[i] = i;
+            z[i] = 1;
+        }
+    }
+    int32_t class_id(int32_t a) const { return y[a]; }
+    int32_t orbit_size(int32_t a) const { return z[y[a]]; }
     // relabels the smaller orbit; on a tie b's orbit takes a's class id (equiv/src/lib.rs:64-93)
     void join(int32_t a, int32_t b) {
-        if (y[(size_t)a] == y[(size_t)b]) return;
+        if (y[a] == y[b]) return;
         if (orbit_size(a) < orbit_size(b)) std::swap(a, b);
         const int32_t total = orbit_size(a) + orbit_size(b);
-        std::swap(x[(size_t)a], x[(size_t)b]);
-        const int32_t cls = y[(size_t)a];
-        for (int32_t n = x[(size_t)a]; y[(size_t)n] != cls; n = x[(size_t)n]) y[(size_t)n] = cls;
-        z[(size_t)y[(size_t)b]] = total;
+        std::swap(x[a], x[b]);
+        const int32_t cls = y[a];
+        for (int32_t n = x[a]; y[n] != cls; n = x[n]) y[n] = cls;
+        z[y[b]] = total;
     }
 };
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define EJB_ABI_VERSION 2
+#define EJB_ABI_VERSION 3
 #define EJB_NONE (-1)
 
 typedef enum ejb_status {
@@ -200,6 +200,12 @@ typedef struct ejb_stats {
     int64_t overflow_retries;   /* rounds that overflowed the work buffers and were split + re-run   */
     double ms_device_total;     /* pack .. finalize, CUDA events                                  */
     double ms_total;            /* wall clock of the whole call                                   */
+    /* two-reference candidates (rows whose V/J reference sets differ, join_one.rs:331-341) and how they ended */
+    int64_t stage1_ref_kills;   /* CDR3-close pairs dropped in stage 1: one row is already known to fail the
+                                   degradation test (join_one.rs:434-440) against the other's reference set */
+    int64_t stage2_two_ref;     /* stage-2a candidates with two reference sets                    */
+    int64_t stage2_memo_dead;   /* ... rejected on memoised totals                                */
+    int64_t stage2_degr_dead;   /* ... rejected by the degradation test on computed totals        */
 } ejb_stats;
 
 /*

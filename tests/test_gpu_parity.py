@@ -225,3 +225,39 @@ def test_randomized_differential(gpu_ctx, block):
         assert_same_result(gpu_ctx.join(p, inp.to_packed()), want, f"fuzz seed {seed} packed")
         n_edges += len(want["edge_k1"])
     assert n_edges > 0
+
+
+def _join_without_tags(ctx, p, inp):
+    import os
+    os.environ["EJB_NO_TAGS"] = "1"
+    try:
+        return ctx.join(p, inp)
+    finally:
+        del os.environ["EJB_NO_TAGS"]
+
+
+def test_reference_set_tags_do_not_change_the_result(gpu_ctx):
+    """Stage 1 drops CDR3-close pairs one of whose rows is already known to fail the degradation test
+    (join_one.rs:434-440) against the other's reference set.  Pure work saving: same edges, tuples and EquivRel
+    as the oracle and as a run with the tags switched off."""
+    rep = E.generate(1, n_cells=60000, seed=5)
+    p = E.default_params(True)
+    want = pyoracle.run(p, rep.c_ptr, threads=0)
+    got = gpu_ctx.join(p, rep)
+    assert_same_result(got, want, "tags on")
+    off = _join_without_tags(gpu_ctx, p, rep)
+    assert_same_result(off, want, "tags off")
+    assert off.stats["stage1_ref_kills"] == 0
+
+
+def test_reference_set_tags_at_scale(gpu_ctx):
+    rep = E.generate(1, n_cells=300000, seed=4)
+    p = E.default_params(True)
+    inp = rep.to_join_input().to_packed()
+    on = gpu_ctx.join(p, inp)
+    off = _join_without_tags(gpu_ctx, p, inp)
+    for f in ("edge_k1", "edge_k2", "edge_cd", "edge_shares", "edge_indeps", "edge_score", "labels", "eq_x", "eq_y", "eq_z"):
+        assert np.array_equal(getattr(on, f), getattr(off, f)), f
+    assert off.stats["stage1_ref_kills"] == 0
+    assert on.stats["stage1_ref_kills"] > 0, "a 300k-cell heavy-tailed repertoire with 1 % indel rows must exercise the kill"
+    assert on.stats["stage1_candidates"] < off.stats["stage1_candidates"]
