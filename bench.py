@@ -6,9 +6,9 @@
 One "step" = one pass of the hot path (bucketer -> pair kernels -> forest -> union-find) over the whole
 synthetic repertoire.  N=1 workload: BASELINE.json configs[1] (1M-cell heavy-tailed human BCR repertoire).
 N>1 (weak scaling): the same clone-size law at N x 1M cells (N=8 ~ configs[4]); rank 0 generates the
-repertoire, whole lens-buckets are assigned to ranks by pair count (LPT) and each rank receives, uploads and
-joins only its buckets — no collective on the data path; the per-rank edge lists are gathered GPU-to-GPU to
-rank 0 over NCCL and merged there.
+repertoire, sub-buckets are assigned to ranks by a cost model (LPT), the heaviest cut into row ranges, and each
+rank receives, uploads and joins only its share — no collective on the data path; the per-rank edge lists are
+gathered GPU-to-GPU to rank 0 over NCCL and merged there (forest of the partial forests of split sub-buckets).
 
   value   pairs/s with inputs resident in HBM (ejb_run), device time from CUDA events on the launching stream
   e2e     pairs/s through ejb_join with HOST (pinned) buffers: H2D + run + D2H + EquivRel replay in the timed region
@@ -221,11 +221,14 @@ def main():
             rep.close()
             full_rows, row_exact_full = full.n_rows, full.a["row_exact"].copy()
             parts = []
-            for rows in multi.partition_buckets(full, world):
-                sub, _ = full.subset_rows(rows)
-                parts.append((sub, rows))
+            wparts, split_rows = multi.partition_work(full, world)
+            ncells_row = multi.ncells_per_row(full)
+            for wp in wparts:
+                sub, _ = full.subset_rows(wp.rows)
+                parts.append((sub, wp.rows, wp.roles))
+            n_split_rows = int(split_rows.sum())
             del full
-        inp, my_rows = multi.scatter_parts(parts, dev)
+        inp, my_rows, my_roles = multi.scatter_parts(parts, dev)
         del parts
         fr = torch.tensor([full_rows], dtype=torch.int64, device=dev)
         dist.broadcast(fr, src=0)
@@ -238,19 +241,31 @@ def main():
         inp = inp.to_packed()
     t_gen = time.time() - t_gen
     params = E.default_params(True)
-    # pin the caller's host buffers (the e2e contract copies from pinned host memory)
-    cudart = torch.cuda.cudart()
-    pinned = []
+    # the caller's host buffers live in page-locked memory (the e2e contract copies from pinned host memory): every array is
+    # moved into a cudaHostAlloc'ed buffer once, outside the timed regions (cudaHostRegister on malloc'ed numpy memory reaches
+    # only ~30 GB/s on this platform, cudaHostAlloc ~55 GB/s)
+    pinned, views = [], {}
     for name, arr in inp.a.items():
-        if arr.nbytes >= 1 << 16:
-            if int(cudart.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)) == 0:
-                pinned.append(arr)
+        if arr.nbytes >= 1 << 12:
+            t = torch.empty(arr.nbytes, dtype=torch.uint8).pin_memory()
+            view = t.numpy().view(arr.dtype).reshape(arr.shape)
+            view[...] = arr
+            views[name] = view
+            pinned.append(t)
+        else:
+            views[name] = arr
+    inp = E.JoinInput(**views)     # same dtypes, contiguous: the struct points straight into the pinned buffers
+    assert all(inp.a[n].ctypes.data == views[n].ctypes.data for n in views if views[n].size)
     ctx = E.JoinContext(device=local_rank)
     peaks = ctx.measure_peaks() if rank == 0 else None
     rows_dev = torch.from_numpy(my_rows).to(dev) if my_rows is not None else None
+    if world > 1:
+        ctx.set_row_roles(my_roles)   # row ranges of split sub-buckets (None: this rank holds whole sub-buckets only)
+        split_dev = torch.from_numpy(split_rows).to(dev) if rank == 0 else None
 
-    def gather_keys(key):
-        """per-rank sorted 64-bit (k1<<32|k2) keys (global row ids) -> rank 0 over NCCL, merged by a device sort"""
+    def gather_keys(key, aux):
+        """per-rank 64-bit (k1<<32|k2) keys (global row ids) + (cd<<32|min_shares) -> rank 0 over NCCL; there: one device sort,
+        then the edges of split sub-buckets (partial forests) are reduced to their forest and two-cell filtered"""
         if world == 1:
             return key
         n = torch.tensor([key.numel()], dtype=torch.int64, device=dev)
@@ -258,13 +273,29 @@ def main():
         dist.all_gather(sizes, n)
         sizes = [int(x.item()) for x in sizes]
         mx = max(max(sizes), 1)
-        pad = torch.full((mx,), -1, dtype=torch.int64, device=dev)
-        pad[: key.numel()] = key
-        bufs = [torch.empty(mx, dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
+        pad = torch.full((2, mx), -1, dtype=torch.int64, device=dev)
+        pad[0, : key.numel()] = key
+        pad[1, : key.numel()] = aux
+        bufs = [torch.empty((2, mx), dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
         dist.gather(pad, bufs, dst=0)
         if rank != 0:
             return None
-        return torch.sort(torch.cat([bufs[r][: sizes[r]] for r in range(world)])).values
+        k, o = torch.sort(torch.cat([bufs[r][0, : sizes[r]] for r in range(world)]))
+        if n_split_rows:
+            a = torch.cat([bufs[r][1, : sizes[r]] for r in range(world)])[o]
+            idx = torch.nonzero(split_dev[k >> 32]).squeeze(1)
+            if idx.numel():
+                ks, au = k[idx].cpu().numpy(), a[idx].cpu().numpy()
+                keep = multi.merge_split_edges(full_rows, ks >> 32, ks & 0xffffffff, au >> 32, au & 0xffffffff, split_rows, ncells_row)
+                mask = torch.ones(k.numel(), dtype=torch.bool, device=dev)
+                mask[idx[torch.from_numpy(~keep).to(dev)]] = False
+                k = k[mask]
+        return k
+
+    def edge_aux(cd, nrefs, shares):
+        """(cd << 32) | min(shares): what the two-cell filter needs (join.rs:120-178)"""
+        sh = shares.reshape(-1, 2).long()
+        return (cd.long() << 32) | torch.where(nrefs == 2, torch.minimum(sh[:, 0], sh[:, 1]), sh[:, 0])
 
     # ---------------- device-resident arm: value ----------------
     ctx.upload(params, inp)
@@ -277,7 +308,7 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             k1, k2 = ctx.device_edges()     # device pointers, no host round trip
-            gather_keys((rows_dev[k1.long()] << 32) | rows_dev[k2.long()])
+            gather_keys((rows_dev[k1.long()] << 32) | rows_dev[k2.long()], edge_aux(*ctx.device_tuples()))
             e1.record()
             gather_ms.append((e0, e1))
         return st
@@ -321,7 +352,9 @@ def main():
         res = ctx.join(params, inp, copy=False)   # zero-copy views into the library's pinned result arena
         if world > 1:
             key = torch.from_numpy(my_rows[res.edge_k1].astype(np.int64) << 32 | my_rows[res.edge_k2].astype(np.int64)).to(dev)
-            merged = gather_keys(key)
+            aux = edge_aux(torch.from_numpy(np.ascontiguousarray(res.edge_cd)), torch.from_numpy(np.ascontiguousarray(res.edge_nrefs)),
+                           torch.from_numpy(np.ascontiguousarray(res.edge_shares))).to(dev)
+            merged = gather_keys(key, aux)
             if rank == 0:   # raw_joins of the whole repertoire + the EquivRel finish_join returns
                 k = merged.cpu().numpy()
                 E.equiv_replay(full_rows, (k >> 32).astype(np.int32), (k & 0xffffffff).astype(np.int32), row_exact_full)
@@ -369,9 +402,9 @@ def main():
         line = {
             "metric": METRIC, "value": pairs / (t_step / 1e3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 popc + f64 score", "data": "synthetic",
-            "config": {"workload": (WORKLOAD if world == 1 else f"configs[1] clone-size law at {world} x 1M cells, lens-buckets partitioned over {world} ranks") if args.cells is None else f"DEBUG {args.cells}-cell-per-GPU variant of configs[1]", "cells": int(base_cells * world), "rows": int(full_rows), "rows_rank0": int(inp.n_rows),
+            "config": {"workload": (WORKLOAD if world == 1 else f"configs[1] clone-size law at {world} x 1M cells, sub-buckets partitioned over {world} ranks (the heaviest cut into row ranges)") if args.cells is None else f"DEBUG {args.cells}-cell-per-GPU variant of configs[1]", "cells": int(base_cells * world), "rows": int(full_rows), "rows_rank0": int(inp.n_rows),
                        "pairs_scored": int(pairs), "pairs_lens_buckets": int(stats["pairs_lens"]), "sub_buckets": int(stats["n_subbuckets"]),
-                       "parallelism": f"bucket-sharded x{world}, weak scaling (1M cells per GPU)" if world > 1 else "single GPU",
+                       "parallelism": f"bucket-sharded x{world}, weak scaling (1M cells per GPU), {n_split_rows} rows in sub-buckets split by row ranges" if world > 1 else "single GPU",
                        "l2": f"inputs ({stats['h2d_bytes'] / 1e6:.0f} MB raw + packed row store) exceed the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the library's launching stream (ejb_stats.ms_device_total)" if world == 1 else "device clock: CUDA events of the join on the library's stream + CUDA events of the NCCL edge gather and merge on torch's stream, max over ranks",
                        "wall_ms_per_step": wall_ms, "generate_s": t_gen, "per_rank": per_rank,
@@ -400,8 +433,6 @@ def main():
             line["cpu_baseline"] = {"value": r["pairs_scored"] / r["seconds_join"], "unit": "pairs/s", "cores": int(r["threads"]), "kind": "port",
                                     "sample": desc, "seconds": r["seconds_join"], "join_one_calls": int(r["join_one_calls"]), "pairs": int(r["pairs_scored"])}
         print(json.dumps(line))
-    for arr in pinned:
-        cudart.cudaHostUnregister(arr.ctypes.data)
     ctx.close()
     if world > 1:
         dist.barrier()

@@ -279,5 +279,11 @@ def load_join():
         L.ejb_p1_batch.restype = C.c_int
         L.ejb_measure_peaks.argtypes = [C.c_void_p, _f64p, _f64p, _f64p]
         L.ejb_measure_peaks.restype = C.c_int
+        L.ejb_set_row_roles.argtypes = [C.c_void_p, _u8p, C.c_int64]
+        L.ejb_set_row_roles.restype = C.c_int
+        L.ejb_forest_merge.argtypes = [C.c_int32, _i32p, _i32p, C.c_int64, _u8p]
+        L.ejb_forest_merge.restype = C.c_int
+        L.ejb_device_tuples.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.ejb_device_tuples.restype = C.c_int
         _cache["join"] = L
     return _cache["join"]

@@ -148,13 +148,16 @@ __global__ void k_q_of_row(const int32_t* __restrict__ rowq, int64_t n_pos, int3
 // join.rs:120-178: an orbit of exactly two rows holding two cells in total loses its edge when
 // cd > min(shares) / 2 (unless EASY).  keep[i] = 0 for deleted edges; parent[] is un-merged.
 __global__ void k_two_cell(DevIn in, DevParams P, const unsigned long long* __restrict__ forest, int64_t n, const int32_t* __restrict__ deg,
-                           const EdgeTuple* __restrict__ tuples, int32_t* __restrict__ parent, uint8_t* __restrict__ keep, Counters* ctr) {
+                           const EdgeTuple* __restrict__ tuples, int32_t* __restrict__ parent, uint8_t* __restrict__ keep, Counters* ctr,
+                           const uint8_t* __restrict__ roles) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long e = forest[i];
     const int a = (int)(e >> 28), b = (int)(e & 0xfffffffull);
     int kp = 1;
-    if (deg[a] == 1 && deg[b] == 1) {
+    // rows of a sub-bucket that was split over several contexts: this forest is partial, the caller filters after merging
+    const bool partial = roles && (roles[a] & ROLE_SPLIT);
+    if (!partial && deg[a] == 1 && deg[b] == 1) {
         const int ea = in.row_exact[a], eb = in.row_exact[b];
         const long long ncells = (in.ex_cell_off[ea + 1] - in.ex_cell_off[ea]) + (in.ex_cell_off[eb + 1] - in.ex_cell_off[eb]);
         if (ncells == 2) {

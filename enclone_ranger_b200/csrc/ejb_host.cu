@@ -105,6 +105,9 @@ struct ejb_ctx {
     int64_t h2d_bytes = 0;
     double ms_h2d = 0;
     int64_t n_canon_segs = 0;   // distinct seg contents (canonical ids are 0 .. n_canon_segs-1)
+    DevBuf d_roles, d_subroles; // ejb_set_row_roles (per canonical row), per-sub-bucket summary
+    std::vector<uint8_t> roles; // host copy; in force for every run until cleared
+    bool have_roles = false;    // roles are in force for the current run
 
     // derived (per run)
     DevBuf d_head, d_scan, d_keys, d_keys2, d_vals, d_vals2, d_cubtmp, d_subhead, d_subincl, d_subinfo;
@@ -797,6 +800,13 @@ extern "C" int ejb_run(ejb_ctx* c) {
         int rc = p1_cache_clear(c);
         if (rc) return rc;
     }
+    c->have_roles = false;
+    if (!c->roles.empty()) {
+        if ((int64_t)c->roles.size() != N) return fail(c, EJB_ERR_INVALID, "row roles were set for %zu rows, the input has %lld", c->roles.size(), (long long)N);
+        CK(c->d_roles.ensure((size_t)N));
+        CK(cudaMemcpyAsync(c->d_roles.p, c->roles.data(), (size_t)N, cudaMemcpyHostToDevice, st));
+        c->have_roles = true;
+    }
     c->subs.clear();
     c->n_active = c->n_pos = c->n_blocks = c->n_final = 0;
     std::vector<RoundTimes> times;
@@ -847,8 +857,21 @@ extern "C" int ejb_run(ejb_ctx* c) {
         c->stats.kernel_launches += 2;
         std::vector<SubInfo> si((size_t)n_subs);
         CK(cudaMemcpyAsync(si.data(), c->d_subinfo.p, (size_t)n_subs * sizeof(SubInfo), cudaMemcpyDeviceToHost, st));
+        std::vector<SubRole> sroles;
+        if (c->have_roles) {
+            sroles.resize((size_t)n_subs);
+            CK(c->d_subroles.ensure((size_t)n_subs * sizeof(SubRole)));
+            CK(cudaMemsetAsync(c->d_subroles.p, 0, (size_t)n_subs * sizeof(SubRole), st));
+            k_subroles<<<nblk(NA, 256), 256, 0, st>>>(c->d_roles.as<uint8_t>(), row_of, c->d_subhead.as<int32_t>(), c->d_subincl.as<int32_t>(), NA,
+                                                     c->d_subroles.as<SubRole>(), c->d_err.as<unsigned int>());
+            c->stats.kernel_launches++;
+            CK(cudaMemcpyAsync(sroles.data(), c->d_subroles.p, (size_t)n_subs * sizeof(SubRole), cudaMemcpyDeviceToHost, st));
+        }
+        unsigned int role_err = 0;
+        CK(cudaMemcpyAsync(&role_err, c->d_err.p, 4, cudaMemcpyDeviceToHost, st));
         mark("subinfo");
         CK(cudaStreamSynchronize(st));
+        if (role_err & 16384u) return fail(c, EJB_ERR_INVALID, "row roles: column-only rows must form a suffix of their sub-bucket");
         c->stats.d2h_bytes += (int64_t)n_subs * sizeof(SubInfo);
 
         // ---- sub-bucket table, offsets, thresholds ----
@@ -877,6 +900,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
             sb.gap = si[s].gap & 3;
             sb.rec_u4 = rec_planes(0, sb.gap & 1) * sb.W4h + rec_planes(1, sb.gap & 2) * sb.W4l;
             sb.pad = 0;
+            sb.n_act = c->have_roles ? sroles[(size_t)s].n_act : sb.n;
+            sb.raw = c->have_roles ? sroles[(size_t)s].raw : 0;
             sb.q0 = q;
             sb.s1_off = s1;
             sb.rs_off = rs;
@@ -900,7 +925,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
             s1 += (int64_t)2 * sb.W1 * sb.npad;
             rs += (int64_t)sb.n * sb.rec_u4;
             blk += (sb.n + TILE - 1) / TILE;
-            c->stats.pairs_scored += (int64_t)sb.n * (sb.n - 1) / 2;
+            // pairs whose first row is one of the n_act leading rows (all n(n-1)/2 without row roles)
+            c->stats.pairs_scored += (int64_t)sb.n_act * (sb.n - 1) - (int64_t)sb.n_act * (sb.n_act - 1) / 2;
             const uint64_t b = si[s].key >> 32;
             if (b != cur_bucket) {
                 c->stats.pairs_lens += bucket_rows * (bucket_rows - 1) / 2;
@@ -1039,12 +1065,12 @@ extern "C" int ejb_run(ejb_ctx* c) {
         std::vector<double> prate(subs.size(), 1.0);         // pass edges per candidate of the last committed unit
         std::vector<std::vector<Known>> known(subs.size());  // counted, not yet committed row ranges (ascending)
         for (int s = 0; s < (int)subs.size(); s++)
-            if (subs[s].n >= 2 && subs[s].owner == c->shard_rank) live.push_back(s);
+            if (subs[s].n >= 2 && subs[s].n_act >= 1 && subs[s].owner == c->shard_rank) live.push_back(s);
         const double cap_round = 0.5 * (double)c->cand_cap;                      // expected candidates allowed per round
         const double target_pass = std::max(4096.0, (double)c->cand_cap / 64.0);   // pass edges one unit should not exceed by much
         int stalls = 0;
         // developer knobs for the unit schedule (first unit, growth factor of the rows done so far)
-        long long first_unit = 8, growth = 4;
+        long long first_unit = 1, growth = 8;   // measured on configs[1] (1M cells): 8/4 -> 10.5 ms, 2/8 -> 9.4 ms, 1/8 -> 9.2 ms
         if (const char* e = getenv("EJB_FIRST_UNIT")) first_unit = std::max(1ll, atoll(e));
         if (const char* e = getenv("EJB_GROWTH")) growth = std::max(1ll, atoll(e));
         while (!live.empty()) {
@@ -1092,7 +1118,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
                     }
                 } else {
                     const long long want = (r0 == 0) ? first_unit : std::max<long long>(first_unit, growth * r0);   // optimistic growth: rows done so far x growth
-                    r1 = (int)std::min<long long>((long long)r0 + want, sb.n);
+                    r1 = (int)std::min<long long>((long long)r0 + want, sb.n_act);
                     ex = (rho[s] > 0.0 ? rho[s] : std::min<double>(64.0, (double)sb.n)) * (double)(r1 - r0);
                     // capacity: never plan more expected candidates than a round may hold
                     if (ex > 0.5 * cap_round) {
@@ -1100,7 +1126,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
                         ex = 0.5 * cap_round;
                     }
                 }
-                r1 = std::min(r1, sb.n);
+                r1 = std::min(r1, sb.n_act);
                 while (r1 - r0 > 1 && unit_pairs(r0, r1) > budget / 2) r1 = r0 + (r1 - r0) / 2;
                 const unsigned long long up = unit_pairs(r0, r1);
                 if (!units.empty() && (pairs + up > budget || expect + ex > cap_round)) {
@@ -1144,7 +1170,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
                     next_row[u.sub] = u.r1;
                     known[u.sub].clear();            // stale after a commit
                     if (u.cand > 0.0) prate[u.sub] = std::min(1.0, u.pass / u.cand);
-                    if (u.r1 < subs[u.sub].n - 1) still.push_back(u.sub);   // the last row has no pair to its right
+                    if (u.r1 < std::min(subs[u.sub].n_act, subs[u.sub].n - 1)) still.push_back(u.sub);   // the last row has no pair to its right
                 }
                 // candidate density of the last committed row range predicts the rows that follow (capacity planning)
                 for (size_t t = 0; t < c->task_meta.size(); t++) {
@@ -1198,7 +1224,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
             c->p1_count += c->h_ctr->n_newkeys;
         }
         k_two_cell<<<nblk(NF, 256), 256, 0, st>>>(din, make_dev_params(c->params), c->d_forest.as<unsigned long long>(), NF, c->d_deg.as<int32_t>(),
-                                                 c->d_tuples.as<EdgeTuple>(), c->d_parent.as<int32_t>(), c->d_keep.as<uint8_t>(), c->d_ctr.as<Counters>());
+                                                 c->d_tuples.as<EdgeTuple>(), c->d_parent.as<int32_t>(), c->d_keep.as<uint8_t>(), c->d_ctr.as<Counters>(),
+                                                 c->have_roles ? c->d_roles.as<uint8_t>() : nullptr);
         c->stats.kernel_launches++;
         CK(c->d_fkeys.ensure((size_t)NF * 8)); CK(c->d_fkeys2.ensure((size_t)NF * 8));
         CK(c->d_fidx.ensure((size_t)NF * 4)); CK(c->d_fidx2.ensure((size_t)NF * 4));
@@ -1384,6 +1411,49 @@ int ejb_device_edges(ejb_ctx* c, int64_t* n_edges, const int32_t** d_k1, const i
     if (d_k1) *d_k1 = c->n_final > 0 ? c->d_o_k1.as<const int32_t>() : nullptr;
     if (d_k2) *d_k2 = c->n_final > 0 ? c->d_o_k2.as<const int32_t>() : nullptr;
     if (d_labels) *d_labels = c->d_labels.as<const int32_t>();
+    return EJB_OK;
+}
+
+int ejb_device_tuples(ejb_ctx* c, const int32_t** d_cd, const int32_t** d_nrefs, const int32_t** d_shares) {
+    if (!c) return EJB_ERR_INVALID;
+    if (!c->have_run) return fail(c, EJB_ERR_INVALID, "ejb_device_tuples without ejb_run");
+    const bool any = c->n_final > 0;
+    if (d_cd) *d_cd = any ? c->d_o_cd.as<const int32_t>() : nullptr;
+    if (d_nrefs) *d_nrefs = any ? c->d_o_nrefs.as<const int32_t>() : nullptr;
+    if (d_shares) *d_shares = any ? c->d_o_sh.as<const int32_t>() : nullptr;
+    return EJB_OK;
+}
+
+int ejb_set_row_roles(ejb_ctx* c, const uint8_t* roles, int64_t n_rows) {
+    if (!c || n_rows < 0) return EJB_ERR_INVALID;
+    c->roles.clear();
+    if (!roles || n_rows == 0) return EJB_OK;
+    for (int64_t i = 0; i < n_rows; i++)
+        if (roles[i] > 3) return fail(c, EJB_ERR_INVALID, "row role %lld out of range", (long long)i);
+    c->roles.assign(roles, roles + n_rows);
+    return EJB_OK;
+}
+
+// Kruskal over an edge list sorted by (k1, k2): keep[i] = 1 iff edge i joins two components of the edges before it.
+// Merges the partial forests of a sub-bucket that was split by row ranges: MSF(G) = MSF(MSF(G1) u MSF(G2) u ...).
+int ejb_forest_merge(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64_t n_edges, uint8_t* keep) {
+    if (n_rows < 0 || n_edges < 0 || (n_edges > 0 && (!k1 || !k2 || !keep))) return EJB_ERR_INVALID;
+    std::vector<int32_t> parent((size_t)n_rows);
+    for (int32_t i = 0; i < n_rows; i++) parent[(size_t)i] = i;
+    auto find = [&](int32_t x) {
+        while (parent[(size_t)x] != x) {
+            parent[(size_t)x] = parent[(size_t)parent[(size_t)x]];
+            x = parent[(size_t)x];
+        }
+        return x;
+    };
+    for (int64_t i = 0; i < n_edges; i++) {
+        if (k1[i] < 0 || k1[i] >= n_rows || k2[i] < 0 || k2[i] >= n_rows) return EJB_ERR_INVALID;
+        if (i > 0 && (k1[i] < k1[i - 1] || (k1[i] == k1[i - 1] && k2[i] < k2[i - 1]))) return EJB_ERR_INVALID;   // not sorted
+        const int32_t a = find(k1[i]), b = find(k2[i]);
+        keep[i] = a != b;
+        if (a != b) parent[(size_t)std::max(a, b)] = std::min(a, b);
+    }
     return EJB_OK;
 }
 

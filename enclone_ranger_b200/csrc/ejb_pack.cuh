@@ -115,6 +115,22 @@ __global__ void k_subinfo(DevIn in, const uint64_t* keys, const uint32_t* row_of
     if (g) atomicOr(&out[s].gap, g);
 }
 
+// Row roles (ejb_set_row_roles): per sub-bucket the number of rows that act as first rows, the split flag, and a check that
+// column-only rows form a suffix of the sub-bucket (bit 16384 of the validation mask otherwise).
+struct SubRole {
+    int32_t n_act, raw;
+};
+__global__ void k_subroles(const uint8_t* __restrict__ roles, const uint32_t* __restrict__ row_of, const int32_t* __restrict__ head,
+                           const int32_t* __restrict__ sub_incl, int64_t n_active, SubRole* __restrict__ out, unsigned int* __restrict__ err) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_active) return;
+    const int s = sub_incl[j] - 1;
+    const uint8_t r = roles[row_of[j]];
+    if (!(r & ROLE_COLUMN_ONLY)) atomicAdd(&out[s].n_act, 1);
+    if (r & ROLE_SPLIT) atomicOr(&out[s].raw, 1);
+    if (j > 0 && !head[j] && !(r & ROLE_COLUMN_ONLY) && (roles[row_of[j - 1]] & ROLE_COLUMN_ONLY)) atomicOr(err, 16384u);
+}
+
 // per exact: donor set as a 64-bit mask (join_one.rs:301-315) and sort keys for the barcode lists
 __global__ void k_exact_prep(DevIn in, unsigned long long* donor_mask, uint64_t* bc_keys) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -74,7 +74,11 @@ struct SubBucket {
     int32_t n3;       // 3 * (Lh + Ll)  (join_one.rs:499)
     int32_t owner;    // rank that owns this sub-bucket (multi-GPU sharding)
     int32_t pad;
+    int32_t n_act;    // leading rows that act as the FIRST row of a pair (== n unless the caller split the sub-bucket by row
+                      // ranges across contexts, ejb_set_row_roles); the rest are columns only
+    int32_t raw;      // part of a split sub-bucket: its forest edges are returned without the two-cell filter
 };
+constexpr uint8_t ROLE_COLUMN_ONLY = 1, ROLE_SPLIT = 2;
 // Row record layout.  Per chain m the record is PLANE-MAJOR with a fixed plane order; W4 (uint4 per plane) is 4
 // for contigs up to 512 nt and 8 up to 1024 nt, so that the common case has a compile-time plane stride:
 //     chain m, plane pl, window g (128 positions)  ->  uint4 index  off_m + pl * W4_m + g

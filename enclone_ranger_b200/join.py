@@ -167,6 +167,34 @@ class JoinContext:
         self.L.ejb_result_free(self.h, C.byref(r))
         return out
 
+    def set_row_roles(self, roles):
+        """Row roles of a sub-bucket split over several contexts (ejb_set_row_roles): uint8 per row of the input the next
+        runs work on (bit 0 column-only, bit 1 split sub-bucket); None clears them."""
+        if roles is None:
+            self._ck(self.L.ejb_set_row_roles(self.h, None, 0))
+            return
+        r = np.ascontiguousarray(roles, dtype=np.uint8)
+        self._ck(self.L.ejb_set_row_roles(self.h, r.ctypes.data_as(C.POINTER(C.c_uint8)), r.size))
+
+    def device_tuples(self):
+        """(cd, nrefs, shares[2n]) of the last run()'s edges as zero-copy torch CUDA tensors."""
+        import torch
+        n = C.c_int64()
+        self.L.ejb_device_edges.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
+        self._ck(self.L.ejb_device_edges(self.h, C.byref(n), None, None, None))
+        dev = f"cuda:{self.device}"
+        if n.value == 0:
+            e = torch.zeros(0, dtype=torch.int32, device=dev)
+            return e, e.clone(), e.clone()
+        cd, nr, sh = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.L.ejb_device_tuples(self.h, C.byref(cd), C.byref(nr), C.byref(sh)))
+
+        class _Dev:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        return (torch.as_tensor(_Dev(cd.value, n.value), device=dev), torch.as_tensor(_Dev(nr.value, n.value), device=dev),
+                torch.as_tensor(_Dev(sh.value, 2 * n.value), device=dev))
+
     def device_edges(self):
         """(k1, k2) of the last run() as zero-copy torch CUDA tensors (valid until the next run())."""
         import torch
@@ -203,6 +231,20 @@ def join_exacts(ctx, params, inp):
     """Drop-in for enclone::join::join_exacts: returns (EquivRel, JoinResult)."""
     res = ctx.join(params, inp)
     return res.equiv(), res
+
+
+def forest_merge(n_rows, k1, k2):
+    """Kruskal over edges sorted by (k1, k2): boolean mask of the edges that join two components (ejb_forest_merge)."""
+    L = _abi.load_join()
+    k1 = np.ascontiguousarray(k1, dtype=np.int32)
+    k2 = np.ascontiguousarray(k2, dtype=np.int32)
+    keep = np.zeros(len(k1), dtype=np.uint8)
+    if len(k1):
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        rc = L.ejb_forest_merge(int(n_rows), ip(k1), ip(k2), len(k1), keep.ctypes.data_as(C.POINTER(C.c_uint8)))
+        if rc != 0:
+            raise JoinError(rc, "ejb_forest_merge (edges must be sorted by (k1, k2))")
+    return keep.astype(bool)
 
 
 def equiv_replay(n_rows, k1, k2, row_exact=None):

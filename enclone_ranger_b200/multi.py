@@ -121,17 +121,20 @@ def partition_buckets(inp, world, foreign_weight=100.0):
 
 
 def scatter_parts(parts, device, src=0, group=None):
-    """rank `src` holds `parts` = list (one per rank) of (JoinInput, global_rows); every rank gets its own.
+    """rank `src` holds `parts` = list (one per rank) of (JoinInput, global_rows[, roles]); every rank gets its own as
+    (JoinInput, rows, roles) — roles is None unless a sub-bucket was split (partition_work).
     Arrays travel as byte tensors over the process group (NCCL: device tensors)."""
     from .inputs import JoinInput, _FIELDS
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    names = list(_FIELDS.keys()) + ["__rows__"]
+    names = list(_FIELDS.keys()) + ["__rows__", "__roles__"]
     mine = None
     for r in range(world):
         if rank == src:
-            inp, rows = parts[r]
+            inp, rows = parts[r][0], parts[r][1]
+            roles = parts[r][2] if len(parts[r]) > 2 else None
             arrs = {n: inp.a[n] for n in _FIELDS}
             arrs["__rows__"] = np.asarray(rows, dtype=np.int64)
+            arrs["__roles__"] = np.zeros(0, dtype=np.uint8) if roles is None else np.asarray(roles, dtype=np.uint8)
             sizes = torch.tensor([arrs[n].nbytes for n in names], dtype=torch.int64, device=device)
         else:
             sizes = torch.zeros(len(names), dtype=torch.int64, device=device)
@@ -148,7 +151,7 @@ def scatter_parts(parts, device, src=0, group=None):
             dist.recv(sizes, src=src, group=group)
             mine = {}
             for n, sz in zip(names, sizes.tolist()):
-                dt = np.int64 if n == "__rows__" else _FIELDS[n]
+                dt = np.int64 if n == "__rows__" else (np.uint8 if n == "__roles__" else _FIELDS[n])
                 if sz:
                     t = torch.empty(int(sz), dtype=torch.uint8, device=device)
                     dist.recv(t, src=src, group=group)
@@ -156,4 +159,160 @@ def scatter_parts(parts, device, src=0, group=None):
                 else:
                     mine[n] = np.zeros(0, dtype=dt)
     rows = mine.pop("__rows__")
-    return JoinInput(**mine), rows
+    roles = mine.pop("__roles__")
+    return JoinInput(**mine), rows, (roles if roles.size else None)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Sub-bucket granular partitioning with row-range splits of the heaviest sub-buckets (ejb_set_row_roles).
+# ------------------------------------------------------------------------------------------------------------
+ROLE_COLUMN_ONLY, ROLE_SPLIT = 1, 2
+BIG_REFSET = 32          # rows; smaller reference sets (indel-edited references, ...) are killed by the stage-1 tags
+W_CROSS = 40.0           # cost of one stage-2 candidate in units of one CDR3 pair (measured: 0.083 ns vs 0.002 ns)
+
+
+def _sub_bucket_table(inp):
+    """(rows2, sub_of, n_sub): the 2-chain rows (ascending), the sub-bucket index of each, the number of sub-buckets.
+    Sub-bucket = run of equal lens (join.rs:68-88) x (heavy, light) CDR3 length."""
+    bucket = bucket_ids(inp)
+    two = np.nonzero(inp.a["row_nchains"] == 2)[0]
+    c3 = inp.a["row_cdr3_len"].reshape(-1, 2)
+    key = (bucket[two].astype(np.int64) << 32) | (c3[two, 0].astype(np.int64) << 16) | c3[two, 1].astype(np.int64)
+    uniq, sub_of = np.unique(key, return_inverse=True)
+    # a partial bucket must not fuse with another run of the same lens once rows in between are taken away
+    lens = inp.a["row_len"].reshape(-1, 2)
+    first = np.nonzero(np.diff(np.concatenate([[-1], bucket])))[0]
+    lk = (lens[first, 0].astype(np.int64) << 32) | lens[first, 1].astype(np.int64) | (inp.a["row_nchains"][first].astype(np.int64) << 60)
+    if len(np.unique(lk)) != len(lk):
+        raise ValueError("equal lens occur in several runs (unsorted info); use in-library sharding (ejb_set_shard) instead")
+    return two, sub_of.reshape(-1), len(uniq)
+
+
+def _row_costs(ref):
+    """Cost of every row of ONE sub-bucket acting as the first row of its pairs: the pairs to its right, plus W_CROSS for each
+    row to its right that carries a different BIG reference set when its own is big too (such pairs reach stage 2 one by
+    one — e.g. two large clones on two alleles of one V gene — and nothing short-cuts them)."""
+    n = len(ref)
+    cost = (n - 1 - np.arange(n)).astype(np.float64)
+    u, inv, cnt = np.unique(ref, return_inverse=True, return_counts=True)
+    big = np.nonzero(cnt >= BIG_REFSET)[0]
+    if len(big) >= 2:
+        is_big = np.isin(inv, big)
+        big_right = np.cumsum(is_big[::-1])[::-1] - is_big          # big rows strictly to the right
+        same_right = np.zeros(n, dtype=np.int64)
+        for g in big:
+            m = inv == g
+            same_right[m] = (np.cumsum(m[::-1])[::-1] - m)[m]
+        cost += W_CROSS * np.where(is_big, big_right - same_right, 0)
+    return cost + 64.0
+
+
+class WorkPart:
+    """What one rank joins: global row ids (ascending) and, when a sub-bucket was split, the row roles."""
+
+    def __init__(self, rows, roles):
+        self.rows = rows
+        self.roles = roles if roles is not None and roles.any() else None
+
+
+def partition_work(inp, world, split_above=0.5, piece=0.34):
+    """Longest-processing-time assignment of sub-buckets to `world` ranks; a sub-bucket whose cost exceeds `split_above` x the
+    per-rank share is cut into row ranges of about `piece` x that share (each part = the pairs whose FIRST row lies in the
+    range; it needs the rows of the range and every row after it).  Returns (parts, split_rows): one WorkPart per rank and
+    a boolean mask over all rows marking the split sub-buckets (their partial forests are merged by merge_split_edges)."""
+    two, sub_of, n_sub = _sub_bucket_table(inp)
+    vs = inp.a["row_vs"].reshape(-1, 2)[two].astype(np.int64)
+    js = inp.a["row_js"].reshape(-1, 2)[two].astype(np.int64)
+    ref = ((vs[:, 0] * 1000003 + vs[:, 1]) * 1000003 + js[:, 0]) * 1000003 + js[:, 1]
+    order = np.argsort(sub_of, kind="stable")           # rows grouped by sub-bucket, ascending inside
+    starts = np.concatenate([[0], np.cumsum(np.bincount(sub_of, minlength=n_sub))])
+    costs = [None] * n_sub
+    total = 0.0
+    for s in range(n_sub):
+        idx = order[starts[s]:starts[s + 1]]
+        if len(idx) < 2:
+            continue
+        if len(idx) < 2 * BIG_REFSET:
+            c = float(len(idx)) * (len(idx) - 1) / 2 + 64.0 * len(idx)
+        else:
+            costs[s] = _row_costs(ref[idx])
+            c = float(costs[s].sum())
+        costs[s] = (c, costs[s])
+        total += c
+    share = total / max(world, 1)
+    units = []    # (cost, sub, lo, hi, n_parts)
+    for s in range(n_sub):
+        if costs[s] is None:
+            continue
+        c, per_row = costs[s]
+        n = int(starts[s + 1] - starts[s])
+        if world > 1 and per_row is not None and c > split_above * share:
+            parts = int(min(world, np.ceil(c / (piece * share))))
+            cum = np.cumsum(per_row)
+            cuts = [0] + [int(np.searchsorted(cum, c * i / parts)) + 1 for i in range(1, parts)] + [n]
+            cuts = sorted(set(min(max(x, 0), n) for x in cuts))
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                if hi > lo:
+                    units.append((float(per_row[lo:hi].sum()), s, lo, hi, len(cuts) - 1))
+        else:
+            units.append((c, s, 0, n, 1))
+    units.sort(key=lambda u: -u[0])
+    load = np.zeros(world)
+    holder = {}                                          # sub -> ranks already holding one of its parts
+    take = [[] for _ in range(world)]
+    for c, s, lo, hi, nparts in units:
+        cand = np.argsort(load, kind="stable")
+        r = next(int(x) for x in cand if int(x) not in holder.get(s, ()))
+        holder.setdefault(s, set()).add(r)
+        load[r] += c
+        take[r].append((s, lo, hi, nparts))
+    split_rows = np.zeros(inp.n_rows, dtype=bool)
+    parts = []
+    for r in range(world):
+        rows, roles = [], []
+        for s, lo, hi, nparts in take[r]:
+            idx = two[order[starts[s]:starts[s + 1]]]
+            if nparts == 1:
+                rows.append(idx)
+                roles.append(np.zeros(len(idx), dtype=np.uint8))
+            else:
+                split_rows[idx] = True
+                rows.append(idx[lo:])
+                ro = np.full(len(idx) - lo, ROLE_SPLIT, dtype=np.uint8)
+                ro[hi - lo:] |= ROLE_COLUMN_ONLY
+                roles.append(ro)
+        rows = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+        roles = np.concatenate(roles) if roles else np.zeros(0, dtype=np.uint8)
+        o = np.argsort(rows, kind="stable")
+        parts.append(WorkPart(rows[o].astype(np.int64), roles[o]))
+    return parts, split_rows
+
+
+def merge_split_edges(n_rows, k1, k2, cd, min_sh, split_rows, ncells_row, easy=False):
+    """Edges of all ranks sorted by (k1, k2) (global row ids) -> boolean keep mask.  Edges of split sub-buckets are the union
+    of partial forests: keep their minimum spanning forest (ejb_forest_merge, Kruskal in (k1, k2) order), then apply the
+    two-cell filter (join.rs:120-178: an orbit of exactly two rows holding two cells in total loses its edge when
+    cd > min(shares) / 2, unless EASY) that the parts had to skip.  Edges of whole sub-buckets are kept as they are."""
+    from .join import forest_merge
+    k1 = np.asarray(k1)
+    k2 = np.asarray(k2)
+    keep = np.ones(len(k1), dtype=bool)
+    sel = np.nonzero(split_rows[k1])[0]
+    if len(sel) == 0:
+        return keep
+    f = forest_merge(n_rows, k1[sel], k2[sel])
+    keep[sel[~f]] = False
+    sel = sel[f]
+    a, b = k1[sel], k2[sel]
+    deg = np.bincount(np.concatenate([a, b]), minlength=n_rows)
+    two_cell = (deg[a] == 1) & (deg[b] == 1) & (ncells_row[a] + ncells_row[b] == 2) & (np.asarray(cd)[sel] > np.asarray(min_sh)[sel] // 2)
+    if not easy:
+        keep[sel[two_cell]] = False
+    return keep
+
+
+def ncells_per_row(inp):
+    """exact_clonotypes[info[k].clonotype_id].ncells() for every row."""
+    off = inp.a["ex_cell_off"]
+    ex = inp.a["row_exact"]
+    return (off[ex + 1] - off[ex]).astype(np.int64)

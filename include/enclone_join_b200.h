@@ -298,6 +298,25 @@ int ejb_equiv_replay(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64
  * per-rank edges GPU-to-GPU (NCCL) without a host round trip.                                       */
 int ejb_device_edges(ejb_ctx* ctx, int64_t* n_edges, const int32_t** d_k1, const int32_t** d_k2, const int32_t** d_labels);
 
+/* PotentialJoin numerics of the same edges (device pointers, same lifetime): cd, nrefs, shares[2*i + u].      */
+int ejb_device_tuples(ejb_ctx* ctx, const int32_t** d_cd, const int32_t** d_nrefs, const int32_t** d_shares);
+
+/* Multi-GPU, one LARGE sub-bucket (equal lens and CDR3 lengths) split over several contexts by row ranges.
+ * The pairs (k1 < k2) of a sub-bucket are partitioned by their FIRST row: a context that is given the rows
+ * [lo, n) of the sub-bucket with roles[] = 0 for [lo, hi) and EJB_ROLE_COLUMN_ONLY for [hi, n) evaluates exactly
+ * the pairs whose first row lies in [lo, hi) and returns the lexicographic spanning forest of THOSE pass edges
+ * (join_core.rs:23-50 restricted to them).  Rows of a split sub-bucket also carry EJB_ROLE_SPLIT: their edges are
+ * returned without the two-cell filter (join.rs:120-178), which only makes sense on the merged forest.  The
+ * caller concatenates the parts' edges, sorts them by (k1, k2), keeps what ejb_forest_merge keeps (the minimum
+ * spanning forest of a union of graphs is the minimum spanning forest of the union of their forests), applies
+ * the two-cell filter and replays the EquivRel (enclone_ranger_b200/multi.py does all of this).
+ * roles: one byte per row of the input the NEXT ejb_run / ejb_join calls work on; they stay in force on this
+ * context until cleared with roles == NULL (a run on an input with another row count fails).                 */
+#define EJB_ROLE_COLUMN_ONLY 1
+#define EJB_ROLE_SPLIT 2
+int ejb_set_row_roles(ejb_ctx* ctx, const uint8_t* roles, int64_t n_rows);
+int ejb_forest_merge(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64_t n_edges, uint8_t* keep);
+
 int ejb_abi_version(void);
 /* sizeof(ejb_params), sizeof(ejb_input), sizeof(ejb_stats), sizeof(ejb_result) as the library was
  * compiled — lets a binding verify its struct mirrors.                                          */

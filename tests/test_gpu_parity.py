@@ -261,3 +261,41 @@ def test_reference_set_tags_at_scale(gpu_ctx):
     assert off.stats["stage1_ref_kills"] == 0
     assert on.stats["stage1_ref_kills"] > 0, "a 300k-cell heavy-tailed repertoire with 1 % indel rows must exercise the kill"
     assert on.stats["stage1_candidates"] < off.stats["stage1_candidates"]
+
+
+@pytest.mark.parametrize("config,cells,world,seed", [(1, 40000, 4, 31), (1, 60000, 8, 32), (3, 30000, 3, 33)])
+def test_row_range_split_of_large_sub_buckets(gpu_ctx, config, cells, world, seed):
+    """The multi-GPU partitioner cuts the heaviest sub-buckets into row ranges (ejb_set_row_roles); every part is joined on
+    its own (here: back to back on one GPU), the partial forests are merged (forest of forests + two-cell filter) and the
+    result must be the oracle's: edges, PotentialJoin numerics, EquivRel."""
+    from enclone_ranger_b200 import multi
+    rep = E.generate(config, n_cells=cells, seed=seed)
+    inp = rep.to_join_input()
+    p = E.default_params(bool(rep.config.is_bcr))
+    want = pyoracle.run(p, inp.c_ptr(), threads=0)
+    parts, split = multi.partition_work(inp, world)
+    assert split.any()
+    got, pairs = [], 0
+    try:
+        for part in parts:
+            sub, _ = inp.subset_rows(part.rows)
+            gpu_ctx.set_row_roles(part.roles)
+            res = gpu_ctx.join(p, sub)
+            pairs += res.stats["pairs_scored"]
+            d = {f: getattr(res, f) for f in multi.EDGE_FIELDS}
+            d["edge_k1"] = part.rows[res.edge_k1].astype(np.int32)
+            d["edge_k2"] = part.rows[res.edge_k2].astype(np.int32)
+            got.append(d)
+    finally:
+        gpu_ctx.set_row_roles(None)
+    assert pairs == want["pairs_scored"]
+    merged = multi.merge_edge_parts(got)
+    sh = merged["edge_shares"]
+    min_sh = np.where(merged["edge_nrefs"] == 2, sh.min(axis=1), sh[:, 0])
+    keep = multi.merge_split_edges(inp.n_rows, merged["edge_k1"], merged["edge_k2"], merged["edge_cd"], min_sh, split, multi.ncells_per_row(inp))
+    assert (~keep).any(), "partial forests overlap: the merge must drop something"
+    final = {f: v[keep] for f, v in merged.items()}
+    assert_same_result(final, {k: want[k] for k in want if k.startswith("edge_")}, "row-range split")
+    eq, lab = E.equiv_replay(inp.n_rows, final["edge_k1"], final["edge_k2"], inp.a["row_exact"])
+    assert np.array_equal(eq.x, want["eq_x"]) and np.array_equal(eq.y, want["eq_y"]) and np.array_equal(eq.z, want["eq_z"])
+    assert np.array_equal(lab, want["labels"])

@@ -15,7 +15,7 @@ from enclone_ranger_b200 import multi
 ap = argparse.ArgumentParser()
 ap.add_argument("--world", type=int, default=8)
 ap.add_argument("--cells-per-rank", type=int, default=1000000)
-ap.add_argument("--weights", type=str, default="100,10")
+ap.add_argument("--weights", type=str, default="40")
 ap.add_argument("--no-gpu", action="store_true", help="only time the host-side partitioning")
 a = ap.parse_args()
 t = time.time()
@@ -27,24 +27,27 @@ p = E.default_params(True)
 ctx = None if a.no_gpu else E.JoinContext()
 for w in [float(x) for x in a.weights.split(",")]:
     t = time.time()
-    parts = multi.partition_buckets(full, a.world, foreign_weight=w)
+    multi.W_CROSS = w
+    parts, split = multi.partition_work(full, a.world)
     t_part = time.time() - t
     per = []
-    for rows in parts:
+    for part in parts:
+        rows = part.rows
         t = time.time()
         sub, _ = full.subset_rows(rows)
         pk = sub.to_packed()
         t_sub = time.time() - t
         if ctx is None:
-            per.append({"rows": int(len(rows)), "subset_s": round(t_sub, 2)})
+            per.append({"rows": int(len(rows)), "subset_s": round(t_sub, 2), "column_only": 0 if part.roles is None else int((part.roles & 1).sum())})
             continue
+        ctx.set_row_roles(part.roles)
         ctx.upload(p, pk)
         ctx.run()
         s = ctx.run()
         per.append({"rows": int(len(rows)), "device_ms": round(s["ms_device_total"], 2), "pairs_scored": int(s["pairs_scored"]),
                     "stage1_candidates": int(s["stage1_candidates"]), "stage1_ref_kills": int(s["stage1_ref_kills"]),
                     "ms_stage1": round(s["ms_stage1"], 2), "ms_stage2a": round(s["ms_stage2a"], 2), "rounds": int(s["rounds"]), "subset_s": round(t_sub, 2)})
-    out = {"world": a.world, "foreign_weight": w, "partition_s": round(t_part, 2), "per_rank": per}
+    out = {"world": a.world, "w_cross": w, "split_rows": int(split.sum()), "partition_s": round(t_part, 2), "per_rank": per}
     if ctx is not None:
         ms = [x["device_ms"] for x in per]
         out["max_ms"] = max(ms)

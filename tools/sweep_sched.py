@@ -14,7 +14,7 @@ p = E.default_params(bool(rep.config.is_bcr))
 rep.close()
 ctx = E.JoinContext()
 ctx.upload(p, inp)
-for first, growth in ((8, 4), (2, 4), (1, 4), (2, 8), (4, 8), (1, 8), (2, 16), (8, 4)):
+for first, growth in ((1, 8), (1, 12), (1, 16), (1, 32), (2, 12), (1, 6), (1, 8)):
     os.environ["EJB_FIRST_UNIT"] = str(first)
     os.environ["EJB_GROWTH"] = str(growth)
     ctx.run()
