@@ -221,7 +221,11 @@ def main():
             rep.close()
             full_rows, row_exact_full = full.n_rows, full.a["row_exact"].copy()
             parts = []
-            wparts, split_rows = multi.partition_work(full, world)
+            # sample join on this rank's GPU: which large sub-buckets hold pairs that are scored in full and do not join
+            probe_ctx = E.JoinContext(device=local_rank)
+            live = multi.probe_live_fractions(full, probe_ctx, E.default_params(True))
+            probe_ctx.close()
+            wparts, split_rows = multi.partition_work(full, world, live_fraction=live)
             ncells_row = multi.ncells_per_row(full)
             for wp in wparts:
                 sub, _ = full.subset_rows(wp.rows)

@@ -332,6 +332,7 @@ S2Ctx make_s2ctx(ejb_ctx* c, int tuple_mode) {
     X.slow_slot = c->d_slowslot.as<uint32_t>();
     X.slow_cap = c->cand_cap;
     X.tuple_mode = tuple_mode;
+    X.trace = getenv("EJB_TRACE") != nullptr;
     return X;
 }
 
@@ -764,6 +765,16 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     }
     CK(cudaEventRecord(rt.e3, c->stream));
     times.push_back(rt);
+    if (getenv("EJB_TRACE")) {   // developer aid: what the round was made of
+        size_t top = 0;
+        for (size_t i = 1; i < units.size(); i++)
+            if (units[i].cand > units[top].cand) top = i;
+        const Counters& hh = *c->h_ctr;
+        fprintf(stderr, "[ejb trace] round %lld: %zu units, cand %llu surv %llu pass %llu; top unit: sub %d (n %d) rows [%d,%d) cand %.0f pass %.0f\n",
+                (long long)c->stats.rounds, units.size(), hh.n_cand, hh.n_surv_total, hh.n_pass, units.empty() ? -1 : units[top].sub,
+                units.empty() ? 0 : subs[units[top].sub].n, units.empty() ? 0 : units[top].r0, units.empty() ? 0 : units[top].r1,
+                units.empty() ? 0.0 : units[top].cand, units.empty() ? 0.0 : units[top].pass);
+    }
     c->stats.rounds++;
     return EJB_OK;
 }
@@ -1292,6 +1303,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
             fprintf(stderr, " %s %.3f ms;", tr[i].first, ms);
         }
         fprintf(stderr, " total pack %.3f ms\n", c->stats.ms_pack);
+        fprintf(stderr, "[ejb trace] integer-test rejections: ident %llu max_diffs %llu max_cdr3 %llu donors %llu cd>=mult*indeps %llu cref %llu\n", c->h_ctr->n_rej[0],
+                c->h_ctr->n_rej[1], c->h_ctr->n_rej[2], c->h_ctr->n_rej[3], c->h_ctr->n_rej[4], c->h_ctr->n_rej[5]);
         for (size_t i = 0; i < times.size(); i++) {
             float a, b, d;
             cudaEventElapsedTime(&a, times[i].e0, times[i].e1);

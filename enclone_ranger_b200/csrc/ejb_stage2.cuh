@@ -38,6 +38,7 @@ struct S2Ctx {
     uint32_t* slow_slot;
     unsigned long long slow_cap;
     int tuple_mode;              // 0: filter -> pass edges; 1: write an EdgeTuple per input pair
+    int trace;                   // count the rejections of the integer tests by reason (developer aid, EJB_TRACE)
 };
 
 struct RegionDiffs {
@@ -58,33 +59,35 @@ __device__ __forceinline__ bool s2_integer_tests(const S2Ctx& X, uint32_t q1, ui
     const uint32_t f1 = (uint32_t)a1[AX_FLAGS];
     const int cd = cd1 + cd2;
     bool ok = pre_ok;
+    int why = -1;   // first failing test (trace only)
     // join_one.rs:216-234
     if (P.is_bcr) {
         const int total = sb.ch + sb.cl;
-        if ((double)cd / (double)total > P.cdr3_ident_thr) ok = false;
+        if ((double)cd / (double)total > P.cdr3_ident_thr) { ok = false; if (why < 0) why = 0; }
     }
     // :238-267
     if (!P.is_bcr || P.max_diffs < 1000000) {
-        if (diffs > P.max_diffs) ok = false;
-        if (!P.is_bcr && diffs > 5) ok = false;
+        if (diffs > P.max_diffs) { ok = false; if (why < 0) why = 1; }
+        if (!P.is_bcr && diffs > 5) { ok = false; if (why < 0) why = 1; }
     }
     // :286-290
-    if ((P.max_cdr3_diffs < 1000 || !P.is_bcr) && (cd > P.max_cdr3_diffs || (!P.is_bcr && cd > 0))) ok = false;
+    if ((P.max_cdr3_diffs < 1000 || !P.is_bcr) && (cd > P.max_cdr3_diffs || (!P.is_bcr && cd > 0))) { ok = false; if (why < 0) why = 2; }
     // :301-323
     const unsigned long long m1 = ((unsigned long long)(uint32_t)a1[AX_DONHI] << 32) | (uint32_t)a1[AX_DONLO];
     const unsigned long long m2 = ((unsigned long long)(uint32_t)a2[AX_DONHI] << 32) | (uint32_t)a2[AX_DONLO];
-    if (!P.mix_donors && m1 != 0 && m2 != 0 && m1 != m2) ok = false;
+    if (!P.mix_donors && m1 != 0 && m2 != 0 && m1 != m2) { ok = false; if (why < 0) why = 3; }
     const bool err = (m1 != m2) || __popcll(m1) != 1 || __popcll(m2) != 1;
     // :444-447
     const int min_sh = (nrefs == 2) ? min(sh0, sh1) : sh0;
     const int min_in = (nrefs == 2) ? min(in0, in1) : in0;
     // :474-476
-    if ((double)cd >= P.cdr3_mult * (double)max(1, min_in)) ok = false;
+    if ((double)cd >= P.cdr3_mult * (double)max(1, min_in)) { ok = false; if (why < 0) why = 4; }
     // :481-493
     if (!P.old_light && cd > 0) {
-        if (!(f1 & B_LEFT_H) && a1[AX_CREFH] != -1 && a2[AX_CREFH] != -1 && a1[AX_CREFH] != a2[AX_CREFH]) ok = false;
-        if (!(f1 & B_LEFT_L) && a1[AX_CREFL] != -1 && a2[AX_CREFL] != -1 && a1[AX_CREFL] != a2[AX_CREFL]) ok = false;
+        if (!(f1 & B_LEFT_H) && a1[AX_CREFH] != -1 && a2[AX_CREFH] != -1 && a1[AX_CREFH] != a2[AX_CREFH]) { ok = false; if (why < 0) why = 5; }
+        if (!(f1 & B_LEFT_L) && a1[AX_CREFL] != -1 && a2[AX_CREFL] != -1 && a1[AX_CREFL] != a2[AX_CREFL]) { ok = false; if (why < 0) why = 5; }
     }
+    if (X.trace && pre_ok && why >= 0 && !X.tuple_mode) atomicAdd(&X.ctr->n_rej[why], 1ull);
     if (!ok && !force_emit) return false;
     const int k = min_in + 2 * min_sh;
     if (k > SR_NMAX) {

@@ -149,6 +149,8 @@ struct Counters {       // device-side counters, one instance per context
     unsigned long long n_two_ref;     // stage-2a candidates with two reference sets (filter mode)
     unsigned long long n_memo_dead;   // ... of which rejected on memoised totals (phase 0)
     unsigned long long n_degr_dead;   // ... of which rejected by the degradation test on freshly computed totals
+    unsigned long long n_rej[8];      // filter-mode rejections of the integer tests by first failing test (EJB_TRACE): 0 CDR3 identity,
+                                      // 1 max_diffs, 2 max_cdr3_diffs, 3 donors, 4 cd >= cdr3_mult * indeps, 5 constant regions, 6 k range
 };
 
 // Reference-set tags (stage-1 kill of pairs that are known to fail join_one.rs:434-440).

@@ -167,8 +167,7 @@ def scatter_parts(parts, device, src=0, group=None):
 # Sub-bucket granular partitioning with row-range splits of the heaviest sub-buckets (ejb_set_row_roles).
 # ------------------------------------------------------------------------------------------------------------
 ROLE_COLUMN_ONLY, ROLE_SPLIT = 1, 2
-BIG_REFSET = 32          # rows; smaller reference sets (indel-edited references, ...) are killed by the stage-1 tags
-W_CROSS = 40.0           # cost of one stage-2 candidate in units of one CDR3 pair (measured: 0.083 ns vs 0.002 ns)
+W_CROSS = 60.0           # cost of one fully scored stage-2 candidate in units of one CDR3 pair (fit on the 8 x 1M-cell run: 0.12 ns vs 1.9 ps)
 
 
 def _sub_bucket_table(inp):
@@ -188,23 +187,88 @@ def _sub_bucket_table(inp):
     return two, sub_of.reshape(-1), len(uniq)
 
 
-def _row_costs(ref):
-    """Cost of every row of ONE sub-bucket acting as the first row of its pairs: the pairs to its right, plus W_CROSS for each
-    row to its right that carries a different BIG reference set when its own is big too (such pairs reach stage 2 one by
-    one — e.g. two large clones on two alleles of one V gene — and nothing short-cuts them)."""
-    n = len(ref)
-    cost = (n - 1 - np.arange(n)).astype(np.float64)
-    u, inv, cnt = np.unique(ref, return_inverse=True, return_counts=True)
-    big = np.nonzero(cnt >= BIG_REFSET)[0]
-    if len(big) >= 2:
-        is_big = np.isin(inv, big)
-        big_right = np.cumsum(is_big[::-1])[::-1] - is_big          # big rows strictly to the right
-        same_right = np.zeros(n, dtype=np.int64)
-        for g in big:
-            m = inv == g
-            same_right[m] = (np.cumsum(m[::-1])[::-1] - m)[m]
-        cost += W_CROSS * np.where(is_big, big_right - same_right, 0)
-    return cost + 64.0
+def _seg(inp, i):
+    off = inp.a["seg_off"]
+    return inp.a["seg_bytes"][off[i]:off[i + 1]]
+
+
+def _refsets_compatible(inp, ra, rb, max_degradation):
+    """Can a row on reference set ra survive the degradation test (join_one.rs:434-440) against rb?  The count of
+    differences of one contig to two references differs by at most their Hamming distance, so references further apart than
+    max_degradation (different genes) kill the pair — once per row, then the stage-1 tags drop it — while near-identical
+    ones (two alleles of one gene) let every CDR3-close pair through to the full two-reference scoring."""
+    d = 0
+    for x, y in zip(ra, rb):
+        if x == y:
+            continue
+        sx, sy = _seg(inp, x), _seg(inp, y)
+        if len(sx) != len(sy):
+            return False
+        d += int(np.count_nonzero(sx != sy))
+        if d > max_degradation:
+            return False
+    return True
+
+
+def probe_live_fractions(inp, ctx, params, min_rows=4096, sample=256):
+    """Estimate, for every large sub-bucket, the fraction of its pairs that reach the full stage-2 scoring and do NOT join
+    (two big clones on one V/J gene pair with similar junctions, or on two alleles of one gene): such pairs cost ~W_CROSS
+    times a CDR3 comparison each and decide how evenly ranks are loaded, but nothing short of the join itself tells them
+    from pairs inside one clone.  So the join is run on a SAMPLE: `sample` evenly spaced rows of each sub-bucket with at
+    least `min_rows` rows go through `ctx` (one small join for all of them), and a sampled pair counts as live when it is
+    CDR3-close (join_one.rs:216-234), ends in different clonotypes and its reference sets are equal or compatible.
+    Returns {sub-bucket index (as in partition_work): fraction}."""
+    two, sub_of, n_sub = _sub_bucket_table(inp)
+    cnt = np.bincount(sub_of, minlength=n_sub)
+    order = np.argsort(sub_of, kind="stable")
+    starts = np.concatenate([[0], np.cumsum(cnt)])
+    big = np.nonzero(cnt >= min_rows)[0]
+    if len(big) == 0:
+        return {}
+    picks = {}
+    for s in big:
+        idx = two[order[starts[s]:starts[s + 1]]]
+        picks[s] = idx[np.unique(np.linspace(0, len(idx) - 1, sample).astype(np.int64))]
+    rows = np.sort(np.concatenate(list(picks.values())))
+    probe, _ = inp.subset_rows(rows)
+    ctx.set_row_roles(None)
+    labels = np.asarray(ctx.join(params, probe).labels)
+    lab_of = np.full(inp.n_rows, -1, dtype=np.int64)
+    lab_of[rows] = labels
+    thr = 1.0 - params.join_cdr3_ident / 100.0
+    c3off = inp.a["row_cdr3_off"].reshape(-1, 2)
+    c3len = inp.a["row_cdr3_len"].reshape(-1, 2)
+    c3 = inp.a["cdr3_bytes"]
+    vs = inp.a["row_vs"].reshape(-1, 2)
+    js = inp.a["row_js"].reshape(-1, 2)
+    out = {}
+    for s, r in picks.items():
+        m = len(r)
+        ch, cl = int(c3len[r[0], 0]), int(c3len[r[0], 1])
+        T = ch + cl
+        if m < 2 or T == 0:
+            continue
+        seq = np.empty((m, T), dtype=np.uint8)
+        for i, k in enumerate(r):
+            seq[i, :ch] = c3[c3off[k, 0]:c3off[k, 0] + ch]
+            seq[i, ch:] = c3[c3off[k, 1]:c3off[k, 1] + cl]
+        cd = (seq[:, None, :] != seq[None, :, :]).sum(axis=2)
+        close = (cd.astype(np.float64) / T <= thr) if params.is_bcr else (cd == 0)
+        lab = lab_of[r]
+        live = close & (lab[:, None] != lab[None, :])
+        refs = np.concatenate([vs[r], js[r]], axis=1)
+        u, inv = np.unique(refs, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        if len(u) > 1:
+            comp = np.eye(len(u), dtype=bool)
+            cntu = np.bincount(inv)
+            for a in range(len(u)):
+                for b in range(a + 1, len(u)):
+                    if cntu[a] * cntu[b] * 50 >= m:      # rare pairings cannot move the estimate
+                        comp[a, b] = comp[b, a] = _refsets_compatible(inp, u[a], u[b], int(params.max_degradation))
+            live &= comp[inv[:, None], inv[None, :]]
+        out[int(s)] = float(np.triu(live, 1).sum()) / (m * (m - 1) / 2)
+    return out
 
 
 class WorkPart:
@@ -215,30 +279,31 @@ class WorkPart:
         self.roles = roles if roles is not None and roles.any() else None
 
 
-def partition_work(inp, world, split_above=0.5, piece=0.34):
+def partition_work(inp, world, live_fraction=None, split_above=0.5, piece=0.34):
     """Longest-processing-time assignment of sub-buckets to `world` ranks; a sub-bucket whose cost exceeds `split_above` x the
     per-rank share is cut into row ranges of about `piece` x that share (each part = the pairs whose FIRST row lies in the
-    range; it needs the rows of the range and every row after it).  Returns (parts, split_rows): one WorkPart per rank and
-    a boolean mask over all rows marking the split sub-buckets (their partial forests are merged by merge_split_edges)."""
+    range; it needs the rows of the range and every row after it).
+    Cost of a row acting as first row = (rows to its right) x (1 + W_CROSS x live fraction of its sub-bucket) + 64;
+    live_fraction = probe_live_fractions(...) (None: pairs only).
+    Returns (parts, split_rows): one WorkPart per rank and a boolean mask over all rows marking the split sub-buckets
+    (their partial forests are merged by merge_split_edges)."""
     two, sub_of, n_sub = _sub_bucket_table(inp)
-    vs = inp.a["row_vs"].reshape(-1, 2)[two].astype(np.int64)
-    js = inp.a["row_js"].reshape(-1, 2)[two].astype(np.int64)
-    ref = ((vs[:, 0] * 1000003 + vs[:, 1]) * 1000003 + js[:, 0]) * 1000003 + js[:, 1]
     order = np.argsort(sub_of, kind="stable")           # rows grouped by sub-bucket, ascending inside
     starts = np.concatenate([[0], np.cumsum(np.bincount(sub_of, minlength=n_sub))])
+    live_fraction = live_fraction or {}
     costs = [None] * n_sub
     total = 0.0
     for s in range(n_sub):
-        idx = order[starts[s]:starts[s + 1]]
-        if len(idx) < 2:
+        n = int(starts[s + 1] - starts[s])
+        if n < 2:
             continue
-        if len(idx) < 2 * BIG_REFSET:
-            c = float(len(idx)) * (len(idx) - 1) / 2 + 64.0 * len(idx)
+        scale = 1.0 + W_CROSS * live_fraction.get(s, 0.0)
+        if n < 1024:
+            costs[s] = (scale * n * (n - 1) / 2 + 64.0 * n, None)
         else:
-            costs[s] = _row_costs(ref[idx])
-            c = float(costs[s].sum())
-        costs[s] = (c, costs[s])
-        total += c
+            per_row = scale * (n - 1 - np.arange(n)).astype(np.float64) + 64.0
+            costs[s] = (float(per_row.sum()), per_row)
+        total += costs[s][0]
     share = total / max(world, 1)
     units = []    # (cost, sub, lo, hi, n_parts)
     for s in range(n_sub):

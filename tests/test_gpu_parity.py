@@ -299,3 +299,20 @@ def test_row_range_split_of_large_sub_buckets(gpu_ctx, config, cells, world, see
     eq, lab = E.equiv_replay(inp.n_rows, final["edge_k1"], final["edge_k2"], inp.a["row_exact"])
     assert np.array_equal(eq.x, want["eq_x"]) and np.array_equal(eq.y, want["eq_y"]) and np.array_equal(eq.z, want["eq_z"])
     assert np.array_equal(lab, want["labels"])
+
+
+def test_probe_live_fractions(gpu_ctx):
+    """The partitioner's sample join: fractions in [0, 1] for the large sub-buckets only, and a partition built from them
+    still covers every row once."""
+    from enclone_ranger_b200 import multi
+    rep = E.generate(1, n_cells=120000, seed=41)
+    inp = rep.to_join_input()
+    p = E.default_params(True)
+    live = multi.probe_live_fractions(inp, gpu_ctx, p, min_rows=1024, sample=128)
+    assert len(live) >= 1 and all(0.0 <= v <= 1.0 for v in live.values())
+    parts, split = multi.partition_work(inp, 4, live_fraction=live)
+    first = np.zeros(inp.n_rows, dtype=np.int64)
+    for part in parts:
+        roles = part.roles if part.roles is not None else np.zeros(len(part.rows), dtype=np.uint8)
+        first[part.rows[(roles & multi.ROLE_COLUMN_ONLY) == 0]] += 1
+    assert first.max() == 1

@@ -15,7 +15,7 @@ from enclone_ranger_b200 import multi
 ap = argparse.ArgumentParser()
 ap.add_argument("--world", type=int, default=8)
 ap.add_argument("--cells-per-rank", type=int, default=1000000)
-ap.add_argument("--weights", type=str, default="40")
+ap.add_argument("--weights", type=str, default="45")
 ap.add_argument("--no-gpu", action="store_true", help="only time the host-side partitioning")
 a = ap.parse_args()
 t = time.time()
@@ -28,7 +28,10 @@ ctx = None if a.no_gpu else E.JoinContext()
 for w in [float(x) for x in a.weights.split(",")]:
     t = time.time()
     multi.W_CROSS = w
-    parts, split = multi.partition_work(full, a.world)
+    t0 = time.time()
+    live = multi.probe_live_fractions(full, ctx, p) if ctx is not None else {}
+    t_probe = time.time() - t0
+    parts, split = multi.partition_work(full, a.world, live_fraction=live)
     t_part = time.time() - t
     per = []
     for part in parts:
@@ -47,7 +50,7 @@ for w in [float(x) for x in a.weights.split(",")]:
         per.append({"rows": int(len(rows)), "device_ms": round(s["ms_device_total"], 2), "pairs_scored": int(s["pairs_scored"]),
                     "stage1_candidates": int(s["stage1_candidates"]), "stage1_ref_kills": int(s["stage1_ref_kills"]),
                     "ms_stage1": round(s["ms_stage1"], 2), "ms_stage2a": round(s["ms_stage2a"], 2), "rounds": int(s["rounds"]), "subset_s": round(t_sub, 2)})
-    out = {"world": a.world, "w_cross": w, "split_rows": int(split.sum()), "partition_s": round(t_part, 2), "per_rank": per}
+    out = {"world": a.world, "w_cross": w, "split_rows": int(split.sum()), "probe_s": round(t_probe, 2), "live": {str(k): round(v, 4) for k, v in sorted(live.items(), key=lambda kv: -kv[1])[:12]}, "partition_s": round(t_part, 2), "per_rank": per}
     if ctx is not None:
         ms = [x["device_ms"] for x in per]
         out["max_ms"] = max(ms)
