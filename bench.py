@@ -342,7 +342,7 @@ def main():
         ln = torch.tensor([launches, pairs], dtype=torch.int64, device=dev)
         dist.all_reduce(ln)
         launches, pairs = int(ln[0].item()), int(ln[1].item())
-        keys = ("pairs_scored", "pairs_evaluated", "stage1_candidates", "stage1_ref_kills", "stage2_survivors", "pass_edges", "rounds", "overflow_retries",
+        keys = ("pairs_scored", "pairs_evaluated", "stage1_candidates", "stage1_ref_kills", "stage1_donor_kills", "stage2_survivors", "pass_edges", "rounds", "overflow_retries",
                 "ms_pack", "ms_stage1", "ms_stage2", "ms_stage2a", "ms_forest", "ms_finalize")
         pr = [torch.zeros(2 + len(keys), dtype=torch.float64, device=dev) for _ in range(world)]
         dist.all_gather(pr, torch.tensor([wall_ms, sum(dev_ms) / len(dev_ms)] + [float(stats[k]) for k in keys], dtype=torch.float64, device=dev))
@@ -427,7 +427,7 @@ def main():
                                         "frac": (pairs / (t_step / 1e3)) / (peaks["popc_per_s"] / (p1_avg + p2_avg * stats["stage1_candidates"] / max(pairs, 1)))},
                          "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (t_step / 1e3) / 1e9, "peak_gbs": hbm_peak}},
             "stage_ms": {k: stats[k] for k in ("ms_pack", "ms_stage1", "ms_stage2", "ms_stage2a", "ms_forest", "ms_finalize")},
-            "counts": {k: int(stats[k]) for k in ("pairs_evaluated", "stage1_candidates", "stage1_ref_kills", "stage2_two_ref", "stage2_memo_dead", "stage2_degr_dead", "stage2_slow", "stage2_survivors", "pass_edges", "forest_edges", "joins", "rounds")},
+            "counts": {k: int(stats[k]) for k in ("pairs_evaluated", "stage1_candidates", "stage1_ref_kills", "stage1_donor_kills", "stage2_two_ref", "stage2_memo_dead", "stage2_degr_dead", "stage2_slow", "stage2_survivors", "pass_edges", "forest_edges", "joins", "rounds")},
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle   # CPU baseline leg only: the checker timed as a baseline, never on the product path

@@ -148,6 +148,7 @@ class EjbStats(C.Structure):
         ("stage2_two_ref", C.c_int64),
         ("stage2_memo_dead", C.c_int64),
         ("stage2_degr_dead", C.c_int64),
+        ("stage1_donor_kills", C.c_int64),
     ]
 
     def as_dict(self):

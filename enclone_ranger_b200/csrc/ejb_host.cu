@@ -113,7 +113,7 @@ struct ejb_ctx {
     DevBuf d_head, d_scan, d_keys, d_keys2, d_vals, d_vals2, d_cubtmp, d_subhead, d_subincl, d_subinfo;
     DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_aux;
     DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
-    DevBuf d_unitcand, d_qcut, d_subpass, d_segpl, d_memo, d_tagq, d_deadq;
+    DevBuf d_unitcand, d_qcut, d_subpass, d_segpl, d_memo, d_tagq, d_deadq, d_donq;
     bool tags_on = false;      // reference-set tags in use (every canonical seg id < 65535)
     int s1_mode = S1_RUNI | S1_TAGS;   // stage-1 kernel variant (EJB_S1_MODE, developer knob)
     std::vector<unsigned int> h_subpass;
@@ -256,7 +256,8 @@ void launch_stage1_wm(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_ta
     k_stage1<W1, MODE><<<(unsigned int)n_ctas, S1_THREADS, 0, c->stream>>>(c->d_subs.as<SubBucket>(), tasks, n_tasks, c->d_cdr3w.as<uint32_t>(),
                                                                             c->d_labq.as<int32_t>(), c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(),
                                                                             c->cand_cap, c->d_ctr.as<Counters>(), c->d_unitcand.as<unsigned long long>(),
-                                                                            c->d_tagq.as<unsigned long long>(), c->d_deadq.as<unsigned long long>());
+                                                                            c->d_tagq.as<unsigned long long>(), c->d_deadq.as<unsigned long long>(),
+                                                                            c->d_donq.as<unsigned long long>());
 }
 template <int W1>
 void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks) {
@@ -1019,7 +1020,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
         if (const char* e = getenv("EJB_S1_MODE")) c->s1_mode = atoi(e) & 3;
         c->tags_on = c->n_canon_segs < 65535 && !getenv("EJB_NO_TAGS") && (c->s1_mode & S1_TAGS);
         if (c->tags_on) {
-            CK(c->d_tagq.ensure(np * 8)); CK(c->d_deadq.ensure(np * 8));
+            CK(c->d_tagq.ensure(np * 8)); CK(c->d_deadq.ensure(np * 8)); CK(c->d_donq.ensure(np * 8));
+            CK(cudaMemsetAsync(c->d_donq.p, 0, np * 8, st));       // padding positions
             CK(cudaMemsetAsync(c->d_tagq.p, 0xff, np * 8, st));    // padding positions: never part of a valid pair
             CK(cudaMemsetAsync(c->d_deadq.p, 0xff, np * 8, st));   // DEAD_NONE
         }
@@ -1029,7 +1031,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
         k_pack_rows<<<nblk(NA * 32, 256), 256, 0, st>>>(din, P, c->d_subs.as<SubBucket>(), c->d_subincl.as<int32_t>(), row_of, NA,
                                                        c->d_donor.as<unsigned long long>(), c->d_segpl.as<uint32_t>(), c->d_cdr3w.as<uint32_t>(), c->d_rowstore.as<uint4>(),
                                                        c->d_aux.as<int32_t>(), c->d_m_row.as<int32_t>(), c->d_m_sub.as<int32_t>(),
-                                                       c->tags_on ? c->d_tagq.as<unsigned long long>() : nullptr);
+                                                       c->tags_on ? c->d_tagq.as<unsigned long long>() : nullptr,
+                                                       c->tags_on ? c->d_donq.as<unsigned long long>() : nullptr);
         c->stats.kernel_launches += 2;
         c->stats.kernel_launches++;
         mark("pack_rows");
@@ -1279,7 +1282,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
     if (rc) return rc;
     CK(cudaGetLastError());
     c->stats.two_cell_deleted = (int64_t)c->h_ctr->n_two_cell;
-    c->stats.stage1_ref_kills = (int64_t)c->h_ctr->n_s1_kill;
+    c->stats.stage1_ref_kills = (int64_t)(c->h_ctr->n_s1_kill - c->h_ctr->n_s1_donor);
+    c->stats.stage1_donor_kills = (int64_t)c->h_ctr->n_s1_donor;
     c->stats.stage2_two_ref = (int64_t)c->h_ctr->n_two_ref;
     c->stats.stage2_memo_dead = (int64_t)c->h_ctr->n_memo_dead;
     c->stats.stage2_degr_dead = (int64_t)c->h_ctr->n_degr_dead;

@@ -194,7 +194,7 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
                             const uint32_t* __restrict__ row_of, int64_t n_active, const unsigned long long* __restrict__ donor_mask,
                             const uint32_t* __restrict__ segpl, uint32_t* __restrict__ cdr3w, uint4* __restrict__ rowstore,
                             int32_t* __restrict__ aux, int32_t* __restrict__ rowq, int32_t* __restrict__ subq,
-                            unsigned long long* __restrict__ tagq) {
+                            unsigned long long* __restrict__ tagq, unsigned long long* __restrict__ donq) {
     const int lane = threadIdx.x & 31;
     const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= n_active) return;
@@ -449,7 +449,10 @@ __global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__
         a[AX_CHH] = ch;
         a[AX_CHL] = cl;
         a[AX_PAD1] = a[AX_PAD2] = a[AX_PAD3] = 0;
-        if (tagq) tagq[q] = (flags & F_SLOWMASK) ? TAG_SLOW : make_ref_tag(a[AX_VSH], a[AX_VSL], a[AX_JSH], a[AX_JSL]);
+        if (tagq) {
+            tagq[q] = (flags & F_SLOWMASK) ? TAG_SLOW : make_ref_tag(a[AX_VSH], a[AX_VSL], a[AX_JSH], a[AX_JSL]);
+            donq[q] = P.mix_donors ? 0ull : dmask;   // join_one.rs:301-323 only rejects when donors are not mixed
+        }
     }
     __syncwarp();
     if (lane < AUX_INTS / 4) reinterpret_cast<uint4*>(aux + q * AUX_INTS)[lane] = reinterpret_cast<const uint4*>(a)[lane];

@@ -45,9 +45,12 @@ __device__ __forceinline__ int cdr3_dist(const uint32_t* rl, const uint32_t* rh,
 
 // MODE bits (compile time):
 //   S1_RUNI   one warp vote per column when the thread's 8 rows and the column carry one class label
-//   S1_TAGS   reference-set tags staged next to the labels; after the pair loop of a half tile the hit list is compacted in
-//             place, dropping hits one of whose rows is known (from an earlier round's stage 2a) to fail the degradation test
-//             of join_one.rs:434-440 against the other row's reference set — the decision stage 2a would take from its memo
+//   S1_TAGS   per-row tags staged next to the labels; after the pair loop of a half tile the hit list is compacted in place,
+//             dropping hits that join_one is known to reject without looking at the sequences:
+//             * one row is known (from an earlier round's stage 2a) to fail the degradation test of join_one.rs:434-440
+//               against the other row's reference set — the decision stage 2a would take from its memo;
+//             * the two exact subclonotypes come from different donor sets (join_one.rs:301-323; donq is 0 for rows without a
+//               donor and for every row under MIX_DONORS).  That test precedes everything that can panic in join_one.
 constexpr int S1_RUNI = 1, S1_TAGS = 2;
 
 template <int W1, int MODE>
@@ -56,11 +59,12 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
                                                        const int32_t* __restrict__ blk_lab, uint2* __restrict__ cand,
                                                        unsigned long long cand_cap, Counters* __restrict__ ctr,
                                                        unsigned long long* __restrict__ unit_cand,
-                                                       const unsigned long long* __restrict__ tagq, const unsigned long long* __restrict__ deadq) {
+                                                       const unsigned long long* __restrict__ tagq, const unsigned long long* __restrict__ deadq,
+                                                       const unsigned long long* __restrict__ donq) {
     constexpr bool RUNI = (MODE & S1_RUNI) != 0, TAGS = (MODE & S1_TAGS) != 0;
     constexpr int NP = 2 * W1;            // plane-words per row
     constexpr int TAG0 = (NP + 1) * TILE; // word offset of the staged reference-set tags (uint64 x TILE), then the dead tags
-    constexpr int SLOT = (NP + 1 + (TAGS ? 4 : 0)) * TILE;   // words per staged tile (planes + labels [+ tags + dead tags])
+    constexpr int SLOT = (NP + 1 + (TAGS ? 6 : 0)) * TILE;   // words per staged tile (planes + labels [+ tags + dead tags + donor sets])
     __shared__ __align__(16) uint32_t s_row[SLOT];
     __shared__ __align__(16) uint32_t s_col[2][SLOT];
     __shared__ __align__(8) uint64_t s_bar[3];
@@ -112,13 +116,14 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
         const int r0 = blk * TILE;
         const int cnt = min(TILE, sb.npad - r0);  // npad is a multiple of 4
         const uint32_t bytes = (uint32_t)cnt * 4u;
-        mbar_expect_tx(bar, bytes * (NP + 1 + (TAGS ? 4 : 0)));
+        mbar_expect_tx(bar, bytes * (NP + 1 + (TAGS ? 6 : 0)));
 #pragma unroll
         for (int pw = 0; pw < NP; pw++) tma_load_1d(dst + pw * TILE, base + (int64_t)pw * sb.npad + r0, bytes, bar);
         tma_load_1d(dst + NP * TILE, labq + sb.q0 + r0, bytes, bar);   // q0 is a multiple of 4
         if (TAGS) {
             tma_load_1d(dst + TAG0, tagq + sb.q0 + r0, bytes * 2, bar);
             tma_load_1d(dst + TAG0 + 2 * TILE, deadq + sb.q0 + r0, bytes * 2, bar);
+            tma_load_1d(dst + TAG0 + 4 * TILE, donq + sb.q0 + r0, bytes * 2, bar);
         }
     };
     if (tid == 0) {
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
     const int row_lim = min(sb.n - rb * TILE, t.row_hi);  // valid local rows are row_lo <= r < row_lim
     const int maxcd = sb.maxcd;
     unsigned long long evaluated = 0, killed = 0;   // thread 0 only
+    unsigned int donor_kills = 0;                    // per thread
 
     for (int it = 0; it < ncb; it++) {
         const int cb = s_cbs[it];
@@ -229,7 +235,10 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
                         if (h < nh0) {
                             v = s_hits[h];
                             const int r = v >> 7, c = v & 127;
-                            keep = !(rt[TILE + r] == ct[c] || ct[TILE + c] == rt[r]);
+                            const unsigned long long dr = rt[2 * TILE + r], dc = ct[2 * TILE + c];
+                            const bool donors = dr != 0 && dc != 0 && dr != dc;
+                            keep = !(donors || rt[TILE + r] == ct[c] || ct[TILE + c] == rt[r]);
+                            donor_kills += donors;
                         }
                         __syncthreads();   // entries [b0, b0 + 256) are in registers; kept ones land below b0 + 256
                         if (keep) s_hits[atomicAdd(&s_nkeep, 1u)] = v;
@@ -284,6 +293,11 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
     if (tid == 0) {
         atomicAdd(&ctr->pairs_eval, evaluated);
         if (killed) atomicAdd(&ctr->n_s1_kill, killed);
+    }
+    if (TAGS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) donor_kills += __shfl_xor_sync(0xffffffffu, donor_kills, o);
+        if ((tid & 31) == 0 && donor_kills) atomicAdd(&ctr->n_s1_donor, (unsigned long long)donor_kills);
     }
 }
 

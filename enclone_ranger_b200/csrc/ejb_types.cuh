@@ -145,7 +145,8 @@ struct Counters {       // device-side counters, one instance per context
     unsigned long long n_cand, n_slow, n_surv, n_pass, n_newkeys, pairs_eval, n_forest, n_alive;
     unsigned long long n_two_cell, n_errflag_range, n_errflag_panic, overflow, n_slow_total, n_surv_total, n_pass_total;
     unsigned long long p1_unique, s2_work;
-    unsigned long long n_s1_kill;     // stage-1 hits dropped because one row is known dead against the other's reference set
+    unsigned long long n_s1_kill;     // stage-1 hits dropped: known dead against the other's reference set, or different donor sets
+    unsigned long long n_s1_donor;    // ... of which for the donor sets
     unsigned long long n_two_ref;     // stage-2a candidates with two reference sets (filter mode)
     unsigned long long n_memo_dead;   // ... of which rejected on memoised totals (phase 0)
     unsigned long long n_degr_dead;   // ... of which rejected by the degradation test on freshly computed totals

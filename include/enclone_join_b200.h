@@ -206,6 +206,7 @@ typedef struct ejb_stats {
     int64_t stage2_two_ref;     /* stage-2a candidates with two reference sets                    */
     int64_t stage2_memo_dead;   /* ... rejected on memoised totals                                */
     int64_t stage2_degr_dead;   /* ... rejected by the degradation test on computed totals        */
+    int64_t stage1_donor_kills; /* CDR3-close pairs dropped in stage 1: different donor sets (join_one.rs:301-323) */
 } ejb_stats;
 
 /*

@@ -58,7 +58,7 @@ pub mod sys {
         pub launches: [i64; 3],       // stage1_launches, stage2a_launches, overflow_retries
         pub ms_device_total: f64,
         pub ms_total: f64,
-        pub two_ref: [i64; 4],        // stage1_ref_kills, stage2_two_ref, stage2_memo_dead, stage2_degr_dead
+        pub two_ref: [i64; 5],        // stage1_ref_kills, stage2_two_ref, stage2_memo_dead, stage2_degr_dead, stage1_donor_kills
     }
 
     #[repr(C)]

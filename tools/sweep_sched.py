@@ -14,13 +14,13 @@ p = E.default_params(bool(rep.config.is_bcr))
 rep.close()
 ctx = E.JoinContext()
 ctx.upload(p, inp)
-for first, growth in ((1, 8), (1, 12), (1, 16), (1, 32), (2, 12), (1, 6), (1, 8)):
+for first, growth in ((1, 8), (2, 12), (1, 16), (2, 16), (4, 16), (1, 8)):
     os.environ["EJB_FIRST_UNIT"] = str(first)
     os.environ["EJB_GROWTH"] = str(growth)
     ctx.run()
     ss = [ctx.run() for _ in range(3)]
     s = min(ss, key=lambda x: x["ms_device_total"])
     keys = ("ms_device_total", "ms_pack", "ms_stage1", "ms_stage2", "ms_stage2a", "ms_forest", "ms_finalize", "pairs_evaluated", "stage1_candidates",
-            "stage1_ref_kills", "stage2_survivors", "pass_edges", "rounds", "kernel_launches")
+            "stage1_ref_kills", "stage1_donor_kills", "stage2_survivors", "pass_edges", "rounds", "kernel_launches")
     print(json.dumps(dict({"first": first, "growth": growth}, **{k: (round(s[k], 3) if isinstance(s[k], float) else int(s[k])) for k in keys})), flush=True)
 ctx.close()

@@ -27,7 +27,7 @@ for r, part in enumerate(parts):
     s = ctx.run()
     res.append((s["ms_device_total"], r))
     print(json.dumps({"rank": r, "rows": len(part.rows), "device_ms": round(s["ms_device_total"], 2), "cands": int(s["stage1_candidates"]),
-                      "kills": int(s["stage1_ref_kills"]), "two_ref": int(s["stage2_two_ref"]), "memo_dead": int(s["stage2_memo_dead"]), "degr_dead": int(s["stage2_degr_dead"]),
+                      "kills": int(s["stage1_ref_kills"]), "donor_kills": int(s["stage1_donor_kills"]), "two_ref": int(s["stage2_two_ref"]), "memo_dead": int(s["stage2_memo_dead"]), "degr_dead": int(s["stage2_degr_dead"]),
                       "surv": int(s["stage2_survivors"]), "pass": int(s["pass_edges"]), "ms_stage2a": round(s["ms_stage2a"], 2), "rounds": int(s["rounds"]),
                       "pairs_eval": int(s["pairs_evaluated"]), "pairs": int(s["pairs_scored"])}), flush=True)
 res.sort(reverse=True)
