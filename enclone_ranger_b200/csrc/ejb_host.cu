@@ -1084,7 +1084,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
         const double target_pass = std::max(4096.0, (double)c->cand_cap / 64.0);   // pass edges one unit should not exceed by much
         int stalls = 0;
         // developer knobs for the unit schedule (first unit, growth factor of the rows done so far)
-        long long first_unit = 1, growth = 8;   // measured on configs[1] (1M cells): 8/4 -> 10.5 ms, 2/8 -> 9.4 ms, 1/8 -> 9.2 ms
+        long long first_unit = 2, growth = 12;   // measured on configs[1] (1M cells): 8/4 -> 10.5 ms, 1/8 -> 8.95 ms, 2/12 -> 8.74 ms, 4/16 -> 8.75 ms
         if (const char* e = getenv("EJB_FIRST_UNIT")) first_unit = std::max(1ll, atoll(e));
         if (const char* e = getenv("EJB_GROWTH")) growth = std::max(1ll, atoll(e));
         while (!live.empty()) {

@@ -210,13 +210,28 @@ def _refsets_compatible(inp, ra, rb, max_degradation):
     return True
 
 
+def _donor_masks(inp, rows):
+    """64-bit donor-set mask of the exact subclonotype of each given row (join_one.rs:301-315)."""
+    off = inp.a["ex_cell_off"]
+    don = inp.a["cell_donor"]
+    ex = inp.a["row_exact"][rows]
+    out = np.zeros(len(rows), dtype=np.uint64)
+    for i, e in enumerate(ex):
+        d = don[off[e]:off[e + 1]]
+        d = d[d >= 0]
+        if len(d):
+            out[i] = np.bitwise_or.reduce(np.uint64(1) << d.astype(np.uint64))
+    return out
+
+
 def probe_live_fractions(inp, ctx, params, min_rows=4096, sample=256):
     """Estimate, for every large sub-bucket, the fraction of its pairs that reach the full stage-2 scoring and do NOT join
     (two big clones on one V/J gene pair with similar junctions, or on two alleles of one gene): such pairs cost ~W_CROSS
     times a CDR3 comparison each and decide how evenly ranks are loaded, but nothing short of the join itself tells them
     from pairs inside one clone.  So the join is run on a SAMPLE: `sample` evenly spaced rows of each sub-bucket with at
     least `min_rows` rows go through `ctx` (one small join for all of them), and a sampled pair counts as live when it is
-    CDR3-close (join_one.rs:216-234), ends in different clonotypes and its reference sets are equal or compatible.
+    CDR3-close (join_one.rs:216-234), ends in different clonotypes, its reference sets are equal or compatible and its
+    donor sets do not already reject it (join_one.rs:301-323; stage 1 drops those pairs for free).
     Returns {sub-bucket index (as in partition_work): fraction}."""
     two, sub_of, n_sub = _sub_bucket_table(inp)
     cnt = np.bincount(sub_of, minlength=n_sub)
@@ -256,6 +271,9 @@ def probe_live_fractions(inp, ctx, params, min_rows=4096, sample=256):
         close = (cd.astype(np.float64) / T <= thr) if params.is_bcr else (cd == 0)
         lab = lab_of[r]
         live = close & (lab[:, None] != lab[None, :])
+        if not params.mix_donors:
+            dm = _donor_masks(inp, r)
+            live &= ~((dm[:, None] != 0) & (dm[None, :] != 0) & (dm[:, None] != dm[None, :]))
         refs = np.concatenate([vs[r], js[r]], axis=1)
         u, inv = np.unique(refs, axis=0, return_inverse=True)
         inv = inv.reshape(-1)
