@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=None, help="override the repertoire size (debug only; the number is then not the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="N>1 debug: rank 0 also joins the whole repertoire on its own GPU and compares the merged edge list and EquivRel")
+    ap.add_argument("--split-above", type=float, default=0.5, help="N>1: split sub-buckets whose cost exceeds this fraction of a rank's share")
     ap.add_argument("--ascii", action="store_true", help="hand every contig over as ASCII (info[k].tigs) instead of 2-bit packed (tigsp)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -225,12 +227,13 @@ def main():
             probe_ctx = E.JoinContext(device=local_rank)
             live = multi.probe_live_fractions(full, probe_ctx, E.default_params(True))
             probe_ctx.close()
-            wparts, split_rows = multi.partition_work(full, world, live_fraction=live)
+            wparts, split_rows = multi.partition_work(full, world, live_fraction=live, split_above=args.split_above)
             ncells_row = multi.ncells_per_row(full)
             for wp in wparts:
                 sub, _ = full.subset_rows(wp.rows)
                 parts.append((sub, wp.rows, wp.roles))
             n_split_rows = int(split_rows.sum())
+            full_keep = full.to_packed() if args.verify else None
             del full
         inp, my_rows, my_roles = multi.scatter_parts(parts, dev)
         del parts
@@ -352,6 +355,8 @@ def main():
         per_rank = None
 
     # ---------------- end-to-end arm: host buffers through ejb_join ----------------
+    last_merged = {}
+
     def step_e2e():
         res = ctx.join(params, inp, copy=False)   # zero-copy views into the library's pinned result arena
         if world > 1:
@@ -361,7 +366,8 @@ def main():
             merged = gather_keys(key, aux)
             if rank == 0:   # raw_joins of the whole repertoire + the EquivRel finish_join returns
                 k = merged.cpu().numpy()
-                E.equiv_replay(full_rows, (k >> 32).astype(np.int32), (k & 0xffffffff).astype(np.int32), row_exact_full)
+                last_merged["k"] = k
+                last_merged["eq"] = E.equiv_replay(full_rows, (k >> 32).astype(np.int32), (k & 0xffffffff).astype(np.int32), row_exact_full)
         return res
 
     step_e2e()
@@ -377,6 +383,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_stats = res.stats
+    if args.verify and world > 1 and rank == 0:
+        vctx = E.JoinContext(device=local_rank)
+        ref = vctx.join(params, full_keep)
+        kref = ref.edge_k1.astype(np.int64) << 32 | ref.edge_k2.astype(np.int64)
+        eq, lab = last_merged["eq"]
+        ok = bool(np.array_equal(kref, last_merged["k"]) and np.array_equal(eq.x, ref.eq_x) and np.array_equal(eq.y, ref.eq_y) and np.array_equal(eq.z, ref.eq_z)
+                  and np.array_equal(lab, ref.labels))
+        print(f"[verify] {world}-rank merged result == single-GPU join of the whole repertoire: {ok} ({len(kref)} edges, {n_split_rows} rows in split sub-buckets)",
+              file=sys.stderr, flush=True)
+        vctx.close()
+        if not ok:
+            raise SystemExit("verification failed")
 
     if rank == 0:
         p1_avg, p2_avg, dom_pairs, packed_bytes = algorithmic_popc(inp_ascii)
