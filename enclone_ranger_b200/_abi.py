@@ -252,7 +252,7 @@ def load_join():
             raise RuntimeError(
                 f"{LIB_JOIN} is missing — the CUDA extension must be built "
                 "(`python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
-        L = C.CDLL(LIB_JOIN)
+        L = C.CDLL(os.environ.get("EJB_LIB", LIB_JOIN))   # EJB_LIB: developer override to A/B a differently built library
         L.ejb_abi_version.restype = C.c_int
         L.ejb_abi_sizes.argtypes = [_i64p]
         L.ejb_abi_sizes.restype = None
@@ -280,6 +280,8 @@ def load_join():
         L.ejb_p1_batch.restype = C.c_int
         L.ejb_measure_peaks.argtypes = [C.c_void_p, _f64p, _f64p, _f64p]
         L.ejb_measure_peaks.restype = C.c_int
+        L.ejb_set_input_arena.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.ejb_set_input_arena.restype = C.c_int
         L.ejb_set_row_roles.argtypes = [C.c_void_p, _u8p, C.c_int64]
         L.ejb_set_row_roles.restype = C.c_int
         L.ejb_forest_merge.argtypes = [C.c_int32, _i32p, _i32p, C.c_int64, _u8p]

@@ -105,6 +105,9 @@ struct ejb_ctx {
     int64_t h2d_bytes = 0;
     double ms_h2d = 0;
     int64_t n_canon_segs = 0;   // distinct seg contents (canonical ids are 0 .. n_canon_segs-1)
+    const char* arena_base = nullptr;   // ejb_set_input_arena: one host allocation holding (most of) the input arrays
+    size_t arena_bytes = 0;
+    DevBuf d_arena;
     DevBuf d_roles, d_subroles; // ejb_set_row_roles (per canonical row), per-sub-bucket summary
     std::vector<uint8_t> roles; // host copy; in force for every run until cleared
     bool have_roles = false;    // roles are in force for the current run
@@ -195,6 +198,14 @@ const std::vector<dd_t>& sr_table_host() {
 
 template <class T>
 int upload_array(ejb_ctx* c, const T* src, int64_t n, const T** dst) {
+    // inside the caller's arena: already on its way with the single arena copy
+    if (n > 0 && src && c->arena_base && c->d_arena.p) {
+        const char* p = reinterpret_cast<const char*>(src);
+        if (p >= c->arena_base && p + (size_t)n * sizeof(T) <= c->arena_base + c->arena_bytes) {
+            *dst = reinterpret_cast<const T*>(c->d_arena.as<char>() + (p - c->arena_base));
+            return EJB_OK;
+        }
+    }
     if (c->in_used == c->in_bufs.size()) c->in_bufs.emplace_back();
     DevBuf& b = c->in_bufs[c->in_used++];
     const size_t bytes = (size_t)std::max<int64_t>(n, 1) * sizeof(T);
@@ -476,6 +487,17 @@ int ejb_set_shard(ejb_ctx* c, int rank, int world) {
     return EJB_OK;
 }
 
+int ejb_set_input_arena(ejb_ctx* c, const void* base, uint64_t bytes) {
+    if (!c) return EJB_ERR_INVALID;
+    c->arena_base = nullptr;
+    c->arena_bytes = 0;
+    if (!base || bytes == 0) return EJB_OK;
+    if ((reinterpret_cast<uintptr_t>(base) & 255u) != 0) return fail(c, EJB_ERR_INVALID, "input arena must be 256-byte aligned");
+    c->arena_base = reinterpret_cast<const char*>(base);
+    c->arena_bytes = (size_t)bytes;
+    return EJB_OK;
+}
+
 int ejb_set_capacity(ejb_ctx* c, unsigned long long cand_cap, unsigned long long pair_budget) {
     if (!c) return EJB_ERR_INVALID;
     if (cand_cap) {
@@ -507,6 +529,11 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     d.n_tig_bytes = in->n_tig_bytes; d.n_cdr3_bytes = in->n_cdr3_bytes; d.n_amino_bytes = in->n_amino_bytes;
     d.n_tig2_words = in->row_tig2_off ? in->n_tig2_words : 0;
     const int64_t N = in->n_rows;
+    if (c->arena_base) {   // one DMA for everything the caller keeps in its arena
+        CK(c->d_arena.ensure(c->arena_bytes + 256));
+        CK(cudaMemcpyAsync(c->d_arena.p, c->arena_base, c->arena_bytes, cudaMemcpyHostToDevice, c->up_stream[c->up_next++ % ejb_ctx::N_UP]));
+        c->h2d_bytes += (int64_t)c->arena_bytes;
+    }
     // host-side: seg / ref byte totals need the last offset
     if (in->n_segs > 0 && !in->seg_off) return fail(c, EJB_ERR_INVALID, "seg_off is null");
     if (in->n_refs > 0 && !in->ref_off) return fail(c, EJB_ERR_INVALID, "ref_off is null");

@@ -190,7 +190,10 @@ __device__ __forceinline__ uint32_t plane_bits(const uint32_t* __restrict__ pl, 
 //     coordinates, compare mask, reference-difference bitmap d, optional gap plane
 //   * the aux record (AUX_INTS ints) and rowq / subq
 // ------------------------------------------------------------------------------------------------
-__global__ void k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__ subs, const int32_t* __restrict__ sub_incl,
+#ifndef PACK_MINB
+#define PACK_MINB 1
+#endif
+__global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__ subs, const int32_t* __restrict__ sub_incl,
                             const uint32_t* __restrict__ row_of, int64_t n_active, const unsigned long long* __restrict__ donor_mask,
                             const uint32_t* __restrict__ segpl, uint32_t* __restrict__ cdr3w, uint4* __restrict__ rowstore,
                             int32_t* __restrict__ aux, int32_t* __restrict__ rowq, int32_t* __restrict__ subq,

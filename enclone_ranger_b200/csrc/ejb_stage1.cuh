@@ -53,8 +53,18 @@ __device__ __forceinline__ int cdr3_dist(const uint32_t* rl, const uint32_t* rh,
 //               donor and for every row under MIX_DONORS).  That test precedes everything that can panic in join_one.
 constexpr int S1_RUNI = 1, S1_TAGS = 2;
 
+// S1_NOVOTE: no per-row warp vote before the distance (the column-level vote S1_RUNI already skips uniform 16 x 16 groups)
+#ifndef S1_NOVOTE
+#define S1_NOVOTE 0
+#endif
+#ifndef S1_MINB2
+#define S1_MINB2 4
+#endif
+#ifndef S1_MINB3
+#define S1_MINB3 3
+#endif
 template <int W1, int MODE>
-__global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2)) k_stage1(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, int n_tasks,
+__global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) ? S1_MINB3 : 2)) k_stage1(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, int n_tasks,
                                                        const uint32_t* __restrict__ cdr3w, const int32_t* __restrict__ labq,
                                                        const int32_t* __restrict__ blk_lab, uint2* __restrict__ cand,
                                                        unsigned long long cand_cap, Counters* __restrict__ ctr,
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
                         // class test first (join_core.rs:32): a warp whose 32 pairs are all already connected skips the
                         // distance entirely — the common case inside a clone once its first rows have been processed
                         const bool need = rlab[i] != clab;
-                        if (__any_sync(0xffffffffu, need)) {
+                        if (S1_NOVOTE || __any_sync(0xffffffffu, need)) {
                             const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
                             if (need && cd <= maxcd) {
                                 const unsigned int h = atomicAdd(&s_nhits, 1u);
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? 4 : ((W1 <= 3) ? 3 : 2
                     for (int i = 0; i < 8; i++) {
                         const int r = i * 16 + ty;
                         const bool need = r >= row_lo && r < row_lim && c < col_lim && (!diag || r < c) && rlab[i] != clab;
-                        if (__any_sync(0xffffffffu, need)) {
+                        if (S1_NOVOTE || __any_sync(0xffffffffu, need)) {
                             const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
                             if (need && cd <= maxcd) {
                                 const unsigned int h = atomicAdd(&s_nhits, 1u);

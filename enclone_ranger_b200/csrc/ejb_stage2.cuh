@@ -348,7 +348,10 @@ __device__ __forceinline__ void s2_planes(const S2Ctx& X, const CandInfo& ci, in
 //   phase 2: one lane per candidate runs the scalar integer tests and emits the survivor.
 // A CTA takes CONTIGUOUS chunks of the candidate list: consecutive candidates come from one stage-1 tile
 // (<= 128 + 64 distinct rows), so their row records are re-read from L1 instead of L2.
-__global__ void __launch_bounds__(256, 3) k_stage2a(S2Ctx X, const uint2* __restrict__ cand, const uint32_t* __restrict__ cand_slot,
+#ifndef S2A_MINB
+#define S2A_MINB 3
+#endif
+__global__ void __launch_bounds__(256, S2A_MINB) k_stage2a(S2Ctx X, const uint2* __restrict__ cand, const uint32_t* __restrict__ cand_slot,
                                                     const unsigned long long* __restrict__ n_cand_p, unsigned long long cand_cap) {
     constexpr unsigned long long S2A_CHUNK = 2048;
     __shared__ unsigned long long s_chunk;
@@ -625,7 +628,10 @@ __device__ __forceinline__ bool bc_meet(const S2Ctx& X, int e1, int e2) {
 }
 
 // Stage 2b: one thread per survivor.  Emits pass edges (filter mode) or EdgeTuples (tuple mode).
-__global__ void __launch_bounds__(256) k_stage2b(S2Ctx X, const unsigned long long* __restrict__ n_surv_p, unsigned long long* __restrict__ pass_w,
+#ifndef S2B_MINB
+#define S2B_MINB 1
+#endif
+__global__ void __launch_bounds__(256, S2B_MINB) k_stage2b(S2Ctx X, const unsigned long long* __restrict__ n_surv_p, unsigned long long* __restrict__ pass_w,
                                                  unsigned long long pass_cap, EdgeTuple* __restrict__ tuples) {
     const unsigned long long n_surv = min(*n_surv_p, X.surv_cap);
     const DevIn& in = X.in;

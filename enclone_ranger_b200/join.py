@@ -167,6 +167,11 @@ class JoinContext:
         self.L.ejb_result_free(self.h, C.byref(r))
         return out
 
+    def set_input_arena(self, address, nbytes):
+        """Declare one (page-locked) host allocation that holds the input arrays of the following uploads: it is copied
+        with a single DMA (ejb_set_input_arena).  address=None clears."""
+        self._ck(self.L.ejb_set_input_arena(self.h, C.c_void_p(address) if address else None, int(nbytes) if address else 0))
+
     def set_row_roles(self, roles):
         """Row roles of a sub-bucket split over several contexts (ejb_set_row_roles): uint8 per row of the input the next
         runs work on (bit 0 column-only, bit 1 split sub-bucket); None clears them."""

@@ -283,6 +283,14 @@ int ejb_measure_peaks(ejb_ctx* ctx, double* popc_per_s, double* lop3_per_s, doub
  * caller concatenates the per-rank edge lists, sorts them by (k1, k2) and calls ejb_equiv_replay. */
 int ejb_set_shard(ejb_ctx* ctx, int rank, int world);
 
+/* Input arena.  Every host->device copy pays a fixed setup cost (about 0.1 ms on PCIe Gen5 here), so ~36 separate input
+ * arrays upload at half the bandwidth of one large copy.  A caller that flattens its records into ONE page-locked
+ * allocation (the Rust shim does: it owns every buffer it passes) declares it here; ejb_upload / ejb_join then move the
+ * whole arena with a single DMA and resolve every ejb_input array that lies inside it by offset.  Arrays outside the
+ * arena are copied one by one as before.  base must be 256-byte aligned and readable for `bytes` bytes; the setting stays
+ * in force until cleared with base == NULL.  Keep each array aligned to its element size inside the arena.            */
+int ejb_set_input_arena(ejb_ctx* ctx, const void* base, uint64_t bytes);
+
 /* Work-buffer sizing: cand_cap = capacity (entries) of the candidate / survivor / pass-edge
  * buffers; pair_budget = upper bound on the pairs one scheduler round evaluates.  0 keeps the
  * current value.  Defaults: 2^26 and 2^32 (env EJB_CAND_CAP / EJB_PAIR_BUDGET).                */

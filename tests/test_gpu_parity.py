@@ -316,3 +316,34 @@ def test_probe_live_fractions(gpu_ctx):
         roles = part.roles if part.roles is not None else np.zeros(len(part.rows), dtype=np.uint8)
         first[part.rows[(roles & multi.ROLE_COLUMN_ONLY) == 0]] += 1
     assert first.max() == 1
+
+
+def test_input_arena_single_copy_upload(gpu_ctx):
+    """ejb_set_input_arena: arrays inside the declared arena are uploaded with one copy and resolved by offset; arrays
+    outside it (here: cdr3_bytes) go one by one.  Same result, fewer bytes in separate copies."""
+    rep = E.generate(1, n_cells=30000, seed=51)
+    inp = rep.to_join_input().to_packed()
+    p = E.default_params(True)
+    want = gpu_ctx.join(p, inp)
+    total = sum((a.nbytes + 255) & ~255 for a in inp.a.values())
+    arena = np.zeros(total + 512, dtype=np.uint8)
+    off0 = (-arena.ctypes.data) & 255
+    off, views = off0, {}
+    for name, a in inp.a.items():
+        if name == "cdr3_bytes":
+            views[name] = a
+            continue
+        v = arena[off:off + a.nbytes].view(a.dtype).reshape(a.shape)
+        v[...] = a
+        views[name] = v
+        off += (a.nbytes + 255) & ~255
+    inp2 = E.JoinInput(**views)
+    try:
+        gpu_ctx.set_input_arena(arena.ctypes.data + off0, off - off0)
+        got = gpu_ctx.join(p, inp2)
+        again = gpu_ctx.join(p, inp)          # an input that lives outside the arena still works while it is set
+    finally:
+        gpu_ctx.set_input_arena(None, 0)
+    for f in ("edge_k1", "edge_k2", "edge_cd", "edge_shares", "edge_indeps", "edge_score", "labels", "eq_x", "eq_y", "eq_z"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+        assert np.array_equal(getattr(again, f), getattr(want, f)), f
