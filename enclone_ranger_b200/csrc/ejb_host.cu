@@ -1409,8 +1409,8 @@ int ejb_download(ejb_ctx* c, ejb_result* out) {
     const double t1 = now_ms();
     if (N > 0) {   // sharded contexts: the state of the local edges only
         ejbhost::EquivRel eq((int32_t)N, ex, ey, ez);
-        for (int64_t i = 0; i < E; i++) eq.join(k1[i], k2[i]);
-        ejbhost::finish_join_merge(eq, row_exact, N);
+        ejbhost::replay_edges(eq, k1, k2, E);
+        ejbhost::finish_join_merge(eq, row_exact, N, c->din.n_exacts);
     }
     c->stats.ms_replay = now_ms() - t1;
     CK(cudaStreamSynchronize(st));
@@ -1566,11 +1566,10 @@ int ejb_measure_peaks(ejb_ctx* c, double* popc_per_s, double* lop3_per_s, double
 int ejb_equiv_replay(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64_t n_edges, const int32_t* row_exact, int32_t* x, int32_t* y, int32_t* z,
                      int32_t* labels) {
     if (n_rows < 0 || n_edges < 0) return EJB_ERR_INVALID;
-    ejbhost::EquivRel eq(n_rows);
-    for (int64_t i = 0; i < n_edges; i++) {
+    for (int64_t i = 0; i < n_edges; i++)
         if (k1[i] < 0 || k1[i] >= n_rows || k2[i] < 0 || k2[i] >= n_rows) return EJB_ERR_INVALID;
-        eq.join(k1[i], k2[i]);
-    }
+    ejbhost::EquivRel eq(n_rows);
+    ejbhost::replay_edges(eq, k1, k2, n_edges);
     if (row_exact) ejbhost::finish_join_merge(eq, row_exact, n_rows);
     if (x) memcpy(x, eq.x, (size_t)n_rows * 4);
     if (y) memcpy(y, eq.y, (size_t)n_rows * 4);

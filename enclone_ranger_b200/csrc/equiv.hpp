@@ -48,11 +48,17 @@ struct EquivRel {
 // note that the joined values are CLASS IDS used as element ids (join2.rs:81).
 // Only clonotype_ids owning two or more rows can cause a join, so the sort is restricted to those
 // rows (same join sequence as sorting everything: ids ascending, class ids ascending inside an id).
-inline void finish_join_merge(EquivRel& eq, const int32_t* row_exact, int64_t n_rows) {
-    int32_t max_id = -1;
-    for (int64_t i = 0; i < n_rows; i++) max_id = std::max(max_id, row_exact[i]);
-    std::vector<int32_t> cnt((size_t)max_id + 2, 0);
-    for (int64_t i = 0; i < n_rows; i++) cnt[(size_t)row_exact[i]]++;
+inline void finish_join_merge(EquivRel& eq, const int32_t* row_exact, int64_t n_rows, int64_t n_exacts = -1) {
+    if (n_exacts < 0) {
+        int32_t max_id = -1;
+        for (int64_t i = 0; i < n_rows; i++) max_id = std::max(max_id, row_exact[i]);
+        n_exacts = (int64_t)max_id + 1;
+    }
+    std::vector<uint8_t> cnt((size_t)n_exacts + 1, 0);   // saturating at 2: all that matters
+    for (int64_t i = 0; i < n_rows; i++) {
+        uint8_t& c = cnt[(size_t)row_exact[i]];
+        if (c < 2) c++;
+    }
     std::vector<std::pair<int32_t, int32_t>> ox;
     for (int64_t i = 0; i < n_rows; i++)
         if (cnt[(size_t)row_exact[i]] >= 2) ox.emplace_back(row_exact[i], eq.class_id((int32_t)i));
@@ -63,6 +69,22 @@ inline void finish_join_merge(EquivRel& eq, const int32_t* row_exact, int64_t n_
         while (j < ox.size() && ox[j].first == ox[i].first) j++;
         for (size_t k = i; k + 1 < j; k++) eq.join(ox[k].second, ox[k + 1].second);
         i = j;
+    }
+}
+
+// Replay of an ordered edge list (join2.rs:45-54).  The walk is bound by the latency of the scattered x / y / z reads, so the
+// entries of the edges a few steps ahead are prefetched.
+inline void replay_edges(EquivRel& eq, const int32_t* k1, const int32_t* k2, int64_t n_edges) {
+    constexpr int64_t AHEAD = 12;
+    for (int64_t i = 0; i < n_edges; i++) {
+        if (i + AHEAD < n_edges) {
+            const int32_t a = k1[i + AHEAD], b = k2[i + AHEAD];
+            __builtin_prefetch(&eq.y[a]);
+            __builtin_prefetch(&eq.y[b]);
+            __builtin_prefetch(&eq.x[a], 1);
+            __builtin_prefetch(&eq.x[b], 1);
+        }
+        eq.join(k1[i], k2[i]);
     }
 }
 
