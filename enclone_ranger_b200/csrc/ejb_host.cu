@@ -883,6 +883,19 @@ extern "C" int ejb_run(ejb_ctx* c) {
     const uint32_t* row_of = c->d_vals2.as<uint32_t>();
     int n_subs = 0;
     if (NA > 0) {
+        // Work that only needs the raw input is queued first: it keeps the device busy while the host waits for the two small
+        // read-backs below and builds the sub-bucket table.
+        // per exact: donor masks + sorted barcode lists (the bucketer copies the masks into the row records)
+        CK(c->d_donor.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 8));
+        CK(c->d_bckeys.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
+        CK(c->d_bckeys2.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
+        k_exact_prep<<<nblk(din.n_exacts, 256), 256, 0, st>>>(din, c->d_donor.as<unsigned long long>(), c->d_bckeys.as<uint64_t>());
+        if (din.n_cells > 0) {
+            int rc2 = cub_sort_keys64(c, c->d_bckeys.as<uint64_t>(), c->d_bckeys2.as<uint64_t>(), din.n_cells);
+            if (rc2) return rc2;
+        }
+        CK(c->d_segpl.ensure((size_t)std::max<int64_t>(din.n_segs, 1) * 2 * SEGPL_WORDS * 4));
+        k_seg_planes<<<nblk(din.n_segs * 32, 256), 256, 0, st>>>(din, c->d_segpl.as<uint32_t>());
         CK(c->d_subhead.ensure((size_t)NA * 4));
         CK(c->d_subincl.ensure((size_t)NA * 4));
         k_subheads<<<nblk(NA, 256), 256, 0, st>>>(keys_sorted, NA, c->d_subhead.as<int32_t>());
@@ -1032,15 +1045,6 @@ extern "C" int ejb_run(ejb_ctx* c) {
         CK(cudaMemsetAsync(c->d_m_row.p, 0xff, np * 4, st));   // -1 = padding position
         CK(cudaMemsetAsync(c->d_labq.p, 0xff, np * 4, st));
         CK(cudaMemsetAsync(c->d_cdr3w.p, 0, (size_t)(s1 + 4) * 4, st));
-        // per exact: donor masks + sorted barcode lists (the bucketer copies the masks into the row records)
-        CK(c->d_donor.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 8));
-        CK(c->d_bckeys.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
-        CK(c->d_bckeys2.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
-        k_exact_prep<<<nblk(din.n_exacts, 256), 256, 0, st>>>(din, c->d_donor.as<unsigned long long>(), c->d_bckeys.as<uint64_t>());
-        if (din.n_cells > 0) {
-            int rc2 = cub_sort_keys64(c, c->d_bckeys.as<uint64_t>(), c->d_bckeys2.as<uint64_t>(), din.n_cells);
-            if (rc2) return rc2;
-        }
         CK(c->d_memo.ensure(np * 32));
         CK(cudaMemsetAsync(c->d_memo.p, 0, np * 32, st));
         c->s1_mode = S1_RUNI | S1_TAGS;
@@ -1052,8 +1056,6 @@ extern "C" int ejb_run(ejb_ctx* c) {
             CK(cudaMemsetAsync(c->d_tagq.p, 0xff, np * 8, st));    // padding positions: never part of a valid pair
             CK(cudaMemsetAsync(c->d_deadq.p, 0xff, np * 8, st));   // DEAD_NONE
         }
-        CK(c->d_segpl.ensure((size_t)std::max<int64_t>(din.n_segs, 1) * 2 * SEGPL_WORDS * 4));
-        k_seg_planes<<<nblk(din.n_segs * 32, 256), 256, 0, st>>>(din, c->d_segpl.as<uint32_t>());
         mark("tables+memsets+bcsort");
         k_pack_rows<<<nblk(NA * 32, 256), 256, 0, st>>>(din, P, c->d_subs.as<SubBucket>(), c->d_subincl.as<int32_t>(), row_of, NA,
                                                        c->d_donor.as<unsigned long long>(), c->d_segpl.as<uint32_t>(), c->d_cdr3w.as<uint32_t>(), c->d_rowstore.as<uint4>(),

@@ -24,7 +24,10 @@ namespace ejb {
 
 constexpr int TILE = 128;          // rows / cols of one stage-1 tile
 constexpr int S1_THREADS = 256;
-constexpr int S1_STRIP = 4;        // column tiles per CTA (row fragment stays in registers)
+#ifndef S1_STRIP_N
+#define S1_STRIP_N 4
+#endif
+constexpr int S1_STRIP = S1_STRIP_N;   // column tiles per CTA (row fragment stays in registers)
 constexpr int MAXW1 = 6;           // concatenated CDR3 (heavy+light) up to 192 nt on the fast path
 constexpr int MAXW4 = 8;           // contig up to 1024 nt on the stage-2 fast path
 constexpr int SR_NMAX = 3000;      // stirling2_ratio_table_double(3000), start.rs:344
