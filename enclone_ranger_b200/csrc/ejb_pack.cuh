@@ -191,7 +191,7 @@ __device__ __forceinline__ uint32_t plane_bits(const uint32_t* __restrict__ pl, 
 //   * the aux record (AUX_INTS ints) and rowq / subq
 // ------------------------------------------------------------------------------------------------
 #ifndef PACK_MINB
-#define PACK_MINB 5   // latency-bound: occupancy wins over spills (1: 2.6 ms prepare phase, 4: 1.97 ms, 5: 1.82 ms)
+#define PACK_MINB 8   // latency-bound: occupancy wins over spills (prepare phase: 1 -> 2.6 ms, 4 -> 1.97, 5 -> 1.82, 8 -> 1.72)
 #endif
 __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__ subs, const int32_t* __restrict__ sub_incl,
                             const uint32_t* __restrict__ row_of, int64_t n_active, const unsigned long long* __restrict__ donor_mask,
