@@ -116,7 +116,7 @@ struct ejb_ctx {
     DevBuf d_head, d_scan, d_keys, d_keys2, d_vals, d_vals2, d_cubtmp, d_subhead, d_subincl, d_subinfo;
     DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_aux;
     DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
-    DevBuf d_unitcand, d_qcut, d_subpass, d_segpl, d_memo, d_tagq, d_deadq, d_donq;
+    DevBuf d_unitcand, d_qcut, d_subpass, d_segpl, d_memo, d_tagq, d_deadq, d_donq, d_flagq, d_subdom;
     bool tags_on = false;      // reference-set tags in use (every canonical seg id < 65535)
     int s1_mode = S1_RUNI | S1_TAGS;   // stage-1 kernel variant (EJB_S1_MODE, developer knob)
     std::vector<unsigned int> h_subpass;
@@ -268,7 +268,7 @@ void launch_stage1_wm(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_ta
                                                                             c->d_labq.as<int32_t>(), c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(),
                                                                             c->cand_cap, c->d_ctr.as<Counters>(), c->d_unitcand.as<unsigned long long>(),
                                                                             c->d_tagq.as<unsigned long long>(), c->d_deadq.as<unsigned long long>(),
-                                                                            c->d_donq.as<unsigned long long>());
+                                                                            c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>());
 }
 template <int W1>
 void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks) {
@@ -672,6 +672,12 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     CK(zero_counter(c, offsetof(Counters, n_pass)));
     CK(zero_counter(c, offsetof(Counters, overflow)));
     CK(cudaEventRecord(rt.e0, c->stream));
+    if (c->tags_on && (c->s1_mode & S1_TAGS)) {
+        k_row_flags<<<nblk(c->n_pos, 256), 256, 0, c->stream>>>(c->d_m_sub.as<int32_t>(), c->d_m_row.as<int32_t>(), c->n_pos, c->d_subdom.as<SubDom>(),
+                                                               c->d_tagq.as<unsigned long long>(), c->d_deadq.as<unsigned long long>(),
+                                                               c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>());
+        c->stats.kernel_launches++;
+    }
     size_t off = 0;
     for (int w = 0; w <= MAXW1; w++) {
         if (tasks[w].empty()) continue;
@@ -1053,6 +1059,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
         if (c->tags_on) {
             CK(c->d_tagq.ensure(np * 8)); CK(c->d_deadq.ensure(np * 8)); CK(c->d_donq.ensure(np * 8));
             CK(cudaMemsetAsync(c->d_donq.p, 0, np * 8, st));       // padding positions
+            CK(c->d_flagq.ensure(np * 4));
+            CK(c->d_subdom.ensure((size_t)n_subs * sizeof(SubDom)));
             CK(cudaMemsetAsync(c->d_tagq.p, 0xff, np * 8, st));    // padding positions: never part of a valid pair
             CK(cudaMemsetAsync(c->d_deadq.p, 0xff, np * 8, st));   // DEAD_NONE
         }
@@ -1064,6 +1072,11 @@ extern "C" int ejb_run(ejb_ctx* c) {
                                                        c->tags_on ? c->d_donq.as<unsigned long long>() : nullptr);
         c->stats.kernel_launches += 2;
         c->stats.kernel_launches++;
+        if (c->tags_on) {
+            k_sub_dominant<<<nblk(n_subs, 128), 128, 0, st>>>(c->d_subs.as<SubBucket>(), n_subs, c->d_tagq.as<unsigned long long>(),
+                                                             c->d_donq.as<unsigned long long>(), c->d_subdom.as<SubDom>());
+            c->stats.kernel_launches++;
+        }
         mark("pack_rows");
         CK(cudaGetLastError());
     }

@@ -131,6 +131,52 @@ __global__ void k_subroles(const uint8_t* __restrict__ roles, const uint32_t* __
     if (j > 0 && !head[j] && !(r & ROLE_COLUMN_ONLY) && (roles[row_of[j - 1]] & ROLE_COLUMN_ONLY)) atomicOr(err, 16384u);
 }
 
+// Dominant reference-set tag and donor set of every sub-bucket: the most frequent value among five evenly spaced rows (a
+// wrong guess only makes the flag shortcut of stage 1 fire less often; the exact 64-bit tests behind it do not depend on it).
+struct SubDom {
+    unsigned long long tag, don;
+};
+__global__ void k_sub_dominant(const SubBucket* __restrict__ subs, int n_subs, const unsigned long long* __restrict__ tagq,
+                               const unsigned long long* __restrict__ donq, SubDom* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_subs) return;
+    const SubBucket sb = subs[s];
+    unsigned long long t[5], d[5];
+    for (int i = 0; i < 5; i++) {
+        const int64_t q = sb.q0 + (int64_t)(((int64_t)sb.n * (2 * i + 1)) / 10);
+        t[i] = tagq[q];
+        d[i] = donq[q];
+    }
+    int bt = 0, bd = 0, ct = 0, cd = 0;
+    for (int i = 0; i < 5; i++) {
+        int a = 0, b = 0;
+        for (int j = 0; j < 5; j++) {
+            a += t[j] == t[i];
+            b += d[j] == d[i];
+        }
+        if (a > ct && t[i] != TAG_SLOW) { ct = a; bt = i; }
+        if (b > cd && d[i] != 0) { cd = b; bd = i; }
+    }
+    out[s].tag = ct ? t[bt] : DEAD_NONE;   // DEAD_NONE never equals a tag
+    out[s].don = cd ? d[bd] : 0ull;
+}
+// flagq: see RF_* in ejb_stage1.cuh; refreshed before every stage-1 launch (deadq grows while stage 2a learns)
+__global__ void k_row_flags(const int32_t* __restrict__ subq, const int32_t* __restrict__ rowq, int64_t n_pos, const SubDom* __restrict__ dom,
+                            const unsigned long long* __restrict__ tagq, const unsigned long long* __restrict__ deadq,
+                            const unsigned long long* __restrict__ donq, uint32_t* __restrict__ flagq) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pos) return;
+    uint32_t f = 0;
+    if (rowq[q] >= 0) {
+        const SubDom d = dom[subq[q]];
+        if (deadq[q] == d.tag) f |= 1u;
+        if (tagq[q] == d.tag) f |= 2u;
+        const unsigned long long m = donq[q];
+        if (d.don != 0 && m != 0) f |= (m == d.don) ? 8u : 4u;
+    }
+    flagq[q] = f;
+}
+
 // per exact: donor set as a 64-bit mask (join_one.rs:301-315) and sort keys for the barcode lists
 __global__ void k_exact_prep(DevIn in, unsigned long long* donor_mask, uint64_t* bc_keys) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -53,6 +53,21 @@ __device__ __forceinline__ int cdr3_dist(const uint32_t* rl, const uint32_t* rh,
 //               donor and for every row under MIX_DONORS).  That test precedes everything that can panic in join_one.
 constexpr int S1_RUNI = 1, S1_TAGS = 2;
 
+// Row flags (flagq): relation of a row to the dominant reference set / donor set of its sub-bucket.
+constexpr uint32_t RF_DEAD_VS_DOM = 1u;   // deadq[q] == dominant tag: the row fails the degradation test against the dominant reference set
+constexpr uint32_t RF_HAS_DOM = 2u;       // tagq[q]  == dominant tag
+constexpr uint32_t RF_FOREIGN_DON = 4u;   // donor set non-empty and different from the dominant (non-empty) donor set
+constexpr uint32_t RF_DOM_DON = 8u;       // donor set == dominant (non-empty) donor set
+// pair rejected by the flags alone?  (dead-vs-dominant x has-dominant, foreign-donor x dominant-donor, either way round)
+__device__ __forceinline__ bool flag_kill(uint32_t fr, uint32_t fc, unsigned int& donor_kills, unsigned int& flag_kills) {
+    const uint32_t g = ((fr & 5u) << 1) | ((fr & 10u) >> 1);
+    const uint32_t k = g & fc;
+    if (!k) return false;
+    flag_kills++;
+    if (!(k & 3u)) donor_kills++;
+    return true;
+}
+
 // S1_NOVOTE: no per-row warp vote before the distance (the column-level vote S1_RUNI already skips uniform 16 x 16 groups)
 #ifndef S1_NOVOTE
 #define S1_NOVOTE 0
@@ -70,11 +85,12 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
                                                        unsigned long long cand_cap, Counters* __restrict__ ctr,
                                                        unsigned long long* __restrict__ unit_cand,
                                                        const unsigned long long* __restrict__ tagq, const unsigned long long* __restrict__ deadq,
-                                                       const unsigned long long* __restrict__ donq) {
+                                                       const unsigned long long* __restrict__ donq, const uint32_t* __restrict__ flagq) {
     constexpr bool RUNI = (MODE & S1_RUNI) != 0, TAGS = (MODE & S1_TAGS) != 0;
     constexpr int NP = 2 * W1;            // plane-words per row
     constexpr int TAG0 = (NP + 1) * TILE; // word offset of the staged reference-set tags (uint64 x TILE), then the dead tags
-    constexpr int SLOT = (NP + 1 + (TAGS ? 6 : 0)) * TILE;   // words per staged tile (planes + labels [+ tags + dead tags + donor sets])
+    constexpr int FLAG0 = (NP + 7) * TILE; // word offset of the staged flag words
+    constexpr int SLOT = (NP + 1 + (TAGS ? 7 : 0)) * TILE;   // words per staged tile (planes + labels [+ tags + dead tags + donor sets + flags])
     __shared__ __align__(16) uint32_t s_row[SLOT];
     __shared__ __align__(16) uint32_t s_col[2][SLOT];
     __shared__ __align__(8) uint64_t s_bar[3];
@@ -126,7 +142,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         const int r0 = blk * TILE;
         const int cnt = min(TILE, sb.npad - r0);  // npad is a multiple of 4
         const uint32_t bytes = (uint32_t)cnt * 4u;
-        mbar_expect_tx(bar, bytes * (NP + 1 + (TAGS ? 6 : 0)));
+        mbar_expect_tx(bar, bytes * (NP + 1 + (TAGS ? 7 : 0)));
 #pragma unroll
         for (int pw = 0; pw < NP; pw++) tma_load_1d(dst + pw * TILE, base + (int64_t)pw * sb.npad + r0, bytes, bar);
         tma_load_1d(dst + NP * TILE, labq + sb.q0 + r0, bytes, bar);   // q0 is a multiple of 4
@@ -134,6 +150,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
             tma_load_1d(dst + TAG0, tagq + sb.q0 + r0, bytes * 2, bar);
             tma_load_1d(dst + TAG0 + 2 * TILE, deadq + sb.q0 + r0, bytes * 2, bar);
             tma_load_1d(dst + TAG0 + 4 * TILE, donq + sb.q0 + r0, bytes * 2, bar);
+            tma_load_1d(dst + FLAG0, flagq + sb.q0 + r0, bytes, bar);
         }
     };
     if (tid == 0) {
@@ -167,7 +184,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     const int row_lim = min(sb.n - rb * TILE, t.row_hi);  // valid local rows are row_lo <= r < row_lim
     const int maxcd = sb.maxcd;
     unsigned long long evaluated = 0, killed = 0;   // thread 0 only
-    unsigned int donor_kills = 0;                    // per thread
+    unsigned int donor_kills = 0, flag_kills = 0;    // per thread
 
     for (int it = 0; it < ncb; it++) {
         const int cb = s_cbs[it];
@@ -199,6 +216,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
                         if (S1_NOVOTE || __any_sync(0xffffffffu, need)) {
                             const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
                             if (need && cd <= maxcd) {
+                                if (TAGS && flag_kill(s_row[FLAG0 + i * 16 + ty], sc[FLAG0 + c], donor_kills, flag_kills)) continue;
                                 const unsigned int h = atomicAdd(&s_nhits, 1u);
                                 s_hits[h] = (uint16_t)(((i * 16 + ty) << 7) | c);
                             }
@@ -223,6 +241,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
                         if (S1_NOVOTE || __any_sync(0xffffffffu, need)) {
                             const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
                             if (need && cd <= maxcd) {
+                                if (TAGS && flag_kill(s_row[FLAG0 + r], sc[FLAG0 + c], donor_kills, flag_kills)) continue;
                                 const unsigned int h = atomicAdd(&s_nhits, 1u);
                                 s_hits[h] = (uint16_t)((r << 7) | c);
                             }
@@ -306,8 +325,12 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     }
     if (TAGS) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) donor_kills += __shfl_xor_sync(0xffffffffu, donor_kills, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            donor_kills += __shfl_xor_sync(0xffffffffu, donor_kills, o);
+            flag_kills += __shfl_xor_sync(0xffffffffu, flag_kills, o);
+        }
         if ((tid & 31) == 0 && donor_kills) atomicAdd(&ctr->n_s1_donor, (unsigned long long)donor_kills);
+        if ((tid & 31) == 0 && flag_kills) atomicAdd(&ctr->n_s1_kill, (unsigned long long)flag_kills);   // n_s1_kill counts every kind
     }
 }
 

@@ -41,7 +41,7 @@ rr = list(csv.reader(raw.splitlines()))
 hh = rr[0]
 ix = {n: i for i, n in enumerate(hh)}
 want = {"t": "gpu__time_duration.sum", "rd": "dram__bytes_read.sum", "wr": "dram__bytes_write.sum", "inst": "smsp__inst_executed.sum",
-        "regs": "launch__registers_per_thread", "warps": "sm__warps_active.avg.pct_of_peak_sustained_active", "issue": "smsp__issue_active.avg.pct",
+        "regs": "launch__registers_per_thread", "warps": "sm__warps_active.avg.pct_of_peak_sustained_active", "issue": "sm__inst_issued.avg.pct_of_peak_sustained_active",
         "xu": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "alu": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "l1": "l1tex__t_sector_hit_rate.pct", "l2": "lts__t_sector_hit_rate.pct"}
 units = rr[1]
