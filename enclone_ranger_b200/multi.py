@@ -167,6 +167,7 @@ def scatter_parts(parts, device, src=0, group=None):
 # Sub-bucket granular partitioning with row-range splits of the heaviest sub-buckets (ejb_set_row_roles).
 # ------------------------------------------------------------------------------------------------------------
 ROLE_COLUMN_ONLY, ROLE_SPLIT = 1, 2
+W_KILL = 3.0             # cost of a CDR3-close pair that stage 1 drops from its per-row tags (measured: ~6 ps)
 W_CROSS = 60.0           # cost of one fully scored stage-2 candidate in units of one CDR3 pair (fit on the 8 x 1M-cell run: 0.12 ns vs 1.9 ps)
 
 
@@ -232,7 +233,9 @@ def probe_live_fractions(inp, ctx, params, min_rows=4096, sample=256):
     least `min_rows` rows go through `ctx` (one small join for all of them), and a sampled pair counts as live when it is
     CDR3-close (join_one.rs:216-234), ends in different clonotypes, its reference sets are equal or compatible and its
     donor sets do not already reject it (join_one.rs:301-323; stage 1 drops those pairs for free).
-    Returns {sub-bucket index (as in partition_work): fraction}."""
+    CDR3-close pairs that stage 1 rejects from its per-row tags (other donor set, incompatible reference sets) are counted
+    with the small weight W_KILL / W_CROSS.
+    Returns {sub-bucket index (as in partition_work): effective fraction}."""
     two, sub_of, n_sub = _sub_bucket_table(inp)
     cnt = np.bincount(sub_of, minlength=n_sub)
     order = np.argsort(sub_of, kind="stable")
@@ -271,9 +274,12 @@ def probe_live_fractions(inp, ctx, params, min_rows=4096, sample=256):
         close = (cd.astype(np.float64) / T <= thr) if params.is_bcr else (cd == 0)
         lab = lab_of[r]
         live = close & (lab[:, None] != lab[None, :])
+        killed = np.zeros_like(live)          # CDR3-close pairs stage 1 rejects from its per-row tags (cheap, but not free)
         if not params.mix_donors:
             dm = _donor_masks(inp, r)
-            live &= ~((dm[:, None] != 0) & (dm[None, :] != 0) & (dm[:, None] != dm[None, :]))
+            rej = (dm[:, None] != 0) & (dm[None, :] != 0) & (dm[:, None] != dm[None, :])
+            killed |= live & rej
+            live &= ~rej
         refs = np.concatenate([vs[r], js[r]], axis=1)
         u, inv = np.unique(refs, axis=0, return_inverse=True)
         inv = inv.reshape(-1)
@@ -284,8 +290,10 @@ def probe_live_fractions(inp, ctx, params, min_rows=4096, sample=256):
                 for b in range(a + 1, len(u)):
                     if cntu[a] * cntu[b] * 50 >= m:      # rare pairings cannot move the estimate
                         comp[a, b] = comp[b, a] = _refsets_compatible(inp, u[a], u[b], int(params.max_degradation))
-            live &= comp[inv[:, None], inv[None, :]]
-        out[int(s)] = float(np.triu(live, 1).sum()) / (m * (m - 1) / 2)
+            cm = comp[inv[:, None], inv[None, :]]
+            killed |= live & ~cm
+            live &= cm
+        out[int(s)] = (float(np.triu(live, 1).sum()) + (W_KILL / W_CROSS) * float(np.triu(killed, 1).sum())) / (m * (m - 1) / 2)
     return out
 
 
