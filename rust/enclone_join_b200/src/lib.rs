@@ -81,6 +81,12 @@ pub mod sys {
         pub fn ejb_join(ctx: *mut EjbCtx, p: *const EjbParams, input: *const EjbInput, out: *mut EjbResult) -> c_int;
         pub fn ejb_result_free(ctx: *mut EjbCtx, out: *mut EjbResult);
         pub fn ejb_abi_sizes(out: *mut i64);
+        /// One page-locked allocation holding the flattened input arrays: uploaded with a single DMA.
+        pub fn ejb_set_input_arena(ctx: *mut EjbCtx, base: *const c_void, bytes: u64) -> c_int;
+        /// Multi-GPU only (one process per GPU): row ranges of a sub-bucket split over several contexts, and the merge of
+        /// their partial forests on rank 0.
+        pub fn ejb_set_row_roles(ctx: *mut EjbCtx, roles: *const u8, n_rows: i64) -> c_int;
+        pub fn ejb_forest_merge(n_rows: i32, k1: *const i32, k2: *const i32, n_edges: i64, keep: *mut u8) -> c_int;
     }
 }
 

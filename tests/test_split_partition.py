@@ -123,3 +123,53 @@ def test_merge_split_edges_two_cell_filter():
     assert multi.merge_split_edges(8, k1, k2, cd, msh, split, ncells).tolist() == [True, True, True]
     ncells[0] = 1
     assert multi.merge_split_edges(8, k1, k2, cd, msh, split, ncells, easy=True).tolist() == [True, True, True]
+
+
+def test_probe_live_fractions_with_a_stub_context():
+    """The partitioner's sample join, with the join replaced by a stub that returns the generator's true clone of every sampled
+    row: pairs inside one clone never count, the stub that joins nothing makes every CDR3-close, not donor-rejected pair
+    count, and a partition built from the fractions still gives every row exactly one first-row owner."""
+    rep = E.generate(1, n_cells=120000, seed=41)
+    inp = rep.to_join_input()
+    clone = np.asarray(rep.row_clone()).copy()
+    p = E.default_params(True)
+
+    class Stub:
+        def __init__(self, labels_of):
+            self.labels_of = labels_of
+            self.rows = None
+
+        def set_row_roles(self, roles):
+            assert roles is None
+
+        def join(self, params, probe):
+            class R:
+                pass
+            r = R()
+            r.labels = self.labels_of(self.rows)
+            assert len(r.labels) == probe.n_rows
+            return r
+
+    orig = inp.subset_rows
+
+    def run(stub):
+        def capture(rows):
+            stub.rows = rows
+            return orig(rows)
+        inp.subset_rows = capture
+        try:
+            return multi.probe_live_fractions(inp, stub, p, min_rows=1024, sample=128)
+        finally:
+            inp.subset_rows = orig
+
+    true = run(Stub(lambda rows: clone[rows]))
+    none = run(Stub(lambda rows: np.arange(len(rows))))
+    assert len(true) >= 1 and set(true) == set(none)
+    assert all(0.0 <= v <= 1.0 for v in true.values()) and all(0.0 <= v <= 1.0 + 1e-9 for v in none.values())
+    assert max(none.values()) > 0.5 and all(none[s] >= true[s] for s in true)
+    parts, split = multi.partition_work(inp, 4, live_fraction=none)
+    first = np.zeros(inp.n_rows, dtype=np.int64)
+    for part in parts:
+        roles = part.roles if part.roles is not None else np.zeros(len(part.rows), dtype=np.uint8)
+        first[part.rows[(roles & multi.ROLE_COLUMN_ONLY) == 0]] += 1
+    assert first.max() == 1
