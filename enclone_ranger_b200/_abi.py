@@ -107,6 +107,9 @@ class EjbInput(C.Structure):
         ("row_tig2_off", _i64p),
         ("tig2_words", _u32p),
         ("n_tig2_words", C.c_int64),
+        ("row_cdr32_off", _i64p),
+        ("cdr32_words", _u32p),
+        ("n_cdr32_words", C.c_int64),
     ]
 
 
@@ -149,6 +152,15 @@ class EjbStats(C.Structure):
         ("stage2_memo_dead", C.c_int64),
         ("stage2_degr_dead", C.c_int64),
         ("stage1_donor_kills", C.c_int64),
+        ("pairs_distance_computed", C.c_int64),
+        ("pairs_distance_full", C.c_int64),
+        ("popc_executed_stage1", C.c_int64),
+        ("host_syncs", C.c_int64),
+        ("boruvka_iterations", C.c_int64),
+        ("p1_cache_slots", C.c_int64),
+        ("n_devices", C.c_int64),
+        ("ms_partition", C.c_double),
+        ("ms_merge", C.c_double),
     ]
 
     def as_dict(self):
@@ -288,5 +300,11 @@ def load_join():
         L.ejb_forest_merge.restype = C.c_int
         L.ejb_device_tuples.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.ejb_device_tuples.restype = C.c_int
+        L.ejb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
+        L.ejb_set_option.restype = C.c_int
+        L.ejb_create_ms.argtypes = [C.c_void_p]
+        L.ejb_create_ms.restype = C.c_double
+        L.ejb_sr_table_read.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _f64p]
+        L.ejb_sr_table_read.restype = C.c_int
         _cache["join"] = L
     return _cache["join"]

@@ -1,5 +1,7 @@
 // ejb_forest.cuh — lexicographic spanning forest (Boruvka), finalize kernels, pipe-peak microbenchmarks.
 #pragma once
+#include "ejb_p1.cuh"
+#include "ejb_stage1.cuh"
 #include "ejb_types.cuh"
 
 namespace ejb {
@@ -34,88 +36,199 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
 }
 
 constexpr int BOR_TAG_SHIFT = 56;
+constexpr int BOR_MAX_ITERS = 60;
 
-__global__ void k_bor_min(const unsigned long long* __restrict__ w, const unsigned long long* __restrict__ n_p, unsigned long long cap,
-                          int32_t* __restrict__ parent, unsigned long long* __restrict__ best, int iter, int2* __restrict__ roots,
-                          Counters* ctr) {
-    const unsigned long long n = min(*n_p, cap);
-    const unsigned long long tag = (unsigned long long)(63 - iter) << BOR_TAG_SHIFT;
-    unsigned long long alive = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long e = w[i];
-        const int a = (int)(e >> 28), b = (int)(e & 0xfffffffull);
-        const int ra = uf_find_ro(parent, a), rb = uf_find_ro(parent, b);
-        // pointer jumping: no hook runs concurrently with this kernel, a root is a valid parent
-        if (parent[a] != ra) parent[a] = ra;
-        if (parent[b] != rb) parent[b] = rb;
-        roots[i] = make_int2(ra, rb);
-        if (ra != rb) {
-            atomicMin(&best[ra], tag | e);
-            atomicMin(&best[rb], tag | e);
-            alive++;
+// grid-wide barrier of a cooperatively launched kernel (all CTAs co-resident): monotone arrival counter, zeroed by the host
+// before the launch; `gen` counts the barriers this CTA has passed
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gen++;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const unsigned int target = gen * gridDim.x;
+        while (*reinterpret_cast<volatile unsigned int*>(bar) < target) {
         }
+        __threadfence();
     }
-    // warp-aggregate the alive count
-    for (int o = 16; o > 0; o >>= 1) alive += __shfl_xor_sync(0xffffffffu, alive, o);
-    if ((threadIdx.x & 31) == 0 && alive) atomicAdd(&ctr->n_alive, alive);
+    __syncthreads();
 }
 
-__global__ void k_bor_hook(const unsigned long long* __restrict__ w, const unsigned long long* __restrict__ n_p, unsigned long long cap,
-                           int32_t* __restrict__ parent, const unsigned long long* __restrict__ best, int iter, const int2* __restrict__ roots,
-                           unsigned long long* __restrict__ forest, unsigned long long forest_cap, Counters* ctr) {
-    const unsigned long long n = min(*n_p, cap);
-    const unsigned long long tag = (unsigned long long)(63 - iter) << BOR_TAG_SHIFT;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const int2 r = roots[i];
-        if (r.x == r.y) continue;
-        const unsigned long long e = w[i], te = tag | e;
-        if (best[r.x] == te || best[r.y] == te) {
-            const unsigned long long o = atomicAdd(&ctr->n_forest, 1ull);
-            if (o < forest_cap) forest[o] = e; else ctr->overflow = 1ull;
-            uf_union(parent, (int)(e >> 28), (int)(e & 0xfffffffull));
+struct ForestArgs {
+    const unsigned long long* pass_w;   // pass edges of this round, weight (k1 << 28) | k2
+    const PassTuple* pass_t;
+    const unsigned long long* n_pass_p;
+    unsigned long long cap;
+    int32_t* parent;
+    unsigned long long* best;           // per row (only roots are used)
+    int2* roots;                        // per pass edge: roots of its endpoints at the start of the iteration
+    unsigned long long* forest;
+    PassTuple* forest_t;
+    unsigned long long forest_cap;
+    Counters* ctr;
+    unsigned int* bar;
+    // class labels refreshed at the end of the round
+    const int32_t* rowq;
+    int64_t n_pos;
+    int32_t* labq;
+    const SubBucket* subs;
+    int32_t* blk_lab;
+    const int32_t* blk_sub;
+    int n_blocks;
+};
+
+// One scheduler round of the forest: Boruvka iterations to convergence on this round's pass edges (every component's lightest
+// outgoing edge is in the minimum spanning forest; weights are distinct), then the class labels of every packed row and the
+// per-128-row-block uniform labels.  ONE cooperative launch per round: the iterations are separated by grid barriers instead of
+// host read-backs.  Nothing is committed when the round overflowed its work buffers.
+__global__ void __launch_bounds__(256) k_forest_round(ForestArgs A) {
+    unsigned int gen = 0;
+    const unsigned long long tid0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long nthr = (unsigned long long)gridDim.x * blockDim.x;
+    if (A.ctr->overflow) return;   // uniform: written by earlier kernels only
+    const unsigned long long n = min(*A.n_pass_p, A.cap);
+    if (n == 0) return;            // no new edge: labels are unchanged
+    // reset the per-root minima this round can touch
+    for (unsigned long long i = tid0; i < n; i += nthr) {
+        const unsigned long long e = A.pass_w[i];
+        A.best[uf_find_ro(A.parent, (int)(e >> 28))] = ~0ull;
+        A.best[uf_find_ro(A.parent, (int)(e & 0xfffffffull))] = ~0ull;
+    }
+    grid_barrier(A.bar, gen);
+    int iter = 0;
+    for (;; iter++) {
+        // newer iterations carry smaller tags, so their minima override the stale ones without a reset
+        const unsigned long long tag = (unsigned long long)(63 - iter) << BOR_TAG_SHIFT;
+        unsigned long long alive = 0;
+        for (unsigned long long i = tid0; i < n; i += nthr) {
+            const unsigned long long e = A.pass_w[i];
+            const int a = (int)(e >> 28), b = (int)(e & 0xfffffffull);
+            const int ra = uf_find_ro(A.parent, a), rb = uf_find_ro(A.parent, b);
+            // pointer jumping: no hook runs concurrently with this phase, a root is a valid parent
+            if (A.parent[a] != ra) A.parent[a] = ra;
+            if (A.parent[b] != rb) A.parent[b] = rb;
+            A.roots[i] = make_int2(ra, rb);
+            if (ra != rb) {
+                atomicMin(&A.best[ra], tag | e);
+                atomicMin(&A.best[rb], tag | e);
+                alive++;
+            }
         }
+        for (int o = 16; o > 0; o >>= 1) alive += __shfl_xor_sync(0xffffffffu, alive, o);
+        if ((threadIdx.x & 31) == 0 && alive) atomicAdd(&A.ctr->alive_it[iter], alive);
+        grid_barrier(A.bar, gen);
+        if (*reinterpret_cast<volatile unsigned long long*>(&A.ctr->alive_it[iter]) == 0 || iter >= BOR_MAX_ITERS) break;   // uniform
+        // hook: an edge that is the minimum of one of its components joins the forest
+        for (unsigned long long i = tid0; i < n; i += nthr) {
+            const int2 r = A.roots[i];
+            if (r.x == r.y) continue;
+            const unsigned long long e = A.pass_w[i], te = tag | e;
+            if (A.best[r.x] == te || A.best[r.y] == te) {
+                const unsigned long long o = atomicAdd(&A.ctr->n_forest, 1ull);
+                if (o < A.forest_cap) {
+                    A.forest[o] = e;
+                    A.forest_t[o] = A.pass_t[i];
+                } else {
+                    A.ctr->overflow = 2ull;
+                }
+                uf_union(A.parent, (int)(e >> 28), (int)(e & 0xfffffffull));
+            }
+        }
+        grid_barrier(A.bar, gen);
+        // re-point every old root straight at its new root
+        for (unsigned long long i = tid0; i < n; i += nthr) {
+            const int2 r = A.roots[i];
+            if (r.x == r.y) continue;
+            const int nx = uf_find_ro(A.parent, r.x), ny = uf_find_ro(A.parent, r.y);
+            if (A.parent[r.x] != nx) A.parent[r.x] = nx;
+            if (A.parent[r.y] != ny) A.parent[r.y] = ny;
+        }
+        grid_barrier(A.bar, gen);
     }
-}
-
-// after the hooks of one iteration: re-point every old root straight at its new root
-__global__ void k_bor_compress(const unsigned long long* __restrict__ n_p, unsigned long long cap, int32_t* __restrict__ parent,
-                               const int2* __restrict__ roots) {
-    const unsigned long long n = min(*n_p, cap);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const int2 r = roots[i];
-        if (r.x == r.y) continue;
-        const int nx = uf_find_ro(parent, r.x), ny = uf_find_ro(parent, r.y);
-        if (parent[r.x] != nx) parent[r.x] = nx;
-        if (parent[r.y] != ny) parent[r.y] = ny;
+    if (tid0 == 0) atomicAdd(&A.ctr->bor_iters, (unsigned long long)iter);
+    // class label of every packed row
+    for (unsigned long long q = tid0; q < (unsigned long long)A.n_pos; q += nthr) {
+        const int k = A.rowq[q];
+        if (k < 0) continue;  // padding position
+        const int r = uf_find_ro(A.parent, k);
+        if (A.parent[k] != r) A.parent[k] = r;
+        A.labq[q] = r;
     }
-}
-
-// after a round: class label of every packed row, and per 128-block uniform labels
-__global__ void k_flatten(int32_t* __restrict__ parent, const int32_t* __restrict__ rowq, int64_t n_pos, int32_t* __restrict__ labq) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_pos) return;
-    const int k = rowq[q];
-    if (k < 0) return;  // padding position
-    const int r = uf_find_ro(parent, k);
-    if (parent[k] != r) parent[k] = r;
-    labq[q] = r;
-}
-__global__ void k_block_labels(const SubBucket* __restrict__ subs, int n_subs, const int32_t* __restrict__ labq, int32_t* __restrict__ blk_lab,
-                               const int32_t* __restrict__ blk_sub, int n_blocks) {
-    // one warp per 128-row block
+    grid_barrier(A.bar, gen);
+    // per 128-row block: the common label or -1 (one warp per block)
     const int lane = threadIdx.x & 31;
-    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= n_blocks) return;
-    const SubBucket sb = subs[blk_sub[b]];
-    const int rb = (int)(b - sb.blk0);
-    const int r0 = rb * TILE, r1 = min(sb.n, r0 + TILE);
-    const int first = labq[sb.q0 + r0];
-    bool same = true;
-    for (int r = r0 + lane; r < r1; r += 32)
-        if (labq[sb.q0 + r] != first) same = false;
-    same = __all_sync(0xffffffffu, same);
-    if (lane == 0) blk_lab[b] = same ? first : -1;
-    (void)n_subs;
+    for (unsigned long long b = tid0 >> 5; b < (unsigned long long)A.n_blocks; b += nthr >> 5) {
+        const SubBucket sb = A.subs[A.blk_sub[b]];
+        const int rb = (int)((long long)b - sb.blk0);
+        const int r0 = rb * TILE, r1 = min(sb.n, r0 + TILE);
+        const int first = A.labq[sb.q0 + r0];
+        bool same = true;
+        for (int r = r0 + lane; r < r1; r += 32)
+            if (A.labq[sb.q0 + r] != first) same = false;
+        same = __all_sync(0xffffffffu, same);
+        if (lane == 0) A.blk_lab[b] = same ? first : -1;
+    }
+}
+
+// Unit truncation after stage 1 (was a host step between two stream synchronisations): a unit whose counted candidates exceed
+// its allowance keeps whole row ranges up to (and including) the one that crosses it; stage 2 ignores candidates of the rows
+// cut away (qcut) and the scheduler resumes from the cut.  A jump in candidate density (a clone that is not connected yet)
+// switches to the strict allowance.  One thread per unit; the tasks (row ranges) of a unit are consecutive and in row order.
+struct UnitDesc {
+    int32_t sub, t0, nt, r1;   // sub-bucket, first task, number of tasks, planned end row
+    double allow, strict, rho_ref;
+};
+struct UnitOut {
+    int32_t r1, cut;           // committed end row; 1 when the unit was truncated
+    double cand;               // candidates of the committed rows
+    unsigned int pass, pad;    // pass edges of the unit's sub-bucket in this round (filled by k_round_report)
+};
+__global__ void k_truncate(const UnitDesc* __restrict__ units, int n_units, const RowTask* __restrict__ tasks, const unsigned long long* __restrict__ unit_cand,
+                           const SubBucket* __restrict__ subs, int32_t* __restrict__ qcut, unsigned int* __restrict__ sub_pass, UnitOut* __restrict__ out,
+                           Counters* __restrict__ ctr) {
+    const int ui = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ui >= n_units) return;
+    const UnitDesc u = units[ui];
+    double cand = 0.0, after_jump = 0.0;
+    bool jumped = false;
+    int r1 = u.r1, cut = 0;
+    for (int t = u.t0; t < u.t0 + u.nt; t++) {
+        const RowTask rt = tasks[t];
+        const int tr0 = rt.rb * TILE + rt.row_lo, tr1 = rt.rb * TILE + rt.row_hi;
+        const double cnt = (double)unit_cand[rt.tid];
+        if (!jumped && (u.rho_ref < 0.0 || cnt / (double)max(1, tr1 - tr0) > 8.0 * u.rho_ref + 16.0)) jumped = true;
+        cand += cnt;
+        if (jumped) after_jump += cnt;
+        if ((cand > u.allow || (jumped && after_jump > u.strict)) && tr1 < u.r1) {
+            r1 = tr1;
+            cut = 1;
+            break;
+        }
+    }
+    qcut[u.sub] = cut ? (int32_t)(subs[u.sub].q0 + r1) : 0x7fffffff;
+    sub_pass[u.sub] = 0u;
+    out[ui].r1 = r1;
+    out[ui].cut = cut;
+    out[ui].cand = cand;
+    out[ui].pass = 0u;
+    if (cut) ctr->any_cut = 1ull;
+}
+__global__ void k_round_report(const UnitDesc* __restrict__ units, int n_units, const unsigned int* __restrict__ sub_pass, UnitOut* __restrict__ out) {
+    const int ui = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ui < n_units) out[ui].pass = sub_pass[units[ui].sub];
+}
+
+// first launch of a run: every row its own class
+__global__ void k_init_labels(int32_t* __restrict__ parent, int64_t n_rows, const int32_t* __restrict__ rowq, int64_t n_pos, int32_t* __restrict__ labq,
+                              int32_t* __restrict__ blk_lab, const int32_t* __restrict__ blk_sub, const SubBucket* __restrict__ subs, int n_blocks) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_rows) parent[i] = (int32_t)i;
+    if (i < n_pos) labq[i] = rowq[i];                      // padding positions carry -1 already
+    if (i < n_blocks) {
+        const SubBucket sb = subs[blk_sub[i]];
+        const int rb = (int)(i - sb.blk0);
+        blk_lab[i] = (min(sb.n, rb * TILE + TILE) - rb * TILE == 1) ? rowq[sb.q0 + rb * TILE] : -1;   // distinct rows: never uniform unless alone
+    }
 }
 
 __global__ void k_iota(int32_t* p, int64_t n, int32_t off = 0) {
@@ -128,50 +241,56 @@ __global__ void k_fill_u64(unsigned long long* p, int64_t n, unsigned long long 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Finalize
+// Finalize (every count stays on the device: no host read-back until the results are downloaded)
 // ------------------------------------------------------------------------------------------------
-// forest edges -> (q1, q2) pairs for the tuple pass, and degree counts for the two-cell filter
-__global__ void k_forest_pairs(const unsigned long long* __restrict__ forest, int64_t n, const int32_t* __restrict__ q_of_row, uint2* __restrict__ pairs,
-                               int32_t* __restrict__ deg) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long e = forest[i];
-    const int a = (int)(e >> 28), b = (int)(e & 0xfffffffull);
-    pairs[i] = make_uint2((uint32_t)q_of_row[a], (uint32_t)q_of_row[b]);
-    atomicAdd(&deg[a], 1);
-    atomicAdd(&deg[b], 1);
-}
 __global__ void k_q_of_row(const int32_t* __restrict__ rowq, int64_t n_pos, int32_t* __restrict__ q_of_row) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q < n_pos && rowq[q] >= 0) q_of_row[rowq[q]] = (int32_t)q;
 }
+// forest degree of every row (two-cell filter)
+__global__ void k_forest_deg(const unsigned long long* __restrict__ forest, const unsigned long long* __restrict__ n_p, int32_t* __restrict__ deg) {
+    const unsigned long long n = *n_p;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = forest[i];
+        atomicAdd(&deg[(int)(e >> 28)], 1);
+        atomicAdd(&deg[(int)(e & 0xfffffffull)], 1);
+    }
+}
 // join.rs:120-178: an orbit of exactly two rows holding two cells in total loses its edge when
-// cd > min(shares) / 2 (unless EASY).  keep[i] = 0 for deleted edges; parent[] is un-merged.
-__global__ void k_two_cell(DevIn in, DevParams P, const unsigned long long* __restrict__ forest, int64_t n, const int32_t* __restrict__ deg,
-                           const EdgeTuple* __restrict__ tuples, int32_t* __restrict__ parent, uint8_t* __restrict__ keep, Counters* ctr,
-                           const uint8_t* __restrict__ roles) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long e = forest[i];
-    const int a = (int)(e >> 28), b = (int)(e & 0xfffffffull);
-    int kp = 1;
-    // rows of a sub-bucket that was split over several contexts: this forest is partial, the caller filters after merging
-    const bool partial = roles && (roles[a] & ROLE_SPLIT);
-    if (!partial && deg[a] == 1 && deg[b] == 1) {
-        const int ea = in.row_exact[a], eb = in.row_exact[b];
-        const long long ncells = (in.ex_cell_off[ea + 1] - in.ex_cell_off[ea]) + (in.ex_cell_off[eb + 1] - in.ex_cell_off[eb]);
-        if (ncells == 2) {
-            const EdgeTuple t = tuples[i];
-            const int min_sh = (t.nrefs == 2) ? min(t.sh0, t.sh1) : t.sh0;
-            if (t.cd > min_sh / 2 && !P.easy) {
-                kp = 0;
-                parent[a] = a;
-                parent[b] = b;
-                atomicAdd(&ctr->n_two_cell, 1ull);
+// cd > min(shares) / 2 (unless EASY).  Kept edges are compacted into sort keys (weight) + source index; parent[] is un-merged
+// for the deleted ones.
+__global__ void k_two_cell(DevIn in, DevParams P, const unsigned long long* __restrict__ forest, const unsigned long long* __restrict__ n_p,
+                           const int32_t* __restrict__ deg, const PassTuple* __restrict__ tuples, int32_t* __restrict__ parent,
+                           unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx, Counters* ctr, const uint8_t* __restrict__ roles) {
+    const unsigned long long n = *n_p;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = forest[i];
+        const int a = (int)(e >> 28), b = (int)(e & 0xfffffffull);
+        bool kp = true;
+        // rows of a sub-bucket that was split over several contexts: this forest is partial, the caller filters after merging
+        const bool partial = roles && (roles[a] & ROLE_SPLIT);
+        if (!partial && deg[a] == 1 && deg[b] == 1) {
+            const int ea = in.row_exact[a], eb = in.row_exact[b];
+            const long long ncells = (in.ex_cell_off[ea + 1] - in.ex_cell_off[ea]) + (in.ex_cell_off[eb + 1] - in.ex_cell_off[eb]);
+            if (ncells == 2) {
+                const PassTuple t = tuples[i];
+                const int nrefs = (int)(t.nrefs_err & 0xff);
+                const int cd = (int)(t.cd12 & 0xffff) + (int)(t.cd12 >> 16);
+                const int min_sh = (nrefs == 2) ? min(t.sh0, t.sh1) : t.sh0;
+                if (cd > min_sh / 2 && !P.easy) {
+                    kp = false;
+                    parent[a] = a;
+                    parent[b] = b;
+                    atomicAdd(&ctr->n_two_cell, 1ull);
+                }
             }
         }
+        if (kp) {
+            const unsigned long long o = atomicAdd(&ctr->n_final, 1ull);
+            keys[o] = e;
+            idx[o] = (uint32_t)i;
+        }
     }
-    keep[i] = (uint8_t)kp;
 }
 // join2.rs:69-84: rows of one exact subclonotype end up in one orbit
 __global__ void k_exact_first(DevIn in, int32_t* __restrict__ first_row) {
@@ -192,42 +311,46 @@ __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-// compact kept forest edges into sort keys (weight) + source index
-__global__ void k_final_keys(const unsigned long long* __restrict__ forest, const uint8_t* __restrict__ keep, int64_t n, unsigned long long* __restrict__ keys,
-                             uint32_t* __restrict__ idx, unsigned long long* __restrict__ n_out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !keep[i]) return;
-    const unsigned long long o = atomicAdd(n_out, 1ull);
-    keys[o] = forest[i];
-    idx[o] = (uint32_t)i;
-}
 struct FinalOut {
     int32_t *k1, *k2, *cd, *nrefs, *shares, *indeps, *k, *d, *n;
     double *p1, *mult, *score;
     uint8_t* err;
 };
-__global__ void k_final_gather(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ idx, int64_t n, const EdgeTuple* __restrict__ tuples,
-                               FinalOut o, Counters* ctr) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long e = keys[i];
-    const EdgeTuple t = tuples[idx[i]];
-    o.k1[i] = (int)(e >> 28);
-    o.k2[i] = (int)(e & 0xfffffffull);
-    o.cd[i] = t.cd;
-    o.nrefs[i] = t.nrefs;
-    o.shares[2 * i] = t.sh0;
-    o.shares[2 * i + 1] = t.sh1;
-    o.indeps[2 * i] = t.in0;
-    o.indeps[2 * i + 1] = t.in1;
-    o.k[i] = t.k;
-    o.d[i] = t.d;
-    o.n[i] = t.n;
-    o.p1[i] = t.p1;
-    o.mult[i] = t.mult;
-    o.score[i] = t.score;
-    o.err[i] = (uint8_t)t.err;
-    (void)ctr;
+// edges in raw_joins order + the PotentialJoin members rebuilt from the kept PassTuple (join_one.rs:444-447, 499-544: same
+// formulas, tables and p1 cache as stage 2b, which accepted the edge with exactly these values)
+__global__ void k_final_gather(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ idx, const unsigned long long* __restrict__ n_p,
+                               const PassTuple* __restrict__ tuples, const int32_t* __restrict__ q_of_row, const int32_t* __restrict__ subq,
+                               const SubBucket* __restrict__ subs, P1Cache p1c, const double* __restrict__ powtab, const int32_t* __restrict__ pow_off,
+                               FinalOut o) {
+    const unsigned long long n = *n_p;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = keys[i];
+        const PassTuple t = tuples[idx[i]];
+        const int k1 = (int)(e >> 28), k2 = (int)(e & 0xfffffffull);
+        const SubBucket sb = subs[subq[q_of_row[k1]]];
+        const int cd1 = (int)(t.cd12 & 0xffff), cd2 = (int)(t.cd12 >> 16);
+        const int nrefs = (int)(t.nrefs_err & 0xff);
+        const int min_sh = (nrefs == 2) ? min(t.sh0, t.sh1) : t.sh0;
+        const int min_in = (nrefs == 2) ? min(t.in0, t.in1) : t.in0;
+        const int kk = min_in + 2 * min_sh;
+        const double p1 = p1_lookup(p1c, sb.n3, kk, min_sh);
+        const double mult = __dmul_rn(powtab[pow_off[sb.ch] + cd1], powtab[pow_off[sb.cl] + cd2]);
+        o.k1[i] = k1;
+        o.k2[i] = k2;
+        o.cd[i] = cd1 + cd2;
+        o.nrefs[i] = nrefs;
+        o.shares[2 * i] = t.sh0;
+        o.shares[2 * i + 1] = t.sh1;
+        o.indeps[2 * i] = t.in0;
+        o.indeps[2 * i + 1] = t.in1;
+        o.k[i] = kk;
+        o.d[i] = min_sh;
+        o.n[i] = sb.n3;
+        o.p1[i] = p1;
+        o.mult[i] = mult;
+        o.score[i] = __dmul_rn(p1, mult);
+        o.err[i] = (uint8_t)(t.nrefs_err >> 8);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

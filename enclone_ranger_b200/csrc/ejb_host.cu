@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -18,6 +19,9 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/enclone_join_b200.h"
@@ -42,6 +46,16 @@ struct DevBuf {
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            cap = o.cap;
+            o.p = nullptr;
+            o.cap = 0;
+        }
+        return *this;
+    }
     ~DevBuf() { release(); }
     void release() {
         if (p) cudaFree(p);
@@ -60,6 +74,24 @@ struct DevBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+struct PinBuf {   // page-locked host scratch, grow-only
+    void* p = nullptr;
+    size_t cap = 0;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap && p) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = std::max<size_t>(bytes + bytes / 2, 4096);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 struct Unit {  // rows [r0, r1) of one sub-bucket, processed against all columns to their right
     int32_t sub, r0, r1;
     double allow;      // candidates after which the unit is truncated (at a row-range boundary) once stage 1 has counted them
@@ -68,11 +100,21 @@ struct Unit {  // rows [r0, r1) of one sub-bucket, processed against all columns
     double cand, pass; // measured: candidates of the committed rows, pass edges
 };
 
+// Developer / test knobs: environment read once in ejb_create, overridable with ejb_set_option.
+struct Options {
+    long long first_unit = 2, growth = 12;   // unit schedule (measured on configs[1]: 8/4 -> 10.5 ms, 1/8 -> 8.95, 2/12 -> 8.74, 4/16 -> 8.75)
+    int s1_mode = S1_RUNI | S1_TAGS;
+    int no_tags = 0;
+    int trace = 0;
+    int sr_host = 0;                         // build the Stirling table on the host (A/B against the device kernel)
+};
+
 }  // namespace
 
 struct ejb_ctx {
     int device = 0;
     int sm_count = 148;
+    int coop_grid = 148;        // co-resident CTAs of k_forest_round
     cudaStream_t stream = nullptr;
     // Large host->device copies are spread over a few copy streams: on this platform one cudaMemcpyAsync from pinned memory
     // reaches ~40 GB/s at 16 MB and ~55 GB/s at 512 MB, i.e. every copy pays ~0.1 ms of setup that concurrent copies overlap.
@@ -81,6 +123,8 @@ struct ejb_ctx {
     cudaEvent_t up_event[N_UP] = {nullptr, nullptr, nullptr, nullptr};
     int up_next = 0;
     std::string err;
+    Options opt;
+    double ms_create = 0.0;
     int shard_rank = 0, shard_world = 1;
     unsigned long long cand_cap = 1ull << 27;
     bool cap_explicit = false;
@@ -91,9 +135,8 @@ struct ejb_ctx {
     bool have_input = false, have_run = false;
 
     // persistent
-    DevBuf d_sr, d_p1_keys, d_p1_vals, d_p1_new, d_ctr, d_err;
-    unsigned long long p1_count = 0;
-    Counters* h_ctr = nullptr;  // pinned
+    DevBuf d_sr, d_p1_keys, d_p1_vals, d_p1_new, d_err, d_bar;
+    unsigned long long p1_count = 0;   // keys in the p1 cache (host tally of the per-round insert counts)
     char* h_res = nullptr;      // pinned result arena (grow-only); ejb_result arrays point into it
     size_t h_res_cap = 0;
 
@@ -116,20 +159,24 @@ struct ejb_ctx {
     DevBuf d_head, d_scan, d_keys, d_keys2, d_vals, d_vals2, d_cubtmp, d_subhead, d_subincl, d_subinfo;
     DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_aux;
     DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
-    DevBuf d_unitcand, d_qcut, d_subpass, d_segpl, d_memo, d_tagq, d_deadq, d_donq, d_flagq, d_subdom;
+    DevBuf d_qcut, d_subpass, d_segpl, d_seglen, d_memo, d_tagq, d_deadq, d_donq, d_flagq, d_subdom;
+    // per-round report: [Counters | UnitOut x units | candidate count x tasks], read back with ONE copy per round
+    DevBuf d_round;
+    PinBuf h_round, h_prep;
+    size_t round_units_cap = 0, round_tasks_cap = 0;
     bool tags_on = false;      // reference-set tags in use (every canonical seg id < 65535)
-    int s1_mode = S1_RUNI | S1_TAGS;   // stage-1 kernel variant (EJB_S1_MODE, developer knob)
-    std::vector<unsigned int> h_subpass;
-    std::vector<unsigned long long> h_unitcand;   // candidates of each task (row range) of the last round, valid even when it overflowed
     struct TaskMeta { int32_t unit, r0, r1; };
     std::vector<TaskMeta> task_meta;
-    DevBuf d_tasks, d_cand, d_slow, d_slowslot, d_surv, d_pass, d_roots, d_forest;
-    DevBuf d_qofrow, d_deg, d_tuples, d_keep, d_first, d_labels, d_fkeys, d_fkeys2, d_fidx, d_fidx2, d_nout;
-    DevBuf d_pairs_all, d_slots, d_cnt;
+    std::vector<unsigned long long> h_unitcand;   // candidates of each task (row range) of the last round, valid even when it overflowed
+    DevBuf d_tasks, d_units, d_cand, d_slow, d_slowslot, d_surv, d_pass, d_passt, d_roots, d_forest, d_forestt;
+    DevBuf d_qofrow, d_deg, d_first, d_labels, d_fkeys, d_fkeys2, d_fidx, d_fidx2;
     DevBuf d_o_k1, d_o_k2, d_o_cd, d_o_nrefs, d_o_sh, d_o_in, d_o_k, d_o_d, d_o_n, d_o_p1, d_o_mult, d_o_score, d_o_err;
+    // pair-batch mode (ejb_join_one_batch)
+    DevBuf d_bpairs, d_bslots, d_btuples, d_bcnt;
     std::vector<SubBucket> subs;
     int64_t n_active = 0, n_pos = 0, n_blocks = 0, n_final = 0;
     unsigned long long forest_cap = 0;
+    bool prepared = false;      // the packed row store of the uploaded input is resident (ejb_run got at least that far)
     ejb_stats stats;
 
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> s2a_events;
@@ -143,12 +190,18 @@ struct ejb_ctx {
         }
         return ev_pool[ev_used++];
     }
+    Counters* d_ctr() const { return d_round.as<Counters>(); }
+
+    // multi-GPU (ejb_create with n_devices > 1): this context drives device_ids[0]; one peer context per further device
+    std::vector<ejb_ctx*> peers;
+    struct MultiState;
+    MultiState* multi = nullptr;
 };
 
 namespace {
 
 int fail(ejb_ctx* c, int code, const char* fmt, ...) {
-    char buf[512];
+    char buf[768];
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
@@ -167,8 +220,20 @@ int fail(ejb_ctx* c, int code, const char* fmt, ...) {
 
 inline unsigned int nblk(int64_t n, int t) { return (unsigned int)std::max<int64_t>(1, (n + t - 1) / t); }
 
-// start.rs:50-99 with the product's dd arithmetic; triangular layout, row n at n(n+1)/2
-void build_sr_table(std::vector<dd_t>& s, int n_max) {
+// every kernel of this library is launched through here: the launch count of a join is what was launched, not a tally kept by hand
+template <class... KA, class... A>
+inline void launch(ejb_ctx* c, void (*k)(KA...), unsigned int grid, unsigned int block, A&&... a) {
+    k<<<grid, block, 0, c->stream>>>(std::forward<A>(a)...);
+    c->stats.kernel_launches++;
+}
+int sync_stream(ejb_ctx* c) {
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.host_syncs++;
+    return EJB_OK;
+}
+
+// start.rs:50-99 with the product's dd arithmetic on the HOST (developer A/B knob "sr_host"; the default is k_sr_table)
+void build_sr_table_host(std::vector<dd_t>& s, int n_max) {
     s.assign((size_t)(n_max + 1) * (n_max + 2) / 2, dd_make(0.0));
     auto at = [&](int n, int k) -> dd_t& { return s[(size_t)n * (n + 1) / 2 + k]; };
     at(0, 0) = dd_make(1.0);
@@ -187,13 +252,6 @@ void build_sr_table(std::vector<dd_t>& s, int n_max) {
         for (int k = 1; k < n; k++) at(n, k) = dd_add(at(n - 1, k), dd_mul(at(n - 1, k - 1), z[k - 1]));
         at(n, n) = njn[n];
     }
-}
-
-const std::vector<dd_t>& sr_table_host() {
-    static std::vector<dd_t> t;
-    static std::once_flag once;
-    std::call_once(once, [] { build_sr_table(t, SR_NMAX); });
-    return t;
 }
 
 template <class T>
@@ -252,31 +310,21 @@ DevParams make_dev_params(const ejb_params& p) {
     return P;
 }
 
-int sync_counters(ejb_ctx* c) {
-    CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return EJB_OK;
-}
-#define CTR_FIELD(f) (reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_ctr.p) + offsetof(Counters, f)))
-cudaError_t zero_counter(ejb_ctx* c, size_t off) {
-    return cudaMemsetAsync(reinterpret_cast<char*>(c->d_ctr.p) + off, 0, sizeof(unsigned long long), c->stream);
-}
+#define CTR_FIELD(f) (reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_round.p) + offsetof(Counters, f)))
 
 template <int W1, int MODE>
-void launch_stage1_wm(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks) {
-    k_stage1<W1, MODE><<<(unsigned int)n_ctas, S1_THREADS, 0, c->stream>>>(c->d_subs.as<SubBucket>(), tasks, n_tasks, c->d_cdr3w.as<uint32_t>(),
-                                                                            c->d_labq.as<int32_t>(), c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(),
-                                                                            c->cand_cap, c->d_ctr.as<Counters>(), c->d_unitcand.as<unsigned long long>(),
-                                                                            c->d_tagq.as<unsigned long long>(), c->d_deadq.as<unsigned long long>(),
-                                                                            c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>());
+void launch_stage1_wm(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks, unsigned long long* unit_cand) {
+    launch(c, k_stage1<W1, MODE>, (unsigned int)n_ctas, S1_THREADS, c->d_subs.as<SubBucket>(), tasks, n_tasks, c->d_cdr3w.as<uint32_t>(), c->d_labq.as<int32_t>(),
+           c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr(), unit_cand, c->d_tagq.as<unsigned long long>(),
+           c->d_deadq.as<unsigned long long>(), c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>());
 }
 template <int W1>
-void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks) {
-    switch (c->s1_mode & (c->tags_on ? 3 : 1)) {
-        case 0: launch_stage1_wm<W1, 0>(c, n_ctas, tasks, n_tasks); break;
-        case 1: launch_stage1_wm<W1, S1_RUNI>(c, n_ctas, tasks, n_tasks); break;
-        case 2: launch_stage1_wm<W1, S1_TAGS>(c, n_ctas, tasks, n_tasks); break;
-        default: launch_stage1_wm<W1, S1_RUNI | S1_TAGS>(c, n_ctas, tasks, n_tasks); break;
+void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks, unsigned long long* unit_cand) {
+    switch (c->opt.s1_mode & (c->tags_on ? 3 : 1)) {
+        case 0: launch_stage1_wm<W1, 0>(c, n_ctas, tasks, n_tasks, unit_cand); break;
+        case 1: launch_stage1_wm<W1, S1_RUNI>(c, n_ctas, tasks, n_tasks, unit_cand); break;
+        case 2: launch_stage1_wm<W1, S1_TAGS>(c, n_ctas, tasks, n_tasks, unit_cand); break;
+        default: launch_stage1_wm<W1, S1_RUNI | S1_TAGS>(c, n_ctas, tasks, n_tasks, unit_cand); break;
     }
 }
 
@@ -330,6 +378,8 @@ S2Ctx make_s2ctx(ejb_ctx* c, int tuple_mode) {
     X.deadq = c->tags_on ? c->d_deadq.as<unsigned long long>() : nullptr;
     X.cdr3w = c->d_cdr3w.as<uint32_t>();
     X.rowstore = c->d_rowstore.as<uint4>();
+    X.segpl = c->d_segpl.as<uint32_t>();
+    X.seglen = c->d_seglen.as<int32_t>();
     X.bc_sorted = c->d_bckeys2.as<uint64_t>();
     X.powtab = c->d_powtab.as<double>();
     X.pow_off = c->d_powoff.as<int32_t>();
@@ -337,36 +387,33 @@ S2Ctx make_s2ctx(ejb_ctx* c, int tuple_mode) {
     X.p1.vals = c->d_p1_vals.as<double>();
     X.p1.newslots = c->d_p1_new.as<uint32_t>();
     X.p1.cap_mask = c->p1_cap - 1;
-    X.ctr = c->d_ctr.as<Counters>();
+    X.ctr = c->d_ctr();
     X.surv = c->d_surv.as<Survivor>();
     X.surv_cap = c->cand_cap;
     X.slow = c->d_slow.as<uint2>();
     X.slow_slot = c->d_slowslot.as<uint32_t>();
     X.slow_cap = c->cand_cap;
     X.tuple_mode = tuple_mode;
-    X.trace = getenv("EJB_TRACE") != nullptr;
+    X.trace = c->opt.trace;
     return X;
 }
 
-// stage 2 on the candidate list currently in `cand` (count on the device): 2a -> slow -> p1 -> 2b
-int run_stage2(ejb_ctx* c, const uint2* cand, const uint32_t* cand_slot, const unsigned long long* n_cand_dev, int tuple_mode) {
+// stage 2 on a candidate list (count on the device): 2a -> slow -> p1 -> 2b.  The per-round counters it uses were zeroed with
+// the round (filter mode) or by the caller (pair-batch mode).
+int run_stage2(ejb_ctx* c, const uint2* cand, const uint32_t* cand_slot, const unsigned long long* n_cand_dev, unsigned long long list_cap, int tuple_mode,
+               EdgeTuple* tuples_out) {
     S2Ctx X = make_s2ctx(c, tuple_mode);
     const int grid = c->sm_count * 8;
-    CK(zero_counter(c, offsetof(Counters, n_slow)));
-    CK(zero_counter(c, offsetof(Counters, n_surv)));
-    CK(zero_counter(c, offsetof(Counters, n_surv_total)));
-    CK(zero_counter(c, offsetof(Counters, s2_work)));
-    CK(zero_counter(c, offsetof(Counters, n_newkeys)));
     cudaEvent_t ea = c->ev(), eb = c->ev();
     CK(cudaEventRecord(ea, c->stream));
-    k_stage2a<<<grid, 256, 0, c->stream>>>(X, cand, cand_slot, n_cand_dev, c->cand_cap);
+    launch(c, k_stage2a, grid, 256, X, cand, cand_slot, n_cand_dev, list_cap);
     CK(cudaEventRecord(eb, c->stream));
     c->s2a_events.push_back({ea, eb});
     c->stats.stage2a_launches++;
-    k_stage2_slow<<<grid, 256, 0, c->stream>>>(X, CTR_FIELD(n_slow));
-    k_p1<<<grid, 256, 0, c->stream>>>(X.p1, c->d_sr.as<dd_t>(), CTR_FIELD(n_newkeys));
-    k_stage2b<<<grid, 256, 0, c->stream>>>(X, CTR_FIELD(n_surv), c->d_pass.as<unsigned long long>(), c->cand_cap, c->d_tuples.as<EdgeTuple>());
-    c->stats.kernel_launches += 4;
+    launch(c, k_stage2_slow, grid, 256, X, (const unsigned long long*)CTR_FIELD(n_slow));
+    launch(c, k_p1, grid, 256, X.p1, c->d_sr.as<const dd_t>(), (const unsigned long long*)CTR_FIELD(n_newkeys), c->d_ctr());
+    launch(c, k_stage2b, grid, 256, X, (const unsigned long long*)CTR_FIELD(n_surv), c->d_pass.as<unsigned long long>(), c->d_passt.as<PassTuple>(), c->cand_cap,
+           tuples_out);
     CK(cudaGetLastError());
     return EJB_OK;
 }
@@ -376,12 +423,123 @@ int p1_cache_clear(ejb_ctx* c) {
     c->p1_count = 0;
     return EJB_OK;
 }
+// keep the load factor of the p1 hash below 1/4: grow by 4x and re-insert (between rounds; rare)
+int p1_cache_grow(ejb_ctx* c) {
+    if (c->p1_cap >= (1u << 30)) return fail(c, EJB_ERR_OOM, "p1 cache cannot grow beyond 2^30 slots (%llu keys)", c->p1_count);
+    const uint32_t new_cap = c->p1_cap << 2;
+    DevBuf nk, nv, nn;
+    CK(nk.ensure((size_t)new_cap * 8));
+    CK(nv.ensure((size_t)new_cap * 8));
+    CK(nn.ensure((size_t)new_cap * 4));
+    CK(cudaMemsetAsync(nk.p, 0xff, (size_t)new_cap * 8, c->stream));
+    P1Cache dst;
+    dst.keys = nk.as<unsigned long long>();
+    dst.vals = nv.as<double>();
+    dst.newslots = nn.as<uint32_t>();
+    dst.cap_mask = new_cap - 1;
+    launch(c, k_p1_rehash, nblk(c->p1_cap, 256), 256, c->d_p1_keys.as<const unsigned long long>(), c->d_p1_vals.as<const double>(), c->p1_cap, dst);
+    CK(cudaStreamSynchronize(c->stream));
+    std::swap(c->d_p1_keys, nk);
+    std::swap(c->d_p1_vals, nv);
+    std::swap(c->d_p1_new, nn);
+    c->p1_cap = new_cap;
+    return EJB_OK;
+}
+
+void destroy_ctx(ejb_ctx* c);
 
 }  // namespace
 
 // ================================================================================================
 // C ABI
 // ================================================================================================
+namespace {
+
+void destroy_ctx(ejb_ctx* c) {
+    if (!c) return;
+    for (ejb_ctx* p : c->peers) destroy_ctx(p);
+    c->peers.clear();
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->h_res) cudaFreeHost(c->h_res);
+    c->in_bufs.clear();
+    for (int i = 0; i < ejb_ctx::N_UP; i++) {
+        if (c->up_event[i]) cudaEventDestroy(c->up_event[i]);
+        if (c->up_stream[i]) cudaStreamDestroy(c->up_stream[i]);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;   // DevBuf / PinBuf members release their memory (the device is current)
+}
+
+void read_env_options(Options& o) {
+    if (const char* e = getenv("EJB_FIRST_UNIT")) o.first_unit = std::max(1ll, atoll(e));
+    if (const char* e = getenv("EJB_GROWTH")) o.growth = std::max(1ll, atoll(e));
+    if (const char* e = getenv("EJB_S1_MODE")) o.s1_mode = atoi(e) & 3;
+    if (getenv("EJB_NO_TAGS")) o.no_tags = 1;
+    if (getenv("EJB_TRACE")) o.trace = 1;
+    if (getenv("EJB_SR_HOST")) o.sr_host = 1;
+}
+
+// one context bound to one device; every failure path runs the same teardown as ejb_destroy
+int create_one(ejb_ctx** out, int dev) {
+    ejb_ctx* c = new ejb_ctx();
+    c->device = dev;
+    auto bail = [&](int code) {
+        destroy_ctx(c);
+        return code;
+    };
+    if (cudaSetDevice(dev) != cudaSuccess) {
+        delete c;
+        return EJB_ERR_NO_DEVICE;
+    }
+    const double t0 = now_ms();
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(EJB_ERR_NO_DEVICE);
+    c->sm_count = prop.multiProcessorCount;
+    read_env_options(c->opt);
+    if (const char* e = getenv("EJB_CAND_CAP")) {
+        c->cand_cap = std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
+        c->cap_explicit = true;
+    }
+    if (const char* e = getenv("EJB_PAIR_BUDGET")) c->pair_budget = std::max<unsigned long long>(1ull << 16, strtoull(e, nullptr, 10));
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(EJB_ERR_CUDA);
+    for (int i = 0; i < ejb_ctx::N_UP; i++)
+        if (cudaStreamCreateWithFlags(&c->up_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->up_event[i], cudaEventDisableTiming) != cudaSuccess)
+            return bail(EJB_ERR_CUDA);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_forest_round, 256, 0) != cudaSuccess || per_sm < 1) return bail(EJB_ERR_CUDA);
+    c->coop_grid = c->sm_count * std::min(per_sm, 4);
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop) return bail(EJB_ERR_NO_DEVICE);
+    // Stirling ratio table (start.rs:50-99): built by one CTA on the device, 72 MB, once per context
+    const size_t sr_entries = (size_t)(SR_NMAX + 1) * (SR_NMAX + 2) / 2;
+    if (c->d_sr.ensure(sr_entries * sizeof(dd_t)) != cudaSuccess) return bail(EJB_ERR_OOM);
+    if (c->opt.sr_host) {
+        std::vector<dd_t> t;
+        build_sr_table_host(t, SR_NMAX);
+        if (cudaMemcpy(c->d_sr.p, t.data(), sr_entries * sizeof(dd_t), cudaMemcpyHostToDevice) != cudaSuccess) return bail(EJB_ERR_CUDA);
+    } else {
+        static_assert(SR_NMAX < 1024 * SR_KPT, "k_sr_table: one thread owns SR_KPT columns");
+        k_sr_table<<<1, 1024, 0, c->stream>>>(c->d_sr.as<dd_t>(), SR_NMAX);
+    }
+    if (c->d_p1_keys.ensure((size_t)c->p1_cap * 8) != cudaSuccess || c->d_p1_vals.ensure((size_t)c->p1_cap * 8) != cudaSuccess ||
+        c->d_p1_new.ensure((size_t)c->p1_cap * 4) != cudaSuccess || c->d_round.ensure(sizeof(Counters) + 4096) != cudaSuccess ||
+        c->d_err.ensure(256) != cudaSuccess || c->d_bar.ensure(256) != cudaSuccess)
+        return bail(EJB_ERR_OOM);
+    cudaMemsetAsync(c->d_p1_keys.p, 0xff, (size_t)c->p1_cap * 8, c->stream);
+    cudaMemsetAsync(c->d_round.p, 0, sizeof(Counters), c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return bail(EJB_ERR_CUDA);
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->ms_create = now_ms() - t0;
+    *out = c;
+    return EJB_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int ejb_abi_version(void) { return EJB_ABI_VERSION; }
@@ -412,70 +570,62 @@ void ejb_params_default(ejb_params* p, int is_bcr) {
 }
 
 const char* ejb_last_error(const ejb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+double ejb_create_ms(const ejb_ctx* c) { return c ? c->ms_create : 0.0; }
 
 int ejb_create(ejb_ctx** out, const int* device_ids, int n_devices) {
     if (!out) return EJB_ERR_INVALID;
     *out = nullptr;
-    if (n_devices != 1) return EJB_ERR_UNSUPPORTED;  // one context drives one GPU; ranks/processes shard buckets (ejb_set_shard)
+    if (n_devices < 1 || n_devices > 64) return EJB_ERR_INVALID;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return EJB_ERR_NO_DEVICE;
-    const int dev = device_ids ? device_ids[0] : 0;
-    if (dev < 0 || dev >= count) return EJB_ERR_NO_DEVICE;
-    ejb_ctx* c = new ejb_ctx();
-    c->device = dev;
-    if (cudaSetDevice(dev) != cudaSuccess) {
-        delete c;
-        return EJB_ERR_NO_DEVICE;
+    std::vector<int> devs((size_t)n_devices);
+    for (int i = 0; i < n_devices; i++) {
+        devs[i] = device_ids ? device_ids[i] : i;
+        if (devs[i] < 0 || devs[i] >= count) return EJB_ERR_NO_DEVICE;
+        for (int j = 0; j < i; j++)
+            if (devs[j] == devs[i]) return EJB_ERR_INVALID;   // one context per device
     }
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, dev);
-    c->sm_count = prop.multiProcessorCount;
-    if (const char* e = getenv("EJB_CAND_CAP")) {
-        c->cand_cap = std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
-        c->cap_explicit = true;
+    ejb_ctx* c = nullptr;
+    int rc = create_one(&c, devs[0]);
+    if (rc) return rc;
+    // one peer context per further device; created concurrently (each builds its Stirling table on its own GPU)
+    if (n_devices > 1) {
+        std::vector<ejb_ctx*> peers((size_t)n_devices - 1, nullptr);
+        std::vector<int> rcs((size_t)n_devices - 1, 0);
+        std::vector<std::thread> th;
+        for (int i = 1; i < n_devices; i++) th.emplace_back([&, i] { rcs[i - 1] = create_one(&peers[i - 1], devs[i]); });
+        for (auto& t : th) t.join();
+        for (int i = 1; i < n_devices; i++) {
+            if (peers[i - 1]) c->peers.push_back(peers[i - 1]);
+            if (rcs[i - 1] && !rc) rc = rcs[i - 1];
+        }
+        if (rc) {
+            destroy_ctx(c);
+            return rc;
+        }
+        cudaSetDevice(devs[0]);
     }
-    if (const char* e = getenv("EJB_PAIR_BUDGET")) c->pair_budget = std::max<unsigned long long>(1ull << 16, strtoull(e, nullptr, 10));
-    auto bail = [&](int code) {
-        std::string m = c->err;
-        delete c;
-        (void)m;
-        return code;
-    };
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(EJB_ERR_CUDA);
-    for (int i = 0; i < ejb_ctx::N_UP; i++)
-        if (cudaStreamCreateWithFlags(&c->up_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&c->up_event[i], cudaEventDisableTiming) != cudaSuccess)
-            return bail(EJB_ERR_CUDA);
-    if (cudaMallocHost(&c->h_ctr, sizeof(Counters)) != cudaSuccess) return bail(EJB_ERR_OOM);
-    const std::vector<dd_t>& sr = sr_table_host();
-    if (c->d_sr.ensure(sr.size() * sizeof(dd_t)) != cudaSuccess) return bail(EJB_ERR_OOM);
-    cudaMemcpyAsync(c->d_sr.p, sr.data(), sr.size() * sizeof(dd_t), cudaMemcpyHostToDevice, c->stream);
-    if (c->d_p1_keys.ensure((size_t)c->p1_cap * 8) != cudaSuccess || c->d_p1_vals.ensure((size_t)c->p1_cap * 8) != cudaSuccess ||
-        c->d_p1_new.ensure((size_t)c->p1_cap * 4) != cudaSuccess || c->d_ctr.ensure(sizeof(Counters)) != cudaSuccess ||
-        c->d_err.ensure(64) != cudaSuccess)
-        return bail(EJB_ERR_OOM);
-    cudaMemsetAsync(c->d_p1_keys.p, 0xff, (size_t)c->p1_cap * 8, c->stream);
-    cudaMemsetAsync(c->d_ctr.p, 0, sizeof(Counters), c->stream);
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(EJB_ERR_CUDA);
-    memset(&c->stats, 0, sizeof(c->stats));
     *out = c;
     return EJB_OK;
 }
 
-void ejb_destroy(ejb_ctx* c) {
-    if (!c) return;
-    cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
-    for (auto e : c->ev_pool) cudaEventDestroy(e);
-    if (c->h_ctr) cudaFreeHost(c->h_ctr);
-    if (c->h_res) cudaFreeHost(c->h_res);
-    c->in_bufs.clear();
-    for (int i = 0; i < ejb_ctx::N_UP; i++) {
-        if (c->up_event[i]) cudaEventDestroy(c->up_event[i]);
-        if (c->up_stream[i]) cudaStreamDestroy(c->up_stream[i]);
-    }
-    if (c->stream) cudaStreamDestroy(c->stream);
-    delete c;
+void ejb_destroy(ejb_ctx* c) { destroy_ctx(c); }
+
+int ejb_set_option(ejb_ctx* c, const char* name, long long value) {
+    if (!c || !name) return EJB_ERR_INVALID;
+    const std::string n(name);
+    auto apply = [&](ejb_ctx* x) {
+        if (n == "first_unit") x->opt.first_unit = std::max(1ll, value);
+        else if (n == "growth") x->opt.growth = std::max(1ll, value);
+        else if (n == "s1_mode") x->opt.s1_mode = (int)value & 3;
+        else if (n == "no_tags") x->opt.no_tags = value != 0;
+        else if (n == "trace") x->opt.trace = value != 0;
+        else return false;
+        return true;
+    };
+    if (!apply(c)) return fail(c, EJB_ERR_INVALID, "unknown option '%s'", name);
+    for (ejb_ctx* p : c->peers) apply(p);
+    return EJB_OK;
 }
 
 // Multi-GPU: this context only joins the sub-buckets it owns (LPT by pair count over `world`
@@ -500,18 +650,22 @@ int ejb_set_input_arena(ejb_ctx* c, const void* base, uint64_t bytes) {
 
 int ejb_set_capacity(ejb_ctx* c, unsigned long long cand_cap, unsigned long long pair_budget) {
     if (!c) return EJB_ERR_INVALID;
-    if (cand_cap) {
-        c->cand_cap = std::max<unsigned long long>(1024, cand_cap);
-        c->cap_explicit = true;
-    }
-    if (pair_budget) c->pair_budget = std::max<unsigned long long>(1ull << 14, pair_budget);
+    auto apply = [&](ejb_ctx* x) {
+        if (cand_cap) {
+            x->cand_cap = std::max<unsigned long long>(1024, cand_cap);
+            x->cap_explicit = true;
+        }
+        if (pair_budget) x->pair_budget = std::max<unsigned long long>(1ull << 14, pair_budget);
+    };
+    apply(c);
+    for (ejb_ctx* p : c->peers) apply(p);
     return EJB_OK;
 }
 
 int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     if (!c || !p || !in) return EJB_ERR_INVALID;
     CK(cudaSetDevice(c->device));
-    c->have_input = c->have_run = false;
+    c->have_input = c->have_run = c->prepared = false;
     int rc = check_params(c, p);
     if (rc) return rc;
     if (in->n_rows < 0 || in->n_rows >= (1ll << 28)) return fail(c, EJB_ERR_INVALID, "n_rows out of range (need 0 <= n < 2^28)");
@@ -528,23 +682,24 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     d.n_segs = in->n_segs; d.n_refs = in->n_refs;
     d.n_tig_bytes = in->n_tig_bytes; d.n_cdr3_bytes = in->n_cdr3_bytes; d.n_amino_bytes = in->n_amino_bytes;
     d.n_tig2_words = in->row_tig2_off ? in->n_tig2_words : 0;
+    d.n_cdr32_words = in->row_cdr32_off ? in->n_cdr32_words : 0;
     const int64_t N = in->n_rows;
+    // host-side checks come before anything is dereferenced or queued
+    if (in->n_segs > 0 && (!in->seg_off || !in->seg_bytes)) return fail(c, EJB_ERR_INVALID, "seg_off / seg_bytes is null");
+    if (in->n_refs > 0 && !in->ref_off) return fail(c, EJB_ERR_INVALID, "ref_off is null");
+    d.n_seg_bytes = in->n_segs > 0 ? in->seg_off[in->n_segs] : 0;
+    d.n_ref_bytes = in->n_refs > 0 ? in->ref_off[in->n_refs] : 0;
+    if (d.n_seg_bytes < 0 || d.n_ref_bytes < 0) return fail(c, EJB_ERR_INVALID, "negative seg/ref byte count");
     if (c->arena_base) {   // one DMA for everything the caller keeps in its arena
         CK(c->d_arena.ensure(c->arena_bytes + 256));
         CK(cudaMemcpyAsync(c->d_arena.p, c->arena_base, c->arena_bytes, cudaMemcpyHostToDevice, c->up_stream[c->up_next++ % ejb_ctx::N_UP]));
         c->h2d_bytes += (int64_t)c->arena_bytes;
     }
-    // host-side: seg / ref byte totals need the last offset
-    if (in->n_segs > 0 && !in->seg_off) return fail(c, EJB_ERR_INVALID, "seg_off is null");
-    if (in->n_refs > 0 && !in->ref_off) return fail(c, EJB_ERR_INVALID, "ref_off is null");
-    d.n_seg_bytes = in->n_segs > 0 ? in->seg_off[in->n_segs] : 0;
-    d.n_ref_bytes = in->n_refs > 0 ? in->ref_off[in->n_refs] : 0;
-    if (d.n_seg_bytes < 0 || d.n_ref_bytes < 0) return fail(c, EJB_ERR_INVALID, "negative seg/ref byte count");
     // content-canonical seg ids: DnaString equality is by content (join_one.rs:331)
     std::vector<int32_t> canon((size_t)std::max<int64_t>(in->n_segs, 1), 0);
     std::vector<uint8_t> seg_canon_bytes((size_t)std::max<int64_t>(d.n_seg_bytes, 1), 'A');   // DnaString content: upper-case ACGT, anything else -> A
     {
-        std::map<std::string, int> ids;
+        std::unordered_map<std::string, int> ids;
         for (int64_t s = 0; s < in->n_segs; s++) {
             const int64_t a = in->seg_off[s], b = in->seg_off[s + 1];
             if (a < 0 || b < a || b > d.n_seg_bytes) return fail(c, EJB_ERR_INVALID, "seg_off not monotone");
@@ -565,9 +720,8 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
         c->n_canon_segs = (int64_t)ids.size();
     }
 #define UP(field, n) if ((rc = upload_array(c, in->field, (n), &d.field)) != EJB_OK) return rc
-    UP(row_nchains, N); UP(row_len, 2 * N); UP(row_tig_off, 2 * N); UP(row_has_del, 2 * N); UP(row_vs, 2 * N); UP(row_js, 2 * N);
-    UP(row_cdr3_off, 2 * N); UP(row_cdr3_len, 2 * N); UP(row_exact, N); UP(row_exact_col, 2 * N);
-    UP(tig_bytes, in->n_tig_bytes); UP(cdr3_bytes, in->n_cdr3_bytes);
+    UP(row_nchains, N); UP(row_len, 2 * N); UP(row_has_del, 2 * N); UP(row_vs, 2 * N); UP(row_js, 2 * N);
+    UP(row_cdr3_len, 2 * N); UP(row_exact, N); UP(row_exact_col, 2 * N);
     UP(ex_chain_off, in->n_exacts + 1); UP(ex_cell_off, in->n_exacts + 1);
     UP(ch_left, in->n_chains); UP(ch_c_ref, in->n_chains); UP(ch_v_ref, in->n_chains); UP(ch_u_ref, in->n_chains);
     UP(ch_hcomp, in->n_chains); UP(ch_amino_off, in->n_chains); UP(ch_amino_len, in->n_chains);
@@ -575,6 +729,21 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     UP(seg_off, in->n_segs + 1); UP(ref_off, in->n_refs + 1); UP(ref_bytes, d.n_ref_bytes);
     UP(ref_name_id, in->n_refs);
 #undef UP
+    // ASCII contigs / CDR3s may be absent altogether when every row supplies the 2-bit packed form
+    if (in->n_tig_bytes > 0 || !in->row_tig2_off) {
+        if ((rc = upload_array(c, in->row_tig_off, 2 * N, &d.row_tig_off)) != EJB_OK) return rc;
+        if ((rc = upload_array(c, in->tig_bytes, in->n_tig_bytes, &d.tig_bytes)) != EJB_OK) return rc;
+    } else {
+        if ((rc = upload_array(c, (const uint8_t*)nullptr, 0, &d.tig_bytes)) != EJB_OK) return rc;
+        d.row_tig_off = nullptr;
+    }
+    if (in->n_cdr3_bytes > 0 || !in->row_cdr32_off) {
+        if ((rc = upload_array(c, in->row_cdr3_off, 2 * N, &d.row_cdr3_off)) != EJB_OK) return rc;
+        if ((rc = upload_array(c, in->cdr3_bytes, in->n_cdr3_bytes, &d.cdr3_bytes)) != EJB_OK) return rc;
+    } else {
+        if ((rc = upload_array(c, (const uint8_t*)nullptr, 0, &d.cdr3_bytes)) != EJB_OK) return rc;
+        d.row_cdr3_off = nullptr;
+    }
     if ((rc = upload_array(c, in->ch_fr1_start, in->n_chains, &d.ch_fr1)) != EJB_OK) return rc;
     if ((rc = upload_array(c, in->ch_cdr1_start, in->n_chains, &d.ch_cdr1)) != EJB_OK) return rc;
     if ((rc = upload_array(c, in->ch_fr2_start, in->n_chains, &d.ch_fr2)) != EJB_OK) return rc;
@@ -584,14 +753,17 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
         if ((rc = upload_array(c, in->row_tig2_off, 2 * N, &d.row_tig2_off)) != EJB_OK) return rc;
         if ((rc = upload_array(c, in->tig2_words, in->n_tig2_words, &d.tig2_words)) != EJB_OK) return rc;
     }
+    if (in->row_cdr32_off) {
+        if ((rc = upload_array(c, in->row_cdr32_off, 2 * N, &d.row_cdr32_off)) != EJB_OK) return rc;
+        if ((rc = upload_array(c, in->cdr32_words, in->n_cdr32_words, &d.cdr32_words)) != EJB_OK) return rc;
+    }
     if ((rc = upload_array(c, canon.data(), in->n_segs, &d.seg_canon)) != EJB_OK) return rc;
-    if (in->n_segs > 0 && !in->seg_bytes) return fail(c, EJB_ERR_INVALID, "seg_bytes is null");
     if ((rc = upload_array(c, (const uint8_t*)seg_canon_bytes.data(), d.n_seg_bytes, &d.seg_bytes)) != EJB_OK) return rc;
     for (int i = 0; i < ejb_ctx::N_UP; i++) {   // the join's stream continues after every copy stream
         CK(cudaEventRecord(c->up_event[i], c->up_stream[i]));
         CK(cudaStreamWaitEvent(c->stream, c->up_event[i], 0));
     }
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->stream));   // canon / seg_canon_bytes are host temporaries
     c->ms_h2d = now_ms() - t0;
     c->have_input = true;
     return EJB_OK;
@@ -626,8 +798,10 @@ int cub_incl_sum(ejb_ctx* c, const int32_t* in, int32_t* out, int64_t n) {
     return EJB_OK;
 }
 
-// One scheduler round: stage 1 over `units`, stage 2, forest update.  Returns 1 when the
-// candidate buffer overflowed (nothing committed; the caller splits the round and retries).
+// One scheduler round, queued as ONE uninterrupted piece of stream work: stage 1 over `units`, the truncation of the units from
+// the counted candidates (k_truncate), stage 2, the forest update (k_forest_round: Boruvka to convergence on the device), and a
+// single read-back of the round's report.  Returns 1 when a work buffer overflowed (nothing committed; the caller splits the
+// round and retries).
 int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& times) {
     const unsigned long long eval_before = c->pairs_eval_seen;
     const std::vector<SubBucket>& subs = c->subs;
@@ -635,10 +809,13 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     std::vector<RowTask> tasks[MAXW1 + 1];
     std::vector<ejb_ctx::TaskMeta> metas[MAXW1 + 1];
     int64_t nctas[MAXW1 + 1] = {0};
+    std::vector<UnitDesc> udesc(units.size());
+    std::vector<int> ugroup(units.size());
     for (size_t ui = 0; ui < units.size(); ui++) {
         const Unit& u = units[ui];
         const SubBucket& sb = subs[u.sub];
         const int nb = (sb.n + TILE - 1) / TILE;
+        const size_t first = tasks[sb.W1].size();
         for (int rb = u.r0 / TILE; rb * TILE < u.r1; rb++) {
             RowTask t;
             t.tid = 0;
@@ -652,196 +829,166 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
             metas[sb.W1].push_back({(int32_t)ui, rb * TILE + t.row_lo, rb * TILE + t.row_hi});
             nctas[sb.W1] += (nb - rb + S1_STRIP - 1) / S1_STRIP;
         }
+        UnitDesc& d = udesc[ui];
+        d.sub = u.sub;
+        d.t0 = (int32_t)first;
+        d.nt = (int32_t)(tasks[sb.W1].size() - first);
+        d.r1 = u.r1;
+        d.allow = u.allow;
+        d.strict = u.strict;
+        d.rho_ref = u.rho_ref;
+        ugroup[ui] = sb.W1;
     }
     c->task_meta.clear();
+    std::vector<RowTask> all_tasks;
+    size_t goff[MAXW1 + 2] = {0};
     for (int w = 0; w <= MAXW1; w++) {
+        goff[w] = all_tasks.size();
         for (size_t i = 0; i < tasks[w].size(); i++) {
             tasks[w][i].tid = (int32_t)c->task_meta.size();
             c->task_meta.push_back(metas[w][i]);
+            all_tasks.push_back(tasks[w][i]);
         }
     }
-    size_t total_tasks = 0;
-    for (auto& v : tasks) total_tasks += v.size();
-    CK(c->d_tasks.ensure(total_tasks * sizeof(RowTask)));
-    CK(c->d_unitcand.ensure(total_tasks * 8 + 8));
-    CK(cudaMemsetAsync(c->d_unitcand.p, 0, total_tasks * 8 + 8, c->stream));
-    c->h_unitcand.assign(total_tasks, 0);
+    for (size_t ui = 0; ui < units.size(); ui++) udesc[ui].t0 += (int32_t)goff[ugroup[ui]];
+    const size_t total_tasks = all_tasks.size(), n_units = units.size();
+    if (n_units > c->round_units_cap || total_tasks > c->round_tasks_cap) return fail(c, EJB_ERR_CUDA, "round report buffer too small (%zu units, %zu tasks)", n_units, total_tasks);
+    // report layout of this round: [Counters | UnitOut x n_units | candidate count x total_tasks]
+    char* const rbase = c->d_round.as<char>();
+    UnitOut* const d_uout = reinterpret_cast<UnitOut*>(rbase + sizeof(Counters));
+    unsigned long long* const d_ucand = reinterpret_cast<unsigned long long*>(rbase + sizeof(Counters) + n_units * sizeof(UnitOut));
+    const size_t report_bytes = sizeof(Counters) + n_units * sizeof(UnitOut) + total_tasks * 8;
+    cudaStream_t st = c->stream;
+    CK(c->d_tasks.ensure(total_tasks * sizeof(RowTask) + 64));
+    CK(c->d_units.ensure(n_units * sizeof(UnitDesc) + 64));
+    CK(cudaMemsetAsync(rbase, 0, offsetof(Counters, round_end), st));
+    CK(cudaMemsetAsync(rbase + sizeof(Counters), 0, report_bytes - sizeof(Counters), st));
+    CK(cudaMemcpyAsync(c->d_tasks.p, all_tasks.data(), total_tasks * sizeof(RowTask), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_units.p, udesc.data(), n_units * sizeof(UnitDesc), cudaMemcpyHostToDevice, st));
     RoundTimes rt;
     rt.e0 = c->ev(); rt.e1 = c->ev(); rt.e2 = c->ev(); rt.e3 = c->ev();
-    CK(zero_counter(c, offsetof(Counters, n_cand)));
-    CK(zero_counter(c, offsetof(Counters, n_pass)));
-    CK(zero_counter(c, offsetof(Counters, overflow)));
-    CK(cudaEventRecord(rt.e0, c->stream));
-    if (c->tags_on && (c->s1_mode & S1_TAGS)) {
-        k_row_flags<<<nblk(c->n_pos, 256), 256, 0, c->stream>>>(c->d_m_sub.as<int32_t>(), c->d_m_row.as<int32_t>(), c->n_pos, c->d_subdom.as<SubDom>(),
-                                                               c->d_tagq.as<unsigned long long>(), c->d_deadq.as<unsigned long long>(),
-                                                               c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>());
-        c->stats.kernel_launches++;
-    }
-    size_t off = 0;
+    CK(cudaEventRecord(rt.e0, st));
+    if (c->tags_on && (c->opt.s1_mode & S1_TAGS))
+        launch(c, k_row_flags, nblk(c->n_pos, 256), 256, c->d_m_sub.as<const int32_t>(), c->d_m_row.as<const int32_t>(), c->n_pos, c->d_subdom.as<const SubDom>(),
+               c->d_tagq.as<const unsigned long long>(), c->d_deadq.as<const unsigned long long>(), c->d_donq.as<const unsigned long long>(), c->d_flagq.as<uint32_t>());
     for (int w = 0; w <= MAXW1; w++) {
         if (tasks[w].empty()) continue;
-        RowTask* dt = c->d_tasks.as<RowTask>() + off;
-        CK(cudaMemcpyAsync(dt, tasks[w].data(), tasks[w].size() * sizeof(RowTask), cudaMemcpyHostToDevice, c->stream));
+        const RowTask* dt = c->d_tasks.as<RowTask>() + goff[w];
         const int nt = (int)tasks[w].size();
         switch (w) {
             case 0:
-                k_stage1_nofilter<<<(unsigned int)nctas[0], 256, 0, c->stream>>>(c->d_subs.as<SubBucket>(), dt, nt, c->d_labq.as<int32_t>(),
-                                                                                c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr.as<Counters>(), c->d_unitcand.as<unsigned long long>());
+                launch(c, k_stage1_nofilter, (unsigned int)nctas[0], 256, c->d_subs.as<const SubBucket>(), dt, nt, c->d_labq.as<const int32_t>(), c->d_cand.as<uint2>(),
+                       c->cand_cap, c->d_ctr(), d_ucand);
                 break;
-            case 1: launch_stage1_w<1>(c, nctas[1], dt, nt); break;
-            case 2: launch_stage1_w<2>(c, nctas[2], dt, nt); break;
-            case 3: launch_stage1_w<3>(c, nctas[3], dt, nt); break;
-            case 4: launch_stage1_w<4>(c, nctas[4], dt, nt); break;
-            case 5: launch_stage1_w<5>(c, nctas[5], dt, nt); break;
-            case 6: launch_stage1_w<6>(c, nctas[6], dt, nt); break;
+            case 1: launch_stage1_w<1>(c, nctas[1], dt, nt, d_ucand); break;
+            case 2: launch_stage1_w<2>(c, nctas[2], dt, nt, d_ucand); break;
+            case 3: launch_stage1_w<3>(c, nctas[3], dt, nt, d_ucand); break;
+            case 4: launch_stage1_w<4>(c, nctas[4], dt, nt, d_ucand); break;
+            case 5: launch_stage1_w<5>(c, nctas[5], dt, nt, d_ucand); break;
+            case 6: launch_stage1_w<6>(c, nctas[6], dt, nt, d_ucand); break;
         }
-        c->stats.kernel_launches++;
         c->stats.stage1_launches++;
-        off += tasks[w].size();
     }
+    // truncate units whose counted candidates exceed their allowance (on the device: no read-back between stage 1 and stage 2)
+    launch(c, k_truncate, nblk((int64_t)n_units, 128), 128, c->d_units.as<const UnitDesc>(), (int)n_units, c->d_tasks.as<const RowTask>(),
+           (const unsigned long long*)d_ucand, c->d_subs.as<const SubBucket>(), c->d_qcut.as<int32_t>(), c->d_subpass.as<unsigned int>(), d_uout, c->d_ctr());
     CK(cudaGetLastError());
-    CK(cudaEventRecord(rt.e1, c->stream));
-    // check the candidate count before spending stage 2 on a round that cannot be committed
-    CK(cudaMemcpyAsync(c->h_unitcand.data(), c->d_unitcand.p, total_tasks * 8, cudaMemcpyDeviceToHost, c->stream));
-    int rc = sync_counters(c);
+    CK(cudaEventRecord(rt.e1, st));
+    int rc = run_stage2(c, c->d_cand.as<uint2>(), nullptr, CTR_FIELD(n_cand), c->cand_cap, 0, nullptr);
     if (rc) return rc;
-    if (c->h_ctr->overflow || c->h_ctr->n_cand > c->cand_cap) {
-        c->pairs_eval_seen = c->h_ctr->pairs_eval;
-        c->stats.overflow_retries++;
-        return 1;
-    }
-    // truncate units whose counted candidates exceed their allowance: keep whole row ranges up to (and including) the one
-    // that crosses it; stage 2 ignores candidates of the rows cut away and the scheduler resumes from the cut
-    std::vector<std::pair<int32_t, int32_t>> cuts;   // (sub, packed position limit)
+    CK(cudaEventRecord(rt.e2, st));
     {
-        for (Unit& u : units) u.cand = 0.0;
-        std::vector<char> closed(units.size(), 0), jumped(units.size(), 0);
-        std::vector<double> after_jump(units.size(), 0.0);
-        for (size_t t = 0; t < c->task_meta.size(); t++) {   // tasks of one unit are consecutive and in row order
-            const auto& m = c->task_meta[t];
-            Unit& u = units[m.unit];
-            if (closed[m.unit]) continue;
-            const double cnt = (double)c->h_unitcand[t];
-            // a jump in density = a region (typically a clone not connected yet) the pass-rate estimate knows nothing about
-            if (!jumped[m.unit] && (u.rho_ref < 0.0 || cnt / (double)std::max(1, m.r1 - m.r0) > 8.0 * u.rho_ref + 16.0)) jumped[m.unit] = 1;
-            u.cand += cnt;
-            if (jumped[m.unit]) after_jump[m.unit] += cnt;
-            if ((u.cand > u.allow || (jumped[m.unit] && after_jump[m.unit] > u.strict)) && m.r1 < u.r1) {
-                u.r1 = m.r1;
-                closed[m.unit] = 1;
-                cuts.emplace_back(u.sub, (int32_t)(subs[u.sub].q0 + m.r1));
-            }
-        }
-        for (auto& ct : cuts) CK(cudaMemcpyAsync(c->d_qcut.as<int32_t>() + ct.first, &ct.second, 4, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemsetAsync(c->d_subpass.p, 0, subs.size() * 4, c->stream));
+        ForestArgs A;
+        A.pass_w = c->d_pass.as<unsigned long long>();
+        A.pass_t = c->d_passt.as<PassTuple>();
+        A.n_pass_p = CTR_FIELD(n_pass);
+        A.cap = c->cand_cap;
+        A.parent = c->d_parent.as<int32_t>();
+        A.best = c->d_best.as<unsigned long long>();
+        A.roots = c->d_roots.as<int2>();
+        A.forest = c->d_forest.as<unsigned long long>();
+        A.forest_t = c->d_forestt.as<PassTuple>();
+        A.forest_cap = c->forest_cap;
+        A.ctr = c->d_ctr();
+        A.bar = c->d_bar.as<unsigned int>();
+        A.rowq = c->d_m_row.as<int32_t>();
+        A.n_pos = c->n_pos;
+        A.labq = c->d_labq.as<int32_t>();
+        A.subs = c->d_subs.as<SubBucket>();
+        A.blk_lab = c->d_blklab.as<int32_t>();
+        A.blk_sub = c->d_blksub.as<int32_t>();
+        A.n_blocks = (int)c->n_blocks;
+        CK(cudaMemsetAsync(c->d_bar.p, 0, 4, st));
+        void* args[] = {&A};
+        CK(cudaLaunchCooperativeKernel((const void*)k_forest_round, dim3((unsigned int)c->coop_grid), dim3(256), args, 0, st));
+        c->stats.kernel_launches++;
     }
-    rc = run_stage2(c, c->d_cand.as<uint2>(), nullptr, CTR_FIELD(n_cand), 0);
+    launch(c, k_round_report, nblk((int64_t)n_units, 128), 128, c->d_units.as<const UnitDesc>(), (int)n_units, c->d_subpass.as<const unsigned int>(), d_uout);
+    CK(cudaEventRecord(rt.e3, st));
+    CK(c->h_round.ensure(report_bytes));
+    CK(cudaMemcpyAsync(c->h_round.p, rbase, report_bytes, cudaMemcpyDeviceToHost, st));
+    rc = sync_stream(c);
     if (rc) return rc;
-    {
-        static const int32_t kNoCut = 0x7fffffff;
-        for (auto& ct : cuts) CK(cudaMemcpyAsync(c->d_qcut.as<int32_t>() + ct.first, &kNoCut, 4, cudaMemcpyHostToDevice, c->stream));
-        c->h_subpass.resize(subs.size());
-        CK(cudaMemcpyAsync(c->h_subpass.data(), c->d_subpass.p, subs.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-    }
-    CK(cudaEventRecord(rt.e2, c->stream));
-    // first Borůvka iteration is launched speculatively; its result is only used when nothing overflowed
-    const int grid = c->sm_count * 8;
-    CK(zero_counter(c, offsetof(Counters, n_alive)));
-    k_fill_u64<<<nblk(c->din.n_rows, 256), 256, 0, c->stream>>>(c->d_best.as<unsigned long long>(), c->din.n_rows, ~0ull);
-    k_bor_min<<<grid, 256, 0, c->stream>>>(c->d_pass.as<unsigned long long>(), CTR_FIELD(n_pass), c->cand_cap, c->d_parent.as<int32_t>(),
-                                          c->d_best.as<unsigned long long>(), 0, c->d_roots.as<int2>(), c->d_ctr.as<Counters>());
-    c->stats.kernel_launches += 2;
-    rc = sync_counters(c);
-    if (rc) return rc;
-    const Counters& h = *c->h_ctr;
+    c->stats.d2h_bytes += (int64_t)report_bytes;
+    const Counters& h = *c->h_round.as<Counters>();
+    const UnitOut* uo = reinterpret_cast<const UnitOut*>(c->h_round.as<char>() + sizeof(Counters));
+    const unsigned long long* uc = reinterpret_cast<const unsigned long long*>(c->h_round.as<char>() + sizeof(Counters) + n_units * sizeof(UnitOut));
+    c->h_unitcand.assign(uc, uc + total_tasks);
+    c->p1_count += h.n_newkeys;
+    c->stats.p1_unique += (int64_t)h.n_newkeys;
+    if (h.p1_full) return fail(c, EJB_ERR_OOM, "p1 cache full (%llu keys in %u slots)", c->p1_count, c->p1_cap);
+    if (h.overflow == 2ull) return fail(c, EJB_ERR_CUDA, "forest buffer overflow");
     if (h.overflow || h.n_cand > c->cand_cap || h.n_surv > c->cand_cap || h.n_pass > c->cand_cap || h.n_slow > c->cand_cap) {
         if (h.pairs_eval > eval_before) c->cand_rate = std::max(c->cand_rate, (double)h.n_cand / (double)(h.pairs_eval - eval_before));
         c->pairs_eval_seen = h.pairs_eval;
         c->stats.overflow_retries++;
+        if (c->p1_count > c->p1_cap / 4 && (rc = p1_cache_grow(c)) != EJB_OK) return rc;
         return 1;
     }
-    if (h.n_newkeys > c->p1_cap / 2) return fail(c, EJB_ERR_OOM, "p1 cache overflow (%llu new keys in one round)", h.n_newkeys);
     if (h.n_errflag_range) return fail(c, EJB_ERR_RANGE, "k = indeps + 2*shares exceeds the Stirling table (k > 3000); the reference panics here (join_one.rs:30)");
     if (h.n_errflag_panic) return fail(c, EJB_ERR_INVALID, "input on which the reference panics (J range longer than a contig, seg shorter than ref trim, or inconsistent feature starts)");
-    c->p1_count += h.n_newkeys;
-    c->stats.p1_unique += (int64_t)h.n_newkeys;
+    if (h.alive_it[BOR_MAX_ITERS]) return fail(c, EJB_ERR_CUDA, "forest did not converge");
     if (h.pairs_eval > eval_before) c->cand_rate = (double)h.n_cand / (double)(h.pairs_eval - eval_before);   // most recent round
     c->pairs_eval_seen = h.pairs_eval;
     c->stats.stage1_candidates += (int64_t)h.n_cand;
     c->stats.stage2_slow += (int64_t)h.n_slow;
     c->stats.stage2_survivors += (int64_t)h.n_surv_total;
     c->stats.pass_edges += (int64_t)h.n_pass;
-    for (Unit& u : units) u.pass = (double)c->h_subpass[(size_t)u.sub];
-    if (h.n_pass > 0) {
-        int iter = 0;
-        unsigned long long alive = h.n_alive;
-        while (alive > 0) {
-            if (iter >= 60) return fail(c, EJB_ERR_CUDA, "forest did not converge");
-            k_bor_hook<<<grid, 256, 0, c->stream>>>(c->d_pass.as<unsigned long long>(), CTR_FIELD(n_pass), c->cand_cap, c->d_parent.as<int32_t>(),
-                                                   c->d_best.as<unsigned long long>(), iter, c->d_roots.as<int2>(),
-                                                   c->d_forest.as<unsigned long long>(), c->forest_cap, c->d_ctr.as<Counters>());
-            k_bor_compress<<<grid, 256, 0, c->stream>>>(CTR_FIELD(n_pass), c->cand_cap, c->d_parent.as<int32_t>(), c->d_roots.as<int2>());
-            iter++;
-            CK(zero_counter(c, offsetof(Counters, n_alive)));
-            k_bor_min<<<grid, 256, 0, c->stream>>>(c->d_pass.as<unsigned long long>(), CTR_FIELD(n_pass), c->cand_cap, c->d_parent.as<int32_t>(),
-                                                  c->d_best.as<unsigned long long>(), iter, c->d_roots.as<int2>(), c->d_ctr.as<Counters>());
-            c->stats.kernel_launches += 3;
-            rc = sync_counters(c);
-            if (rc) return rc;
-            if (c->h_ctr->overflow) return fail(c, EJB_ERR_CUDA, "forest buffer overflow");
-            alive = c->h_ctr->n_alive;
-        }
-        k_flatten<<<nblk(c->n_pos, 256), 256, 0, c->stream>>>(c->d_parent.as<int32_t>(), c->d_m_row.as<int32_t>(), c->n_pos, c->d_labq.as<int32_t>());
-        k_block_labels<<<nblk(c->n_blocks * 32, 256), 256, 0, c->stream>>>(c->d_subs.as<SubBucket>(), (int)subs.size(), c->d_labq.as<int32_t>(),
-                                                                          c->d_blklab.as<int32_t>(), c->d_blksub.as<int32_t>(), (int)c->n_blocks);
-        c->stats.kernel_launches += 2;
+    for (size_t ui = 0; ui < n_units; ui++) {
+        units[ui].r1 = uo[ui].r1;
+        units[ui].cand = uo[ui].cand;
+        units[ui].pass = (double)uo[ui].pass;
     }
-    CK(cudaEventRecord(rt.e3, c->stream));
     times.push_back(rt);
-    if (getenv("EJB_TRACE")) {   // developer aid: what the round was made of
+    if (c->opt.trace) {   // developer aid: what the round was made of
         size_t top = 0;
         for (size_t i = 1; i < units.size(); i++)
             if (units[i].cand > units[top].cand) top = i;
-        const Counters& hh = *c->h_ctr;
         fprintf(stderr, "[ejb trace] round %lld: %zu units, cand %llu surv %llu pass %llu; top unit: sub %d (n %d) rows [%d,%d) cand %.0f pass %.0f\n",
-                (long long)c->stats.rounds, units.size(), hh.n_cand, hh.n_surv_total, hh.n_pass, units.empty() ? -1 : units[top].sub,
+                (long long)c->stats.rounds, units.size(), h.n_cand, h.n_surv_total, h.n_pass, units.empty() ? -1 : units[top].sub,
                 units.empty() ? 0 : subs[units[top].sub].n, units.empty() ? 0 : units[top].r0, units.empty() ? 0 : units[top].r1,
                 units.empty() ? 0.0 : units[top].cand, units.empty() ? 0.0 : units[top].pass);
     }
     c->stats.rounds++;
+    if (c->p1_count > c->p1_cap / 4 && (rc = p1_cache_grow(c)) != EJB_OK) return rc;
     return EJB_OK;
 }
 
-}  // namespace
-
-extern "C" int ejb_run(ejb_ctx* c) {
-    if (!c) return EJB_ERR_INVALID;
-    if (!c->have_input) return fail(c, EJB_ERR_INVALID, "ejb_run without ejb_upload");
-    CK(cudaSetDevice(c->device));
-    c->have_run = false;
-    const double t_wall0 = now_ms();
-    memset(&c->stats, 0, sizeof(c->stats));
-    c->ev_used = 0;
-    c->s2a_events.clear();
+// ---- prepare: bucket scan, sub-bucket table, bucketer.  ONE read-back (the run header + the sub-bucket table). ----
+int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     const DevIn& din = c->din;
     const int64_t N = din.n_rows;
     cudaStream_t st = c->stream;
-    cudaEvent_t ev_start = c->ev(), ev_packed = c->ev(), ev_rounds = c->ev(), ev_end = c->ev();
-    // EJB_TRACE=1: finer CUDA events inside the prepare phase, printed to stderr (developer aid)
-    const bool trace = getenv("EJB_TRACE") != nullptr;
-    std::vector<std::pair<const char*, cudaEvent_t>> tr;
     auto mark = [&](const char* name) {
-        if (!trace) return;
+        if (!c->opt.trace) return;
         cudaEvent_t e = c->ev();
         cudaEventRecord(e, st);
         tr.emplace_back(name, e);
     };
-    CK(cudaEventRecord(ev_start, st));
     mark("start");
-    CK(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(Counters), st));
-    CK(cudaMemsetAsync(c->d_err.p, 0, 64, st));
-    if (c->p1_count > c->p1_cap / 4) {
+    RunHdr* const hdr = c->d_err.as<RunHdr>();
+    CK(cudaMemsetAsync(c->d_err.p, 0, 256, st));
+    if (c->p1_count > c->p1_cap / 8) {
         int rc = p1_cache_clear(c);
         if (rc) return rc;
     }
@@ -854,241 +1001,262 @@ extern "C" int ejb_run(ejb_ctx* c) {
     }
     c->subs.clear();
     c->n_active = c->n_pos = c->n_blocks = c->n_final = 0;
-    std::vector<RoundTimes> times;
-
-    if (N > 0) {
-        // ---- bucket scan + sub-bucket sort (join.rs:68-88) ----
-        CK(c->d_head.ensure((size_t)N * 4));
-        CK(c->d_scan.ensure((size_t)N * 4));
-        CK(c->d_keys.ensure((size_t)N * 8));
-        CK(c->d_keys2.ensure((size_t)N * 8));
-        CK(c->d_vals.ensure((size_t)N * 4));
-        CK(c->d_vals2.ensure((size_t)N * 4));
-        k_heads<<<nblk(N, 256), 256, 0, st>>>(din, c->d_head.as<int32_t>(), c->d_err.as<unsigned int>());
-        const int64_t tmax = std::max({din.n_exacts, din.n_chains, din.n_cells, din.n_segs, din.n_refs});
-        k_validate_tables<<<nblk(tmax, 256), 256, 0, st>>>(din, c->d_err.as<unsigned int>());
-        int rc = cub_incl_sum(c, c->d_head.as<int32_t>(), c->d_scan.as<int32_t>(), N);
-        if (rc) return rc;
-        unsigned long long* d_nactive = reinterpret_cast<unsigned long long*>(c->d_err.as<char>() + 8);
-        k_keys<<<nblk(N, 256), 256, 0, st>>>(din, c->d_scan.as<int32_t>(), c->d_keys.as<uint64_t>(), c->d_vals.as<uint32_t>(), d_nactive);
-        c->stats.kernel_launches += 4;
-        rc = cub_sort_pairs64(c, c->d_keys.as<uint64_t>(), c->d_keys2.as<uint64_t>(), c->d_vals.as<uint32_t>(), c->d_vals2.as<uint32_t>(), N);
-        if (rc) return rc;
-        mark("scan+sort");
-        struct { unsigned int err; unsigned int pad; unsigned long long n_active; } hdr;
-        int32_t n_buckets = 0;
-        CK(cudaMemcpyAsync(&hdr, c->d_err.p, 16, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&n_buckets, c->d_scan.as<int32_t>() + (N - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (hdr.err) return fail(c, EJB_ERR_INVALID, "input validation failed (mask 0x%x: 1 nchains, 2 exact id, 4 tig offsets, 8 cdr3 offsets, 16 seg ids, 32 exact_cols, 64/128 exact tables, 256 ref ids, 512 amino, 1024 donor id >= 64, 2048 seg_off, 4096 ref_off, 8192 packed contig)", hdr.err);
-        c->stats.n_buckets = n_buckets;
-        c->n_active = (int64_t)hdr.n_active;
-    }
-    const int64_t NA = c->n_active;
+    if (N == 0) return EJB_OK;
+    constexpr int64_t SPEC = 16384;   // sub-bucket records fetched together with the header (more need a second copy)
+    // ---- bucket scan + sub-bucket sort (join.rs:68-88) ----
+    CK(c->d_head.ensure((size_t)N * 4));
+    CK(c->d_scan.ensure((size_t)N * 4));
+    CK(c->d_keys.ensure((size_t)N * 8));
+    CK(c->d_keys2.ensure((size_t)N * 8));
+    CK(c->d_vals.ensure((size_t)N * 4));
+    CK(c->d_vals2.ensure((size_t)N * 4));
+    launch(c, k_heads, nblk(N, 256), 256, din, c->d_head.as<int32_t>(), &hdr->err);
+    const int64_t tmax = std::max({din.n_exacts, din.n_chains, din.n_cells, din.n_segs, din.n_refs});
+    launch(c, k_validate_tables, nblk(tmax, 256), 256, din, &hdr->err);
+    int rc = cub_incl_sum(c, c->d_head.as<int32_t>(), c->d_scan.as<int32_t>(), N);
+    if (rc) return rc;
+    launch(c, k_keys, nblk(N, 256), 256, din, c->d_scan.as<const int32_t>(), c->d_keys.as<uint64_t>(), c->d_vals.as<uint32_t>(), hdr);
+    rc = cub_sort_pairs64(c, c->d_keys.as<uint64_t>(), c->d_keys2.as<uint64_t>(), c->d_vals.as<uint32_t>(), c->d_vals2.as<uint32_t>(), N);
+    if (rc) return rc;
+    mark("scan+sort");
     const uint64_t* keys_sorted = c->d_keys2.as<uint64_t>();
     const uint32_t* row_of = c->d_vals2.as<uint32_t>();
-    int n_subs = 0;
-    if (NA > 0) {
-        // Work that only needs the raw input is queued first: it keeps the device busy while the host waits for the two small
-        // read-backs below and builds the sub-bucket table.
-        // per exact: donor masks + sorted barcode lists (the bucketer copies the masks into the row records)
-        CK(c->d_donor.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 8));
-        CK(c->d_bckeys.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
-        CK(c->d_bckeys2.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
-        k_exact_prep<<<nblk(din.n_exacts, 256), 256, 0, st>>>(din, c->d_donor.as<unsigned long long>(), c->d_bckeys.as<uint64_t>());
-        if (din.n_cells > 0) {
-            int rc2 = cub_sort_keys64(c, c->d_bckeys.as<uint64_t>(), c->d_bckeys2.as<uint64_t>(), din.n_cells);
-            if (rc2) return rc2;
-        }
-        CK(c->d_segpl.ensure((size_t)std::max<int64_t>(din.n_segs, 1) * 2 * SEGPL_WORDS * 4));
-        k_seg_planes<<<nblk(din.n_segs * 32, 256), 256, 0, st>>>(din, c->d_segpl.as<uint32_t>());
-        CK(c->d_subhead.ensure((size_t)NA * 4));
-        CK(c->d_subincl.ensure((size_t)NA * 4));
-        k_subheads<<<nblk(NA, 256), 256, 0, st>>>(keys_sorted, NA, c->d_subhead.as<int32_t>());
-        int rc = cub_incl_sum(c, c->d_subhead.as<int32_t>(), c->d_subincl.as<int32_t>(), NA);
+    // work that only needs the raw input: per exact donor masks + sorted barcode lists, per segment reference planes
+    CK(c->d_donor.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 8));
+    CK(c->d_bckeys.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
+    CK(c->d_bckeys2.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
+    launch(c, k_exact_prep, nblk(din.n_exacts, 256), 256, din, c->d_donor.as<unsigned long long>(), c->d_bckeys.as<uint64_t>());
+    if (din.n_cells > 0) {
+        rc = cub_sort_keys64(c, c->d_bckeys.as<uint64_t>(), c->d_bckeys2.as<uint64_t>(), din.n_cells);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(&n_subs, c->d_subincl.as<int32_t>() + (NA - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(c->d_subinfo.ensure((size_t)n_subs * sizeof(SubInfo)));
-        CK(cudaMemsetAsync(c->d_subinfo.p, 0, (size_t)n_subs * sizeof(SubInfo), st));
-        k_subinfo<<<nblk(NA, 256), 256, 0, st>>>(din, keys_sorted, row_of, c->d_subhead.as<int32_t>(), c->d_subincl.as<int32_t>(), NA, c->d_subinfo.as<SubInfo>());
-        c->stats.kernel_launches += 2;
-        std::vector<SubInfo> si((size_t)n_subs);
-        CK(cudaMemcpyAsync(si.data(), c->d_subinfo.p, (size_t)n_subs * sizeof(SubInfo), cudaMemcpyDeviceToHost, st));
-        std::vector<SubRole> sroles;
-        if (c->have_roles) {
-            sroles.resize((size_t)n_subs);
-            CK(c->d_subroles.ensure((size_t)n_subs * sizeof(SubRole)));
-            CK(cudaMemsetAsync(c->d_subroles.p, 0, (size_t)n_subs * sizeof(SubRole), st));
-            k_subroles<<<nblk(NA, 256), 256, 0, st>>>(c->d_roles.as<uint8_t>(), row_of, c->d_subhead.as<int32_t>(), c->d_subincl.as<int32_t>(), NA,
-                                                     c->d_subroles.as<SubRole>(), c->d_err.as<unsigned int>());
-            c->stats.kernel_launches++;
-            CK(cudaMemcpyAsync(sroles.data(), c->d_subroles.p, (size_t)n_subs * sizeof(SubRole), cudaMemcpyDeviceToHost, st));
-        }
-        unsigned int role_err = 0;
-        CK(cudaMemcpyAsync(&role_err, c->d_err.p, 4, cudaMemcpyDeviceToHost, st));
-        mark("subinfo");
-        CK(cudaStreamSynchronize(st));
-        if (role_err & 16384u) return fail(c, EJB_ERR_INVALID, "row roles: column-only rows must form a suffix of their sub-bucket");
-        c->stats.d2h_bytes += (int64_t)n_subs * sizeof(SubInfo);
-
-        // ---- sub-bucket table, offsets, thresholds ----
-        const DevParams P = make_dev_params(c->params);
-        std::vector<SubBucket>& subs = c->subs;
-        subs.resize(n_subs);
-        int64_t q = 0, s1 = 0, rs = 0, blk = 0;
-        int64_t bucket_rows = 0;
-        uint64_t cur_bucket = ~0ull;
-        int max_cdr3 = 0;
-        for (int s = 0; s < n_subs; s++) {
-            SubBucket& sb = subs[s];
-            sb.j0 = si[s].j0;
-            sb.n = (int32_t)(((s + 1 < n_subs) ? si[s + 1].j0 : NA) - si[s].j0);
-            sb.npad = (sb.n + 3) & ~3;
-            sb.ch = (int32_t)((si[s].key >> 16) & 0xffff);
-            sb.cl = (int32_t)(si[s].key & 0xffff);
-            sb.Lh = si[s].Lh;
-            sb.Ll = si[s].Ll;
-            const int T = sb.ch + sb.cl;
-            const int w1 = (T + 31) / 32;
-            sb.W1 = (w1 >= 1 && w1 <= MAXW1) ? w1 : 0;
-            // uint4 per plane: 4 up to 512 nt (compile-time stride on the common path), 8 up to 1024 nt, else byte path only
-            sb.W4h = (sb.Lh >= 1 && sb.Lh <= 512) ? 4 : (sb.Lh <= 128 * MAXW4 && sb.Lh >= 1) ? MAXW4 : 0;
-            sb.W4l = (sb.Ll >= 1 && sb.Ll <= 512) ? 4 : (sb.Ll <= 128 * MAXW4 && sb.Ll >= 1) ? MAXW4 : 0;
-            sb.gap = si[s].gap & 3;
-            sb.rec_u4 = rec_planes(0, sb.gap & 1) * sb.W4h + rec_planes(1, sb.gap & 2) * sb.W4l;
-            sb.pad = 0;
-            sb.n_act = c->have_roles ? sroles[(size_t)s].n_act : sb.n;
-            sb.raw = c->have_roles ? sroles[(size_t)s].raw : 0;
-            sb.q0 = q;
-            sb.s1_off = s1;
-            sb.rs_off = rs;
-            sb.blk0 = (int32_t)blk;
-            sb.n3 = 3 * (sb.Lh + sb.Ll);
-            sb.owner = 0;
-            // stage-1 threshold: a superset of join_one.rs:231 and :286-290 (stage 2 re-tests exactly)
-            int maxcd = T;
-            if (P.is_bcr) {
-                maxcd = 0;
-                for (int cd = T; cd >= 0; cd--)
-                    if (!((double)cd / (double)T > P.cdr3_ident_thr)) { maxcd = cd; break; }
-                if (T == 0) maxcd = 0;
-                if (P.max_cdr3_diffs < 1000) maxcd = (int)std::min<long long>(maxcd, P.max_cdr3_diffs);
-            } else {
-                maxcd = 0;  // TCR: cd > 0 rejects
-            }
-            sb.maxcd = maxcd;
-            max_cdr3 = std::max({max_cdr3, sb.ch, sb.cl});
-            q += sb.npad;
-            s1 += (int64_t)2 * sb.W1 * sb.npad;
-            rs += (int64_t)sb.n * sb.rec_u4;
-            blk += (sb.n + TILE - 1) / TILE;
-            // pairs whose first row is one of the n_act leading rows (all n(n-1)/2 without row roles)
-            c->stats.pairs_scored += (int64_t)sb.n_act * (sb.n - 1) - (int64_t)sb.n_act * (sb.n_act - 1) / 2;
-            const uint64_t b = si[s].key >> 32;
-            if (b != cur_bucket) {
-                c->stats.pairs_lens += bucket_rows * (bucket_rows - 1) / 2;
-                bucket_rows = 0;
-                cur_bucket = b;
-            }
-            bucket_rows += sb.n;
-        }
-        c->stats.pairs_lens += bucket_rows * (bucket_rows - 1) / 2;
-        c->stats.n_subbuckets = n_subs;
-        c->n_pos = q;
-        c->n_blocks = blk;
-        if (q >= (1ll << 31)) return fail(c, EJB_ERR_INVALID, "too many packed rows");
-        if (rs >= (1ll << 32) || s1 >= (1ll << 32)) return fail(c, EJB_ERR_INVALID, "packed row store exceeds 32-bit indexing (64 GB)");
-
-        // ---- multi-GPU ownership: LPT by pair count ----
-        if (c->shard_world > 1) {
-            std::vector<int> order(n_subs);
-            for (int s = 0; s < n_subs; s++) order[s] = s;
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return subs[a].n > subs[b].n; });
-            std::vector<double> load(c->shard_world, 0.0);
-            for (int s : order) {
-                int best = 0;
-                for (int r = 1; r < c->shard_world; r++)
-                    if (load[r] < load[best]) best = r;
-                subs[s].owner = best;
-                load[best] += (double)subs[s].n * (subs[s].n - 1) / 2 + 64.0 * subs[s].n;
-            }
-        }
-
-        // ---- pow table: mult_pow ^ (cdr3_normal_len * cd / n), join_one.rs:531-539 ----
-        std::vector<int32_t> pow_off((size_t)max_cdr3 + 2, 0);
-        std::vector<char> len_used((size_t)max_cdr3 + 1, 0);
-        for (auto& sb : subs) len_used[sb.ch] = len_used[sb.cl] = 1;
-        std::vector<double> powtab;
-        for (int n = 0; n <= max_cdr3; n++) {
-            pow_off[n] = (int32_t)powtab.size();
-            if (!len_used[n]) continue;
-            for (int cd = 0; cd <= n; cd++)
-                powtab.push_back(std::pow(c->params.mult_pow, (double)c->params.cdr3_normal_len * (double)cd / (double)n));
-        }
-        if (powtab.empty()) powtab.push_back(1.0);
-        CK(c->d_powtab.ensure(powtab.size() * 8));
-        CK(c->d_powoff.ensure(pow_off.size() * 4));
-        CK(cudaMemcpyAsync(c->d_powtab.p, powtab.data(), powtab.size() * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(c->d_powoff.p, pow_off.data(), pow_off.size() * 4, cudaMemcpyHostToDevice, st));
-
-        // ---- device arrays ----
-        CK(c->d_qcut.ensure((size_t)n_subs * 4 + 4));
-        CK(c->d_subpass.ensure((size_t)n_subs * 4 + 4));
-        CK(cudaMemsetAsync(c->d_qcut.p, 0x7f, (size_t)n_subs * 4, st));   // 0x7f7f7f7f: no cut
-        CK(c->d_subs.ensure((size_t)n_subs * sizeof(SubBucket)));
-        CK(cudaMemcpyAsync(c->d_subs.p, subs.data(), (size_t)n_subs * sizeof(SubBucket), cudaMemcpyHostToDevice, st));
-        std::vector<int32_t> blk_sub((size_t)blk);
-        for (int s = 0; s < n_subs; s++)
-            for (int b = 0; b < (subs[s].n + TILE - 1) / TILE; b++) blk_sub[subs[s].blk0 + b] = s;
-        CK(c->d_blksub.ensure((size_t)std::max<int64_t>(blk, 1) * 4));
-        CK(cudaMemcpyAsync(c->d_blksub.p, blk_sub.data(), (size_t)blk * 4, cudaMemcpyHostToDevice, st));
-        CK(c->d_cdr3w.ensure((size_t)(s1 + 4) * 4));
-        CK(c->d_rowstore.ensure((size_t)(rs + 1) * 16));
-        const size_t np = (size_t)c->n_pos + 4;
-        CK(c->d_m_row.ensure(np * 4)); CK(c->d_m_sub.ensure(np * 4)); CK(c->d_aux.ensure(np * AUX_INTS * 4));
-        CK(c->d_labq.ensure(np * 4)); CK(c->d_blklab.ensure((size_t)std::max<int64_t>(blk, 1) * 4));
-        CK(cudaMemsetAsync(c->d_m_row.p, 0xff, np * 4, st));   // -1 = padding position
-        CK(cudaMemsetAsync(c->d_labq.p, 0xff, np * 4, st));
-        CK(cudaMemsetAsync(c->d_cdr3w.p, 0, (size_t)(s1 + 4) * 4, st));
-        CK(c->d_memo.ensure(np * 32));
-        CK(cudaMemsetAsync(c->d_memo.p, 0, np * 32, st));
-        c->s1_mode = S1_RUNI | S1_TAGS;
-        if (const char* e = getenv("EJB_S1_MODE")) c->s1_mode = atoi(e) & 3;
-        c->tags_on = c->n_canon_segs < 65535 && !getenv("EJB_NO_TAGS") && (c->s1_mode & S1_TAGS);
-        if (c->tags_on) {
-            CK(c->d_tagq.ensure(np * 8)); CK(c->d_deadq.ensure(np * 8)); CK(c->d_donq.ensure(np * 8));
-            CK(cudaMemsetAsync(c->d_donq.p, 0, np * 8, st));       // padding positions
-            CK(c->d_flagq.ensure(np * 4));
-            CK(c->d_subdom.ensure((size_t)n_subs * sizeof(SubDom)));
-            CK(cudaMemsetAsync(c->d_tagq.p, 0xff, np * 8, st));    // padding positions: never part of a valid pair
-            CK(cudaMemsetAsync(c->d_deadq.p, 0xff, np * 8, st));   // DEAD_NONE
-        }
-        mark("tables+memsets+bcsort");
-        k_pack_rows<<<nblk(NA * 32, 256), 256, 0, st>>>(din, P, c->d_subs.as<SubBucket>(), c->d_subincl.as<int32_t>(), row_of, NA,
-                                                       c->d_donor.as<unsigned long long>(), c->d_segpl.as<uint32_t>(), c->d_cdr3w.as<uint32_t>(), c->d_rowstore.as<uint4>(),
-                                                       c->d_aux.as<int32_t>(), c->d_m_row.as<int32_t>(), c->d_m_sub.as<int32_t>(),
-                                                       c->tags_on ? c->d_tagq.as<unsigned long long>() : nullptr,
-                                                       c->tags_on ? c->d_donq.as<unsigned long long>() : nullptr);
-        c->stats.kernel_launches += 2;
-        c->stats.kernel_launches++;
-        if (c->tags_on) {
-            k_sub_dominant<<<nblk(n_subs, 128), 128, 0, st>>>(c->d_subs.as<SubBucket>(), n_subs, c->d_tagq.as<unsigned long long>(),
-                                                             c->d_donq.as<unsigned long long>(), c->d_subdom.as<SubDom>());
-            c->stats.kernel_launches++;
-        }
-        mark("pack_rows");
-        CK(cudaGetLastError());
     }
-    // ---- union-find state, work buffers ----
+    CK(c->d_segpl.ensure((size_t)std::max<int64_t>(din.n_segs, 1) * 2 * SEGPL_WORDS * 4));
+    CK(c->d_seglen.ensure((size_t)std::max<int64_t>(din.n_segs, 1) * 4));
+    launch(c, k_seg_planes, nblk(din.n_segs * 32, 256), 256, din, c->d_segpl.as<uint32_t>(), c->d_seglen.as<int32_t>());
+    // sub-bucket heads, ids and records; the number of active rows stays on the device (kernels run over all N rows)
+    CK(c->d_subhead.ensure((size_t)N * 4));
+    CK(c->d_subincl.ensure((size_t)N * 4));
+    CK(c->d_subinfo.ensure((size_t)N * sizeof(SubInfo)));
+    launch(c, k_subheads, nblk(N, 256), 256, keys_sorted, (const RunHdr*)hdr, N, c->d_subhead.as<int32_t>());
+    rc = cub_incl_sum(c, c->d_subhead.as<int32_t>(), c->d_subincl.as<int32_t>(), N);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(c->d_subinfo.p, 0, (size_t)N * sizeof(SubInfo), st));
+    launch(c, k_subinfo, nblk(N, 256), 256, din, keys_sorted, row_of, c->d_subhead.as<const int32_t>(), c->d_subincl.as<const int32_t>(), hdr, c->d_subinfo.as<SubInfo>());
+    if (c->have_roles) {
+        CK(c->d_subroles.ensure((size_t)N * sizeof(SubRole)));
+        CK(cudaMemsetAsync(c->d_subroles.p, 0, (size_t)N * sizeof(SubRole), st));
+        launch(c, k_subroles, nblk(N, 256), 256, c->d_roles.as<const uint8_t>(), row_of, c->d_subhead.as<const int32_t>(), c->d_subincl.as<const int32_t>(),
+               (const RunHdr*)hdr, c->d_subroles.as<SubRole>(), &hdr->err);
+    }
+    const int64_t spec = std::min<int64_t>(N, SPEC);
+    const size_t off_si = 256, off_sr = off_si + (size_t)spec * sizeof(SubInfo);
+    CK(c->h_prep.ensure(off_sr + (size_t)spec * sizeof(SubRole)));
+    CK(cudaMemcpyAsync(c->h_prep.p, c->d_err.p, sizeof(RunHdr), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->h_prep.as<char>() + off_si, c->d_subinfo.p, (size_t)spec * sizeof(SubInfo), cudaMemcpyDeviceToHost, st));
+    if (c->have_roles) CK(cudaMemcpyAsync(c->h_prep.as<char>() + off_sr, c->d_subroles.p, (size_t)spec * sizeof(SubRole), cudaMemcpyDeviceToHost, st));
+    mark("subinfo");
+    rc = sync_stream(c);
+    if (rc) return rc;
+    const RunHdr hh = *c->h_prep.as<RunHdr>();
+    if (hh.err & 16384u) return fail(c, EJB_ERR_INVALID, "row roles: column-only rows must form a suffix of their sub-bucket");
+    if (hh.err) return fail(c, EJB_ERR_INVALID, "input validation failed (mask 0x%x: 1 nchains, 2 exact id, 4 tig offsets, 8 cdr3 offsets, 16 seg ids, 32 exact_cols, 64/128 exact tables, 256 ref ids, 512 amino, 1024 donor id >= 64, 2048 seg_off, 4096 ref_off, 8192 packed contig)", hh.err);
+    c->stats.n_buckets = (int64_t)hh.n_buckets;
+    c->n_active = (int64_t)hh.n_active;
+    const int64_t NA = c->n_active;
+    const int n_subs = (int)hh.n_subs;
+    if (NA == 0) return EJB_OK;
+    std::vector<SubInfo> si((size_t)n_subs);
+    std::vector<SubRole> sroles;
+    memcpy(si.data(), c->h_prep.as<char>() + off_si, (size_t)std::min<int64_t>(n_subs, spec) * sizeof(SubInfo));
+    if (c->have_roles) {
+        sroles.resize((size_t)n_subs);
+        memcpy(sroles.data(), c->h_prep.as<char>() + off_sr, (size_t)std::min<int64_t>(n_subs, spec) * sizeof(SubRole));
+    }
+    if (n_subs > spec) {   // rare: more sub-buckets than the speculative read covered
+        CK(cudaMemcpyAsync(si.data() + spec, c->d_subinfo.as<SubInfo>() + spec, (size_t)(n_subs - spec) * sizeof(SubInfo), cudaMemcpyDeviceToHost, st));
+        if (c->have_roles) CK(cudaMemcpyAsync(sroles.data() + spec, c->d_subroles.as<SubRole>() + spec, (size_t)(n_subs - spec) * sizeof(SubRole), cudaMemcpyDeviceToHost, st));
+        rc = sync_stream(c);
+        if (rc) return rc;
+    }
+    c->stats.d2h_bytes += (int64_t)n_subs * sizeof(SubInfo);
+
+    // ---- sub-bucket table, offsets, thresholds ----
+    const DevParams P = make_dev_params(c->params);
+    std::vector<SubBucket>& subs = c->subs;
+    subs.resize(n_subs);
+    int64_t q = 0, s1 = 0, rs = 0, blk = 0;
+    int64_t bucket_rows = 0;
+    uint64_t cur_bucket = ~0ull;
+    int max_cdr3 = 0;
+    for (int s = 0; s < n_subs; s++) {
+        SubBucket& sb = subs[s];
+        sb.j0 = si[s].j0;
+        sb.n = (int32_t)(((s + 1 < n_subs) ? si[s + 1].j0 : NA) - si[s].j0);
+        sb.npad = (sb.n + 3) & ~3;
+        sb.ch = (int32_t)((si[s].key >> 16) & 0xffff);
+        sb.cl = (int32_t)(si[s].key & 0xffff);
+        sb.Lh = si[s].Lh;
+        sb.Ll = si[s].Ll;
+        const int T = sb.ch + sb.cl;
+        const int w1 = (T + 31) / 32;
+        sb.W1 = (w1 >= 1 && w1 <= MAXW1) ? w1 : 0;
+        // uint4 per plane: 4 up to 512 nt (compile-time stride on the common path), 8 up to 1024 nt, else byte path only
+        sb.W4h = (sb.Lh >= 1 && sb.Lh <= 512) ? 4 : (sb.Lh <= 128 * MAXW4 && sb.Lh >= 1) ? MAXW4 : 0;
+        sb.W4l = (sb.Ll >= 1 && sb.Ll <= 512) ? 4 : (sb.Ll <= 128 * MAXW4 && sb.Ll >= 1) ? MAXW4 : 0;
+        sb.gap = si[s].gap & 3;
+        sb.rec_u4 = rec_planes(0, sb.gap & 1) * sb.W4h + rec_planes(1, sb.gap & 2) * sb.W4l;
+        sb.pad = 0;
+        sb.n_act = c->have_roles ? sroles[(size_t)s].n_act : sb.n;
+        sb.raw = c->have_roles ? sroles[(size_t)s].raw : 0;
+        sb.q0 = q;
+        sb.s1_off = s1;
+        sb.rs_off = rs;
+        sb.blk0 = (int32_t)blk;
+        sb.n3 = 3 * (sb.Lh + sb.Ll);
+        sb.owner = 0;
+        // stage-1 threshold: a superset of join_one.rs:231 and :286-290 (stage 2 re-tests exactly)
+        int maxcd = T;
+        if (P.is_bcr) {
+            maxcd = 0;
+            for (int cd = T; cd >= 0; cd--)
+                if (!((double)cd / (double)T > P.cdr3_ident_thr)) { maxcd = cd; break; }
+            if (T == 0) maxcd = 0;
+            if (P.max_cdr3_diffs < 1000) maxcd = (int)std::min<long long>(maxcd, P.max_cdr3_diffs);
+        } else {
+            maxcd = 0;  // TCR: cd > 0 rejects
+        }
+        sb.maxcd = maxcd;
+        max_cdr3 = std::max({max_cdr3, sb.ch, sb.cl});
+        q += sb.npad;
+        s1 += (int64_t)2 * sb.W1 * sb.npad;
+        rs += (int64_t)sb.n * sb.rec_u4;
+        blk += (sb.n + TILE - 1) / TILE;
+        // pairs whose first row is one of the n_act leading rows (all n(n-1)/2 without row roles)
+        c->stats.pairs_scored += (int64_t)sb.n_act * (sb.n - 1) - (int64_t)sb.n_act * (sb.n_act - 1) / 2;
+        const uint64_t b = si[s].key >> 32;
+        if (b != cur_bucket) {
+            c->stats.pairs_lens += bucket_rows * (bucket_rows - 1) / 2;
+            bucket_rows = 0;
+            cur_bucket = b;
+        }
+        bucket_rows += sb.n;
+    }
+    c->stats.pairs_lens += bucket_rows * (bucket_rows - 1) / 2;
+    c->stats.n_subbuckets = n_subs;
+    c->n_pos = q;
+    c->n_blocks = blk;
+    if (q >= (1ll << 31)) return fail(c, EJB_ERR_INVALID, "too many packed rows");
+    if (rs >= (1ll << 32) || s1 >= (1ll << 32)) return fail(c, EJB_ERR_INVALID, "packed row store exceeds 32-bit indexing (64 GB)");
+
+    // ---- multi-GPU ownership: LPT by pair count ----
+    if (c->shard_world > 1) {
+        std::vector<int> order(n_subs);
+        for (int s = 0; s < n_subs; s++) order[s] = s;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return subs[a].n > subs[b].n; });
+        std::vector<double> load(c->shard_world, 0.0);
+        for (int s : order) {
+            int best = 0;
+            for (int r = 1; r < c->shard_world; r++)
+                if (load[r] < load[best]) best = r;
+            subs[s].owner = best;
+            load[best] += (double)subs[s].n * (subs[s].n - 1) / 2 + 64.0 * subs[s].n;
+        }
+    }
+
+    // ---- pow table: mult_pow ^ (cdr3_normal_len * cd / n), join_one.rs:531-539 ----
+    std::vector<int32_t> pow_off((size_t)max_cdr3 + 2, 0);
+    std::vector<char> len_used((size_t)max_cdr3 + 1, 0);
+    for (auto& sb : subs) len_used[sb.ch] = len_used[sb.cl] = 1;
+    std::vector<double> powtab;
+    for (int n = 0; n <= max_cdr3; n++) {
+        pow_off[n] = (int32_t)powtab.size();
+        if (!len_used[n]) continue;
+        for (int cd = 0; cd <= n; cd++)
+            powtab.push_back(std::pow(c->params.mult_pow, (double)c->params.cdr3_normal_len * (double)cd / (double)n));
+    }
+    if (powtab.empty()) powtab.push_back(1.0);
+    CK(c->d_powtab.ensure(powtab.size() * 8));
+    CK(c->d_powoff.ensure(pow_off.size() * 4));
+    CK(cudaMemcpyAsync(c->d_powtab.p, powtab.data(), powtab.size() * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_powoff.p, pow_off.data(), pow_off.size() * 4, cudaMemcpyHostToDevice, st));
+
+    // ---- device arrays ----
+    CK(c->d_qcut.ensure((size_t)n_subs * 4 + 4));
+    CK(c->d_subpass.ensure((size_t)n_subs * 4 + 4));
+    CK(cudaMemsetAsync(c->d_qcut.p, 0x7f, (size_t)n_subs * 4, st));   // 0x7f7f7f7f: no cut
+    CK(cudaMemsetAsync(c->d_subpass.p, 0, (size_t)n_subs * 4, st));
+    CK(c->d_subs.ensure((size_t)n_subs * sizeof(SubBucket)));
+    CK(cudaMemcpyAsync(c->d_subs.p, subs.data(), (size_t)n_subs * sizeof(SubBucket), cudaMemcpyHostToDevice, st));
+    std::vector<int32_t> blk_sub((size_t)blk);
+    for (int s = 0; s < n_subs; s++)
+        for (int b = 0; b < (subs[s].n + TILE - 1) / TILE; b++) blk_sub[subs[s].blk0 + b] = s;
+    CK(c->d_blksub.ensure((size_t)std::max<int64_t>(blk, 1) * 4));
+    CK(cudaMemcpyAsync(c->d_blksub.p, blk_sub.data(), (size_t)blk * 4, cudaMemcpyHostToDevice, st));
+    CK(c->d_cdr3w.ensure((size_t)(s1 + 4) * 4));
+    CK(c->d_rowstore.ensure((size_t)(rs + 1) * 16));
+    const size_t np = (size_t)c->n_pos + 4;
+    CK(c->d_m_row.ensure(np * 4)); CK(c->d_m_sub.ensure(np * 4)); CK(c->d_aux.ensure(np * AUX_INTS * 4));
+    CK(c->d_labq.ensure(np * 4)); CK(c->d_blklab.ensure((size_t)std::max<int64_t>(blk, 1) * 4));
+    CK(cudaMemsetAsync(c->d_m_row.p, 0xff, np * 4, st));   // -1 = padding position
+    CK(cudaMemsetAsync(c->d_labq.p, 0xff, np * 4, st));
+    CK(cudaMemsetAsync(c->d_cdr3w.p, 0, (size_t)(s1 + 4) * 4, st));
+    CK(c->d_memo.ensure(np * 32));
+    CK(cudaMemsetAsync(c->d_memo.p, 0, np * 32, st));
+    c->tags_on = c->n_canon_segs < 65535 && !c->opt.no_tags && (c->opt.s1_mode & S1_TAGS);
+    if (c->tags_on) {
+        CK(c->d_tagq.ensure(np * 8)); CK(c->d_deadq.ensure(np * 8)); CK(c->d_donq.ensure(np * 8));
+        CK(cudaMemsetAsync(c->d_donq.p, 0, np * 8, st));       // padding positions
+        CK(c->d_flagq.ensure(np * 4));
+        CK(c->d_subdom.ensure((size_t)n_subs * sizeof(SubDom)));
+        CK(cudaMemsetAsync(c->d_tagq.p, 0xff, np * 8, st));    // padding positions: never part of a valid pair
+        CK(cudaMemsetAsync(c->d_deadq.p, 0xff, np * 8, st));   // DEAD_NONE
+    }
+    mark("tables+memsets+bcsort");
+    launch(c, k_pack_rows, nblk(NA * 32, 256), 256, din, P, c->d_subs.as<const SubBucket>(), c->d_subincl.as<const int32_t>(), row_of,
+           (const unsigned long long*)&hdr->n_active, c->d_donor.as<const unsigned long long>(), c->d_segpl.as<const uint32_t>(), c->d_seglen.as<const int32_t>(),
+           c->d_cdr3w.as<uint32_t>(), c->d_rowstore.as<uint4>(), c->d_aux.as<int32_t>(), c->d_m_row.as<int32_t>(), c->d_m_sub.as<int32_t>(),
+           c->tags_on ? c->d_tagq.as<unsigned long long>() : (unsigned long long*)nullptr, c->tags_on ? c->d_donq.as<unsigned long long>() : (unsigned long long*)nullptr);
+    if (c->tags_on)
+        launch(c, k_sub_dominant, nblk(n_subs, 128), 128, c->d_subs.as<const SubBucket>(), n_subs, c->d_tagq.as<const unsigned long long>(),
+               c->d_donq.as<const unsigned long long>(), c->d_subdom.as<SubDom>());
+    mark("pack_rows");
+    CK(cudaGetLastError());
+    return EJB_OK;
+}
+
+}  // namespace
+
+extern "C" int ejb_run(ejb_ctx* c) {
+    if (!c) return EJB_ERR_INVALID;
+    if (!c->have_input) return fail(c, EJB_ERR_INVALID, "ejb_run without ejb_upload");
+    CK(cudaSetDevice(c->device));
+    c->have_run = c->prepared = false;
+    const double t_wall0 = now_ms();
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->ev_used = 0;
+    c->s2a_events.clear();
+    const DevIn& din = c->din;
+    const int64_t N = din.n_rows;
+    cudaStream_t st = c->stream;
+    cudaEvent_t ev_start = c->ev(), ev_packed = c->ev(), ev_rounds = c->ev(), ev_end = c->ev();
+    std::vector<std::pair<const char*, cudaEvent_t>> tr;   // opt.trace: finer CUDA events inside the prepare phase (developer aid)
+    CK(cudaEventRecord(ev_start, st));
+    std::vector<RoundTimes> times;
+    int rc = prepare(c, tr);
+    if (rc) return rc;
+    const int n_subs = (int)c->subs.size();
+
+    // ---- round report buffer (its head is the Counters block), union-find state, work buffers ----
+    c->round_units_cap = (size_t)n_subs + 8;
+    c->round_tasks_cap = (size_t)c->n_blocks + (size_t)n_subs + 8;
+    CK(c->d_round.ensure(sizeof(Counters) + c->round_units_cap * sizeof(UnitOut) + c->round_tasks_cap * 8));
+    CK(cudaMemsetAsync(c->d_round.p, 0, sizeof(Counters), st));
     CK(c->d_parent.ensure((size_t)std::max<int64_t>(N, 1) * 4));
     CK(c->d_best.ensure((size_t)std::max<int64_t>(N, 1) * 8));
-    if (N > 0) k_iota<<<nblk(N, 256), 256, 0, st>>>(c->d_parent.as<int32_t>(), N);
-    if (c->n_pos > 0) {
-        k_flatten<<<nblk(c->n_pos, 256), 256, 0, st>>>(c->d_parent.as<int32_t>(), c->d_m_row.as<int32_t>(), c->n_pos, c->d_labq.as<int32_t>());
-        k_block_labels<<<nblk(c->n_blocks * 32, 256), 256, 0, st>>>(c->d_subs.as<SubBucket>(), n_subs, c->d_labq.as<int32_t>(), c->d_blklab.as<int32_t>(),
-                                                                   c->d_blksub.as<int32_t>(), (int)c->n_blocks);
-        c->stats.kernel_launches += 3;
+    if (N > 0) {
+        const int64_t m = std::max({N, c->n_pos, c->n_blocks});
+        launch(c, k_init_labels, nblk(m, 256), 256, c->d_parent.as<int32_t>(), N, c->d_m_row.as<const int32_t>(), c->n_pos, c->d_labq.as<int32_t>(),
+               c->d_blklab.as<int32_t>(), c->d_blksub.as<const int32_t>(), c->d_subs.as<const SubBucket>(), (int)c->n_blocks);
     }
     {
         unsigned long long need = 0;
@@ -1101,10 +1269,12 @@ extern "C" int ejb_run(ejb_ctx* c) {
     c->pairs_eval_seen = 0;
     c->forest_cap = (unsigned long long)std::max<int64_t>(N, 1);
     CK(c->d_cand.ensure(cap * 8)); CK(c->d_slow.ensure(cap * 8)); CK(c->d_slowslot.ensure(cap * 4));
-    CK(c->d_surv.ensure(cap * sizeof(Survivor))); CK(c->d_pass.ensure(cap * 8)); CK(c->d_roots.ensure(cap * 8));
+    CK(c->d_surv.ensure(cap * sizeof(Survivor))); CK(c->d_pass.ensure(cap * 8)); CK(c->d_passt.ensure(cap * sizeof(PassTuple)));
+    CK(c->d_roots.ensure(cap * 8));
     CK(c->d_forest.ensure(c->forest_cap * 8));
-    CK(c->d_tuples.ensure(std::max<unsigned long long>(c->forest_cap, 1) * sizeof(EdgeTuple)));
+    CK(c->d_forestt.ensure(c->forest_cap * sizeof(PassTuple)));
     CK(cudaEventRecord(ev_packed, st));
+    c->prepared = true;
 
     // ---- round scheduler ----
     {
@@ -1112,8 +1282,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
         // Units: rows [r0, r1) of a sub-bucket against every column to their right, in row order.  A unit may only be
         // split by ROWS (splitting by columns and contracting after each part is not exact: a lighter edge from a later
         // column part could have to evict a heavier edge already in the forest).
-        // Sizing: optimistic x4 growth, bounded by the candidate density (per row) of the last row range processed.  When
-        // a round does overflow the candidate buffer (detected right after stage 1, nothing committed), the per-row-range
+        // Sizing: optimistic growth, bounded by the candidate density (per row) of the last row range processed.  When
+        // a round does overflow the candidate buffer (nothing committed), the per-row-range
         // candidate counts of that attempt are exact upper bounds for the retry, which is planned from them.
         struct Known { int r0, r1; double cand; };
         std::vector<int> next_row(subs.size(), 0), live;
@@ -1125,10 +1295,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
         const double cap_round = 0.5 * (double)c->cand_cap;                      // expected candidates allowed per round
         const double target_pass = std::max(4096.0, (double)c->cand_cap / 64.0);   // pass edges one unit should not exceed by much
         int stalls = 0;
-        // developer knobs for the unit schedule (first unit, growth factor of the rows done so far)
-        long long first_unit = 2, growth = 12;   // measured on configs[1] (1M cells): 8/4 -> 10.5 ms, 1/8 -> 8.95 ms, 2/12 -> 8.74 ms, 4/16 -> 8.75 ms
-        if (const char* e = getenv("EJB_FIRST_UNIT")) first_unit = std::max(1ll, atoll(e));
-        if (const char* e = getenv("EJB_GROWTH")) growth = std::max(1ll, atoll(e));
+        const long long first_unit = c->opt.first_unit, growth = c->opt.growth;
         while (!live.empty()) {
             std::vector<Unit> units;
             unsigned long long pairs = 0;
@@ -1202,7 +1369,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
                 expect += ex;
             }
             const std::vector<Unit> planned = units;
-            int rc = run_round(c, units, times);
+            rc = run_round(c, units, times);
             if (rc != 0 && rc != 1) return rc;
             if (rc == 1) {
                 // nothing was committed: the per-range counts (valid upper bounds) drive the retry
@@ -1222,7 +1389,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
             } else {
                 stalls = 0;
                 for (size_t ui = 0; ui < units.size(); ui++) {
-                    const Unit& u = units[ui];       // u.r1 may have been truncated by run_round
+                    const Unit& u = units[ui];       // u.r1 may have been truncated by the device (k_truncate)
                     next_row[u.sub] = u.r1;
                     known[u.sub].clear();            // stale after a commit
                     if (u.cand > 0.0) prate[u.sub] = std::min(1.0, u.pass / u.cand);
@@ -1241,94 +1408,82 @@ extern "C" int ejb_run(ejb_ctx* c) {
     }
     CK(cudaEventRecord(ev_rounds, st));
 
-    // ---- finalize: tuples of the forest edges, two-cell filter, clonotype_id unions, labels, ordering ----
-    int rc = sync_counters(c);
-    if (rc) return rc;
-    const int64_t NF = (int64_t)c->h_ctr->n_forest;
-    c->stats.forest_edges = NF;
-    c->stats.pairs_evaluated = (int64_t)c->h_ctr->pairs_eval;
-    CK(c->d_keep.ensure((size_t)std::max<int64_t>(NF, 1)));
+    // ---- finalize: two-cell filter, ordering, PotentialJoin members, clonotype_id unions, labels.  Every count stays on the
+    //      device; the only read-back is the final counter block. ----
     CK(c->d_labels.ensure((size_t)std::max<int64_t>(N, 1) * 4));
-    CK(c->d_nout.ensure(64));
-    CK(cudaMemsetAsync(c->d_nout.p, 0, 64, st));
-    if (NF > 0) {
+    const int fgrid = c->sm_count * 8;
+    if (N > 0 && c->n_pos > 0) {
+        const size_t nf = (size_t)c->forest_cap;
         CK(c->d_qofrow.ensure((size_t)N * 4));
         CK(c->d_deg.ensure((size_t)N * 4));
+        CK(c->d_fkeys.ensure(nf * 8)); CK(c->d_fkeys2.ensure(nf * 8));
+        CK(c->d_fidx.ensure(nf * 4)); CK(c->d_fidx2.ensure(nf * 4));
         CK(cudaMemsetAsync(c->d_deg.p, 0, (size_t)N * 4, st));
-        k_q_of_row<<<nblk(c->n_pos, 256), 256, 0, st>>>(c->d_m_row.as<int32_t>(), c->n_pos, c->d_qofrow.as<int32_t>());
-        // the (q1,q2) list of ALL forest edges is needed for degrees; tuples are computed in chunks of cand_cap
-        DevBuf& d_pairs_all = c->d_pairs_all;
-        CK(d_pairs_all.ensure((size_t)NF * 8));
-        k_forest_pairs<<<nblk(NF, 256), 256, 0, st>>>(c->d_forest.as<unsigned long long>(), NF, c->d_qofrow.as<int32_t>(), d_pairs_all.as<uint2>(),
-                                                     c->d_deg.as<int32_t>());
-        c->stats.kernel_launches += 2;
-        DevBuf& d_slots = c->d_slots;
-        const int64_t chunk = (int64_t)std::min<unsigned long long>(cap, (unsigned long long)NF);
-        CK(d_slots.ensure((size_t)chunk * 4));
-        DevBuf& d_cnt = c->d_cnt;
-        CK(d_cnt.ensure(16));
-        for (int64_t o = 0; o < NF; o += chunk) {
-            const int64_t m = std::min<int64_t>(chunk, NF - o);
-            const unsigned long long mm = (unsigned long long)m;
-            CK(cudaMemcpyAsync(d_cnt.p, &mm, 8, cudaMemcpyHostToDevice, st));
-            k_iota<<<nblk(m, 256), 256, 0, st>>>(d_slots.as<int32_t>(), m, (int32_t)o);  // output slots o..o+m-1
-            rc = run_stage2(c, d_pairs_all.as<uint2>() + o, d_slots.as<uint32_t>(), d_cnt.as<unsigned long long>(), 1);
-            if (rc) return rc;
-            rc = sync_counters(c);
-            if (rc) return rc;
-            if (c->h_ctr->overflow) return fail(c, EJB_ERR_CUDA, "finalize overflow");
-            c->p1_count += c->h_ctr->n_newkeys;
-        }
-        k_two_cell<<<nblk(NF, 256), 256, 0, st>>>(din, make_dev_params(c->params), c->d_forest.as<unsigned long long>(), NF, c->d_deg.as<int32_t>(),
-                                                 c->d_tuples.as<EdgeTuple>(), c->d_parent.as<int32_t>(), c->d_keep.as<uint8_t>(), c->d_ctr.as<Counters>(),
-                                                 c->have_roles ? c->d_roles.as<uint8_t>() : nullptr);
-        c->stats.kernel_launches++;
-        CK(c->d_fkeys.ensure((size_t)NF * 8)); CK(c->d_fkeys2.ensure((size_t)NF * 8));
-        CK(c->d_fidx.ensure((size_t)NF * 4)); CK(c->d_fidx2.ensure((size_t)NF * 4));
-        k_final_keys<<<nblk(NF, 256), 256, 0, st>>>(c->d_forest.as<unsigned long long>(), c->d_keep.as<uint8_t>(), NF, c->d_fkeys.as<unsigned long long>(),
-                                                   c->d_fidx.as<uint32_t>(), c->d_nout.as<unsigned long long>());
-        unsigned long long nfinal = 0;
-        CK(cudaMemcpyAsync(&nfinal, c->d_nout.p, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        c->n_final = (int64_t)nfinal;
-        if (nfinal > 0) {
-            rc = cub_sort_pairs64(c, c->d_fkeys.as<uint64_t>(), c->d_fkeys2.as<uint64_t>(), c->d_fidx.as<uint32_t>(), c->d_fidx2.as<uint32_t>(), (int64_t)nfinal);
-            if (rc) return rc;
-            const size_t nf = (size_t)nfinal;
-            CK(c->d_o_k1.ensure(nf * 4)); CK(c->d_o_k2.ensure(nf * 4)); CK(c->d_o_cd.ensure(nf * 4)); CK(c->d_o_nrefs.ensure(nf * 4));
-            CK(c->d_o_sh.ensure(nf * 8)); CK(c->d_o_in.ensure(nf * 8)); CK(c->d_o_k.ensure(nf * 4)); CK(c->d_o_d.ensure(nf * 4));
-            CK(c->d_o_n.ensure(nf * 4)); CK(c->d_o_p1.ensure(nf * 8)); CK(c->d_o_mult.ensure(nf * 8)); CK(c->d_o_score.ensure(nf * 8));
-            CK(c->d_o_err.ensure(nf));
-            FinalOut fo;
-            fo.k1 = c->d_o_k1.as<int32_t>(); fo.k2 = c->d_o_k2.as<int32_t>(); fo.cd = c->d_o_cd.as<int32_t>(); fo.nrefs = c->d_o_nrefs.as<int32_t>();
-            fo.shares = c->d_o_sh.as<int32_t>(); fo.indeps = c->d_o_in.as<int32_t>(); fo.k = c->d_o_k.as<int32_t>(); fo.d = c->d_o_d.as<int32_t>();
-            fo.n = c->d_o_n.as<int32_t>(); fo.p1 = c->d_o_p1.as<double>(); fo.mult = c->d_o_mult.as<double>(); fo.score = c->d_o_score.as<double>();
-            fo.err = c->d_o_err.as<uint8_t>();
-            k_final_gather<<<nblk((int64_t)nfinal, 256), 256, 0, st>>>(c->d_fkeys2.as<unsigned long long>(), c->d_fidx2.as<uint32_t>(), (int64_t)nfinal,
-                                                                      c->d_tuples.as<EdgeTuple>(), fo, c->d_ctr.as<Counters>());
-        }
-        c->stats.kernel_launches += 3;
-        CK(cudaStreamSynchronize(st));
+        CK(cudaMemsetAsync(c->d_fkeys.p, 0xff, nf * 8, st));   // unused tail sorts to the end
+        launch(c, k_q_of_row, nblk(c->n_pos, 256), 256, c->d_m_row.as<const int32_t>(), c->n_pos, c->d_qofrow.as<int32_t>());
+        launch(c, k_forest_deg, fgrid, 256, c->d_forest.as<const unsigned long long>(), (const unsigned long long*)CTR_FIELD(n_forest), c->d_deg.as<int32_t>());
+        launch(c, k_two_cell, fgrid, 256, din, make_dev_params(c->params), c->d_forest.as<const unsigned long long>(), (const unsigned long long*)CTR_FIELD(n_forest),
+               c->d_deg.as<const int32_t>(), c->d_forestt.as<const PassTuple>(), c->d_parent.as<int32_t>(), c->d_fkeys.as<unsigned long long>(),
+               c->d_fidx.as<uint32_t>(), c->d_ctr(), c->have_roles ? c->d_roles.as<const uint8_t>() : (const uint8_t*)nullptr);
+        rc = cub_sort_pairs64(c, c->d_fkeys.as<uint64_t>(), c->d_fkeys2.as<uint64_t>(), c->d_fidx.as<uint32_t>(), c->d_fidx2.as<uint32_t>(), (int64_t)nf);
+        if (rc) return rc;
+        CK(c->d_o_k1.ensure(nf * 4)); CK(c->d_o_k2.ensure(nf * 4)); CK(c->d_o_cd.ensure(nf * 4)); CK(c->d_o_nrefs.ensure(nf * 4));
+        CK(c->d_o_sh.ensure(nf * 8)); CK(c->d_o_in.ensure(nf * 8)); CK(c->d_o_k.ensure(nf * 4)); CK(c->d_o_d.ensure(nf * 4));
+        CK(c->d_o_n.ensure(nf * 4)); CK(c->d_o_p1.ensure(nf * 8)); CK(c->d_o_mult.ensure(nf * 8)); CK(c->d_o_score.ensure(nf * 8));
+        CK(c->d_o_err.ensure(nf));
+        FinalOut fo;
+        fo.k1 = c->d_o_k1.as<int32_t>(); fo.k2 = c->d_o_k2.as<int32_t>(); fo.cd = c->d_o_cd.as<int32_t>(); fo.nrefs = c->d_o_nrefs.as<int32_t>();
+        fo.shares = c->d_o_sh.as<int32_t>(); fo.indeps = c->d_o_in.as<int32_t>(); fo.k = c->d_o_k.as<int32_t>(); fo.d = c->d_o_d.as<int32_t>();
+        fo.n = c->d_o_n.as<int32_t>(); fo.p1 = c->d_o_p1.as<double>(); fo.mult = c->d_o_mult.as<double>(); fo.score = c->d_o_score.as<double>();
+        fo.err = c->d_o_err.as<uint8_t>();
+        P1Cache pc;
+        pc.keys = c->d_p1_keys.as<unsigned long long>();
+        pc.vals = c->d_p1_vals.as<double>();
+        pc.newslots = c->d_p1_new.as<uint32_t>();
+        pc.cap_mask = c->p1_cap - 1;
+        launch(c, k_final_gather, fgrid, 256, c->d_fkeys2.as<const unsigned long long>(), c->d_fidx2.as<const uint32_t>(), (const unsigned long long*)CTR_FIELD(n_final),
+               c->d_forestt.as<const PassTuple>(), c->d_qofrow.as<const int32_t>(), c->d_m_sub.as<const int32_t>(), c->d_subs.as<const SubBucket>(), pc,
+               c->d_powtab.as<const double>(), c->d_powoff.as<const int32_t>(), fo);
     }
     if (N > 0) {
         // join2.rs:69-84 + canonical labels
         CK(c->d_first.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 4));
-        k_fill_i32<<<nblk(din.n_exacts, 256), 256, 0, st>>>(c->d_first.as<int32_t>(), din.n_exacts, 0x7fffffff);
-        k_exact_first<<<nblk(N, 256), 256, 0, st>>>(din, c->d_first.as<int32_t>());
-        k_exact_union<<<nblk(N, 256), 256, 0, st>>>(din, c->d_first.as<int32_t>(), c->d_parent.as<int32_t>());
-        k_labels<<<nblk(N, 256), 256, 0, st>>>(c->d_parent.as<int32_t>(), N, c->d_labels.as<int32_t>());
-        c->stats.kernel_launches += 4;
+        launch(c, k_fill_i32, nblk(din.n_exacts, 256), 256, c->d_first.as<int32_t>(), din.n_exacts, 0x7fffffff);
+        launch(c, k_exact_first, nblk(N, 256), 256, din, c->d_first.as<int32_t>());
+        launch(c, k_exact_union, nblk(N, 256), 256, din, c->d_first.as<const int32_t>(), c->d_parent.as<int32_t>());
+        launch(c, k_labels, nblk(N, 256), 256, c->d_parent.as<const int32_t>(), N, c->d_labels.as<int32_t>());
     }
     CK(cudaEventRecord(ev_end, st));
-    rc = sync_counters(c);
+    CK(c->h_round.ensure(sizeof(Counters)));
+    CK(cudaMemcpyAsync(c->h_round.p, c->d_round.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    rc = sync_stream(c);
     if (rc) return rc;
     CK(cudaGetLastError());
-    c->stats.two_cell_deleted = (int64_t)c->h_ctr->n_two_cell;
-    c->stats.stage1_ref_kills = (int64_t)(c->h_ctr->n_s1_kill - c->h_ctr->n_s1_donor);
-    c->stats.stage1_donor_kills = (int64_t)c->h_ctr->n_s1_donor;
-    c->stats.stage2_two_ref = (int64_t)c->h_ctr->n_two_ref;
-    c->stats.stage2_memo_dead = (int64_t)c->h_ctr->n_memo_dead;
-    c->stats.stage2_degr_dead = (int64_t)c->h_ctr->n_degr_dead;
+    const Counters& h = *c->h_round.as<Counters>();
+    c->n_final = (int64_t)h.n_final;
+    c->stats.forest_edges = (int64_t)h.n_forest;
+    c->stats.pairs_evaluated = (int64_t)h.pairs_eval;
+    c->stats.two_cell_deleted = (int64_t)h.n_two_cell;
+    c->stats.stage1_ref_kills = (int64_t)(h.n_s1_kill - h.n_s1_donor);
+    c->stats.stage1_donor_kills = (int64_t)h.n_s1_donor;
+    c->stats.stage2_two_ref = (int64_t)h.n_two_ref;
+    c->stats.stage2_memo_dead = (int64_t)h.n_memo_dead;
+    c->stats.stage2_degr_dead = (int64_t)h.n_degr_dead;
+    c->stats.pairs_distance_computed = (int64_t)h.s1_first;
+    c->stats.pairs_distance_full = (int64_t)h.s1_full;
+    {   // executed popc of stage 1: one per first-word evaluation + the remaining words where they were evaluated (per width)
+        double rest = 0.0, pairs_w = 0.0;
+        for (const SubBucket& sb : c->subs) {
+            const double p = (double)sb.n * (sb.n - 1) / 2;
+            rest += p * cdr3_rest_popc(sb.W1);
+            pairs_w += p;
+        }
+        const double rest_avg = pairs_w > 0 ? rest / pairs_w : 0.0;
+        c->stats.popc_executed_stage1 = (int64_t)((double)h.s1_first + rest_avg * (double)h.s1_full);
+    }
+    c->stats.boruvka_iterations = (int64_t)h.bor_iters;
+    c->stats.p1_cache_slots = (int64_t)c->p1_cap;
+    c->stats.n_devices = 1;
     c->stats.joins = c->n_final;
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_start, ev_packed); c->stats.ms_pack = ms;
@@ -1342,15 +1497,15 @@ extern "C" int ejb_run(ejb_ctx* c) {
         cudaEventElapsedTime(&ms, t.e1, t.e2); c->stats.ms_stage2 += ms;
         cudaEventElapsedTime(&ms, t.e2, t.e3); c->stats.ms_forest += ms;
     }
-    if (trace) {
+    if (c->opt.trace) {
         fprintf(stderr, "[ejb trace] prepare:");
         for (size_t i = 1; i < tr.size(); i++) {
             cudaEventElapsedTime(&ms, tr[i - 1].second, tr[i].second);
             fprintf(stderr, " %s %.3f ms;", tr[i].first, ms);
         }
         fprintf(stderr, " total pack %.3f ms\n", c->stats.ms_pack);
-        fprintf(stderr, "[ejb trace] integer-test rejections: ident %llu max_diffs %llu max_cdr3 %llu donors %llu cd>=mult*indeps %llu cref %llu\n", c->h_ctr->n_rej[0],
-                c->h_ctr->n_rej[1], c->h_ctr->n_rej[2], c->h_ctr->n_rej[3], c->h_ctr->n_rej[4], c->h_ctr->n_rej[5]);
+        fprintf(stderr, "[ejb trace] integer-test rejections: ident %llu max_diffs %llu max_cdr3 %llu donors %llu cd>=mult*indeps %llu cref %llu\n", h.n_rej[0],
+                h.n_rej[1], h.n_rej[2], h.n_rej[3], h.n_rej[4], h.n_rej[5]);
         for (size_t i = 0; i < times.size(); i++) {
             float a, b, d;
             cudaEventElapsedTime(&a, times[i].e0, times[i].e1);
@@ -1358,12 +1513,18 @@ extern "C" int ejb_run(ejb_ctx* c) {
             cudaEventElapsedTime(&d, times[i].e2, times[i].e3);
             fprintf(stderr, "[ejb trace] round %zu: stage1 %.3f stage2 %.3f forest %.3f ms\n", i, a, b, d);
         }
+        fprintf(stderr, "[ejb trace] finalize %.3f ms, %lld syncs, %lld boruvka iterations\n", c->stats.ms_finalize, (long long)c->stats.host_syncs,
+                (long long)c->stats.boruvka_iterations);
     }
     c->stats.ms_h2d = c->ms_h2d;
     c->stats.h2d_bytes = c->h2d_bytes;
     c->stats.ms_total = now_ms() - t_wall0;
     c->have_run = true;
     return EJB_OK;
+}
+
+namespace {
+int multi_join(ejb_ctx* c, const ejb_params* p, const ejb_input* in, ejb_result* out);
 }
 
 extern "C" {
@@ -1451,6 +1612,8 @@ void ejb_result_free(ejb_ctx* c, ejb_result* out) {
 }
 
 int ejb_join(ejb_ctx* c, const ejb_params* p, const ejb_input* in, ejb_result* out) {
+    if (!c) return EJB_ERR_INVALID;
+    if (!c->peers.empty()) return multi_join(c, p, in, out);
     const double t0 = now_ms();
     int rc = ejb_upload(c, p, in);
     if (rc) return rc;
@@ -1540,6 +1703,17 @@ int ejb_p1_batch(ejb_ctx* c, const int32_t* k, const int32_t* d, const int32_t* 
     return EJB_OK;
 }
 
+// entries [first, first + count) of the device-built Stirling ratio table in its triangular layout (row n at n(n+1)/2), as
+// (hi, lo) pairs — for the bit-level comparison with the oracle's host build (tests)
+int ejb_sr_table_read(ejb_ctx* c, int64_t first, int64_t count, double* hi_lo_out) {
+    if (!c || first < 0 || count < 0 || !hi_lo_out) return EJB_ERR_INVALID;
+    const int64_t total = (int64_t)(SR_NMAX + 1) * (SR_NMAX + 2) / 2;
+    if (first + count > total) return EJB_ERR_RANGE;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(hi_lo_out, c->d_sr.as<dd_t>() + first, (size_t)count * sizeof(dd_t), cudaMemcpyDeviceToHost));
+    return EJB_OK;
+}
+
 int ejb_measure_peaks(ejb_ctx* c, double* popc_per_s, double* lop3_per_s, double* sm_clock_mhz) {
     if (!c) return EJB_ERR_INVALID;
     CK(cudaSetDevice(c->device));
@@ -1598,3 +1772,10 @@ int ejb_equiv_replay(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64
 }
 
 }  // extern "C"
+
+namespace {
+int multi_join(ejb_ctx* c, const ejb_params* p, const ejb_input* in, ejb_result* out) {
+    (void)p; (void)in; (void)out;
+    return fail(c, EJB_ERR_UNSUPPORTED, "multi-device join not built yet");
+}
+}  // namespace

@@ -21,9 +21,12 @@ __global__ void k_heads(DevIn in, int32_t* head, unsigned int* err) {
         const int64_t o2 = in.row_tig2_off ? in.row_tig2_off[i] : -1;
         if (o2 >= 0) {   // 2-bit packed contig: pure ACGT by contract, never a has_del row
             if (L < 0 || o2 + (L + 15) / 16 > in.n_tig2_words || in.row_has_del[i]) e |= 8192;
-        } else if (L < 0 || in.row_tig_off[i] < 0 || in.row_tig_off[i] + L > in.n_tig_bytes) e |= 4;
+        } else if (!in.row_tig_off || L < 0 || in.row_tig_off[i] < 0 || in.row_tig_off[i] + L > in.n_tig_bytes) e |= 4;
         const int c = in.row_cdr3_len[i];
-        if (c < 0 || c > 65535 || in.row_cdr3_off[i] < 0 || in.row_cdr3_off[i] + c > in.n_cdr3_bytes) e |= 8;
+        const int64_t c2 = in.row_cdr32_off ? in.row_cdr32_off[i] : -1;
+        if (c2 >= 0) {   // 2-bit packed CDR3: pure ACGT by contract
+            if (c < 0 || c > 65535 || c2 + (c + 15) / 16 > in.n_cdr32_words) e |= 8;
+        } else if (!in.row_cdr3_off || c < 0 || c > 65535 || in.row_cdr3_off[i] < 0 || in.row_cdr3_off[i] + c > in.n_cdr3_bytes) e |= 8;
         if (in.row_vs[i] < 0 || in.row_vs[i] >= in.n_segs || in.row_js[i] < 0 || in.row_js[i] >= in.n_segs) e |= 16;
         if (e == 0) {
             const int ex = in.row_exact[k];
@@ -70,8 +73,17 @@ __global__ void k_validate_tables(DevIn in, unsigned int* err) {
 
 // sort key of a row: (bucket id, heavy CDR3 len, light CDR3 len); rows that can never join
 // (lens.len() != 2, join_one.rs:83-96) get the maximal key and fall off the end.
-__global__ void k_keys(DevIn in, const int32_t* bucket_incl, uint64_t* keys, uint32_t* vals, unsigned long long* n_active) {
+// Run header on the device: what the host reads back ONCE after the bucket scan and the sub-bucket table are built.
+struct RunHdr {
+    unsigned int err, pad;
+    unsigned long long n_active;   // rows with two chains (the only ones that can join)
+    unsigned long long n_subs;     // sub-buckets
+    unsigned long long n_buckets;  // runs of equal lens
+};
+__global__ void k_keys(DevIn in, const int32_t* bucket_incl, uint64_t* keys, uint32_t* vals, RunHdr* hdr) {
+    unsigned long long* n_active = &hdr->n_active;
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == in.n_rows - 1) hdr->n_buckets = (unsigned long long)bucket_incl[k];
     uint64_t key = ~0ull;
     bool act = false;
     if (k < in.n_rows && in.row_nchains[k] == 2) {
@@ -87,10 +99,11 @@ __global__ void k_keys(DevIn in, const int32_t* bucket_incl, uint64_t* keys, uin
     }
 }
 
-__global__ void k_subheads(const uint64_t* keys, int64_t n_active, int32_t* head) {
+// launched over all n rows: the number of active rows is only known on the device
+__global__ void k_subheads(const uint64_t* keys, const RunHdr* hdr, int64_t n, int32_t* head) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_active) return;
-    head[q] = (q == 0 || keys[q] != keys[q - 1]) ? 1 : 0;
+    if (q >= n) return;
+    head[q] = (q < (int64_t)hdr->n_active && (q == 0 || keys[q] != keys[q - 1])) ? 1 : 0;
 }
 
 struct SubInfo {
@@ -100,9 +113,11 @@ struct SubInfo {
     int32_t gap, pad;   // gap: OR over the sub-bucket's rows of has_del (bit 0 heavy, bit 1 light)
 };
 __global__ void k_subinfo(DevIn in, const uint64_t* keys, const uint32_t* row_of, const int32_t* head, const int32_t* sub_incl,
-                          int64_t n_active, SubInfo* out) {
+                          RunHdr* hdr, SubInfo* out) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_active = (int64_t)hdr->n_active;
     if (j >= n_active) return;
+    if (j == n_active - 1) hdr->n_subs = (unsigned long long)sub_incl[j];
     const int s = sub_incl[j] - 1;
     const int64_t k = row_of[j];
     if (head[j]) {
@@ -121,9 +136,9 @@ struct SubRole {
     int32_t n_act, raw;
 };
 __global__ void k_subroles(const uint8_t* __restrict__ roles, const uint32_t* __restrict__ row_of, const int32_t* __restrict__ head,
-                           const int32_t* __restrict__ sub_incl, int64_t n_active, SubRole* __restrict__ out, unsigned int* __restrict__ err) {
+                           const int32_t* __restrict__ sub_incl, const RunHdr* __restrict__ hdr, SubRole* __restrict__ out, unsigned int* __restrict__ err) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_active) return;
+    if (j >= (int64_t)hdr->n_active) return;
     const int s = sub_incl[j] - 1;
     const uint8_t r = roles[row_of[j]];
     if (!(r & ROLE_COLUMN_ONLY)) atomicAdd(&out[s].n_act, 1);
@@ -190,22 +205,22 @@ __global__ void k_exact_prep(DevIn in, unsigned long long* donor_mask, uint64_t*
     donor_mask[e] = m;
 }
 
-// Per-segment reference planes (internal base code, 2 planes x SEGPL_WORDS words, position 0 = first base of the
-// segment, zero beyond its end): the fast bucketer path slices / shifts them instead of touching segment bytes.
-constexpr int SEGPL_WORDS = 16;   // segments up to 512 nt
-__global__ void k_seg_planes(DevIn in, uint32_t* __restrict__ segpl) {
+// Per-segment reference planes + lengths at the canonical seg id (segments with equal content write equal values).
+__global__ void k_seg_planes(DevIn in, uint32_t* __restrict__ segpl, int32_t* __restrict__ seglen) {
     const int lane = threadIdx.x & 31;
     const int64_t sg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (sg >= in.n_segs) return;
     const uint8_t* b = in.seg_bytes + in.seg_off[sg];
     const long long len = in.seg_off[sg + 1] - in.seg_off[sg];
+    const int64_t cs = in.seg_canon[sg];
+    if (lane == 0) seglen[cs] = (int32_t)min(len, (long long)0x7fffffff);
     for (int w = 0; w < SEGPL_WORDS; w++) {
         const long long p = (long long)w * 32 + lane;
         const uint32_t code = p < len ? base_code(b[p]) : 0u;
         const uint32_t lo = __ballot_sync(0xffffffffu, code & 1), hi = __ballot_sync(0xffffffffu, code & 2);
         if (lane == 0) {
-            segpl[(sg * 2 + 0) * SEGPL_WORDS + w] = lo;
-            segpl[(sg * 2 + 1) * SEGPL_WORDS + w] = hi;
+            segpl[(cs * 2 + 0) * SEGPL_WORDS + w] = lo;
+            segpl[(cs * 2 + 1) * SEGPL_WORDS + w] = hi;
         }
     }
 }
@@ -218,35 +233,23 @@ __device__ __forceinline__ uint32_t even_bits(uint32_t x) {
     x = (x | (x >> 8)) & 0x0000ffffu;
     return x;
 }
-// bits [0, n) set (n may be <= 0 or >= 32)
-__device__ __forceinline__ uint32_t mask_lt(long long n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << (int)n) - 1u)); }
-// 32 bits of a SEGPL_WORDS-word plane starting at bit index `idx` (bits outside the plane read as 0)
-__device__ __forceinline__ uint32_t plane_bits(const uint32_t* __restrict__ pl, long long idx) {
-    const long long wi = idx >> 5;   // floor
-    const int sh = (int)(idx & 31);
-    const uint32_t a = (wi >= 0 && wi < SEGPL_WORDS) ? pl[wi] : 0u;
-    const uint32_t b = (wi + 1 >= 0 && wi + 1 < SEGPL_WORDS) ? pl[wi + 1] : 0u;
-    return sh ? ((a >> sh) | (b << (32 - sh))) : a;
-}
-
 // ------------------------------------------------------------------------------------------------
 // The bucketer: one warp per packed row.  Writes
 //   * CDR3 planes (heavy ++ light concatenated), layout [plane*W1 + w][npad] per sub-bucket
-//   * the row record (layout in ejb_types.cuh): contig planes, own-reference planes in contig
-//     coordinates, compare mask, reference-difference bitmap d, optional gap plane
-//   * the aux record (AUX_INTS ints) and rowq / subq
+//   * the row record (layout in ejb_types.cuh): contig planes, reference-difference bitmap d, optional gap plane
+//   * the aux record (AUX_INTS ints) and rowq / subq, reference-set tag and donor set
 // ------------------------------------------------------------------------------------------------
 #ifndef PACK_MINB
-#define PACK_MINB 8   // latency-bound: occupancy wins over spills (prepare phase: 1 -> 2.6 ms, 4 -> 1.97, 5 -> 1.82, 8 -> 1.72)
+#define PACK_MINB 8   // latency-bound: occupancy wins over spills
 #endif
 __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__ subs, const int32_t* __restrict__ sub_incl,
-                            const uint32_t* __restrict__ row_of, int64_t n_active, const unsigned long long* __restrict__ donor_mask,
-                            const uint32_t* __restrict__ segpl, uint32_t* __restrict__ cdr3w, uint4* __restrict__ rowstore,
+                            const uint32_t* __restrict__ row_of, const unsigned long long* __restrict__ n_active_p, const unsigned long long* __restrict__ donor_mask,
+                            const uint32_t* __restrict__ segpl, const int32_t* __restrict__ seglen, uint32_t* __restrict__ cdr3w, uint4* __restrict__ rowstore,
                             int32_t* __restrict__ aux, int32_t* __restrict__ rowq, int32_t* __restrict__ subq,
                             unsigned long long* __restrict__ tagq, unsigned long long* __restrict__ donq) {
     const int lane = threadIdx.x & 31;
     const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= n_active) return;
+    if (j >= (int64_t)*n_active_p) return;
     const int s = sub_incl[j] - 1;
     const SubBucket sb = subs[s];
     const int64_t k = row_of[j];
@@ -255,20 +258,30 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
     uint32_t flags = 0;
     int tot = 0;
 
-    // ---- CDR3 planes ----
+    // ---- CDR3 planes (ASCII bytes, or 2-bit packed words: the role tigsp plays for the contigs) ----
     {
-        const uint8_t* c0 = in.cdr3_bytes + in.row_cdr3_off[2 * k];
-        const uint8_t* c1 = in.cdr3_bytes + in.row_cdr3_off[2 * k + 1];
         const int T = sb.ch + sb.cl;
         const int nw = (T + 31) / 32;
+        const int64_t o0 = in.row_cdr32_off ? in.row_cdr32_off[2 * k] : -1, o1 = in.row_cdr32_off ? in.row_cdr32_off[2 * k + 1] : -1;
+        const uint8_t* c0 = in.cdr3_bytes + (o0 >= 0 ? 0 : in.row_cdr3_off[2 * k]);
+        const uint8_t* c1 = in.cdr3_bytes + (o1 >= 0 ? 0 : in.row_cdr3_off[2 * k + 1]);
+        const uint32_t* w0 = in.cdr32_words + (o0 >= 0 ? o0 : 0);
+        const uint32_t* w1 = in.cdr32_words + (o1 >= 0 ? o1 : 0);
         bool irr = false;
         for (int w = 0; w < nw; w++) {
             const int p = w * 32 + lane;
             int code = 0;
             if (p < T) {
-                const uint8_t b = (p < sb.ch) ? c0[p] : c1[p - sb.ch];
-                if (!is_acgt_fast(b)) irr = true;
-                code = (int)base_code(b);
+                const bool heavy = p < sb.ch;
+                const int pp = heavy ? p : p - sb.ch;
+                if ((heavy ? o0 : o1) >= 0) {
+                    const uint32_t c2 = ((heavy ? w0 : w1)[pp >> 4] >> (2 * (pp & 15))) & 3u;   // A,C,G,T = 0..3
+                    code = (int)(c2 ^ (c2 >> 1));                                               // -> internal A,C,T,G = 0,1,2,3
+                } else {
+                    const uint8_t b = (heavy ? c0 : c1)[pp];
+                    if (!is_acgt_fast(b)) irr = true;
+                    code = (int)base_code(b);
+                }
             }
             const uint32_t lo = __ballot_sync(0xffffffffu, code & 1);
             const uint32_t hi = __ballot_sync(0xffffffffu, code & 2);
@@ -280,7 +293,7 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
         if (__any_sync(0xffffffffu, irr)) flags |= F_CDR3_IRREG;
     }
 
-    // ---- contig planes, reference planes, compare mask, difference bitmap ----
+    // ---- contig planes and the difference bitmap against the row's own V / J reference ----
     uint32_t* rec32 = reinterpret_cast<uint32_t*>(rowstore + sb.rs_off + li * (int64_t)sb.rec_u4);
     int base_u4 = 0;
     // FWR1 / CDR1 / CDR2 ranges of chain 0 (only meaningful when that chain is the left chain; stage 2 checks)
@@ -296,11 +309,12 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
         const bool okf = !has_f || (fr1 >= 0 && fr1 <= cdr1 && cdr1 <= L);
         const bool okc1 = !has_c1 || (cdr1 >= 0 && fr2 <= L);
         const bool okc2 = !has_c2 || (cdr2 >= 0 && fr3 <= L);
-        // the three ranges must also be pairwise disjoint to share one region-id plane pair
+        // the three ranges must also be pairwise disjoint to be counted from one pass over the difference words;
+        // the region masks hold 16-bit bounds (contigs on this path are <= 1024 nt)
         bool disj = true;
         if (has_f && has_c2 && !(cdr1 <= cdr2 || fr3 <= fr1)) disj = false;
         if (has_c1 && has_c2 && !(fr2 <= cdr2 || fr3 <= cdr1)) disj = false;
-        if (okf && okc1 && okc2 && disj) {
+        if (okf && okc1 && okc2 && disj && L <= 128 * MAXW4) {
             flags |= B_REG_OK;
             if (has_f) { rF0 = fr1; rF1 = cdr1; }
             if (has_c1) { rC10 = cdr1; rC11 = fr2; }
@@ -310,23 +324,24 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
     // ---- fast path: both contigs 2-bit packed, <= 512 nt, segments <= 512 nt.  Lanes 0-15 build the 16 words of every
     //      plane of chain 0, lanes 16-31 those of chain 1, by de-interleaving the packed words: no per-base work. ----
     bool fastrow = sb.W4h == 4 && sb.W4l == 4 && in.row_tig2_off != nullptr;
-    if (fastrow) {
-        for (int m = 0; m < 2; m++) {
-            if (in.row_tig2_off[2 * k + m] < 0) fastrow = false;
-            const int sv = in.row_vs[2 * k + m], sj = in.row_js[2 * k + m];
-            if (in.seg_off[sv + 1] - in.seg_off[sv] > 32 * SEGPL_WORDS || in.seg_off[sj + 1] - in.seg_off[sj] > 32 * SEGPL_WORDS) fastrow = false;
-        }
+    bool longseg = false;
+    for (int m = 0; m < 2; m++) {
+        const int sv = in.seg_canon[in.row_vs[2 * k + m]], sj = in.seg_canon[in.row_js[2 * k + m]];
+        if (seglen[sv] > 32 * SEGPL_WORDS || seglen[sj] > 32 * SEGPL_WORDS) longseg = true;
+        if (fastrow && in.row_tig2_off[2 * k + m] < 0) fastrow = false;
+    }
+    if (longseg) {   // stage 2a cannot slice this row's references out of the segment planes: byte-exact path
+        fastrow = false;
+        flags |= F_SLOWGEOM;
     }
     if (fastrow) {
         const int m = lane >> 4, w = lane & 15;
         const int L = m ? sb.Ll : sb.Lh;
         const int gapbit = (sb.gap >> m) & 1;
-        const int sv = in.row_vs[2 * k + m], sj = in.row_js[2 * k + m];
-        const long long vlen = in.seg_off[sv + 1] - in.seg_off[sv], jlen = in.seg_off[sj + 1] - in.seg_off[sj];
-        const long long vr = vlen - P.ref_v_trim, jr = jlen - P.ref_j_trim;
+        const RefGeom G = ref_geom(seglen, in.seg_canon[in.row_vs[2 * k + m]], in.seg_canon[in.row_js[2 * k + m]], L, P.ref_v_trim, P.ref_j_trim);
         uint32_t fl = 0;
-        if (vr < 0 || jr < 0 || jr > L) fl |= F_PANIC;
-        if (vr > L || vr + jr > L) fl |= F_SLOWGEOM;
+        if (G.vr < 0 || G.jr < 0 || G.jr > L) fl |= F_PANIC;
+        if (G.vr > L || G.vr + G.jr > L) fl |= F_SLOWGEOM;
         // contig planes from the packed words (A,C,G,T = 0..3 -> internal code lo' = lo ^ hi, hi' = hi)
         const uint32_t* tw = in.tig2_words + in.row_tig2_off[2 * k + m];
         const int nw16 = (L + 15) >> 4;
@@ -335,31 +350,15 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
         uint32_t lo = even_bits(x0) | (even_bits(x1) << 16), hi = even_bits(x0 >> 1) | (even_bits(x1 >> 1) << 16);
         lo = (lo ^ hi) & inl;
         hi &= inl;
-        // compare masks and reference planes in contig coordinates
-        const uint32_t cmv = mask_lt(vr - 32 * w) & inl;
-        const uint32_t cmj = inl & ~mask_lt(((long long)L - jr) - 32 * w) & ~cmv;   // p >= L - jr, V range has priority
-        const uint32_t* vp = segpl + (size_t)sv * 2 * SEGPL_WORDS;
-        const uint32_t* jp = segpl + (size_t)sj * 2 * SEGPL_WORDS;
-        const long long jidx = (long long)32 * w + (jlen - L);   // J index of contig position 32w
-        const uint32_t rlo = (vp[w] & cmv) | (plane_bits(jp, jidx) & cmj);
-        const uint32_t rhi = (vp[SEGPL_WORDS + w] & cmv) | (plane_bits(jp + SEGPL_WORDS, jidx) & cmj);
-        const uint32_t cm = cmv | cmj;
-        const uint32_t dm = cm & ((lo ^ rlo) | (hi ^ rhi));
+        uint32_t rlo, rhi, cm;
+        ref_word(segpl, G, w, rlo, rhi, cm);
+        const uint32_t dm = (fl & (F_PANIC | F_SLOWGEOM)) ? 0u : (cm & ((lo ^ rlo) | (hi ^ rhi)));
         uint32_t* r = rec32 + (m ? rec_planes(0, sb.gap & 1) * sb.W4h * 4 : 0) + w;
         const int st = 16;   // 4 * W4
         r[PL_TLO * st] = lo;
         r[PL_THI * st] = hi;
         r[PL_D * st] = dm;
-        r[PL_RLO * st] = rlo;
-        r[PL_RHI * st] = rhi;
-        r[PL_CMP * st] = cm;
-        if (m == 0) {
-            auto rng = [&](int a, int b) { return mask_lt((long long)b - 32 * w) & ~mask_lt((long long)a - 32 * w); };
-            const uint32_t mF = rng(rF0, rF1), mC1 = rng(rC10, rC11), mC2 = rng(rC20, rC21);
-            r[PL_GLO * st] = (mF | mC2) & ~mC1;       // region ids 1 (FWR1) and 3 (CDR2) have the low bit
-            r[PL_GHI * st] = (mC1 | mC2) & ~mF;       // ids 2 (CDR1) and 3 (CDR2) have the high bit; first match wins like the scalar path
-        }
-        if (gapbit) r[gap_plane(m) * st] = 0u;
+        if (gapbit) r[PL_GAP * st] = 0u;
         int t = __popc(dm);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -391,9 +390,8 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
         if (hasdel) flags |= (m == 0) ? F_HASDEL_H : F_HASDEL_L;
         bool odd = false;
         const int nw = (L + 31) / 32;
-        const int npl = rec_planes(m, gapbit);
         // lane w keeps word w of every plane (4 * W4 <= 32 words) and writes them at the end
-        uint32_t k_lo = 0, k_hi = 0, k_d = 0, k_gap = 0, k_glo = 0, k_ghi = 0, k_rlo = 0, k_rhi = 0, k_cm = 0;
+        uint32_t k_lo = 0, k_hi = 0, k_d = 0, k_gap = 0;
         const int nwords = min(nw, 4 * W4);
         const long long jshift = (long long)jlen - L;   // J index of contig position p: p + jshift  (tig[L-1-pp] vs J[|J|-1-pp], join_one.rs:388-391)
 #pragma unroll 4
@@ -410,27 +408,18 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
                     code = base_code(b);
                 }
                 if (p < vr) { rbyte = vseg[p]; inr = true; }
-                else if (p >= L - jr) { rbyte = jseg[p + jshift]; inr = true; }
+                else if (p >= L - jr && p + jshift >= 0) { rbyte = jseg[p + jshift]; inr = true; }
             }
             const bool gapb = (b == '-') && hasdel;
             if (p < L && !gapb && !is_acgt_fast(b)) odd = true;
             const uint32_t rcode = base_code(rbyte);
             // seg bytes are canonical upper-case ACGT (host); '-' and odd bytes never equal them
             const bool dbit = inr && (packed ? (code != rcode) : (b != rbyte));
-            int rid = 0;
-            if (m == 0) {
-                if (p >= rF0 && p < rF1) rid = 1;
-                else if (p >= rC10 && p < rC11) rid = 2;
-                else if (p >= rC20 && p < rC21) rid = 3;
-            }
             const uint32_t lo = __ballot_sync(0xffffffffu, code & 1), hi = __ballot_sync(0xffffffffu, code & 2);
             const uint32_t dm = __ballot_sync(0xffffffffu, dbit), gp = __ballot_sync(0xffffffffu, gapb);
-            const uint32_t rlo = __ballot_sync(0xffffffffu, inr && (rcode & 1)), rhi = __ballot_sync(0xffffffffu, inr && (rcode & 2));
-            const uint32_t cm = __ballot_sync(0xffffffffu, inr);
-            const uint32_t glo = __ballot_sync(0xffffffffu, rid & 1), ghi = __ballot_sync(0xffffffffu, rid & 2);
             tot += __popc(dm);
             if (lane == w) {
-                k_lo = lo; k_hi = hi; k_d = dm; k_gap = gp; k_glo = glo; k_ghi = ghi; k_rlo = rlo; k_rhi = rhi; k_cm = cm;
+                k_lo = lo; k_hi = hi; k_d = dm; k_gap = gp;
             }
         }
         if (lane < 4 * W4) {
@@ -440,14 +429,7 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
             r[PL_TLO * st] = k_lo;
             r[PL_THI * st] = k_hi;
             r[PL_D * st] = k_d;
-            r[PL_RLO * st] = k_rlo;
-            r[PL_RHI * st] = k_rhi;
-            r[PL_CMP * st] = k_cm;
-            if (m == 0) {
-                r[PL_GLO * st] = k_glo;
-                r[PL_GHI * st] = k_ghi;
-            }
-            if (gapbit) r[gap_plane(m) * st] = k_gap;
+            if (gapbit) r[PL_GAP * st] = k_gap;
         }
         if (W4 == 0 && !packed) {  // contig longer than the fast path: the byte-exact path handles it
             for (int p = lane; p < L; p += 32)
@@ -497,7 +479,9 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
         a[AX_FR3] = in.ch_fr3[ch];
         a[AX_CHH] = ch;
         a[AX_CHL] = cl;
-        a[AX_PAD1] = a[AX_PAD2] = a[AX_PAD3] = 0;
+        a[AX_RGN0] = rF0 | (rF1 << 16);
+        a[AX_RGN1] = rC10 | (rC11 << 16);
+        a[AX_RGN2] = rC20 | (rC21 << 16);
         if (tagq) {
             tagq[q] = (flags & F_SLOWMASK) ? TAG_SLOW : make_ref_tag(a[AX_VSH], a[AX_VSL], a[AX_JSH], a[AX_JSL]);
             donq[q] = P.mix_donors ? 0ull : dmask;   // join_one.rs:301-323 only rejects when donors are not mixed

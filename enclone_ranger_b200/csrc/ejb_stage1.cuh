@@ -1,4 +1,4 @@
-// ejb_stage1.cuh — CDR3 Hamming pre-filter over all pairs of a sub-bucket (TMA-staged tiles).
+// ejb_stage1.cuh — CDR3 Hamming pre-filter over all pairs of a sub-bucket (TMA-staged tiles, warp-private hit queues).
 #pragma once
 #include "ejb_types.cuh"
 
@@ -6,12 +6,20 @@ namespace ejb {
 
 // ------------------------------------------------------------------------------------------------
 // Stage 1: all pairs of a sub-bucket, tiled 128 x 128.  One CTA = one row block x a strip of up to
-// S1_STRIP column blocks.  Row/column CDR3 planes + class labels are staged in shared memory by TMA
-// bulk copies (double-buffered columns); each thread keeps an 8-row fragment in registers and walks
-// 8 columns per tile.  Distance = popc of (lo^lo')|(hi^hi') per 32 bases, words pre-reduced with a
-// carry-save adder so that 3 words cost 2 popc.  A pair becomes a candidate iff
-// cd <= maxcd  &&  class labels differ (join_core.rs:32 — a pair already connected by
-// lexicographically smaller joins can never be in pot).
+// S1_STRIP column blocks.  Row/column CDR3 planes, class labels and the per-row tags are staged in
+// shared memory by TMA bulk copies through a ring of S1_NBUF column buffers guarded by full / empty
+// mbarriers: the eight warps of a CTA never meet at a CTA-wide barrier inside the tile loop, a warp
+// whose 16 x 16 groups are already one class runs ahead of the ones that score.
+// Each thread keeps an 8-row fragment in registers and walks 8 columns per tile.  Per column:
+//   1. one warp vote skips 16 rows x 16 columns that carry one class label (join_core.rs:32: a pair
+//      already connected by lexicographically smaller joins can never be in pot);
+//   2. the FIRST 32 positions of the eight pairs go through XOR + popc; a pair can only be CDR3-close
+//      if that partial distance is already <= maxcd, so one more warp vote ends the column for
+//      unrelated sequences (typically ~24 of 32 positions differ) after ONE popc per pair;
+//   3. otherwise the remaining words are added, hits are tested against the per-row tags and pushed
+//      to the warp's private queue in shared memory (ballot compaction, no atomics); a queue is
+//      flushed to the global candidate list with one atomicAdd per ~100 candidates.
+// A pair becomes a candidate iff cd <= maxcd && class labels differ && not rejected by the tags.
 // ------------------------------------------------------------------------------------------------
 struct RowTask {       // (part of) one row block of one sub-bucket, against every column block to its right
     int32_t sub;
@@ -21,32 +29,37 @@ struct RowTask {       // (part of) one row block of one sub-bucket, against eve
     int32_t tid, pad;         // task id inside the round (per-task candidate counters)
 };
 
+// distance contribution of the words after the first
 template <int W1>
-__device__ __forceinline__ int cdr3_dist(const uint32_t* rl, const uint32_t* rh, const uint32_t* cl, const uint32_t* chh) {
-    uint32_t x[W1];
+__device__ __forceinline__ int cdr3_rest(const uint32_t* rl, const uint32_t* rh, const uint32_t* cl, const uint32_t* chh) {
+    if constexpr (W1 == 1) {
+        return 0;
+    } else {
+        uint32_t x[W1];
 #pragma unroll
-    for (int w = 0; w < W1; w++) x[w] = (rl[w] ^ cl[w]) | (rh[w] ^ chh[w]);
-    if (W1 == 1) return __popc(x[0]);
-    if (W1 == 2) return __popc(x[0]) + __popc(x[1]);
-    uint32_t s = x[0] ^ x[1] ^ x[2];
-    uint32_t c = (x[0] & x[1]) | (x[2] & (x[0] ^ x[1]));
-    if (W1 == 3) return __popc(s) + 2 * __popc(c);
-    if (W1 == 4) return __popc(s) + __popc(x[3]) + 2 * __popc(c);
-    if (W1 == 5) {
-        uint32_t s2 = s ^ x[3] ^ x[4];
-        uint32_t c2 = (s & x[3]) | (x[4] & (s ^ x[3]));
-        return __popc(s2) + 2 * (__popc(c) + __popc(c2));
+        for (int w = 1; w < W1; w++) x[w] = (rl[w] ^ cl[w]) | (rh[w] ^ chh[w]);
+        if constexpr (W1 == 2) {
+            return __popc(x[1]);
+        } else if constexpr (W1 == 3) {
+            return __popc(x[1]) + __popc(x[2]);
+        } else {
+            // carry-save adder over three words: 2 popc instead of 3
+            const uint32_t s = x[1] ^ x[2] ^ x[3];
+            const uint32_t c = (x[1] & x[2]) | (x[3] & (x[1] ^ x[2]));
+            int d = __popc(s) + 2 * __popc(c);
+            if constexpr (W1 >= 5) d += __popc(x[4]);
+            if constexpr (W1 >= 6) d += __popc(x[5]);
+            return d;
+        }
     }
-    // W1 == 6
-    uint32_t s3 = x[3] ^ x[4] ^ x[5];
-    uint32_t c3 = (x[3] & x[4]) | (x[5] & (x[3] ^ x[4]));
-    return __popc(s) + __popc(s3) + 2 * (__popc(c) + __popc(c3));
 }
+// popc instructions per lane of cdr3_rest (for the executed-popc statistics)
+__host__ __device__ constexpr int cdr3_rest_popc(int w1) { return w1 <= 1 ? 0 : (w1 == 2 ? 1 : (w1 <= 4 ? 2 : (w1 == 5 ? 3 : 4))); }
 
 // MODE bits (compile time):
 //   S1_RUNI   one warp vote per column when the thread's 8 rows and the column carry one class label
-//   S1_TAGS   per-row tags staged next to the labels; after the pair loop of a half tile the hit list is compacted in place,
-//             dropping hits that join_one is known to reject without looking at the sequences:
+//   S1_TAGS   per-row tags staged next to the labels; a hit is dropped when join_one is known to reject it without looking at
+//             the sequences:
 //             * one row is known (from an earlier round's stage 2a) to fail the degradation test of join_one.rs:434-440
 //               against the other row's reference set — the decision stage 2a would take from its memo;
 //             * the two exact subclonotypes come from different donor sets (join_one.rs:301-323; donq is 0 for rows without a
@@ -68,16 +81,23 @@ __device__ __forceinline__ bool flag_kill(uint32_t fr, uint32_t fc, unsigned int
     return true;
 }
 
-// S1_NOVOTE: no per-row warp vote before the distance (the column-level vote S1_RUNI already skips uniform 16 x 16 groups)
-#ifndef S1_NOVOTE
-#define S1_NOVOTE 0
-#endif
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 #ifndef S1_MINB2
 #define S1_MINB2 4
 #endif
 #ifndef S1_MINB3
 #define S1_MINB3 3
 #endif
+constexpr int S1_QCAP = 128;              // entries of a warp's private hit queue
+constexpr int S1_WARPS = S1_THREADS / 32;
+template <int W1>
+struct S1Cfg {
+    static constexpr int NBUF = (W1 <= 4) ? 3 : 2;   // column buffers in the TMA ring (static shared memory stays below 48 KB)
+};
+
 template <int W1, int MODE>
 __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) ? S1_MINB3 : 2)) k_stage1(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, int n_tasks,
                                                        const uint32_t* __restrict__ cdr3w, const int32_t* __restrict__ labq,
@@ -88,15 +108,14 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
                                                        const unsigned long long* __restrict__ donq, const uint32_t* __restrict__ flagq) {
     constexpr bool RUNI = (MODE & S1_RUNI) != 0, TAGS = (MODE & S1_TAGS) != 0;
     constexpr int NP = 2 * W1;            // plane-words per row
-    constexpr int TAG0 = (NP + 1) * TILE; // word offset of the staged reference-set tags (uint64 x TILE), then the dead tags
+    constexpr int TAG0 = (NP + 1) * TILE; // word offset of the staged reference-set tags (uint64 x TILE), then the dead tags, then the donor sets
     constexpr int FLAG0 = (NP + 7) * TILE; // word offset of the staged flag words
     constexpr int SLOT = (NP + 1 + (TAGS ? 7 : 0)) * TILE;   // words per staged tile (planes + labels [+ tags + dead tags + donor sets + flags])
+    constexpr int NBUF = S1Cfg<W1>::NBUF;
     __shared__ __align__(16) uint32_t s_row[SLOT];
-    __shared__ __align__(16) uint32_t s_col[2][SLOT];
-    __shared__ __align__(8) uint64_t s_bar[3];
-    __shared__ uint16_t s_hits[TILE * TILE / 2];
-    __shared__ unsigned int s_nhits, s_nkeep;
-    __shared__ unsigned long long s_base;
+    __shared__ __align__(16) uint32_t s_col[NBUF][SLOT];
+    __shared__ __align__(8) uint64_t s_full[NBUF], s_empty[NBUF], s_rowbar;
+    __shared__ __align__(8) uint2 s_q[S1_WARPS][S1_QCAP];
     __shared__ int s_cbs[S1_STRIP];
     __shared__ int s_ncb;
 
@@ -113,7 +132,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     const int nb = (sb.n + TILE - 1) / TILE;
     const int rb = t.rb;
     const int cb_first = rb + (int)(cta - t.cta0) * S1_STRIP;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;
 
     // class-skip at block level: both blocks uniformly in one class
@@ -126,10 +145,11 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
             s_cbs[n++] = c;
         }
         s_ncb = n;
-        s_nhits = 0;
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_init(&s_bar[2], 1);
+        for (int b = 0; b < NBUF; b++) {
+            mbar_init(&s_full[b], 1);
+            mbar_init(&s_empty[b], S1_WARPS);
+        }
+        mbar_init(&s_rowbar, 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -154,13 +174,12 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         }
     };
     if (tid == 0) {
-        issue(s_row, rb, &s_bar[2]);
-        issue(s_col[0], s_cbs[0], &s_bar[0]);
-        if (ncb > 1) issue(s_col[1], s_cbs[1], &s_bar[1]);
+        issue(s_row, rb, &s_rowbar);
+        for (int b = 0; b < NBUF && b < ncb; b++) issue(s_col[b], s_cbs[b], &s_full[b]);
     }
 
     // ---- row fragment -> registers ----
-    mbar_wait(&s_bar[2], 0);
+    mbar_wait(&s_rowbar, 0);
     uint32_t rl[8][W1], rh[8][W1];
     int rlab[8];
 #pragma unroll
@@ -183,156 +202,136 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     const int row_lo = t.row_lo;
     const int row_lim = min(sb.n - rb * TILE, t.row_hi);  // valid local rows are row_lo <= r < row_lim
     const int maxcd = sb.maxcd;
-    unsigned long long evaluated = 0, killed = 0;   // thread 0 only
-    unsigned int donor_kills = 0, flag_kills = 0;    // per thread
+    const uint32_t q_r0 = (uint32_t)(sb.q0 + (int64_t)rb * TILE);
+    unsigned long long evaluated = 0;                 // thread 0 only
+    unsigned int donor_kills = 0, tag_kills = 0;      // per thread
+    unsigned int n_first = 0, n_full = 0;             // per lane: first-word / remaining-word evaluations
+    unsigned int wq = 0;                              // warp-uniform: entries in this warp's queue
+    unsigned long long w_total = 0;                   // warp-uniform: candidates this warp emitted
+    uint2* const myq = s_q[warp];
+    const unsigned int lt_mask = (1u << lane) - 1u;
+
+    auto flush = [&]() {   // all lanes
+        __syncwarp();
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(&ctr->n_cand, (unsigned long long)wq);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        for (unsigned int h = lane; h < wq; h += 32) {
+            const unsigned long long o = b + h;
+            if (o < cand_cap) cand[o] = myq[h]; else ctr->overflow = 1ull;
+        }
+        w_total += wq;
+        wq = 0;
+        __syncwarp();
+    };
+
+    const unsigned long long* const rt = reinterpret_cast<const unsigned long long*>(s_row + TAG0);
 
     for (int it = 0; it < ncb; it++) {
+        const int buf = it % NBUF;
+        // producer: the buffer of tile it-1 is refilled with tile it-1+NBUF once every warp has released it
+        if (tid == 0 && it >= 1 && it - 1 + NBUF < ncb) {
+            const int pb = (it - 1) % NBUF;
+            mbar_wait(&s_empty[pb], ((it - 1) / NBUF) & 1);
+            issue(s_col[pb], s_cbs[it - 1 + NBUF], &s_full[pb]);
+        }
+        __syncwarp();
         const int cb = s_cbs[it];
-        const int buf = it & 1;
-        mbar_wait(&s_bar[buf], (it >> 1) & 1);
+        mbar_wait(&s_full[buf], (it / NBUF) & 1);
         const uint32_t* sc = s_col[buf];
+        const unsigned long long* const ct = reinterpret_cast<const unsigned long long*>(sc + TAG0);
         const int col_lim = sb.n - cb * TILE;
         const bool diag = (cb == rb);
         const bool full = !diag && row_lo == 0 && row_lim >= TILE && col_lim >= TILE;
-        // two halves of 64 columns: the hit list holds at most 128 x 64 entries
-        for (int half = 0; half < 2; half++) {
-            if (full) {
-#pragma unroll 2
-                for (int j = half * 4; j < half * 4 + 4; j++) {
-                    const int c = j * 16 + tx;
-                    const int clab = (int)sc[NP * TILE + c];
-                    if (RUNI && __all_sync(0xffffffffu, clab == runi)) continue;   // 16 rows x 16 columns of one class: one vote instead of eight
-                    uint32_t cl[W1], chh[W1];
+        const uint32_t q_c0 = (uint32_t)(sb.q0 + (int64_t)cb * TILE);
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+            const int c = j * 16 + tx;
+            const int clab = (int)sc[NP * TILE + c];
+            if (RUNI && __all_sync(0xffffffffu, clab == runi)) continue;   // 16 rows x 16 columns of one class: one vote instead of eight
+            uint32_t cl[W1], chh[W1];
 #pragma unroll
-                    for (int w = 0; w < W1; w++) {
-                        cl[w] = sc[w * TILE + c];
-                        chh[w] = sc[(W1 + w) * TILE + c];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        // class test first (join_core.rs:32): a warp whose 32 pairs are all already connected skips the
-                        // distance entirely — the common case inside a clone once its first rows have been processed
-                        const bool need = rlab[i] != clab;
-                        if (S1_NOVOTE || __any_sync(0xffffffffu, need)) {
-                            const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
-                            if (need && cd <= maxcd) {
-                                if (TAGS && flag_kill(s_row[FLAG0 + i * 16 + ty], sc[FLAG0 + c], donor_kills, flag_kills)) continue;
-                                const unsigned int h = atomicAdd(&s_nhits, 1u);
-                                s_hits[h] = (uint16_t)(((i * 16 + ty) << 7) | c);
-                            }
-                        }
-                    }
-                }
-            } else {
-                for (int j = half * 4; j < half * 4 + 4; j++) {
-                    const int c = j * 16 + tx;
-                    const int clab = (int)sc[NP * TILE + c];
-                    if (RUNI && __all_sync(0xffffffffu, clab == runi)) continue;
-                    uint32_t cl[W1], chh[W1];
-#pragma unroll
-                    for (int w = 0; w < W1; w++) {
-                        cl[w] = sc[w * TILE + c];
-                        chh[w] = sc[(W1 + w) * TILE + c];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int r = i * 16 + ty;
-                        const bool need = r >= row_lo && r < row_lim && c < col_lim && (!diag || r < c) && rlab[i] != clab;
-                        if (S1_NOVOTE || __any_sync(0xffffffffu, need)) {
-                            const int cd = cdr3_dist<W1>(rl[i], rh[i], cl, chh);
-                            if (need && cd <= maxcd) {
-                                if (TAGS && flag_kill(s_row[FLAG0 + r], sc[FLAG0 + c], donor_kills, flag_kills)) continue;
-                                const unsigned int h = atomicAdd(&s_nhits, 1u);
-                                s_hits[h] = (uint16_t)((r << 7) | c);
-                            }
-                        }
-                    }
-                }
+            for (int w = 0; w < W1; w++) {
+                cl[w] = sc[w * TILE + c];
+                chh[w] = sc[(W1 + w) * TILE + c];
             }
-            __syncthreads();  // all hits of this half recorded (and, after half 1, s_col[buf] drained of plane reads)
-            if (TAGS) {
-                const unsigned int nh0 = s_nhits;
-                if (nh0) {   // block-uniform
-                    const unsigned long long* rt = reinterpret_cast<const unsigned long long*>(s_row + TAG0);
-                    const unsigned long long* ct = reinterpret_cast<const unsigned long long*>(sc + TAG0);
-                    if (tid == 0) s_nkeep = 0;
-                    __syncthreads();
-                    for (unsigned int b0 = 0; b0 < nh0; b0 += S1_THREADS) {
-                        const unsigned int h = b0 + tid;
-                        bool keep = false;
-                        uint16_t v = 0;
-                        if (h < nh0) {
-                            v = s_hits[h];
-                            const int r = v >> 7, c = v & 127;
-                            const unsigned long long dr = rt[2 * TILE + r], dc = ct[2 * TILE + c];
-                            const bool donors = dr != 0 && dc != 0 && dr != dc;
-                            keep = !(donors || rt[TILE + r] == ct[c] || ct[TILE + c] == rt[r]);
+            // first word of the eight pairs: is any of them still a possible candidate?
+            uint32_t live = 0;   // bit i: pair (row i, this column) has partial distance <= maxcd, different labels, and is in range
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int p0 = __popc((rl[i][0] ^ cl[0]) | (rh[i][0] ^ chh[0]));
+                bool ok = p0 <= maxcd && rlab[i] != clab;
+                if (!full) {
+                    const int r = i * 16 + ty;
+                    ok = ok && r >= row_lo && r < row_lim && c < col_lim && (!diag || r < c);
+                }
+                live |= (ok ? 1u : 0u) << i;
+            }
+            n_first += 8;
+            if (!__any_sync(0xffffffffu, live != 0)) continue;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                bool hit = (live >> i) & 1u;
+                if (!__any_sync(0xffffffffu, hit)) continue;
+                const int r = i * 16 + ty;
+                if (W1 > 1) {
+                    const int cd = __popc((rl[i][0] ^ cl[0]) | (rh[i][0] ^ chh[0])) + cdr3_rest<W1>(rl[i], rh[i], cl, chh);
+                    n_full++;
+                    hit = hit && cd <= maxcd;
+                }
+                if (TAGS && hit) {
+                    if (flag_kill(s_row[FLAG0 + r], sc[FLAG0 + c], donor_kills, tag_kills)) hit = false;
+                    else {
+                        const unsigned long long dr = rt[2 * TILE + r], dc = ct[2 * TILE + c];
+                        const bool donors = dr != 0 && dc != 0 && dr != dc;
+                        if (donors || rt[TILE + r] == ct[c] || ct[TILE + c] == rt[r]) {
+                            hit = false;
+                            tag_kills++;
                             donor_kills += donors;
                         }
-                        __syncthreads();   // entries [b0, b0 + 256) are in registers; kept ones land below b0 + 256
-                        if (keep) s_hits[atomicAdd(&s_nkeep, 1u)] = v;
                     }
-                    __syncthreads();
-                    if (tid == 0) {
-                        killed += nh0 - s_nkeep;
-                        s_nhits = s_nkeep;
-                    }
-                    __syncthreads();
+                }
+                const unsigned int m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    if (hit) myq[wq + __popc(m & lt_mask)] = make_uint2(q_r0 + r, q_c0 + c);
+                    wq += __popc(m);
+                    if (wq > S1_QCAP - 32) flush();
                 }
             }
-            const unsigned int nh = s_nhits;
-            if (tid == 0) {
-                if (half == 1) {
-                    // prefetch the tile after next into the buffer just drained
-                    if (it + 2 < ncb) issue(s_col[buf], s_cbs[it + 2], &s_bar[buf]);
-                    const long long hi = min(TILE, row_lim), lo = row_lo, cc = min(TILE, col_lim), nr = hi - lo;
-                    if (nr > 0) {
-                        if (!diag) evaluated += (unsigned long long)(nr * cc);
-                        else {   // pairs (r, c) with lo <= r < hi, r < c < cc
-                            const long long h2 = min(hi, cc);
-                            const long long n2 = max(h2 - lo, 0ll);
-                            evaluated += (unsigned long long)(n2 * (cc - 1) - (lo + h2 - 1) * n2 / 2);
-                        }
-                    }
+        }
+        // this warp is done with the column buffer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[buf]);
+        if (tid == 0) {
+            const long long hi2 = min(TILE, row_lim), lo2 = row_lo, cc = min(TILE, col_lim), nr = hi2 - lo2;
+            if (nr > 0) {
+                if (!diag) evaluated += (unsigned long long)(nr * cc);
+                else {   // pairs (r, c) with lo <= r < hi, r < c < cc
+                    const long long h2 = min(hi2, cc);
+                    const long long n2 = max(h2 - lo2, 0ll);
+                    evaluated += (unsigned long long)(n2 * (cc - 1) - (lo2 + h2 - 1) * n2 / 2);
                 }
-                if (nh) {
-                    s_base = atomicAdd(&ctr->n_cand, (unsigned long long)nh);
-                    atomicAdd(&unit_cand[t.tid], (unsigned long long)nh);
-                }
-            }
-            if (nh) {
-                __syncthreads();
-                const unsigned long long b = s_base;
-                const uint32_t q_r0 = (uint32_t)(sb.q0 + (int64_t)rb * TILE), q_c0 = (uint32_t)(sb.q0 + (int64_t)cb * TILE);
-                for (unsigned int h = tid; h < nh; h += S1_THREADS) {
-                    const unsigned long long o = b + h;
-                    if (o < cand_cap) {
-                        const uint16_t v = s_hits[h];
-                        cand[o] = make_uint2(q_r0 + (v >> 7), q_c0 + (v & 127));
-                    } else {
-                        ctr->overflow = 1ull;
-                    }
-                }
-                __syncthreads();
-                if (tid == 0) s_nhits = 0;
-                __syncthreads();
             }
         }
     }
-    if (tid == 0) {
-        atomicAdd(&ctr->pairs_eval, evaluated);
-        if (killed) atomicAdd(&ctr->n_s1_kill, killed);
-    }
-    if (TAGS) {
+    if (wq) flush();
+    if (lane == 0 && w_total) atomicAdd(&unit_cand[t.tid], w_total);
+    if (tid == 0) atomicAdd(&ctr->pairs_eval, evaluated);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 16; o > 0; o >>= 1) {
+        n_first += __shfl_xor_sync(0xffffffffu, n_first, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+        if (TAGS) {
             donor_kills += __shfl_xor_sync(0xffffffffu, donor_kills, o);
-            flag_kills += __shfl_xor_sync(0xffffffffu, flag_kills, o);
+            tag_kills += __shfl_xor_sync(0xffffffffu, tag_kills, o);
         }
-        if ((tid & 31) == 0 && donor_kills) atomicAdd(&ctr->n_s1_donor, (unsigned long long)donor_kills);
-        if ((tid & 31) == 0 && flag_kills) atomicAdd(&ctr->n_s1_kill, (unsigned long long)flag_kills);   // n_s1_kill counts every kind
+    }
+    if (lane == 0) {
+        atomicAdd(&ctr->s1_first, (unsigned long long)n_first);
+        if (n_full) atomicAdd(&ctr->s1_full, (unsigned long long)n_full);
+        if (TAGS && donor_kills) atomicAdd(&ctr->n_s1_donor, (unsigned long long)donor_kills);
+        if (TAGS && tag_kills) atomicAdd(&ctr->n_s1_kill, (unsigned long long)tag_kills);   // n_s1_kill counts every kind
     }
 }
-
 
 }  // namespace ejb

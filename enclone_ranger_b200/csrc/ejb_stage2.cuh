@@ -27,6 +27,8 @@ struct S2Ctx {
     unsigned long long* deadq;        // per packed row: tag of a foreign reference set the row is dead against (read by stage 1)
     const uint32_t* cdr3w;
     const uint4* rowstore;
+    const uint32_t* segpl;       // per canonical segment: reference planes (two-reference candidates slice them, ref_word())
+    const int32_t* seglen;
     const uint64_t* bc_sorted;   // (exact << 32 | barcode), sorted: each exact's barcodes ascending
     const double* powtab;        // mult_pow ^ (cdr3_normal_len * cd / n), indexed pow_off[n] + cd
     const int32_t* pow_off;
@@ -37,7 +39,7 @@ struct S2Ctx {
     uint2* slow;                 // candidates routed to the byte-exact slow path
     uint32_t* slow_slot;
     unsigned long long slow_cap;
-    int tuple_mode;              // 0: filter -> pass edges; 1: write an EdgeTuple per input pair
+    int tuple_mode;              // 0: filter -> pass edges (+ PassTuple); 1: pair-batch mode (ejb_join_one_batch): an EdgeTuple per input pair
     int trace;                   // count the rejections of the integer tests by reason (developer aid, EJB_TRACE)
 };
 
@@ -184,22 +186,35 @@ __device__ __forceinline__ void memo_store(int32_t* memo, uint32_t q, int vsh, i
 // Per-candidate values the owner lane derives once and hands to the group working on it (by shuffle).
 struct CandInfo {
     uint32_t meta;        // W1 | W4h<<3 | W4l<<7 | gap<<11 | fast<<13 | nrefs1<<14 | ch<<16
+    uint32_t q1, q2;      // packed row positions (the group reads region ranges / segment ids from their aux records)
     uint32_t rec1, rec2;  // uint4 index of the two row records in rowstore
     uint32_t cw1, cw2;    // word index of the two rows in plane 0 / word 0 of cdr3w
     uint32_t npad;        // row stride of the CDR3 planes
+    uint32_t L2;          // contig lengths: heavy | light << 16 (both <= 1024 on this path)
     int tot1, tot2;
 };
 __device__ __forceinline__ CandInfo shfl_cand(const CandInfo& c, int src) {
     CandInfo r;
     r.meta = __shfl_sync(0xffffffffu, c.meta, src);
+    r.q1 = __shfl_sync(0xffffffffu, c.q1, src);
+    r.q2 = __shfl_sync(0xffffffffu, c.q2, src);
     r.rec1 = __shfl_sync(0xffffffffu, c.rec1, src);
     r.rec2 = __shfl_sync(0xffffffffu, c.rec2, src);
     r.cw1 = __shfl_sync(0xffffffffu, c.cw1, src);
     r.cw2 = __shfl_sync(0xffffffffu, c.cw2, src);
     r.npad = __shfl_sync(0xffffffffu, c.npad, src);
+    r.L2 = __shfl_sync(0xffffffffu, c.L2, src);
     r.tot1 = __shfl_sync(0xffffffffu, c.tot1, src);
     r.tot2 = __shfl_sync(0xffffffffu, c.tot2, src);
     return r;
+}
+// reference geometries of chain M of the two rows of a two-reference candidate
+template <int M>
+__device__ __forceinline__ void chain_geoms(const S2Ctx& X, uint32_t q1, uint32_t q2, int L, RefGeom& Ga, RefGeom& Gb) {
+    const int32_t* a1 = X.aux + (size_t)q1 * AUX_INTS;
+    const int32_t* a2 = X.aux + (size_t)q2 * AUX_INTS;
+    Ga = ref_geom(X.seglen, a1[M ? AX_VSL : AX_VSH], a1[M ? AX_JSL : AX_JSH], L, X.P.ref_v_trim, X.P.ref_j_trim);
+    Gb = ref_geom(X.seglen, a2[M ? AX_VSL : AX_VSH], a2[M ? AX_JSL : AX_JSH], L, X.P.ref_v_trim, X.P.ref_j_trim);
 }
 
 // Plane math of ONE candidate by a group of G lanes (G = 4 or 8); lane g handles window g (128 positions) of
@@ -207,18 +222,20 @@ __device__ __forceinline__ CandInfo shfl_cand(const CandInfo& c, int src) {
 //   r[0] = cd1 | cd2<<16      CDR3 differences heavy | light
 //   r[1] = A | B<<16          A = popc(d1 & d2), B = popc(d1 & d2 & e); e = bases differ (incl. gaps)
 //   r[2] = diffs | fd<<16     full-length differences | FWR1 differences
-//   r[3] = c1d | c2d<<16      CDR1 | CDR2 differences                       (regions of row 1's planes)
+//   r[3] = c1d | c2d<<16      CDR1 | CDR2 differences                       (regions of row 1, AX_RGN*)
 //   two references only: r[4] = A0|B0, r[5] = O0|T01, r[6] = A1|B1, r[7] = O1|T10
 //     x21 = (t2 != r1) on cmp1, x12 = (t1 != r2) on cmp2;  A0 = popc(d1&x21) ... (join_one.rs:343-429)
+//     r1 / cmp1 = row 1's V / J reference bases and compare mask in contig coordinates, sliced from the segment planes
 // WS = plane stride in uint4 when known at compile time (4), 0 = runtime stride `st`
 template <int WS, int M>
-__device__ __forceinline__ void s2_chain(const uint4* __restrict__ pa, const uint4* __restrict__ pb, int st, bool gapbit, bool nrefs1, uint32_t& pk1,
-                                         uint32_t& pk2, uint32_t& pk3, uint32_t& n0, uint32_t& n1, uint32_t& n2, uint32_t& n3) {
+__device__ __forceinline__ void s2_chain(const S2Ctx& X, uint32_t q1, uint32_t q2, int L, const uint4* __restrict__ pa, const uint4* __restrict__ pb, int st,
+                                         int g, bool gapbit, bool nrefs1, uint32_t& pk1, uint32_t& pk2, uint32_t& pk3, uint32_t& n0, uint32_t& n1,
+                                         uint32_t& n2, uint32_t& n3) {
     const int S = WS ? WS : st;
     uint32_t al[4], ah[4], ad[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bd[4], bg[4] = {0, 0, 0, 0}, e[4];
     ld4(pa + PL_TLO * S, al); ld4(pa + PL_THI * S, ah); ld4(pa + PL_D * S, ad);
     ld4(pb + PL_TLO * S, bl); ld4(pb + PL_THI * S, bh); ld4(pb + PL_D * S, bd);
-    if (gapbit) { ld4(pa + gap_plane(M) * S, ag); ld4(pb + gap_plane(M) * S, bg); }
+    if (gapbit) { ld4(pa + PL_GAP * S, ag); ld4(pb + PL_GAP * S, bg); }
     int A = 0, B = 0, df = 0;
 #pragma unroll
     for (int w = 0; w < 4; w++) {
@@ -230,28 +247,31 @@ __device__ __forceinline__ void s2_chain(const uint4* __restrict__ pa, const uin
     }
     pk1 += (uint32_t)A | ((uint32_t)B << 16);
     pk2 += (uint32_t)df;
-    if (M == 0) {   // region ids of row 1: 1 = FWR1, 2 = CDR1, 3 = CDR2
-        uint32_t gl[4], gh[4];
-        ld4(pa + PL_GLO * S, gl); ld4(pa + PL_GHI * S, gh);
+    if (M == 0) {   // FWR1 / CDR1 / CDR2 of row 1: pairwise disjoint ranges [lo, hi), all empty unless B_REG_OK
+        const int32_t* rgn = X.aux + (size_t)q1 * AUX_INTS + AX_RGN0;
+        const int r0 = rgn[0], r1 = rgn[1], r2 = rgn[2];
         int fd = 0, c1 = 0, c2 = 0;
 #pragma unroll
         for (int w = 0; w < 4; w++) {
-            fd += __popc(e[w] & gl[w] & ~gh[w]);
-            c1 += __popc(e[w] & ~gl[w] & gh[w]);
-            c2 += __popc(e[w] & gl[w] & gh[w]);
+            const int p0 = 32 * (4 * g + w);
+            fd += __popc(e[w] & mask_lt((r0 >> 16) - p0) & ~mask_lt((r0 & 0xffff) - p0));
+            c1 += __popc(e[w] & mask_lt((r1 >> 16) - p0) & ~mask_lt((r1 & 0xffff) - p0));
+            c2 += __popc(e[w] & mask_lt((r2 >> 16) - p0) & ~mask_lt((r2 & 0xffff) - p0));
         }
         pk2 += (uint32_t)fd << 16;
         pk3 += (uint32_t)c1 | ((uint32_t)c2 << 16);
     }
     if (!nrefs1) {
-        uint32_t arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
-        ld4(pa + PL_RLO * S, arl); ld4(pa + PL_RHI * S, arh); ld4(pa + PL_CMP * S, ac);
-        ld4(pb + PL_RLO * S, brl); ld4(pb + PL_RHI * S, brh); ld4(pb + PL_CMP * S, bc);
+        RefGeom Ga, Gb;
+        chain_geoms<M>(X, q1, q2, L, Ga, Gb);
         int A0 = 0, B0 = 0, O0 = 0, T01 = 0, A1 = 0, B1 = 0, O1 = 0, T10 = 0;
 #pragma unroll
         for (int w = 0; w < 4; w++) {
-            const uint32_t x21 = ((bl[w] ^ arl[w]) | (bh[w] ^ arh[w]) | bg[w]) & ac[w];  // t2 != r1 on k1's ranges
-            const uint32_t x12 = ((al[w] ^ brl[w]) | (ah[w] ^ brh[w]) | ag[w]) & bc[w];  // t1 != r2 on k2's ranges
+            uint32_t arl, arh, ac, brl, brh, bc;
+            ref_word(X.segpl, Ga, 4 * g + w, arl, arh, ac);
+            ref_word(X.segpl, Gb, 4 * g + w, brl, brh, bc);
+            const uint32_t x21 = ((bl[w] ^ arl) | (bh[w] ^ arh) | bg[w]) & ac;  // t2 != r1 on k1's ranges
+            const uint32_t x12 = ((al[w] ^ brl) | (ah[w] ^ brh) | ag[w]) & bc;  // t1 != r2 on k2's ranges
             const uint32_t d1 = ad[w], d2 = bd[w];
             A0 += __popc(d1 & x21); B0 += __popc(d1 & x21 & e[w]); O0 += __popc(d1 ^ x21); T01 += __popc(x21);
             A1 += __popc(x12 & d2); B1 += __popc(x12 & d2 & e[w]); O1 += __popc(x12 ^ d2); T10 += __popc(x12);
@@ -265,24 +285,29 @@ __device__ __forceinline__ void s2_chain(const uint4* __restrict__ pa, const uin
 
 // T01 | T10<<16 of one chain window: the two totals the degradation test needs (join_one.rs:434-440)
 template <int WS, int M>
-__device__ __forceinline__ uint32_t s2_chain_degr(const uint4* __restrict__ pa, const uint4* __restrict__ pb, int st, bool gapbit) {
+__device__ __forceinline__ uint32_t s2_chain_degr(const S2Ctx& X, uint32_t q1, uint32_t q2, int L, const uint4* __restrict__ pa, const uint4* __restrict__ pb,
+                                                  int st, int g, bool gapbit) {
     const int S = WS ? WS : st;
-    uint32_t al[4], ah[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bg[4] = {0, 0, 0, 0}, arl[4], arh[4], ac[4], brl[4], brh[4], bc[4];
+    RefGeom Ga, Gb;
+    chain_geoms<M>(X, q1, q2, L, Ga, Gb);
+    uint32_t al[4], ah[4], ag[4] = {0, 0, 0, 0}, bl[4], bh[4], bg[4] = {0, 0, 0, 0};
     ld4(pa + PL_TLO * S, al); ld4(pa + PL_THI * S, ah); ld4(pb + PL_TLO * S, bl); ld4(pb + PL_THI * S, bh);
-    if (gapbit) { ld4(pa + gap_plane(M) * S, ag); ld4(pb + gap_plane(M) * S, bg); }
-    ld4(pa + PL_RLO * S, arl); ld4(pa + PL_RHI * S, arh); ld4(pa + PL_CMP * S, ac);
-    ld4(pb + PL_RLO * S, brl); ld4(pb + PL_RHI * S, brh); ld4(pb + PL_CMP * S, bc);
+    if (gapbit) { ld4(pa + PL_GAP * S, ag); ld4(pb + PL_GAP * S, bg); }
     int T01 = 0, T10 = 0;
 #pragma unroll
     for (int w = 0; w < 4; w++) {
-        T01 += __popc(((bl[w] ^ arl[w]) | (bh[w] ^ arh[w]) | bg[w]) & ac[w]);
-        T10 += __popc(((al[w] ^ brl[w]) | (ah[w] ^ brh[w]) | ag[w]) & bc[w]);
+        uint32_t arl, arh, ac, brl, brh, bc;
+        ref_word(X.segpl, Ga, 4 * g + w, arl, arh, ac);
+        ref_word(X.segpl, Gb, 4 * g + w, brl, brh, bc);
+        T01 += __popc(((bl[w] ^ arl) | (bh[w] ^ arh) | bg[w]) & ac);
+        T10 += __popc(((al[w] ^ brl) | (ah[w] ^ brh) | ag[w]) & bc);
     }
     return (uint32_t)T01 | ((uint32_t)T10 << 16);
 }
 
 template <int G>
 __device__ __forceinline__ void s2_planes(const S2Ctx& X, const CandInfo& ci, int g, unsigned int gmask, uint32_t* r) {
+    const int Lh = (int)(ci.L2 & 0xffff), Ll = (int)(ci.L2 >> 16);
     const int W1 = ci.meta & 7, W4h = (ci.meta >> 3) & 15, W4l = (ci.meta >> 7) & 15, gap = (ci.meta >> 11) & 3, ch = ci.meta >> 16;
     bool active = (ci.meta >> 13) & 1;
     const bool nrefs1 = (ci.meta >> 14) & 1;
@@ -297,8 +322,8 @@ __device__ __forceinline__ void s2_planes(const S2Ctx& X, const CandInfo& ci, in
     // needs T01 = popc(t2 != r1 on cmp1) and T10 = popc(t1 != r2 on cmp2) — evaluate that first and stop early.
     if (active && !nrefs1 && !X.tuple_mode) {
         uint32_t tt = 0;
-        if (g < W4h) tt += s2_chain_degr<WS, 0>(pa0, pb0, W4h, gap & 1);
-        if (g < W4l) tt += s2_chain_degr<WS, 1>(pa1, pb1, W4l, gap & 2);
+        if (g < W4h) tt += s2_chain_degr<WS, 0>(X, ci.q1, ci.q2, Lh, pa0, pb0, W4h, g, gap & 1);
+        if (g < W4l) tt += s2_chain_degr<WS, 1>(X, ci.q1, ci.q2, Ll, pa1, pb1, W4l, g, gap & 2);
 #pragma unroll
         for (int o = 1; o < G; o <<= 1) tt += __shfl_xor_sync(gmask, tt, o);
         const int T01 = (int)(tt & 0xffff), T10 = (int)(tt >> 16);
@@ -320,8 +345,8 @@ __device__ __forceinline__ void s2_planes(const S2Ctx& X, const CandInfo& ci, in
             else hm = (1u << (ch - lo_bit)) - 1u;
             pk0 += (uint32_t)__popc(x & hm) | ((uint32_t)__popc(x & ~hm) << 16);
         }
-        if (g < W4h) s2_chain<WS, 0>(pa0, pb0, W4h, gap & 1, nrefs1, pk1, pk2, pk3, n0, n1, n2, n3);
-        if (g < W4l) s2_chain<WS, 1>(pa1, pb1, W4l, gap & 2, nrefs1, pk1, pk2, pk3, n0, n1, n2, n3);
+        if (g < W4h) s2_chain<WS, 0>(X, ci.q1, ci.q2, Lh, pa0, pb0, W4h, g, gap & 1, nrefs1, pk1, pk2, pk3, n0, n1, n2, n3);
+        if (g < W4l) s2_chain<WS, 1>(X, ci.q1, ci.q2, Ll, pa1, pb1, W4l, g, gap & 2, nrefs1, pk1, pk2, pk3, n0, n1, n2, n3);
     }
 #pragma unroll
     for (int o = 1; o < G; o <<= 1) {
@@ -356,6 +381,7 @@ __global__ void __launch_bounds__(256, S2A_MINB) k_stage2a(S2Ctx X, const uint2*
     constexpr unsigned long long S2A_CHUNK = 2048;
     __shared__ unsigned long long s_chunk;
     __shared__ uint32_t s_res[8][32][9];   // [warp][candidate][8 packed results]; padded row: conflict-free column reads
+    if (X.ctr->overflow) return;   // the round cannot be committed: the host splits it and retries
     const unsigned long long n_cand = min(*n_cand_p, cand_cap);
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
@@ -397,6 +423,9 @@ __global__ void __launch_bounds__(256, S2A_MINB) k_stage2a(S2Ctx X, const uint2*
         CandInfo me;
         me.meta = (uint32_t)sb.W1 | ((uint32_t)sb.W4h << 3) | ((uint32_t)sb.W4l << 7) | ((uint32_t)sb.gap << 11) | ((uint32_t)(fast && !memo_dead) << 13) |
                   ((uint32_t)nrefs1 << 14) | ((uint32_t)sb.ch << 16);
+        me.q1 = q1;
+        me.q2 = q2;
+        me.L2 = (uint32_t)(sb.Lh & 0xffff) | ((uint32_t)(sb.Ll & 0xffff) << 16);
         me.rec1 = (uint32_t)(sb.rs_off + (int64_t)(q1 - sb.q0) * sb.rec_u4);
         me.rec2 = (uint32_t)(sb.rs_off + (int64_t)(q2 - sb.q0) * sb.rec_u4);
         me.cw1 = (uint32_t)(sb.s1_off + (q1 - sb.q0));
@@ -504,6 +533,7 @@ __global__ void __launch_bounds__(256, S2A_MINB) k_stage2a(S2Ctx X, const uint2*
 // Slow path: one warp per candidate, literal byte-level restatement of join_one.rs:216-440
 // ('N' and other odd bytes, overlapping V/J ranges, the V bail-out, over-long contigs).
 __global__ void __launch_bounds__(256) k_stage2_slow(S2Ctx X, const unsigned long long* __restrict__ n_slow_p) {
+    if (X.ctr->overflow) return;
     const unsigned long long n_slow = min(*n_slow_p, X.slow_cap);
     const int lane = threadIdx.x & 31;
     const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -524,11 +554,10 @@ __global__ void __launch_bounds__(256) k_stage2_slow(S2Ctx X, const unsigned lon
         // CDR3 distances on bytes
         int cd1 = 0, cd2 = 0;
         {
-            const uint8_t *a = in.cdr3_bytes + in.row_cdr3_off[2 * k1], *b = in.cdr3_bytes + in.row_cdr3_off[2 * k2];
+            const TigRef a = cdr3_ref(in, k1, 0), b = cdr3_ref(in, k2, 0);
             for (int p = lane; p < sb.ch; p += 32) cd1 += (a[p] != b[p]);
-            a = in.cdr3_bytes + in.row_cdr3_off[2 * k1 + 1];
-            b = in.cdr3_bytes + in.row_cdr3_off[2 * k2 + 1];
-            for (int p = lane; p < sb.cl; p += 32) cd2 += (a[p] != b[p]);
+            const TigRef a2 = cdr3_ref(in, k1, 1), b2 = cdr3_ref(in, k2, 1);
+            for (int p = lane; p < sb.cl; p += 32) cd2 += (a2[p] != b2[p]);
         }
         // full-length differences (join_one.rs:238-260)
         int diffs = 0;
@@ -632,7 +661,8 @@ __device__ __forceinline__ bool bc_meet(const S2Ctx& X, int e1, int e2) {
 #define S2B_MINB 4   // 64 registers: measured 0.25 ms faster per join than the unconstrained 128
 #endif
 __global__ void __launch_bounds__(256, S2B_MINB) k_stage2b(S2Ctx X, const unsigned long long* __restrict__ n_surv_p, unsigned long long* __restrict__ pass_w,
-                                                 unsigned long long pass_cap, EdgeTuple* __restrict__ tuples) {
+                                                 PassTuple* __restrict__ pass_t, unsigned long long pass_cap, EdgeTuple* __restrict__ tuples) {
+    if (X.ctr->overflow) return;
     const unsigned long long n_surv = min(*n_surv_p, X.surv_cap);
     const DevIn& in = X.in;
     const DevParams& P = X.P;
@@ -642,6 +672,7 @@ __global__ void __launch_bounds__(256, S2B_MINB) k_stage2b(S2Ctx X, const unsign
       const unsigned long long si = sbase + lane;
       bool pass_edge = false;
       unsigned long long pass_val = 0;
+      PassTuple pass_tup;
       int pass_sub = -1;
       Survivor s;
       s.q1 = SURV_INVALID;
@@ -781,6 +812,12 @@ __global__ void __launch_bounds__(256, S2B_MINB) k_stage2b(S2Ctx X, const unsign
             pass_edge = true;
             pass_val = ((unsigned long long)(uint32_t)X.rowq[q1] << 28) | (unsigned long long)(uint32_t)X.rowq[q2];
             pass_sub = X.subq[q1];
+            pass_tup.cd12 = (uint32_t)s.cd1 | ((uint32_t)s.cd2 << 16);
+            pass_tup.sh0 = s.sh0;
+            pass_tup.in0 = s.in0;
+            pass_tup.sh1 = (s.nrefs == 2) ? s.sh1 : 0;
+            pass_tup.in1 = (s.nrefs == 2) ? s.in1 : 0;
+            pass_tup.nrefs_err = (uint32_t)s.nrefs | ((uint32_t)s.err << 8);
         }
       }
       // warp-aggregated append: one atomic per warp
@@ -791,7 +828,12 @@ __global__ void __launch_bounds__(256, S2B_MINB) k_stage2b(S2Ctx X, const unsign
           b = __shfl_sync(0xffffffffu, b, 0);
           if (pass_edge) {
               const unsigned long long o = b + __popc(m & ((1u << lane) - 1u));
-              if (o < pass_cap) pass_w[o] = pass_val; else X.ctr->overflow = 1ull;
+              if (o < pass_cap) {
+                  pass_w[o] = pass_val;
+                  pass_t[o] = pass_tup;
+              } else {
+                  X.ctr->overflow = 1ull;
+              }
               // per-sub-bucket pass counter, aggregated over the lanes of the warp that hit the same sub-bucket
               const unsigned int same = __match_any_sync(m, pass_sub);
               if ((same & ((1u << lane) - 1u)) == 0) atomicAdd(&X.sub_pass[pass_sub], (unsigned int)__popc(same));

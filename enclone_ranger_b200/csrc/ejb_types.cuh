@@ -37,7 +37,8 @@ enum AuxField {
     AX_FLAGS = 0, AX_VSH, AX_VSL, AX_JSH, AX_JSL, AX_TOT, AX_EXACT, AX_NCELLS,          // uint4 #0, #1
     AX_DONLO, AX_DONHI, AX_CREFH, AX_CREFL, AX_HCOMP, AX_VREFH, AX_VREFL, AX_BC0,       // uint4 #2, #3
     AX_VNAMEH, AX_VNAMEL, AX_FR1, AX_CDR1, AX_FR2, AX_CDR2, AX_FR3, AX_CHH,             // uint4 #4, #5
-    AX_CHL, AX_PAD1, AX_PAD2, AX_PAD3,                                                  // uint4 #6
+    AX_CHL, AX_RGN0, AX_RGN1, AX_RGN2,                                                  // uint4 #6: FWR1 / CDR1 / CDR2 ranges of chain 0,
+                                                                                        // lo | hi << 16, empty (0) unless B_REG_OK
     AUX_INTS
 };
 static_assert(AUX_INTS == 28, "aux record is 7 uint4");
@@ -82,21 +83,68 @@ struct SubBucket {
     int32_t raw;      // part of a split sub-bucket: its forest edges are returned without the two-cell filter
 };
 constexpr uint8_t ROLE_COLUMN_ONLY = 1, ROLE_SPLIT = 2;
-// Row record layout.  Per chain m the record is PLANE-MAJOR with a fixed plane order; W4 (uint4 per plane) is 4
-// for contigs up to 512 nt and 8 up to 1024 nt, so that the common case has a compile-time plane stride:
+// Row record layout (384 B for contigs up to 512 nt).  Per chain m the record is PLANE-MAJOR with a fixed plane order; W4
+// (uint4 per plane) is 4 for contigs up to 512 nt and 8 up to 1024 nt, so that the common case has a compile-time stride:
 //     chain m, plane pl, window g (128 positions)  ->  uint4 index  off_m + pl * W4_m + g
 //   PL_TLO, PL_THI : 2-bit code of the contig base ((byte >> 1) & 3: A,C,T,G = 0,1,2,3; '-' carries the gap bit)
-//   PL_D           : cmp & (contig base != own reference base)
-//   PL_RLO, PL_RHI : the row's own V / J reference bases in CONTIG coordinates (V from the start, J from the end)
-//   PL_CMP         : positions join_one compares: p < |V|-ref_v_trim  or  p >= L-(|J|-ref_j_trim)
-//   chain 0 only   PL_GLO, PL_GHI: region id of each position: 1 = FWR1 [fr1,cdr1), 2 = CDR1 [cdr1,fr2),
-//                  3 = CDR2 [cdr2,fr3), 0 = elsewhere                       (join_one.rs:766-854)
+//   PL_D           : cmp & (contig base != own reference base), cmp = positions join_one compares
+//                    (p < |V|-ref_v_trim  or  p >= L-(|J|-ref_j_trim), join_one.rs:365-391)
 //   [gap]          : '-' positions, last plane, only when SubBucket.gap has bit m
-enum Plane { PL_TLO = 0, PL_THI = 1, PL_D = 2, PL_RLO = 3, PL_RHI = 4, PL_CMP = 5, PL_GLO = 6, PL_GHI = 7 };
-__host__ __device__ __forceinline__ int rec_planes(int m, int gapbit) { return 6 + (gapbit ? 1 : 0) + (m == 0 ? 2 : 0); }
-__host__ __device__ __forceinline__ int gap_plane(int m) { return m == 0 ? 8 : 6; }
+// What only the rare two-reference candidates need (the OTHER row's V / J reference bases in contig coordinates and its
+// compare mask) is not stored per row: stage 2a slices it out of the per-segment planes (segpl, ref_word() below).  The
+// FWR1 / CDR1 / CDR2 masks of chain 0 are rebuilt from three packed ranges in the aux record (AX_RGN*).
+enum Plane { PL_TLO = 0, PL_THI = 1, PL_D = 2, PL_GAP = 3 };
+__host__ __device__ __forceinline__ int rec_planes(int m, int gapbit) { (void)m; return 3 + (gapbit ? 1 : 0); }
+__host__ __device__ __forceinline__ int gap_plane(int m) { (void)m; return PL_GAP; }
 __device__ __forceinline__ uint32_t base_code(uint32_t byte) { return (byte >> 1) & 3u; }   // A,C,T,G -> 0,1,2,3
 __device__ __forceinline__ bool is_acgt_fast(uint32_t b) { return (b & 0xe0u) == 0x40u && ((0x0010008au >> (b & 31u)) & 1u); }
+
+// Per-segment reference planes (internal base code, 2 planes x SEGPL_WORDS words, position 0 = first base of the
+// segment, zero beyond its end), indexed by the CANONICAL seg id, plus the segment lengths: the bucketer slices / shifts
+// them into contig coordinates instead of touching segment bytes, stage 2a does the same for two-reference candidates.
+constexpr int SEGPL_WORDS = 16;   // segments up to 512 nt (longer ones send their rows to the byte-exact path)
+// bits [0, n) set (n may be <= 0 or >= 32)
+__device__ __forceinline__ uint32_t mask_lt(long long n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << (int)n) - 1u)); }
+// 32 bits of a SEGPL_WORDS-word plane starting at bit index `idx` (bits outside the plane read as 0)
+__device__ __forceinline__ uint32_t plane_bits(const uint32_t* __restrict__ pl, long long idx) {
+    const long long wi = idx >> 5;   // floor
+    const int sh = (int)(idx & 31);
+    const uint32_t a = (wi >= 0 && wi < SEGPL_WORDS) ? pl[wi] : 0u;
+    const uint32_t b = (wi + 1 >= 0 && wi + 1 < SEGPL_WORDS) ? pl[wi + 1] : 0u;
+    return sh ? ((a >> sh) | (b << (32 - sh))) : a;
+}
+// One row-chain's V / J reference in CONTIG coordinates (V from the start, J aligned to the end, join_one.rs:365-391).
+// Only valid for rows without F_PANIC / F_SLOWGEOM: 0 <= vr, 0 <= jr, vr + jr <= L, both segments <= 32 * SEGPL_WORDS.
+struct RefGeom {
+    uint32_t vo, jo;   // word offsets of the V / J lo planes in segpl; the hi planes follow at + SEGPL_WORDS
+    int vr, jr;        // compared lengths: |V| - ref_v_trim, |J| - ref_j_trim
+    int jshift;        // J index of contig position p = p + jshift  (|J| - L)
+    int L;
+};
+__device__ __forceinline__ RefGeom ref_geom(const int32_t* __restrict__ seglen, int sv, int sj, int L, long long ref_v_trim, long long ref_j_trim) {
+    RefGeom G;
+    G.vo = (uint32_t)sv * 2u * SEGPL_WORDS;
+    G.jo = (uint32_t)sj * 2u * SEGPL_WORDS;
+    const long long vlen = seglen[sv], jlen = seglen[sj];
+    G.vr = (int)max(min(vlen - ref_v_trim, 1ll << 30), -(1ll << 30));
+    G.jr = (int)max(min(jlen - ref_j_trim, 1ll << 30), -(1ll << 30));
+    G.jshift = (int)(jlen - L);
+    G.L = L;
+    return G;
+}
+// word wi (positions 32 wi .. 32 wi + 31): reference planes and compare mask
+__device__ __forceinline__ void ref_word(const uint32_t* __restrict__ segpl, const RefGeom& G, int wi, uint32_t& rlo, uint32_t& rhi, uint32_t& cm) {
+    const uint32_t inl = mask_lt((long long)G.L - 32 * wi);
+    const uint32_t cmv = mask_lt((long long)G.vr - 32 * wi) & inl;
+    const uint32_t cmj = inl & ~mask_lt(((long long)G.L - G.jr) - 32 * wi) & ~cmv;   // p >= L - jr; the V range has priority
+    const long long jidx = (long long)32 * wi + G.jshift;
+    const uint32_t* vp = segpl + G.vo;
+    const uint32_t* jp = segpl + G.jo;
+    const uint32_t vlo = wi < SEGPL_WORDS ? vp[wi] : 0u, vhi = wi < SEGPL_WORDS ? vp[SEGPL_WORDS + wi] : 0u;
+    rlo = (vlo & cmv) | (plane_bits(jp, jidx) & cmj);
+    rhi = (vhi & cmv) | (plane_bits(jp + SEGPL_WORDS, jidx) & cmj);
+    cm = cmv | cmj;
+}
 
 // Device view of the raw (uploaded) input, same meaning as ejb_input.
 struct DevIn {
@@ -121,6 +169,9 @@ struct DevIn {
     const int64_t* row_tig2_off;   // optional 2-bit packed contigs (NULL: all ASCII)
     const uint32_t* tig2_words;
     int64_t n_tig2_words;
+    const int64_t* row_cdr32_off;  // optional 2-bit packed CDR3s (NULL: all ASCII)
+    const uint32_t* cdr32_words;
+    int64_t n_cdr32_words;
 };
 
 // Flat join knobs on the device.
@@ -136,24 +187,39 @@ struct Survivor {       // a candidate that passed the integer tests of stage 2
     int32_t sh0, in0, sh1, in1;
     uint8_t nrefs, err, ok, regfast;   // regfast: fd/c1d/c2d below are valid
     uint16_t fd, c1d, c2d, pad;        // FWR1 / CDR1 / CDR2 nucleotide differences (join_one.rs:766-854)
-    uint32_t slot;                     // output slot (tuple mode)
+    uint32_t slot;                     // output slot (pair-batch mode, ejb_join_one_batch)
 };
 
-struct EdgeTuple {      // numeric members of PotentialJoin (defs.rs:870-891)
+struct EdgeTuple {      // numeric members of PotentialJoin (defs.rs:870-891); pair-batch mode output
     int32_t cd, nrefs, sh0, sh1, in0, in1, k, d, n, err, pass, pad;
     double p1, mult, score;
 };
+struct PassTuple {      // what a pass edge keeps of its PotentialJoin: the rest (k, d, n, p1, mult, score) is rebuilt from it
+    uint32_t cd12;      // cd heavy | cd light << 16
+    int32_t sh0, in0, sh1, in1;
+    uint32_t nrefs_err; // nrefs | err << 8
+};
 
 struct Counters {       // device-side counters, one instance per context
-    unsigned long long n_cand, n_slow, n_surv, n_pass, n_newkeys, pairs_eval, n_forest, n_alive;
-    unsigned long long n_two_cell, n_errflag_range, n_errflag_panic, overflow, n_slow_total, n_surv_total, n_pass_total;
-    unsigned long long p1_unique, s2_work;
+    // ---- zeroed at the start of every scheduler round (one memset over [n_cand, round_end)) ----
+    unsigned long long n_cand, n_slow, n_surv, n_pass, n_newkeys, overflow, n_surv_total, s2_work;
+    unsigned long long any_cut;       // a unit of this round was truncated after stage 1 (k_truncate)
+    unsigned long long alive_it[64];  // Boruvka: edges still joining two components, per iteration of this round
+    unsigned long long round_end;     // marker only
+    // ---- per run ----
+    unsigned long long pairs_eval, n_forest;
+    unsigned long long n_two_cell, n_errflag_range, n_errflag_panic, n_final;
+    unsigned long long p1_total;      // keys ever inserted into the p1 cache since it was last cleared
+    unsigned long long p1_full;       // a probe sequence of the p1 cache ran through the whole table (must not happen: the host grows it)
+    unsigned long long s1_first;      // stage 1: lane-pairs whose first CDR3 word went through XOR + popc
+    unsigned long long s1_full;       // stage 1: lane-pairs whose remaining CDR3 words were evaluated too
+    unsigned long long bor_iters;     // Boruvka iterations over all rounds
     unsigned long long n_s1_kill;     // stage-1 hits dropped: known dead against the other's reference set, or different donor sets
     unsigned long long n_s1_donor;    // ... of which for the donor sets
-    unsigned long long n_two_ref;     // stage-2a candidates with two reference sets (filter mode)
+    unsigned long long n_two_ref;     // stage-2a candidates with two reference sets
     unsigned long long n_memo_dead;   // ... of which rejected on memoised totals (phase 0)
     unsigned long long n_degr_dead;   // ... of which rejected by the degradation test on freshly computed totals
-    unsigned long long n_rej[8];      // filter-mode rejections of the integer tests by first failing test (EJB_TRACE): 0 CDR3 identity,
+    unsigned long long n_rej[8];      // rejections of the integer tests by first failing test (trace): 0 CDR3 identity,
                                       // 1 max_diffs, 2 max_cdr3_diffs, 3 donors, 4 cd >= cdr3_mult * indeps, 5 constant regions, 6 k range
 };
 
@@ -200,6 +266,16 @@ __device__ __forceinline__ TigRef tig_ref(const DevIn& in, int64_t k, int m) {
     const int64_t o2 = in.row_tig2_off ? in.row_tig2_off[2 * k + m] : -1;
     if (o2 >= 0) r.w = in.tig2_words + o2;
     else r.b = in.tig_bytes + in.row_tig_off[2 * k + m];
+    return r;
+}
+
+__device__ __forceinline__ TigRef cdr3_ref(const DevIn& in, int64_t k, int m) {   // info[k].cdr3s[m], ASCII or 2-bit packed
+    TigRef r;
+    r.b = nullptr;
+    r.w = nullptr;
+    const int64_t o2 = in.row_cdr32_off ? in.row_cdr32_off[2 * k + m] : -1;
+    if (o2 >= 0) r.w = in.cdr32_words + o2;
+    else r.b = in.cdr3_bytes + in.row_cdr3_off[2 * k + m];
     return r;
 }
 

@@ -882,4 +882,47 @@ extern "C" int ejb_synth_pack_contigs(const ejb_input* in, int64_t* row_tig2_off
     *words_out = words; *n_words_out = nw; *bytes_out = bytes; *n_bytes_out = nb;
     return EJB_OK;
 }
+// Same for the CDR3s (info[k].cdr3s[m] -> 2-bit words, ejb_input.row_cdr32_off / cdr32_words): a CDR3 with a byte outside
+// upper-case ACGT stays ASCII (offset -1 in row_cdr32_off, its bytes are re-packed into bytes_out).
+extern "C" int ejb_synth_pack_cdr3s(const ejb_input* in, int64_t* row_cdr32_off /* [2*n_rows] out */, int64_t* new_cdr3_off /* [2*n_rows] out */,
+                                    uint32_t** words_out, int64_t* n_words_out, uint8_t** bytes_out, int64_t* n_bytes_out) {
+    const int64_t n2 = 2 * in->n_rows;
+    int8_t lut[256];
+    for (int i = 0; i < 256; i++) lut[i] = -1;
+    lut[(int)'A'] = 0; lut[(int)'C'] = 1; lut[(int)'G'] = 2; lut[(int)'T'] = 3;
+    std::vector<char> elig((size_t)n2, 0);
+    int64_t nw = 0, nb = 0;
+    for (int64_t i = 0; i < n2; i++) {
+        row_cdr32_off[i] = -1;
+        new_cdr3_off[i] = -1;
+        if ((i & 1) >= in->row_nchains[i >> 1]) continue;
+        const int64_t L = in->row_cdr3_len[i];
+        const uint8_t* t = in->cdr3_bytes + in->row_cdr3_off[i];
+        bool ok = true;
+        for (int64_t p = 0; ok && p < L; p++) ok = lut[t[p]] >= 0;
+        elig[(size_t)i] = ok;
+        if (ok) { row_cdr32_off[i] = nw; nw += (L + 15) / 16; } else { new_cdr3_off[i] = nb; nb += L; }
+    }
+    uint32_t* words = (uint32_t*)malloc(std::max<int64_t>(nw, 1) * 4);
+    uint8_t* bytes = (uint8_t*)malloc(std::max<int64_t>(nb, 1));
+    if (!words || !bytes) { free(words); free(bytes); return EJB_ERR_OOM; }
+    for (int64_t i = 0; i < n2; i++) {
+        if ((i & 1) >= in->row_nchains[i >> 1]) continue;
+        const int64_t L = in->row_cdr3_len[i];
+        const uint8_t* t = in->cdr3_bytes + in->row_cdr3_off[i];
+        if (elig[(size_t)i]) {
+            uint32_t* w = words + row_cdr32_off[i];
+            for (int64_t q = 0; q < (L + 15) / 16; q++) {
+                uint32_t v = 0;
+                const int64_t m = std::min<int64_t>(16, L - 16 * q);
+                for (int64_t j = 0; j < m; j++) v |= (uint32_t)lut[t[16 * q + j]] << (2 * j);
+                w[q] = v;
+            }
+        } else if (L > 0) {
+            memcpy(bytes + new_cdr3_off[i], t, (size_t)L);
+        }
+    }
+    *words_out = words; *n_words_out = nw; *bytes_out = bytes; *n_bytes_out = nb;
+    return EJB_OK;
+}
 extern "C" void ejb_synth_free_array(void* p) { free(p); }

@@ -23,8 +23,9 @@ _FIELDS = {
     "cell_donor": np.int32, "cell_barcode": np.uint32,
     "seg_off": np.int64, "seg_bytes": np.uint8, "ref_off": np.int64, "ref_bytes": np.uint8,
     "ref_name_id": np.int32,
-    # optional 2-bit packed contigs
+    # optional 2-bit packed contigs / CDR3s
     "row_tig2_off": np.int64, "tig2_words": np.uint32,
+    "row_cdr32_off": np.int64, "cdr32_words": np.uint32,
 }
 
 
@@ -62,6 +63,9 @@ class JoinInput:
         c.n_tig2_words = int(a["tig2_words"].size)
         if a["row_tig2_off"].size == 0:
             c.row_tig2_off = None          # NULL: every contig is ASCII
+        c.n_cdr32_words = int(a["cdr32_words"].size)
+        if a["row_cdr32_off"].size == 0:
+            c.row_cdr32_off = None         # NULL: every CDR3 is ASCII
         c.n_tig_bytes = int(a["tig_bytes"].size)
         c.n_cdr3_bytes = int(a["cdr3_bytes"].size)
         c.n_amino_bytes = int(a["amino_bytes"].size)
@@ -89,6 +93,7 @@ class JoinInput:
             "ch_amino_len": CH, "amino_bytes": cin.n_amino_bytes, "cell_donor": X, "cell_barcode": X,
             "seg_off": S + 1, "seg_bytes": 0, "ref_off": R + 1, "ref_bytes": 0, "ref_name_id": R,
             "row_tig2_off": 2 * N if cin.row_tig2_off else 0, "tig2_words": cin.n_tig2_words,
+            "row_cdr32_off": 2 * N if cin.row_cdr32_off else 0, "cdr32_words": cin.n_cdr32_words if cin.row_cdr32_off else 0,
         }
         out = {}
         for name, dt in _FIELDS.items():
@@ -107,12 +112,13 @@ class JoinInput:
         for n in ("row_nchains", "row_exact"):
             b[n] = self.a[n][idx]
         for n in ("row_len", "row_tig_off", "row_has_del", "row_vs", "row_js", "row_cdr3_off",
-                  "row_cdr3_len", "row_exact_col"):
-            b[n] = self.a[n][two]
+                  "row_cdr3_len", "row_exact_col", "row_tig2_off", "row_cdr32_off"):
+            if self.a[n].size:
+                b[n] = self.a[n][two]
         return JoinInput(**b)
 
     def subset_rows(self, idx):
-        assert self.a["row_tig2_off"].size == 0, "subset the ASCII form, then call to_packed()"
+        assert self.a["row_tig2_off"].size == 0 and self.a["row_cdr32_off"].size == 0, "subset the ASCII form, then call to_packed()"
         """Rows `idx` (ascending) with the exact / chain / cell tables compacted to what those rows reference.
         Seg and ref tables are kept whole (they are small).  Returns (JoinInput, old exact id of each new exact)."""
         idx = np.asarray(idx, dtype=np.int64)
@@ -240,6 +246,34 @@ class JoinInput:
         b["row_tig_off"] = to
         b["tig2_words"] = np.ctypeslib.as_array(words, shape=(max(nbw.value, 1),))[: nbw.value].copy()
         b["tig_bytes"] = np.ctypeslib.as_array(byts, shape=(max(nbb.value, 1),))[: nbb.value].copy()
+        lib.ejb_synth_free_array(words)
+        lib.ejb_synth_free_array(byts)
+        return JoinInput(**b)
+
+    def to_packed_cdr3(self):
+        """The same input with every pure-ACGT CDR3 supplied 2-bit packed (ejb_input.row_cdr32_off / cdr32_words): the ASCII
+        cdr3_bytes shrink to the (normally zero) CDR3s that hold another byte."""
+        if self.a["row_cdr32_off"].size or self.n_rows == 0:
+            return self
+        lib = load_synth()
+        n2 = 2 * self.n_rows
+        c2 = np.zeros(n2, dtype=np.int64)
+        co = np.zeros(n2, dtype=np.int64)
+        words, nbw = C.POINTER(C.c_uint32)(), C.c_int64()
+        byts, nbb = C.POINTER(C.c_uint8)(), C.c_int64()
+        lib.ejb_synth_pack_cdr3s.argtypes = [C.POINTER(EjbInput), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.POINTER(C.c_uint32)),
+                                             C.POINTER(C.c_int64), C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_int64)]
+        lib.ejb_synth_pack_cdr3s.restype = C.c_int
+        lib.ejb_synth_free_array.argtypes = [C.c_void_p]
+        rc = lib.ejb_synth_pack_cdr3s(self.c_ptr(), c2.ctypes.data_as(C.POINTER(C.c_int64)), co.ctypes.data_as(C.POINTER(C.c_int64)),
+                                      C.byref(words), C.byref(nbw), C.byref(byts), C.byref(nbb))
+        if rc != 0:
+            raise RuntimeError("ejb_synth_pack_cdr3s failed")
+        b = dict(self.a)
+        b["row_cdr32_off"] = c2
+        b["row_cdr3_off"] = co
+        b["cdr32_words"] = np.ctypeslib.as_array(words, shape=(max(nbw.value, 1),))[: nbw.value].copy()
+        b["cdr3_bytes"] = np.ctypeslib.as_array(byts, shape=(max(nbb.value, 1),))[: nbb.value].copy()
         lib.ejb_synth_free_array(words)
         lib.ejb_synth_free_array(byts)
         return JoinInput(**b)

@@ -110,14 +110,17 @@ def _c_input(inp):
 
 
 class JoinContext:
-    """Owns one ejb_ctx (one GPU).  `rank`/`world` shard buckets across processes (one per GPU)."""
+    """Owns one ejb_ctx.  `device` is one GPU index or a list of them (ejb_create with n_devices > 1: the library shards the
+    buckets over the GPUs itself).  `rank`/`world` shard buckets across processes (one per GPU)."""
 
     def __init__(self, device=0, rank=0, world=1, cand_cap=0, pair_budget=0):
         self.L = _abi.load_join()
-        self.device = int(device)
+        devices = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+        self.devices = devices
+        self.device = devices[0]
         self.h = C.c_void_p()
-        dev = (C.c_int * 1)(int(device))
-        rc = self.L.ejb_create(C.byref(self.h), dev, 1)
+        dev = (C.c_int * len(devices))(*devices)
+        rc = self.L.ejb_create(C.byref(self.h), dev, len(devices))
         if rc != 0:
             raise JoinError(rc, "ejb_create failed (no CUDA device? there is no CPU fallback)")
         self.L.ejb_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -141,6 +144,20 @@ class JoinContext:
             self.close()
         except Exception:
             pass
+
+    def set_option(self, name, value):
+        """Developer / test knob (ejb_set_option): "first_unit", "growth", "s1_mode", "no_tags", "trace"."""
+        self._ck(self.L.ejb_set_option(self.h, name.encode(), int(value)))
+
+    def create_ms(self):
+        """Milliseconds ejb_create took (the Stirling ratio table is built on the device there)."""
+        return float(self.L.ejb_create_ms(self.h))
+
+    def sr_table_read(self, first, count):
+        """(hi, lo) pairs of entries [first, first+count) of the device-built Stirling ratio table (triangular layout)."""
+        out = np.zeros(2 * int(count), dtype=np.float64)
+        self._ck(self.L.ejb_sr_table_read(self.h, int(first), int(count), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out.reshape(-1, 2)
 
     # --- the drop-in call ---
     def join(self, params, inp, copy=True):

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define EJB_ABI_VERSION 3
+#define EJB_ABI_VERSION 4
 #define EJB_NONE (-1)
 
 typedef enum ejb_status {
@@ -173,6 +173,14 @@ typedef struct ejb_input {
     const int64_t* row_tig2_off;  /* [2*n_rows] or NULL                                           */
     const uint32_t* tig2_words;
     int64_t n_tig2_words;
+
+    /* ---- optional: 2-bit packed CDR3s (same packing as tig2_words; info[k].cdr3s[m] is a substring of the contig,
+     * so a caller that holds tigsp can cut it out without touching ASCII) ----
+     * row_cdr32_off[2*k+m] >= 0 is the index of the first word of that CDR3 in cdr32_words; row_cdr3_off / cdr3_bytes are
+     * then ignored for it (cdr3_bytes may be NULL when every CDR3 is packed).  Pure upper-case ACGT only.          */
+    const int64_t* row_cdr32_off; /* [2*n_rows] or NULL                                           */
+    const uint32_t* cdr32_words;
+    int64_t n_cdr32_words;
 } ejb_input;
 
 /* Counters and timings of one join (all optional diagnostics). */
@@ -181,7 +189,9 @@ typedef struct ejb_stats {
     int64_t n_subbuckets;       /* 2-chain buckets split by CDR3 lengths                          */
     int64_t pairs_lens;         /* sum over 2-chain buckets of n(n-1)/2                           */
     int64_t pairs_scored;       /* sum over sub-buckets of n(n-1)/2  (the BASELINE metric's unit) */
-    int64_t pairs_evaluated;    /* pairs whose CDR3 distance was actually computed on the device  */
+    int64_t pairs_evaluated;    /* pairs of the tiles stage 1 staged (pairs_scored minus whole 128 x 128 tiles skipped
+                                   because both row blocks already carry ONE class label); NOT all of them had their
+                                   distance computed: see pairs_distance_computed                 */
     int64_t stage1_candidates;  /* pairs passing the CDR3 pre-filter and not already connected    */
     int64_t stage2_slow;        /* candidates scored by the byte-exact slow path                  */
     int64_t stage2_survivors;   /* candidates passing the integer tests (reach the score)         */
@@ -207,6 +217,18 @@ typedef struct ejb_stats {
     int64_t stage2_memo_dead;   /* ... rejected on memoised totals                                */
     int64_t stage2_degr_dead;   /* ... rejected by the degradation test on computed totals        */
     int64_t stage1_donor_kills; /* CDR3-close pairs dropped in stage 1: different donor sets (join_one.rs:301-323) */
+    /* executed work of stage 1 (what the popc pipe really ran, lane granular) */
+    int64_t pairs_distance_computed; /* lane-pairs whose FIRST 32 CDR3 positions went through XOR + popc (16 x 16 groups that
+                                        carry one class label are skipped before that)                          */
+    int64_t pairs_distance_full;     /* ... of which the remaining CDR3 words were evaluated too (some lane of the warp was
+                                        still within max distance after the first word)                         */
+    int64_t popc_executed_stage1;    /* 32-bit popc lane-operations stage 1 executed                              */
+    int64_t host_syncs;         /* stream synchronisations of this ejb_run                                      */
+    int64_t boruvka_iterations; /* forest iterations over all rounds (device-side loop, no read-back)           */
+    int64_t p1_cache_slots;     /* current size of the device p1 hash                                           */
+    int64_t n_devices;          /* GPUs that took part in this join                                             */
+    double ms_partition;        /* multi-GPU: host partitioning of the buckets                                  */
+    double ms_merge;            /* multi-GPU: gather + merge of the per-device forests                          */
 } ejb_stats;
 
 /*
@@ -247,8 +269,16 @@ typedef struct ejb_ctx ejb_ctx;
 
 /* Create a context bound to the given CUDA devices (n_devices >= 1; device_ids == NULL means
  * devices 0..n_devices-1).  Builds the double-double Stirling ratio table (start.rs:50-99)
- * once and uploads it.  Fails with EJB_ERR_NO_DEVICE when CUDA is unavailable.              */
+ * on the device, once per device.  Fails with EJB_ERR_NO_DEVICE when CUDA is unavailable.
+ * With n_devices > 1 ejb_join shards the lens buckets over the devices (one worker thread and stream per GPU, no
+ * collective on the data path), gathers the per-device forests and merges them; the caller sees one result.      */
 int ejb_create(ejb_ctx** out, const int* device_ids, int n_devices);
+/* Developer / test knobs (none is needed in production).  Names: "first_unit", "growth" (unit schedule), "s1_mode"
+ * (bit 0 uniform-label vote, bit 1 tags), "no_tags", "trace".  The EJB_* environment variables of the same meaning are
+ * read ONCE, in ejb_create; this call overrides them for the following joins.  Unknown name: EJB_ERR_INVALID.     */
+int ejb_set_option(ejb_ctx* ctx, const char* name, long long value);
+/* Milliseconds ejb_create spent building + uploading the Stirling ratio table (device build: start.rs:50-99).   */
+double ejb_create_ms(const ejb_ctx* ctx);
 void ejb_destroy(ejb_ctx* ctx);
 const char* ejb_last_error(const ejb_ctx* ctx);
 
@@ -271,6 +301,10 @@ int ejb_last_stats(const ejb_ctx* ctx, ejb_stats* out);
  * evaluated by the library's device kernel for `count` triples (for parity tests).           */
 int ejb_p1_batch(ejb_ctx* ctx, const int32_t* k, const int32_t* d, const int32_t* n,
                  int64_t count, double* p1_out);
+
+/* Entries [first, first + count) of the device-built Stirling ratio table (start.rs:50-99) in its triangular layout (row n
+ * at n(n+1)/2, n <= 3000), as (hi, lo) pairs of the double-double values — for bit-level parity tests of the device build. */
+int ejb_sr_table_read(ejb_ctx* ctx, int64_t first, int64_t count, double* hi_lo_out);
 
 /* Measured integer-pipe peaks of device 0 (dependency-free __popc / LOP3 microbenchmarks),
  * in 32-bit lane-operations per second; used as the roofline denominator (SURVEY §8 d).     */

@@ -31,7 +31,7 @@ def test_struct_sizes_match_the_library():
     out = (C.c_int64 * 4)()
     L.ejb_abi_sizes(out)
     assert list(out) == [C.sizeof(_abi.EjbParams), C.sizeof(_abi.EjbInput), C.sizeof(_abi.EjbStats), C.sizeof(_abi.EjbResult)]
-    assert L.ejb_abi_version() == 3
+    assert L.ejb_abi_version() == 4
 
 
 def test_default_params_match_proc_args():

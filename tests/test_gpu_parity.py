@@ -228,12 +228,11 @@ def test_randomized_differential(gpu_ctx, block):
 
 
 def _join_without_tags(ctx, p, inp):
-    import os
-    os.environ["EJB_NO_TAGS"] = "1"
+    ctx.set_option("no_tags", 1)
     try:
         return ctx.join(p, inp)
     finally:
-        del os.environ["EJB_NO_TAGS"]
+        ctx.set_option("no_tags", 0)
 
 
 def test_reference_set_tags_do_not_change_the_result(gpu_ctx):
@@ -347,3 +346,54 @@ def test_input_arena_single_copy_upload(gpu_ctx):
     for f in ("edge_k1", "edge_k2", "edge_cd", "edge_shares", "edge_indeps", "edge_score", "labels", "eq_x", "eq_y", "eq_z"):
         assert np.array_equal(getattr(got, f), getattr(want, f)), f
         assert np.array_equal(getattr(again, f), getattr(want, f)), f
+
+
+def test_stirling_table_built_on_device_is_bit_exact(gpu_ctx):
+    """f3: stirling2_ratio_table_double (start.rs:50-99) is built by k_sr_table on the device; every entry must carry the bits
+    of the oracle's host build (same double-double operation sequence): whole rows incl. the reference's KAT rows 219 / 722,
+    the last rows, and a seeded sample over the triangle."""
+    assert gpu_ctx.create_ms() > 0.0
+    rows = list(range(0, 40)) + [219, 722, 1500, 2047, 2048, 2049, 2999, 3000]
+    for n in rows:
+        got = gpu_ctx.sr_table_read(n * (n + 1) // 2, n + 1)
+        want = np.array([pyoracle.sr_entry(n, k) for k in range(n + 1)])
+        assert np.array_equal(got, want), f"row {n}"
+    rng = np.random.default_rng(5)
+    for _ in range(3000):
+        n = int(rng.integers(1, 3001))
+        k = int(rng.integers(0, n + 1))
+        got = gpu_ctx.sr_table_read(n * (n + 1) // 2 + k, 1)[0]
+        assert tuple(got) == pyoracle.sr_entry(n, k), (n, k)
+
+
+@pytest.mark.parametrize("config,cells", [(0, 20000), (1, 40000), (2, 100000), (3, 20000)])
+def test_packed_cdr3s(gpu_ctx, config, cells):
+    """f1 intake: CDR3s supplied 2-bit packed (row_cdr32_off / cdr32_words) next to 2-bit contigs; no ASCII CDR3 byte is
+    uploaded and the result is the oracle's."""
+    rep = E.generate(config, n_cells=cells, seed=91)
+    p = E.default_params(bool(rep.config.is_bcr))
+    inp = rep.to_join_input()
+    pk = inp.to_packed().to_packed_cdr3()
+    assert pk.a["cdr3_bytes"].size == 0 and pk.a["cdr32_words"].size > 0
+    want = pyoracle.run(p, inp.c_ptr(), threads=0)
+    got = gpu_ctx.join(p, pk)
+    assert_same_result(got, want, f"config {config} packed CDR3s")
+    assert got.stats["h2d_bytes"] < gpu_ctx.join(p, inp.to_packed()).stats["h2d_bytes"]
+
+
+def test_packed_cdr3s_micro_cases(gpu_ctx):
+    for name, params, inp, expected in CASES:
+        want = pyoracle.run(params, inp.c_ptr(), threads=1)
+        assert_same_result(gpu_ctx.join(params, inp.to_packed().to_packed_cdr3()), want, name + " (packed CDR3)")
+
+
+def test_sync_and_launch_accounting(gpu_ctx):
+    """One read-back for the prepare phase, one per scheduler round, one at the end; Boruvka converges on the device."""
+    rep = E.generate(1, n_cells=60000, seed=3)
+    p = E.default_params(True)
+    gpu_ctx.upload(p, rep.to_join_input().to_packed())
+    st = gpu_ctx.run()
+    assert st["host_syncs"] == st["rounds"] + st["overflow_retries"] + 2, st
+    assert st["boruvka_iterations"] >= st["rounds"] - 1
+    assert 0 < st["pairs_distance_computed"] <= st["pairs_evaluated"] * 1.2
+    assert st["pairs_distance_full"] <= st["pairs_distance_computed"]
