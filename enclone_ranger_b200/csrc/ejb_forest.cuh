@@ -100,17 +100,35 @@ __global__ void __launch_bounds__(256) k_forest_round(ForestArgs A) {
         // newer iterations carry smaller tags, so their minima override the stale ones without a reset
         const unsigned long long tag = (unsigned long long)(63 - iter) << BOR_TAG_SHIFT;
         unsigned long long alive = 0;
-        for (unsigned long long i = tid0; i < n; i += nthr) {
-            const unsigned long long e = A.pass_w[i];
-            const int a = (int)(e >> 28), b = (int)(e & 0xfffffffull);
-            const int ra = uf_find_ro(A.parent, a), rb = uf_find_ro(A.parent, b);
-            // pointer jumping: no hook runs concurrently with this phase, a root is a valid parent
-            if (A.parent[a] != ra) A.parent[a] = ra;
-            if (A.parent[b] != rb) A.parent[b] = rb;
-            A.roots[i] = make_int2(ra, rb);
-            if (ra != rb) {
-                atomicMin(&A.best[ra], tag | e);
-                atomicMin(&A.best[rb], tag | e);
+        for (unsigned long long i0 = tid0 - (threadIdx.x & 31); i0 < n; i0 += nthr) {   // warp-uniform trip count
+            const unsigned long long i = i0 + (threadIdx.x & 31);
+            int ra = -1, rb = -1;
+            unsigned long long e = 0;
+            if (i < n) {
+                e = A.pass_w[i];
+                const int a = (int)(e >> 28), b = (int)(e & 0xfffffffull);
+                ra = uf_find_ro(A.parent, a);
+                rb = uf_find_ro(A.parent, b);
+                // pointer jumping: no hook runs concurrently with this phase, a root is a valid parent
+                if (A.parent[a] != ra) A.parent[a] = ra;
+                if (A.parent[b] != rb) A.parent[b] = rb;
+                A.roots[i] = make_int2(ra, rb);
+            }
+            const bool live = i < n && ra != rb;
+            const unsigned int lm = __ballot_sync(0xffffffffu, live);
+            if (live) {
+                // Consecutive pass edges mostly share a root (one clone): the lanes that update the same root reduce their
+                // minimum first, so that a root costs one atomic per warp instead of up to 32 serialized ones.
+                const unsigned long long v = tag | e;
+                const int lane = threadIdx.x & 31;
+#pragma unroll
+                for (int side = 0; side < 2; side++) {
+                    const int root = side ? rb : ra;
+                    const unsigned int g = __match_any_sync(lm, root);
+                    const unsigned int hi = __reduce_min_sync(g, (unsigned int)(v >> 32));
+                    const unsigned int lo = __reduce_min_sync(g, (unsigned int)(v >> 32) == hi ? (unsigned int)v : 0xffffffffu);
+                    if (lane == __ffs(g) - 1) atomicMin(&A.best[root], ((unsigned long long)hi << 32) | lo);
+                }
                 alive++;
             }
         }
@@ -186,32 +204,60 @@ struct UnitOut {
 __global__ void k_truncate(const UnitDesc* __restrict__ units, int n_units, const RowTask* __restrict__ tasks, const unsigned long long* __restrict__ unit_cand,
                            const SubBucket* __restrict__ subs, int32_t* __restrict__ qcut, unsigned int* __restrict__ sub_pass, UnitOut* __restrict__ out,
                            Counters* __restrict__ ctr) {
-    const int ui = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per unit: the tasks are scanned 32 at a time (prefix sums by shuffles) instead of one dependent load after another
+    const int lane = threadIdx.x & 31;
+    const int ui = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (ui >= n_units) return;
     const UnitDesc u = units[ui];
-    double cand = 0.0, after_jump = 0.0;
+    double carry_cand = 0.0, carry_aj = 0.0, cand_out = 0.0;
     bool jumped = false;
     int r1 = u.r1, cut = 0;
-    for (int t = u.t0; t < u.t0 + u.nt; t++) {
-        const RowTask rt = tasks[t];
-        const int tr0 = rt.rb * TILE + rt.row_lo, tr1 = rt.rb * TILE + rt.row_hi;
-        const double cnt = (double)unit_cand[rt.tid];
-        if (!jumped && (u.rho_ref < 0.0 || cnt / (double)max(1, tr1 - tr0) > 8.0 * u.rho_ref + 16.0)) jumped = true;
-        cand += cnt;
-        if (jumped) after_jump += cnt;
-        if ((cand > u.allow || (jumped && after_jump > u.strict)) && tr1 < u.r1) {
-            r1 = tr1;
+    for (int base = 0; base < u.nt && !cut; base += 32) {
+        const int t = base + lane;
+        const bool valid = t < u.nt;
+        double cnt = 0.0;
+        int tr0 = 0, tr1 = 0;
+        if (valid) {
+            const RowTask rt = tasks[u.t0 + t];
+            tr0 = rt.rb * TILE + rt.row_lo;
+            tr1 = rt.rb * TILE + rt.row_hi;
+            cnt = (double)unit_cand[rt.tid];
+        }
+        const bool dj = valid && (u.rho_ref < 0.0 || cnt / (double)max(1, tr1 - tr0) > 8.0 * u.rho_ref + 16.0);
+        const unsigned int jm = __ballot_sync(0xffffffffu, dj);
+        const int J = jumped ? 0 : (jm ? __ffs(jm) - 1 : 32);   // first lane of this chunk that counts towards the strict allowance
+        double incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const double excl_at_J = (J < 32) ? __shfl_sync(0xffffffffu, incl - cnt, J & 31) : 0.0;
+        const double aj = carry_aj + (lane >= J ? incl - excl_at_J : 0.0);
+        const double cum = carry_cand + incl;
+        const bool cross = valid && (cum > u.allow || (lane >= J && aj > u.strict)) && tr1 < u.r1;
+        const unsigned int cm = __ballot_sync(0xffffffffu, cross);
+        if (cm) {
+            const int L = __ffs(cm) - 1;
+            r1 = __shfl_sync(0xffffffffu, tr1, L);
+            cand_out = __shfl_sync(0xffffffffu, cum, L);
             cut = 1;
-            break;
+        } else {
+            carry_cand = __shfl_sync(0xffffffffu, cum, 31);
+            carry_aj = __shfl_sync(0xffffffffu, aj, 31);
+            if (J < 32) jumped = true;
+            cand_out = carry_cand;
         }
     }
-    qcut[u.sub] = cut ? (int32_t)(subs[u.sub].q0 + r1) : 0x7fffffff;
-    sub_pass[u.sub] = 0u;
-    out[ui].r1 = r1;
-    out[ui].cut = cut;
-    out[ui].cand = cand;
-    out[ui].pass = 0u;
-    if (cut) ctr->any_cut = 1ull;
+    if (lane == 0) {
+        qcut[u.sub] = cut ? (int32_t)(subs[u.sub].q0 + r1) : 0x7fffffff;
+        sub_pass[u.sub] = 0u;
+        out[ui].r1 = r1;
+        out[ui].cut = cut;
+        out[ui].cand = cand_out;
+        out[ui].pass = 0u;
+        if (cut) ctr->any_cut = 1ull;
+    }
 }
 __global__ void k_round_report(const UnitDesc* __restrict__ units, int n_units, const unsigned int* __restrict__ sub_pass, UnitOut* __restrict__ out) {
     const int ui = blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,9 +289,23 @@ __global__ void k_fill_u64(unsigned long long* p, int64_t n, unsigned long long 
 // ------------------------------------------------------------------------------------------------
 // Finalize (every count stays on the device: no host read-back until the results are downloaded)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_q_of_row(const int32_t* __restrict__ rowq, int64_t n_pos, int32_t* __restrict__ q_of_row) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < n_pos && rowq[q] >= 0) q_of_row[rowq[q]] = (int32_t)q;
+// merge of partial forests (multi-GPU): every edge's p1 key is requested on the merging context (its cache only knows the keys
+// of its own part; k_p1 then evaluates the missing ones)
+__global__ void k_p1_request_forest(const unsigned long long* __restrict__ forest, const PassTuple* __restrict__ tuples, const unsigned long long* __restrict__ n_p,
+                                    DevIn in, P1Cache p1c, Counters* ctr) {
+    const unsigned long long n = *n_p;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const int64_t k1 = (int64_t)(forest[i] >> 28);
+        const PassTuple t = tuples[i];
+        const int nrefs = (int)(t.nrefs_err & 0xff);
+        const int min_sh = (nrefs == 2) ? min(t.sh0, t.sh1) : t.sh0;
+        const int min_in = (nrefs == 2) ? min(t.in0, t.in1) : t.in0;
+        p1_request(p1c, 3 * (in.row_len[2 * k1] + in.row_len[2 * k1 + 1]), min_in + 2 * min_sh, min_sh, ctr);
+    }
+}
+__global__ void k_init_parent(int32_t* __restrict__ parent, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) parent[i] = (int32_t)i;
 }
 // forest degree of every row (two-cell filter)
 __global__ void k_forest_deg(const unsigned long long* __restrict__ forest, const unsigned long long* __restrict__ n_p, int32_t* __restrict__ deg) {
@@ -319,22 +379,23 @@ struct FinalOut {
 // edges in raw_joins order + the PotentialJoin members rebuilt from the kept PassTuple (join_one.rs:444-447, 499-544: same
 // formulas, tables and p1 cache as stage 2b, which accepted the edge with exactly these values)
 __global__ void k_final_gather(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ idx, const unsigned long long* __restrict__ n_p,
-                               const PassTuple* __restrict__ tuples, const int32_t* __restrict__ q_of_row, const int32_t* __restrict__ subq,
-                               const SubBucket* __restrict__ subs, P1Cache p1c, const double* __restrict__ powtab, const int32_t* __restrict__ pow_off,
-                               FinalOut o) {
+                               const PassTuple* __restrict__ tuples, DevIn in, P1Cache p1c, const double* __restrict__ powtab,
+                               const int32_t* __restrict__ pow_off, FinalOut o) {
     const unsigned long long n = *n_p;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long e = keys[i];
         const PassTuple t = tuples[idx[i]];
         const int k1 = (int)(e >> 28), k2 = (int)(e & 0xfffffffull);
-        const SubBucket sb = subs[subq[q_of_row[k1]]];
+        // the edge's sub-bucket facts straight from its first row (rows of other shards are not packed on this context)
+        const int n3 = 3 * (in.row_len[2 * (int64_t)k1] + in.row_len[2 * (int64_t)k1 + 1]);               // join_one.rs:499
+        const int ch = in.row_cdr3_len[2 * (int64_t)k1], cl = in.row_cdr3_len[2 * (int64_t)k1 + 1];
         const int cd1 = (int)(t.cd12 & 0xffff), cd2 = (int)(t.cd12 >> 16);
         const int nrefs = (int)(t.nrefs_err & 0xff);
         const int min_sh = (nrefs == 2) ? min(t.sh0, t.sh1) : t.sh0;
         const int min_in = (nrefs == 2) ? min(t.in0, t.in1) : t.in0;
         const int kk = min_in + 2 * min_sh;
-        const double p1 = p1_lookup(p1c, sb.n3, kk, min_sh);
-        const double mult = __dmul_rn(powtab[pow_off[sb.ch] + cd1], powtab[pow_off[sb.cl] + cd2]);
+        const double p1 = p1_lookup(p1c, n3, kk, min_sh);
+        const double mult = __dmul_rn(powtab[pow_off[ch] + cd1], powtab[pow_off[cl] + cd2]);
         o.k1[i] = k1;
         o.k2[i] = k2;
         o.cd[i] = cd1 + cd2;
@@ -345,7 +406,7 @@ __global__ void k_final_gather(const unsigned long long* __restrict__ keys, cons
         o.indeps[2 * i + 1] = t.in1;
         o.k[i] = kk;
         o.d[i] = min_sh;
-        o.n[i] = sb.n3;
+        o.n[i] = n3;
         o.p1[i] = p1;
         o.mult[i] = mult;
         o.score[i] = __dmul_rn(p1, mult);

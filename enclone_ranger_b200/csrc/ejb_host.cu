@@ -157,7 +157,7 @@ struct ejb_ctx {
 
     // derived (per run)
     DevBuf d_head, d_scan, d_keys, d_keys2, d_vals, d_vals2, d_cubtmp, d_subhead, d_subincl, d_subinfo;
-    DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_aux;
+    DevBuf d_subs, d_cdr3w, d_rowstore, d_m_row, d_m_sub, d_aux, d_packoff, d_packsub, d_bstart;
     DevBuf d_donor, d_bckeys, d_bckeys2, d_powtab, d_powoff, d_labq, d_blklab, d_blksub, d_parent, d_best;
     DevBuf d_qcut, d_subpass, d_segpl, d_seglen, d_memo, d_tagq, d_deadq, d_donq, d_flagq, d_subdom;
     // per-round report: [Counters | UnitOut x units | candidate count x tasks], read back with ONE copy per round
@@ -169,12 +169,12 @@ struct ejb_ctx {
     std::vector<TaskMeta> task_meta;
     std::vector<unsigned long long> h_unitcand;   // candidates of each task (row range) of the last round, valid even when it overflowed
     DevBuf d_tasks, d_units, d_cand, d_slow, d_slowslot, d_surv, d_pass, d_passt, d_roots, d_forest, d_forestt;
-    DevBuf d_qofrow, d_deg, d_first, d_labels, d_fkeys, d_fkeys2, d_fidx, d_fidx2;
+    DevBuf d_deg, d_first, d_labels, d_fkeys, d_fkeys2, d_fidx, d_fidx2;
     DevBuf d_o_k1, d_o_k2, d_o_cd, d_o_nrefs, d_o_sh, d_o_in, d_o_k, d_o_d, d_o_n, d_o_p1, d_o_mult, d_o_score, d_o_err;
     // pair-batch mode (ejb_join_one_batch)
     DevBuf d_bpairs, d_bslots, d_btuples, d_bcnt;
     std::vector<SubBucket> subs;
-    int64_t n_active = 0, n_pos = 0, n_blocks = 0, n_final = 0;
+    int64_t n_active = 0, n_pos = 0, n_blocks = 0, n_final = 0, n_buckets = 0;
     unsigned long long forest_cap = 0;
     bool prepared = false;      // the packed row store of the uploaded input is resident (ejb_run got at least that far)
     ejb_stats stats;
@@ -890,7 +890,7 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
         c->stats.stage1_launches++;
     }
     // truncate units whose counted candidates exceed their allowance (on the device: no read-back between stage 1 and stage 2)
-    launch(c, k_truncate, nblk((int64_t)n_units, 128), 128, c->d_units.as<const UnitDesc>(), (int)n_units, c->d_tasks.as<const RowTask>(),
+    launch(c, k_truncate, nblk((int64_t)n_units * 32, 128), 128, c->d_units.as<const UnitDesc>(), (int)n_units, c->d_tasks.as<const RowTask>(),
            (const unsigned long long*)d_ucand, c->d_subs.as<const SubBucket>(), c->d_qcut.as<int32_t>(), c->d_subpass.as<unsigned int>(), d_uout, c->d_ctr());
     CK(cudaGetLastError());
     CK(cudaEventRecord(rt.e1, st));
@@ -972,6 +972,68 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     c->stats.rounds++;
     if (c->p1_count > c->p1_cap / 4 && (rc = p1_cache_grow(c)) != EJB_OK) return rc;
     return EJB_OK;
+}
+
+// Multi-GPU ownership.  Sub-buckets are independent units (join.rs:70-88), so ranks shard them with no collective on the data
+// path.  Longest-processing-time assignment on a cost model (a row acting as first row costs the rows to its right + 64); a
+// sub-bucket whose cost exceeds `split_above` x a rank's share is cut into row ranges of about `piece` x the share (each part =
+// the pairs whose FIRST row lies in the range; it returns the lexicographic spanning forest of ITS pass edges, and the merge
+// keeps the minimum spanning forest of the union of the partial forests: MSF(G) = MSF(MSF(G1) u MSF(G2) u ...)).  Parts of one
+// sub-bucket go to different ranks.  Deterministic: every rank computes the same assignment from the same table.
+void shard_assign(std::vector<SubBucket>& subs, int rank, int world, double split_above = 0.25, double piece = 0.125) {
+    struct Item { double cost; int sub, lo, hi, nparts; };
+    auto cum = [](double n, double r) { return r * (n - 1.0) - r * (r - 1.0) / 2.0 + 64.0 * r; };   // cost of first rows [0, r)
+    double total = 0.0;
+    for (const SubBucket& sb : subs)
+        if (sb.n >= 2) total += cum(sb.n, sb.n);
+    const double share = total / std::max(world, 1);
+    std::vector<Item> items;
+    for (int s = 0; s < (int)subs.size(); s++) {
+        const SubBucket& sb = subs[s];
+        if (sb.n < 2) continue;
+        const double c = cum(sb.n, sb.n);
+        if (sb.n >= 1024 && c > split_above * share) {
+            const int parts = (int)std::min<double>(world, std::ceil(c / (piece * share)));
+            std::vector<int> cuts;
+            cuts.push_back(0);
+            for (int i = 1; i < parts; i++) {   // smallest r with cum(r) >= c i / parts
+                int lo = 0, hi = sb.n;
+                const double want = c * i / parts;
+                while (lo < hi) {
+                    const int mid = (lo + hi) / 2;
+                    if (cum(sb.n, mid) >= want) hi = mid; else lo = mid + 1;
+                }
+                if (lo > cuts.back() && lo < sb.n) cuts.push_back(lo);
+            }
+            cuts.push_back(sb.n);
+            for (size_t i = 0; i + 1 < cuts.size(); i++)
+                items.push_back({cum(sb.n, cuts[i + 1]) - cum(sb.n, cuts[i]), s, cuts[i], cuts[i + 1], (int)cuts.size() - 1});
+        } else {
+            items.push_back({c, s, 0, sb.n, 1});
+        }
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
+    std::vector<double> load((size_t)world, 0.0);
+    std::vector<uint64_t> holder(subs.size(), 0);   // ranks already holding a part of the sub-bucket (world <= 64)
+    for (SubBucket& sb : subs) {
+        sb.owner = -1;
+        sb.r_beg = sb.n_act = 0;
+    }
+    for (const Item& it : items) {
+        int best = -1;
+        for (int r = 0; r < world; r++) {
+            if (holder[(size_t)it.sub] >> r & 1) continue;
+            if (best < 0 || load[(size_t)r] < load[(size_t)best]) best = r;
+        }
+        if (best < 0) best = 0;   // cannot happen: parts <= world
+        holder[(size_t)it.sub] |= 1ull << best;
+        load[(size_t)best] += it.cost;
+        if (best == rank) {
+            subs[(size_t)it.sub].r_beg = it.lo;
+            subs[(size_t)it.sub].n_act = it.hi;
+            subs[(size_t)it.sub].owner = it.nparts == 1 ? rank : -1;
+        }
+    }
 }
 
 // ---- prepare: bucket scan, sub-bucket table, bucketer.  ONE read-back (the run header + the sub-bucket table). ----
@@ -1064,6 +1126,9 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     c->n_active = (int64_t)hh.n_active;
     const int64_t NA = c->n_active;
     const int n_subs = (int)hh.n_subs;
+    c->n_buckets = (int64_t)hh.n_buckets;
+    CK(c->d_bstart.ensure((size_t)std::max<int64_t>(c->n_buckets, 1) * 4));
+    launch(c, k_bucket_starts, nblk(N, 256), 256, c->d_head.as<const int32_t>(), c->d_scan.as<const int32_t>(), N, c->d_bstart.as<int32_t>());
     if (NA == 0) return EJB_OK;
     std::vector<SubInfo> si((size_t)n_subs);
     std::vector<SubRole> sroles;
@@ -1080,13 +1145,10 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     }
     c->stats.d2h_bytes += (int64_t)n_subs * sizeof(SubInfo);
 
-    // ---- sub-bucket table, offsets, thresholds ----
+    // ---- sub-bucket table: sizes and thresholds first, then ownership (multi-GPU), then offsets of what this context packs ----
     const DevParams P = make_dev_params(c->params);
     std::vector<SubBucket>& subs = c->subs;
     subs.resize(n_subs);
-    int64_t q = 0, s1 = 0, rs = 0, blk = 0;
-    int64_t bucket_rows = 0;
-    uint64_t cur_bucket = ~0ull;
     int max_cdr3 = 0;
     for (int s = 0; s < n_subs; s++) {
         SubBucket& sb = subs[s];
@@ -1105,13 +1167,11 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
         sb.W4l = (sb.Ll >= 1 && sb.Ll <= 512) ? 4 : (sb.Ll <= 128 * MAXW4 && sb.Ll >= 1) ? MAXW4 : 0;
         sb.gap = si[s].gap & 3;
         sb.rec_u4 = rec_planes(0, sb.gap & 1) * sb.W4h + rec_planes(1, sb.gap & 2) * sb.W4l;
-        sb.pad = 0;
+        sb.rot = (sb.W1 >= 2 && sb.ch > 32) ? (sb.ch - 32) / 2 : 0;   // word 0 = the middle of the heavy junction
+        sb.pad2 = 0;
+        sb.r_beg = 0;
         sb.n_act = c->have_roles ? sroles[(size_t)s].n_act : sb.n;
         sb.raw = c->have_roles ? sroles[(size_t)s].raw : 0;
-        sb.q0 = q;
-        sb.s1_off = s1;
-        sb.rs_off = rs;
-        sb.blk0 = (int32_t)blk;
         sb.n3 = 3 * (sb.Lh + sb.Ll);
         sb.owner = 0;
         // stage-1 threshold: a superset of join_one.rs:231 and :286-290 (stage 2 re-tests exactly)
@@ -1127,12 +1187,37 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
         }
         sb.maxcd = maxcd;
         max_cdr3 = std::max({max_cdr3, sb.ch, sb.cl});
-        q += sb.npad;
-        s1 += (int64_t)2 * sb.W1 * sb.npad;
-        rs += (int64_t)sb.n * sb.rec_u4;
-        blk += (sb.n + TILE - 1) / TILE;
-        // pairs whose first row is one of the n_act leading rows (all n(n-1)/2 without row roles)
-        c->stats.pairs_scored += (int64_t)sb.n_act * (sb.n - 1) - (int64_t)sb.n_act * (sb.n_act - 1) / 2;
+    }
+    // ---- multi-GPU ownership (identical on every rank: same table, same deterministic assignment) ----
+    if (c->shard_world > 1) shard_assign(subs, c->shard_rank, c->shard_world);
+    int64_t q = 0, s1 = 0, rs = 0, blk = 0;
+    int64_t bucket_rows = 0;
+    uint64_t cur_bucket = ~0ull;
+    std::vector<int64_t> pack_off;
+    std::vector<int32_t> pack_sub;
+    pack_off.push_back(0);
+    for (int s = 0; s < n_subs; s++) {
+        SubBucket& sb = subs[s];
+        const bool packed = sb.n_act > sb.r_beg || (c->shard_world == 1);   // single context: everything is packed (labels cover all rows)
+        sb.q0 = q;
+        sb.s1_off = s1;
+        sb.rs_off = rs;
+        sb.blk0 = (int32_t)blk;
+        if (packed) {
+            q += sb.npad;
+            s1 += (int64_t)2 * sb.W1 * sb.npad;
+            rs += (int64_t)sb.n * sb.rec_u4;
+            blk += (sb.n + TILE - 1) / TILE;
+            pack_sub.push_back(s);
+            pack_off.push_back(pack_off.back() + sb.n);
+        } else {
+            sb.r_beg = sb.n_act = 0;
+        }
+        // pairs whose first row is one of the rows [r_beg, n_act) (all n(n-1)/2 when the whole sub-bucket is joined here)
+        {
+            const int64_t a0 = sb.r_beg, a1 = sb.n_act, m = a1 - a0;
+            if (m > 0) c->stats.pairs_scored += m * (sb.n - 1) - (a0 + a1 - 1) * m / 2;
+        }
         const uint64_t b = si[s].key >> 32;
         if (b != cur_bucket) {
             c->stats.pairs_lens += bucket_rows * (bucket_rows - 1) / 2;
@@ -1147,21 +1232,6 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     c->n_blocks = blk;
     if (q >= (1ll << 31)) return fail(c, EJB_ERR_INVALID, "too many packed rows");
     if (rs >= (1ll << 32) || s1 >= (1ll << 32)) return fail(c, EJB_ERR_INVALID, "packed row store exceeds 32-bit indexing (64 GB)");
-
-    // ---- multi-GPU ownership: LPT by pair count ----
-    if (c->shard_world > 1) {
-        std::vector<int> order(n_subs);
-        for (int s = 0; s < n_subs; s++) order[s] = s;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return subs[a].n > subs[b].n; });
-        std::vector<double> load(c->shard_world, 0.0);
-        for (int s : order) {
-            int best = 0;
-            for (int r = 1; r < c->shard_world; r++)
-                if (load[r] < load[best]) best = r;
-            subs[s].owner = best;
-            load[best] += (double)subs[s].n * (subs[s].n - 1) / 2 + 64.0 * subs[s].n;
-        }
-    }
 
     // ---- pow table: mult_pow ^ (cdr3_normal_len * cd / n), join_one.rs:531-539 ----
     std::vector<int32_t> pow_off((size_t)max_cdr3 + 2, 0);
@@ -1188,7 +1258,7 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     CK(c->d_subs.ensure((size_t)n_subs * sizeof(SubBucket)));
     CK(cudaMemcpyAsync(c->d_subs.p, subs.data(), (size_t)n_subs * sizeof(SubBucket), cudaMemcpyHostToDevice, st));
     std::vector<int32_t> blk_sub((size_t)blk);
-    for (int s = 0; s < n_subs; s++)
+    for (int s : pack_sub)
         for (int b = 0; b < (subs[s].n + TILE - 1) / TILE; b++) blk_sub[subs[s].blk0 + b] = s;
     CK(c->d_blksub.ensure((size_t)std::max<int64_t>(blk, 1) * 4));
     CK(cudaMemcpyAsync(c->d_blksub.p, blk_sub.data(), (size_t)blk * 4, cudaMemcpyHostToDevice, st));
@@ -1212,8 +1282,14 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
         CK(cudaMemsetAsync(c->d_deadq.p, 0xff, np * 8, st));   // DEAD_NONE
     }
     mark("tables+memsets+bcsort");
-    launch(c, k_pack_rows, nblk(NA * 32, 256), 256, din, P, c->d_subs.as<const SubBucket>(), c->d_subincl.as<const int32_t>(), row_of,
-           (const unsigned long long*)&hdr->n_active, c->d_donor.as<const unsigned long long>(), c->d_segpl.as<const uint32_t>(), c->d_seglen.as<const int32_t>(),
+    const int n_pack = (int)pack_sub.size();
+    CK(c->d_packoff.ensure(pack_off.size() * 8));
+    CK(c->d_packsub.ensure((size_t)std::max(n_pack, 1) * 4));
+    CK(cudaMemcpyAsync(c->d_packoff.p, pack_off.data(), pack_off.size() * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_packsub.p, pack_sub.data(), (size_t)n_pack * 4, cudaMemcpyHostToDevice, st));
+    if (n_pack > 0)
+    launch(c, k_pack_rows, nblk(pack_off.back() * 32, 256), 256, din, P, c->d_subs.as<const SubBucket>(), c->d_packoff.as<const int64_t>(),
+           c->d_packsub.as<const int32_t>(), n_pack, row_of, c->d_donor.as<const unsigned long long>(), c->d_segpl.as<const uint32_t>(), c->d_seglen.as<const int32_t>(),
            c->d_cdr3w.as<uint32_t>(), c->d_rowstore.as<uint4>(), c->d_aux.as<int32_t>(), c->d_m_row.as<int32_t>(), c->d_m_sub.as<int32_t>(),
            c->tags_on ? c->d_tagq.as<unsigned long long>() : (unsigned long long*)nullptr, c->tags_on ? c->d_donq.as<unsigned long long>() : (unsigned long long*)nullptr);
     if (c->tags_on)
@@ -1221,6 +1297,59 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
                c->d_donq.as<const unsigned long long>(), c->d_subdom.as<SubDom>());
     mark("pack_rows");
     CK(cudaGetLastError());
+    return EJB_OK;
+}
+
+}  // namespace
+
+namespace {
+// ---- finalize: two-cell filter, ordering, PotentialJoin members, clonotype_id unions, labels.  Every count stays on the
+//      device; the only read-back is the final counter block (queued by the caller). ----
+int finalize(ejb_ctx* c) {
+    const DevIn& din = c->din;
+    const int64_t N = din.n_rows;
+    cudaStream_t st = c->stream;
+    int rc = EJB_OK;
+    CK(c->d_labels.ensure((size_t)std::max<int64_t>(N, 1) * 4));
+    const int fgrid = c->sm_count * 8;
+    if (N > 0) {
+        const size_t nf = (size_t)c->forest_cap;
+        CK(c->d_deg.ensure((size_t)N * 4));
+        CK(c->d_fkeys.ensure(nf * 8)); CK(c->d_fkeys2.ensure(nf * 8));
+        CK(c->d_fidx.ensure(nf * 4)); CK(c->d_fidx2.ensure(nf * 4));
+        CK(cudaMemsetAsync(c->d_deg.p, 0, (size_t)N * 4, st));
+        CK(cudaMemsetAsync(c->d_fkeys.p, 0xff, nf * 8, st));   // unused tail sorts to the end
+        launch(c, k_forest_deg, fgrid, 256, c->d_forest.as<const unsigned long long>(), (const unsigned long long*)CTR_FIELD(n_forest), c->d_deg.as<int32_t>());
+        launch(c, k_two_cell, fgrid, 256, din, make_dev_params(c->params), c->d_forest.as<const unsigned long long>(), (const unsigned long long*)CTR_FIELD(n_forest),
+               c->d_deg.as<const int32_t>(), c->d_forestt.as<const PassTuple>(), c->d_parent.as<int32_t>(), c->d_fkeys.as<unsigned long long>(),
+               c->d_fidx.as<uint32_t>(), c->d_ctr(), c->have_roles ? c->d_roles.as<const uint8_t>() : (const uint8_t*)nullptr);
+        rc = cub_sort_pairs64(c, c->d_fkeys.as<uint64_t>(), c->d_fkeys2.as<uint64_t>(), c->d_fidx.as<uint32_t>(), c->d_fidx2.as<uint32_t>(), (int64_t)nf);
+        if (rc) return rc;
+        CK(c->d_o_k1.ensure(nf * 4)); CK(c->d_o_k2.ensure(nf * 4)); CK(c->d_o_cd.ensure(nf * 4)); CK(c->d_o_nrefs.ensure(nf * 4));
+        CK(c->d_o_sh.ensure(nf * 8)); CK(c->d_o_in.ensure(nf * 8)); CK(c->d_o_k.ensure(nf * 4)); CK(c->d_o_d.ensure(nf * 4));
+        CK(c->d_o_n.ensure(nf * 4)); CK(c->d_o_p1.ensure(nf * 8)); CK(c->d_o_mult.ensure(nf * 8)); CK(c->d_o_score.ensure(nf * 8));
+        CK(c->d_o_err.ensure(nf));
+        FinalOut fo;
+        fo.k1 = c->d_o_k1.as<int32_t>(); fo.k2 = c->d_o_k2.as<int32_t>(); fo.cd = c->d_o_cd.as<int32_t>(); fo.nrefs = c->d_o_nrefs.as<int32_t>();
+        fo.shares = c->d_o_sh.as<int32_t>(); fo.indeps = c->d_o_in.as<int32_t>(); fo.k = c->d_o_k.as<int32_t>(); fo.d = c->d_o_d.as<int32_t>();
+        fo.n = c->d_o_n.as<int32_t>(); fo.p1 = c->d_o_p1.as<double>(); fo.mult = c->d_o_mult.as<double>(); fo.score = c->d_o_score.as<double>();
+        fo.err = c->d_o_err.as<uint8_t>();
+        P1Cache pc;
+        pc.keys = c->d_p1_keys.as<unsigned long long>();
+        pc.vals = c->d_p1_vals.as<double>();
+        pc.newslots = c->d_p1_new.as<uint32_t>();
+        pc.cap_mask = c->p1_cap - 1;
+        launch(c, k_final_gather, fgrid, 256, c->d_fkeys2.as<const unsigned long long>(), c->d_fidx2.as<const uint32_t>(), (const unsigned long long*)CTR_FIELD(n_final),
+               c->d_forestt.as<const PassTuple>(), din, pc, c->d_powtab.as<const double>(), c->d_powoff.as<const int32_t>(), fo);
+    }
+    if (N > 0) {
+        // join2.rs:69-84 + canonical labels
+        CK(c->d_first.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 4));
+        launch(c, k_fill_i32, nblk(din.n_exacts, 256), 256, c->d_first.as<int32_t>(), din.n_exacts, 0x7fffffff);
+        launch(c, k_exact_first, nblk(N, 256), 256, din, c->d_first.as<int32_t>());
+        launch(c, k_exact_union, nblk(N, 256), 256, din, c->d_first.as<const int32_t>(), c->d_parent.as<int32_t>());
+        launch(c, k_labels, nblk(N, 256), 256, c->d_parent.as<const int32_t>(), N, c->d_labels.as<int32_t>());
+    }
     return EJB_OK;
 }
 
@@ -1261,7 +1390,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
     {
         unsigned long long need = 0;
         for (const SubBucket& sb : c->subs)
-            if (sb.owner == c->shard_rank) need = std::max<unsigned long long>(need, (unsigned long long)TILE * (unsigned long long)sb.n);
+            if (sb.n_act > sb.r_beg) need = std::max<unsigned long long>(need, (unsigned long long)TILE * (unsigned long long)sb.n);
         if (need > c->cand_cap && !c->cap_explicit) c->cand_cap = need;   // worst case of ONE row block: all of its pairs are candidates
     }
     const unsigned long long cap = c->cand_cap;
@@ -1287,11 +1416,12 @@ extern "C" int ejb_run(ejb_ctx* c) {
         // candidate counts of that attempt are exact upper bounds for the retry, which is planned from them.
         struct Known { int r0, r1; double cand; };
         std::vector<int> next_row(subs.size(), 0), live;
+        for (size_t s = 0; s < subs.size(); s++) next_row[s] = subs[s].r_beg;
         std::vector<double> rho(subs.size(), -1.0);          // candidates per row of the last committed row range
         std::vector<double> prate(subs.size(), 1.0);         // pass edges per candidate of the last committed unit
         std::vector<std::vector<Known>> known(subs.size());  // counted, not yet committed row ranges (ascending)
         for (int s = 0; s < (int)subs.size(); s++)
-            if (subs[s].n >= 2 && subs[s].n_act >= 1 && subs[s].owner == c->shard_rank) live.push_back(s);
+            if (subs[s].n >= 2 && subs[s].n_act > subs[s].r_beg && subs[s].r_beg < subs[s].n - 1) live.push_back(s);
         const double cap_round = 0.5 * (double)c->cand_cap;                      // expected candidates allowed per round
         const double target_pass = std::max(4096.0, (double)c->cand_cap / 64.0);   // pass edges one unit should not exceed by much
         int stalls = 0;
@@ -1340,7 +1470,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
                         ex = kn.front().cand / (double)std::max(1, kn.front().r1 - kn.front().r0);
                     }
                 } else {
-                    const long long want = (r0 == 0) ? first_unit : std::max<long long>(first_unit, growth * r0);   // optimistic growth: rows done so far x growth
+                    const long long done = r0 - sb.r_beg;   // rows this context has processed as first rows
+                    const long long want = (done == 0) ? first_unit : std::max<long long>(first_unit, growth * done);   // optimistic growth: rows done so far x growth
                     r1 = (int)std::min<long long>((long long)r0 + want, sb.n_act);
                     ex = (rho[s] > 0.0 ? rho[s] : std::min<double>(64.0, (double)sb.n)) * (double)(r1 - r0);
                     // capacity: never plan more expected candidates than a round may hold
@@ -1408,51 +1539,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
     }
     CK(cudaEventRecord(ev_rounds, st));
 
-    // ---- finalize: two-cell filter, ordering, PotentialJoin members, clonotype_id unions, labels.  Every count stays on the
-    //      device; the only read-back is the final counter block. ----
-    CK(c->d_labels.ensure((size_t)std::max<int64_t>(N, 1) * 4));
-    const int fgrid = c->sm_count * 8;
-    if (N > 0 && c->n_pos > 0) {
-        const size_t nf = (size_t)c->forest_cap;
-        CK(c->d_qofrow.ensure((size_t)N * 4));
-        CK(c->d_deg.ensure((size_t)N * 4));
-        CK(c->d_fkeys.ensure(nf * 8)); CK(c->d_fkeys2.ensure(nf * 8));
-        CK(c->d_fidx.ensure(nf * 4)); CK(c->d_fidx2.ensure(nf * 4));
-        CK(cudaMemsetAsync(c->d_deg.p, 0, (size_t)N * 4, st));
-        CK(cudaMemsetAsync(c->d_fkeys.p, 0xff, nf * 8, st));   // unused tail sorts to the end
-        launch(c, k_q_of_row, nblk(c->n_pos, 256), 256, c->d_m_row.as<const int32_t>(), c->n_pos, c->d_qofrow.as<int32_t>());
-        launch(c, k_forest_deg, fgrid, 256, c->d_forest.as<const unsigned long long>(), (const unsigned long long*)CTR_FIELD(n_forest), c->d_deg.as<int32_t>());
-        launch(c, k_two_cell, fgrid, 256, din, make_dev_params(c->params), c->d_forest.as<const unsigned long long>(), (const unsigned long long*)CTR_FIELD(n_forest),
-               c->d_deg.as<const int32_t>(), c->d_forestt.as<const PassTuple>(), c->d_parent.as<int32_t>(), c->d_fkeys.as<unsigned long long>(),
-               c->d_fidx.as<uint32_t>(), c->d_ctr(), c->have_roles ? c->d_roles.as<const uint8_t>() : (const uint8_t*)nullptr);
-        rc = cub_sort_pairs64(c, c->d_fkeys.as<uint64_t>(), c->d_fkeys2.as<uint64_t>(), c->d_fidx.as<uint32_t>(), c->d_fidx2.as<uint32_t>(), (int64_t)nf);
-        if (rc) return rc;
-        CK(c->d_o_k1.ensure(nf * 4)); CK(c->d_o_k2.ensure(nf * 4)); CK(c->d_o_cd.ensure(nf * 4)); CK(c->d_o_nrefs.ensure(nf * 4));
-        CK(c->d_o_sh.ensure(nf * 8)); CK(c->d_o_in.ensure(nf * 8)); CK(c->d_o_k.ensure(nf * 4)); CK(c->d_o_d.ensure(nf * 4));
-        CK(c->d_o_n.ensure(nf * 4)); CK(c->d_o_p1.ensure(nf * 8)); CK(c->d_o_mult.ensure(nf * 8)); CK(c->d_o_score.ensure(nf * 8));
-        CK(c->d_o_err.ensure(nf));
-        FinalOut fo;
-        fo.k1 = c->d_o_k1.as<int32_t>(); fo.k2 = c->d_o_k2.as<int32_t>(); fo.cd = c->d_o_cd.as<int32_t>(); fo.nrefs = c->d_o_nrefs.as<int32_t>();
-        fo.shares = c->d_o_sh.as<int32_t>(); fo.indeps = c->d_o_in.as<int32_t>(); fo.k = c->d_o_k.as<int32_t>(); fo.d = c->d_o_d.as<int32_t>();
-        fo.n = c->d_o_n.as<int32_t>(); fo.p1 = c->d_o_p1.as<double>(); fo.mult = c->d_o_mult.as<double>(); fo.score = c->d_o_score.as<double>();
-        fo.err = c->d_o_err.as<uint8_t>();
-        P1Cache pc;
-        pc.keys = c->d_p1_keys.as<unsigned long long>();
-        pc.vals = c->d_p1_vals.as<double>();
-        pc.newslots = c->d_p1_new.as<uint32_t>();
-        pc.cap_mask = c->p1_cap - 1;
-        launch(c, k_final_gather, fgrid, 256, c->d_fkeys2.as<const unsigned long long>(), c->d_fidx2.as<const uint32_t>(), (const unsigned long long*)CTR_FIELD(n_final),
-               c->d_forestt.as<const PassTuple>(), c->d_qofrow.as<const int32_t>(), c->d_m_sub.as<const int32_t>(), c->d_subs.as<const SubBucket>(), pc,
-               c->d_powtab.as<const double>(), c->d_powoff.as<const int32_t>(), fo);
-    }
-    if (N > 0) {
-        // join2.rs:69-84 + canonical labels
-        CK(c->d_first.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 4));
-        launch(c, k_fill_i32, nblk(din.n_exacts, 256), 256, c->d_first.as<int32_t>(), din.n_exacts, 0x7fffffff);
-        launch(c, k_exact_first, nblk(N, 256), 256, din, c->d_first.as<int32_t>());
-        launch(c, k_exact_union, nblk(N, 256), 256, din, c->d_first.as<const int32_t>(), c->d_parent.as<int32_t>());
-        launch(c, k_labels, nblk(N, 256), 256, c->d_parent.as<const int32_t>(), N, c->d_labels.as<int32_t>());
-    }
+    // a shard returns its partial forest (ejb_part_forest); the merging context finalizes the union (ejb_merge_parts)
+    if (c->shard_world == 1 && (rc = finalize(c)) != EJB_OK) return rc;
     CK(cudaEventRecord(ev_end, st));
     CK(c->h_round.ensure(sizeof(Counters)));
     CK(cudaMemcpyAsync(c->h_round.p, c->d_round.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));

@@ -71,6 +71,13 @@ __global__ void k_validate_tables(DevIn in, unsigned int* err) {
     if (e) atomicOr(err, e);
 }
 
+// first row of every lens bucket (runs of equal lens are contiguous in row order): what the host needs to replay the
+// EquivRel of independent buckets in parallel
+__global__ void k_bucket_starts(const int32_t* __restrict__ head, const int32_t* __restrict__ bucket_incl, int64_t n, int32_t* __restrict__ starts) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n && head[k]) starts[bucket_incl[k] - 1] = (int32_t)k;
+}
+
 // sort key of a row: (bucket id, heavy CDR3 len, light CDR3 len); rows that can never join
 // (lens.len() != 2, join_one.rs:83-96) get the maximal key and fall off the end.
 // Run header on the device: what the host reads back ONCE after the bucket scan and the sub-bucket table are built.
@@ -156,6 +163,11 @@ __global__ void k_sub_dominant(const SubBucket* __restrict__ subs, int n_subs, c
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_subs) return;
     const SubBucket sb = subs[s];
+    if (sb.n_act <= sb.r_beg) {   // not packed on this context (another shard owns it)
+        out[s].tag = DEAD_NONE;
+        out[s].don = 0ull;
+        return;
+    }
     unsigned long long t[5], d[5];
     for (int i = 0; i < 5; i++) {
         const int64_t q = sb.q0 + (int64_t)(((int64_t)sb.n * (2 * i + 1)) / 10);
@@ -242,18 +254,25 @@ __device__ __forceinline__ uint32_t even_bits(uint32_t x) {
 #ifndef PACK_MINB
 #define PACK_MINB 8   // latency-bound: occupancy wins over spills
 #endif
-__global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__ subs, const int32_t* __restrict__ sub_incl,
-                            const uint32_t* __restrict__ row_of, const unsigned long long* __restrict__ n_active_p, const unsigned long long* __restrict__ donor_mask,
+// pack_off / pack_sub: the sub-buckets this context packs (all of them, or the ones its shard owns) and the prefix sums of
+// their row counts; warp w handles row w - pack_off[i] of sub-bucket pack_sub[i].
+__global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__ subs, const int64_t* __restrict__ pack_off,
+                            const int32_t* __restrict__ pack_sub, int n_pack, const uint32_t* __restrict__ row_of, const unsigned long long* __restrict__ donor_mask,
                             const uint32_t* __restrict__ segpl, const int32_t* __restrict__ seglen, uint32_t* __restrict__ cdr3w, uint4* __restrict__ rowstore,
                             int32_t* __restrict__ aux, int32_t* __restrict__ rowq, int32_t* __restrict__ subq,
                             unsigned long long* __restrict__ tagq, unsigned long long* __restrict__ donq) {
     const int lane = threadIdx.x & 31;
-    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= (int64_t)*n_active_p) return;
-    const int s = sub_incl[j] - 1;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= pack_off[n_pack]) return;
+    int plo = 0, phi = n_pack - 1;
+    while (plo < phi) {   // last i with pack_off[i] <= w
+        const int mid = (plo + phi + 1) >> 1;
+        if (pack_off[mid] <= w) plo = mid; else phi = mid - 1;
+    }
+    const int s = pack_sub[plo];
     const SubBucket sb = subs[s];
-    const int64_t k = row_of[j];
-    const int64_t li = j - sb.j0;
+    const int64_t li = w - pack_off[plo];
+    const int64_t k = row_of[sb.j0 + li];
     const int64_t q = sb.q0 + li;
     uint32_t flags = 0;
     int tot = 0;
@@ -272,8 +291,10 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
             const int p = w * 32 + lane;
             int code = 0;
             if (p < T) {
-                const bool heavy = p < sb.ch;
-                const int pp = heavy ? p : p - sb.ch;
+                int op = p + sb.rot;                 // stored position p holds original position (p + rot) mod T
+                if (op >= T) op -= T;
+                const bool heavy = op < sb.ch;
+                const int pp = heavy ? op : op - sb.ch;
                 if ((heavy ? o0 : o1) >= 0) {
                     const uint32_t c2 = ((heavy ? w0 : w1)[pp >> 4] >> (2 * (pp & 15))) & 3u;   // A,C,G,T = 0..3
                     code = (int)(c2 ^ (c2 >> 1));                                               // -> internal A,C,T,G = 0,1,2,3
@@ -346,7 +367,7 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
         const uint32_t* tw = in.tig2_words + in.row_tig2_off[2 * k + m];
         const int nw16 = (L + 15) >> 4;
         const uint32_t x0 = (2 * w < nw16) ? tw[2 * w] : 0u, x1 = (2 * w + 1 < nw16) ? tw[2 * w + 1] : 0u;
-        const uint32_t inl = mask_lt((long long)L - 32 * w);
+        const uint32_t inl = mask_lt32(L - 32 * w);
         uint32_t lo = even_bits(x0) | (even_bits(x1) << 16), hi = even_bits(x0 >> 1) | (even_bits(x1 >> 1) << 16);
         lo = (lo ^ hi) & inl;
         hi &= inl;

@@ -86,7 +86,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 #ifndef S1_MINB2
-#define S1_MINB2 4
+#define S1_MINB2 3   // 85 registers: the 8-row fragment (32 words + 8 labels at W1 = 2) stays in registers; 4 CTAs (64 registers) spill it
 #endif
 #ifndef S1_MINB3
 #define S1_MINB3 3
@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
 #pragma unroll
         for (int i = 1; i < 8; i++)
             if (rlab[i] != runi) runi = -2;
+        runi = __shfl_sync(0xffffffffu, runi, lane);   // identity shuffle: keeps the value in a register (ptxas otherwise re-derives it
+                                                       // from the eight labels for every column, 14 instructions instead of none)
     }
     const int row_lo = t.row_lo;
     const int row_lim = min(sb.n - rb * TILE, t.row_hi);  // valid local rows are row_lo <= r < row_lim
@@ -244,40 +246,44 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         const bool diag = (cb == rb);
         const bool full = !diag && row_lo == 0 && row_lim >= TILE && col_lim >= TILE;
         const uint32_t q_c0 = (uint32_t)(sb.q0 + (int64_t)cb * TILE);
+        const uint32_t* pc = sc + tx;   // this thread's column of the staged tile, advanced by 16 per step
 #pragma unroll 1
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 8; j++, pc += 16) {
             const int c = j * 16 + tx;
-            const int clab = (int)sc[NP * TILE + c];
+            const int clab = (int)pc[NP * TILE];
             if (RUNI && __all_sync(0xffffffffu, clab == runi)) continue;   // 16 rows x 16 columns of one class: one vote instead of eight
+            // first word of the eight pairs (the 32 most diverse CDR3 positions, SubBucket::rot): is any pair still a possible candidate?
+            const uint32_t cl0 = pc[0], ch0 = pc[W1 * TILE];
+            bool any = false;
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) any |= (__popc((rl[i][0] ^ cl0) | (rh[i][0] ^ ch0)) <= maxcd) & (rlab[i] != clab);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int r = i * 16 + ty;
+                    any |= (__popc((rl[i][0] ^ cl0) | (rh[i][0] ^ ch0)) <= maxcd) & (rlab[i] != clab) & (r >= row_lo) & (r < row_lim) & (c < col_lim) & (!diag | (r < c));
+                }
+            }
+            n_first += 8;
+            if (!__any_sync(0xffffffffu, any)) continue;
+            // rare: some pair of this warp passed the first word — full distances for the rows that still have a live pair
             uint32_t cl[W1], chh[W1];
 #pragma unroll
             for (int w = 0; w < W1; w++) {
-                cl[w] = sc[w * TILE + c];
-                chh[w] = sc[(W1 + w) * TILE + c];
+                cl[w] = pc[w * TILE];
+                chh[w] = pc[(W1 + w) * TILE];
             }
-            // first word of the eight pairs: is any of them still a possible candidate?
-            uint32_t live = 0;   // bit i: pair (row i, this column) has partial distance <= maxcd, different labels, and is in range
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int p0 = __popc((rl[i][0] ^ cl[0]) | (rh[i][0] ^ chh[0]));
-                bool ok = p0 <= maxcd && rlab[i] != clab;
-                if (!full) {
-                    const int r = i * 16 + ty;
-                    ok = ok && r >= row_lo && r < row_lim && c < col_lim && (!diag || r < c);
-                }
-                live |= (ok ? 1u : 0u) << i;
-            }
-            n_first += 8;
-            if (!__any_sync(0xffffffffu, live != 0)) continue;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                bool hit = (live >> i) & 1u;
-                if (!__any_sync(0xffffffffu, hit)) continue;
                 const int r = i * 16 + ty;
+                const int p0 = __popc((rl[i][0] ^ cl[0]) | (rh[i][0] ^ chh[0]));
+                bool hit = p0 <= maxcd && rlab[i] != clab;
+                if (!full) hit = hit && r >= row_lo && r < row_lim && c < col_lim && (!diag || r < c);
+                if (!__any_sync(0xffffffffu, hit)) continue;
                 if (W1 > 1) {
-                    const int cd = __popc((rl[i][0] ^ cl[0]) | (rh[i][0] ^ chh[0])) + cdr3_rest<W1>(rl[i], rh[i], cl, chh);
                     n_full++;
-                    hit = hit && cd <= maxcd;
+                    hit = hit && p0 + cdr3_rest<W1>(rl[i], rh[i], cl, chh) <= maxcd;
                 }
                 if (TAGS && hit) {
                     if (flag_kill(s_row[FLAG0 + r], sc[FLAG0 + c], donor_kills, tag_kills)) hit = false;

@@ -191,6 +191,7 @@ struct CandInfo {
     uint32_t cw1, cw2;    // word index of the two rows in plane 0 / word 0 of cdr3w
     uint32_t npad;        // row stride of the CDR3 planes
     uint32_t L2;          // contig lengths: heavy | light << 16 (both <= 1024 on this path)
+    uint32_t rc;          // CDR3 rotation | light CDR3 length << 16
     int tot1, tot2;
 };
 __device__ __forceinline__ CandInfo shfl_cand(const CandInfo& c, int src) {
@@ -204,6 +205,7 @@ __device__ __forceinline__ CandInfo shfl_cand(const CandInfo& c, int src) {
     r.cw2 = __shfl_sync(0xffffffffu, c.cw2, src);
     r.npad = __shfl_sync(0xffffffffu, c.npad, src);
     r.L2 = __shfl_sync(0xffffffffu, c.L2, src);
+    r.rc = __shfl_sync(0xffffffffu, c.rc, src);
     r.tot1 = __shfl_sync(0xffffffffu, c.tot1, src);
     r.tot2 = __shfl_sync(0xffffffffu, c.tot2, src);
     return r;
@@ -254,9 +256,9 @@ __device__ __forceinline__ void s2_chain(const S2Ctx& X, uint32_t q1, uint32_t q
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             const int p0 = 32 * (4 * g + w);
-            fd += __popc(e[w] & mask_lt((r0 >> 16) - p0) & ~mask_lt((r0 & 0xffff) - p0));
-            c1 += __popc(e[w] & mask_lt((r1 >> 16) - p0) & ~mask_lt((r1 & 0xffff) - p0));
-            c2 += __popc(e[w] & mask_lt((r2 >> 16) - p0) & ~mask_lt((r2 & 0xffff) - p0));
+            fd += __popc(e[w] & mask_lt32((r0 >> 16) - p0) & ~mask_lt32((r0 & 0xffff) - p0));
+            c1 += __popc(e[w] & mask_lt32((r1 >> 16) - p0) & ~mask_lt32((r1 & 0xffff) - p0));
+            c2 += __popc(e[w] & mask_lt32((r2 >> 16) - p0) & ~mask_lt32((r2 & 0xffff) - p0));
         }
         pk2 += (uint32_t)fd << 16;
         pk3 += (uint32_t)c1 | ((uint32_t)c2 << 16);
@@ -334,15 +336,14 @@ __device__ __forceinline__ void s2_planes(const S2Ctx& X, const CandInfo& ci, in
         }
     }
     if (active) {
-        // CDR3 distances, split at the heavy/light boundary of the concatenated planes
+        // CDR3 distances heavy | light.  The stored concatenation is rotated left by `rot`: stored positions [0, ch - rot) and
+        // [T - rot, T) are heavy, the ones in between light (bits >= T are zero in every plane).
+        const int rot = (int)(ci.rc & 0xffff), T = ch + (int)(ci.rc >> 16);
         for (int w = g; w < W1; w += G) {
             const uint32_t* b = X.cdr3w;
             const uint32_t x = (b[ci.cw1 + w * ci.npad] ^ b[ci.cw2 + w * ci.npad]) | (b[ci.cw1 + (W1 + w) * ci.npad] ^ b[ci.cw2 + (W1 + w) * ci.npad]);
             const int lo_bit = w * 32;
-            uint32_t hm;  // bits of this word that belong to the heavy CDR3
-            if (ch >= lo_bit + 32) hm = 0xffffffffu;
-            else if (ch <= lo_bit) hm = 0u;
-            else hm = (1u << (ch - lo_bit)) - 1u;
+            const uint32_t hm = mask_lt32(ch - rot - lo_bit) | (mask_lt32(T - lo_bit) & ~mask_lt32(T - rot - lo_bit));
             pk0 += (uint32_t)__popc(x & hm) | ((uint32_t)__popc(x & ~hm) << 16);
         }
         if (g < W4h) s2_chain<WS, 0>(X, ci.q1, ci.q2, Lh, pa0, pb0, W4h, g, gap & 1, nrefs1, pk1, pk2, pk3, n0, n1, n2, n3);
@@ -426,6 +427,7 @@ __global__ void __launch_bounds__(256, S2A_MINB) k_stage2a(S2Ctx X, const uint2*
         me.q1 = q1;
         me.q2 = q2;
         me.L2 = (uint32_t)(sb.Lh & 0xffff) | ((uint32_t)(sb.Ll & 0xffff) << 16);
+        me.rc = (uint32_t)(sb.rot & 0xffff) | ((uint32_t)(sb.cl & 0xffff) << 16);
         me.rec1 = (uint32_t)(sb.rs_off + (int64_t)(q1 - sb.q0) * sb.rec_u4);
         me.rec2 = (uint32_t)(sb.rs_off + (int64_t)(q2 - sb.q0) * sb.rec_u4);
         me.cw1 = (uint32_t)(sb.s1_off + (q1 - sb.q0));

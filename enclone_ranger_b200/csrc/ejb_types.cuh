@@ -76,11 +76,15 @@ struct SubBucket {
     int32_t maxcd;    // stage-1 threshold on the CDR3 distance (superset of join_one.rs:231,286-290)
     int32_t blk0;     // first global 128-row block id
     int32_t n3;       // 3 * (Lh + Ll)  (join_one.rs:499)
-    int32_t owner;    // rank that owns this sub-bucket (multi-GPU sharding)
-    int32_t pad;
-    int32_t n_act;    // leading rows that act as the FIRST row of a pair (== n unless the caller split the sub-bucket by row
-                      // ranges across contexts, ejb_set_row_roles); the rest are columns only
+    int32_t owner;    // rank that owns this sub-bucket (multi-GPU sharding; -1: split over several ranks by row ranges)
+    int32_t r_beg;    // rows [r_beg, n_act) act as the FIRST row of a pair on this context: [0, n) when it owns the whole
+    int32_t n_act;    // sub-bucket, a sub-range when the sub-bucket is split by row ranges over several contexts (in-library
+                      // sharding, or the caller's ejb_set_row_roles), empty when another shard owns it (then it is not packed)
     int32_t raw;      // part of a split sub-bucket: its forest edges are returned without the two-cell filter
+    int32_t rot;      // the concatenated CDR3 is stored ROTATED left by `rot` positions (Hamming distance does not care): plane
+                      // word 0 then holds the 32 positions centred in the heavy junction — the most diverse ones — instead of the
+                      // germline-encoded V end, which makes stage 1's first-word test reject unrelated pairs after one popc
+    int32_t pad2;
 };
 constexpr uint8_t ROLE_COLUMN_ONLY = 1, ROLE_SPLIT = 2;
 // Row record layout (384 B for contigs up to 512 nt).  Per chain m the record is PLANE-MAJOR with a fixed plane order; W4
@@ -105,6 +109,13 @@ __device__ __forceinline__ bool is_acgt_fast(uint32_t b) { return (b & 0xe0u) ==
 constexpr int SEGPL_WORDS = 16;   // segments up to 512 nt (longer ones send their rows to the byte-exact path)
 // bits [0, n) set (n may be <= 0 or >= 32)
 __device__ __forceinline__ uint32_t mask_lt(long long n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << (int)n) - 1u)); }
+// same for a 32-bit n: PTX shr.u32 clamps shift amounts above 31, so all-ones >> (32 - clamp(n, 0, 32)) needs no branches
+__device__ __forceinline__ uint32_t mask_lt32(int n) {
+    uint32_t r;
+    const int sh = 32 - min(max(n, 0), 32);
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(0xffffffffu), "r"(sh));
+    return r;
+}
 // 32 bits of a SEGPL_WORDS-word plane starting at bit index `idx` (bits outside the plane read as 0)
 __device__ __forceinline__ uint32_t plane_bits(const uint32_t* __restrict__ pl, long long idx) {
     const long long wi = idx >> 5;   // floor
@@ -134,9 +145,9 @@ __device__ __forceinline__ RefGeom ref_geom(const int32_t* __restrict__ seglen, 
 }
 // word wi (positions 32 wi .. 32 wi + 31): reference planes and compare mask
 __device__ __forceinline__ void ref_word(const uint32_t* __restrict__ segpl, const RefGeom& G, int wi, uint32_t& rlo, uint32_t& rhi, uint32_t& cm) {
-    const uint32_t inl = mask_lt((long long)G.L - 32 * wi);
-    const uint32_t cmv = mask_lt((long long)G.vr - 32 * wi) & inl;
-    const uint32_t cmj = inl & ~mask_lt(((long long)G.L - G.jr) - 32 * wi) & ~cmv;   // p >= L - jr; the V range has priority
+    const uint32_t inl = mask_lt32(G.L - 32 * wi);
+    const uint32_t cmv = mask_lt32(G.vr - 32 * wi) & inl;
+    const uint32_t cmj = inl & ~mask_lt32((G.L - G.jr) - 32 * wi) & ~cmv;   // p >= L - jr; the V range has priority
     const long long jidx = (long long)32 * wi + G.jshift;
     const uint32_t* vp = segpl + G.vo;
     const uint32_t* jp = segpl + G.jo;

@@ -66,7 +66,8 @@ def _sampled_buckets_vs_oracle(inp, p, res, n_extra, seed, max_rows):
             rows_left -= int(sizes[b])
     rows = np.nonzero(np.isin(bucket, np.array(chosen)))[0]
     os.environ["ORACLE_P1_MEMO"] = "1"   # p1 is a pure function of (k, d, n): same bits, bounded run time on hypermutated clones
-    want = pyoracle.run(p, inp.take_rows(rows).c_ptr(), threads=0)
+    sub = inp.take_rows(rows)            # keep the subset alive while the oracle reads it
+    want = pyoracle.run(p, sub.c_ptr(), threads=0)
     sel = np.nonzero(np.isin(res.edge_k1, rows))[0]
     got = {f: np.asarray(getattr(res, f))[sel] for f in ARRAYS if f.startswith("edge_")}
     want = {k: v for k, v in want.items() if k.startswith("edge_")}
