@@ -155,6 +155,7 @@ class EjbStats(C.Structure):
         ("pairs_distance_computed", C.c_int64),
         ("pairs_distance_full", C.c_int64),
         ("popc_executed_stage1", C.c_int64),
+        ("stage1_flag_skips", C.c_int64),
         ("host_syncs", C.c_int64),
         ("boruvka_iterations", C.c_int64),
         ("p1_cache_slots", C.c_int64),
@@ -300,6 +301,14 @@ def load_join():
         L.ejb_forest_merge.restype = C.c_int
         L.ejb_device_tuples.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.ejb_device_tuples.restype = C.c_int
+        L.ejb_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ejb_set_shard.restype = C.c_int
+        L.ejb_part_forest.argtypes = [C.c_void_p, _i64p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.ejb_part_forest.restype = C.c_int
+        L.ejb_merge_buffers.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.ejb_merge_buffers.restype = C.c_int
+        L.ejb_merge_parts.argtypes = [C.c_void_p, C.c_int64]
+        L.ejb_merge_parts.restype = C.c_int
         L.ejb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
         L.ejb_set_option.restype = C.c_int
         L.ejb_create_ms.argtypes = [C.c_void_p]

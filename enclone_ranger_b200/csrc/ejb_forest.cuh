@@ -363,6 +363,23 @@ __global__ void k_exact_union(DevIn in, const int32_t* __restrict__ first_row, i
     const int f = first_row[in.row_exact[k]];
     if (f != (int)k) uf_union(parent, f, (int)k);
 }
+// rows per exact subclonotype, then the (exact << 32 | row) list of the exacts that own two or more rows: all the host needs
+// for the clonotype_id merge of finish_join (join2.rs:69-84) — about 2 % of the rows instead of a pass over all of them
+__global__ void k_exact_count(DevIn in, int32_t* __restrict__ count) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < in.n_rows) atomicAdd(&count[in.row_exact[k]], 1);
+}
+__global__ void k_multi_rows(DevIn in, const int32_t* __restrict__ count, unsigned long long* __restrict__ out, Counters* ctr) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool multi = k < in.n_rows && count[in.row_exact[k]] >= 2;
+    const unsigned int m = __ballot_sync(0xffffffffu, multi);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long b = 0;
+    if (lane == __ffs(m) - 1) b = atomicAdd(&ctr->n_multi, (unsigned long long)__popc(m));
+    b = __shfl_sync(0xffffffffu, b, __ffs(m) - 1);
+    if (multi) out[b + __popc(m & ((1u << lane) - 1u))] = ((unsigned long long)(uint32_t)in.row_exact[k] << 32) | (unsigned long long)(uint32_t)k;
+}
 __global__ void k_labels(const int32_t* __restrict__ parent, int64_t n, int32_t* __restrict__ labels) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) labels[k] = uf_find_ro(parent, (int)k);

@@ -168,13 +168,15 @@ struct ejb_ctx {
     struct TaskMeta { int32_t unit, r0, r1; };
     std::vector<TaskMeta> task_meta;
     std::vector<unsigned long long> h_unitcand;   // candidates of each task (row range) of the last round, valid even when it overflowed
+    DevBuf d_mergew, d_merget;   // gathered partial forests (multi-GPU merge)
     DevBuf d_tasks, d_units, d_cand, d_slow, d_slowslot, d_surv, d_pass, d_passt, d_roots, d_forest, d_forestt;
-    DevBuf d_deg, d_first, d_labels, d_fkeys, d_fkeys2, d_fidx, d_fidx2;
+    DevBuf d_deg, d_first, d_labels, d_excount, d_multi, d_multi2, d_fkeys, d_fkeys2, d_fidx, d_fidx2;
     DevBuf d_o_k1, d_o_k2, d_o_cd, d_o_nrefs, d_o_sh, d_o_in, d_o_k, d_o_d, d_o_n, d_o_p1, d_o_mult, d_o_score, d_o_err;
     // pair-batch mode (ejb_join_one_batch)
     DevBuf d_bpairs, d_bslots, d_btuples, d_bcnt;
     std::vector<SubBucket> subs;
-    int64_t n_active = 0, n_pos = 0, n_blocks = 0, n_final = 0, n_buckets = 0;
+    int64_t n_active = 0, n_pos = 0, n_blocks = 0, n_final = 0, n_buckets = 0, n_multi = 0, n_part = 0;
+    bool have_part = false;     // a sharded run left its partial forest on the device (ejb_part_forest)
     unsigned long long forest_cap = 0;
     bool prepared = false;      // the packed row store of the uploaded input is resident (ejb_run got at least that far)
     ejb_stats stats;
@@ -582,8 +584,6 @@ int ejb_create(ejb_ctx** out, const int* device_ids, int n_devices) {
     for (int i = 0; i < n_devices; i++) {
         devs[i] = device_ids ? device_ids[i] : i;
         if (devs[i] < 0 || devs[i] >= count) return EJB_ERR_NO_DEVICE;
-        for (int j = 0; j < i; j++)
-            if (devs[j] == devs[i]) return EJB_ERR_INVALID;   // one context per device
     }
     ejb_ctx* c = nullptr;
     int rc = create_one(&c, devs[0]);
@@ -1349,6 +1349,13 @@ int finalize(ejb_ctx* c) {
         launch(c, k_exact_first, nblk(N, 256), 256, din, c->d_first.as<int32_t>());
         launch(c, k_exact_union, nblk(N, 256), 256, din, c->d_first.as<const int32_t>(), c->d_parent.as<int32_t>());
         launch(c, k_labels, nblk(N, 256), 256, c->d_parent.as<const int32_t>(), N, c->d_labels.as<int32_t>());
+        // what the host needs for the clonotype_id merge of its EquivRel replay: the rows of exacts that own several rows
+        CK(c->d_excount.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 4));
+        CK(c->d_multi.ensure((size_t)N * 8));
+        CK(c->d_multi2.ensure((size_t)N * 8));
+        CK(cudaMemsetAsync(c->d_excount.p, 0, (size_t)std::max<int64_t>(din.n_exacts, 1) * 4, st));
+        launch(c, k_exact_count, nblk(N, 256), 256, din, c->d_excount.as<int32_t>());
+        launch(c, k_multi_rows, nblk(N, 256), 256, din, c->d_excount.as<const int32_t>(), c->d_multi.as<unsigned long long>(), c->d_ctr());
     }
     return EJB_OK;
 }
@@ -1359,7 +1366,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
     if (!c) return EJB_ERR_INVALID;
     if (!c->have_input) return fail(c, EJB_ERR_INVALID, "ejb_run without ejb_upload");
     CK(cudaSetDevice(c->device));
-    c->have_run = c->prepared = false;
+    c->have_run = c->prepared = c->have_part = false;
     const double t_wall0 = now_ms();
     memset(&c->stats, 0, sizeof(c->stats));
     c->ev_used = 0;
@@ -1549,11 +1556,14 @@ extern "C" int ejb_run(ejb_ctx* c) {
     CK(cudaGetLastError());
     const Counters& h = *c->h_round.as<Counters>();
     c->n_final = (int64_t)h.n_final;
+    c->n_multi = (int64_t)h.n_multi;
+    c->n_part = (int64_t)h.n_forest;
     c->stats.forest_edges = (int64_t)h.n_forest;
     c->stats.pairs_evaluated = (int64_t)h.pairs_eval;
     c->stats.two_cell_deleted = (int64_t)h.n_two_cell;
     c->stats.stage1_ref_kills = (int64_t)(h.n_s1_kill - h.n_s1_donor);
     c->stats.stage1_donor_kills = (int64_t)h.n_s1_donor;
+    c->stats.stage1_flag_skips = (int64_t)h.n_s1_flag;
     c->stats.stage2_two_ref = (int64_t)h.n_two_ref;
     c->stats.stage2_memo_dead = (int64_t)h.n_memo_dead;
     c->stats.stage2_degr_dead = (int64_t)h.n_degr_dead;
@@ -1607,7 +1617,8 @@ extern "C" int ejb_run(ejb_ctx* c) {
     c->stats.ms_h2d = c->ms_h2d;
     c->stats.h2d_bytes = c->h2d_bytes;
     c->stats.ms_total = now_ms() - t_wall0;
-    c->have_run = true;
+    c->have_run = c->shard_world == 1;
+    c->have_part = c->shard_world > 1;
     return EJB_OK;
 }
 
@@ -1628,7 +1639,7 @@ int ejb_download(ejb_ctx* c, ejb_result* out) {
     // ---- carve the pinned arena: 13 edge arrays + labels + x/y/z + row_exact scratch ----
     const size_t e1 = (size_t)std::max<int64_t>(E, 1), n1 = (size_t)std::max<int64_t>(N, 1);
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t need = 7 * al(e1 * 4) + 2 * al(e1 * 8) + 3 * al(e1 * 8) + al(e1) + 5 * al(n1 * 4) + 4096;
+    const size_t need = 7 * al(e1 * 4) + 2 * al(e1 * 8) + 3 * al(e1 * 8) + al(e1) + 5 * al(n1 * 4) + al(n1 * 8) + 4096;
     if (need > c->h_res_cap) {
         if (c->h_res) cudaFreeHost(c->h_res);
         c->h_res = nullptr;
@@ -1645,7 +1656,9 @@ int ejb_download(ejb_ctx* c, ejb_result* out) {
     double* p1 = (double*)take(e1 * 8); double* mult = (double*)take(e1 * 8); double* score = (double*)take(e1 * 8);
     uint8_t* err = (uint8_t*)take(e1);
     int32_t* labels = (int32_t*)take(n1 * 4); int32_t* ex = (int32_t*)take(n1 * 4); int32_t* ey = (int32_t*)take(n1 * 4); int32_t* ez = (int32_t*)take(n1 * 4);
-    int32_t* row_exact = (int32_t*)take(n1 * 4);
+    // scratch for the replay: bucket starts + the (exact << 32 | row) list of multi-row exacts (together never more than n1 * 4 + n1 * 8 bytes)
+    int32_t* bstart = (int32_t*)take(n1 * 4);
+    uint64_t* multi = (uint64_t*)take(n1 * 8);
     auto get = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
         if (bytes == 0) return cudaSuccess;
         c->stats.d2h_bytes += (int64_t)bytes;
@@ -1656,7 +1669,13 @@ int ejb_download(ejb_ctx* c, ejb_result* out) {
         CK(get(k1, c->d_o_k1.p, (size_t)E * 4));
         CK(get(k2, c->d_o_k2.p, (size_t)E * 4));
     }
-    if (N > 0) CK(get(row_exact, c->din.row_exact, (size_t)N * 4));
+    const int64_t NB = c->n_buckets, NM = c->n_multi;
+    if (NB > 0) CK(get(bstart, c->d_bstart.p, (size_t)NB * 4));
+    if (NM > 0) {
+        int rc = cub_sort_keys64(c, c->d_multi.as<uint64_t>(), c->d_multi2.as<uint64_t>(), NM);
+        if (rc) return rc;
+        CK(get(multi, c->d_multi2.p, (size_t)NM * 8));
+    }
     cudaEvent_t ev_edges = c->ev();
     CK(cudaEventRecord(ev_edges, st));
     if (E > 0) {
@@ -1671,10 +1690,11 @@ int ejb_download(ejb_ctx* c, ejb_result* out) {
     // replay into the reference's EquivRel (join2.rs:45-54, 69-84) so that x/y/z match from_raw; the state is built in place
     // in the result arena
     const double t1 = now_ms();
-    if (N > 0) {   // sharded contexts: the state of the local edges only
-        ejbhost::EquivRel eq((int32_t)N, ex, ey, ez);
-        ejbhost::replay_edges(eq, k1, k2, E);
-        ejbhost::finish_join_merge(eq, row_exact, N, c->din.n_exacts);
+    if (N > 0) {
+        ejbhost::EquivRel eq(ex, ey, ez);
+        const int threads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+        ejbhost::replay_edges_parallel(eq, N, k1, k2, E, bstart, NB, threads);
+        ejbhost::finish_join_merge_list(eq, multi, NM);
     }
     c->stats.ms_replay = now_ms() - t1;
     CK(cudaStreamSynchronize(st));
@@ -1861,9 +1881,200 @@ int ejb_equiv_replay(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64
 
 }  // extern "C"
 
+// ================================================================================================
+// Multi-GPU: partial forests of sharded runs, merged on one context
+// ================================================================================================
+extern "C" {
+
+// Partial forest of the last sharded ejb_run (ejb_set_shard with world > 1): device pointers, valid until the next run.
+int ejb_part_forest(ejb_ctx* c, int64_t* n_edges, const unsigned long long** d_edges, const void** d_tuples) {
+    if (!c) return EJB_ERR_INVALID;
+    if (!c->have_part) return fail(c, EJB_ERR_INVALID, "ejb_part_forest without a sharded ejb_run");
+    if (n_edges) *n_edges = c->n_part;
+    if (d_edges) *d_edges = c->d_forest.as<const unsigned long long>();
+    if (d_tuples) *d_tuples = c->d_forestt.p;
+    return EJB_OK;
+}
+
+// Device buffers (on the merging context) that receive the concatenated partial forests of ALL parts, `total` entries:
+// 8-byte edge weights and 24-byte tuples.  The caller fills them (NCCL gather, peer copies), then calls ejb_merge_parts.
+int ejb_merge_buffers(ejb_ctx* c, int64_t total, unsigned long long** d_edges, void** d_tuples) {
+    if (!c || total < 0) return EJB_ERR_INVALID;
+    if (!c->have_part) return fail(c, EJB_ERR_INVALID, "ejb_merge_buffers without a sharded ejb_run on the merging context");
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)std::max<int64_t>(total, 1);
+    CK(c->d_mergew.ensure(n * 8));
+    CK(c->d_merget.ensure(n * sizeof(PassTuple)));
+    if (d_edges) *d_edges = c->d_mergew.as<unsigned long long>();
+    if (d_tuples) *d_tuples = c->d_merget.p;
+    return EJB_OK;
+}
+
+// Merge: the gathered edges are the union of the parts' spanning forests.  Sub-buckets that were not split contribute disjoint
+// forests (every edge stays); the parts of a split sub-bucket overlap, and the lexicographic spanning forest of the whole
+// sub-bucket is the minimum spanning forest of the union of the partial forests.  One Boruvka pass over all gathered edges on a
+// fresh union-find computes both at once; then the ordinary finalize runs (two-cell filter on the merged forest, ordering,
+// PotentialJoin members, clonotype_id unions, labels).  ejb_download returns the result of the WHOLE join.
+int ejb_merge_parts(ejb_ctx* c, int64_t total) {
+    if (!c || total < 0) return EJB_ERR_INVALID;
+    if (!c->have_part) return fail(c, EJB_ERR_INVALID, "ejb_merge_parts without a sharded ejb_run on the merging context");
+    CK(cudaSetDevice(c->device));
+    const double t0 = now_ms();
+    const int64_t N = c->din.n_rows;
+    cudaStream_t st = c->stream;
+    if ((unsigned long long)total > c->forest_cap * 64ull) return fail(c, EJB_ERR_INVALID, "more gathered edges than the parts of %lld rows can hold", (long long)N);
+    cudaEvent_t e0 = c->ev(), e1 = c->ev();
+    CK(cudaEventRecord(e0, st));
+    // fresh round counters, forest and final counts; the union-find starts from singletons
+    char* const rbase = c->d_round.as<char>();
+    CK(cudaMemsetAsync(rbase, 0, offsetof(Counters, round_end), st));
+    CK(cudaMemsetAsync(CTR_FIELD(n_forest), 0, 8, st));
+    CK(cudaMemsetAsync(CTR_FIELD(n_final), 0, 8, st));
+    CK(cudaMemsetAsync(CTR_FIELD(n_two_cell), 0, 8, st));
+    CK(cudaMemsetAsync(CTR_FIELD(n_multi), 0, 8, st));
+    const unsigned long long tot = (unsigned long long)total;
+    CK(cudaMemcpyAsync(CTR_FIELD(n_pass), &tot, 8, cudaMemcpyHostToDevice, st));
+    if (N > 0) launch(c, k_init_parent, nblk(N, 256), 256, c->d_parent.as<int32_t>(), N);
+    CK(c->d_roots.ensure((size_t)std::max<int64_t>(total, 1) * 8));
+    if (c->p1_count > c->p1_cap / 8) {
+        int rc = p1_cache_grow(c);
+        if (rc) return rc;
+    }
+    if (total > 0) {
+        ForestArgs A;
+        A.pass_w = c->d_mergew.as<unsigned long long>();
+        A.pass_t = c->d_merget.as<PassTuple>();
+        A.n_pass_p = CTR_FIELD(n_pass);
+        A.cap = (unsigned long long)total;
+        A.parent = c->d_parent.as<int32_t>();
+        A.best = c->d_best.as<unsigned long long>();
+        A.roots = c->d_roots.as<int2>();
+        A.forest = c->d_forest.as<unsigned long long>();
+        A.forest_t = c->d_forestt.as<PassTuple>();
+        A.forest_cap = c->forest_cap;
+        A.ctr = c->d_ctr();
+        A.bar = c->d_bar.as<unsigned int>();
+        A.rowq = c->d_m_row.as<int32_t>();
+        A.n_pos = c->n_pos;
+        A.labq = c->d_labq.as<int32_t>();
+        A.subs = c->d_subs.as<SubBucket>();
+        A.blk_lab = c->d_blklab.as<int32_t>();
+        A.blk_sub = c->d_blksub.as<int32_t>();
+        A.n_blocks = (int)c->n_blocks;
+        CK(cudaMemsetAsync(c->d_bar.p, 0, 4, st));
+        void* args[] = {&A};
+        CK(cudaLaunchCooperativeKernel((const void*)k_forest_round, dim3((unsigned int)c->coop_grid), dim3(256), args, 0, st));
+        c->stats.kernel_launches++;
+        // p1 of every merged edge: this context's cache only holds the keys of its own part
+        P1Cache pc;
+        pc.keys = c->d_p1_keys.as<unsigned long long>();
+        pc.vals = c->d_p1_vals.as<double>();
+        pc.newslots = c->d_p1_new.as<uint32_t>();
+        pc.cap_mask = c->p1_cap - 1;
+        launch(c, k_p1_request_forest, c->sm_count * 8, 256, c->d_forest.as<const unsigned long long>(), c->d_forestt.as<const PassTuple>(),
+               (const unsigned long long*)CTR_FIELD(n_forest), c->din, pc, c->d_ctr());
+        launch(c, k_p1, c->sm_count * 8, 256, pc, c->d_sr.as<const dd_t>(), (const unsigned long long*)CTR_FIELD(n_newkeys), c->d_ctr());
+    }
+    int rc = finalize(c);
+    if (rc) return rc;
+    CK(cudaEventRecord(e1, st));
+    CK(c->h_round.ensure(sizeof(Counters)));
+    CK(cudaMemcpyAsync(c->h_round.p, c->d_round.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    rc = sync_stream(c);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    const Counters& h = *c->h_round.as<Counters>();
+    if (h.p1_full) return fail(c, EJB_ERR_OOM, "p1 cache full during the merge");
+    if (h.overflow) return fail(c, EJB_ERR_CUDA, "forest buffer overflow during the merge");
+    if (h.alive_it[BOR_MAX_ITERS]) return fail(c, EJB_ERR_CUDA, "merge forest did not converge");
+    c->p1_count += h.n_newkeys;
+    c->n_final = (int64_t)h.n_final;
+    c->n_multi = (int64_t)h.n_multi;
+    c->stats.forest_edges = (int64_t)h.n_forest;
+    c->stats.two_cell_deleted = (int64_t)h.n_two_cell;
+    c->stats.joins = c->n_final;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->stats.ms_merge = ms;
+    c->stats.ms_device_total += ms;
+    (void)t0;
+    c->have_run = true;
+    return EJB_OK;
+}
+
+}  // extern "C"
+
 namespace {
+// ejb_create with n_devices > 1: one worker thread per GPU uploads the input and joins its shard; the partial forests are
+// copied GPU-to-GPU into the first context, merged and finalized there; the caller sees ONE result (ejb_join is unchanged).
 int multi_join(ejb_ctx* c, const ejb_params* p, const ejb_input* in, ejb_result* out) {
-    (void)p; (void)in; (void)out;
-    return fail(c, EJB_ERR_UNSUPPORTED, "multi-device join not built yet");
+    const double t0 = now_ms();
+    std::vector<ejb_ctx*> ctxs;
+    ctxs.push_back(c);
+    for (ejb_ctx* x : c->peers) ctxs.push_back(x);
+    const int n = (int)ctxs.size();
+    std::vector<int> rcs((size_t)n, 0);
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; i++)
+        th.emplace_back([&, i] {
+            ejb_ctx* x = ctxs[i];
+            x->shard_rank = i;
+            x->shard_world = n;
+            x->arena_base = c->arena_base;
+            x->arena_bytes = c->arena_bytes;
+            int rc = ejb_upload(x, p, in);
+            if (!rc) rc = ejb_run(x);
+            rcs[i] = rc;
+        });
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; i++)
+        if (rcs[i]) {
+            if (i > 0) c->err = ctxs[i]->err;
+            return rcs[i];
+        }
+    const double t1 = now_ms();
+    int64_t total = 0;
+    for (ejb_ctx* x : ctxs) total += x->n_part;
+    unsigned long long* dw = nullptr;
+    void* dt = nullptr;
+    int rc = ejb_merge_buffers(c, total, &dw, &dt);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    int64_t off = 0;
+    for (ejb_ctx* x : ctxs) {
+        if (x->n_part > 0) {
+            CK(cudaMemcpyPeerAsync(dw + off, c->device, x->d_forest.p, x->device, (size_t)x->n_part * 8, c->stream));
+            CK(cudaMemcpyPeerAsync(reinterpret_cast<char*>(dt) + (size_t)off * sizeof(PassTuple), c->device, x->d_forestt.p, x->device,
+                                   (size_t)x->n_part * sizeof(PassTuple), c->stream));
+        }
+        off += x->n_part;
+    }
+    rc = ejb_merge_parts(c, total);
+    if (rc) return rc;
+    // whole-join statistics: the work counters are sums over the parts, the times those of the slowest part
+    ejb_stats agg = c->stats;
+    for (int i = 1; i < n; i++) {
+        const ejb_stats& s = ctxs[i]->stats;
+        agg.pairs_scored += s.pairs_scored; agg.pairs_evaluated += s.pairs_evaluated; agg.stage1_candidates += s.stage1_candidates;
+        agg.stage2_slow += s.stage2_slow; agg.stage2_survivors += s.stage2_survivors; agg.pass_edges += s.pass_edges;
+        agg.p1_unique += s.p1_unique; agg.kernel_launches += s.kernel_launches; agg.h2d_bytes += s.h2d_bytes;
+        agg.stage1_ref_kills += s.stage1_ref_kills; agg.stage1_flag_skips += s.stage1_flag_skips; agg.stage1_donor_kills += s.stage1_donor_kills; agg.stage2_two_ref += s.stage2_two_ref;
+        agg.pairs_distance_computed += s.pairs_distance_computed; agg.pairs_distance_full += s.pairs_distance_full;
+        agg.popc_executed_stage1 += s.popc_executed_stage1; agg.overflow_retries += s.overflow_retries;
+        agg.rounds = std::max(agg.rounds, s.rounds); agg.host_syncs = std::max(agg.host_syncs, s.host_syncs);
+        agg.ms_device_total = std::max(agg.ms_device_total, s.ms_device_total + c->stats.ms_merge);
+        agg.ms_pack = std::max(agg.ms_pack, s.ms_pack); agg.ms_stage1 = std::max(agg.ms_stage1, s.ms_stage1);
+        agg.ms_stage2 = std::max(agg.ms_stage2, s.ms_stage2); agg.ms_forest = std::max(agg.ms_forest, s.ms_forest);
+        agg.ms_h2d = std::max(agg.ms_h2d, s.ms_h2d);
+    }
+    agg.n_devices = n;
+    c->stats = agg;
+    c->stats.ms_partition = 0.0;
+    rc = ejb_download(c, out);
+    if (rc) return rc;
+    out->stats.ms_total = now_ms() - t0;
+    out->stats.ms_merge = now_ms() - t1 - out->stats.ms_d2h - out->stats.ms_replay;
+    c->stats = out->stats;
+    return EJB_OK;
 }
 }  // namespace

@@ -71,15 +71,7 @@ constexpr uint32_t RF_DEAD_VS_DOM = 1u;   // deadq[q] == dominant tag: the row f
 constexpr uint32_t RF_HAS_DOM = 2u;       // tagq[q]  == dominant tag
 constexpr uint32_t RF_FOREIGN_DON = 4u;   // donor set non-empty and different from the dominant (non-empty) donor set
 constexpr uint32_t RF_DOM_DON = 8u;       // donor set == dominant (non-empty) donor set
-// pair rejected by the flags alone?  (dead-vs-dominant x has-dominant, foreign-donor x dominant-donor, either way round)
-__device__ __forceinline__ bool flag_kill(uint32_t fr, uint32_t fc, unsigned int& donor_kills, unsigned int& flag_kills) {
-    const uint32_t g = ((fr & 5u) << 1) | ((fr & 10u) >> 1);
-    const uint32_t k = g & fc;
-    if (!k) return false;
-    flag_kills++;
-    if (!(k & 3u)) donor_kills++;
-    return true;
-}
+// A pair is rejected by the flags alone when: dead-vs-dominant x has-dominant, or foreign-donor x dominant-donor, either way round.
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -201,6 +193,19 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         runi = __shfl_sync(0xffffffffu, runi, lane);   // identity shuffle: keeps the value in a register (ptxas otherwise re-derives it
                                                        // from the eight labels for every column, 14 instructions instead of none)
     }
+    // row flags of the thread's eight rows as four byte masks (bit i = row i): a column's flag nibble selects, with four
+    // operations, the rows whose pair with that column join_one rejects without looking at the sequences (flag_kill)
+    uint32_t r_dead8 = 0, r_dom8 = 0, r_fd8 = 0, r_dd8 = 0;
+    if (TAGS) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t f = s_row[FLAG0 + i * 16 + ty];
+            r_dead8 |= ((f >> 0) & 1u) << i;
+            r_dom8 |= ((f >> 1) & 1u) << i;
+            r_fd8 |= ((f >> 2) & 1u) << i;
+            r_dd8 |= ((f >> 3) & 1u) << i;
+        }
+    }
     const int row_lo = t.row_lo;
     const int row_lim = min(sb.n - rb * TILE, t.row_hi);  // valid local rows are row_lo <= r < row_lim
     const int maxcd = sb.maxcd;
@@ -208,6 +213,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     unsigned long long evaluated = 0;                 // thread 0 only
     unsigned int donor_kills = 0, tag_kills = 0;      // per thread
     unsigned int n_first = 0, n_full = 0;             // per lane: first-word / remaining-word evaluations
+    unsigned int n_flag = 0;                          // per lane: pairs of computed columns rejected by the row flags alone
     unsigned int wq = 0;                              // warp-uniform: entries in this warp's queue
     unsigned long long w_total = 0;                   // warp-uniform: candidates this warp emitted
     uint2* const myq = s_q[warp];
@@ -254,15 +260,24 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
             if (RUNI && __all_sync(0xffffffffu, clab == runi)) continue;   // 16 rows x 16 columns of one class: one vote instead of eight
             // first word of the eight pairs (the 32 most diverse CDR3 positions, SubBucket::rot): is any pair still a possible candidate?
             const uint32_t cl0 = pc[0], ch0 = pc[W1 * TILE];
+            uint32_t kill8 = 0;   // bit i: the pair (row i, this column) is rejected by the row flags (reference set / donor set)
+            if (TAGS) {
+                const uint32_t fc = pc[FLAG0];
+                kill8 = ((fc & RF_HAS_DOM) ? r_dead8 : 0u) | ((fc & RF_DEAD_VS_DOM) ? r_dom8 : 0u) | ((fc & RF_DOM_DON) ? r_fd8 : 0u) |
+                        ((fc & RF_FOREIGN_DON) ? r_dd8 : 0u);
+                n_flag += __popc(kill8);
+            }
             bool any = false;
             if (full) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) any |= (__popc((rl[i][0] ^ cl0) | (rh[i][0] ^ ch0)) <= maxcd) & (rlab[i] != clab);
+                for (int i = 0; i < 8; i++)
+                    any |= (__popc((rl[i][0] ^ cl0) | (rh[i][0] ^ ch0)) <= maxcd) & (rlab[i] != clab) & !((kill8 >> i) & 1u);
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int r = i * 16 + ty;
-                    any |= (__popc((rl[i][0] ^ cl0) | (rh[i][0] ^ ch0)) <= maxcd) & (rlab[i] != clab) & (r >= row_lo) & (r < row_lim) & (c < col_lim) & (!diag | (r < c));
+                    any |= (__popc((rl[i][0] ^ cl0) | (rh[i][0] ^ ch0)) <= maxcd) & (rlab[i] != clab) & !((kill8 >> i) & 1u) & (r >= row_lo) & (r < row_lim) &
+                           (c < col_lim) & (!diag | (r < c));
                 }
             }
             n_first += 8;
@@ -278,23 +293,20 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
             for (int i = 0; i < 8; i++) {
                 const int r = i * 16 + ty;
                 const int p0 = __popc((rl[i][0] ^ cl[0]) | (rh[i][0] ^ chh[0]));
-                bool hit = p0 <= maxcd && rlab[i] != clab;
+                bool hit = p0 <= maxcd && rlab[i] != clab && !((kill8 >> i) & 1u);
                 if (!full) hit = hit && r >= row_lo && r < row_lim && c < col_lim && (!diag || r < c);
                 if (!__any_sync(0xffffffffu, hit)) continue;
                 if (W1 > 1) {
                     n_full++;
                     hit = hit && p0 + cdr3_rest<W1>(rl[i], rh[i], cl, chh) <= maxcd;
                 }
-                if (TAGS && hit) {
-                    if (flag_kill(s_row[FLAG0 + r], sc[FLAG0 + c], donor_kills, tag_kills)) hit = false;
-                    else {
-                        const unsigned long long dr = rt[2 * TILE + r], dc = ct[2 * TILE + c];
-                        const bool donors = dr != 0 && dc != 0 && dr != dc;
-                        if (donors || rt[TILE + r] == ct[c] || ct[TILE + c] == rt[r]) {
-                            hit = false;
-                            tag_kills++;
-                            donor_kills += donors;
-                        }
+                if (TAGS && hit) {   // the exact 64-bit tests behind the flags (rows off the dominant reference / donor set)
+                    const unsigned long long dr = rt[2 * TILE + r], dc = ct[2 * TILE + c];
+                    const bool donors = dr != 0 && dc != 0 && dr != dc;
+                    if (donors || rt[TILE + r] == ct[c] || ct[TILE + c] == rt[r]) {
+                        hit = false;
+                        tag_kills++;
+                        donor_kills += donors;
                     }
                 }
                 const unsigned int m = __ballot_sync(0xffffffffu, hit);
@@ -328,6 +340,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         n_first += __shfl_xor_sync(0xffffffffu, n_first, o);
         n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
         if (TAGS) {
+            n_flag += __shfl_xor_sync(0xffffffffu, n_flag, o);
             donor_kills += __shfl_xor_sync(0xffffffffu, donor_kills, o);
             tag_kills += __shfl_xor_sync(0xffffffffu, tag_kills, o);
         }
@@ -335,6 +348,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     if (lane == 0) {
         atomicAdd(&ctr->s1_first, (unsigned long long)n_first);
         if (n_full) atomicAdd(&ctr->s1_full, (unsigned long long)n_full);
+        if (TAGS && n_flag) atomicAdd(&ctr->n_s1_flag, (unsigned long long)n_flag);
         if (TAGS && donor_kills) atomicAdd(&ctr->n_s1_donor, (unsigned long long)donor_kills);
         if (TAGS && tag_kills) atomicAdd(&ctr->n_s1_kill, (unsigned long long)tag_kills);   // n_s1_kill counts every kind
     }

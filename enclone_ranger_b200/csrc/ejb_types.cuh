@@ -220,6 +220,7 @@ struct Counters {       // device-side counters, one instance per context
     // ---- per run ----
     unsigned long long pairs_eval, n_forest;
     unsigned long long n_two_cell, n_errflag_range, n_errflag_panic, n_final;
+    unsigned long long n_multi;       // rows whose exact subclonotype owns two or more rows (finish_join's clonotype_id merge, join2.rs:69-84)
     unsigned long long p1_total;      // keys ever inserted into the p1 cache since it was last cleared
     unsigned long long p1_full;       // a probe sequence of the p1 cache ran through the whole table (must not happen: the host grows it)
     unsigned long long s1_first;      // stage 1: lane-pairs whose first CDR3 word went through XOR + popc
@@ -227,6 +228,7 @@ struct Counters {       // device-side counters, one instance per context
     unsigned long long bor_iters;     // Boruvka iterations over all rounds
     unsigned long long n_s1_kill;     // stage-1 hits dropped: known dead against the other's reference set, or different donor sets
     unsigned long long n_s1_donor;    // ... of which for the donor sets
+    unsigned long long n_s1_flag;     // stage-1 pairs skipped on the 4-bit row flags alone, before any distance (not necessarily CDR3-close)
     unsigned long long n_two_ref;     // stage-2a candidates with two reference sets
     unsigned long long n_memo_dead;   // ... of which rejected on memoised totals (phase 0)
     unsigned long long n_degr_dead;   // ... of which rejected by the degradation test on freshly computed totals

@@ -8,6 +8,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -24,8 +25,10 @@ struct EquivRel {
         z = y + n;
         init(n);
     }
-    void init(int32_t n) {
-        for (int32_t i = 0; i < n; i++) {
+    EquivRel(int32_t* xs, int32_t* ys, int32_t* zs) : x(xs), y(ys), z(zs) {}   // arrays initialised by the caller (init_range)
+    void init(int32_t n) { init_range(0, n); }
+    void init_range(int32_t lo, int32_t hi) {
+        for (int32_t i = lo; i < hi; i++) {
             x[i] = y[i] = i;
             z[i] = 1;
         }
@@ -72,6 +75,25 @@ inline void finish_join_merge(EquivRel& eq, const int32_t* row_exact, int64_t n_
     }
 }
 
+// The same merge from the device-built list of the rows whose clonotype_id owns two or more rows, as (id << 32 | row) sorted
+// ascending: identical join sequence (ids ascending, class ids ascending inside an id), O(list) instead of O(rows).
+inline void finish_join_merge_list(EquivRel& eq, const uint64_t* multi, int64_t n_multi) {
+    // the class ids are those BEFORE the first of these joins (join2.rs:70-74 collects them all, then joins)
+    std::vector<int32_t> cls((size_t)n_multi);
+    for (int64_t k = 0; k < n_multi; k++) cls[(size_t)k] = eq.class_id((int32_t)(multi[k] & 0xffffffffu));
+    int64_t i = 0;
+    while (i < n_multi) {
+        int64_t j = i + 1;
+        while (j < n_multi && (multi[j] >> 32) == (multi[i] >> 32)) j++;
+        std::sort(cls.begin() + i, cls.begin() + j);
+        for (int64_t k = i; k + 1 < j; k++) eq.join(cls[(size_t)k], cls[(size_t)k + 1]);
+        i = j;
+    }
+}
+
+// Parallel replay: edges never cross lens buckets and the rows of a bucket are contiguous, so edge ranges cut at bucket
+// boundaries touch disjoint parts of x / y / z and can be replayed by different threads; the state is the sequential one.
+inline void replay_edges(EquivRel& eq, const int32_t* k1, const int32_t* k2, int64_t n_edges);
 // Replay of an ordered edge list (join2.rs:45-54).  The walk is bound by the latency of the scattered x / y / z reads, so the
 // entries of the edges a few steps ahead are prefetched.
 inline void replay_edges(EquivRel& eq, const int32_t* k1, const int32_t* k2, int64_t n_edges) {
@@ -86,6 +108,41 @@ inline void replay_edges(EquivRel& eq, const int32_t* k1, const int32_t* k2, int
         }
         eq.join(k1[i], k2[i]);
     }
+}
+
+inline void replay_edges_parallel(EquivRel& eq, int64_t n_rows, const int32_t* k1, const int32_t* k2, int64_t n_edges, const int32_t* bucket_start,
+                                  int64_t n_buckets, int threads) {
+    if (threads <= 1 || n_buckets < 2 || n_rows < 400000) {
+        eq.init((int32_t)n_rows);
+        replay_edges(eq, k1, k2, n_edges);
+        return;
+    }
+    // thread t owns the rows [cut[t], cut[t+1]) (cut at bucket starts, balanced by edge count) and the edges whose k1 lies there
+    std::vector<int64_t> row_cut((size_t)threads + 1, 0), edge_cut((size_t)threads + 1, 0);
+    row_cut[(size_t)threads] = n_rows;
+    edge_cut[(size_t)threads] = n_edges;
+    for (int t = 1; t < threads; t++) {
+        int64_t r;
+        if (n_edges > 0) {
+            const int64_t e = n_edges * t / threads;
+            const int32_t row = k1[e];
+            const int32_t* b = std::upper_bound(bucket_start, bucket_start + n_buckets, row);   // first bucket starting after `row`
+            r = (b == bucket_start) ? 0 : *(b - 1);
+        } else {
+            const int32_t* b = std::upper_bound(bucket_start, bucket_start + n_buckets, (int32_t)(n_rows * t / threads));
+            r = (b == bucket_start) ? 0 : *(b - 1);
+        }
+        r = std::max<int64_t>(r, row_cut[(size_t)t - 1]);
+        row_cut[(size_t)t] = r;
+        edge_cut[(size_t)t] = std::lower_bound(k1, k1 + n_edges, (int32_t)r) - k1;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++)
+        th.emplace_back([&, t] {
+            eq.init_range((int32_t)row_cut[(size_t)t], (int32_t)row_cut[(size_t)t + 1]);
+            replay_edges(eq, k1 + edge_cut[(size_t)t], k2 + edge_cut[(size_t)t], edge_cut[(size_t)t + 1] - edge_cut[(size_t)t]);
+        });
+    for (auto& x : th) x.join();
 }
 
 }  // namespace ejbhost

@@ -198,6 +198,46 @@ class JoinContext:
         r = np.ascontiguousarray(roles, dtype=np.uint8)
         self._ck(self.L.ejb_set_row_roles(self.h, r.ctypes.data_as(C.POINTER(C.c_uint8)), r.size))
 
+    # --- sharded join: every context holds the whole input, joins its share, one context merges (multi-GPU) ---
+    def set_shard(self, rank, world):
+        self._ck(self.L.ejb_set_shard(self.h, int(rank), int(world)))
+
+    def _dev_tensor(self, ptr, n, typestr):
+        import torch
+
+        class _Dev:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Dev(ptr, n), device=f"cuda:{self.device}")
+
+    def part_forest(self):
+        """Partial forest of the last sharded run(): (n, edges int64[n] = (k1 << 28) | k2 with GLOBAL row ids, tuples uint8[24 n])
+        as zero-copy torch CUDA tensors (valid until the next run)."""
+        import torch
+        n, e, t = C.c_int64(), C.c_void_p(), C.c_void_p()
+        self._ck(self.L.ejb_part_forest(self.h, C.byref(n), C.byref(e), C.byref(t)))
+        if n.value == 0:
+            dev = f"cuda:{self.device}"
+            return 0, torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.uint8, device=dev)
+        return n.value, self._dev_tensor(e.value, n.value, "<i8"), self._dev_tensor(t.value, 24 * n.value, "|u1")
+
+    def merge_buffers(self, total):
+        """Device buffers of the merging context for the concatenated partial forests (edges int64[total], tuples uint8[24 total])."""
+        import torch
+        e, t = C.c_void_p(), C.c_void_p()
+        self._ck(self.L.ejb_merge_buffers(self.h, int(total), C.byref(e), C.byref(t)))
+        if total == 0:
+            dev = f"cuda:{self.device}"
+            return torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.uint8, device=dev)
+        return self._dev_tensor(e.value, int(total), "<i8"), self._dev_tensor(t.value, 24 * int(total), "|u1")
+
+    def merge_parts(self, total):
+        """Forest of the gathered partial forests + finalize on this context; download() then returns the WHOLE join."""
+        self._ck(self.L.ejb_merge_parts(self.h, int(total)))
+        s = EjbStats()
+        self.L.ejb_last_stats(self.h, C.byref(s))
+        return s.as_dict()
+
     def device_tuples(self):
         """(cd, nrefs, shares[2n]) of the last run()'s edges as zero-copy torch CUDA tensors."""
         import torch

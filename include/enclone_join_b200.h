@@ -223,6 +223,9 @@ typedef struct ejb_stats {
     int64_t pairs_distance_full;     /* ... of which the remaining CDR3 words were evaluated too (some lane of the warp was
                                         still within max distance after the first word)                         */
     int64_t popc_executed_stage1;    /* 32-bit popc lane-operations stage 1 executed                              */
+    int64_t stage1_flag_skips;  /* pairs stage 1 skipped on the per-row flag nibbles alone (row known dead against the sub-bucket's
+                                   dominant reference set x row carrying it; foreign x dominant donor set), BEFORE any distance:
+                                   join_one rejects them whatever their CDR3s (join_one.rs:301-323, 434-440)     */
     int64_t host_syncs;         /* stream synchronisations of this ejb_run                                      */
     int64_t boruvka_iterations; /* forest iterations over all rounds (device-side loop, no read-back)           */
     int64_t p1_cache_slots;     /* current size of the device p1 hash                                           */
@@ -316,6 +319,21 @@ int ejb_measure_peaks(ejb_ctx* ctx, double* popc_per_s, double* lop3_per_s, doub
  * ejb_download returns only their edges (labels/eq_* then describe the local edges only); the
  * caller concatenates the per-rank edge lists, sorts them by (k1, k2) and calls ejb_equiv_replay. */
 int ejb_set_shard(ejb_ctx* ctx, int rank, int world);
+
+/* Sharded join across several contexts (one per GPU; one process per GPU under torchrun, or the worker threads of a context
+ * created with n_devices > 1).  EVERY context uploads the whole input and, after ejb_set_shard(rank, world), ejb_run joins only
+ * its share: whole sub-buckets by longest-processing-time assignment on a pair-count cost model, the heaviest sub-buckets cut
+ * into row ranges (identical, deterministic assignment on every rank; no collective on the data path).  A sharded ejb_run ends
+ * before the finalize step and leaves its PARTIAL FOREST on the device:
+ *   ejb_part_forest    -> device pointers to the part's edges (8-byte weights (k1 << 28) | k2, global row ids) and 24-byte tuples
+ *   ejb_merge_buffers  -> on the merging context (any rank that also ran its part): device buffers for the concatenation of all
+ *                         parts; the caller fills them GPU-to-GPU (NCCL gather, peer copies)
+ *   ejb_merge_parts    -> forest of the partial forests (Kruskal of a union of graphs == Kruskal of the union of their forests),
+ *                         two-cell filter on the merged forest, ordering, PotentialJoin members, labels
+ *   ejb_download       -> edges + EquivRel of the WHOLE join.                                                               */
+int ejb_part_forest(ejb_ctx* ctx, int64_t* n_edges, const unsigned long long** d_edges, const void** d_tuples);
+int ejb_merge_buffers(ejb_ctx* ctx, int64_t total_edges, unsigned long long** d_edges, void** d_tuples);
+int ejb_merge_parts(ejb_ctx* ctx, int64_t total_edges);
 
 /* Input arena.  Every host->device copy pays a fixed setup cost (about 0.1 ms on PCIe Gen5 here), so ~36 separate input
  * arrays upload at half the bandwidth of one large copy.  A caller that flattens its records into ONE page-locked

@@ -108,24 +108,64 @@ def test_p1_kernel_bit_exact(gpu_ctx):
     assert f"{got[2]:.7f}" == "0.0005953"   # stirling_numbers/src/lib.rs:315
 
 
-def test_sharded_ranks_union_to_the_full_result():
-    """Two 'ranks' (run back to back on one GPU) own disjoint sub-buckets; their edge lists merge to the
-    single-GPU / oracle result."""
-    from enclone_ranger_b200.multi import merge_edge_parts, EDGE_FIELDS
-    rep = E.generate(1, n_cells=30000, seed=17)
+def _sharded_join(p, inp, world, cand_cap=1 << 23):
+    """`world` contexts (here: all on one GPU, run back to back) each upload the whole input and join their shard; the partial
+    forests are concatenated in the first context's merge buffers and merged there."""
+    import torch
+    ctxs = [E.JoinContext(rank=r, world=world, cand_cap=cand_cap) for r in range(world)]
+    try:
+        parts, pairs = [], 0
+        for c in ctxs:
+            c.upload(p, inp)
+            st = c.run()
+            pairs += st["pairs_scored"]
+            parts.append(c.part_forest())
+        total = sum(n for n, _, _ in parts)
+        ew, tw = ctxs[0].merge_buffers(total)
+        off = 0
+        for n, e, t in parts:
+            ew[off:off + n].copy_(e)
+            tw[24 * off:24 * (off + n)].copy_(t)
+            off += n
+        torch.cuda.synchronize()
+        ctxs[0].merge_parts(total)
+        return ctxs[0].download(), pairs, [n for n, _, _ in parts]
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.parametrize("config,cells,world,seed", [(1, 30000, 3, 17), (1, 60000, 8, 32), (3, 30000, 4, 33), (2, 100000, 2, 5)])
+def test_sharded_contexts_merge_to_the_full_result(config, cells, world, seed):
+    """In-library sharding (ejb_set_shard): whole sub-buckets by LPT, the heaviest cut into row ranges; the merge (forest of
+    the partial forests, two-cell filter, finalize) must give the oracle's edges, tuples and EquivRel of the WHOLE join."""
+    rep = E.generate(config, n_cells=cells, seed=seed)
+    inp = rep.to_join_input()
+    p = E.default_params(bool(rep.config.is_bcr))
+    want = pyoracle.run(p, inp.c_ptr(), threads=0)
+    got, pairs, sizes = _sharded_join(p, inp.to_packed().to_packed_cdr3(), world)
+    assert pairs == want["pairs_scored"], "the shards' pair domains must partition the whole domain"
+    assert_same_result(got, want, f"config {config} sharded x{world}")
+    assert np.array_equal(got.labels, want["labels"])
+    if world == 8:
+        assert sum(sizes) > len(want["edge_k1"]) + want["two_cell_deleted"], "split sub-buckets: the partial forests overlap"
+
+
+def test_multi_device_context_single_call(gpu_ctx):
+    """ejb_create with n_devices > 1 (here: three contexts on the one GPU of the test box): ejb_join shards, gathers GPU-to-GPU,
+    merges and returns one result."""
+    rep = E.generate(1, n_cells=50000, seed=44)
+    inp = rep.to_join_input()
     p = E.default_params(True)
-    want = pyoracle.run(p, rep.c_ptr, threads=0)
-    parts = []
-    for r in range(3):
-        c = E.JoinContext(rank=r, world=3)
-        res = c.join(p, rep)
-        parts.append({f: getattr(res, f) for f in EDGE_FIELDS})
-        c.close()
-    assert all(len(x["edge_k1"]) > 0 for x in parts)
-    merged = merge_edge_parts(parts)
-    assert_same_result(merged, {k: want[k] for k in want if k.startswith("edge_")}, "sharded")
-    eq, lab = E.equiv_replay(rep.c.n_rows, merged["edge_k1"], merged["edge_k2"], rep.to_join_input().a["row_exact"])
-    assert np.array_equal(eq.x, want["eq_x"]) and np.array_equal(eq.y, want["eq_y"]) and np.array_equal(lab, want["labels"])
+    want = pyoracle.run(p, inp.c_ptr(), threads=0)
+    multi = E.JoinContext(device=[0, 0, 0], cand_cap=1 << 23)
+    try:
+        got = multi.join(p, inp.to_packed().to_packed_cdr3())
+        assert got.stats["n_devices"] == 3 and got.stats["pairs_scored"] == want["pairs_scored"]
+        assert_same_result(got, want, "3-context ejb_join")
+        assert np.array_equal(got.labels, want["labels"])
+    finally:
+        multi.close()
 
 
 def test_device_resident_edges_and_host_partitioning(gpu_ctx):
@@ -246,7 +286,7 @@ def test_reference_set_tags_do_not_change_the_result(gpu_ctx):
     assert_same_result(got, want, "tags on")
     off = _join_without_tags(gpu_ctx, p, rep)
     assert_same_result(off, want, "tags off")
-    assert off.stats["stage1_ref_kills"] == 0
+    assert off.stats["stage1_ref_kills"] == 0 and off.stats["stage1_flag_skips"] == 0
 
 
 def test_reference_set_tags_at_scale(gpu_ctx):
@@ -257,8 +297,8 @@ def test_reference_set_tags_at_scale(gpu_ctx):
     off = _join_without_tags(gpu_ctx, p, inp)
     for f in ("edge_k1", "edge_k2", "edge_cd", "edge_shares", "edge_indeps", "edge_score", "labels", "eq_x", "eq_y", "eq_z"):
         assert np.array_equal(getattr(on, f), getattr(off, f)), f
-    assert off.stats["stage1_ref_kills"] == 0
-    assert on.stats["stage1_ref_kills"] > 0, "a 300k-cell heavy-tailed repertoire with 1 % indel rows must exercise the kill"
+    assert off.stats["stage1_ref_kills"] == 0 and off.stats["stage1_flag_skips"] == 0
+    assert on.stats["stage1_ref_kills"] + on.stats["stage1_flag_skips"] > 0, "a 300k-cell heavy-tailed repertoire with 1 % indel rows must exercise the kill"
     assert on.stats["stage1_candidates"] < off.stats["stage1_candidates"]
 
 
