@@ -1,22 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — clonotype-join throughput on B200 (BASELINE.json metric: exact-subclonotype pairs scored/sec).
+"""bench.py — clonotype-join throughput on B200 (BASELINE.json metric: exact-subclonotype pairs scored/sec; join wall time at
+1M / 10M cells on 1/2/4/8 GPUs).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path (bucketer -> pair kernels -> forest -> union-find) over the whole
-synthetic repertoire.  N=1 workload: BASELINE.json configs[1] (1M-cell heavy-tailed human BCR repertoire).
-N>1 (weak scaling): the same clone-size law at N x 1M cells (N=8 ~ configs[4]); rank 0 generates the
-repertoire, sub-buckets are assigned to ranks by a cost model (LPT), the heaviest cut into row ranges, and each
-rank receives, uploads and joins only its share — no collective on the data path; the per-rank edge lists are
-gathered GPU-to-GPU to rank 0 over NCCL and merged there (forest of the partial forests of split sub-buckets).
+One "step" = one pass of the hot path (bucket scan -> bucketer -> pair kernels -> forest -> union-find) over the whole synthetic
+repertoire.  Workload at EVERY N: BASELINE configs[4], the 10M-cell BCR repertoire ("bucket-sharded across 1/2/4/8 B200"), i.e.
+STRONG scaling: the same 4.5e10 pairs at every N.  At N > 1 every rank (one process per GPU) holds the whole input, joins the
+sub-buckets / row ranges the library assigns to it (ejb_set_shard: deterministic LPT, identical on every rank, no collective on
+the data path), the partial forests are gathered GPU-to-GPU over NCCL into rank 0, merged and finalized there on the device.
+The N = 1 line additionally carries `configs1`: the 1M-cell configs[1] measured the same way in the same job (the workload the
+per-kernel roofline work is tracked on), with the WHOLE-workload CPU baseline next to it.
 
-  value   pairs/s with inputs resident in HBM (ejb_run), device time from CUDA events on the launching stream
-  e2e     pairs/s through ejb_join with HOST (pinned) buffers: H2D + run + D2H + EquivRel replay in the timed region
-  roofline  dominant pair kernel vs the popc-pipe peak measured in the same job (SURVEY.md §8 d)
-  cpu_baseline  the CPU oracle (port of the reference join) on a bounded bucket sample of the same workload
+  value     pairs/s with inputs resident in HBM (ejb_run [+ gather + merge]), device time
+  e2e       pairs/s through the public API from HOST (pinned) buffers: H2D + partition + run + gather/merge + D2H + EquivRel replay
+  roofline  popc pipe: algorithmic popc / time vs the popc peak measured in the same job, plus the EXECUTED popc of stage 1
+  cpu_baseline  the CPU oracle (port of the reference join) on the WHOLE configs[1] workload, all host cores
 
---impl reference times the reference's own CPU algorithm (the oracle port; the Rust reference cannot be
-built in this image) on a bounded sample per step.
+--impl reference times the reference's own CPU algorithm (the oracle port; the Rust reference cannot be built in this image) on
+a bounded, seeded bucket sample of the same workload per step, and prints the measured bias of that sampling rule.
 """
 import argparse
 import json
@@ -33,20 +35,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "exact-subclonotype pairs scored/sec"
-CONFIG_INDEX = 1
-WORKLOAD = "BASELINE configs[1]: synthetic 1M-cell human BCR repertoire, heavy-tailed clone sizes (Zipf 1.4, <=50k cells/clone)"
+MAIN_CONFIG, SIDE_CONFIG = 4, 1
+WORKLOADS = {
+    4: "BASELINE configs[4]: synthetic 10M-cell BCR repertoire (configs[1] clone-size law, 16 datasets, 4 donors)",
+    1: "BASELINE configs[1]: synthetic 1M-cell human BCR repertoire, heavy-tailed clone sizes (Zipf 1.4, <=50k cells/clone)",
+}
 
 
 def bucket_table(inp):
-    """Per-row bucket id (runs of equal lens, join.rs:68-88) and sub-bucket statistics computed with numpy."""
+    """Per-row bucket id (runs of equal lens, join.rs:68-88)."""
     a = inp.a
     n = inp.n_rows
     lens = a["row_len"].reshape(-1, 2)
     nch = a["row_nchains"]
     head = np.ones(n, dtype=bool)
     head[1:] = (lens[1:] != lens[:-1]).any(axis=1) | (nch[1:] != nch[:-1])
-    bucket = np.cumsum(head) - 1
-    return bucket, lens, nch
+    return np.cumsum(head) - 1, lens, nch
 
 
 def algorithmic_popc(inp):
@@ -55,39 +59,39 @@ def algorithmic_popc(inp):
     bucket, lens, nch = bucket_table(inp)
     c3 = inp.a["row_cdr3_len"].reshape(-1, 2)
     act = nch == 2
-    key = np.stack([bucket[act], c3[act, 0], c3[act, 1], lens[act, 0], lens[act, 1]], axis=1)
-    uniq, cnt = np.unique(key, axis=0, return_counts=True)
+    key = (bucket[act].astype(np.int64) << 44) | (c3[act, 0].astype(np.int64) << 33) | (c3[act, 1].astype(np.int64) << 22) | \
+          (lens[act, 0].astype(np.int64) << 11) | lens[act, 1].astype(np.int64)
+    uniq, cnt = np.unique(key, return_counts=True)
+    ch, cl, lh, ll = (uniq >> 33) & 0x7ff, (uniq >> 22) & 0x7ff, (uniq >> 11) & 0x7ff, uniq & 0x7ff
     pairs = cnt.astype(np.float64) * (cnt - 1) / 2
-    p1 = np.ceil(uniq[:, 1] / 32) + np.ceil(uniq[:, 2] / 32)
-    p2 = 3 * (np.ceil(uniq[:, 3] / 32) + np.ceil(uniq[:, 4] / 32)) + 6
+    p1 = np.ceil(ch / 32) + np.ceil(cl / 32)
+    p2 = 3 * (np.ceil(lh / 32) + np.ceil(ll / 32)) + 6
     tot = max(pairs.sum(), 1.0)
-    row_bytes = ((np.ceil(uniq[:, 1] / 4) + np.ceil(uniq[:, 2] / 4)) + 7 * 16 * (np.ceil(uniq[:, 3] / 128) + np.ceil(uniq[:, 4] / 128))) * cnt
+    row_bytes = ((np.ceil(ch / 4) + np.ceil(cl / 4)) + 3 * 16 * (np.ceil(lh / 128) + np.ceil(ll / 128)) + 112) * cnt   # CDR3 planes + 3-plane records + aux
     return float((p1 * pairs).sum() / tot), float((p2 * pairs).sum() / tot), float(pairs.sum()), float(row_bytes.sum())
 
 
-def cpu_sample(inp, target_pairs=2.5e8, seed=0):
-    """A bounded sample of the same workload for the CPU baseline: whole lens-buckets taken in a seeded
-    shuffle until their pair count reaches target_pairs."""
+def cpu_sample(inp, row_fraction, seed=0):
+    """A bounded sample of the workload for the per-step reference arm: whole lens-buckets in a seeded shuffle — NO bucket is
+    excluded for its size — until they hold `row_fraction` of the rows."""
     bucket, lens, nch = bucket_table(inp)
     nb = int(bucket[-1]) + 1
     sizes = np.bincount(bucket, minlength=nb).astype(np.int64)
     two = np.zeros(nb, dtype=bool)
     two[bucket[nch == 2]] = True
-    order = np.random.default_rng(seed).permutation(nb)
-    chosen, acc = [], 0.0
-    for b in order:
+    target = row_fraction * inp.n_rows
+    chosen, acc = [], 0
+    for b in np.random.default_rng(seed).permutation(nb):
         if not two[b] or sizes[b] < 2:
             continue
-        p = sizes[b] * (sizes[b] - 1) / 2
-        if p > target_pairs * 0.6:
-            continue
         chosen.append(b)
-        acc += p
-        if acc >= target_pairs:
+        acc += sizes[b]
+        if acc >= target:
             break
     chosen = np.sort(np.array(chosen))
     rows = np.nonzero(np.isin(bucket, chosen))[0]
-    desc = f"{len(chosen)} of {nb} lens-buckets of the workload (seeded shuffle, largest {int(sizes[chosen].max()) if len(chosen) else 0} rows), {len(rows)} rows"
+    desc = (f"{len(chosen)} of {nb} lens-buckets (seeded shuffle, none excluded; largest {int(sizes[chosen].max()) if len(chosen) else 0} rows), "
+            f"{len(rows)} of {inp.n_rows} rows")
     return inp.take_rows(rows), desc
 
 
@@ -137,18 +141,36 @@ class ClockSampler:
         return out
 
 
+def spread(xs):
+    xs = sorted(xs)
+    n = len(xs)
+    return {"min": xs[0], "median": statistics.median(xs), "p95": xs[min(n - 1, int(0.95 * n))], "max": xs[-1], "n": n}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle (port of the Rust join) on a bounded sample per step
+# --------------------------------------------------------------------------------------------------------------------
 def run_reference_arm(args, rank):
-    """The reference's CPU join (oracle port), all host threads, bounded sample per step."""
     if rank != 0:
         return
     import enclone_ranger_b200 as E
     from oracle import pyoracle
-    rep = E.generate(CONFIG_INDEX)
+    p = E.default_params(True)
+    empty = E.JoinInput()
+    pyoracle.run(p, empty.c_ptr(), threads=0)  # builds the Stirling table outside the timed region (start.rs:344 does too)
+    # sampling bias, measured where the whole workload is affordable: configs[1] in full vs the same sampling rule on it
+    rep = E.generate(SIDE_CONFIG)
+    side = rep.to_join_input()
+    rep.close()
+    full = pyoracle.run(p, side.c_ptr(), threads=0)
+    side_sample, side_desc = cpu_sample(side, row_fraction=0.10)
+    ss = pyoracle.run(p, side_sample.c_ptr(), threads=0)
+    full_v, samp_v = full["pairs_scored"] / full["seconds_join"], ss["pairs_scored"] / ss["seconds_join"]
+    del side, side_sample
+    rep = E.generate(MAIN_CONFIG, n_cells=args.cells)
     inp = rep.to_join_input()
     rep.close()
-    sample, desc = cpu_sample(inp, target_pairs=8e7)
-    p = E.default_params(True)
-    pyoracle.run(p, E.JoinInput().c_ptr(), threads=0)  # builds the Stirling table outside the timed region (start.rs:344 does too)
+    sample, desc = cpu_sample(inp, row_fraction=0.02)
     times, pairs, threads = [], 0, 0
     for i in range(args.warmup + args.steps):
         r = pyoracle.run(p, sample.c_ptr(), threads=0)
@@ -159,27 +181,302 @@ def run_reference_arm(args, rank):
     val = pairs / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 popc + f64 score",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "timed": "CPU restatement of join_exacts (oracle port of the Rust reference; rustc/cargo absent)",
-                                          "sample": desc},
-        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc},
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 popc + f64 score",
+        "data": "synthetic",
+        "config": {"workload": WORKLOADS[MAIN_CONFIG], "timed": "CPU restatement of join_exacts (oracle port of the Rust reference; rustc/cargo absent), all host threads",
+                   "sample": desc},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc,
+                         "sample_bias": {"measured_on": WORKLOADS[SIDE_CONFIG], "whole_workload_pairs_per_s": full_v, "whole_workload_seconds": full["seconds_join"],
+                                         "same_rule_sample_pairs_per_s": samp_v, "sample": side_desc, "full_over_sample": full_v / samp_v}},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------------
+def pinned_arena(inp, torch):
+    """Every input array moved once, outside the timed regions, into ONE page-locked allocation, the way the Rust shim flattens
+    its records; the library then uploads it with a single DMA (ejb_set_input_arena)."""
+    import enclone_ranger_b200 as E
+    total = sum((arr.nbytes + 255) & ~255 for arr in inp.a.values())
+    arena = torch.empty(total + 256, dtype=torch.uint8).pin_memory()
+    arena_np = arena.numpy()
+    base_off = (-arena_np.ctypes.data) & 255
+    off, views = base_off, {}
+    for name, arr in inp.a.items():
+        view = arena_np[off:off + arr.nbytes].view(arr.dtype).reshape(arr.shape)
+        view[...] = arr
+        views[name] = view
+        off += (arr.nbytes + 255) & ~255
+    out = E.JoinInput(**views)
+    assert all(out.a[n].ctypes.data == views[n].ctypes.data for n in views if views[n].size)
+    return out, arena, arena_np.ctypes.data + base_off, off - base_off
+
+
+def share_input(inp, rank, world, dist, tag):
+    """rank 0 holds `inp`; every rank returns its own copy (through /dev/shm: one host process would hold the records once,
+    here every rank process needs them in its own page-locked memory)."""
+    import enclone_ranger_b200 as E
+    from enclone_ranger_b200.inputs import _FIELDS
+    d = f"/dev/shm/ejb_bench_{tag}"
+    if rank == 0:
+        os.makedirs(d, exist_ok=True)
+        for name, arr in inp.a.items():
+            np.save(os.path.join(d, name + ".npy"), arr)
+    dist.barrier()
+    if rank != 0:
+        inp = E.JoinInput(**{name: np.load(os.path.join(d, name + ".npy"), mmap_mode="r") for name in _FIELDS})
+    return inp, d
+
+
+def measure_workload(E, torch, dist, args, cfg_index, cells, rank, world, local_rank, dev, peaks, with_cpu_baseline):
+    """Device-resident and end-to-end arms of one workload; returns the result dict on rank 0 (None elsewhere)."""
+    t_gen = time.time()
+    inp_ascii = None
+    if rank == 0:
+        rep = E.generate(cfg_index, n_cells=cells)
+        inp_ascii = rep.to_join_input()
+        rep.close()
+        # host buffers as the Rust shim hands them over: contigs and CDR3s 2-bit packed (info[k].tigsp) where they are pure
+        # ACGT without indel marks, ASCII otherwise
+        inp = inp_ascii if args.ascii else inp_ascii.to_packed().to_packed_cdr3()
+        raw_tig_bytes = int(inp_ascii.a["tig_bytes"].size)
+    else:
+        inp, raw_tig_bytes = None, 0
+    shm_dir = None
+    if world > 1:
+        inp, shm_dir = share_input(inp, rank, world, dist, os.environ.get("MASTER_PORT", "0"))
+    t_gen = time.time() - t_gen
+    params = E.default_params(True)
+    inp, arena, arena_addr, arena_len = pinned_arena(inp, torch)
+    if world > 1:
+        dist.barrier()
+        if rank == 0:
+            import shutil
+            shutil.rmtree(shm_dir, ignore_errors=True)
+    ctx = E.JoinContext(device=local_rank, rank=rank, world=world)
+    ctx.set_input_arena(arena_addr, arena_len)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    merged = {}
+
+    def gather_and_merge():
+        """per-rank partial forests -> rank 0's merge buffers over NCCL (send / recv straight into slices), merge on the device.
+        Returns (gather ms on the device clock, merge ms) of this rank."""
+        if world == 1:
+            return 0.0, 0.0
+        n, e, t = ctx.part_forest()
+        sizes_t = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes_t, torch.tensor([n], dtype=torch.int64, device=dev))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sizes = sizes_t.tolist()
+        total = int(sum(sizes))
+        ops = []
+        if rank == 0:
+            ew, tw = ctx.merge_buffers(total)
+            ew[:n].copy_(e)
+            tw[:24 * n].copy_(t)
+            off = n
+            for r in range(1, world):
+                if sizes[r]:
+                    ops.append(dist.P2POp(dist.irecv, ew[off:off + sizes[r]], r))
+                    ops.append(dist.P2POp(dist.irecv, tw[24 * off:24 * (off + sizes[r])], r))
+                off += sizes[r]
+        elif n:
+            ops.append(dist.P2POp(dist.isend, e, 0))
+            ops.append(dist.P2POp(dist.isend, t, 0))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        e1.record()
+        torch.cuda.synchronize()
+        merge_ms = 0.0
+        if rank == 0:
+            ms = ctx.merge_parts(total)
+            merge_ms = ms["ms_merge"]
+            merged.update({k: ms[k] for k in ("joins", "forest_edges", "two_cell_deleted")})
+        return e0.elapsed_time(e1), merge_ms
+
+    # ---------------- device-resident arm: value ----------------
+    ctx.upload(params, inp)
+
+    def step_resident():
+        st = ctx.run()
+        g_ms, m_ms = gather_and_merge()
+        return st, st["ms_device_total"] + g_ms + m_ms, g_ms, m_ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    dev_ms, launches, stats, g_all, m_all = [], 0, None, [], []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        stats, ms, g_ms, m_ms = step_resident()
+        dev_ms.append(ms)
+        g_all.append(g_ms)
+        m_all.append(m_ms)
+        launches += stats["kernel_launches"]
+    barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3 / args.steps
+    clocks = sampler.stop() if sampler else None
+    t_local = sum(dev_ms) / len(dev_ms)
+    stats = dict(stats)
+    stats.update(merged)
+    stats["ms_merge"] = sum(m_all) / len(m_all)
+    pairs = stats["pairs_scored"]
+    per_rank = None
+    if world > 1:
+        t = torch.tensor([t_local, wall_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_step, wall_ms = float(t[0].item()), float(t[1].item())
+        ln = torch.tensor([launches, pairs], dtype=torch.int64, device=dev)
+        dist.all_reduce(ln)
+        launches, pairs = int(ln[0].item()), int(ln[1].item())
+        keys = ("pairs_scored", "pairs_evaluated", "pairs_distance_computed", "stage1_candidates", "stage2_survivors", "pass_edges", "forest_edges", "rounds",
+                "overflow_retries", "ms_pack", "ms_stage1", "ms_stage2", "ms_stage2a", "ms_forest", "ms_device_total")
+        pr = torch.zeros(world * (2 + len(keys)), dtype=torch.float64, device=dev)
+        mine = torch.tensor([sum(g_all) / len(g_all), sum(m_all) / len(m_all)] + [float(stats[k]) for k in keys], dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(pr, mine)
+        pr = pr.reshape(world, -1).tolist()
+        per_rank = [dict({"gather_ms": round(x[0], 3), "merge_ms": round(x[1], 3)}, **{k: round(v, 3) for k, v in zip(keys, x[2:])}) for x in pr]
+    else:
+        t_step = t_local
+
+    # ---------------- end-to-end arm: host buffers through the public API ----------------
+    def step_e2e():
+        if world == 1:
+            return ctx.join(params, inp, copy=False)   # zero-copy views into the library's pinned result arena
+        ctx.upload(params, inp)
+        ctx.run()
+        gather_and_merge()
+        return ctx.download(copy=False) if rank == 0 else None
+
+    step_e2e()
+    barrier()
+    e2e_times = []
+    res = None
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        res = step_e2e()
+        if world > 1:
+            dist.barrier()
+        e2e_times.append((time.perf_counter() - t0) * 1e3)
+    barrier()
+    e2e_ms = sum(e2e_times) / len(e2e_times)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    out = None
+    if rank == 0:
+        e2e_stats = res.stats
+        # the committed full-size oracle digest of this workload (tests/golden/digests.json): the benchmarked result IS the
+        # reference's result
+        digest_ok = None
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+            from make_digests import ARRAYS, digest_of
+            want = json.load(open(os.path.join(ROOT, "tests", "golden", "digests.json"))).get(f"config{cfg_index}" if cells is None else None)
+            if want is not None:
+                got = digest_of(res, inp.n_rows)
+                digest_ok = all(got[f] == want[f] for f in ARRAYS) and got["n_edges"] == want["n_edges"]
+        except Exception as ex:   # noqa: BLE001
+            digest_ok = f"not checked: {ex}"
+        p1_avg, p2_avg, dom_pairs, packed_bytes = algorithmic_popc(inp_ascii)
+        s1_ms, s2a_ms = stats["ms_stage1"], stats["ms_stage2a"]
+        peak = peaks["popc_per_s"]
+        alg_popc = pairs * p1_avg + sum_stat(per_rank, stats, "stage1_candidates") * p2_avg
+        kernels = {
+            "k_stage1": {"ms_per_step": s1_ms, "launches_per_step": stats["stage1_launches"], "pairs_of_staged_tiles": stats["pairs_evaluated"],
+                         "pairs_distance_computed": stats["pairs_distance_computed"], "pairs_distance_full": stats["pairs_distance_full"],
+                         "popc_algorithmic_per_pair": p1_avg, "popc_executed": stats["popc_executed_stage1"],
+                         "frac_effective": stats["pairs_evaluated"] * p1_avg / max(s1_ms, 1e-9) / 1e-3 / peak,
+                         "frac_executed": stats["popc_executed_stage1"] / max(s1_ms, 1e-9) / 1e-3 / peak,
+                         "note": "effective = algorithmic popc of every pair of the staged tiles (skipped 16x16 groups included) / time / peak; "
+                                 "executed = popc instructions stage 1 really issued (lane granular) / time / peak — compare with ncu smsp__inst_executed_pipe_xu"},
+            "k_stage2a": {"ms_per_step": s2a_ms, "launches_per_step": stats["stage2a_launches"], "candidates": stats["stage1_candidates"], "popc_per_candidate": p2_avg,
+                          "frac_effective": stats["stage1_candidates"] * p2_avg / max(s2a_ms, 1e-9) / 1e-3 / peak},
+        }
+        if world > 1:
+            kernels["note"] = "per-kernel figures are rank 0's share"
+        dom = "k_stage2a" if s2a_ms >= s1_ms else "k_stage1"
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            hbm_src = "MEASURED_PEAKS.json"
+        except Exception:   # noqa: BLE001
+            hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
+        traffic, traffic_src = None, None
+        try:
+            nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")))
+            traffic, traffic_src = nt[dom]["dram_bytes_per_launch"], "profiles/ncu_traffic_r2.json (ncu --set full of configs[1]; dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+        except Exception:   # noqa: BLE001
+            pass
+        alg_bytes = packed_bytes + 8.0 * stats["joins"] + 4.0 * inp.n_rows
+        whole_frac = alg_popc / (t_step * 1e-3) / (peak * world)
+        out = {
+            "value": pairs / (t_step / 1e3), "ms_per_step": t_step, "ms_per_step_spread": spread(dev_ms), "wall_ms_per_step": wall_ms,
+            "workload": WORKLOADS[cfg_index] if cells is None else f"DEBUG {cells}-cell variant of configs[{cfg_index}]",
+            "cells": int(inp_ascii.n_cells), "rows": int(inp.n_rows), "pairs_scored": int(pairs), "pairs_lens_buckets": int(stats["pairs_lens"]),
+            "sub_buckets": int(stats["n_subbuckets"]), "generate_s": t_gen, "per_rank": per_rank, "clocks": clocks, "gpu_launches": int(launches),
+            "contig_encoding": "ASCII" if args.ascii else f"2-bit packed contigs and CDR3s ({raw_tig_bytes / 1e6:.0f} MB ASCII contigs -> {inp.a['tig2_words'].nbytes / 1e6:.0f} MB packed + {inp.a['tig_bytes'].nbytes / 1e6:.0f} MB ASCII)",
+            "oracle_digest_match": digest_ok,
+            "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "ms_per_step": e2e_ms, "ms_per_step_spread": spread(e2e_times),
+                    "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]) * (world if world > 1 else 1), "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]),
+                    "pinned_host_buffers": "one arena per rank (ejb_set_input_arena)",
+                    "breakdown_ms": {k: e2e_stats[k] for k in ("ms_h2d", "ms_device_total", "ms_d2h", "ms_replay")},
+                    "note": "H2D + partition + run + NCCL gather + merge + D2H + EquivRel replay; at N > 1 every rank uploads the whole input" if world > 1 else "H2D + run + D2H + EquivRel replay"},
+            "roofline": {"bound": "popc", "kernel": dom, "achieved": kernels[dom]["frac_effective"] * peak / 1e9, "peak": peak / 1e9, "unit": "Gpopc/s",
+                         "frac": kernels[dom]["frac_effective"], "frac_executed": kernels[dom].get("frac_executed"),
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": "measured in this job (ejb_measure_peaks: dependency-free __popc loop, 16 lanes/clk/SM)",
+                         "lop3_peak_gops": peaks["lop3_per_s"] / 1e9, "kernels": kernels,
+                         "whole_join": {"popc_per_pair": alg_popc / max(pairs, 1), "algorithmic_popc": alg_popc, "n_gpus": world,
+                                        "frac": whole_frac, "note": "algorithmic popc of the whole join / step time / (peak x n_gpus)"},
+                         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (t_step / 1e3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src}},
+            "stage_ms": {k: stats[k] for k in ("ms_pack", "ms_stage1", "ms_stage2", "ms_stage2a", "ms_forest", "ms_finalize", "ms_merge")},
+            "counts": {k: int(stats[k]) for k in ("pairs_evaluated", "pairs_distance_computed", "pairs_distance_full", "popc_executed_stage1", "stage1_candidates",
+                                                  "stage1_flag_skips", "stage1_ref_kills", "stage1_donor_kills", "stage2_two_ref", "stage2_memo_dead", "stage2_degr_dead",
+                                                  "stage2_slow", "stage2_survivors", "pass_edges", "forest_edges", "joins", "rounds", "host_syncs",
+                                                  "boruvka_iterations", "kernel_launches")},
+            "create_ms": ctx.create_ms(),
+        }
+        if with_cpu_baseline:
+            from oracle import pyoracle   # CPU baseline leg only: the checker timed as a baseline, never on the product path
+            empty = E.JoinInput()
+            pyoracle.run(params, empty.c_ptr(), threads=0)
+            r = pyoracle.run(params, inp_ascii.c_ptr(), threads=0)
+            out["cpu_baseline"] = {"value": r["pairs_scored"] / r["seconds_join"], "unit": "pairs/s", "cores": int(r["threads"]), "kind": "port",
+                                   "sample": f"the WHOLE workload ({WORKLOADS[cfg_index]}), one pass", "seconds": r["seconds_join"],
+                                   "join_one_calls": int(r["join_one_calls"]), "pairs": int(r["pairs_scored"]),
+                                   "edges_equal_gpu": bool(len(r["edge_k1"]) == len(res.edge_k1) and np.array_equal(r["edge_k1"], res.edge_k1) and np.array_equal(r["edge_k2"], res.edge_k2))}
+    ctx.close()
+    del arena
+    return out
+
+
+def sum_stat(per_rank, stats, key):
+    return sum(r[key] for r in per_rank) if per_rank else stats[key]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cells", type=int, default=None, help="override the repertoire size (debug only; the number is then not the BASELINE config)")
+    ap.add_argument("--cells", type=int, default=None, help="override the repertoire size of the main workload (debug only; the number is then not the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--verify", action="store_true", help="N>1 debug: rank 0 also joins the whole repertoire on its own GPU and compares the merged edge list and EquivRel")
-    ap.add_argument("--split-above", type=float, default=0.5, help="N>1: split sub-buckets whose cost exceeds this fraction of a rank's share")
-    ap.add_argument("--ascii", action="store_true", help="hand every contig over as ASCII (info[k].tigs) instead of 2-bit packed (tigsp)")
+    ap.add_argument("--no-side", action="store_true", help="skip the configs[1] side measurement of the N = 1 line")
+    ap.add_argument("--ascii", action="store_true", help="hand every contig / CDR3 over as ASCII (info[k].tigs) instead of 2-bit packed (tigsp)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,268 +496,38 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    from enclone_ranger_b200 import multi
-    base_cells = args.cells if args.cells is not None else 1000000
-    t_gen = time.time()
-    full_rows, row_exact_full = 0, None
-    if world == 1:
-        rep = E.generate(CONFIG_INDEX, n_cells=base_cells)
-        inp = rep.to_join_input()      # numpy-owned copies (host buffers of the caller)
-        rep.close()
-        my_rows = None
-        full_rows, row_exact_full = inp.n_rows, inp.a["row_exact"]
-    else:
-        parts = None
-        if rank == 0:
-            rep = E.generate(CONFIG_INDEX, n_cells=base_cells * world)
-            full = rep.to_join_input()
-            rep.close()
-            full_rows, row_exact_full = full.n_rows, full.a["row_exact"].copy()
-            parts = []
-            # sample join on this rank's GPU: which large sub-buckets hold pairs that are scored in full and do not join
-            probe_ctx = E.JoinContext(device=local_rank)
-            live = multi.probe_live_fractions(full, probe_ctx, E.default_params(True))
-            probe_ctx.close()
-            wparts, split_rows = multi.partition_work(full, world, live_fraction=live, split_above=args.split_above)
-            ncells_row = multi.ncells_per_row(full)
-            for wp in wparts:
-                sub, _ = full.subset_rows(wp.rows)
-                parts.append((sub, wp.rows, wp.roles))
-            n_split_rows = int(split_rows.sum())
-            full_keep = full.to_packed() if args.verify else None
-            del full
-        inp, my_rows, my_roles = multi.scatter_parts(parts, dev)
-        del parts
-        fr = torch.tensor([full_rows], dtype=torch.int64, device=dev)
-        dist.broadcast(fr, src=0)
-        full_rows = int(fr.item())
-    # host buffers as the Rust shim hands them over: contigs 2-bit packed (info[k].tigsp) where they are pure ACGT
-    # without indel marks, ASCII otherwise
-    raw_tig_bytes = int(inp.a["tig_bytes"].size)
-    inp_ascii = inp
-    if not args.ascii:
-        inp = inp.to_packed()
-    t_gen = time.time() - t_gen
-    params = E.default_params(True)
-    # the caller's host buffers live in page-locked memory (the e2e contract copies from pinned host memory): every array is
-    # moved once, outside the timed regions, into ONE cudaHostAlloc'ed arena, the way the Rust shim flattens its records; the
-    # library then uploads it with a single DMA (ejb_set_input_arena) instead of ~36 copies that each pay ~0.1 ms of setup
-    views, total = {}, 0
-    for name, arr in inp.a.items():
-        total += (arr.nbytes + 255) & ~255
-    arena = torch.empty(total + 256, dtype=torch.uint8).pin_memory()
-    arena_np = arena.numpy()
-    base_off = (-arena_np.ctypes.data) & 255           # 256-byte aligned start
-    off = base_off
-    for name, arr in inp.a.items():
-        view = arena_np[off:off + arr.nbytes].view(arr.dtype).reshape(arr.shape)
-        view[...] = arr
-        views[name] = view
-        off += (arr.nbytes + 255) & ~255
-    pinned = [arena]
-    arena_addr, arena_len = arena_np.ctypes.data + base_off, off - base_off
-    inp = E.JoinInput(**views)     # same dtypes, contiguous: the struct points straight into the pinned buffers
-    assert all(inp.a[n].ctypes.data == views[n].ctypes.data for n in views if views[n].size)
-    ctx = E.JoinContext(device=local_rank)
-    ctx.set_input_arena(arena_addr, arena_len)
-    peaks = ctx.measure_peaks() if rank == 0 else None
-    rows_dev = torch.from_numpy(my_rows).to(dev) if my_rows is not None else None
-    if world > 1:
-        ctx.set_row_roles(my_roles)   # row ranges of split sub-buckets (None: this rank holds whole sub-buckets only)
-        split_dev = torch.from_numpy(split_rows).to(dev) if rank == 0 else None
-
-    def gather_keys(key, aux):
-        """per-rank 64-bit (k1<<32|k2) keys (global row ids) + (cd<<32|min_shares) -> rank 0 over NCCL; there: one device sort,
-        then the edges of split sub-buckets (partial forests) are reduced to their forest and two-cell filtered"""
-        if world == 1:
-            return key
-        n = torch.tensor([key.numel()], dtype=torch.int64, device=dev)
-        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(sizes, n)
-        sizes = [int(x.item()) for x in sizes]
-        mx = max(max(sizes), 1)
-        pad = torch.full((2, mx), -1, dtype=torch.int64, device=dev)
-        pad[0, : key.numel()] = key
-        pad[1, : key.numel()] = aux
-        bufs = [torch.empty((2, mx), dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, bufs, dst=0)
-        if rank != 0:
-            return None
-        k, o = torch.sort(torch.cat([bufs[r][0, : sizes[r]] for r in range(world)]))
-        if n_split_rows:
-            a = torch.cat([bufs[r][1, : sizes[r]] for r in range(world)])[o]
-            idx = torch.nonzero(split_dev[k >> 32]).squeeze(1)
-            if idx.numel():
-                ks, au = k[idx].cpu().numpy(), a[idx].cpu().numpy()
-                keep = multi.merge_split_edges(full_rows, ks >> 32, ks & 0xffffffff, au >> 32, au & 0xffffffff, split_rows, ncells_row)
-                mask = torch.ones(k.numel(), dtype=torch.bool, device=dev)
-                mask[idx[torch.from_numpy(~keep).to(dev)]] = False
-                k = k[mask]
-        return k
-
-    def edge_aux(cd, nrefs, shares):
-        """(cd << 32) | min(shares): what the two-cell filter needs (join.rs:120-178)"""
-        sh = shares.reshape(-1, 2).long()
-        return (cd.long() << 32) | torch.where(nrefs == 2, torch.minimum(sh[:, 0], sh[:, 1]), sh[:, 0])
-
-    # ---------------- device-resident arm: value ----------------
-    ctx.upload(params, inp)
-
-    gather_ms = []
-
-    def step_resident():
-        st = ctx.run()
-        if world > 1:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            k1, k2 = ctx.device_edges()     # device pointers, no host round trip
-            gather_keys((rows_dev[k1.long()] << 32) | rows_dev[k2.long()], edge_aux(*ctx.device_tuples()))
-            e1.record()
-            gather_ms.append((e0, e1))
-        return st
-
-    for _ in range(args.warmup):
-        step_resident()
-    barrier()
-    gather_ms.clear()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    dev_ms, wall0, launches, stats = [], time.perf_counter(), 0, None
-    for _ in range(args.steps):
-        stats = step_resident()
-        dev_ms.append(stats["ms_device_total"])
-        launches += stats["kernel_launches"]
-    barrier()
-    wall_ms = (time.perf_counter() - wall0) * 1e3 / args.steps
-    clocks = sampler.stop() if sampler else None
-    # per-step time on the device clock: the library's CUDA events around the join (its own stream) + at N>1 torch CUDA events
-    # around the edge gather / merge (torch's stream; it starts after the join has completed); max over ranks below
-    g_ms = [a.elapsed_time(b) for a, b in gather_ms]
-    t_local = (sum(dev_ms) + sum(g_ms)) / len(dev_ms)
-    pairs = stats["pairs_scored"]
-    if world > 1:
-        t = torch.tensor([t_local], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_step = float(t.item())
-        ln = torch.tensor([launches, pairs], dtype=torch.int64, device=dev)
-        dist.all_reduce(ln)
-        launches, pairs = int(ln[0].item()), int(ln[1].item())
-        keys = ("pairs_scored", "pairs_evaluated", "stage1_candidates", "stage1_ref_kills", "stage1_donor_kills", "stage2_survivors", "pass_edges", "rounds", "overflow_retries",
-                "ms_pack", "ms_stage1", "ms_stage2", "ms_stage2a", "ms_forest", "ms_finalize")
-        pr = [torch.zeros(2 + len(keys), dtype=torch.float64, device=dev) for _ in range(world)]
-        dist.all_gather(pr, torch.tensor([wall_ms, sum(dev_ms) / len(dev_ms)] + [float(stats[k]) for k in keys], dtype=torch.float64, device=dev))
-        per_rank = [dict({"wall_ms": round(float(x[0]), 2), "join_device_ms": round(float(x[1]), 2)}, **{k: round(float(v), 2) for k, v in zip(keys, x[2:].tolist())}) for x in pr]
-    else:
-        t_step = t_local
-        per_rank = None
-
-    # ---------------- end-to-end arm: host buffers through ejb_join ----------------
-    last_merged = {}
-
-    def step_e2e():
-        res = ctx.join(params, inp, copy=False)   # zero-copy views into the library's pinned result arena
-        if world > 1:
-            key = torch.from_numpy(my_rows[res.edge_k1].astype(np.int64) << 32 | my_rows[res.edge_k2].astype(np.int64)).to(dev)
-            aux = edge_aux(torch.from_numpy(np.ascontiguousarray(res.edge_cd)), torch.from_numpy(np.ascontiguousarray(res.edge_nrefs)),
-                           torch.from_numpy(np.ascontiguousarray(res.edge_shares))).to(dev)
-            merged = gather_keys(key, aux)
-            if rank == 0:   # raw_joins of the whole repertoire + the EquivRel finish_join returns
-                k = merged.cpu().numpy()
-                last_merged["k"] = k
-                last_merged["eq"] = E.equiv_replay(full_rows, (k >> 32).astype(np.int32), (k & 0xffffffff).astype(np.int32), row_exact_full)
-        return res
-
-    step_e2e()
-    barrier()
-    e2e_wall0 = time.perf_counter()
-    res = None
-    for _ in range(args.steps):
-        res = step_e2e()
-    barrier()
-    e2e_ms = (time.perf_counter() - e2e_wall0) * 1e3 / args.steps
-    if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_stats = res.stats
-    if args.verify and world > 1 and rank == 0:
-        vctx = E.JoinContext(device=local_rank)
-        ref = vctx.join(params, full_keep)
-        kref = ref.edge_k1.astype(np.int64) << 32 | ref.edge_k2.astype(np.int64)
-        eq, lab = last_merged["eq"]
-        ok = bool(np.array_equal(kref, last_merged["k"]) and np.array_equal(eq.x, ref.eq_x) and np.array_equal(eq.y, ref.eq_y) and np.array_equal(eq.z, ref.eq_z)
-                  and np.array_equal(lab, ref.labels))
-        print(f"[verify] {world}-rank merged result == single-GPU join of the whole repertoire: {ok} ({len(kref)} edges, {n_split_rows} rows in split sub-buckets)",
-              file=sys.stderr, flush=True)
-        vctx.close()
-        if not ok:
-            raise SystemExit("verification failed")
-
+    peaks = None
     if rank == 0:
-        p1_avg, p2_avg, dom_pairs, packed_bytes = algorithmic_popc(inp_ascii)
-        s1_ms, s2a_ms = stats["ms_stage1"], stats["ms_stage2a"]
-        s1_ops = stats["pairs_evaluated"] * p1_avg
-        s2_ops = stats["stage1_candidates"] * p2_avg
-        kernels = {
-            "k_stage1": {"ms_per_step": s1_ms, "launches_per_step": stats["stage1_launches"], "units": stats["pairs_evaluated"], "popc_per_unit": p1_avg,
-                         "achieved_gpopc_s": s1_ops / max(s1_ms, 1e-9) / 1e6},
-            "k_stage2a": {"ms_per_step": s2a_ms, "launches_per_step": stats["stage2a_launches"], "units": stats["stage1_candidates"], "popc_per_unit": p2_avg,
-                          "achieved_gpopc_s": s2_ops / max(s2a_ms, 1e-9) / 1e6},
-        }
-        dom = "k_stage2a" if s2a_ms >= s1_ms else "k_stage1"
-        peak_g = peaks["popc_per_s"] / 1e9
-        hbm_peak = None
-        try:
-            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-        except Exception:
-            hbm_peak = 6650.0
-        traffic = None   # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
-        try:
-            nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
-            traffic = nt[dom]["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        alg_bytes = packed_bytes + 8.0 * stats["joins"] + 4.0 * inp.n_rows   # rank 0's share at N > 1
+        pctx = E.JoinContext(device=local_rank)
+        peaks = pctx.measure_peaks()
+        pctx.close()
+    main_res = measure_workload(E, torch, dist, args, MAIN_CONFIG, args.cells, rank, world, local_rank, dev, peaks, with_cpu_baseline=False)
+    side_res = None
+    if world == 1 and not args.no_side:
+        side_res = measure_workload(E, torch, dist, args, SIDE_CONFIG, None, rank, world, local_rank, dev, peaks, with_cpu_baseline=not args.no_cpu_baseline)
+    if rank == 0:
+        m = main_res
         line = {
-            "metric": METRIC, "value": pairs / (t_step / 1e3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 popc + f64 score", "data": "synthetic",
-            "config": {"workload": (WORKLOAD if world == 1 else f"configs[1] clone-size law at {world} x 1M cells, sub-buckets partitioned over {world} ranks (the heaviest cut into row ranges)") if args.cells is None else f"DEBUG {args.cells}-cell-per-GPU variant of configs[1]", "cells": int(base_cells * world), "rows": int(full_rows), "rows_rank0": int(inp.n_rows),
-                       "pairs_scored": int(pairs), "pairs_lens_buckets": int(stats["pairs_lens"]), "sub_buckets": int(stats["n_subbuckets"]),
-                       "parallelism": f"bucket-sharded x{world}, weak scaling (1M cells per GPU), {n_split_rows} rows in sub-buckets split by row ranges" if world > 1 else "single GPU",
-                       "l2": f"inputs ({stats['h2d_bytes'] / 1e6:.0f} MB raw + packed row store) exceed the 126 MB L2; no flush needed",
-                       "timing": "CUDA events on the library's launching stream (ejb_stats.ms_device_total)" if world == 1 else "device clock: CUDA events of the join on the library's stream + CUDA events of the NCCL edge gather and merge on torch's stream, max over ranks",
-                       "wall_ms_per_step": wall_ms, "generate_s": t_gen, "per_rank": per_rank,
-                       "contig_encoding": "ASCII" if args.ascii else f"2-bit packed where eligible ({raw_tig_bytes / 1e6:.0f} MB ASCII -> {inp.a['tig2_words'].nbytes / 1e6:.0f} MB packed + {inp.a['tig_bytes'].nbytes / 1e6:.0f} MB ASCII)"},
-            "clocks": clocks,
-            "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]),
-                    "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]), "pinned_host_buffers": "one arena (ejb_set_input_arena)",
-                    "breakdown_ms": {k: e2e_stats[k] for k in ("ms_h2d", "ms_device_total", "ms_d2h", "ms_replay")}},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "popc", "kernel": dom, "achieved": kernels[dom]["achieved_gpopc_s"], "peak": peak_g, "unit": "Gpopc/s",
-                         "frac": kernels[dom]["achieved_gpopc_s"] / peak_g, "traffic": traffic,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/ncu_traffic_r1.json (ncu --set full, 1M-cell config[1])", "peak_source": "measured in this job (ejb_measure_peaks: dependency-free __popc loop)",
-                         "lop3_peak_gops": peaks["lop3_per_s"] / 1e9, "kernels": kernels,
-                         "whole_join": {"popc_per_pair": p1_avg + p2_avg * stats["stage1_candidates"] / max(pairs, 1),
-                                        "roofline_pairs_per_s": peaks["popc_per_s"] / (p1_avg + p2_avg * stats["stage1_candidates"] / max(pairs, 1)),
-                                        "frac": (pairs / (t_step / 1e3)) / (peaks["popc_per_s"] / (p1_avg + p2_avg * stats["stage1_candidates"] / max(pairs, 1)))},
-                         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (t_step / 1e3) / 1e9, "peak_gbs": hbm_peak}},
-            "stage_ms": {k: stats[k] for k in ("ms_pack", "ms_stage1", "ms_stage2", "ms_stage2a", "ms_forest", "ms_finalize")},
-            "counts": {k: int(stats[k]) for k in ("pairs_evaluated", "stage1_candidates", "stage1_ref_kills", "stage1_donor_kills", "stage2_two_ref", "stage2_memo_dead", "stage2_degr_dead", "stage2_slow", "stage2_survivors", "pass_edges", "forest_edges", "joins", "rounds")},
+            "metric": METRIC, "value": m["value"], "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": m["ms_per_step"], "ms_per_step_spread": m["ms_per_step_spread"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 popc + f64 score", "data": "synthetic",
+            "config": {"workload": m["workload"], "cells": m["cells"], "rows": m["rows"], "pairs_scored": m["pairs_scored"], "pairs_lens_buckets": m["pairs_lens_buckets"],
+                       "sub_buckets": m["sub_buckets"],
+                       "parallelism": (f"strong scaling: the same repertoire sharded over {world} ranks by the library (sub-buckets by LPT, the heaviest cut into row ranges; "
+                                       "partition inside the timed region), partial forests gathered over NCCL and merged on rank 0's GPU") if world > 1 else "single GPU",
+                       "l2": "inputs (GBs of raw input + packed row store) exceed the 126 MB L2; no flush needed",
+                       "timing": ("CUDA events on the library's launching stream (ejb_stats.ms_device_total)" if world == 1 else
+                                  "device clock: CUDA events of the join on the library's stream + CUDA events around the NCCL gather on torch's stream + CUDA events of the merge; max over ranks") +
+                                 "; wall clock of the same K steps (barrier + synchronize on both sides) in wall_ms_per_step",
+                       "wall_ms_per_step": m["wall_ms_per_step"], "generate_s": m["generate_s"], "per_rank": m["per_rank"], "contig_encoding": m["contig_encoding"],
+                       "oracle_digest_match": m["oracle_digest_match"], "create_ms": m["create_ms"]},
+            "clocks": m["clocks"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "roofline": m["roofline"], "stage_ms": m["stage_ms"], "counts": m["counts"],
         }
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import pyoracle   # CPU baseline leg only: the checker timed as a baseline, never on the product path
-            sample, desc = cpu_sample(inp_ascii)
-            pyoracle.run(params, E.JoinInput().c_ptr(), threads=0)
-            r = pyoracle.run(params, sample.c_ptr(), threads=0)
-            line["cpu_baseline"] = {"value": r["pairs_scored"] / r["seconds_join"], "unit": "pairs/s", "cores": int(r["threads"]), "kind": "port",
-                                    "sample": desc, "seconds": r["seconds_join"], "join_one_calls": int(r["join_one_calls"]), "pairs": int(r["pairs_scored"])}
+        if side_res is not None:
+            line["configs1"] = side_res
+            if "cpu_baseline" in side_res:
+                line["cpu_baseline"] = side_res["cpu_baseline"]
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
