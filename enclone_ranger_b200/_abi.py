@@ -194,6 +194,15 @@ class EjbResult(C.Structure):
     ]
 
 
+class EjbPairOut(C.Structure):
+    _fields_ = [
+        ("passed", _u8p),
+        ("cd", _i32p), ("nrefs", _i32p), ("shares", _i32p), ("indeps", _i32p), ("k", _i32p), ("d", _i32p), ("n", _i32p),
+        ("p1", _f64p), ("mult", _f64p), ("score", _f64p),
+        ("err", _u8p),
+    ]
+
+
 class SynthConfig(C.Structure):
     _fields_ = [
         ("seed", C.c_uint64),
@@ -301,6 +310,8 @@ def load_join():
         L.ejb_forest_merge.restype = C.c_int
         L.ejb_device_tuples.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.ejb_device_tuples.restype = C.c_int
+        L.ejb_join_one_batch.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int64, C.POINTER(EjbPairOut)]
+        L.ejb_join_one_batch.restype = C.c_int
         L.ejb_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ejb_set_shard.restype = C.c_int
         L.ejb_part_forest.argtypes = [C.c_void_p, _i64p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]

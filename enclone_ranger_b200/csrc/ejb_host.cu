@@ -162,7 +162,7 @@ struct ejb_ctx {
     DevBuf d_qcut, d_subpass, d_segpl, d_seglen, d_memo, d_tagq, d_deadq, d_donq, d_flagq, d_subdom;
     // per-round report: [Counters | UnitOut x units | candidate count x tasks], read back with ONE copy per round
     DevBuf d_round;
-    PinBuf h_round, h_prep;
+    PinBuf h_round, h_prep, h_stage;
     size_t round_units_cap = 0, round_tasks_cap = 0;
     bool tags_on = false;      // reference-set tags in use (every canonical seg id < 65535)
     struct TaskMeta { int32_t unit, r0, r1; };
@@ -173,7 +173,7 @@ struct ejb_ctx {
     DevBuf d_deg, d_first, d_labels, d_excount, d_multi, d_multi2, d_fkeys, d_fkeys2, d_fidx, d_fidx2;
     DevBuf d_o_k1, d_o_k2, d_o_cd, d_o_nrefs, d_o_sh, d_o_in, d_o_k, d_o_d, d_o_n, d_o_p1, d_o_mult, d_o_score, d_o_err;
     // pair-batch mode (ejb_join_one_batch)
-    DevBuf d_bpairs, d_bslots, d_btuples, d_bcnt;
+    DevBuf d_bpairs, d_bslots, d_btuples, d_bk1, d_bk2, d_qofrow;
     std::vector<SubBucket> subs;
     int64_t n_active = 0, n_pos = 0, n_blocks = 0, n_final = 0, n_buckets = 0, n_multi = 0, n_part = 0;
     bool have_part = false;     // a sharded run left its partial forest on the device (ejb_part_forest)
@@ -359,6 +359,29 @@ __global__ void k_stage1_nofilter(const SubBucket* __restrict__ subs, const RowT
         }
     }
     if (ev) atomicAdd(&ctr->pairs_eval, ev);
+}
+
+// pair-batch mode (ejb_join_one_batch): rows -> packed positions; a pair whose rows cannot pass join_one's first tests (a row
+// without exactly two chains, join_one.rs:83-96; different lens or CDR3 lengths, :101-109) is answered `false` right here
+__global__ void k_q_of_row(const int32_t* __restrict__ rowq, int64_t n_pos, int32_t* __restrict__ q_of_row) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_pos && rowq[q] >= 0) q_of_row[rowq[q]] = (int32_t)q;
+}
+__global__ void k_batch_pairs(const int32_t* __restrict__ k1, const int32_t* __restrict__ k2, int64_t n, int64_t n_rows, const int32_t* __restrict__ q_of_row,
+                              const int32_t* __restrict__ subq, uint2* __restrict__ pairs, uint32_t* __restrict__ slots, unsigned long long* __restrict__ n_out,
+                              unsigned int* __restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = k1[i], b = k2[i];
+    if (a < 0 || a >= n_rows || b < 0 || b >= n_rows) {
+        atomicOr(bad, 1u);
+        return;
+    }
+    const int qa = q_of_row[a], qb = q_of_row[b];
+    if (qa < 0 || qb < 0 || subq[qa] != subq[qb]) return;   // join_one returns false before looking at any sequence
+    const unsigned long long o = atomicAdd(n_out, 1ull);
+    pairs[o] = make_uint2((uint32_t)qa, (uint32_t)qb);
+    slots[o] = (uint32_t)i;
 }
 
 struct RoundTimes {
@@ -803,6 +826,7 @@ int cub_incl_sum(ejb_ctx* c, const int32_t* in, int32_t* out, int64_t n) {
 // single read-back of the round's report.  Returns 1 when a work buffer overflowed (nothing committed; the caller splits the
 // round and retries).
 int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& times) {
+    const double th0 = now_ms();
     const unsigned long long eval_before = c->pairs_eval_seen;
     const std::vector<SubBucket>& subs = c->subs;
     // ---- tasks grouped by W1; task ids number them in launch order ----
@@ -861,10 +885,15 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     cudaStream_t st = c->stream;
     CK(c->d_tasks.ensure(total_tasks * sizeof(RowTask) + 64));
     CK(c->d_units.ensure(n_units * sizeof(UnitDesc) + 64));
+    const double th1 = now_ms();
     CK(cudaMemsetAsync(rbase, 0, offsetof(Counters, round_end), st));
     CK(cudaMemsetAsync(rbase + sizeof(Counters), 0, report_bytes - sizeof(Counters), st));
-    CK(cudaMemcpyAsync(c->d_tasks.p, all_tasks.data(), total_tasks * sizeof(RowTask), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->d_units.p, udesc.data(), n_units * sizeof(UnitDesc), cudaMemcpyHostToDevice, st));
+    // tasks and unit descriptors go through page-locked staging: the copies are queued, not waited for
+    CK(c->h_stage.ensure(total_tasks * sizeof(RowTask) + n_units * sizeof(UnitDesc) + 64));
+    memcpy(c->h_stage.p, all_tasks.data(), total_tasks * sizeof(RowTask));
+    memcpy(c->h_stage.as<char>() + total_tasks * sizeof(RowTask), udesc.data(), n_units * sizeof(UnitDesc));
+    CK(cudaMemcpyAsync(c->d_tasks.p, c->h_stage.p, total_tasks * sizeof(RowTask), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_units.p, c->h_stage.as<char>() + total_tasks * sizeof(RowTask), n_units * sizeof(UnitDesc), cudaMemcpyHostToDevice, st));
     RoundTimes rt;
     rt.e0 = c->ev(); rt.e1 = c->ev(); rt.e2 = c->ev(); rt.e3 = c->ev();
     CK(cudaEventRecord(rt.e0, st));
@@ -927,8 +956,12 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     CK(cudaEventRecord(rt.e3, st));
     CK(c->h_round.ensure(report_bytes));
     CK(cudaMemcpyAsync(c->h_round.p, rbase, report_bytes, cudaMemcpyDeviceToHost, st));
+    const double th2 = now_ms();
     rc = sync_stream(c);
     if (rc) return rc;
+    if (c->opt.trace)
+        fprintf(stderr, "[ejb trace] round %lld host: plan %.3f ms, enqueue %.3f ms, wait %.3f ms (%zu units, %zu tasks)\n", (long long)c->stats.rounds, th1 - th0, th2 - th1,
+                now_ms() - th2, n_units, total_tasks);
     c->stats.d2h_bytes += (int64_t)report_bytes;
     const Counters& h = *c->h_round.as<Counters>();
     const UnitOut* uo = reinterpret_cast<const UnitOut*>(c->h_round.as<char>() + sizeof(Counters));
@@ -1880,6 +1913,68 @@ int ejb_equiv_replay(int32_t n_rows, const int32_t* k1, const int32_t* k2, int64
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// f2: join_one for arbitrary pairs (define_mat's second use of the predicate, enclone_process/src/define_mat.rs:172,247)
+// ================================================================================================
+extern "C" int ejb_join_one_batch(ejb_ctx* c, const int32_t* k1, const int32_t* k2, int64_t n_pairs, const ejb_pair_out* out) {
+    if (!c || n_pairs < 0 || !out || (n_pairs > 0 && (!k1 || !k2))) return EJB_ERR_INVALID;
+    if (!c->prepared || c->shard_world != 1) return fail(c, EJB_ERR_INVALID, "ejb_join_one_batch needs the input of a completed single-context ejb_run / ejb_join");
+    if (n_pairs == 0) return EJB_OK;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int64_t N = c->din.n_rows;
+    CK(c->d_qofrow.ensure((size_t)std::max<int64_t>(N, 1) * 4));
+    CK(cudaMemsetAsync(c->d_qofrow.p, 0xff, (size_t)std::max<int64_t>(N, 1) * 4, st));
+    if (c->n_pos > 0) launch(c, k_q_of_row, nblk(c->n_pos, 256), 256, c->d_m_row.as<const int32_t>(), c->n_pos, c->d_qofrow.as<int32_t>());
+    const int64_t chunk = (int64_t)std::min<unsigned long long>(c->cand_cap, 1ull << 24);
+    CK(c->d_bk1.ensure((size_t)chunk * 4)); CK(c->d_bk2.ensure((size_t)chunk * 4));
+    CK(c->d_bpairs.ensure((size_t)chunk * 8)); CK(c->d_bslots.ensure((size_t)chunk * 4));
+    CK(c->d_btuples.ensure((size_t)chunk * sizeof(EdgeTuple)));
+    std::vector<EdgeTuple> host((size_t)std::min<int64_t>(chunk, n_pairs));
+    unsigned int* const d_bad = c->d_err.as<unsigned int>() + 40;   // scratch word of the header block
+    for (int64_t o = 0; o < n_pairs; o += chunk) {
+        const int64_t m = std::min<int64_t>(chunk, n_pairs - o);
+        char* const rbase = c->d_round.as<char>();
+        CK(cudaMemsetAsync(rbase, 0, offsetof(Counters, round_end), st));   // n_cand counts the pairs that reach stage 2
+        CK(cudaMemsetAsync(d_bad, 0, 4, st));
+        CK(cudaMemsetAsync(c->d_btuples.p, 0, (size_t)m * sizeof(EdgeTuple), st));   // pass = 0 unless stage 2 says otherwise
+        CK(cudaMemcpyAsync(c->d_bk1.p, k1 + o, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->d_bk2.p, k2 + o, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        launch(c, k_batch_pairs, nblk(m, 256), 256, c->d_bk1.as<const int32_t>(), c->d_bk2.as<const int32_t>(), m, N, c->d_qofrow.as<const int32_t>(),
+               c->d_m_sub.as<const int32_t>(), c->d_bpairs.as<uint2>(), c->d_bslots.as<uint32_t>(), CTR_FIELD(n_cand), d_bad);
+        int rc = run_stage2(c, c->d_bpairs.as<uint2>(), c->d_bslots.as<uint32_t>(), CTR_FIELD(n_cand), (unsigned long long)chunk, 1, c->d_btuples.as<EdgeTuple>());
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(host.data(), c->d_btuples.p, (size_t)m * sizeof(EdgeTuple), cudaMemcpyDeviceToHost, st));
+        CK(c->h_round.ensure(sizeof(Counters) + 64));
+        CK(cudaMemcpyAsync(c->h_round.p, c->d_round.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_round.as<char>() + sizeof(Counters), d_bad, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const Counters& h = *c->h_round.as<Counters>();
+        c->p1_count += h.n_newkeys;
+        if (*reinterpret_cast<const unsigned int*>(c->h_round.as<char>() + sizeof(Counters))) return fail(c, EJB_ERR_INVALID, "pair batch: row index out of range");
+        if (h.overflow || h.p1_full) return fail(c, EJB_ERR_OOM, "pair batch overflowed the work buffers");
+        if (h.n_errflag_panic) return fail(c, EJB_ERR_INVALID, "pair batch: input on which the reference panics");
+        if (c->p1_count > c->p1_cap / 4 && (rc = p1_cache_grow(c)) != EJB_OK) return rc;
+        for (int64_t i = 0; i < m; i++) {
+            const EdgeTuple& t = host[(size_t)i];
+            const int64_t g = o + i;
+            if (out->pass) out->pass[g] = (uint8_t)(t.pass != 0);
+            if (out->cd) out->cd[g] = t.cd;
+            if (out->nrefs) out->nrefs[g] = t.nrefs;
+            if (out->shares) { out->shares[2 * g] = t.sh0; out->shares[2 * g + 1] = t.sh1; }
+            if (out->indeps) { out->indeps[2 * g] = t.in0; out->indeps[2 * g + 1] = t.in1; }
+            if (out->k) out->k[g] = t.k;
+            if (out->d) out->d[g] = t.d;
+            if (out->n) out->n[g] = t.n;
+            if (out->p1) out->p1[g] = t.p1;
+            if (out->mult) out->mult[g] = t.mult;
+            if (out->score) out->score[g] = t.score;
+            if (out->err) out->err[g] = (uint8_t)t.err;
+        }
+    }
+    return EJB_OK;
+}
 
 // ================================================================================================
 // Multi-GPU: partial forests of sharded runs, merged on one context

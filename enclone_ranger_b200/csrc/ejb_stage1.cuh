@@ -193,6 +193,12 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         runi = __shfl_sync(0xffffffffu, runi, lane);   // identity shuffle: keeps the value in a register (ptxas otherwise re-derives it
                                                        // from the eight labels for every column, 14 instructions instead of none)
     }
+    // common label of the WARP's 16 rows (-2: mixed): a column tile whose 128 labels all equal it is skipped with one vote
+    int wuni = -2;
+    if (RUNI) {
+        const int r0 = __shfl_sync(0xffffffffu, runi, 0);
+        wuni = (runi != -2 && __all_sync(0xffffffffu, runi == r0)) ? r0 : -2;
+    }
     // row flags of the thread's eight rows as four byte masks (bit i = row i): a column's flag nibble selects, with four
     // operations, the rows whose pair with that column join_one rejects without looking at the sequences (flag_kill)
     uint32_t r_dead8 = 0, r_dom8 = 0, r_fd8 = 0, r_dd8 = 0;
@@ -252,7 +258,14 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         const bool diag = (cb == rb);
         const bool full = !diag && row_lo == 0 && row_lim >= TILE && col_lim >= TILE;
         const uint32_t q_c0 = (uint32_t)(sb.q0 + (int64_t)cb * TILE);
+        // 16 rows x 128 columns of one class (the inside of a connected clone): one vote for the whole warp tile
+        bool tile_uniform = false;
+        if (RUNI && wuni != -2) {
+            const int* lab = reinterpret_cast<const int*>(sc + NP * TILE);
+            tile_uniform = __all_sync(0xffffffffu, lab[lane] == wuni && lab[lane + 32] == wuni && lab[lane + 64] == wuni && lab[lane + 96] == wuni);
+        }
         const uint32_t* pc = sc + tx;   // this thread's column of the staged tile, advanced by 16 per step
+        if (!tile_uniform)
 #pragma unroll 1
         for (int j = 0; j < 8; j++, pc += 16) {
             const int c = j * 16 + tx;

@@ -25,7 +25,7 @@ namespace ejb {
 constexpr int TILE = 128;          // rows / cols of one stage-1 tile
 constexpr int S1_THREADS = 256;
 #ifndef S1_STRIP_N
-#define S1_STRIP_N 4
+#define S1_STRIP_N 16
 #endif
 constexpr int S1_STRIP = S1_STRIP_N;   // column tiles per CTA (row fragment stays in registers)
 constexpr int MAXW1 = 6;           // concatenated CDR3 (heavy+light) up to 192 nt on the fast path

@@ -198,6 +198,24 @@ class JoinContext:
         r = np.ascontiguousarray(roles, dtype=np.uint8)
         self._ck(self.L.ejb_set_row_roles(self.h, r.ctypes.data_as(C.POINTER(C.c_uint8)), r.size))
 
+    # --- f2: the pair predicate for arbitrary pairs (define_mat) ---
+    def join_one_batch(self, k1, k2):
+        """join_one(k1[i], k2[i]) for every pair of rows of the input of the last join()/run() on this context
+        (ejb_join_one_batch): dict with `passed` and the PotentialJoin members."""
+        k1 = np.ascontiguousarray(k1, dtype=np.int32)
+        k2 = np.ascontiguousarray(k2, dtype=np.int32)
+        n = len(k1)
+        out = dict(passed=np.zeros(n, np.uint8), cd=np.zeros(n, np.int32), nrefs=np.zeros(n, np.int32), shares=np.zeros(2 * n, np.int32),
+                   indeps=np.zeros(2 * n, np.int32), k=np.zeros(n, np.int32), d=np.zeros(n, np.int32), n=np.zeros(n, np.int32),
+                   p1=np.zeros(n, np.float64), mult=np.zeros(n, np.float64), score=np.zeros(n, np.float64), err=np.zeros(n, np.uint8))
+        ct = {np.dtype(np.uint8): C.c_uint8, np.dtype(np.int32): C.c_int32, np.dtype(np.float64): C.c_double}
+        po = _abi.EjbPairOut(**{f: out[f].ctypes.data_as(C.POINTER(ct[out[f].dtype])) for f in out})
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        self._ck(self.L.ejb_join_one_batch(self.h, ip(k1), ip(k2), n, C.byref(po)))
+        out["shares"] = out["shares"].reshape(-1, 2)
+        out["indeps"] = out["indeps"].reshape(-1, 2)
+        return out
+
     # --- sharded join: every context holds the whole input, joins its share, one context merges (multi-GPU) ---
     def set_shard(self, rank, world):
         self._ck(self.L.ejb_set_shard(self.h, int(rank), int(world)))

@@ -320,6 +320,21 @@ int ejb_measure_peaks(ejb_ctx* ctx, double* popc_per_s, double* lop3_per_s, doub
  * caller concatenates the per-rank edge lists, sorts them by (k1, k2) and calls ejb_equiv_replay. */
 int ejb_set_shard(ejb_ctx* ctx, int rank, int world);
 
+/* join_one for ARBITRARY pairs of rows of the input of the last completed ejb_join / ejb_run on this context: the second use the
+ * reference makes of the pair predicate, define_mat's extra raw joins (enclone_process/src/define_mat.rs:172,247).  Same
+ * kernels as the join (k_stage2a / k_stage2_slow / k_p1 / k_stage2b), without the same-class skip: every pair is decided on its
+ * own, in the ORDER given (join_one(k1, k2) reads a few facts from its first argument only).  pass[i] = what join_one returns
+ * (the caller filters on equal lens first, as define_mat.rs does; pairs with different lens or a row without exactly two
+ * chains are answered 0).  The other arrays receive the PotentialJoin members join_one would have pushed (meaningful where
+ * pass[i] = 1; any of them may be NULL).  Caller-allocated: [n_pairs], shares / indeps [2 * n_pairs].                    */
+typedef struct ejb_pair_out {
+    uint8_t* pass;
+    int32_t *cd, *nrefs, *shares, *indeps, *k, *d, *n;
+    double *p1, *mult, *score;
+    uint8_t* err;
+} ejb_pair_out;
+int ejb_join_one_batch(ejb_ctx* ctx, const int32_t* k1, const int32_t* k2, int64_t n_pairs, const ejb_pair_out* out);
+
 /* Sharded join across several contexts (one per GPU; one process per GPU under torchrun, or the worker threads of a context
  * created with n_devices > 1).  EVERY context uploads the whole input and, after ejb_set_shard(rank, world), ejb_run joins only
  * its share: whole sub-buckets by longest-processing-time assignment on a pair-count cost model, the heaviest sub-buckets cut

@@ -707,6 +707,62 @@ static T* dup_vec(const std::vector<T>& v) {
     return p;
 }
 
+static void make_in(oracle::In& I, const ejb_params* p, const ejb_input* in) {
+    using namespace oracle;
+    I.in = in;
+    I.p = p;
+    // canonical seg ids by content
+    std::vector<std::pair<std::string, int>> v;
+    for (int64_t s = 0; s < in->n_segs; s++) {
+        std::string str((const char*)in->seg_bytes + in->seg_off[s], (size_t)(in->seg_off[s + 1] - in->seg_off[s]));
+        for (auto& c : str) c = (char)kBits2Base[base2bit((uint8_t)c)];
+        v.emplace_back(std::move(str), (int)s);
+    }
+    std::sort(v.begin(), v.end());
+    I.seg_canon.assign(in->n_segs, 0);
+    int id = -1;
+    for (size_t q = 0; q < v.size(); q++) {
+        if (q == 0 || v[q].first != v[q - 1].first) id++;
+        I.seg_canon[v[q].second] = id;
+    }
+}
+
+// join_one (join_one.rs:66-887) for arbitrary pairs, as define_mat calls it (enclone_process/src/define_mat.rs:172,247): the
+// checker of ejb_join_one_batch.  Outputs are zero where join_one returns false.
+extern "C" int oracle_join_one_batch(const ejb_params* p, const ejb_input* in, const int32_t* k1, const int32_t* k2, int64_t n, uint8_t* pass,
+                                     int32_t* cd, int32_t* nrefs, int32_t* shares, int32_t* indeps, int32_t* k, int32_t* d, int32_t* nn, double* p1,
+                                     double* mult, double* score, uint8_t* err) {
+    using namespace oracle;
+    const SrTable& sr = sr_table();
+    In I;
+    make_in(I, p, in);
+    for (int64_t i = 0; i < n; i++) {
+        std::vector<Pot> pot;
+        std::string why;
+        pass[i] = 0;
+        cd[i] = nrefs[i] = shares[2 * i] = shares[2 * i + 1] = indeps[2 * i] = indeps[2 * i + 1] = k[i] = d[i] = nn[i] = 0;
+        p1[i] = mult[i] = score[i] = 0.0;
+        err[i] = 0;
+        // the caller's filter (define_mat.rs:169, 244): equal lens
+        bool same = in->row_nchains[k1[i]] == in->row_nchains[k2[i]];
+        for (int m = 0; same && m < in->row_nchains[k1[i]] && m < 2; m++) same = in->row_len[2 * (int64_t)k1[i] + m] == in->row_len[2 * (int64_t)k2[i] + m];
+        if (!same) continue;
+        const JoinOneStatus st = join_one(k1[i], k2[i], I, sr, pot, why);
+        if (st == J_PANIC) return EJB_ERR_INVALID;
+        if (st != J_TRUE || pot.empty()) continue;
+        const Pot& q = pot.back();
+        pass[i] = 1;
+        cd[i] = (int32_t)q.cd;
+        nrefs[i] = q.nrefs;
+        shares[2 * i] = (int32_t)q.shares[0]; shares[2 * i + 1] = (int32_t)q.shares[1];
+        indeps[2 * i] = (int32_t)q.indeps[0]; indeps[2 * i + 1] = (int32_t)q.indeps[1];
+        k[i] = (int32_t)q.k; d[i] = (int32_t)q.d; nn[i] = (int32_t)q.n;
+        p1[i] = q.p1; mult[i] = q.mult; score[i] = q.score;
+        err[i] = q.err ? 1 : 0;
+    }
+    return EJB_OK;
+}
+
 int oracle_join(const ejb_params* p, const ejb_input* in, int nthreads, oracle_result* out) {
     using namespace oracle;
     memset(out, 0, sizeof(*out));
@@ -716,23 +772,7 @@ int oracle_join(const ejb_params* p, const ejb_input* in, int nthreads, oracle_r
     }
     const SrTable& sr = sr_table();
     In I;
-    I.in = in;
-    I.p = p;
-    {  // canonical seg ids by content
-        std::vector<std::pair<std::string, int>> v;
-        for (int64_t s = 0; s < in->n_segs; s++) {
-            std::string str((const char*)in->seg_bytes + in->seg_off[s], (size_t)(in->seg_off[s + 1] - in->seg_off[s]));
-            for (auto& c : str) c = (char)kBits2Base[base2bit((uint8_t)c)];
-            v.emplace_back(std::move(str), (int)s);
-        }
-        std::sort(v.begin(), v.end());
-        I.seg_canon.assign(in->n_segs, 0);
-        int id = -1;
-        for (size_t q = 0; q < v.size(); q++) {
-            if (q == 0 || v[q].first != v[q - 1].first) id++;
-            I.seg_canon[v[q].second] = id;
-        }
-    }
+    make_in(I, p, in);
     const int64_t N = in->n_rows;
 
     // join.rs:68-88 — buckets = runs of equal lens

@@ -110,6 +110,28 @@ def run(params, c_input_ptr, threads=0):
     return out
 
 
+def join_one_batch(params, c_input_ptr, k1, k2):
+    """join_one for arbitrary (k1, k2) pairs (define_mat's use): dict with pass + the PotentialJoin members."""
+    L = load_oracle()
+    k1 = np.ascontiguousarray(k1, dtype=np.int32)
+    k2 = np.ascontiguousarray(k2, dtype=np.int32)
+    n = len(k1)
+    out = dict(passed=np.zeros(n, np.uint8), cd=np.zeros(n, np.int32), nrefs=np.zeros(n, np.int32), shares=np.zeros(2 * n, np.int32),
+               indeps=np.zeros(2 * n, np.int32), k=np.zeros(n, np.int32), d=np.zeros(n, np.int32), n=np.zeros(n, np.int32),
+               p1=np.zeros(n, np.float64), mult=np.zeros(n, np.float64), score=np.zeros(n, np.float64), err=np.zeros(n, np.uint8))
+    ct = {np.dtype(np.uint8): C.c_uint8, np.dtype(np.int32): C.c_int32, np.dtype(np.float64): C.c_double}
+    ptr = lambda a: a.ctypes.data_as(C.POINTER(ct[a.dtype]))
+    L.oracle_join_one_batch.restype = C.c_int
+    rc = L.oracle_join_one_batch(C.byref(params), c_input_ptr, ptr(k1), ptr(k2), C.c_int64(n), ptr(out["passed"]), ptr(out["cd"]), ptr(out["nrefs"]),
+                                 ptr(out["shares"]), ptr(out["indeps"]), ptr(out["k"]), ptr(out["d"]), ptr(out["n"]), ptr(out["p1"]), ptr(out["mult"]),
+                                 ptr(out["score"]), ptr(out["err"]))
+    if rc != 0:
+        raise RuntimeError(f"oracle_join_one_batch failed ({rc}): the reference would panic on one of the pairs")
+    out["shares"] = out["shares"].reshape(-1, 2)
+    out["indeps"] = out["indeps"].reshape(-1, 2)
+    return out
+
+
 def p1(k, d, n):
     L = load_oracle()
     v = C.c_double()

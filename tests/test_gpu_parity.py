@@ -437,3 +437,44 @@ def test_sync_and_launch_accounting(gpu_ctx):
     assert st["boruvka_iterations"] >= st["rounds"] - 1
     assert 0 < st["pairs_distance_computed"] <= st["pairs_evaluated"] * 1.2
     assert st["pairs_distance_full"] <= st["pairs_distance_computed"]
+
+
+@pytest.mark.parametrize("config,cells,seed", [(1, 30000, 61), (3, 20000, 62), (2, 60000, 63), (0, 8000, 64)])
+def test_join_one_batch_matches_oracle(gpu_ctx, config, cells, seed):
+    """f2: define_mat's second use of the pair predicate (enclone_process/src/define_mat.rs:172,247).  join_one for arbitrary
+    (k1, k2) lists — joined pairs in both orders, pairs inside one class (no class skip here), random pairs of one lens
+    bucket, pairs across buckets, a row with itself, rows without two chains — must equal the oracle's join_one, members
+    included."""
+    rep = E.generate(config, n_cells=cells, seed=seed)
+    inp = rep.to_join_input()
+    p = E.default_params(bool(rep.config.is_bcr))
+    res = gpu_ctx.join(p, inp.to_packed().to_packed_cdr3())
+    rng = np.random.default_rng(seed)
+    N = inp.n_rows
+    lens = inp.a["row_len"].reshape(-1, 2)
+    head = np.ones(N, dtype=bool)
+    head[1:] = (lens[1:] != lens[:-1]).any(axis=1) | (inp.a["row_nchains"][1:] != inp.a["row_nchains"][:-1])
+    bucket = np.cumsum(head) - 1
+    start = np.nonzero(head)[0]
+    size = np.diff(np.append(start, N))
+    k1, k2 = [res.edge_k1, res.edge_k2], [res.edge_k2, res.edge_k1]           # joined pairs, both orders
+    lab = res.labels
+    order = np.argsort(lab, kind="stable")                                       # pairs inside one class that are not forest edges
+    same = np.nonzero(lab[order][1:] == lab[order][:-1])[0][:4000]
+    k1.append(order[same + 1]); k2.append(order[same])
+    a = rng.integers(0, N, 20000)                                                # random pairs of one lens bucket
+    b = start[bucket[a]] + rng.integers(0, 1 << 30, 20000) % size[bucket[a]]
+    k1.append(a); k2.append(b)
+    k1.append(rng.integers(0, N, 3000)); k2.append(rng.integers(0, N, 3000))     # arbitrary pairs (mostly different lens)
+    k1.append(np.arange(0, N, max(N // 500, 1))); k2.append(np.arange(0, N, max(N // 500, 1)))   # a row with itself
+    k1 = np.concatenate(k1).astype(np.int32)
+    k2 = np.concatenate(k2).astype(np.int32)
+    want = pyoracle.join_one_batch(p, inp.c_ptr(), k1, k2)
+    got = gpu_ctx.join_one_batch(k1, k2)
+    assert np.array_equal(got["passed"], want["passed"]), f"{int((got['passed'] != want['passed']).sum())} of {len(k1)} decisions differ"
+    ok = want["passed"] == 1
+    assert ok.sum() >= len(res.edge_k1), "every forest edge is a pair join_one accepts"
+    for f in ("cd", "nrefs", "shares", "indeps", "k", "d", "n", "p1", "mult", "score", "err"):
+        assert np.array_equal(got[f][ok], want[f][ok]), f
+    # the reverse order of a joined pair is accepted too unless an order-dependent test says otherwise: whatever it is, equal to the oracle
+    assert got["passed"][len(res.edge_k1):2 * len(res.edge_k1)].sum() > 0
