@@ -315,25 +315,25 @@ DevParams make_dev_params(const ejb_params& p) {
 #define CTR_FIELD(f) (reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->d_round.p) + offsetof(Counters, f)))
 
 template <int W1, int MODE>
-void launch_stage1_wm(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks, unsigned long long* unit_cand) {
+void launch_stage1_wm(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks, unsigned long long* unit_cand, int strip) {
     launch(c, k_stage1<W1, MODE>, (unsigned int)n_ctas, S1_THREADS, c->d_subs.as<SubBucket>(), tasks, n_tasks, c->d_cdr3w.as<uint32_t>(), c->d_labq.as<int32_t>(),
            c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr(), unit_cand, c->d_tagq.as<unsigned long long>(),
-           c->d_deadq.as<unsigned long long>(), c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>());
+           c->d_deadq.as<unsigned long long>(), c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>(), strip);
 }
 template <int W1>
-void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks, unsigned long long* unit_cand) {
+void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks, unsigned long long* unit_cand, int strip) {
     switch (c->opt.s1_mode & (c->tags_on ? 3 : 1)) {
-        case 0: launch_stage1_wm<W1, 0>(c, n_ctas, tasks, n_tasks, unit_cand); break;
-        case 1: launch_stage1_wm<W1, S1_RUNI>(c, n_ctas, tasks, n_tasks, unit_cand); break;
-        case 2: launch_stage1_wm<W1, S1_TAGS>(c, n_ctas, tasks, n_tasks, unit_cand); break;
-        default: launch_stage1_wm<W1, S1_RUNI | S1_TAGS>(c, n_ctas, tasks, n_tasks, unit_cand); break;
+        case 0: launch_stage1_wm<W1, 0>(c, n_ctas, tasks, n_tasks, unit_cand, strip); break;
+        case 1: launch_stage1_wm<W1, S1_RUNI>(c, n_ctas, tasks, n_tasks, unit_cand, strip); break;
+        case 2: launch_stage1_wm<W1, S1_TAGS>(c, n_ctas, tasks, n_tasks, unit_cand, strip); break;
+        default: launch_stage1_wm<W1, S1_RUNI | S1_TAGS>(c, n_ctas, tasks, n_tasks, unit_cand, strip); break;
     }
 }
 
 // stage-1 for sub-buckets whose CDR3s exceed the fast path: every not-yet-connected pair is a candidate
 __global__ void k_stage1_nofilter(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, int n_tasks,
                                   const int32_t* __restrict__ labq, uint2* __restrict__ cand, unsigned long long cand_cap, Counters* ctr,
-                                  unsigned long long* __restrict__ unit_cand) {
+                                  unsigned long long* __restrict__ unit_cand, int strip) {
     const int64_t cta = blockIdx.x;
     int lo = 0, hi = n_tasks - 1;
     while (lo < hi) {
@@ -343,9 +343,9 @@ __global__ void k_stage1_nofilter(const SubBucket* __restrict__ subs, const RowT
     const RowTask t = tasks[lo];
     const SubBucket sb = subs[t.sub];
     const int nb = (sb.n + TILE - 1) / TILE;
-    const int cb_first = t.rb + (int)(cta - t.cta0) * S1_STRIP;
+    const int cb_first = t.rb + (int)(cta - t.cta0) * strip;
     unsigned long long ev = 0;
-    for (int cb = cb_first; cb < nb && cb < cb_first + S1_STRIP; cb++) {
+    for (int cb = cb_first; cb < nb && cb < cb_first + strip; cb++) {
         for (int idx = threadIdx.x; idx < TILE * TILE; idx += blockDim.x) {
             const int rl = idx >> 7;
             const int r = t.rb * TILE + rl, cc = cb * TILE + (idx & 127);
@@ -833,12 +833,25 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     std::vector<RowTask> tasks[MAXW1 + 1];
     std::vector<ejb_ctx::TaskMeta> metas[MAXW1 + 1];
     int64_t nctas[MAXW1 + 1] = {0};
+    // column tiles per CTA, per launch: short strips keep the early rounds (a few rows of every sub-bucket) wide enough to fill
+    // the GPU, long strips amortise the per-CTA prologue (task lookup, row fragment) once a launch has tens of thousands of CTAs
+    int strip_of[MAXW1 + 1];
+    {
+        int64_t ctas4[MAXW1 + 1] = {0};
+        for (const Unit& u : units) {
+            const SubBucket& sb = subs[u.sub];
+            const int nb = (sb.n + TILE - 1) / TILE;
+            for (int rb = u.r0 / TILE; rb * TILE < u.r1; rb++) ctas4[sb.W1] += (nb - rb + 3) / 4;
+        }
+        for (int w = 0; w <= MAXW1; w++) strip_of[w] = ctas4[w] > 65536 ? S1_STRIP : (ctas4[w] > 16384 ? 8 : 4);
+    }
     std::vector<UnitDesc> udesc(units.size());
     std::vector<int> ugroup(units.size());
     for (size_t ui = 0; ui < units.size(); ui++) {
         const Unit& u = units[ui];
         const SubBucket& sb = subs[u.sub];
         const int nb = (sb.n + TILE - 1) / TILE;
+        const int strip = strip_of[sb.W1];
         const size_t first = tasks[sb.W1].size();
         for (int rb = u.r0 / TILE; rb * TILE < u.r1; rb++) {
             RowTask t;
@@ -851,7 +864,7 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
             t.cta0 = nctas[sb.W1];
             tasks[sb.W1].push_back(t);
             metas[sb.W1].push_back({(int32_t)ui, rb * TILE + t.row_lo, rb * TILE + t.row_hi});
-            nctas[sb.W1] += (nb - rb + S1_STRIP - 1) / S1_STRIP;
+            nctas[sb.W1] += (nb - rb + strip - 1) / strip;
         }
         UnitDesc& d = udesc[ui];
         d.sub = u.sub;
@@ -892,8 +905,13 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     CK(c->h_stage.ensure(total_tasks * sizeof(RowTask) + n_units * sizeof(UnitDesc) + 64));
     memcpy(c->h_stage.p, all_tasks.data(), total_tasks * sizeof(RowTask));
     memcpy(c->h_stage.as<char>() + total_tasks * sizeof(RowTask), udesc.data(), n_units * sizeof(UnitDesc));
+#ifdef EJB_NO_STAGE
+    CK(cudaMemcpyAsync(c->d_tasks.p, all_tasks.data(), total_tasks * sizeof(RowTask), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_units.p, udesc.data(), n_units * sizeof(UnitDesc), cudaMemcpyHostToDevice, st));
+#else
     CK(cudaMemcpyAsync(c->d_tasks.p, c->h_stage.p, total_tasks * sizeof(RowTask), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->d_units.p, c->h_stage.as<char>() + total_tasks * sizeof(RowTask), n_units * sizeof(UnitDesc), cudaMemcpyHostToDevice, st));
+#endif
     RoundTimes rt;
     rt.e0 = c->ev(); rt.e1 = c->ev(); rt.e2 = c->ev(); rt.e3 = c->ev();
     CK(cudaEventRecord(rt.e0, st));
@@ -907,14 +925,14 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
         switch (w) {
             case 0:
                 launch(c, k_stage1_nofilter, (unsigned int)nctas[0], 256, c->d_subs.as<const SubBucket>(), dt, nt, c->d_labq.as<const int32_t>(), c->d_cand.as<uint2>(),
-                       c->cand_cap, c->d_ctr(), d_ucand);
+                       c->cand_cap, c->d_ctr(), d_ucand, strip_of[0]);
                 break;
-            case 1: launch_stage1_w<1>(c, nctas[1], dt, nt, d_ucand); break;
-            case 2: launch_stage1_w<2>(c, nctas[2], dt, nt, d_ucand); break;
-            case 3: launch_stage1_w<3>(c, nctas[3], dt, nt, d_ucand); break;
-            case 4: launch_stage1_w<4>(c, nctas[4], dt, nt, d_ucand); break;
-            case 5: launch_stage1_w<5>(c, nctas[5], dt, nt, d_ucand); break;
-            case 6: launch_stage1_w<6>(c, nctas[6], dt, nt, d_ucand); break;
+            case 1: launch_stage1_w<1>(c, nctas[1], dt, nt, d_ucand, strip_of[1]); break;
+            case 2: launch_stage1_w<2>(c, nctas[2], dt, nt, d_ucand, strip_of[2]); break;
+            case 3: launch_stage1_w<3>(c, nctas[3], dt, nt, d_ucand, strip_of[3]); break;
+            case 4: launch_stage1_w<4>(c, nctas[4], dt, nt, d_ucand, strip_of[4]); break;
+            case 5: launch_stage1_w<5>(c, nctas[5], dt, nt, d_ucand, strip_of[5]); break;
+            case 6: launch_stage1_w<6>(c, nctas[6], dt, nt, d_ucand, strip_of[6]); break;
         }
         c->stats.stage1_launches++;
     }

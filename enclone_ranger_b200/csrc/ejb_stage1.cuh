@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
                                                        unsigned long long cand_cap, Counters* __restrict__ ctr,
                                                        unsigned long long* __restrict__ unit_cand,
                                                        const unsigned long long* __restrict__ tagq, const unsigned long long* __restrict__ deadq,
-                                                       const unsigned long long* __restrict__ donq, const uint32_t* __restrict__ flagq) {
+                                                       const unsigned long long* __restrict__ donq, const uint32_t* __restrict__ flagq, int strip) {
     constexpr bool RUNI = (MODE & S1_RUNI) != 0, TAGS = (MODE & S1_TAGS) != 0;
     constexpr int NP = 2 * W1;            // plane-words per row
     constexpr int TAG0 = (NP + 1) * TILE; // word offset of the staged reference-set tags (uint64 x TILE), then the dead tags, then the donor sets
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     if (sb.W1 != W1) return;  // launched once per W1; other widths are handled by their own launch
     const int nb = (sb.n + TILE - 1) / TILE;
     const int rb = t.rb;
-    const int cb_first = rb + (int)(cta - t.cta0) * S1_STRIP;
+    const int cb_first = rb + (int)(cta - t.cta0) * strip;   // strip: column tiles per CTA of this launch (host: 4 .. S1_STRIP)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;
 
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     if (tid == 0) {
         int n = 0;
         const int lr = blk_lab[sb.blk0 + rb];
-        for (int c = cb_first; c < nb && c < cb_first + S1_STRIP; c++) {
+        for (int c = cb_first; c < nb && c < cb_first + strip; c++) {
             const int lc = blk_lab[sb.blk0 + c];
             if (lr >= 0 && lr == lc) continue;
             s_cbs[n++] = c;
@@ -193,12 +193,6 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         runi = __shfl_sync(0xffffffffu, runi, lane);   // identity shuffle: keeps the value in a register (ptxas otherwise re-derives it
                                                        // from the eight labels for every column, 14 instructions instead of none)
     }
-    // common label of the WARP's 16 rows (-2: mixed): a column tile whose 128 labels all equal it is skipped with one vote
-    int wuni = -2;
-    if (RUNI) {
-        const int r0 = __shfl_sync(0xffffffffu, runi, 0);
-        wuni = (runi != -2 && __all_sync(0xffffffffu, runi == r0)) ? r0 : -2;
-    }
     // row flags of the thread's eight rows as four byte masks (bit i = row i): a column's flag nibble selects, with four
     // operations, the rows whose pair with that column join_one rejects without looking at the sequences (flag_kill)
     uint32_t r_dead8 = 0, r_dom8 = 0, r_fd8 = 0, r_dd8 = 0;
@@ -258,14 +252,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         const bool diag = (cb == rb);
         const bool full = !diag && row_lo == 0 && row_lim >= TILE && col_lim >= TILE;
         const uint32_t q_c0 = (uint32_t)(sb.q0 + (int64_t)cb * TILE);
-        // 16 rows x 128 columns of one class (the inside of a connected clone): one vote for the whole warp tile
-        bool tile_uniform = false;
-        if (RUNI && wuni != -2) {
-            const int* lab = reinterpret_cast<const int*>(sc + NP * TILE);
-            tile_uniform = __all_sync(0xffffffffu, lab[lane] == wuni && lab[lane + 32] == wuni && lab[lane + 64] == wuni && lab[lane + 96] == wuni);
-        }
         const uint32_t* pc = sc + tx;   // this thread's column of the staged tile, advanced by 16 per step
-        if (!tile_uniform)
 #pragma unroll 1
         for (int j = 0; j < 8; j++, pc += 16) {
             const int c = j * 16 + tx;
