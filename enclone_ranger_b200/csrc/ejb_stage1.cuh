@@ -208,6 +208,12 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     }
     const int row_lo = t.row_lo;
     const int row_lim = min(sb.n - rb * TILE, t.row_hi);  // valid local rows are row_lo <= r < row_lim
+    // a warp none of whose 16 rows belongs to the unit (the first rounds process 2 .. 32 rows of a block) has nothing to do in any
+    // column tile: it only releases the buffers
+    bool warp_rows = false;
+#pragma unroll
+    for (int i = 0; i < 8; i++) warp_rows |= (i * 16 + ty >= row_lo) & (i * 16 + ty < row_lim);
+    warp_rows = __any_sync(0xffffffffu, warp_rows);
     const int maxcd = sb.maxcd;
     const uint32_t q_r0 = (uint32_t)(sb.q0 + (int64_t)rb * TILE);
     unsigned long long evaluated = 0;                 // thread 0 only
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         const uint32_t q_c0 = (uint32_t)(sb.q0 + (int64_t)cb * TILE);
         const uint32_t* pc = sc + tx;   // this thread's column of the staged tile, advanced by 16 per step
 #pragma unroll 1
-        for (int j = 0; j < 8; j++, pc += 16) {
+        for (int j = warp_rows ? 0 : 8; j < 8; j++, pc += 16) {
             const int c = j * 16 + tx;
             const int clab = (int)pc[NP * TILE];
             if (RUNI && __all_sync(0xffffffffu, clab == runi)) continue;   // 16 rows x 16 columns of one class: one vote instead of eight

@@ -435,6 +435,18 @@ __global__ void __launch_bounds__(256, S2A_MINB) k_stage2a(S2Ctx X, const uint2*
         me.npad = (uint32_t)sb.npad;
         me.tot1 = tot1;
         me.tot2 = tot2;
+        // The column row of a candidate is cold more often than not (a row is a column of only a few candidates): every owner
+        // lane asks L2 for the lines of its two records now, so that the plane loads of phase 1 — eight candidates at a time —
+        // find them there instead of paying the DRAM latency one batch after the other.
+        if (fast && !memo_dead) {
+            const char* r1p = reinterpret_cast<const char*>(X.rowstore + me.rec1);
+            const char* r2p = reinterpret_cast<const char*>(X.rowstore + me.rec2);
+            const int rec_bytes = sb.rec_u4 * 16;
+            for (int o = 0; o < rec_bytes; o += 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(r2p + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(r1p + o));
+            }
+        }
         // ---- phase 1 ----
         if (!__any_sync(0xffffffffu, wide)) {
 #pragma unroll 1

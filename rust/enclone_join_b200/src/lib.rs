@@ -5,7 +5,8 @@
 //! empty, as under the default `quiet = true`), same return type: the `EquivRel` is rebuilt with
 //! `EquivRel::from_raw(x, y, z)` (equiv/src/lib.rs:57) from the vectors the library replayed.
 //!
-//! Written against the reference's types; NOT compiled in the development image (no Rust toolchain).
+//! Written against the reference's types; NOT compiled in the development image (no Rust toolchain).  The struct mirrors are
+//! checked at run time against the sizes the library reports (ejb_abi_sizes) and the ABI version (4).
 
 use debruijn::Mer;
 use enclone_core::defs::{CloneInfo, EncloneControl, ExactClonotype};
@@ -48,6 +49,7 @@ pub mod sys {
         pub n_segs: i64, pub seg_off: *const i64, pub seg_bytes: *const u8,
         pub n_refs: i64, pub ref_off: *const i64, pub ref_bytes: *const u8, pub ref_name_id: *const i32,
         pub row_tig2_off: *const i64, pub tig2_words: *const u32, pub n_tig2_words: i64,
+        pub row_cdr32_off: *const i64, pub cdr32_words: *const u32, pub n_cdr32_words: i64,
     }
 
     #[repr(C)]
@@ -59,6 +61,19 @@ pub mod sys {
         pub ms_device_total: f64,
         pub ms_total: f64,
         pub two_ref: [i64; 5],        // stage1_ref_kills, stage2_two_ref, stage2_memo_dead, stage2_degr_dead, stage1_donor_kills
+        pub executed: [i64; 8],       // pairs_distance_computed, pairs_distance_full, popc_executed_stage1, stage1_flag_skips, host_syncs,
+                                      // boruvka_iterations, p1_cache_slots, n_devices
+        pub ms_partition: f64,
+        pub ms_merge: f64,
+    }
+
+    /// Caller-allocated outputs of ejb_join_one_batch (any pointer may be null).
+    #[repr(C)]
+    pub struct EjbPairOut {
+        pub pass: *mut u8,
+        pub cd: *mut i32, pub nrefs: *mut i32, pub shares: *mut i32, pub indeps: *mut i32, pub k: *mut i32, pub d: *mut i32, pub n: *mut i32,
+        pub p1: *mut f64, pub mult: *mut f64, pub score: *mut f64,
+        pub err: *mut u8,
     }
 
     #[repr(C)]
@@ -87,7 +102,50 @@ pub mod sys {
         /// their partial forests on rank 0.
         pub fn ejb_set_row_roles(ctx: *mut EjbCtx, roles: *const u8, n_rows: i64) -> c_int;
         pub fn ejb_forest_merge(n_rows: i32, k1: *const i32, k2: *const i32, n_edges: i64, keep: *mut u8) -> c_int;
+        /// join_one for arbitrary pairs of the rows of the last ejb_join on this context (define_mat.rs:172,247).
+        pub fn ejb_join_one_batch(ctx: *mut EjbCtx, k1: *const i32, k2: *const i32, n_pairs: i64, out: *const EjbPairOut) -> c_int;
+        pub fn ejb_abi_version() -> c_int;
     }
+}
+
+/// ONE context per process (ejb_create builds the Stirling table on the device and allocates the work buffers: not per call).
+/// `ENCLONE_JOIN_GPUS=n` makes it span the first n devices; ejb_join then shards the buckets over them by itself.
+struct Ctx(*mut sys::EjbCtx);
+unsafe impl Send for Ctx {}
+unsafe impl Sync for Ctx {}
+static CTX: std::sync::OnceLock<std::sync::Mutex<Ctx>> = std::sync::OnceLock::new();
+fn context() -> &'static std::sync::Mutex<Ctx> {
+    CTX.get_or_init(|| unsafe {
+        assert!(sys::ejb_abi_version() == 4, "enclone_join_b200: library / binding ABI mismatch");
+        let mut sizes = [0i64; 4];
+        sys::ejb_abi_sizes(sizes.as_mut_ptr());
+        assert!(
+            sizes == [std::mem::size_of::<sys::EjbParams>() as i64, std::mem::size_of::<sys::EjbInput>() as i64,
+                      std::mem::size_of::<sys::EjbStats>() as i64, std::mem::size_of::<sys::EjbResult>() as i64],
+            "enclone_join_b200: struct mirrors out of date"
+        );
+        let n: c_int = std::env::var("ENCLONE_JOIN_GPUS").ok().and_then(|v| v.parse().ok()).unwrap_or(1);
+        let mut ctx: *mut sys::EjbCtx = std::ptr::null_mut();
+        let rc = sys::ejb_create(&mut ctx, std::ptr::null(), n);
+        assert!(rc == 0, "enclone_join_b200: ejb_create failed ({rc}); a CUDA device is required (no CPU fallback)");
+        std::sync::Mutex::new(Ctx(ctx))
+    })
+}
+
+/// The second use of the pair predicate (enclone_process/src/define_mat.rs:172,247): `join_one(k1, k2, ..)` for many pairs of
+/// `info` rows at once, on the rows of the last `join_exacts` call.  Returns what join_one returns for each pair.
+pub fn join_one_batch(pairs: &[(usize, usize)]) -> Vec<bool> {
+    let (k1, k2): (Vec<i32>, Vec<i32>) = pairs.iter().map(|(a, b)| (*a as i32, *b as i32)).unzip();
+    let mut pass = vec![0u8; pairs.len()];
+    let out = sys::EjbPairOut {
+        pass: pass.as_mut_ptr(), cd: std::ptr::null_mut(), nrefs: std::ptr::null_mut(), shares: std::ptr::null_mut(), indeps: std::ptr::null_mut(),
+        k: std::ptr::null_mut(), d: std::ptr::null_mut(), n: std::ptr::null_mut(), p1: std::ptr::null_mut(), mult: std::ptr::null_mut(),
+        score: std::ptr::null_mut(), err: std::ptr::null_mut(),
+    };
+    let g = context().lock().unwrap();
+    let rc = unsafe { sys::ejb_join_one_batch(g.0, k1.as_ptr(), k2.as_ptr(), pairs.len() as i64, &out) };
+    assert!(rc == 0, "enclone_join_b200: ejb_join_one_batch failed ({rc})");
+    pass.into_iter().map(|b| b != 0).collect()
 }
 
 /// EJB_MODE_* bits for the join modes the CUDA path rejects (they are unreachable from enclone_ranger).
@@ -138,6 +196,8 @@ pub fn join_exacts(
     let (mut tig_bytes, mut cdr3_bytes) = (Vec::<u8>::new(), Vec::<u8>::new());
     let mut row_tig2_off = vec![-1i64; 2 * n];
     let mut tig2_words = Vec::<u32>::new();   // 2-bit packed contigs (from tigsp) for rows without indel marks
+    let mut row_cdr32_off = vec![-1i64; 2 * n];
+    let mut cdr32_words = Vec::<u32>::new();  // 2-bit packed CDR3s (same packing); a CDR3 with another byte stays ASCII
     let mut segs: HashMap<Vec<u8>, i32> = HashMap::new();   // DnaString content -> seg id (join_one.rs:331 compares content)
     let (mut seg_off, mut seg_bytes) = (vec![0i64], Vec::<u8>::new());
     let mut seg_id = |s: &debruijn::dna_string::DnaString| -> i32 {
@@ -150,6 +210,9 @@ pub fn join_exacts(
         })
     };
     for (k, x) in info.iter().enumerate() {
+        // the reference indexes exact_clonotypes with clonotype_index for donors / ncells / shares (join_one.rs:303-304,
+        // join.rs:146) and with clonotype_id for to_bc / finish_join; build_info sets both to the same value (info.rs:297-298)
+        assert!(x.clonotype_id == x.clonotype_index, "enclone_join_b200: info[{k}].clonotype_id != clonotype_index");
         row_nchains.push(x.lens.len() as i32);
         row_exact.push(x.clonotype_id as i32);
         for m in 0..x.lens.len().min(2) {
@@ -174,9 +237,23 @@ pub fn join_exacts(
             row_has_del[i] = x.has_del[m] as u8;
             row_vs[i] = seg_id(&x.vs[m]);
             row_js[i] = seg_id(&x.js[m]);
-            row_cdr3_off[i] = cdr3_bytes.len() as i64;
             row_cdr3_len[i] = x.cdr3s[m].len() as i32;
-            cdr3_bytes.extend_from_slice(x.cdr3s[m].as_bytes());
+            let c3 = x.cdr3s[m].as_bytes();
+            if c3.iter().all(|b| matches!(b, b'A' | b'C' | b'G' | b'T')) {
+                row_cdr32_off[i] = cdr32_words.len() as i64;
+                row_cdr3_off[i] = -1;
+                for w in c3.chunks(16) {
+                    let mut v = 0u32;
+                    for (j, b) in w.iter().enumerate() {
+                        let code = match b { b'C' => 1u32, b'G' => 2, b'T' => 3, _ => 0 };
+                        v |= code << (2 * j);
+                    }
+                    cdr32_words.push(v);
+                }
+            } else {
+                row_cdr3_off[i] = cdr3_bytes.len() as i64;
+                cdr3_bytes.extend_from_slice(c3);
+            }
             row_exact_col[i] = x.exact_cols[m] as i32;
         }
     }
@@ -245,18 +322,17 @@ pub fn join_exacts(
         n_segs: (seg_off.len() - 1) as i64, seg_off: seg_off.as_ptr(), seg_bytes: seg_bytes.as_ptr(),
         n_refs: refdata.refs.len() as i64, ref_off: ref_off.as_ptr(), ref_bytes: ref_bytes.as_ptr(), ref_name_id: ref_name_id.as_ptr(),
         row_tig2_off: row_tig2_off.as_ptr(), tig2_words: tig2_words.as_ptr(), n_tig2_words: tig2_words.len() as i64,
+        row_cdr32_off: row_cdr32_off.as_ptr(), cdr32_words: cdr32_words.as_ptr(), n_cdr32_words: cdr32_words.len() as i64,
     };
 
     // ---- call the library; errors become panics, like the reference's own invariant failures ----
+    let g = context().lock().unwrap();
     unsafe {
-        let mut ctx: *mut EjbCtx = std::ptr::null_mut();
-        let rc = ejb_create(&mut ctx, std::ptr::null(), 1);
-        assert!(rc == 0, "enclone_join_b200: ejb_create failed ({rc}); a CUDA device is required (no CPU fallback)");
+        let ctx = g.0;
         let mut res: EjbResult = std::mem::zeroed();
         let rc = ejb_join(ctx, &p, &input, &mut res);
         if rc != 0 {
             let msg = std::ffi::CStr::from_ptr(ejb_last_error(ctx)).to_string_lossy().into_owned();
-            ejb_destroy(ctx);
             panic!("enclone_join_b200: join failed ({rc}): {msg}");
         }
         let e = res.n_edges as usize;
@@ -267,8 +343,7 @@ pub fn join_exacts(
             std::slice::from_raw_parts(res.eq_y, n).to_vec(),
             std::slice::from_raw_parts(res.eq_z, n).to_vec(),
         );
-        ejb_result_free(ctx, &mut res);
-        ejb_destroy(ctx);
+        ejb_result_free(ctx, &mut res);   // the context (and the packed rows join_one_batch works on) stays alive for the process
         eq
     }
 }
