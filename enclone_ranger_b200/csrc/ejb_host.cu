@@ -163,10 +163,11 @@ struct ejb_ctx {
     // per-round report: [Counters | UnitOut x units | candidate count x tasks], read back with ONE copy per round
     DevBuf d_round;
     PinBuf h_round, h_prep, h_stage;
-    size_t round_units_cap = 0, round_tasks_cap = 0;
+    size_t round_units_cap = 0, round_tasks_cap = 0, cur_round_tasks = 0;
     bool tags_on = false;      // reference-set tags in use (every canonical seg id < 65535)
     struct TaskMeta { int32_t unit, r0, r1; };
     std::vector<TaskMeta> task_meta;
+    std::vector<uint8_t> h_taskskip;              // ... tasks of the last round that returned early (not counted)
     std::vector<unsigned long long> h_unitcand;   // candidates of each task (row range) of the last round, valid even when it overflowed
     DevBuf d_mergew, d_merget;   // gathered partial forests (multi-GPU merge)
     DevBuf d_tasks, d_units, d_cand, d_slow, d_slowslot, d_surv, d_pass, d_passt, d_roots, d_forest, d_forestt;
@@ -318,7 +319,8 @@ template <int W1, int MODE>
 void launch_stage1_wm(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks, unsigned long long* unit_cand, int strip) {
     launch(c, k_stage1<W1, MODE>, (unsigned int)n_ctas, S1_THREADS, c->d_subs.as<SubBucket>(), tasks, n_tasks, c->d_cdr3w.as<uint32_t>(), c->d_labq.as<int32_t>(),
            c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr(), unit_cand, c->d_tagq.as<unsigned long long>(),
-           c->d_deadq.as<unsigned long long>(), c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>(), strip);
+           c->d_deadq.as<unsigned long long>(), c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>(), strip,
+           reinterpret_cast<uint8_t*>(unit_cand + c->cur_round_tasks));   // the per-task skip flags follow the counters in the round report
 }
 template <int W1>
 void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks, unsigned long long* unit_cand, int strip) {
@@ -856,7 +858,7 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
         for (int rb = u.r0 / TILE; rb * TILE < u.r1; rb++) {
             RowTask t;
             t.tid = 0;
-            t.pad = 0;
+            t.allow = (int32_t)std::min(u.allow, 2.0e9);
             t.sub = u.sub;
             t.rb = rb;
             t.row_lo = std::max(u.r0 - rb * TILE, 0);
@@ -895,12 +897,14 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     UnitOut* const d_uout = reinterpret_cast<UnitOut*>(rbase + sizeof(Counters));
     unsigned long long* const d_ucand = reinterpret_cast<unsigned long long*>(rbase + sizeof(Counters) + n_units * sizeof(UnitOut));
     const size_t report_bytes = sizeof(Counters) + n_units * sizeof(UnitOut) + total_tasks * 8;
+    const size_t zero_bytes = report_bytes + total_tasks;   // + one skip flag per task (not read back)
+    c->cur_round_tasks = total_tasks;
     cudaStream_t st = c->stream;
     CK(c->d_tasks.ensure(total_tasks * sizeof(RowTask) + 64));
     CK(c->d_units.ensure(n_units * sizeof(UnitDesc) + 64));
     const double th1 = now_ms();
     CK(cudaMemsetAsync(rbase, 0, offsetof(Counters, round_end), st));
-    CK(cudaMemsetAsync(rbase + sizeof(Counters), 0, report_bytes - sizeof(Counters), st));
+    CK(cudaMemsetAsync(rbase + sizeof(Counters), 0, zero_bytes - sizeof(Counters), st));
     // tasks and unit descriptors go through page-locked staging: the copies are queued, not waited for
     CK(c->h_stage.ensure(total_tasks * sizeof(RowTask) + n_units * sizeof(UnitDesc) + 64));
     memcpy(c->h_stage.p, all_tasks.data(), total_tasks * sizeof(RowTask));
@@ -972,8 +976,8 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     }
     launch(c, k_round_report, nblk((int64_t)n_units, 128), 128, c->d_units.as<const UnitDesc>(), (int)n_units, c->d_subpass.as<const unsigned int>(), d_uout);
     CK(cudaEventRecord(rt.e3, st));
-    CK(c->h_round.ensure(report_bytes));
-    CK(cudaMemcpyAsync(c->h_round.p, rbase, report_bytes, cudaMemcpyDeviceToHost, st));
+    CK(c->h_round.ensure(zero_bytes));
+    CK(cudaMemcpyAsync(c->h_round.p, rbase, zero_bytes, cudaMemcpyDeviceToHost, st));
     const double th2 = now_ms();
     rc = sync_stream(c);
     if (rc) return rc;
@@ -985,6 +989,10 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     const UnitOut* uo = reinterpret_cast<const UnitOut*>(c->h_round.as<char>() + sizeof(Counters));
     const unsigned long long* uc = reinterpret_cast<const unsigned long long*>(c->h_round.as<char>() + sizeof(Counters) + n_units * sizeof(UnitOut));
     c->h_unitcand.assign(uc, uc + total_tasks);
+    {   // tasks that returned early behind a dense block were not counted: their numbers say nothing about those rows
+        const uint8_t* skipped = reinterpret_cast<const uint8_t*>(uc + total_tasks);
+        c->h_taskskip.assign(skipped, skipped + total_tasks);
+    }
     c->p1_count += h.n_newkeys;
     c->stats.p1_unique += (int64_t)h.n_newkeys;
     if (h.p1_full) return fail(c, EJB_ERR_OOM, "p1 cache full (%llu keys in %u slots)", c->p1_count, c->p1_cap);
@@ -1436,7 +1444,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
     // ---- round report buffer (its head is the Counters block), union-find state, work buffers ----
     c->round_units_cap = (size_t)n_subs + 8;
     c->round_tasks_cap = (size_t)c->n_blocks + (size_t)n_subs + 8;
-    CK(c->d_round.ensure(sizeof(Counters) + c->round_units_cap * sizeof(UnitOut) + c->round_tasks_cap * 8));
+    CK(c->d_round.ensure(sizeof(Counters) + c->round_units_cap * sizeof(UnitOut) + c->round_tasks_cap * 9 + 64));
     CK(cudaMemsetAsync(c->d_round.p, 0, sizeof(Counters), st));
     CK(c->d_parent.ensure((size_t)std::max<int64_t>(N, 1) * 4));
     CK(c->d_best.ensure((size_t)std::max<int64_t>(N, 1) * 8));
@@ -1572,6 +1580,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
                 }
                 for (size_t t = 0; t < c->task_meta.size(); t++) {
                     const auto& m = c->task_meta[t];
+                    if (c->h_taskskip[t]) continue;
                     known[planned[m.unit].sub].push_back({m.r0, m.r1, 1.25 * (double)c->h_unitcand[t] + 1.0});
                 }
                 for (const Unit& u : planned) std::sort(known[u.sub].begin(), known[u.sub].end(), [](const Known& a, const Known& b) { return a.r0 < b.r0; });

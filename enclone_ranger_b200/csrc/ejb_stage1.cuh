@@ -26,7 +26,9 @@ struct RowTask {       // (part of) one row block of one sub-bucket, against eve
     int32_t rb;
     int64_t cta0;      // first CTA of this task inside the launch
     int32_t row_lo, row_hi;   // local rows [row_lo, row_hi) of the block belong to this round's unit
-    int32_t tid, pad;         // task id inside the round (per-task candidate counters)
+    int32_t tid;              // task id inside the round (per-task candidate counters)
+    int32_t allow;            // the unit's candidate allowance (saturated): once the PREVIOUS row block of the unit has produced more,
+                              // k_truncate is certain to cut the unit before this block, and its CTAs return at once
 };
 
 // distance contribution of the words after the first
@@ -97,7 +99,8 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
                                                        unsigned long long cand_cap, Counters* __restrict__ ctr,
                                                        unsigned long long* __restrict__ unit_cand,
                                                        const unsigned long long* __restrict__ tagq, const unsigned long long* __restrict__ deadq,
-                                                       const unsigned long long* __restrict__ donq, const uint32_t* __restrict__ flagq, int strip) {
+                                                       const unsigned long long* __restrict__ donq, const uint32_t* __restrict__ flagq, int strip,
+                                                       uint8_t* __restrict__ task_skip) {
     constexpr bool RUNI = (MODE & S1_RUNI) != 0, TAGS = (MODE & S1_TAGS) != 0;
     constexpr int NP = 2 * W1;            // plane-words per row
     constexpr int TAG0 = (NP + 1) * TILE; // word offset of the staged reference-set tags (uint64 x TILE), then the dead tags, then the donor sets
@@ -130,8 +133,18 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     // class-skip at block level: both blocks uniformly in one class
     if (tid == 0) {
         int n = 0;
+        // Behind a dense block (a clone that is not connected yet) the rest of the unit is cut away after stage 1 (k_truncate):
+        // candidates of those rows would be thrown away and the rows re-run next round.  The counts only grow, so "the previous
+        // block of my unit is already over the allowance" is a safe reason to stop here (one thread decides for the CTA).
+        bool skip = false;
+        if (lo > 0 && tasks[lo - 1].sub == t.sub && tasks[lo - 1].rb == rb - 1) {
+            const int pt = tasks[lo - 1].tid;
+            skip = *reinterpret_cast<volatile unsigned long long*>(&unit_cand[pt]) > (unsigned long long)t.allow ||
+                   *reinterpret_cast<volatile uint8_t*>(&task_skip[pt]) != 0;
+            if (skip) task_skip[t.tid] = 1;
+        }
         const int lr = blk_lab[sb.blk0 + rb];
-        for (int c = cb_first; c < nb && c < cb_first + strip; c++) {
+        for (int c = cb_first; !skip && c < nb && c < cb_first + strip; c++) {
             const int lc = blk_lab[sb.blk0 + c];
             if (lr >= 0 && lr == lc) continue;
             s_cbs[n++] = c;

@@ -403,17 +403,23 @@ __global__ void __launch_bounds__(256, S2A_MINB) k_stage2a(S2Ctx X, const uint2*
         uint2 pr = make_uint2(0, 0);
         if (valid) pr = cand[ci];
         const uint32_t q1 = pr.x, q2 = pr.y;
-        const int sid = X.subq[q1];
+        const int sid = valid ? X.subq[q1] : 0;
         if (valid && !X.tuple_mode && (int)q1 >= X.qcut[sid]) valid = false;   // row truncated from this round's unit after stage 1
+        // a batch whose candidates were all cut away (the rows behind the first dense block of a unit) costs nothing more
+        if (!__any_sync(0xffffffffu, valid)) continue;
         const SubBucket sb = X.subs[sid];
-        const int32_t* a1 = X.aux + (size_t)q1 * AUX_INTS;
-        const int32_t* a2 = X.aux + (size_t)q2 * AUX_INTS;
-        const uint4 a10 = __ldg(reinterpret_cast<const uint4*>(a1)), a20 = __ldg(reinterpret_cast<const uint4*>(a2));
+        const int32_t* a1 = X.aux + (size_t)(valid ? q1 : 0) * AUX_INTS;
+        const int32_t* a2 = X.aux + (size_t)(valid ? q2 : 0) * AUX_INTS;
+        uint4 a10 = make_uint4(0, 0, 0, 0), a20 = make_uint4(0, 0, 0, 0);
+        if (valid) {
+            a10 = __ldg(reinterpret_cast<const uint4*>(a1));
+            a20 = __ldg(reinterpret_cast<const uint4*>(a2));
+        }
         const uint32_t f1 = a10.x, f2 = a20.x;
-        const bool nrefs1 = (a10.y == a20.y && a10.z == a20.z && a10.w == a20.w && a1[AX_JSL] == a2[AX_JSL]);
+        const bool nrefs1 = valid && (a10.y == a20.y && a10.z == a20.z && a10.w == a20.w && a1[AX_JSL] == a2[AX_JSL]);
         const bool fast = valid && ((f1 | f2) & F_SLOWMASK) == 0 && sb.W1 > 0 && sb.W4h > 0 && sb.W4l > 0;
         const bool wide = fast && (sb.W4h > 4 || sb.W4l > 4);
-        const int tot1 = a1[AX_TOT], tot2 = a2[AX_TOT];
+        const int tot1 = valid ? a1[AX_TOT] : 0, tot2 = valid ? a2[AX_TOT] : 0;
         // phase 0: two references — try the memoised totals first
         bool memo_dead = false;
         if (fast && !nrefs1 && !X.tuple_mode) {
