@@ -164,6 +164,7 @@ struct ejb_ctx {
     DevBuf d_round;
     PinBuf h_round, h_prep, h_stage;
     size_t round_units_cap = 0, round_tasks_cap = 0, cur_round_tasks = 0;
+    double cur_strict = 0.0;    // strict allowance of the units of the round being queued
     bool tags_on = false;      // reference-set tags in use (every canonical seg id < 65535)
     struct TaskMeta { int32_t unit, r0, r1; };
     std::vector<TaskMeta> task_meta;
@@ -320,7 +321,8 @@ void launch_stage1_wm(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_ta
     launch(c, k_stage1<W1, MODE>, (unsigned int)n_ctas, S1_THREADS, c->d_subs.as<SubBucket>(), tasks, n_tasks, c->d_cdr3w.as<uint32_t>(), c->d_labq.as<int32_t>(),
            c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr(), unit_cand, c->d_tagq.as<unsigned long long>(),
            c->d_deadq.as<unsigned long long>(), c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>(), strip,
-           reinterpret_cast<uint8_t*>(unit_cand + c->cur_round_tasks));   // the per-task skip flags follow the counters in the round report
+           reinterpret_cast<uint8_t*>(unit_cand + c->cur_round_tasks),   // the per-task skip flags follow the counters in the round report
+           c->cur_strict);
 }
 template <int W1>
 void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks, unsigned long long* unit_cand, int strip) {
@@ -859,11 +861,12 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
             RowTask t;
             t.tid = 0;
             t.allow = (int32_t)std::min(u.allow, 2.0e9);
+            t.rho_ref = (float)u.rho_ref;
             t.sub = u.sub;
             t.rb = rb;
             t.row_lo = std::max(u.r0 - rb * TILE, 0);
             t.row_hi = std::min(u.r1 - rb * TILE, TILE);
-            t.cta0 = nctas[sb.W1];
+            t.cta0 = (int32_t)nctas[sb.W1];
             tasks[sb.W1].push_back(t);
             metas[sb.W1].push_back({(int32_t)ui, rb * TILE + t.row_lo, rb * TILE + t.row_hi});
             nctas[sb.W1] += (nb - rb + strip - 1) / strip;
@@ -897,8 +900,11 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     UnitOut* const d_uout = reinterpret_cast<UnitOut*>(rbase + sizeof(Counters));
     unsigned long long* const d_ucand = reinterpret_cast<unsigned long long*>(rbase + sizeof(Counters) + n_units * sizeof(UnitOut));
     const size_t report_bytes = sizeof(Counters) + n_units * sizeof(UnitOut) + total_tasks * 8;
-    const size_t zero_bytes = report_bytes + total_tasks;   // + one skip flag per task (not read back)
+    const size_t zero_bytes = report_bytes + total_tasks;   // + one skip flag per task
     c->cur_round_tasks = total_tasks;
+    c->cur_strict = units.empty() ? 0.0 : units[0].strict;   // the same for every unit of a run (target_pass)
+    for (int w = 0; w <= MAXW1; w++)
+        if (nctas[w] >= (1ll << 31)) return fail(c, EJB_ERR_INVALID, "stage-1 launch too large (%lld CTAs)", (long long)nctas[w]);
     cudaStream_t st = c->stream;
     CK(c->d_tasks.ensure(total_tasks * sizeof(RowTask) + 64));
     CK(c->d_units.ensure(n_units * sizeof(UnitDesc) + 64));

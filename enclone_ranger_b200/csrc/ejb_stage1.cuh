@@ -24,12 +24,23 @@ namespace ejb {
 struct RowTask {       // (part of) one row block of one sub-bucket, against every column block to its right
     int32_t sub;
     int32_t rb;
-    int64_t cta0;      // first CTA of this task inside the launch
+    int32_t cta0;      // first CTA of this task inside the launch
     int32_t row_lo, row_hi;   // local rows [row_lo, row_hi) of the block belong to this round's unit
     int32_t tid;              // task id inside the round (per-task candidate counters)
-    int32_t allow;            // the unit's candidate allowance (saturated): once the PREVIOUS row block of the unit has produced more,
-                              // k_truncate is certain to cut the unit before this block, and its CTAs return at once
+    // the unit's truncation rule (k_truncate), for the early return of blocks that are certain to be cut away:
+    int32_t allow;            // candidate allowance of the unit (saturated)
+    float rho_ref;            // candidates per row of the sub-bucket's last committed row range (< 0: unknown)
 };
+// k_truncate cuts a unit at the end of the first row block where the candidates counted so far exceed `allow`, or — once a
+// block's density has jumped above 8 x rho_ref + 16 (a clone that is not connected yet) — where the candidates since the jump
+// exceed `strict`.  The counts only grow, so "the PREVIOUS block of my unit alone already satisfies one of the two" is a
+// sufficient reason for a block to return at once: it will be cut, its candidates thrown away and its rows re-run next round.
+__device__ __forceinline__ bool block_is_cut(const RowTask& prev, unsigned long long prev_cnt, const RowTask& t, double strict) {
+    if (prev_cnt > (unsigned long long)t.allow) return true;
+    const int rows = max(1, prev.row_hi - prev.row_lo);
+    const bool jumped = t.rho_ref < 0.0f || (double)prev_cnt / (double)rows > 8.0 * (double)t.rho_ref + 16.0;
+    return jumped && (double)prev_cnt > strict;
+}
 
 // distance contribution of the words after the first
 template <int W1>
@@ -100,7 +111,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
                                                        unsigned long long* __restrict__ unit_cand,
                                                        const unsigned long long* __restrict__ tagq, const unsigned long long* __restrict__ deadq,
                                                        const unsigned long long* __restrict__ donq, const uint32_t* __restrict__ flagq, int strip,
-                                                       uint8_t* __restrict__ task_skip) {
+                                                       uint8_t* __restrict__ task_skip, double strict) {
     constexpr bool RUNI = (MODE & S1_RUNI) != 0, TAGS = (MODE & S1_TAGS) != 0;
     constexpr int NP = 2 * W1;            // plane-words per row
     constexpr int TAG0 = (NP + 1) * TILE; // word offset of the staged reference-set tags (uint64 x TILE), then the dead tags, then the donor sets
@@ -133,14 +144,12 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     // class-skip at block level: both blocks uniformly in one class
     if (tid == 0) {
         int n = 0;
-        // Behind a dense block (a clone that is not connected yet) the rest of the unit is cut away after stage 1 (k_truncate):
-        // candidates of those rows would be thrown away and the rows re-run next round.  The counts only grow, so "the previous
-        // block of my unit is already over the allowance" is a safe reason to stop here (one thread decides for the CTA).
+        // behind a dense block the rest of the unit is cut away after stage 1 (block_is_cut); one thread decides for the CTA
         bool skip = false;
         if (lo > 0 && tasks[lo - 1].sub == t.sub && tasks[lo - 1].rb == rb - 1) {
-            const int pt = tasks[lo - 1].tid;
-            skip = *reinterpret_cast<volatile unsigned long long*>(&unit_cand[pt]) > (unsigned long long)t.allow ||
-                   *reinterpret_cast<volatile uint8_t*>(&task_skip[pt]) != 0;
+            const RowTask prev = tasks[lo - 1];
+            skip = *reinterpret_cast<volatile uint8_t*>(&task_skip[prev.tid]) != 0 ||
+                   block_is_cut(prev, *reinterpret_cast<volatile unsigned long long*>(&unit_cand[prev.tid]), t, strict);
             if (skip) task_skip[t.tid] = 1;
         }
         const int lr = blk_lab[sb.blk0 + rb];
