@@ -379,11 +379,13 @@ __device__ __forceinline__ void s2_planes(const S2Ctx& X, const CandInfo& ci, in
 #endif
 __global__ void __launch_bounds__(256, S2A_MINB) k_stage2a(S2Ctx X, const uint2* __restrict__ cand, const uint32_t* __restrict__ cand_slot,
                                                     const unsigned long long* __restrict__ n_cand_p, unsigned long long cand_cap) {
-    constexpr unsigned long long S2A_CHUNK = 2048;
     __shared__ unsigned long long s_chunk;
     __shared__ uint32_t s_res[8][32][9];   // [warp][candidate][8 packed results]; padded row: conflict-free column reads
     if (X.ctr->overflow) return;   // the round cannot be committed: the host splits it and retries
     const unsigned long long n_cand = min(*n_cand_p, cand_cap);
+    // contiguous chunks keep the rows of one stage-1 tile in L1; a short list (the later rounds) is cut into smaller chunks so
+    // that it still spreads over every SM instead of keeping a few CTAs busy for eight batches each
+    const unsigned long long S2A_CHUNK = max(256ull, min(2048ull, (n_cand / gridDim.x + 255ull) & ~255ull));
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     SurvWriter wr;
