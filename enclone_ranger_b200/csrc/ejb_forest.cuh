@@ -189,9 +189,11 @@ __global__ void __launch_bounds__(256) k_forest_round(ForestArgs A) {
 }
 
 // Unit truncation after stage 1 (was a host step between two stream synchronisations): a unit whose counted candidates exceed
-// its allowance keeps whole row ranges up to (and including) the one that crosses it; stage 2 ignores candidates of the rows
-// cut away (qcut) and the scheduler resumes from the cut.  A jump in candidate density (a clone that is not connected yet)
-// switches to the strict allowance.  One thread per unit; the tasks (row ranges) of a unit are consecutive and in row order.
+// its allowance keeps whole 16-row BANDS (the rows one stage-1 warp covers) up to and including the one that crosses it; stage 2
+// ignores candidates of the rows cut away (qcut) and the scheduler resumes from the cut.  A jump in candidate density (a clone
+// that is not connected yet) switches to the strict allowance: the fewer rows of such a clone are scored before the class
+// labels are refreshed, the fewer redundant pass edges (every one of its rows joins every other).  One warp per unit; the
+// bands of a unit are consecutive and in row order, 8 per task (row block).
 struct UnitDesc {
     int32_t sub, t0, nt, r1;   // sub-bucket, first task, number of tasks, planned end row
     double allow, strict, rho_ref;
@@ -199,31 +201,33 @@ struct UnitDesc {
 struct UnitOut {
     int32_t r1, cut;           // committed end row; 1 when the unit was truncated
     double cand;               // candidates of the committed rows
+    double rho_last;           // candidates per row of the last committed band that had rows
     unsigned int pass, pad;    // pass edges of the unit's sub-bucket in this round (filled by k_round_report)
 };
 __global__ void k_truncate(const UnitDesc* __restrict__ units, int n_units, const RowTask* __restrict__ tasks, const unsigned long long* __restrict__ unit_cand,
                            const SubBucket* __restrict__ subs, int32_t* __restrict__ qcut, unsigned int* __restrict__ sub_pass, UnitOut* __restrict__ out,
                            Counters* __restrict__ ctr) {
-    // one warp per unit: the tasks are scanned 32 at a time (prefix sums by shuffles) instead of one dependent load after another
     const int lane = threadIdx.x & 31;
     const int ui = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (ui >= n_units) return;
     const UnitDesc u = units[ui];
-    double carry_cand = 0.0, carry_aj = 0.0, cand_out = 0.0;
+    const int n_bands = u.nt * S1_WARPS;
+    double carry_cand = 0.0, carry_aj = 0.0, cand_out = 0.0, rho_last = -1.0;
     bool jumped = false;
     int r1 = u.r1, cut = 0;
-    for (int base = 0; base < u.nt && !cut; base += 32) {
-        const int t = base + lane;
-        const bool valid = t < u.nt;
+    for (int base = 0; base < n_bands && !cut; base += 32) {
+        const int bi = base + lane;
         double cnt = 0.0;
-        int tr0 = 0, tr1 = 0;
-        if (valid) {
-            const RowTask rt = tasks[u.t0 + t];
-            tr0 = rt.rb * TILE + rt.row_lo;
-            tr1 = rt.rb * TILE + rt.row_hi;
-            cnt = (double)unit_cand[rt.tid];
+        int tr0 = 0, tr1 = 0;   // rows of this band that belong to the unit (empty when the band lies outside [row_lo, row_hi))
+        if (bi < n_bands) {
+            const RowTask rt = tasks[u.t0 + bi / S1_WARPS];
+            const int b = bi % S1_WARPS;
+            tr0 = rt.rb * TILE + max(rt.row_lo, 16 * b);
+            tr1 = rt.rb * TILE + min(rt.row_hi, 16 * b + 16);
+            if (tr1 > tr0) cnt = (double)unit_cand[(size_t)rt.tid * S1_WARPS + b];
         }
-        const bool dj = valid && (u.rho_ref < 0.0 || cnt / (double)max(1, tr1 - tr0) > 8.0 * u.rho_ref + 16.0);
+        const bool valid = tr1 > tr0;
+        const bool dj = valid && (u.rho_ref < 0.0 || cnt / (double)(tr1 - tr0) > 8.0 * u.rho_ref + 16.0);
         const unsigned int jm = __ballot_sync(0xffffffffu, dj);
         const int J = jumped ? 0 : (jm ? __ffs(jm) - 1 : 32);   // first lane of this chunk that counts towards the strict allowance
         double incl = cnt;
@@ -237,16 +241,22 @@ __global__ void k_truncate(const UnitDesc* __restrict__ units, int n_units, cons
         const double cum = carry_cand + incl;
         const bool cross = valid && (cum > u.allow || (lane >= J && aj > u.strict)) && tr1 < u.r1;
         const unsigned int cm = __ballot_sync(0xffffffffu, cross);
+        const unsigned int vm = __ballot_sync(0xffffffffu, valid);
         if (cm) {
             const int L = __ffs(cm) - 1;
             r1 = __shfl_sync(0xffffffffu, tr1, L);
             cand_out = __shfl_sync(0xffffffffu, cum, L);
+            rho_last = __shfl_sync(0xffffffffu, cnt / (double)max(1, tr1 - tr0), L);
             cut = 1;
         } else {
             carry_cand = __shfl_sync(0xffffffffu, cum, 31);
             carry_aj = __shfl_sync(0xffffffffu, aj, 31);
             if (J < 32) jumped = true;
             cand_out = carry_cand;
+            if (vm) {
+                const int L = 31 - __clz(vm);   // last band of this chunk with rows
+                rho_last = __shfl_sync(0xffffffffu, cnt / (double)max(1, tr1 - tr0), L);
+            }
         }
     }
     if (lane == 0) {
@@ -255,6 +265,7 @@ __global__ void k_truncate(const UnitDesc* __restrict__ units, int n_units, cons
         out[ui].r1 = r1;
         out[ui].cut = cut;
         out[ui].cand = cand_out;
+        out[ui].rho_last = rho_last;
         out[ui].pass = 0u;
         if (cut) ctr->any_cut = 1ull;
     }

@@ -98,6 +98,7 @@ struct Unit {  // rows [r0, r1) of one sub-bucket, processed against all columns
     double strict;     // ... allowance that applies from the first row range whose density jumps above 8x rho_ref
     double rho_ref;    // candidates per row of the sub-bucket's last committed row range (< 0: unknown)
     double cand, pass; // measured: candidates of the committed rows, pass edges
+    double rho_last;   // measured: candidates per row of the last committed 16-row band (< 0: none)
 };
 
 // Developer / test knobs: environment read once in ejb_create, overridable with ejb_set_option.
@@ -107,6 +108,7 @@ struct Options {
     int no_tags = 0;
     int trace = 0;
     int sr_host = 0;                         // build the Stirling table on the host (A/B against the device kernel)
+    long long strict_div = 64;               // strict allowance of a unit = cand_cap / strict_div candidates
 };
 
 }  // namespace
@@ -321,7 +323,7 @@ void launch_stage1_wm(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_ta
     launch(c, k_stage1<W1, MODE>, (unsigned int)n_ctas, S1_THREADS, c->d_subs.as<SubBucket>(), tasks, n_tasks, c->d_cdr3w.as<uint32_t>(), c->d_labq.as<int32_t>(),
            c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr(), unit_cand, c->d_tagq.as<unsigned long long>(),
            c->d_deadq.as<unsigned long long>(), c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>(), strip,
-           reinterpret_cast<uint8_t*>(unit_cand + c->cur_round_tasks),   // the per-task skip flags follow the counters in the round report
+           reinterpret_cast<uint8_t*>(unit_cand + c->cur_round_tasks * S1_WARPS),   // the per-task skip flags follow the band counters in the round report
            c->cur_strict);
 }
 template <int W1>
@@ -358,7 +360,7 @@ __global__ void k_stage1_nofilter(const SubBucket* __restrict__ subs, const RowT
             const uint32_t q1 = (uint32_t)(sb.q0 + r), q2 = (uint32_t)(sb.q0 + cc);
             if (labq[q1] == labq[q2]) continue;
             const unsigned long long o = atomicAdd(&ctr->n_cand, 1ull);
-            atomicAdd(&unit_cand[t.tid], 1ull);
+            atomicAdd(&unit_cand[(size_t)t.tid * S1_WARPS + (rl >> 4)], 1ull);   // per 16-row band, like k_stage1
             if (o < cand_cap) cand[o] = make_uint2(q1, q2); else ctr->overflow = 1ull;
         }
     }
@@ -505,6 +507,7 @@ void read_env_options(Options& o) {
     if (const char* e = getenv("EJB_FIRST_UNIT")) o.first_unit = std::max(1ll, atoll(e));
     if (const char* e = getenv("EJB_GROWTH")) o.growth = std::max(1ll, atoll(e));
     if (const char* e = getenv("EJB_S1_MODE")) o.s1_mode = atoi(e) & 3;
+    if (const char* e = getenv("EJB_STRICT_DIV")) o.strict_div = std::max(1ll, atoll(e));
     if (getenv("EJB_NO_TAGS")) o.no_tags = 1;
     if (getenv("EJB_TRACE")) o.trace = 1;
     if (getenv("EJB_SR_HOST")) o.sr_host = 1;
@@ -644,6 +647,7 @@ int ejb_set_option(ejb_ctx* c, const char* name, long long value) {
     auto apply = [&](ejb_ctx* x) {
         if (n == "first_unit") x->opt.first_unit = std::max(1ll, value);
         else if (n == "growth") x->opt.growth = std::max(1ll, value);
+        else if (n == "strict_div") x->opt.strict_div = std::max(1ll, value);
         else if (n == "s1_mode") x->opt.s1_mode = (int)value & 3;
         else if (n == "no_tags") x->opt.no_tags = value != 0;
         else if (n == "trace") x->opt.trace = value != 0;
@@ -899,7 +903,8 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     char* const rbase = c->d_round.as<char>();
     UnitOut* const d_uout = reinterpret_cast<UnitOut*>(rbase + sizeof(Counters));
     unsigned long long* const d_ucand = reinterpret_cast<unsigned long long*>(rbase + sizeof(Counters) + n_units * sizeof(UnitOut));
-    const size_t report_bytes = sizeof(Counters) + n_units * sizeof(UnitOut) + total_tasks * 8;
+    const size_t n_bands = total_tasks * S1_WARPS;   // candidate counters: one per 16-row band of every task
+    const size_t report_bytes = sizeof(Counters) + n_units * sizeof(UnitOut) + n_bands * 8;
     const size_t zero_bytes = report_bytes + total_tasks;   // + one skip flag per task
     c->cur_round_tasks = total_tasks;
     c->cur_strict = units.empty() ? 0.0 : units[0].strict;   // the same for every unit of a run (target_pass)
@@ -994,9 +999,11 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     const Counters& h = *c->h_round.as<Counters>();
     const UnitOut* uo = reinterpret_cast<const UnitOut*>(c->h_round.as<char>() + sizeof(Counters));
     const unsigned long long* uc = reinterpret_cast<const unsigned long long*>(c->h_round.as<char>() + sizeof(Counters) + n_units * sizeof(UnitOut));
-    c->h_unitcand.assign(uc, uc + total_tasks);
+    c->h_unitcand.assign(total_tasks, 0ull);
+    for (size_t t = 0; t < total_tasks; t++)
+        for (int b = 0; b < S1_WARPS; b++) c->h_unitcand[t] += uc[t * S1_WARPS + b];
     {   // tasks that returned early behind a dense block were not counted: their numbers say nothing about those rows
-        const uint8_t* skipped = reinterpret_cast<const uint8_t*>(uc + total_tasks);
+        const uint8_t* skipped = reinterpret_cast<const uint8_t*>(uc + n_bands);
         c->h_taskskip.assign(skipped, skipped + total_tasks);
     }
     c->p1_count += h.n_newkeys;
@@ -1023,6 +1030,7 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
         units[ui].r1 = uo[ui].r1;
         units[ui].cand = uo[ui].cand;
         units[ui].pass = (double)uo[ui].pass;
+        units[ui].rho_last = uo[ui].rho_last;
     }
     times.push_back(rt);
     if (c->opt.trace) {   // developer aid: what the round was made of
@@ -1450,7 +1458,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
     // ---- round report buffer (its head is the Counters block), union-find state, work buffers ----
     c->round_units_cap = (size_t)n_subs + 8;
     c->round_tasks_cap = (size_t)c->n_blocks + (size_t)n_subs + 8;
-    CK(c->d_round.ensure(sizeof(Counters) + c->round_units_cap * sizeof(UnitOut) + c->round_tasks_cap * 9 + 64));
+    CK(c->d_round.ensure(sizeof(Counters) + c->round_units_cap * sizeof(UnitOut) + c->round_tasks_cap * (8 * S1_WARPS + 1) + 64));
     CK(cudaMemsetAsync(c->d_round.p, 0, sizeof(Counters), st));
     CK(c->d_parent.ensure((size_t)std::max<int64_t>(N, 1) * 4));
     CK(c->d_best.ensure((size_t)std::max<int64_t>(N, 1) * 8));
@@ -1495,7 +1503,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
         for (int s = 0; s < (int)subs.size(); s++)
             if (subs[s].n >= 2 && subs[s].n_act > subs[s].r_beg && subs[s].r_beg < subs[s].n - 1) live.push_back(s);
         const double cap_round = 0.5 * (double)c->cand_cap;                      // expected candidates allowed per round
-        const double target_pass = std::max(4096.0, (double)c->cand_cap / 64.0);   // pass edges one unit should not exceed by much
+        const double target_pass = std::max(4096.0, (double)c->cand_cap / (double)c->opt.strict_div);   // pass edges one unit should not exceed by much
         int stalls = 0;
         const long long first_unit = c->opt.first_unit, growth = c->opt.growth;
         while (!live.empty()) {
@@ -1567,6 +1575,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
                 u.strict = target_pass;
                 u.rho_ref = rho[s];
                 u.cand = u.pass = 0.0;
+                u.rho_last = -1.0;
                 units.push_back(u);
                 pairs += up;
                 expect += ex;
@@ -1599,11 +1608,9 @@ extern "C" int ejb_run(ejb_ctx* c) {
                     if (u.cand > 0.0) prate[u.sub] = std::min(1.0, u.pass / u.cand);
                     if (u.r1 < std::min(subs[u.sub].n_act, subs[u.sub].n - 1)) still.push_back(u.sub);   // the last row has no pair to its right
                 }
-                // candidate density of the last committed row range predicts the rows that follow (capacity planning)
-                for (size_t t = 0; t < c->task_meta.size(); t++) {
-                    const auto& m = c->task_meta[t];
-                    if (m.r1 == units[m.unit].r1) rho[units[m.unit].sub] = std::max(1e-3, (double)c->h_unitcand[t] / (double)std::max(1, m.r1 - m.r0));
-                }
+                // candidate density of the last committed 16-row band predicts the rows that follow (capacity planning)
+                for (const Unit& u : units)
+                    if (u.rho_last >= 0.0) rho[u.sub] = std::max(1e-3, u.rho_last);
             }
             std::sort(still.begin(), still.end());
             still.erase(std::unique(still.begin(), still.end()), still.end());

@@ -10,7 +10,8 @@ namespace ejb {
 // shared memory by TMA bulk copies through a ring of S1_NBUF column buffers guarded by full / empty
 // mbarriers: the eight warps of a CTA never meet at a CTA-wide barrier inside the tile loop, a warp
 // whose 16 x 16 groups are already one class runs ahead of the ones that score.
-// Each thread keeps an 8-row fragment in registers and walks 8 columns per tile.  Per column:
+// Each thread keeps an 8-row fragment (8 CONSECUTIVE rows; a warp covers a band of 16 consecutive rows, the granularity at
+// which candidates are counted and units are cut) in registers and walks 8 columns per tile.  Per column:
 //   1. one warp vote skips 16 rows x 16 columns that carry one class label (join_core.rs:32: a pair
 //      already connected by lexicographically smaller joins can never be in pot);
 //   2. the FIRST 32 positions of the eight pairs go through XOR + popc; a pair can only be CDR3-close
@@ -31,15 +32,24 @@ struct RowTask {       // (part of) one row block of one sub-bucket, against eve
     int32_t allow;            // candidate allowance of the unit (saturated)
     float rho_ref;            // candidates per row of the sub-bucket's last committed row range (< 0: unknown)
 };
-// k_truncate cuts a unit at the end of the first row block where the candidates counted so far exceed `allow`, or — once a
-// block's density has jumped above 8 x rho_ref + 16 (a clone that is not connected yet) — where the candidates since the jump
-// exceed `strict`.  The counts only grow, so "the PREVIOUS block of my unit alone already satisfies one of the two" is a
-// sufficient reason for a block to return at once: it will be cut, its candidates thrown away and its rows re-run next round.
-__device__ __forceinline__ bool block_is_cut(const RowTask& prev, unsigned long long prev_cnt, const RowTask& t, double strict) {
-    if (prev_cnt > (unsigned long long)t.allow) return true;
-    const int rows = max(1, prev.row_hi - prev.row_lo);
-    const bool jumped = t.rho_ref < 0.0f || (double)prev_cnt / (double)rows > 8.0 * (double)t.rho_ref + 16.0;
-    return jumped && (double)prev_cnt > strict;
+// k_truncate cuts a unit at the end of the first 16-row band where the candidates counted so far exceed `allow`, or — once a
+// band's density has jumped above 8 x rho_ref + 16 (a clone that is not connected yet) — where the candidates since the jump
+// exceed `strict`.  Replaying that rule on the bands of the PREVIOUS block alone (no carry from earlier blocks, counts as they
+// stand: both can only be smaller than what k_truncate will see) gives a sufficient condition for "this block will be cut away":
+// its candidates would be thrown away and its rows re-run next round, so its CTAs return at once.
+__device__ __forceinline__ bool block_is_cut(const RowTask& prev, const unsigned long long* band_cnt /* 8, volatile reads */, const RowTask& t, double strict) {
+    double cum = 0.0, aj = 0.0;
+    bool jumped = t.rho_ref < 0.0f;
+    for (int b = 0; b < 8; b++) {
+        const int rows = min(prev.row_hi, 16 * b + 16) - max(prev.row_lo, 16 * b);
+        if (rows <= 0) continue;
+        const double cnt = (double)*reinterpret_cast<const volatile unsigned long long*>(&band_cnt[b]);
+        if (!jumped && cnt / (double)rows > 8.0 * (double)t.rho_ref + 16.0) jumped = true;
+        cum += cnt;
+        if (jumped) aj += cnt;
+        if (cum > (double)t.allow || (jumped && aj > strict)) return true;
+    }
+    return false;
 }
 
 // distance contribution of the words after the first
@@ -149,7 +159,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         if (lo > 0 && tasks[lo - 1].sub == t.sub && tasks[lo - 1].rb == rb - 1) {
             const RowTask prev = tasks[lo - 1];
             skip = *reinterpret_cast<volatile uint8_t*>(&task_skip[prev.tid]) != 0 ||
-                   block_is_cut(prev, *reinterpret_cast<volatile unsigned long long*>(&unit_cand[prev.tid]), t, strict);
+                   block_is_cut(prev, unit_cand + (size_t)prev.tid * S1_WARPS, t, strict);
             if (skip) task_skip[t.tid] = 1;
         }
         const int lr = blk_lab[sb.blk0 + rb];
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     int rlab[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const int r = i * 16 + ty;
+        const int r = ty * 8 + i;
 #pragma unroll
         for (int w = 0; w < W1; w++) {
             rl[i][w] = s_row[w * TILE + r];
@@ -221,7 +231,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     if (TAGS) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const uint32_t f = s_row[FLAG0 + i * 16 + ty];
+            const uint32_t f = s_row[FLAG0 + ty * 8 + i];
             r_dead8 |= ((f >> 0) & 1u) << i;
             r_dom8 |= ((f >> 1) & 1u) << i;
             r_fd8 |= ((f >> 2) & 1u) << i;
@@ -234,7 +244,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     // column tile: it only releases the buffers
     bool warp_rows = false;
 #pragma unroll
-    for (int i = 0; i < 8; i++) warp_rows |= (i * 16 + ty >= row_lo) & (i * 16 + ty < row_lim);
+    for (int i = 0; i < 8; i++) warp_rows |= (ty * 8 + i >= row_lo) & (ty * 8 + i < row_lim);
     warp_rows = __any_sync(0xffffffffu, warp_rows);
     const int maxcd = sb.maxcd;
     const uint32_t q_r0 = (uint32_t)(sb.q0 + (int64_t)rb * TILE);
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const int r = i * 16 + ty;
+                    const int r = ty * 8 + i;
                     any |= (__popc((rl[i][0] ^ cl0) | (rh[i][0] ^ ch0)) <= maxcd) & (rlab[i] != clab) & !((kill8 >> i) & 1u) & (r >= row_lo) & (r < row_lim) &
                            (c < col_lim) & (!diag | (r < c));
                 }
@@ -319,7 +329,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
             }
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int r = i * 16 + ty;
+                const int r = ty * 8 + i;
                 const int p0 = __popc((rl[i][0] ^ cl[0]) | (rh[i][0] ^ chh[0]));
                 bool hit = p0 <= maxcd && rlab[i] != clab && !((kill8 >> i) & 1u);
                 if (!full) hit = hit && r >= row_lo && r < row_lim && c < col_lim && (!diag || r < c);
@@ -361,7 +371,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
         }
     }
     if (wq) flush();
-    if (lane == 0 && w_total) atomicAdd(&unit_cand[t.tid], w_total);
+    if (lane == 0 && w_total) atomicAdd(&unit_cand[(size_t)t.tid * S1_WARPS + warp], w_total);   // per 16-row band
     if (tid == 0) atomicAdd(&ctr->pairs_eval, evaluated);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
