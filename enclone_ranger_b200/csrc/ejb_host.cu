@@ -103,12 +103,13 @@ struct Unit {  // rows [r0, r1) of one sub-bucket, processed against all columns
 
 // Developer / test knobs: environment read once in ejb_create, overridable with ejb_set_option.
 struct Options {
-    long long first_unit = 2, growth = 12;   // unit schedule (measured on configs[1]: 8/4 -> 10.5 ms, 1/8 -> 8.95, 2/12 -> 8.74, 4/16 -> 8.75)
+    long long first_unit = 2, growth = 6;    // unit schedule (round 2, with per-band cuts: configs[4] 12 -> 84 ms, 6 -> 72 ms; configs[1] indifferent)
     int s1_mode = S1_RUNI | S1_TAGS;
     int no_tags = 0;
     int trace = 0;
     int sr_host = 0;                         // build the Stirling table on the host (A/B against the device kernel)
-    long long strict_div = 64;               // strict allowance of a unit = cand_cap / strict_div candidates
+    long long strict_div = 2048;             // strict allowance of a unit = cand_cap / strict_div candidates
+    int early_return = 0;                    // stage-1 CTAs return when the previous block of their unit is certain to be cut (measured: no gain)
 };
 
 }  // namespace
@@ -167,12 +168,14 @@ struct ejb_ctx {
     PinBuf h_round, h_prep, h_stage;
     size_t round_units_cap = 0, round_tasks_cap = 0, cur_round_tasks = 0;
     double cur_strict = 0.0;    // strict allowance of the units of the round being queued
+    size_t cur_cta_off = 0;     // offset of the current launch in the CTA -> task map
     bool tags_on = false;      // reference-set tags in use (every canonical seg id < 65535)
     struct TaskMeta { int32_t unit, r0, r1; };
     std::vector<TaskMeta> task_meta;
     std::vector<uint8_t> h_taskskip;              // ... tasks of the last round that returned early (not counted)
     std::vector<unsigned long long> h_unitcand;   // candidates of each task (row range) of the last round, valid even when it overflowed
     DevBuf d_mergew, d_merget;   // gathered partial forests (multi-GPU merge)
+    DevBuf d_ctatask;            // CTA -> task map of the stage-1 launches of a round
     DevBuf d_tasks, d_units, d_cand, d_slow, d_slowslot, d_surv, d_pass, d_passt, d_roots, d_forest, d_forestt;
     DevBuf d_deg, d_first, d_labels, d_excount, d_multi, d_multi2, d_fkeys, d_fkeys2, d_fidx, d_fidx2;
     DevBuf d_o_k1, d_o_k2, d_o_cd, d_o_nrefs, d_o_sh, d_o_in, d_o_k, d_o_d, d_o_n, d_o_p1, d_o_mult, d_o_score, d_o_err;
@@ -324,7 +327,7 @@ void launch_stage1_wm(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_ta
            c->d_blklab.as<int32_t>(), c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr(), unit_cand, c->d_tagq.as<unsigned long long>(),
            c->d_deadq.as<unsigned long long>(), c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>(), strip,
            reinterpret_cast<uint8_t*>(unit_cand + c->cur_round_tasks * S1_WARPS),   // the per-task skip flags follow the band counters in the round report
-           c->cur_strict);
+           c->opt.early_return ? c->cur_strict : 0.0, c->d_ctatask.as<const int32_t>() + c->cur_cta_off);
 }
 template <int W1>
 void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tasks, unsigned long long* unit_cand, int strip) {
@@ -334,6 +337,17 @@ void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tas
         case 2: launch_stage1_wm<W1, S1_TAGS>(c, n_ctas, tasks, n_tasks, unit_cand, strip); break;
         default: launch_stage1_wm<W1, S1_RUNI | S1_TAGS>(c, n_ctas, tasks, n_tasks, unit_cand, strip); break;
     }
+}
+
+// CTA -> task map of one stage-1 launch: thread per (task, CTA of the task); replaces a binary search over the task list in the
+// prologue of every CTA (eleven dependent L2 loads) by one load
+__global__ void k_expand_tasks(const RowTask* __restrict__ tasks, int n_tasks, const SubBucket* __restrict__ subs, int strip, int32_t* __restrict__ cta_task) {
+    const int t = blockIdx.x;
+    if (t >= n_tasks) return;
+    const RowTask rt = tasks[t];
+    const int nb = (subs[rt.sub].n + TILE - 1) / TILE;
+    const int n = (nb - rt.rb + strip - 1) / strip;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) cta_task[rt.cta0 + j] = t;
 }
 
 // stage-1 for sub-buckets whose CDR3s exceed the fast path: every not-yet-connected pair is a candidate
@@ -648,6 +662,7 @@ int ejb_set_option(ejb_ctx* c, const char* name, long long value) {
         if (n == "first_unit") x->opt.first_unit = std::max(1ll, value);
         else if (n == "growth") x->opt.growth = std::max(1ll, value);
         else if (n == "strict_div") x->opt.strict_div = std::max(1ll, value);
+        else if (n == "early_return") x->opt.early_return = value != 0;
         else if (n == "s1_mode") x->opt.s1_mode = (int)value & 3;
         else if (n == "no_tags") x->opt.no_tags = value != 0;
         else if (n == "trace") x->opt.trace = value != 0;
@@ -933,10 +948,21 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     if (c->tags_on && (c->opt.s1_mode & S1_TAGS))
         launch(c, k_row_flags, nblk(c->n_pos, 256), 256, c->d_m_sub.as<const int32_t>(), c->d_m_row.as<const int32_t>(), c->n_pos, c->d_subdom.as<const SubDom>(),
                c->d_tagq.as<const unsigned long long>(), c->d_deadq.as<const unsigned long long>(), c->d_donq.as<const unsigned long long>(), c->d_flagq.as<uint32_t>());
+    {
+        size_t total_ctas = 0;
+        for (int w = 1; w <= MAXW1; w++) total_ctas += (size_t)nctas[w];
+        CK(c->d_ctatask.ensure(total_ctas * 4 + 64));
+    }
+    size_t cta_off = 0;
     for (int w = 0; w <= MAXW1; w++) {
         if (tasks[w].empty()) continue;
         const RowTask* dt = c->d_tasks.as<RowTask>() + goff[w];
         const int nt = (int)tasks[w].size();
+        if (w > 0) {
+            launch(c, k_expand_tasks, (unsigned int)nt, 64, dt, nt, c->d_subs.as<const SubBucket>(), strip_of[w], c->d_ctatask.as<int32_t>() + cta_off);
+            c->cur_cta_off = cta_off;
+            cta_off += (size_t)nctas[w];
+        }
         switch (w) {
             case 0:
                 launch(c, k_stage1_nofilter, (unsigned int)nctas[0], 256, c->d_subs.as<const SubBucket>(), dt, nt, c->d_labq.as<const int32_t>(), c->d_cand.as<uint2>(),

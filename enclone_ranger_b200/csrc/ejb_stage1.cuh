@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
                                                        unsigned long long* __restrict__ unit_cand,
                                                        const unsigned long long* __restrict__ tagq, const unsigned long long* __restrict__ deadq,
                                                        const unsigned long long* __restrict__ donq, const uint32_t* __restrict__ flagq, int strip,
-                                                       uint8_t* __restrict__ task_skip, double strict) {
+                                                       uint8_t* __restrict__ task_skip, double strict, const int32_t* __restrict__ cta_task) {
     constexpr bool RUNI = (MODE & S1_RUNI) != 0, TAGS = (MODE & S1_TAGS) != 0;
     constexpr int NP = 2 * W1;            // plane-words per row
     constexpr int TAG0 = (NP + 1) * TILE; // word offset of the staged reference-set tags (uint64 x TILE), then the dead tags, then the donor sets
@@ -135,13 +135,10 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     __shared__ int s_cbs[S1_STRIP];
     __shared__ int s_ncb;
 
-    // ---- locate the task: binary search on cta0 ----
+    // ---- locate the task: one load from the CTA -> task map of this launch (k_expand_tasks) ----
     const int64_t cta = blockIdx.x;
-    int lo = 0, hi = n_tasks - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (tasks[mid].cta0 <= cta) lo = mid; else hi = mid - 1;
-    }
+    const int lo = cta_task[cta];
+    (void)n_tasks;
     const RowTask t = tasks[lo];
     const SubBucket sb = subs[t.sub];
     if (sb.W1 != W1) return;  // launched once per W1; other widths are handled by their own launch
@@ -151,30 +148,37 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;
 
-    // class-skip at block level: both blocks uniformly in one class
-    if (tid == 0) {
-        int n = 0;
-        // behind a dense block the rest of the unit is cut away after stage 1 (block_is_cut); one thread decides for the CTA
+    // class-skip at block level: both blocks uniformly in one class.  Warp 0 looks at the (up to 16) column blocks of the strip
+    // in parallel and compacts the ones that need work.
+    if (warp == 0) {
+        // behind a dense block the rest of the unit is cut away after stage 1 (block_is_cut); one thread decides for the CTA.
+        // strict <= 0 switches the early return off.
         bool skip = false;
-        if (lo > 0 && tasks[lo - 1].sub == t.sub && tasks[lo - 1].rb == rb - 1) {
+        if (lane == 0 && strict > 0.0 && lo > 0 && tasks[lo - 1].sub == t.sub && tasks[lo - 1].rb == rb - 1) {
             const RowTask prev = tasks[lo - 1];
             skip = *reinterpret_cast<volatile uint8_t*>(&task_skip[prev.tid]) != 0 ||
                    block_is_cut(prev, unit_cand + (size_t)prev.tid * S1_WARPS, t, strict);
             if (skip) task_skip[t.tid] = 1;
         }
+        skip = __shfl_sync(0xffffffffu, skip ? 1 : 0, 0) != 0;
         const int lr = blk_lab[sb.blk0 + rb];
-        for (int c = cb_first; !skip && c < nb && c < cb_first + strip; c++) {
-            const int lc = blk_lab[sb.blk0 + c];
-            if (lr >= 0 && lr == lc) continue;
-            s_cbs[n++] = c;
+        const int cbl = cb_first + lane;
+        bool work = false;
+        if (!skip && lane < strip && cbl < nb) {
+            const int lc = blk_lab[sb.blk0 + cbl];
+            work = !(lr >= 0 && lr == lc);
         }
-        s_ncb = n;
-        for (int b = 0; b < NBUF; b++) {
-            mbar_init(&s_full[b], 1);
-            mbar_init(&s_empty[b], S1_WARPS);
+        const unsigned int wm = __ballot_sync(0xffffffffu, work);
+        if (work) s_cbs[__popc(wm & ((1u << lane) - 1u))] = cbl;
+        if (lane == 0) {
+            s_ncb = __popc(wm);
+            for (int b = 0; b < NBUF; b++) {
+                mbar_init(&s_full[b], 1);
+                mbar_init(&s_empty[b], S1_WARPS);
+            }
+            mbar_init(&s_rowbar, 1);
+            mbar_fence_init();
         }
-        mbar_init(&s_rowbar, 1);
-        mbar_fence_init();
     }
     __syncthreads();
     const int ncb = s_ncb;
