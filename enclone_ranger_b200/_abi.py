@@ -312,6 +312,10 @@ def load_join():
         L.ejb_device_tuples.restype = C.c_int
         L.ejb_join_one_batch.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int64, C.POINTER(EjbPairOut)]
         L.ejb_join_one_batch.restype = C.c_int
+        L.ejb_upload_slice.argtypes = [C.c_void_p, C.POINTER(EjbParams), C.POINTER(EjbInput), C.c_int, C.c_int]
+        L.ejb_upload_slice.restype = C.c_int
+        L.ejb_device_arena.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.ejb_device_arena.restype = C.c_int
         L.ejb_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ejb_set_shard.restype = C.c_int
         L.ejb_part_forest.argtypes = [C.c_void_p, _i64p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]

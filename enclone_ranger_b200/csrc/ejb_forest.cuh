@@ -314,6 +314,45 @@ __global__ void k_p1_request_forest(const unsigned long long* __restrict__ fores
         p1_request(p1c, 3 * (in.row_len[2 * k1] + in.row_len[2 * k1 + 1]), min_in + 2 * min_sh, min_sh, ctr);
     }
 }
+// Merge of the gathered partial forests, first pass: an edge of a sub-bucket that ONE rank joined as a whole is final — it goes
+// straight to the merged forest and its endpoints are united; the edges of split sub-buckets (overlapping partial forests) are
+// compacted into the pass-edge list for the Boruvka pass that follows.
+__global__ void k_merge_split(const unsigned long long* __restrict__ w, const PassTuple* __restrict__ t, unsigned long long n, int32_t* __restrict__ parent,
+                              unsigned long long* __restrict__ forest, PassTuple* __restrict__ forest_t, unsigned long long* __restrict__ pass_w,
+                              PassTuple* __restrict__ pass_t, Counters* ctr) {
+    const int lane = threadIdx.x & 31;
+    for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < n; i0 += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long i = i0 + lane;
+        bool whole = false, split = false;
+        unsigned long long e = 0;
+        PassTuple pt;
+        if (i < n) {
+            e = w[i];
+            pt = t[i];
+            split = (pt.nrefs_err & PT_SPLIT) != 0;
+            whole = !split;
+        }
+        const unsigned int mw = __ballot_sync(0xffffffffu, whole), ms = __ballot_sync(0xffffffffu, split);
+        unsigned long long bw = 0, bs = 0;
+        if (lane == 0) {
+            if (mw) bw = atomicAdd(&ctr->n_forest, (unsigned long long)__popc(mw));
+            if (ms) bs = atomicAdd(&ctr->n_pass, (unsigned long long)__popc(ms));
+        }
+        bw = __shfl_sync(0xffffffffu, bw, 0);
+        bs = __shfl_sync(0xffffffffu, bs, 0);
+        const unsigned int lt = (1u << lane) - 1u;
+        if (whole) {
+            const unsigned long long o = bw + __popc(mw & lt);
+            forest[o] = e;
+            forest_t[o] = pt;
+            uf_union(parent, (int)(e >> 28), (int)(e & 0xfffffffull));
+        } else if (split) {
+            const unsigned long long o = bs + __popc(ms & lt);
+            pass_w[o] = e;
+            pass_t[o] = pt;
+        }
+    }
+}
 __global__ void k_init_parent(int32_t* __restrict__ parent, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) parent[i] = (int32_t)i;

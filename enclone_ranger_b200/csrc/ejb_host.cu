@@ -153,6 +153,8 @@ struct ejb_ctx {
     int64_t n_canon_segs = 0;   // distinct seg contents (canonical ids are 0 .. n_canon_segs-1)
     const char* arena_base = nullptr;   // ejb_set_input_arena: one host allocation holding (most of) the input arrays
     size_t arena_bytes = 0;
+    size_t arena_slice = 0;     // bytes per slice of the last sliced upload (0: whole arena uploaded)
+    int arena_parts = 1;
     DevBuf d_arena;
     DevBuf d_roles, d_subroles; // ejb_set_row_roles (per canonical row), per-sub-bucket summary
     std::vector<uint8_t> roles; // host copy; in force for every run until cleared
@@ -647,6 +649,17 @@ int ejb_create(ejb_ctx** out, const int* device_ids, int n_devices) {
             destroy_ctx(c);
             return rc;
         }
+        // direct GPU-to-GPU copies (NVLink) between every pair of devices of the context; "already enabled" is fine
+        for (int i = 0; i < n_devices; i++)
+            for (int j = 0; j < n_devices; j++) {
+                if (devs[i] == devs[j]) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) == cudaSuccess && can) {
+                    cudaSetDevice(devs[i]);
+                    cudaDeviceEnablePeerAccess(devs[j], 0);
+                    cudaGetLastError();
+                }
+            }
         cudaSetDevice(devs[0]);
     }
     *out = c;
@@ -708,7 +721,10 @@ int ejb_set_capacity(ejb_ctx* c, unsigned long long cand_cap, unsigned long long
     return EJB_OK;
 }
 
-int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
+}  // extern "C"
+namespace {
+// part / nparts: copy only slice `part` of the declared input arena (the other slices arrive GPU-to-GPU, ejb_upload_slice)
+int upload_impl(ejb_ctx* c, const ejb_params* p, const ejb_input* in, int part, int nparts) {
     if (!c || !p || !in) return EJB_ERR_INVALID;
     CK(cudaSetDevice(c->device));
     c->have_input = c->have_run = c->prepared = false;
@@ -736,10 +752,26 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     d.n_seg_bytes = in->n_segs > 0 ? in->seg_off[in->n_segs] : 0;
     d.n_ref_bytes = in->n_refs > 0 ? in->ref_off[in->n_refs] : 0;
     if (d.n_seg_bytes < 0 || d.n_ref_bytes < 0) return fail(c, EJB_ERR_INVALID, "negative seg/ref byte count");
+    c->arena_slice = 0;
+    c->arena_parts = 1;
+    if (nparts > 1 && !c->arena_base) return fail(c, EJB_ERR_INVALID, "a sliced upload needs the input arena (ejb_set_input_arena)");
     if (c->arena_base) {   // one DMA for everything the caller keeps in its arena
-        CK(c->d_arena.ensure(c->arena_bytes + 256));
-        CK(cudaMemcpyAsync(c->d_arena.p, c->arena_base, c->arena_bytes, cudaMemcpyHostToDevice, c->up_stream[c->up_next++ % ejb_ctx::N_UP]));
-        c->h2d_bytes += (int64_t)c->arena_bytes;
+        if (nparts > 1) {
+            // equal 256-byte aligned slices, so that the caller's all-gather works on one contiguous device buffer
+            const size_t slice = ((c->arena_bytes + (size_t)nparts - 1) / (size_t)nparts + 255) & ~(size_t)255;
+            CK(c->d_arena.ensure(slice * (size_t)nparts + 256));
+            c->arena_slice = slice;
+            c->arena_parts = nparts;
+            const size_t lo = std::min(slice * (size_t)part, c->arena_bytes), hi = std::min(lo + slice, c->arena_bytes);
+            if (hi > lo) {
+                CK(cudaMemcpyAsync(c->d_arena.as<char>() + lo, c->arena_base + lo, hi - lo, cudaMemcpyHostToDevice, c->up_stream[c->up_next++ % ejb_ctx::N_UP]));
+                c->h2d_bytes += (int64_t)(hi - lo);
+            }
+        } else {
+            CK(c->d_arena.ensure(c->arena_bytes + 256));
+            CK(cudaMemcpyAsync(c->d_arena.p, c->arena_base, c->arena_bytes, cudaMemcpyHostToDevice, c->up_stream[c->up_next++ % ejb_ctx::N_UP]));
+            c->h2d_bytes += (int64_t)c->arena_bytes;
+        }
     }
     // content-canonical seg ids: DnaString equality is by content (join_one.rs:331)
     std::vector<int32_t> canon((size_t)std::max<int64_t>(in->n_segs, 1), 0);
@@ -814,7 +846,27 @@ int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) {
     c->have_input = true;
     return EJB_OK;
 }
+}  // namespace
 
+extern "C" {
+int ejb_upload(ejb_ctx* c, const ejb_params* p, const ejb_input* in) { return upload_impl(c, p, in, 0, 1); }
+
+// Sharded upload for contexts that all need the WHOLE input (ejb_set_shard): context `part` of `nparts` copies only its slice of
+// the declared input arena over PCIe; the caller then completes every context's device arena GPU-to-GPU (an in-place all-gather
+// over NVLink on the buffer ejb_device_arena returns: slice i lives at offset i * slice_bytes) before ejb_run.  The host -> device
+// traffic of N GPUs is the input once instead of N times.
+int ejb_upload_slice(ejb_ctx* c, const ejb_params* p, const ejb_input* in, int part, int nparts) {
+    if (nparts < 1 || part < 0 || part >= nparts) return EJB_ERR_INVALID;
+    return upload_impl(c, p, in, part, nparts);
+}
+int ejb_device_arena(ejb_ctx* c, void** d_base, uint64_t* total_bytes, uint64_t* slice_bytes) {
+    if (!c) return EJB_ERR_INVALID;
+    if (!c->have_input || !c->d_arena.p) return fail(c, EJB_ERR_INVALID, "ejb_device_arena without an uploaded input arena");
+    if (d_base) *d_base = c->d_arena.p;
+    if (slice_bytes) *slice_bytes = (uint64_t)c->arena_slice;
+    if (total_bytes) *total_bytes = c->arena_slice ? (uint64_t)c->arena_slice * (uint64_t)c->arena_parts : (uint64_t)c->arena_bytes;
+    return EJB_OK;
+}
 }  // extern "C"
 
 // ================================================================================================
@@ -1113,6 +1165,7 @@ void shard_assign(std::vector<SubBucket>& subs, int rank, int world, double spli
     }
     std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
     std::vector<double> load((size_t)world, 0.0);
+    if (world > 1) load[0] = 0.2 * share;   // rank 0 also gathers, merges and finalizes (by convention the merging context)
     std::vector<uint64_t> holder(subs.size(), 0);   // ranks already holding a part of the sub-bucket (world <= 64)
     for (SubBucket& sb : subs) {
         sb.owner = -1;
@@ -1186,11 +1239,7 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     CK(c->d_donor.ensure((size_t)std::max<int64_t>(din.n_exacts, 1) * 8));
     CK(c->d_bckeys.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
     CK(c->d_bckeys2.ensure((size_t)std::max<int64_t>(din.n_cells, 1) * 8));
-    launch(c, k_exact_prep, nblk(din.n_exacts, 256), 256, din, c->d_donor.as<unsigned long long>(), c->d_bckeys.as<uint64_t>());
-    if (din.n_cells > 0) {
-        rc = cub_sort_keys64(c, c->d_bckeys.as<uint64_t>(), c->d_bckeys2.as<uint64_t>(), din.n_cells);
-        if (rc) return rc;
-    }
+    launch(c, k_exact_prep, nblk(din.n_exacts, 128), 128, din, c->d_donor.as<unsigned long long>(), c->d_bckeys.as<uint64_t>(), c->d_bckeys2.as<uint64_t>(), hdr);
     CK(c->d_segpl.ensure((size_t)std::max<int64_t>(din.n_segs, 1) * 2 * SEGPL_WORDS * 4));
     CK(c->d_seglen.ensure((size_t)std::max<int64_t>(din.n_segs, 1) * 4));
     launch(c, k_seg_planes, nblk(din.n_segs * 32, 256), 256, din, c->d_segpl.as<uint32_t>(), c->d_seglen.as<int32_t>());
@@ -1223,6 +1272,10 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     if (hh.err) return fail(c, EJB_ERR_INVALID, "input validation failed (mask 0x%x: 1 nchains, 2 exact id, 4 tig offsets, 8 cdr3 offsets, 16 seg ids, 32 exact_cols, 64/128 exact tables, 256 ref ids, 512 amino, 1024 donor id >= 64, 2048 seg_off, 4096 ref_off, 8192 packed contig)", hh.err);
     c->stats.n_buckets = (int64_t)hh.n_buckets;
     c->n_active = (int64_t)hh.n_active;
+    if (hh.big_exacts && din.n_cells > 0) {   // an exact with many cells: one global sort of all barcode lists instead of the per-thread sorts
+        rc = cub_sort_keys64(c, c->d_bckeys.as<uint64_t>(), c->d_bckeys2.as<uint64_t>(), din.n_cells);
+        if (rc) return rc;
+    }
     const int64_t NA = c->n_active;
     const int n_subs = (int)hh.n_subs;
     c->n_buckets = (int64_t)hh.n_buckets;
@@ -2047,6 +2100,23 @@ extern "C" int ejb_join_one_batch(ejb_ctx* c, const int32_t* k1, const int32_t* 
 // ================================================================================================
 extern "C" {
 
+// The shard assignment as a pure host function (tests; no device needed): sub_rows[s] = rows of sub-bucket s.  r_beg[s] / n_act[s]
+// receive the first-row range [r_beg, n_act) of sub-bucket s that `rank` of `world` joins (empty: another rank owns it).
+int ejb_shard_plan(const int32_t* sub_rows, int32_t n_subs, int world, int rank, int32_t* r_beg, int32_t* n_act) {
+    if (!sub_rows || n_subs < 0 || world < 1 || world > 64 || rank < 0 || rank >= world || !r_beg || !n_act) return EJB_ERR_INVALID;
+    std::vector<SubBucket> subs((size_t)n_subs);
+    for (int s = 0; s < n_subs; s++) {
+        memset(&subs[(size_t)s], 0, sizeof(SubBucket));
+        subs[(size_t)s].n = sub_rows[s];
+    }
+    shard_assign(subs, rank, world);
+    for (int s = 0; s < n_subs; s++) {
+        r_beg[s] = subs[(size_t)s].r_beg;
+        n_act[s] = subs[(size_t)s].n_act;
+    }
+    return EJB_OK;
+}
+
 // Partial forest of the last sharded ejb_run (ejb_set_shard with world > 1): device pointers, valid until the next run.
 int ejb_part_forest(ejb_ctx* c, int64_t* n_edges, const unsigned long long** d_edges, const void** d_tuples) {
     if (!c) return EJB_ERR_INVALID;
@@ -2073,9 +2143,10 @@ int ejb_merge_buffers(ejb_ctx* c, int64_t total, unsigned long long** d_edges, v
 
 // Merge: the gathered edges are the union of the parts' spanning forests.  Sub-buckets that were not split contribute disjoint
 // forests (every edge stays); the parts of a split sub-bucket overlap, and the lexicographic spanning forest of the whole
-// sub-bucket is the minimum spanning forest of the union of the partial forests.  One Boruvka pass over all gathered edges on a
-// fresh union-find computes both at once; then the ordinary finalize runs (two-cell filter on the merged forest, ordering,
-// PotentialJoin members, clonotype_id unions, labels).  ejb_download returns the result of the WHOLE join.
+// sub-bucket is the minimum spanning forest of the union of the partial forests.  The edges carry a flag (PT_SPLIT): those of
+// whole sub-buckets are united directly (k_merge_split), one Boruvka pass runs over the edges of split sub-buckets only; then the
+// ordinary finalize (two-cell filter on the merged forest, ordering, PotentialJoin members, clonotype_id unions, labels).
+// ejb_download returns the result of the WHOLE join.
 int ejb_merge_parts(ejb_ctx* c, int64_t total) {
     if (!c || total < 0) return EJB_ERR_INVALID;
     if (!c->have_part) return fail(c, EJB_ERR_INVALID, "ejb_merge_parts without a sharded ejb_run on the merging context");
@@ -2093,18 +2164,22 @@ int ejb_merge_parts(ejb_ctx* c, int64_t total) {
     CK(cudaMemsetAsync(CTR_FIELD(n_final), 0, 8, st));
     CK(cudaMemsetAsync(CTR_FIELD(n_two_cell), 0, 8, st));
     CK(cudaMemsetAsync(CTR_FIELD(n_multi), 0, 8, st));
-    const unsigned long long tot = (unsigned long long)total;
-    CK(cudaMemcpyAsync(CTR_FIELD(n_pass), &tot, 8, cudaMemcpyHostToDevice, st));
     if (N > 0) launch(c, k_init_parent, nblk(N, 256), 256, c->d_parent.as<int32_t>(), N);
     CK(c->d_roots.ensure((size_t)std::max<int64_t>(total, 1) * 8));
+    CK(c->d_pass.ensure((size_t)std::max<int64_t>(total, 1) * 8));
+    CK(c->d_passt.ensure((size_t)std::max<int64_t>(total, 1) * sizeof(PassTuple)));
     if (c->p1_count > c->p1_cap / 8) {
         int rc = p1_cache_grow(c);
         if (rc) return rc;
     }
     if (total > 0) {
+        // edges of whole sub-buckets: final, united directly; edges of split sub-buckets: compacted for the Boruvka pass
+        launch(c, k_merge_split, c->sm_count * 8, 256, c->d_mergew.as<const unsigned long long>(), c->d_merget.as<const PassTuple>(), (unsigned long long)total,
+               c->d_parent.as<int32_t>(), c->d_forest.as<unsigned long long>(), c->d_forestt.as<PassTuple>(), c->d_pass.as<unsigned long long>(),
+               c->d_passt.as<PassTuple>(), c->d_ctr());
         ForestArgs A;
-        A.pass_w = c->d_mergew.as<unsigned long long>();
-        A.pass_t = c->d_merget.as<PassTuple>();
+        A.pass_w = c->d_pass.as<unsigned long long>();
+        A.pass_t = c->d_passt.as<PassTuple>();
         A.n_pass_p = CTR_FIELD(n_pass);
         A.cap = (unsigned long long)total;
         A.parent = c->d_parent.as<int32_t>();
@@ -2176,6 +2251,7 @@ int multi_join(ejb_ctx* c, const ejb_params* p, const ejb_input* in, ejb_result*
     const int n = (int)ctxs.size();
     std::vector<int> rcs((size_t)n, 0);
     std::vector<std::thread> th;
+    const bool sliced = c->arena_base != nullptr;   // with a declared arena the input crosses PCIe once: 1/n per GPU, the rest over NVLink
     for (int i = 0; i < n; i++)
         th.emplace_back([&, i] {
             ejb_ctx* x = ctxs[i];
@@ -2183,10 +2259,29 @@ int multi_join(ejb_ctx* c, const ejb_params* p, const ejb_input* in, ejb_result*
             x->shard_world = n;
             x->arena_base = c->arena_base;
             x->arena_bytes = c->arena_bytes;
-            int rc = ejb_upload(x, p, in);
-            if (!rc) rc = ejb_run(x);
-            rcs[i] = rc;
+            rcs[i] = sliced ? ejb_upload_slice(x, p, in, i, n) : ejb_upload(x, p, in);
         });
+    for (auto& t : th) t.join();
+    th.clear();
+    for (int i = 0; i < n; i++)
+        if (rcs[i]) {
+            if (i > 0) c->err = ctxs[i]->err;
+            return rcs[i];
+        }
+    if (sliced) {   // all-gather of the arena slices by peer copies: context j pulls slice i from context i
+        const size_t slice = c->arena_slice;
+        for (int j = 0; j < n; j++) {
+            CK(cudaSetDevice(ctxs[j]->device));
+            for (int i = 0; i < n; i++) {
+                if (i == j) continue;
+                const size_t lo = std::min(slice * (size_t)i, c->arena_bytes), hi = std::min(lo + slice, c->arena_bytes);
+                if (hi > lo) CK(cudaMemcpyPeerAsync(ctxs[j]->d_arena.as<char>() + lo, ctxs[j]->device, ctxs[i]->d_arena.as<char>() + lo, ctxs[i]->device, hi - lo, ctxs[j]->stream));
+            }
+        }
+        CK(cudaSetDevice(c->device));
+    }
+    for (int i = 0; i < n; i++)
+        th.emplace_back([&, i] { rcs[i] = ejb_run(ctxs[i]); });
     for (auto& t : th) t.join();
     for (int i = 0; i < n; i++)
         if (rcs[i]) {

@@ -82,7 +82,7 @@ __global__ void k_bucket_starts(const int32_t* __restrict__ head, const int32_t*
 // (lens.len() != 2, join_one.rs:83-96) get the maximal key and fall off the end.
 // Run header on the device: what the host reads back ONCE after the bucket scan and the sub-bucket table are built.
 struct RunHdr {
-    unsigned int err, pad;
+    unsigned int err, big_exacts;   // validation mask; an exact subclonotype with more than BC_SMALL cells exists
     unsigned long long n_active;   // rows with two chains (the only ones that can join)
     unsigned long long n_subs;     // sub-buckets
     unsigned long long n_buckets;  // runs of equal lens
@@ -204,17 +204,38 @@ __global__ void k_row_flags(const int32_t* __restrict__ subq, const int32_t* __r
     flagq[q] = f;
 }
 
-// per exact: donor set as a 64-bit mask (join_one.rs:301-315) and sort keys for the barcode lists
-__global__ void k_exact_prep(DevIn in, unsigned long long* donor_mask, uint64_t* bc_keys) {
+// per exact: donor set as a 64-bit mask (join_one.rs:301-315) and the exact's barcode list in ascending order (the sorted lists
+// the barcode meet of join_one.rs:451-470 walks).  Nearly every exact has a handful of cells: the thread sorts up to
+// BC_SMALL of them itself; a larger exact raises hdr->big_exacts and the host falls back to one global radix sort of the
+// (exact << 32 | barcode) keys, which this kernel writes as well.
+constexpr int BC_SMALL = 32;
+__global__ void k_exact_prep(DevIn in, unsigned long long* donor_mask, uint64_t* bc_keys, uint64_t* bc_sorted, RunHdr* hdr) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= in.n_exacts) return;
     unsigned long long m = 0;
-    for (int64_t j = in.ex_cell_off[e]; j < in.ex_cell_off[e + 1]; j++) {
+    const int64_t j0 = in.ex_cell_off[e], j1 = in.ex_cell_off[e + 1];
+    const int64_t n = j1 - j0;
+    uint32_t loc[BC_SMALL];
+    for (int64_t j = j0; j < j1; j++) {
         const int d = in.cell_donor[j];
         if (d >= 0) m |= 1ull << d;
-        bc_keys[j] = ((uint64_t)e << 32) | (uint64_t)in.cell_barcode[j];
+        const uint32_t bc = in.cell_barcode[j];
+        bc_keys[j] = ((uint64_t)e << 32) | (uint64_t)bc;
+        if (n <= BC_SMALL) {   // insertion into the sorted prefix
+            int i = (int)(j - j0);
+            while (i > 0 && loc[i - 1] > bc) {
+                loc[i] = loc[i - 1];
+                i--;
+            }
+            loc[i] = bc;
+        }
     }
     donor_mask[e] = m;
+    if (n <= BC_SMALL) {
+        for (int i = 0; i < (int)n; i++) bc_sorted[j0 + i] = ((uint64_t)e << 32) | (uint64_t)loc[i];
+    } else {
+        hdr->big_exacts = 1u;
+    }
 }
 
 // Per-segment reference planes + lengths at the canonical seg id (segments with equal content write equal values).

@@ -208,8 +208,9 @@ struct EdgeTuple {      // numeric members of PotentialJoin (defs.rs:870-891); p
 struct PassTuple {      // what a pass edge keeps of its PotentialJoin: the rest (k, d, n, p1, mult, score) is rebuilt from it
     uint32_t cd12;      // cd heavy | cd light << 16
     int32_t sh0, in0, sh1, in1;
-    uint32_t nrefs_err; // nrefs | err << 8
+    uint32_t nrefs_err; // nrefs | err << 8 | PT_SPLIT
 };
+constexpr uint32_t PT_SPLIT = 1u << 16;   // the edge comes from a PART of a sub-bucket that was split over several ranks by row ranges
 
 struct Counters {       // device-side counters, one instance per context
     // ---- zeroed at the start of every scheduler round (one memset over [n_cand, round_end)) ----

@@ -228,6 +228,17 @@ class JoinContext:
                 self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
         return torch.as_tensor(_Dev(ptr, n), device=f"cuda:{self.device}")
 
+    def upload_slice(self, params, inp, part, nparts):
+        """Sharded upload (ejb_upload_slice): only slice `part` of the declared input arena crosses PCIe; complete the device
+        arena with an all-gather on device_arena() before run()."""
+        self._ck(self.L.ejb_upload_slice(self.h, C.byref(params), _c_input(inp), int(part), int(nparts)))
+
+    def device_arena(self):
+        """(uint8 CUDA tensor over the whole device arena, slice_bytes): slice i lives at [i * slice_bytes, (i + 1) * slice_bytes)."""
+        p, total, sl = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._ck(self.L.ejb_device_arena(self.h, C.byref(p), C.byref(total), C.byref(sl)))
+        return self._dev_tensor(p.value, int(total.value), "|u1"), int(sl.value)
+
     def part_forest(self):
         """Partial forest of the last sharded run(): (n, edges int64[n] = (k1 << 28) | k2 with GLOBAL row ids, tuples uint8[24 n])
         as zero-copy torch CUDA tensors (valid until the next run)."""

@@ -346,6 +346,18 @@ int ejb_join_one_batch(ejb_ctx* ctx, const int32_t* k1, const int32_t* k2, int64
  *   ejb_merge_parts    -> forest of the partial forests (Kruskal of a union of graphs == Kruskal of the union of their forests),
  *                         two-cell filter on the merged forest, ordering, PotentialJoin members, labels
  *   ejb_download       -> edges + EquivRel of the WHOLE join.                                                               */
+/* Sharded upload: every context of a sharded join needs the whole input on its GPU, but it need not cross PCIe N times.  With an
+ * input arena declared (ejb_set_input_arena), context `part` of `nparts` copies only ITS slice of the arena host -> device; the
+ * caller completes the device arenas GPU-to-GPU — an in-place all-gather (NCCL / peer copies over NVLink) on the buffer
+ * ejb_device_arena returns, slice i at offset i * slice_bytes, total_bytes = nparts * slice_bytes — and then calls ejb_run.
+ * ejb_join on a multi-device context does exactly this by itself.                                                          */
+int ejb_upload_slice(ejb_ctx* ctx, const ejb_params* p, const ejb_input* in, int part, int nparts);
+int ejb_device_arena(ejb_ctx* ctx, void** d_base, uint64_t* total_bytes, uint64_t* slice_bytes);
+
+/* The assignment itself, as a pure host function (no device; tests and planning tools): sub_rows[s] = rows of sub-bucket s in the
+ * library's order; r_beg[s] / n_act[s] receive the first-row range [r_beg, n_act) that `rank` of `world` joins (empty when
+ * another rank owns the sub-bucket).                                                                                       */
+int ejb_shard_plan(const int32_t* sub_rows, int32_t n_subs, int world, int rank, int32_t* r_beg, int32_t* n_act);
 int ejb_part_forest(ejb_ctx* ctx, int64_t* n_edges, const unsigned long long** d_edges, const void** d_tuples);
 int ejb_merge_buffers(ejb_ctx* ctx, int64_t total_edges, unsigned long long** d_edges, void** d_tuples);
 int ejb_merge_parts(ejb_ctx* ctx, int64_t total_edges);

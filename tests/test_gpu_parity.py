@@ -478,3 +478,32 @@ def test_join_one_batch_matches_oracle(gpu_ctx, config, cells, seed):
         assert np.array_equal(got[f][ok], want[f][ok]), f
     # the reverse order of a joined pair is accepted too unless an order-dependent test says otherwise: whatever it is, equal to the oracle
     assert got["passed"][len(res.edge_k1):2 * len(res.edge_k1)].sum() > 0
+
+
+def test_multi_device_context_with_sliced_arena_upload():
+    """ejb_join on a multi-device context with a declared input arena: every context uploads only its slice of the arena, the
+    rest arrives by GPU-to-GPU copies (the input crosses PCIe once).  Same result as the oracle."""
+    rep = E.generate(1, n_cells=50000, seed=45)
+    src = rep.to_join_input()
+    inp = src.to_packed().to_packed_cdr3()
+    p = E.default_params(True)
+    want = pyoracle.run(p, src.c_ptr(), threads=0)
+    total = sum((a.nbytes + 255) & ~255 for a in inp.a.values())
+    arena = np.zeros(total + 512, dtype=np.uint8)
+    off0 = (-arena.ctypes.data) & 255
+    off, views = off0, {}
+    for name, a in inp.a.items():
+        v = arena[off:off + a.nbytes].view(a.dtype).reshape(a.shape)
+        v[...] = a
+        views[name] = v
+        off += (a.nbytes + 255) & ~255
+    inp2 = E.JoinInput(**views)
+    multi = E.JoinContext(device=[0, 0, 0, 0], cand_cap=1 << 23)
+    try:
+        multi.set_input_arena(arena.ctypes.data + off0, off - off0)
+        got = multi.join(p, inp2)
+        assert got.stats["n_devices"] == 4
+        assert got.stats["h2d_bytes"] < 1.3 * (off - off0), "the arena must cross PCIe once, not once per context"
+        assert_same_result(got, want, "4-context ejb_join, sliced arena")
+    finally:
+        multi.close()
