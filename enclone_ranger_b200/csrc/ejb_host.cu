@@ -184,6 +184,8 @@ struct ejb_ctx {
     // pair-batch mode (ejb_join_one_batch)
     DevBuf d_bpairs, d_bslots, d_btuples, d_bk1, d_bk2, d_qofrow;
     std::vector<SubBucket> subs;
+    std::map<int, std::vector<double>> pow_rows;   // mult_pow ^ (cdr3_normal_len * cd / n) per CDR3 length n, kept across joins
+    double pow_base = -1.0, pow_norm = -1.0;
     int64_t n_active = 0, n_pos = 0, n_blocks = 0, n_final = 0, n_buckets = 0, n_multi = 0, n_part = 0;
     bool have_part = false;     // a sharded run left its partial forest on the device (ejb_part_forest)
     unsigned long long forest_cap = 0;
@@ -874,12 +876,17 @@ int ejb_device_arena(ejb_ctx* c, void** d_base, uint64_t* total_bytes, uint64_t*
 // ================================================================================================
 namespace {
 
-int cub_sort_pairs64(ejb_ctx* c, const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, int64_t n) {
+int cub_sort_pairs64(ejb_ctx* c, const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, int64_t n, int end_bit = 64) {
     size_t tmp = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, (int)n, 0, 64, c->stream));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, (int)n, 0, end_bit, c->stream));
     CK(c->d_cubtmp.ensure(tmp));
-    CK(cub::DeviceRadixSort::SortPairs(c->d_cubtmp.p, tmp, kin, kout, vin, vout, (int)n, 0, 64, c->stream));
+    CK(cub::DeviceRadixSort::SortPairs(c->d_cubtmp.p, tmp, kin, kout, vin, vout, (int)n, 0, end_bit, c->stream));
     return EJB_OK;
+}
+inline int bits_for(int64_t n) {   // bits needed for values 0 .. n
+    int b = 1;
+    while (b < 63 && (1ll << b) <= n) b++;
+    return b;
 }
 int cub_sort_keys64(ejb_ctx* c, const uint64_t* kin, uint64_t* kout, int64_t n) {
     size_t tmp = 0;
@@ -1202,7 +1209,7 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     mark("start");
     RunHdr* const hdr = c->d_err.as<RunHdr>();
     CK(cudaMemsetAsync(c->d_err.p, 0, 256, st));
-    if (c->p1_count > c->p1_cap / 8) {
+    if (c->p1_count > (1ull << 23)) {   // the cache persists across joins (p1 is a pure function) and grows on demand; reset only when huge
         int rc = p1_cache_clear(c);
         if (rc) return rc;
     }
@@ -1230,7 +1237,8 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     int rc = cub_incl_sum(c, c->d_head.as<int32_t>(), c->d_scan.as<int32_t>(), N);
     if (rc) return rc;
     launch(c, k_keys, nblk(N, 256), 256, din, c->d_scan.as<const int32_t>(), c->d_keys.as<uint64_t>(), c->d_vals.as<uint32_t>(), hdr);
-    rc = cub_sort_pairs64(c, c->d_keys.as<uint64_t>(), c->d_keys2.as<uint64_t>(), c->d_vals.as<uint32_t>(), c->d_vals2.as<uint32_t>(), N);
+    // keys: (bucket id << 32) | (c_h << 16) | c_l, bucket id < N; rows that never join carry ~0 (one extra bit keeps them last)
+    rc = cub_sort_pairs64(c, c->d_keys.as<uint64_t>(), c->d_keys2.as<uint64_t>(), c->d_vals.as<uint32_t>(), c->d_vals2.as<uint32_t>(), N, std::min(64, 33 + bits_for(N)));
     if (rc) return rc;
     mark("scan+sort");
     const uint64_t* keys_sorted = c->d_keys2.as<uint64_t>();
@@ -1390,11 +1398,19 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     std::vector<char> len_used((size_t)max_cdr3 + 1, 0);
     for (auto& sb : subs) len_used[sb.ch] = len_used[sb.cl] = 1;
     std::vector<double> powtab;
+    // rows of the table are kept across joins (std::pow is ~25 ns a call and a repertoire uses ~100 CDR3 lengths x their length)
+    if (c->pow_base != c->params.mult_pow || c->pow_norm != (double)c->params.cdr3_normal_len) {
+        c->pow_rows.clear();
+        c->pow_base = c->params.mult_pow;
+        c->pow_norm = (double)c->params.cdr3_normal_len;
+    }
     for (int n = 0; n <= max_cdr3; n++) {
         pow_off[n] = (int32_t)powtab.size();
         if (!len_used[n]) continue;
-        for (int cd = 0; cd <= n; cd++)
-            powtab.push_back(std::pow(c->params.mult_pow, (double)c->params.cdr3_normal_len * (double)cd / (double)n));
+        std::vector<double>& row = c->pow_rows[n];
+        if (row.empty())
+            for (int cd = 0; cd <= n; cd++) row.push_back(std::pow(c->params.mult_pow, (double)c->params.cdr3_normal_len * (double)cd / (double)n));
+        powtab.insert(powtab.end(), row.begin(), row.end());
     }
     if (powtab.empty()) powtab.push_back(1.0);
     CK(c->d_powtab.ensure(powtab.size() * 8));
@@ -1475,7 +1491,8 @@ int finalize(ejb_ctx* c) {
         launch(c, k_two_cell, fgrid, 256, din, make_dev_params(c->params), c->d_forest.as<const unsigned long long>(), (const unsigned long long*)CTR_FIELD(n_forest),
                c->d_deg.as<const int32_t>(), c->d_forestt.as<const PassTuple>(), c->d_parent.as<int32_t>(), c->d_fkeys.as<unsigned long long>(),
                c->d_fidx.as<uint32_t>(), c->d_ctr(), c->have_roles ? c->d_roles.as<const uint8_t>() : (const uint8_t*)nullptr);
-        rc = cub_sort_pairs64(c, c->d_fkeys.as<uint64_t>(), c->d_fkeys2.as<uint64_t>(), c->d_fidx.as<uint32_t>(), c->d_fidx2.as<uint32_t>(), (int64_t)nf);
+        // keys: (k1 << 28) | k2 with k1 < N; the unused tail is ~0 (one extra bit keeps it last)
+        rc = cub_sort_pairs64(c, c->d_fkeys.as<uint64_t>(), c->d_fkeys2.as<uint64_t>(), c->d_fidx.as<uint32_t>(), c->d_fidx2.as<uint32_t>(), (int64_t)nf, std::min(64, 29 + bits_for(N)));
         if (rc) return rc;
         CK(c->d_o_k1.ensure(nf * 4)); CK(c->d_o_k2.ensure(nf * 4)); CK(c->d_o_cd.ensure(nf * 4)); CK(c->d_o_nrefs.ensure(nf * 4));
         CK(c->d_o_sh.ensure(nf * 8)); CK(c->d_o_in.ensure(nf * 8)); CK(c->d_o_k.ensure(nf * 4)); CK(c->d_o_d.ensure(nf * 4));
