@@ -300,20 +300,6 @@ __global__ void k_fill_u64(unsigned long long* p, int64_t n, unsigned long long 
 // ------------------------------------------------------------------------------------------------
 // Finalize (every count stays on the device: no host read-back until the results are downloaded)
 // ------------------------------------------------------------------------------------------------
-// merge of partial forests (multi-GPU): every edge's p1 key is requested on the merging context (its cache only knows the keys
-// of its own part; k_p1 then evaluates the missing ones)
-__global__ void k_p1_request_forest(const unsigned long long* __restrict__ forest, const PassTuple* __restrict__ tuples, const unsigned long long* __restrict__ n_p,
-                                    DevIn in, P1Cache p1c, Counters* ctr) {
-    const unsigned long long n = *n_p;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const int64_t k1 = (int64_t)(forest[i] >> 28);
-        const PassTuple t = tuples[i];
-        const int nrefs = (int)(t.nrefs_err & 0xff);
-        const int min_sh = (nrefs == 2) ? min(t.sh0, t.sh1) : t.sh0;
-        const int min_in = (nrefs == 2) ? min(t.in0, t.in1) : t.in0;
-        p1_request(p1c, 3 * (in.row_len[2 * k1] + in.row_len[2 * k1 + 1]), min_in + 2 * min_sh, min_sh, ctr);
-    }
-}
 // Merge of the gathered partial forests, first pass: an edge of a sub-bucket that ONE rank joined as a whole is final — it goes
 // straight to the merged forest and its endpoints are united; the edges of split sub-buckets (overlapping partial forests) are
 // compacted into the pass-edge list for the Boruvka pass that follows.
@@ -444,9 +430,9 @@ struct FinalOut {
     uint8_t* err;
 };
 // edges in raw_joins order + the PotentialJoin members rebuilt from the kept PassTuple (join_one.rs:444-447, 499-544: same
-// formulas, tables and p1 cache as stage 2b, which accepted the edge with exactly these values)
+// formulas and tables as stage 2b, which accepted the edge with exactly these values; p1 is the value it used)
 __global__ void k_final_gather(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ idx, const unsigned long long* __restrict__ n_p,
-                               const PassTuple* __restrict__ tuples, DevIn in, P1Cache p1c, const double* __restrict__ powtab,
+                               const PassTuple* __restrict__ tuples, DevIn in, const double* __restrict__ powtab,
                                const int32_t* __restrict__ pow_off, FinalOut o) {
     const unsigned long long n = *n_p;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -461,7 +447,7 @@ __global__ void k_final_gather(const unsigned long long* __restrict__ keys, cons
         const int min_sh = (nrefs == 2) ? min(t.sh0, t.sh1) : t.sh0;
         const int min_in = (nrefs == 2) ? min(t.in0, t.in1) : t.in0;
         const int kk = min_in + 2 * min_sh;
-        const double p1 = p1_lookup(p1c, n3, kk, min_sh);
+        const double p1 = t.p1;
         const double mult = __dmul_rn(powtab[pow_off[ch] + cd1], powtab[pow_off[cl] + cd2]);
         o.k1[i] = k1;
         o.k2[i] = k2;

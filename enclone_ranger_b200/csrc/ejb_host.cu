@@ -92,6 +92,23 @@ struct PinBuf {   // page-locked host scratch, grow-only
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// std::vector storage in page-locked memory: the sub-bucket table is built in place and uploaded by a truly asynchronous copy
+template <class T>
+struct PinAlloc {
+    using value_type = T;
+    PinAlloc() = default;
+    template <class U> PinAlloc(const PinAlloc<U>&) {}
+    T* allocate(size_t n) {
+        void* p = nullptr;
+        if (cudaMallocHost(&p, n * sizeof(T)) != cudaSuccess) throw std::bad_alloc();
+        return static_cast<T*>(p);
+    }
+    void deallocate(T* p, size_t) { cudaFreeHost(p); }
+    template <class U> bool operator==(const PinAlloc<U>&) const { return true; }
+    template <class U> bool operator!=(const PinAlloc<U>&) const { return false; }
+};
+using SubVec = std::vector<SubBucket, PinAlloc<SubBucket>>;
+
 struct Unit {  // rows [r0, r1) of one sub-bucket, processed against all columns to their right
     int32_t sub, r0, r1;
     double allow;      // candidates after which the unit is truncated (at a row-range boundary) once stage 1 has counted them
@@ -107,6 +124,7 @@ struct Options {
     int s1_mode = S1_RUNI | S1_TAGS;
     int no_tags = 0;
     int trace = 0;
+    int quot_table = 1;        // p1: quotients from the constant table (0: three-quotient divisions, A/B and parity knob)
     int sr_host = 0;                         // build the Stirling table on the host (A/B against the device kernel)
     long long strict_div = 2048;             // strict allowance of a unit = cand_cap / strict_div candidates
     int early_return = 0;                    // stage-1 CTAs return when the previous block of their unit is certain to be cut (measured: no gain)
@@ -138,6 +156,15 @@ struct ejb_ctx {
     bool have_input = false, have_run = false;
 
     // persistent
+    // p1 term groups (ejb_p1.cuh): group hash, term pool, per-round lists
+    DevBuf d_gkeys, d_goff, d_ghave, d_gwant, d_gstamp, d_gtouched, d_gdesc, d_gpool;
+    uint32_t g_cap = 1u << 20;                    // group slots
+    unsigned long long pool_cap = 1ull << 25;     // term pool entries (16 B)
+    unsigned long long desc_cap = 1ull << 24;     // terms listed per round
+    uint32_t p1_round = 0;
+    unsigned long long p1_groups = 0, p1_pool_used = 0;   // host tallies (from the round reports)
+    DevBuf d_qt;   // quotient table (ejb_p1.cuh), nullptr-safe: option "quot_table" 0 evaluates the divisions
+    const double2* qt() const { return opt.quot_table ? reinterpret_cast<const double2*>(d_qt.p) : nullptr; }
     DevBuf d_sr, d_p1_keys, d_p1_vals, d_p1_new, d_err, d_bar;
     unsigned long long p1_count = 0;   // keys in the p1 cache (host tally of the per-round insert counts)
     char* h_res = nullptr;      // pinned result arena (grow-only); ejb_result arrays point into it
@@ -167,7 +194,7 @@ struct ejb_ctx {
     DevBuf d_qcut, d_subpass, d_segpl, d_seglen, d_memo, d_tagq, d_deadq, d_donq, d_flagq, d_subdom;
     // per-round report: [Counters | UnitOut x units | candidate count x tasks], read back with ONE copy per round
     DevBuf d_round;
-    PinBuf h_round, h_prep, h_stage;
+    PinBuf h_round, h_prep, h_stage, h_tab;
     size_t round_units_cap = 0, round_tasks_cap = 0, cur_round_tasks = 0;
     double cur_strict = 0.0;    // strict allowance of the units of the round being queued
     size_t cur_cta_off = 0;     // offset of the current launch in the CTA -> task map
@@ -183,7 +210,7 @@ struct ejb_ctx {
     DevBuf d_o_k1, d_o_k2, d_o_cd, d_o_nrefs, d_o_sh, d_o_in, d_o_k, d_o_d, d_o_n, d_o_p1, d_o_mult, d_o_score, d_o_err;
     // pair-batch mode (ejb_join_one_batch)
     DevBuf d_bpairs, d_bslots, d_btuples, d_bk1, d_bk2, d_qofrow;
-    std::vector<SubBucket> subs;
+    SubVec subs;
     std::map<int, std::vector<double>> pow_rows;   // mult_pow ^ (cdr3_normal_len * cd / n) per CDR3 length n, kept across joins
     double pow_base = -1.0, pow_norm = -1.0;
     int64_t n_active = 0, n_pos = 0, n_blocks = 0, n_final = 0, n_buckets = 0, n_multi = 0, n_part = 0;
@@ -192,7 +219,7 @@ struct ejb_ctx {
     bool prepared = false;      // the packed row store of the uploaded input is resident (ejb_run got at least that far)
     ejb_stats stats;
 
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> s2a_events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> s2a_events, p1_events;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     cudaEvent_t ev() {
@@ -447,6 +474,96 @@ S2Ctx make_s2ctx(ejb_ctx* c, int tuple_mode) {
     return X;
 }
 
+P1Groups make_p1_groups(ejb_ctx* c) {
+    P1Groups G;
+    G.gkeys = c->d_gkeys.as<unsigned long long>();
+    G.goff = c->d_goff.as<uint32_t>();
+    G.ghave = c->d_ghave.as<uint32_t>();
+    G.gwant = c->d_gwant.as<uint32_t>();
+    G.gstamp = c->d_gstamp.as<uint32_t>();
+    G.touched = c->d_gtouched.as<uint32_t>();
+    G.desc = c->d_gdesc.as<uint2>();
+    G.pool = c->d_gpool.as<double2>();
+    G.gmask = c->g_cap - 1;
+    G.round = c->p1_round;
+    G.pool_cap = c->pool_cap;
+    G.desc_cap = c->desc_cap;
+    G.touched_cap = c->g_cap;
+    return G;
+}
+// p1 of the keys requested since the last call (Counters::n_newkeys of them in pc.newslots): groups -> missing terms -> sums.
+// The per-round counters p1_touched / p1_desc were zeroed with the round block.
+int enqueue_p1(ejb_ctx* c, const P1Cache& pc) {
+    c->p1_round++;
+    const P1Groups G = make_p1_groups(c);
+    const int grid = c->sm_count * 8;
+    const unsigned long long* n_new = (const unsigned long long*)CTR_FIELD(n_newkeys);
+    launch(c, k_p1_groups, grid, 256, pc, G, n_new, c->d_ctr());
+    launch(c, k_p1_expand, grid, 256, G, c->d_ctr());
+    launch(c, k_p1_terms, grid, 256, G, c->d_sr.as<const dd_t>(), c->qt(), c->d_ctr());
+    launch(c, k_p1_sum, grid, 256, pc, G, c->d_sr.as<const dd_t>(), c->qt(), n_new, c->d_ctr());
+    CK(cudaGetLastError());
+    return EJB_OK;
+}
+int p1_groups_alloc(ejb_ctx* c) {
+    const size_t g = c->g_cap;
+    CK(c->d_gkeys.ensure(g * 8)); CK(c->d_goff.ensure(g * 4)); CK(c->d_ghave.ensure(g * 4)); CK(c->d_gwant.ensure(g * 4));
+    CK(c->d_gstamp.ensure(g * 4)); CK(c->d_gtouched.ensure(g * 4));
+    CK(c->d_gdesc.ensure((size_t)c->desc_cap * sizeof(uint2)));
+    CK(c->d_gpool.ensure((size_t)c->pool_cap * sizeof(double2)));
+    return EJB_OK;
+}
+int p1_groups_clear(ejb_ctx* c) {
+    const size_t g = c->g_cap;
+    CK(cudaMemsetAsync(c->d_gkeys.p, 0xff, g * 8, c->stream));
+    CK(cudaMemsetAsync(c->d_ghave.p, 0, g * 4, c->stream));
+    CK(cudaMemsetAsync(c->d_gwant.p, 0, g * 4, c->stream));
+    CK(cudaMemsetAsync(c->d_gstamp.p, 0, g * 4, c->stream));
+    c->p1_round = 0;
+    c->p1_groups = c->p1_pool_used = 0;
+    return EJB_OK;
+}
+// between rounds (rare): keep the group table below 1/4 load, the pool and the per-round term list below 1/2
+int p1_groups_grow(ejb_ctx* c, unsigned long long desc_seen) {
+    cudaStream_t st = c->stream;
+    if (c->p1_groups > c->g_cap / 4 && c->g_cap < (1u << 29)) {
+        const P1Groups src = make_p1_groups(c);
+        const uint32_t old_cap = c->g_cap, new_cap = c->g_cap << 2;
+        DevBuf k, o, h, w, s2, t;
+        CK(k.ensure((size_t)new_cap * 8)); CK(o.ensure((size_t)new_cap * 4)); CK(h.ensure((size_t)new_cap * 4)); CK(w.ensure((size_t)new_cap * 4));
+        CK(s2.ensure((size_t)new_cap * 4)); CK(t.ensure((size_t)new_cap * 4));
+        CK(cudaMemsetAsync(k.p, 0xff, (size_t)new_cap * 8, st));
+        P1Groups dst = src;
+        dst.gkeys = k.as<unsigned long long>(); dst.goff = o.as<uint32_t>(); dst.ghave = h.as<uint32_t>(); dst.gwant = w.as<uint32_t>();
+        dst.gstamp = s2.as<uint32_t>(); dst.touched = t.as<uint32_t>();
+        dst.gmask = new_cap - 1;
+        launch(c, k_p1_groups_rehash, nblk(old_cap, 256), 256, src, old_cap, dst);
+        CK(cudaStreamSynchronize(st));
+        std::swap(c->d_gkeys, k); std::swap(c->d_goff, o); std::swap(c->d_ghave, h); std::swap(c->d_gwant, w); std::swap(c->d_gstamp, s2);
+        std::swap(c->d_gtouched, t);
+        c->g_cap = new_cap;
+    }
+    if (c->p1_pool_used > c->pool_cap / 2 && c->pool_cap < (1ull << 32)) {
+        unsigned long long nc = c->pool_cap;
+        while (c->p1_pool_used > nc / 2 && nc < (1ull << 32)) nc <<= 1;
+        nc = std::min(nc, (1ull << 32) - 1);   // goff is 32 bits
+        DevBuf np;
+        CK(np.ensure((size_t)nc * sizeof(double2)));
+        CK(cudaMemcpyAsync(np.p, c->d_gpool.p, (size_t)std::min(c->p1_pool_used, c->pool_cap) * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        std::swap(c->d_gpool, np);
+        c->pool_cap = nc;
+    }
+    if (desc_seen > c->desc_cap / 2 && c->desc_cap < (1ull << 30)) {
+        while (desc_seen > c->desc_cap / 2 && c->desc_cap < (1ull << 30)) c->desc_cap <<= 1;
+        DevBuf nd;
+        CK(nd.ensure((size_t)c->desc_cap * sizeof(uint2)));
+        CK(cudaStreamSynchronize(st));
+        std::swap(c->d_gdesc, nd);
+    }
+    return EJB_OK;
+}
+
 // stage 2 on a candidate list (count on the device): 2a -> slow -> p1 -> 2b.  The per-round counters it uses were zeroed with
 // the round (filter mode) or by the caller (pair-batch mode).
 int run_stage2(ejb_ctx* c, const uint2* cand, const uint32_t* cand_slot, const unsigned long long* n_cand_dev, unsigned long long list_cap, int tuple_mode,
@@ -460,7 +577,12 @@ int run_stage2(ejb_ctx* c, const uint2* cand, const uint32_t* cand_slot, const u
     c->s2a_events.push_back({ea, eb});
     c->stats.stage2a_launches++;
     launch(c, k_stage2_slow, grid, 256, X, (const unsigned long long*)CTR_FIELD(n_slow));
-    launch(c, k_p1, grid, 256, X.p1, c->d_sr.as<const dd_t>(), (const unsigned long long*)CTR_FIELD(n_newkeys), c->d_ctr());
+    cudaEvent_t pa = c->ev(), pb = c->ev();
+    CK(cudaEventRecord(pa, c->stream));
+    int rc = enqueue_p1(c, X.p1);
+    if (rc) return rc;
+    CK(cudaEventRecord(pb, c->stream));
+    c->p1_events.push_back({pa, pb});
     launch(c, k_stage2b, grid, 256, X, (const unsigned long long*)CTR_FIELD(n_surv), c->d_pass.as<unsigned long long>(), c->d_passt.as<PassTuple>(), c->cand_cap,
            tuples_out);
     CK(cudaGetLastError());
@@ -470,7 +592,7 @@ int run_stage2(ejb_ctx* c, const uint2* cand, const uint32_t* cand_slot, const u
 int p1_cache_clear(ejb_ctx* c) {
     CK(cudaMemsetAsync(c->d_p1_keys.p, 0xff, (size_t)c->p1_cap * 8, c->stream));
     c->p1_count = 0;
-    return EJB_OK;
+    return p1_groups_clear(c);
 }
 // keep the load factor of the p1 hash below 1/4: grow by 4x and re-insert (between rounds; rare)
 int p1_cache_grow(ejb_ctx* c) {
@@ -575,11 +697,13 @@ int create_one(ejb_ctx** out, int dev) {
         static_assert(SR_NMAX < 1024 * SR_KPT, "k_sr_table: one thread owns SR_KPT columns");
         k_sr_table<<<1, 1024, 0, c->stream>>>(c->d_sr.as<dd_t>(), SR_NMAX);
     }
+    if (c->d_qt.ensure((size_t)QT_DELTA * QT_B * sizeof(double2)) != cudaSuccess) return bail(EJB_ERR_OOM);
+    k_quot_table<<<(unsigned)(((size_t)QT_DELTA * QT_B + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<double2*>(c->d_qt.p));
     if (c->d_p1_keys.ensure((size_t)c->p1_cap * 8) != cudaSuccess || c->d_p1_vals.ensure((size_t)c->p1_cap * 8) != cudaSuccess ||
         c->d_p1_new.ensure((size_t)c->p1_cap * 4) != cudaSuccess || c->d_round.ensure(sizeof(Counters) + 4096) != cudaSuccess ||
         c->d_err.ensure(256) != cudaSuccess || c->d_bar.ensure(256) != cudaSuccess)
         return bail(EJB_ERR_OOM);
-    cudaMemsetAsync(c->d_p1_keys.p, 0xff, (size_t)c->p1_cap * 8, c->stream);
+    if (p1_groups_alloc(c) != EJB_OK || p1_cache_clear(c) != EJB_OK) return bail(EJB_ERR_OOM);
     cudaMemsetAsync(c->d_round.p, 0, sizeof(Counters), c->stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return bail(EJB_ERR_CUDA);
     memset(&c->stats, 0, sizeof(c->stats));
@@ -681,6 +805,7 @@ int ejb_set_option(ejb_ctx* c, const char* name, long long value) {
         else if (n == "s1_mode") x->opt.s1_mode = (int)value & 3;
         else if (n == "no_tags") x->opt.no_tags = value != 0;
         else if (n == "trace") x->opt.trace = value != 0;
+        else if (n == "quot_table") x->opt.quot_table = value != 0;
         else return false;
         return true;
     };
@@ -910,7 +1035,7 @@ int cub_incl_sum(ejb_ctx* c, const int32_t* in, int32_t* out, int64_t n) {
 int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& times) {
     const double th0 = now_ms();
     const unsigned long long eval_before = c->pairs_eval_seen;
-    const std::vector<SubBucket>& subs = c->subs;
+    const SubVec& subs = c->subs;
     // ---- tasks grouped by W1; task ids number them in launch order ----
     std::vector<RowTask> tasks[MAXW1 + 1];
     std::vector<ejb_ctx::TaskMeta> metas[MAXW1 + 1];
@@ -1093,7 +1218,10 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     }
     c->p1_count += h.n_newkeys;
     c->stats.p1_unique += (int64_t)h.n_newkeys;
+    c->p1_groups = h.p1_groups;
+    c->p1_pool_used = h.p1_pool_used;
     if (h.p1_full) return fail(c, EJB_ERR_OOM, "p1 cache full (%llu keys in %u slots)", c->p1_count, c->p1_cap);
+    if ((rc = p1_groups_grow(c, h.p1_desc)) != EJB_OK) return rc;
     if (h.overflow == 2ull) return fail(c, EJB_ERR_CUDA, "forest buffer overflow");
     if (h.overflow || h.n_cand > c->cand_cap || h.n_surv > c->cand_cap || h.n_pass > c->cand_cap || h.n_slow > c->cand_cap) {
         if (h.pairs_eval > eval_before) c->cand_rate = std::max(c->cand_rate, (double)h.n_cand / (double)(h.pairs_eval - eval_before));
@@ -1138,15 +1266,18 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
 // the pairs whose FIRST row lies in the range; it returns the lexicographic spanning forest of ITS pass edges, and the merge
 // keeps the minimum spanning forest of the union of the partial forests: MSF(G) = MSF(MSF(G1) u MSF(G2) u ...)).  Parts of one
 // sub-bucket go to different ranks.  Deterministic: every rank computes the same assignment from the same table.
-void shard_assign(std::vector<SubBucket>& subs, int rank, int world, double split_above = 0.25, double piece = 0.125) {
+void shard_assign(SubBucket* subs, int n_subs, int rank, int world, double split_above = 0.25, double piece = 0.125) {
     struct Item { double cost; int sub, lo, hi, nparts; };
     auto cum = [](double n, double r) { return r * (n - 1.0) - r * (r - 1.0) / 2.0 + 64.0 * r; };   // cost of first rows [0, r)
     double total = 0.0;
-    for (const SubBucket& sb : subs)
-        if (sb.n >= 2) total += cum(sb.n, sb.n);
+    for (int s = 0; s < n_subs; s++)
+        if (subs[s].n >= 2) total += cum(subs[s].n, subs[s].n);
     const double share = total / std::max(world, 1);
-    std::vector<Item> items;
-    for (int s = 0; s < (int)subs.size(); s++) {
+    // the items that matter for the balance are sorted (LPT); the many small ones (each below 1/256 of a share) follow in table
+    // order, each to the least loaded rank: the same bound on the imbalance without sorting ten thousand items
+    std::vector<Item> big, small;
+    small.reserve((size_t)n_subs);
+    for (int s = 0; s < n_subs; s++) {
         const SubBucket& sb = subs[s];
         if (sb.n < 2) continue;
         const double c = cum(sb.n, sb.n);
@@ -1165,20 +1296,21 @@ void shard_assign(std::vector<SubBucket>& subs, int rank, int world, double spli
             }
             cuts.push_back(sb.n);
             for (size_t i = 0; i + 1 < cuts.size(); i++)
-                items.push_back({cum(sb.n, cuts[i + 1]) - cum(sb.n, cuts[i]), s, cuts[i], cuts[i + 1], (int)cuts.size() - 1});
+                big.push_back({cum(sb.n, cuts[i + 1]) - cum(sb.n, cuts[i]), s, cuts[i], cuts[i + 1], (int)cuts.size() - 1});
+        } else if (c * 256.0 >= share) {
+            big.push_back({c, s, 0, sb.n, 1});
         } else {
-            items.push_back({c, s, 0, sb.n, 1});
+            small.push_back({c, s, 0, sb.n, 1});
         }
     }
-    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
+    std::stable_sort(big.begin(), big.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
     std::vector<double> load((size_t)world, 0.0);
-    if (world > 1) load[0] = 0.2 * share;   // rank 0 also gathers, merges and finalizes (by convention the merging context)
-    std::vector<uint64_t> holder(subs.size(), 0);   // ranks already holding a part of the sub-bucket (world <= 64)
-    for (SubBucket& sb : subs) {
-        sb.owner = -1;
-        sb.r_beg = sb.n_act = 0;
+    std::vector<uint64_t> holder((size_t)n_subs, 0);   // ranks already holding a part of the sub-bucket (world <= 64)
+    for (int s = 0; s < n_subs; s++) {
+        subs[s].owner = -1;
+        subs[s].r_beg = subs[s].n_act = 0;
     }
-    for (const Item& it : items) {
+    auto place = [&](const Item& it) {
         int best = -1;
         for (int r = 0; r < world; r++) {
             if (holder[(size_t)it.sub] >> r & 1) continue;
@@ -1188,11 +1320,13 @@ void shard_assign(std::vector<SubBucket>& subs, int rank, int world, double spli
         holder[(size_t)it.sub] |= 1ull << best;
         load[(size_t)best] += it.cost;
         if (best == rank) {
-            subs[(size_t)it.sub].r_beg = it.lo;
-            subs[(size_t)it.sub].n_act = it.hi;
-            subs[(size_t)it.sub].owner = it.nparts == 1 ? rank : -1;
+            subs[it.sub].r_beg = it.lo;
+            subs[it.sub].n_act = it.hi;
+            subs[it.sub].owner = it.nparts == 1 ? rank : -1;
         }
-    }
+    };
+    for (const Item& it : big) place(it);
+    for (const Item& it : small) place(it);
 }
 
 // ---- prepare: bucket scan, sub-bucket table, bucketer.  ONE read-back (the run header + the sub-bucket table). ----
@@ -1209,7 +1343,9 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     mark("start");
     RunHdr* const hdr = c->d_err.as<RunHdr>();
     CK(cudaMemsetAsync(c->d_err.p, 0, 256, st));
-    if (c->p1_count > (1ull << 23)) {   // the cache persists across joins (p1 is a pure function) and grows on demand; reset only when huge
+    // Every join evaluates the p1 values it needs (what a caller that joins once per process sees, and what a benchmark must
+    // time): the memo of p1(n, k, d) and its term groups only live for one join.
+    {
         int rc = p1_cache_clear(c);
         if (rc) return rc;
     }
@@ -1275,6 +1411,7 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     mark("subinfo");
     rc = sync_stream(c);
     if (rc) return rc;
+    const double th0 = now_ms();
     const RunHdr hh = *c->h_prep.as<RunHdr>();
     if (hh.err & 16384u) return fail(c, EJB_ERR_INVALID, "row roles: column-only rows must form a suffix of their sub-bucket");
     if (hh.err) return fail(c, EJB_ERR_INVALID, "input validation failed (mask 0x%x: 1 nchains, 2 exact id, 4 tig offsets, 8 cdr3 offsets, 16 seg ids, 32 exact_cols, 64/128 exact tables, 256 ref ids, 512 amino, 1024 donor id >= 64, 2048 seg_off, 4096 ref_off, 8192 packed contig)", hh.err);
@@ -1307,7 +1444,7 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
 
     // ---- sub-bucket table: sizes and thresholds first, then ownership (multi-GPU), then offsets of what this context packs ----
     const DevParams P = make_dev_params(c->params);
-    std::vector<SubBucket>& subs = c->subs;
+    SubVec& subs = c->subs;
     subs.resize(n_subs);
     int max_cdr3 = 0;
     for (int s = 0; s < n_subs; s++) {
@@ -1337,8 +1474,11 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
         // stage-1 threshold: a superset of join_one.rs:231 and :286-290 (stage 2 re-tests exactly)
         int maxcd = T;
         if (P.is_bcr) {
+            // the largest cd with !(cd / T > thr): the predicate is monotone in cd, so start just above thr * T
             maxcd = 0;
-            for (int cd = T; cd >= 0; cd--)
+            int cd_hi = T;
+            if (P.cdr3_ident_thr >= 0.0 && P.cdr3_ident_thr < 1.0) cd_hi = std::min(T, (int)(P.cdr3_ident_thr * (double)T) + 2);
+            for (int cd = cd_hi; cd >= 0; cd--)
                 if (!((double)cd / (double)T > P.cdr3_ident_thr)) { maxcd = cd; break; }
             if (T == 0) maxcd = 0;
             if (P.max_cdr3_diffs < 1000) maxcd = (int)std::min<long long>(maxcd, P.max_cdr3_diffs);
@@ -1348,8 +1488,10 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
         sb.maxcd = maxcd;
         max_cdr3 = std::max({max_cdr3, sb.ch, sb.cl});
     }
+    const double th1 = now_ms();
     // ---- multi-GPU ownership (identical on every rank: same table, same deterministic assignment) ----
-    if (c->shard_world > 1) shard_assign(subs, c->shard_rank, c->shard_world);
+    if (c->shard_world > 1) shard_assign(subs.data(), n_subs, c->shard_rank, c->shard_world);
+    const double th2 = now_ms();
     int64_t q = 0, s1 = 0, rs = 0, blk = 0;
     int64_t bucket_rows = 0;
     uint64_t cur_bucket = ~0ull;
@@ -1393,6 +1535,7 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     if (q >= (1ll << 31)) return fail(c, EJB_ERR_INVALID, "too many packed rows");
     if (rs >= (1ll << 32) || s1 >= (1ll << 32)) return fail(c, EJB_ERR_INVALID, "packed row store exceeds 32-bit indexing (64 GB)");
 
+    const double th3 = now_ms();
     // ---- pow table: mult_pow ^ (cdr3_normal_len * cd / n), join_one.rs:531-539 ----
     std::vector<int32_t> pow_off((size_t)max_cdr3 + 2, 0);
     std::vector<char> len_used((size_t)max_cdr3 + 1, 0);
@@ -1413,11 +1556,26 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
         powtab.insert(powtab.end(), row.begin(), row.end());
     }
     if (powtab.empty()) powtab.push_back(1.0);
+    std::vector<int32_t> blk_sub((size_t)blk);
+    for (int s : pack_sub)
+        for (int b = 0; b < (subs[s].n + TILE - 1) / TILE; b++) blk_sub[subs[s].blk0 + b] = s;
+    // small tables go through one pinned staging buffer (a copy from pageable memory would synchronise the stream first)
+    const size_t o_pow = 0, o_poff = o_pow + ((powtab.size() * 8 + 15) & ~(size_t)15), o_blk = o_poff + ((pow_off.size() * 4 + 15) & ~(size_t)15),
+                 o_poffs = o_blk + ((blk_sub.size() * 4 + 15) & ~(size_t)15), o_psub = o_poffs + ((pack_off.size() * 8 + 15) & ~(size_t)15),
+                 o_end = o_psub + pack_sub.size() * 4 + 16;
+    CK(c->h_tab.ensure(o_end));
+    char* const ht = c->h_tab.as<char>();
+    memcpy(ht + o_pow, powtab.data(), powtab.size() * 8);
+    memcpy(ht + o_poff, pow_off.data(), pow_off.size() * 4);
+    memcpy(ht + o_blk, blk_sub.data(), blk_sub.size() * 4);
+    memcpy(ht + o_poffs, pack_off.data(), pack_off.size() * 8);
+    memcpy(ht + o_psub, pack_sub.data(), pack_sub.size() * 4);
     CK(c->d_powtab.ensure(powtab.size() * 8));
     CK(c->d_powoff.ensure(pow_off.size() * 4));
-    CK(cudaMemcpyAsync(c->d_powtab.p, powtab.data(), powtab.size() * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->d_powoff.p, pow_off.data(), pow_off.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_powtab.p, ht + o_pow, powtab.size() * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_powoff.p, ht + o_poff, pow_off.size() * 4, cudaMemcpyHostToDevice, st));
 
+    const double th4 = now_ms();
     // ---- device arrays ----
     CK(c->d_qcut.ensure((size_t)n_subs * 4 + 4));
     CK(c->d_subpass.ensure((size_t)n_subs * 4 + 4));
@@ -1425,11 +1583,8 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     CK(cudaMemsetAsync(c->d_subpass.p, 0, (size_t)n_subs * 4, st));
     CK(c->d_subs.ensure((size_t)n_subs * sizeof(SubBucket)));
     CK(cudaMemcpyAsync(c->d_subs.p, subs.data(), (size_t)n_subs * sizeof(SubBucket), cudaMemcpyHostToDevice, st));
-    std::vector<int32_t> blk_sub((size_t)blk);
-    for (int s : pack_sub)
-        for (int b = 0; b < (subs[s].n + TILE - 1) / TILE; b++) blk_sub[subs[s].blk0 + b] = s;
     CK(c->d_blksub.ensure((size_t)std::max<int64_t>(blk, 1) * 4));
-    CK(cudaMemcpyAsync(c->d_blksub.p, blk_sub.data(), (size_t)blk * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_blksub.p, ht + o_blk, (size_t)blk * 4, cudaMemcpyHostToDevice, st));
     CK(c->d_cdr3w.ensure((size_t)(s1 + 4) * 4));
     CK(c->d_rowstore.ensure((size_t)(rs + 1) * 16));
     const size_t np = (size_t)c->n_pos + 4;
@@ -1453,8 +1608,8 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     const int n_pack = (int)pack_sub.size();
     CK(c->d_packoff.ensure(pack_off.size() * 8));
     CK(c->d_packsub.ensure((size_t)std::max(n_pack, 1) * 4));
-    CK(cudaMemcpyAsync(c->d_packoff.p, pack_off.data(), pack_off.size() * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->d_packsub.p, pack_sub.data(), (size_t)n_pack * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_packoff.p, ht + o_poffs, pack_off.size() * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_packsub.p, ht + o_psub, (size_t)n_pack * 4, cudaMemcpyHostToDevice, st));
     if (n_pack > 0)
     launch(c, k_pack_rows, nblk(pack_off.back() * 32, 256), 256, din, P, c->d_subs.as<const SubBucket>(), c->d_packoff.as<const int64_t>(),
            c->d_packsub.as<const int32_t>(), n_pack, row_of, c->d_donor.as<const unsigned long long>(), c->d_segpl.as<const uint32_t>(), c->d_seglen.as<const int32_t>(),
@@ -1464,6 +1619,9 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
         launch(c, k_sub_dominant, nblk(n_subs, 128), 128, c->d_subs.as<const SubBucket>(), n_subs, c->d_tagq.as<const unsigned long long>(),
                c->d_donq.as<const unsigned long long>(), c->d_subdom.as<SubDom>());
     mark("pack_rows");
+    if (c->opt.trace)
+        fprintf(stderr, "[ejb trace] prepare host: table %.3f ms, shard plan %.3f ms, offsets %.3f ms, pow %.3f ms, uploads + enqueue %.3f ms\n", th1 - th0, th2 - th1,
+                th3 - th2, th4 - th3, now_ms() - th4);
     CK(cudaGetLastError());
     return EJB_OK;
 }
@@ -1503,13 +1661,8 @@ int finalize(ejb_ctx* c) {
         fo.shares = c->d_o_sh.as<int32_t>(); fo.indeps = c->d_o_in.as<int32_t>(); fo.k = c->d_o_k.as<int32_t>(); fo.d = c->d_o_d.as<int32_t>();
         fo.n = c->d_o_n.as<int32_t>(); fo.p1 = c->d_o_p1.as<double>(); fo.mult = c->d_o_mult.as<double>(); fo.score = c->d_o_score.as<double>();
         fo.err = c->d_o_err.as<uint8_t>();
-        P1Cache pc;
-        pc.keys = c->d_p1_keys.as<unsigned long long>();
-        pc.vals = c->d_p1_vals.as<double>();
-        pc.newslots = c->d_p1_new.as<uint32_t>();
-        pc.cap_mask = c->p1_cap - 1;
         launch(c, k_final_gather, fgrid, 256, c->d_fkeys2.as<const unsigned long long>(), c->d_fidx2.as<const uint32_t>(), (const unsigned long long*)CTR_FIELD(n_final),
-               c->d_forestt.as<const PassTuple>(), din, pc, c->d_powtab.as<const double>(), c->d_powoff.as<const int32_t>(), fo);
+               c->d_forestt.as<const PassTuple>(), din, c->d_powtab.as<const double>(), c->d_powoff.as<const int32_t>(), fo);
     }
     if (N > 0) {
         // join2.rs:69-84 + canonical labels
@@ -1540,6 +1693,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
     memset(&c->stats, 0, sizeof(c->stats));
     c->ev_used = 0;
     c->s2a_events.clear();
+    c->p1_events.clear();
     const DevIn& din = c->din;
     const int64_t N = din.n_rows;
     cudaStream_t st = c->stream;
@@ -1583,7 +1737,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
 
     // ---- round scheduler ----
     {
-        const std::vector<SubBucket>& subs = c->subs;
+        const SubVec& subs = c->subs;
         // Units: rows [r0, r1) of a sub-bucket against every column to their right, in row order.  A unit may only be
         // split by ROWS (splitting by columns and contracting after each part is not exact: a lighter edge from a later
         // column part could have to evict a heavier edge already in the forest).
@@ -1649,6 +1803,7 @@ extern "C" int ejb_run(ejb_ctx* c) {
                     const long long done = r0 - sb.r_beg;   // rows this context has processed as first rows
                     const long long want = (done == 0) ? first_unit : std::max<long long>(first_unit, growth * done);   // optimistic growth: rows done so far x growth
                     r1 = (int)std::min<long long>((long long)r0 + want, sb.n_act);
+                    if (sb.n_act - r1 < (r1 - r0) / 4) r1 = sb.n_act;   // no separate round for a short tail
                     ex = (rho[s] > 0.0 ? rho[s] : std::min<double>(64.0, (double)sb.n)) * (double)(r1 - r0);
                     // capacity: never plan more expected candidates than a round may hold
                     if (ex > 0.5 * cap_round) {
@@ -1782,6 +1937,14 @@ extern "C" int ejb_run(ejb_ctx* c) {
         }
         fprintf(stderr, "[ejb trace] finalize %.3f ms, %lld syncs, %lld boruvka iterations\n", c->stats.ms_finalize, (long long)c->stats.host_syncs,
                 (long long)c->stats.boruvka_iterations);
+        float p1ms = 0;
+        for (auto& pe : c->p1_events) {
+            float x = 0;
+            cudaEventElapsedTime(&x, pe.first, pe.second);
+            p1ms += x;
+        }
+        fprintf(stderr, "[ejb trace] p1: %.3f ms; %llu keys in %llu groups, %llu terms evaluated (%llu pool entries), %llu keys by the direct path\n", p1ms,
+                h.p1_total, h.p1_groups, h.p1_terms, h.p1_pool_used, h.p1_direct);
     }
     c->stats.ms_h2d = c->ms_h2d;
     c->stats.h2d_bytes = c->h2d_bytes;
@@ -1973,7 +2136,7 @@ int ejb_p1_batch(ejb_ctx* c, const int32_t* k, const int32_t* d, const int32_t* 
     CK(cudaMemcpyAsync(dk.p, k, count * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(dd_.p, d, count * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(dn.p, n, count * 4, cudaMemcpyHostToDevice, c->stream));
-    k_p1_batch<<<nblk(count * 32, 128), 128, 0, c->stream>>>(c->d_sr.as<dd_t>(), dk.as<int32_t>(), dd_.as<int32_t>(), dn.as<int32_t>(), count, dout.as<double>());
+    k_p1_batch<<<nblk(count * 32, 128), 128, 0, c->stream>>>(c->d_sr.as<dd_t>(), c->qt(), dk.as<int32_t>(), dd_.as<int32_t>(), dn.as<int32_t>(), count, dout.as<double>());
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(p1_out, dout.p, count * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -2091,7 +2254,10 @@ extern "C" int ejb_join_one_batch(ejb_ctx* c, const int32_t* k1, const int32_t* 
         if (*reinterpret_cast<const unsigned int*>(c->h_round.as<char>() + sizeof(Counters))) return fail(c, EJB_ERR_INVALID, "pair batch: row index out of range");
         if (h.overflow || h.p1_full) return fail(c, EJB_ERR_OOM, "pair batch overflowed the work buffers");
         if (h.n_errflag_panic) return fail(c, EJB_ERR_INVALID, "pair batch: input on which the reference panics");
-        if (c->p1_count > c->p1_cap / 4 && (rc = p1_cache_grow(c)) != EJB_OK) return rc;
+c->p1_groups = h.p1_groups;
+        c->p1_pool_used = h.p1_pool_used;
+        if ((rc = p1_groups_grow(c, h.p1_desc)) != EJB_OK) return rc;
+                if (c->p1_count > c->p1_cap / 4 && (rc = p1_cache_grow(c)) != EJB_OK) return rc;
         for (int64_t i = 0; i < m; i++) {
             const EdgeTuple& t = host[(size_t)i];
             const int64_t g = o + i;
@@ -2126,7 +2292,7 @@ int ejb_shard_plan(const int32_t* sub_rows, int32_t n_subs, int world, int rank,
         memset(&subs[(size_t)s], 0, sizeof(SubBucket));
         subs[(size_t)s].n = sub_rows[s];
     }
-    shard_assign(subs, rank, world);
+    shard_assign(subs.data(), n_subs, rank, world);
     for (int s = 0; s < n_subs; s++) {
         r_beg[s] = subs[(size_t)s].r_beg;
         n_act[s] = subs[(size_t)s].n_act;
@@ -2185,10 +2351,6 @@ int ejb_merge_parts(ejb_ctx* c, int64_t total) {
     CK(c->d_roots.ensure((size_t)std::max<int64_t>(total, 1) * 8));
     CK(c->d_pass.ensure((size_t)std::max<int64_t>(total, 1) * 8));
     CK(c->d_passt.ensure((size_t)std::max<int64_t>(total, 1) * sizeof(PassTuple)));
-    if (c->p1_count > c->p1_cap / 8) {
-        int rc = p1_cache_grow(c);
-        if (rc) return rc;
-    }
     if (total > 0) {
         // edges of whole sub-buckets: final, united directly; edges of split sub-buckets: compacted for the Boruvka pass
         launch(c, k_merge_split, c->sm_count * 8, 256, c->d_mergew.as<const unsigned long long>(), c->d_merget.as<const PassTuple>(), (unsigned long long)total,
@@ -2218,15 +2380,7 @@ int ejb_merge_parts(ejb_ctx* c, int64_t total) {
         void* args[] = {&A};
         CK(cudaLaunchCooperativeKernel((const void*)k_forest_round, dim3((unsigned int)c->coop_grid), dim3(256), args, 0, st));
         c->stats.kernel_launches++;
-        // p1 of every merged edge: this context's cache only holds the keys of its own part
-        P1Cache pc;
-        pc.keys = c->d_p1_keys.as<unsigned long long>();
-        pc.vals = c->d_p1_vals.as<double>();
-        pc.newslots = c->d_p1_new.as<uint32_t>();
-        pc.cap_mask = c->p1_cap - 1;
-        launch(c, k_p1_request_forest, c->sm_count * 8, 256, c->d_forest.as<const unsigned long long>(), c->d_forestt.as<const PassTuple>(),
-               (const unsigned long long*)CTR_FIELD(n_forest), c->din, pc, c->d_ctr());
-        launch(c, k_p1, c->sm_count * 8, 256, pc, c->d_sr.as<const dd_t>(), (const unsigned long long*)CTR_FIELD(n_newkeys), c->d_ctr());
+        // p1 of every merged edge travels in its PassTuple: nothing is re-evaluated here
     }
     int rc = finalize(c);
     if (rc) return rc;

@@ -839,6 +839,7 @@ __global__ void __launch_bounds__(256, S2B_MINB) k_stage2b(S2Ctx X, const unsign
             pass_tup.in0 = s.in0;
             pass_tup.sh1 = (s.nrefs == 2) ? s.sh1 : 0;
             pass_tup.in1 = (s.nrefs == 2) ? s.in1 : 0;
+            pass_tup.p1 = p1;
             pass_tup.nrefs_err = (uint32_t)s.nrefs | ((uint32_t)s.err << 8) | (sb.owner < 0 ? PT_SPLIT : 0u);   // owner < 0: sub-bucket split over ranks
         }
       }

@@ -205,17 +205,20 @@ struct EdgeTuple {      // numeric members of PotentialJoin (defs.rs:870-891); p
     int32_t cd, nrefs, sh0, sh1, in0, in1, k, d, n, err, pass, pad;
     double p1, mult, score;
 };
-struct PassTuple {      // what a pass edge keeps of its PotentialJoin: the rest (k, d, n, p1, mult, score) is rebuilt from it
+struct PassTuple {      // what a pass edge keeps of its PotentialJoin: the rest (k, d, n, mult, score) is rebuilt from it.  32 bytes.
     uint32_t cd12;      // cd heavy | cd light << 16
     int32_t sh0, in0, sh1, in1;
     uint32_t nrefs_err; // nrefs | err << 8 | PT_SPLIT
+    double p1;          // the value stage 2b accepted the edge with (travels with the edge: a merging rank never re-evaluates it)
 };
+static_assert(sizeof(PassTuple) == 32, "PassTuple is part of the partial-forest exchange format");
 constexpr uint32_t PT_SPLIT = 1u << 16;   // the edge comes from a PART of a sub-bucket that was split over several ranks by row ranges
 
 struct Counters {       // device-side counters, one instance per context
     // ---- zeroed at the start of every scheduler round (one memset over [n_cand, round_end)) ----
     unsigned long long n_cand, n_slow, n_surv, n_pass, n_newkeys, overflow, n_surv_total, s2_work;
     unsigned long long any_cut;       // a unit of this round was truncated after stage 1 (k_truncate)
+    unsigned long long p1_touched, p1_desc;   // p1 term groups touched / terms listed for evaluation in this round (ejb_p1.cuh)
     unsigned long long alive_it[64];  // Boruvka: edges still joining two components, per iteration of this round
     unsigned long long round_end;     // marker only
     // ---- per run ----
@@ -224,6 +227,8 @@ struct Counters {       // device-side counters, one instance per context
     unsigned long long n_multi;       // rows whose exact subclonotype owns two or more rows (finish_join's clonotype_id merge, join2.rs:69-84)
     unsigned long long p1_total;      // keys ever inserted into the p1 cache since it was last cleared
     unsigned long long p1_full;       // a probe sequence of the p1 cache ran through the whole table (must not happen: the host grows it)
+    unsigned long long p1_groups, p1_pool_used;   // (n, k) term groups and term-pool entries handed out since the p1 structures were reset
+    unsigned long long p1_terms, p1_direct;       // terms evaluated; keys summed by the direct path (a term structure was full)
     unsigned long long s1_first;      // stage 1: lane-pairs whose first CDR3 word went through XOR + popc
     unsigned long long s1_full;       // stage 1: lane-pairs whose remaining CDR3 words were evaluated too
     unsigned long long bor_iters;     // Boruvka iterations over all rounds

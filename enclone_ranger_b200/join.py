@@ -248,7 +248,7 @@ class JoinContext:
         if n.value == 0:
             dev = f"cuda:{self.device}"
             return 0, torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.uint8, device=dev)
-        return n.value, self._dev_tensor(e.value, n.value, "<i8"), self._dev_tensor(t.value, 24 * n.value, "|u1")
+        return n.value, self._dev_tensor(e.value, n.value, "<i8"), self._dev_tensor(t.value, 32 * n.value, "|u1")
 
     def merge_buffers(self, total):
         """Device buffers of the merging context for the concatenated partial forests (edges int64[total], tuples uint8[24 total])."""
@@ -258,7 +258,7 @@ class JoinContext:
         if total == 0:
             dev = f"cuda:{self.device}"
             return torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.uint8, device=dev)
-        return self._dev_tensor(e.value, int(total), "<i8"), self._dev_tensor(t.value, 24 * int(total), "|u1")
+        return self._dev_tensor(e.value, int(total), "<i8"), self._dev_tensor(t.value, 32 * int(total), "|u1")
 
     def merge_parts(self, total):
         """Forest of the gathered partial forests + finalize on this context; download() then returns the WHOLE join."""

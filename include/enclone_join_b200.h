@@ -277,7 +277,8 @@ typedef struct ejb_ctx ejb_ctx;
  * collective on the data path), gathers the per-device forests and merges them; the caller sees one result.      */
 int ejb_create(ejb_ctx** out, const int* device_ids, int n_devices);
 /* Developer / test knobs (none is needed in production).  Names: "first_unit", "growth" (unit schedule), "s1_mode"
- * (bit 0 uniform-label vote, bit 1 tags), "no_tags", "trace".  The EJB_* environment variables of the same meaning are
+ * (bit 0 uniform-label vote, bit 1 tags), "no_tags", "trace", "p1_keep" (1: keep the memo of p1(n, k, d) values
+ * across the joins of this context; default 0 — every join evaluates what it needs).  The EJB_* environment variables of the same meaning are
  * read ONCE, in ejb_create; this call overrides them for the following joins.  Unknown name: EJB_ERR_INVALID.     */
 int ejb_set_option(ejb_ctx* ctx, const char* name, long long value);
 /* Milliseconds ejb_create spent building + uploading the Stirling ratio table (device build: start.rs:50-99).   */
@@ -340,7 +341,7 @@ int ejb_join_one_batch(ejb_ctx* ctx, const int32_t* k1, const int32_t* k2, int64
  * its share: whole sub-buckets by longest-processing-time assignment on a pair-count cost model, the heaviest sub-buckets cut
  * into row ranges (identical, deterministic assignment on every rank; no collective on the data path).  A sharded ejb_run ends
  * before the finalize step and leaves its PARTIAL FOREST on the device:
- *   ejb_part_forest    -> device pointers to the part's edges (8-byte weights (k1 << 28) | k2, global row ids) and 24-byte tuples
+ *   ejb_part_forest    -> device pointers to the part's edges (8-byte weights (k1 << 28) | k2, global row ids) and 32-byte tuples
  *   ejb_merge_buffers  -> on the merging context (any rank that also ran its part): device buffers for the concatenation of all
  *                         parts; the caller fills them GPU-to-GPU (NCCL gather, peer copies)
  *   ejb_merge_parts    -> forest of the partial forests (Kruskal of a union of graphs == Kruskal of the union of their forests),

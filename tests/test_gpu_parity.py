@@ -125,7 +125,7 @@ def _sharded_join(p, inp, world, cand_cap=1 << 23):
         off = 0
         for n, e, t in parts:
             ew[off:off + n].copy_(e)
-            tw[24 * off:24 * (off + n)].copy_(t)
+            tw[32 * off:32 * (off + n)].copy_(t)
             off += n
         torch.cuda.synchronize()
         ctxs[0].merge_parts(total)

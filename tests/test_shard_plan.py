@@ -51,8 +51,9 @@ def test_plan_partitions_the_pair_domain(world):
     total = sum(int(n) * (int(n) - 1) // 2 for n in sizes)
     assert load.sum() == total
     if world > 1:
-        # pair counts are what the cost model balances; rank 0 gets a fifth of a share less (it also merges)
-        assert load[1:].max() / load[1:].mean() < 1.05 and load[0] < load[1:].mean(), load
+        # pair counts are what the cost model balances (the merging rank gets a full share: the merge only starts when the
+        # slowest part is in, so an early rank 0 would shorten nothing)
+        assert load.max() / load.mean() < 1.05, load
         assert split > 0, "a 52k-row sub-bucket must be cut into row ranges"
 
 
