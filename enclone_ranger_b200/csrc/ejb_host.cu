@@ -124,6 +124,7 @@ struct Options {
     int s1_mode = S1_RUNI | S1_TAGS;
     int no_tags = 0;
     int trace = 0;
+    int thin = 1;              // stage 1: units of at most 16 rows go to k_stage1_thin (0: always k_stage1, A/B and parity knob)
     int quot_table = 1;        // p1: quotients from the constant table (0: three-quotient divisions, A/B and parity knob)
     int sr_host = 0;                         // build the Stirling table on the host (A/B against the device kernel)
     long long strict_div = 2048;             // strict allowance of a unit = cand_cap / strict_div candidates
@@ -163,6 +164,7 @@ struct ejb_ctx {
     unsigned long long desc_cap = 1ull << 24;     // terms listed per round
     uint32_t p1_round = 0;
     unsigned long long p1_groups = 0, p1_pool_used = 0;   // host tallies (from the round reports)
+    DevBuf d_slowrows;   // rows the 8-lane bucketer left to the generic kernel
     DevBuf d_qt;   // quotient table (ejb_p1.cuh), nullptr-safe: option "quot_table" 0 evaluates the divisions
     const double2* qt() const { return opt.quot_table ? reinterpret_cast<const double2*>(d_qt.p) : nullptr; }
     DevBuf d_sr, d_p1_keys, d_p1_vals, d_p1_new, d_err, d_bar;
@@ -368,6 +370,19 @@ void launch_stage1_w(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, int n_tas
         case 2: launch_stage1_wm<W1, S1_TAGS>(c, n_ctas, tasks, n_tasks, unit_cand, strip); break;
         default: launch_stage1_wm<W1, S1_RUNI | S1_TAGS>(c, n_ctas, tasks, n_tasks, unit_cand, strip); break;
     }
+}
+
+template <int W1>
+void launch_stage1_thin(ejb_ctx* c, int64_t n_ctas, const RowTask* tasks, unsigned long long* unit_cand, int strip) {
+    const bool tags = c->tags_on && (c->opt.s1_mode & S1_TAGS);
+    if (tags)
+        launch(c, k_stage1_thin<W1, true>, (unsigned int)n_ctas, S1_THREADS, c->d_subs.as<SubBucket>(), tasks, c->d_cdr3w.as<uint32_t>(), c->d_labq.as<int32_t>(),
+               c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr(), unit_cand, c->d_tagq.as<unsigned long long>(), c->d_deadq.as<unsigned long long>(),
+               c->d_donq.as<unsigned long long>(), c->d_flagq.as<uint32_t>(), strip, c->d_ctatask.as<const int32_t>() + c->cur_cta_off);
+    else
+        launch(c, k_stage1_thin<W1, false>, (unsigned int)n_ctas, S1_THREADS, c->d_subs.as<SubBucket>(), tasks, c->d_cdr3w.as<uint32_t>(), c->d_labq.as<int32_t>(),
+               c->d_cand.as<uint2>(), c->cand_cap, c->d_ctr(), unit_cand, (const unsigned long long*)nullptr, (const unsigned long long*)nullptr,
+               (const unsigned long long*)nullptr, (const uint32_t*)nullptr, strip, c->d_ctatask.as<const int32_t>() + c->cur_cta_off);
 }
 
 // CTA -> task map of one stage-1 launch: thread per (task, CTA of the task); replaces a binary search over the task list in the
@@ -806,6 +821,7 @@ int ejb_set_option(ejb_ctx* c, const char* name, long long value) {
         else if (n == "no_tags") x->opt.no_tags = value != 0;
         else if (n == "trace") x->opt.trace = value != 0;
         else if (n == "quot_table") x->opt.quot_table = value != 0;
+        else if (n == "thin") x->opt.thin = value != 0;
         else return false;
         return true;
     };
@@ -1037,20 +1053,27 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     const unsigned long long eval_before = c->pairs_eval_seen;
     const SubVec& subs = c->subs;
     // ---- tasks grouped by W1; task ids number them in launch order ----
-    std::vector<RowTask> tasks[MAXW1 + 1];
-    std::vector<ejb_ctx::TaskMeta> metas[MAXW1 + 1];
-    int64_t nctas[MAXW1 + 1] = {0};
+    // groups 0 .. MAXW1: k_stage1 per CDR3 width (0: no filter); groups MAXW1+1+W1: the THIN units of that width (at most
+    // S1_THIN_ROWS rows: the first rounds of every sub-bucket), scored by k_stage1_thin
+    constexpr int NG = 2 * (MAXW1 + 1);
+    auto group_of = [&](const Unit& u, const SubBucket& sb) {
+        return (c->opt.thin && sb.W1 >= 1 && u.r1 - u.r0 <= S1_THIN_ROWS) ? MAXW1 + 1 + sb.W1 : sb.W1;
+    };
+    std::vector<RowTask> tasks[NG];
+    std::vector<ejb_ctx::TaskMeta> metas[NG];
+    int64_t nctas[NG] = {0};
     // column tiles per CTA, per launch: short strips keep the early rounds (a few rows of every sub-bucket) wide enough to fill
     // the GPU, long strips amortise the per-CTA prologue (task lookup, row fragment) once a launch has tens of thousands of CTAs
-    int strip_of[MAXW1 + 1];
+    int strip_of[NG];
     {
-        int64_t ctas4[MAXW1 + 1] = {0};
+        int64_t ctas4[NG] = {0};
         for (const Unit& u : units) {
             const SubBucket& sb = subs[u.sub];
             const int nb = (sb.n + TILE - 1) / TILE;
-            for (int rb = u.r0 / TILE; rb * TILE < u.r1; rb++) ctas4[sb.W1] += (nb - rb + 3) / 4;
+            for (int rb = u.r0 / TILE; rb * TILE < u.r1; rb++) ctas4[group_of(u, sb)] += (nb - rb + 3) / 4;
         }
         for (int w = 0; w <= MAXW1; w++) strip_of[w] = ctas4[w] > 65536 ? S1_STRIP : (ctas4[w] > 16384 ? 8 : 4);
+        for (int w = MAXW1 + 1; w < NG; w++) strip_of[w] = 8;   // thin: a CTA walks 1024 columns, four per thread
     }
     std::vector<UnitDesc> udesc(units.size());
     std::vector<int> ugroup(units.size());
@@ -1058,8 +1081,9 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
         const Unit& u = units[ui];
         const SubBucket& sb = subs[u.sub];
         const int nb = (sb.n + TILE - 1) / TILE;
-        const int strip = strip_of[sb.W1];
-        const size_t first = tasks[sb.W1].size();
+        const int grp = group_of(u, sb);
+        const int strip = strip_of[grp];
+        const size_t first = tasks[grp].size();
         for (int rb = u.r0 / TILE; rb * TILE < u.r1; rb++) {
             RowTask t;
             t.tid = 0;
@@ -1069,25 +1093,25 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
             t.rb = rb;
             t.row_lo = std::max(u.r0 - rb * TILE, 0);
             t.row_hi = std::min(u.r1 - rb * TILE, TILE);
-            t.cta0 = (int32_t)nctas[sb.W1];
-            tasks[sb.W1].push_back(t);
-            metas[sb.W1].push_back({(int32_t)ui, rb * TILE + t.row_lo, rb * TILE + t.row_hi});
-            nctas[sb.W1] += (nb - rb + strip - 1) / strip;
+            t.cta0 = (int32_t)nctas[grp];
+            tasks[grp].push_back(t);
+            metas[grp].push_back({(int32_t)ui, rb * TILE + t.row_lo, rb * TILE + t.row_hi});
+            nctas[grp] += (nb - rb + strip - 1) / strip;
         }
         UnitDesc& d = udesc[ui];
         d.sub = u.sub;
         d.t0 = (int32_t)first;
-        d.nt = (int32_t)(tasks[sb.W1].size() - first);
+        d.nt = (int32_t)(tasks[grp].size() - first);
         d.r1 = u.r1;
         d.allow = u.allow;
         d.strict = u.strict;
         d.rho_ref = u.rho_ref;
-        ugroup[ui] = sb.W1;
+        ugroup[ui] = grp;
     }
     c->task_meta.clear();
     std::vector<RowTask> all_tasks;
-    size_t goff[MAXW1 + 2] = {0};
-    for (int w = 0; w <= MAXW1; w++) {
+    size_t goff[NG + 1] = {0};
+    for (int w = 0; w < NG; w++) {
         goff[w] = all_tasks.size();
         for (size_t i = 0; i < tasks[w].size(); i++) {
             tasks[w][i].tid = (int32_t)c->task_meta.size();
@@ -1107,7 +1131,7 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     const size_t zero_bytes = report_bytes + total_tasks;   // + one skip flag per task
     c->cur_round_tasks = total_tasks;
     c->cur_strict = units.empty() ? 0.0 : units[0].strict;   // the same for every unit of a run (target_pass)
-    for (int w = 0; w <= MAXW1; w++)
+    for (int w = 0; w < NG; w++)
         if (nctas[w] >= (1ll << 31)) return fail(c, EJB_ERR_INVALID, "stage-1 launch too large (%lld CTAs)", (long long)nctas[w]);
     cudaStream_t st = c->stream;
     CK(c->d_tasks.ensure(total_tasks * sizeof(RowTask) + 64));
@@ -1134,11 +1158,11 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
                c->d_tagq.as<const unsigned long long>(), c->d_deadq.as<const unsigned long long>(), c->d_donq.as<const unsigned long long>(), c->d_flagq.as<uint32_t>());
     {
         size_t total_ctas = 0;
-        for (int w = 1; w <= MAXW1; w++) total_ctas += (size_t)nctas[w];
+        for (int w = 1; w < NG; w++) total_ctas += (size_t)nctas[w];
         CK(c->d_ctatask.ensure(total_ctas * 4 + 64));
     }
     size_t cta_off = 0;
-    for (int w = 0; w <= MAXW1; w++) {
+    for (int w = 0; w < NG; w++) {
         if (tasks[w].empty()) continue;
         const RowTask* dt = c->d_tasks.as<RowTask>() + goff[w];
         const int nt = (int)tasks[w].size();
@@ -1158,6 +1182,12 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
             case 4: launch_stage1_w<4>(c, nctas[4], dt, nt, d_ucand, strip_of[4]); break;
             case 5: launch_stage1_w<5>(c, nctas[5], dt, nt, d_ucand, strip_of[5]); break;
             case 6: launch_stage1_w<6>(c, nctas[6], dt, nt, d_ucand, strip_of[6]); break;
+            case MAXW1 + 2: launch_stage1_thin<1>(c, nctas[w], dt, d_ucand, strip_of[w]); break;
+            case MAXW1 + 3: launch_stage1_thin<2>(c, nctas[w], dt, d_ucand, strip_of[w]); break;
+            case MAXW1 + 4: launch_stage1_thin<3>(c, nctas[w], dt, d_ucand, strip_of[w]); break;
+            case MAXW1 + 5: launch_stage1_thin<4>(c, nctas[w], dt, d_ucand, strip_of[w]); break;
+            case MAXW1 + 6: launch_stage1_thin<5>(c, nctas[w], dt, d_ucand, strip_of[w]); break;
+            case MAXW1 + 7: launch_stage1_thin<6>(c, nctas[w], dt, d_ucand, strip_of[w]); break;
         }
         c->stats.stage1_launches++;
     }
@@ -1610,11 +1640,21 @@ int prepare(ejb_ctx* c, std::vector<std::pair<const char*, cudaEvent_t>>& tr) {
     CK(c->d_packsub.ensure((size_t)std::max(n_pack, 1) * 4));
     CK(cudaMemcpyAsync(c->d_packoff.p, ht + o_poffs, pack_off.size() * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->d_packsub.p, ht + o_psub, (size_t)n_pack * 4, cudaMemcpyHostToDevice, st));
-    if (n_pack > 0)
-    launch(c, k_pack_rows, nblk(pack_off.back() * 32, 256), 256, din, P, c->d_subs.as<const SubBucket>(), c->d_packoff.as<const int64_t>(),
-           c->d_packsub.as<const int32_t>(), n_pack, row_of, c->d_donor.as<const unsigned long long>(), c->d_segpl.as<const uint32_t>(), c->d_seglen.as<const int32_t>(),
-           c->d_cdr3w.as<uint32_t>(), c->d_rowstore.as<uint4>(), c->d_aux.as<int32_t>(), c->d_m_row.as<int32_t>(), c->d_m_sub.as<int32_t>(),
-           c->tags_on ? c->d_tagq.as<unsigned long long>() : (unsigned long long*)nullptr, c->tags_on ? c->d_donq.as<unsigned long long>() : (unsigned long long*)nullptr);
+    if (n_pack > 0) {
+        // fast path first (8 lanes per row); the rows it cannot take are listed and packed by the generic warp-per-row kernel
+        CK(c->d_slowrows.ensure((size_t)pack_off.back() * 4 + 4));
+        unsigned long long* const n_slow_rows = reinterpret_cast<unsigned long long*>(c->d_err.as<char>() + 64);   // zeroed with the run header
+        unsigned long long* const tq = c->tags_on ? c->d_tagq.as<unsigned long long>() : (unsigned long long*)nullptr;
+        unsigned long long* const dq = c->tags_on ? c->d_donq.as<unsigned long long>() : (unsigned long long*)nullptr;
+        launch(c, k_pack_rows8, nblk(((pack_off.back() + 3) / 4) * 32, 256), 256, din, P, c->d_subs.as<const SubBucket>(), c->d_packoff.as<const int64_t>(),
+               c->d_packsub.as<const int32_t>(), n_pack, row_of, c->d_donor.as<const unsigned long long>(), c->d_segpl.as<const uint32_t>(),
+               c->d_seglen.as<const int32_t>(), c->d_cdr3w.as<uint32_t>(), c->d_rowstore.as<uint4>(), c->d_aux.as<int32_t>(), c->d_m_row.as<int32_t>(),
+               c->d_m_sub.as<int32_t>(), tq, dq, c->d_slowrows.as<uint32_t>(), n_slow_rows);
+        launch(c, k_pack_rows, c->sm_count * 8, 256, din, P, c->d_subs.as<const SubBucket>(), c->d_packoff.as<const int64_t>(),
+               c->d_packsub.as<const int32_t>(), n_pack, row_of, c->d_donor.as<const unsigned long long>(), c->d_segpl.as<const uint32_t>(),
+               c->d_seglen.as<const int32_t>(), c->d_cdr3w.as<uint32_t>(), c->d_rowstore.as<uint4>(), c->d_aux.as<int32_t>(), c->d_m_row.as<int32_t>(),
+               c->d_m_sub.as<int32_t>(), tq, dq, c->d_slowrows.as<const uint32_t>(), (const unsigned long long*)n_slow_rows);
+    }
     if (c->tags_on)
         launch(c, k_sub_dominant, nblk(n_subs, 128), 128, c->d_subs.as<const SubBucket>(), n_subs, c->d_tagq.as<const unsigned long long>(),
                c->d_donq.as<const unsigned long long>(), c->d_subdom.as<SubDom>());
@@ -1860,8 +1900,9 @@ extern "C" int ejb_run(ejb_ctx* c) {
                     if (u.r1 < std::min(subs[u.sub].n_act, subs[u.sub].n - 1)) still.push_back(u.sub);   // the last row has no pair to its right
                 }
                 // candidate density of the last committed 16-row band predicts the rows that follow (capacity planning)
+                // (not below the unit's own average: one sparse band must not make the next ordinary band look like a jump)
                 for (const Unit& u : units)
-                    if (u.rho_last >= 0.0) rho[u.sub] = std::max(1e-3, u.rho_last);
+                    if (u.rho_last >= 0.0) rho[u.sub] = std::max({1e-3, u.rho_last, u.cand / (double)std::max(1, u.r1 - u.r0)});
             }
             std::sort(still.begin(), still.end());
             still.erase(std::unique(still.begin(), still.end()), still.end());

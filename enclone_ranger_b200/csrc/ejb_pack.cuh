@@ -277,14 +277,20 @@ __device__ __forceinline__ uint32_t even_bits(uint32_t x) {
 #endif
 // pack_off / pack_sub: the sub-buckets this context packs (all of them, or the ones its shard owns) and the prefix sums of
 // their row counts; warp w handles row w - pack_off[i] of sub-bucket pack_sub[i].
+// The generic path (ASCII contigs or CDR3s, '-', contigs over 512 nt, segments over 512 nt): one warp per row of the list that
+// k_pack_rows8 left (slow_rows == nullptr: every row, in pack order).
 __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParams P, const SubBucket* __restrict__ subs, const int64_t* __restrict__ pack_off,
                             const int32_t* __restrict__ pack_sub, int n_pack, const uint32_t* __restrict__ row_of, const unsigned long long* __restrict__ donor_mask,
                             const uint32_t* __restrict__ segpl, const int32_t* __restrict__ seglen, uint32_t* __restrict__ cdr3w, uint4* __restrict__ rowstore,
                             int32_t* __restrict__ aux, int32_t* __restrict__ rowq, int32_t* __restrict__ subq,
-                            unsigned long long* __restrict__ tagq, unsigned long long* __restrict__ donq) {
+                            unsigned long long* __restrict__ tagq, unsigned long long* __restrict__ donq, const uint32_t* __restrict__ slow_rows,
+                            const unsigned long long* __restrict__ n_slow_rows) {
     const int lane = threadIdx.x & 31;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= pack_off[n_pack]) return;
+    const int64_t n_list = slow_rows ? (int64_t)*n_slow_rows : pack_off[n_pack];
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    __shared__ __align__(16) int32_t s_aux[8][AUX_INTS];
+    for (int64_t wl = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wl < n_list; wl += nwarps) {
+    const int64_t w = slow_rows ? (int64_t)slow_rows[wl] : wl;
     int plo = 0, phi = n_pack - 1;
     while (plo < phi) {   // last i with pack_off[i] <= w
         const int mid = (plo + phi + 1) >> 1;
@@ -480,8 +486,8 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
         if (__any_sync(0xffffffffu, odd)) flags |= (m == 0) ? F_ODDBYTE_H : F_ODDBYTE_L;
         base_u4 += rec_planes(m, gapbit) * W4;
     }
-    __shared__ __align__(16) int32_t s_aux[8][AUX_INTS];
     int32_t* const a = s_aux[(threadIdx.x >> 5) & 7];
+    __syncwarp();
     if (lane == 0) {
         rowq[q] = (int32_t)k;
         subq[q] = s;
@@ -531,6 +537,196 @@ __global__ void __launch_bounds__(256, PACK_MINB) k_pack_rows(DevIn in, DevParam
     }
     __syncwarp();
     if (lane < AUX_INTS / 4) reinterpret_cast<uint4*>(aux + q * AUX_INTS)[lane] = reinterpret_cast<const uint4*>(a)[lane];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The bucketer's fast path: EIGHT lanes per row, four rows per warp.  Rows whose contigs and CDR3s arrive 2-bit packed
+// (<= 512 nt, segments <= 512 nt) need no per-base work: lane g of a row's octet builds words g and g + 8 of every plane of
+// both chains by bit de-interleaving, the CDR3 planes four positions at a time (octet-wide redux.or), and lane 0 of the octet
+// gathers the aux record.  The per-row scalar work (sub-bucket lookup, geometry, feature ranges) is shared by 8 lanes instead
+// of 32: 4x fewer warp instructions per row than the warp-per-row kernel.  Rows that do not qualify go to `slow_rows`.
+// ------------------------------------------------------------------------------------------------
+#ifndef PACK8_MINB
+#define PACK8_MINB 4
+#endif
+__global__ void __launch_bounds__(256, PACK8_MINB) k_pack_rows8(DevIn in, DevParams P, const SubBucket* __restrict__ subs, const int64_t* __restrict__ pack_off,
+                            const int32_t* __restrict__ pack_sub, int n_pack, const uint32_t* __restrict__ row_of, const unsigned long long* __restrict__ donor_mask,
+                            const uint32_t* __restrict__ segpl, const int32_t* __restrict__ seglen, uint32_t* __restrict__ cdr3w, uint4* __restrict__ rowstore,
+                            int32_t* __restrict__ aux, int32_t* __restrict__ rowq, int32_t* __restrict__ subq,
+                            unsigned long long* __restrict__ tagq, unsigned long long* __restrict__ donq, uint32_t* __restrict__ slow_rows,
+                            unsigned long long* __restrict__ n_slow_rows) {
+    const int lane = threadIdx.x & 31, g = lane & 7, oct = lane >> 3;
+    const unsigned int omask = 0xffu << (oct * 8);
+    const int64_t w = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2) + oct;
+    if (w >= pack_off[n_pack]) return;   // whole octets leave together: the collectives below name octets only
+    int plo = 0, phi = n_pack - 1;
+    while (plo < phi) {   // last i with pack_off[i] <= w
+        const int mid = (plo + phi + 1) >> 1;
+        if (pack_off[mid] <= w) plo = mid; else phi = mid - 1;
+    }
+    const int s = pack_sub[plo];
+    const SubBucket sb = subs[s];
+    const int64_t li = w - pack_off[plo];
+    const int64_t k = row_of[sb.j0 + li];
+    const int64_t q = sb.q0 + li;
+    const int64_t o0 = in.row_cdr32_off ? in.row_cdr32_off[2 * k] : -1, o1 = in.row_cdr32_off ? in.row_cdr32_off[2 * k + 1] : -1;
+    int sv[2], sj[2];
+    bool fast = sb.W4h == 4 && sb.W4l == 4 && in.row_tig2_off != nullptr && o0 >= 0 && o1 >= 0;
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        sv[m] = in.seg_canon[in.row_vs[2 * k + m]];
+        sj[m] = in.seg_canon[in.row_js[2 * k + m]];
+        if (seglen[sv[m]] > 32 * SEGPL_WORDS || seglen[sj[m]] > 32 * SEGPL_WORDS) fast = false;
+        if (fast && in.row_tig2_off[2 * k + m] < 0) fast = false;
+    }
+    if (!fast) {
+        if (g == 0) slow_rows[atomicAdd(n_slow_rows, 1ull)] = (uint32_t)w;
+        return;
+    }
+    uint32_t flags = 0;
+
+    // ---- CDR3 planes from the 2-bit words: lane g owns positions 4g .. 4g+3 of every 32-position word ----
+    {
+        const int T = sb.ch + sb.cl;
+        const int nw = (T + 31) / 32;
+        const uint32_t* w0 = in.cdr32_words + o0;
+        const uint32_t* w1 = in.cdr32_words + o1;
+        for (int wd = 0; wd < nw; wd++) {
+            uint32_t lo4 = 0, hi4 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int p = wd * 32 + g * 4 + j;
+                if (p < T) {
+                    int op = p + sb.rot;   // stored position p holds original position (p + rot) mod T
+                    if (op >= T) op -= T;
+                    const bool heavy = op < sb.ch;
+                    const int pp = heavy ? op : op - sb.ch;
+                    const uint32_t c2 = ((heavy ? w0 : w1)[pp >> 4] >> (2 * (pp & 15))) & 3u;   // A,C,G,T = 0..3
+                    const uint32_t code = c2 ^ (c2 >> 1);                                        // -> internal A,C,T,G = 0,1,2,3
+                    lo4 |= (code & 1u) << j;
+                    hi4 |= (code >> 1) << j;
+                }
+            }
+            const uint32_t lo = __reduce_or_sync(omask, lo4 << (4 * g)), hi = __reduce_or_sync(omask, hi4 << (4 * g));
+            if (sb.W1 > 0 && g == 0) {
+                cdr3w[sb.s1_off + (int64_t)wd * sb.npad + li] = lo;
+                cdr3w[sb.s1_off + (int64_t)(sb.W1 + wd) * sb.npad + li] = hi;
+            }
+        }
+    }
+
+    // ---- contig planes and the difference bitmap against the row's own V / J reference: words g and g + 8 of both chains ----
+    uint32_t* rec32 = reinterpret_cast<uint32_t*>(rowstore + sb.rs_off + li * (int64_t)sb.rec_u4);
+    int t = 0;
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        const int L = m ? sb.Ll : sb.Lh;
+        const int gapbit = (sb.gap >> m) & 1;
+        const RefGeom G = ref_geom(seglen, sv[m], sj[m], L, P.ref_v_trim, P.ref_j_trim);
+        uint32_t fl = 0;
+        if (G.vr < 0 || G.jr < 0 || G.jr > L) fl |= F_PANIC;
+        if (G.vr > L || G.vr + G.jr > L) fl |= F_SLOWGEOM;
+        flags |= fl;
+        // contig planes from the packed words (A,C,G,T = 0..3 -> internal code lo' = lo ^ hi, hi' = hi)
+        const uint32_t* tw = in.tig2_words + in.row_tig2_off[2 * k + m];
+        const int nw16 = (L + 15) >> 4;
+        uint32_t* const rbase = rec32 + (m ? rec_planes(0, sb.gap & 1) * sb.W4h * 4 : 0);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int wi = g + 8 * h;
+            const uint32_t x0 = (2 * wi < nw16) ? tw[2 * wi] : 0u, x1 = (2 * wi + 1 < nw16) ? tw[2 * wi + 1] : 0u;
+            const uint32_t inl = mask_lt32(L - 32 * wi);
+            uint32_t lo = even_bits(x0) | (even_bits(x1) << 16), hi = even_bits(x0 >> 1) | (even_bits(x1 >> 1) << 16);
+            lo = (lo ^ hi) & inl;
+            hi &= inl;
+            uint32_t rlo, rhi, cm;
+            ref_word(segpl, G, wi, rlo, rhi, cm);
+            const uint32_t dm = fl ? 0u : (cm & ((lo ^ rlo) | (hi ^ rhi)));
+            uint32_t* r = rbase + wi;
+            const int st = 16;   // 4 * W4
+            r[PL_TLO * st] = lo;
+            r[PL_THI * st] = hi;
+            r[PL_D * st] = dm;
+            if (gapbit) r[PL_GAP * st] = 0u;
+            t += __popc(dm);
+        }
+    }
+    const int tot = (int)__reduce_add_sync(omask, (unsigned int)t);
+
+    // ---- aux record: lane 0 of the octet gathers, the octet stores ----
+    __shared__ __align__(16) int32_t s_aux[8][4][AUX_INTS];
+    int32_t* const a = s_aux[(threadIdx.x >> 5) & 7][oct];
+    if (g == 0) {
+        const int ex = in.row_exact[k];
+        const int64_t c0 = in.ex_chain_off[ex], nch = in.ex_chain_off[ex + 1] - c0;
+        const int ch = (int)(c0 + in.row_exact_col[2 * k]), cl = (int)(c0 + in.row_exact_col[2 * k + 1]);
+        // FWR1 / CDR1 / CDR2 ranges of chain 0 (only meaningful when that chain is the left chain; stage 2 checks)
+        int rF0 = 0, rF1 = 0, rC10 = 0, rC11 = 0, rC20 = 0, rC21 = 0;
+        const int fr1 = in.ch_fr1[ch], cdr1 = in.ch_cdr1[ch], fr2 = in.ch_fr2[ch], cdr2 = in.ch_cdr2[ch], fr3 = in.ch_fr3[ch];
+        {
+            const int L = sb.Lh;
+            const bool has_f = cdr1 != -1;
+            const bool has_c1 = cdr1 != -1 && fr2 != -1 && cdr1 <= fr2;
+            const bool has_c2 = cdr2 != -1 && fr3 != -1 && cdr2 <= fr3;
+            const bool okf = !has_f || (fr1 >= 0 && fr1 <= cdr1 && cdr1 <= L);
+            const bool okc1 = !has_c1 || (cdr1 >= 0 && fr2 <= L);
+            const bool okc2 = !has_c2 || (cdr2 >= 0 && fr3 <= L);
+            bool disj = true;
+            if (has_f && has_c2 && !(cdr1 <= cdr2 || fr3 <= fr1)) disj = false;
+            if (has_c1 && has_c2 && !(fr2 <= cdr2 || fr3 <= cdr1)) disj = false;
+            if (okf && okc1 && okc2 && disj && L <= 128 * MAXW4) {
+                flags |= B_REG_OK;
+                if (has_f) { rF0 = fr1; rF1 = cdr1; }
+                if (has_c1) { rC10 = cdr1; rC11 = fr2; }
+                if (has_c2) { rC20 = cdr2; rC21 = fr3; }
+            }
+        }
+        rowq[q] = (int32_t)k;
+        subq[q] = s;
+        if (nch >= 2 && nch <= 3) flags |= B_NCH_OK;
+        if (nch == 2) flags |= B_NCH2;
+        if (nch >= 2 && in.ch_left[c0] != in.ch_left[c0 + 1]) flags |= B_JUN_LEFT;
+        if (in.ch_left[ch]) flags |= B_LEFT_H;
+        if (in.ch_left[cl]) flags |= B_LEFT_L;
+        if (in.ch_amino_off[ch] == -1) flags |= B_AMINO_TIG_H;
+        const int64_t x0 = in.ex_cell_off[ex], ncells = in.ex_cell_off[ex + 1] - x0;
+        const unsigned long long dmask = donor_mask[ex];
+        a[AX_FLAGS] = (int32_t)flags;
+        a[AX_VSH] = sv[0];
+        a[AX_VSL] = sv[1];
+        a[AX_JSH] = sj[0];
+        a[AX_JSL] = sj[1];
+        a[AX_TOT] = tot;
+        a[AX_EXACT] = ex;
+        a[AX_NCELLS] = (int32_t)ncells;
+        a[AX_DONLO] = (int32_t)(uint32_t)(dmask & 0xffffffffull);
+        a[AX_DONHI] = (int32_t)(uint32_t)(dmask >> 32);
+        a[AX_CREFH] = in.ch_c_ref[ch];
+        a[AX_CREFL] = in.ch_c_ref[cl];
+        a[AX_HCOMP] = in.ch_hcomp[ch];
+        a[AX_VREFH] = in.ch_v_ref[ch];
+        a[AX_VREFL] = in.ch_v_ref[cl];
+        a[AX_BC0] = ncells > 0 ? (int32_t)in.cell_barcode[x0] : -1;
+        a[AX_VNAMEH] = in.ref_name_id[in.ch_v_ref[ch]];
+        a[AX_VNAMEL] = in.ref_name_id[in.ch_v_ref[cl]];
+        a[AX_FR1] = fr1;
+        a[AX_CDR1] = cdr1;
+        a[AX_FR2] = fr2;
+        a[AX_CDR2] = cdr2;
+        a[AX_FR3] = fr3;
+        a[AX_CHH] = ch;
+        a[AX_CHL] = cl;
+        a[AX_RGN0] = rF0 | (rF1 << 16);
+        a[AX_RGN1] = rC10 | (rC11 << 16);
+        a[AX_RGN2] = rC20 | (rC21 << 16);
+        if (tagq) {
+            tagq[q] = (flags & F_SLOWMASK) ? TAG_SLOW : make_ref_tag(sv[0], sv[1], sj[0], sj[1]);
+            donq[q] = P.mix_donors ? 0ull : dmask;   // join_one.rs:301-323 only rejects when donors are not mixed
+        }
+    }
+    __syncwarp(omask);
+    if (g < AUX_INTS / 4) reinterpret_cast<uint4*>(aux + q * AUX_INTS)[g] = reinterpret_cast<const uint4*>(a)[g];
 }
 
 }  // namespace ejb

@@ -396,4 +396,152 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stage 1 for THIN tasks: at most 16 rows of a row block (the first units of every sub-bucket: 2 rows, then 12) against
+// every column to their right.  k_stage1 stages 128-column tiles for 128 rows, so a thin task pays the whole tile pipeline
+// for 1/64 .. 1/8 of a tile of pairs; here the roles are swapped: the rows (planes, labels, flags, tags) sit in shared memory,
+// a THREAD owns a column (coalesced loads of the plane-major CDR3 words, labels and flags) and walks the rows.  Same
+// predicates, in the same order, as k_stage1: first word, class labels, row flags, remaining words, the exact 64-bit tag tests.
+// One CTA = `strip` column blocks of the task (the CTA -> task map of k_expand_tasks is shared with k_stage1).
+// ------------------------------------------------------------------------------------------------
+constexpr int S1_THIN_ROWS = 16;
+template <int W1, bool TAGS>
+__global__ void __launch_bounds__(S1_THREADS) k_stage1_thin(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, const uint32_t* __restrict__ cdr3w,
+                                                            const int32_t* __restrict__ labq, uint2* __restrict__ cand, unsigned long long cand_cap,
+                                                            Counters* __restrict__ ctr, unsigned long long* __restrict__ unit_cand,
+                                                            const unsigned long long* __restrict__ tagq, const unsigned long long* __restrict__ deadq,
+                                                            const unsigned long long* __restrict__ donq, const uint32_t* __restrict__ flagq, int strip,
+                                                            const int32_t* __restrict__ cta_task) {
+    __shared__ uint32_t s_rl[S1_THIN_ROWS][W1], s_rh[S1_THIN_ROWS][W1];
+    __shared__ int s_lab[S1_THIN_ROWS];
+    __shared__ uint32_t s_flag[S1_THIN_ROWS];
+    __shared__ unsigned long long s_tag[S1_THIN_ROWS], s_dead[S1_THIN_ROWS], s_don[S1_THIN_ROWS];
+    __shared__ __align__(8) uint2 s_q[S1_WARPS][S1_QCAP];
+    const int64_t cta = blockIdx.x;
+    const RowTask t = tasks[cta_task[cta]];
+    const SubBucket sb = subs[t.sub];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int R0 = t.rb * TILE + t.row_lo;                                  // first row (sub-bucket local)
+    const int nr = min(min(t.row_hi, sb.n - t.rb * TILE) - t.row_lo, S1_THIN_ROWS);   // rows of the task
+    if (nr <= 0) return;
+    const uint32_t* base = cdr3w + sb.s1_off;
+    if (tid < nr) {
+        const int r = R0 + tid;
+#pragma unroll
+        for (int w = 0; w < W1; w++) {
+            s_rl[tid][w] = base[(int64_t)w * sb.npad + r];
+            s_rh[tid][w] = base[(int64_t)(W1 + w) * sb.npad + r];
+        }
+        s_lab[tid] = labq[sb.q0 + r];
+        if (TAGS) {
+            s_flag[tid] = flagq[sb.q0 + r];
+            s_tag[tid] = tagq[sb.q0 + r];
+            s_dead[tid] = deadq[sb.q0 + r];
+            s_don[tid] = donq[sb.q0 + r];
+        }
+    }
+    __syncthreads();
+    const int maxcd = sb.maxcd;
+    const int c_beg = max((t.rb + (int)(cta - t.cta0) * strip) * TILE, R0 + 1);
+    const int c_end = min(sb.n, (t.rb + (int)(cta - t.cta0) * strip + strip) * TILE);
+    uint2* const myq = s_q[warp];
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    unsigned int wq = 0;
+    unsigned long long w_band[2] = {0, 0};   // warp-uniform: candidates per 16-row band (a thin task touches at most two)
+    const int band0 = t.row_lo >> 4;
+    unsigned int n_first = 0, n_full = 0, n_flag = 0, donor_kills = 0, tag_kills = 0;
+    auto flush = [&]() {   // all lanes
+        __syncwarp();
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(&ctr->n_cand, (unsigned long long)wq);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        for (unsigned int h = lane; h < wq; h += 32) {
+            const unsigned long long o = b + h;
+            if (o < cand_cap) cand[o] = myq[h]; else ctr->overflow = 1ull;
+        }
+        wq = 0;
+        __syncwarp();
+    };
+    // whole warps walk the column range so that the ballots below are warp-wide
+    for (int c0 = c_beg - (c_beg & 31) + warp * 32; c0 < c_end; c0 += S1_THREADS) {
+        const int c = c0 + lane;
+        const bool cv = c >= c_beg && c < c_end;
+        uint32_t cl[W1], chh[W1];
+        int clab = 0;
+        uint32_t fc = 0;
+        if (cv) {
+#pragma unroll
+            for (int w = 0; w < W1; w++) {
+                cl[w] = base[(int64_t)w * sb.npad + c];
+                chh[w] = base[(int64_t)(W1 + w) * sb.npad + c];
+            }
+            clab = labq[sb.q0 + c];
+            if (TAGS) fc = flagq[sb.q0 + c];
+        } else {
+#pragma unroll
+            for (int w = 0; w < W1; w++) cl[w] = chh[w] = 0u;
+        }
+        for (int i = 0; i < nr; i++) {
+            const int r = R0 + i;
+            bool hit = cv && c > r;
+            if (hit) n_first++;
+            bool fk = false;
+            if (TAGS) {
+                const uint32_t fr = s_flag[i];
+                fk = ((fc & RF_HAS_DOM) && (fr & RF_DEAD_VS_DOM)) || ((fc & RF_DEAD_VS_DOM) && (fr & RF_HAS_DOM)) || ((fc & RF_DOM_DON) && (fr & RF_FOREIGN_DON)) ||
+                     ((fc & RF_FOREIGN_DON) && (fr & RF_DOM_DON));
+                if (hit && fk) n_flag++;
+            }
+            const int p0 = __popc((s_rl[i][0] ^ cl[0]) | (s_rh[i][0] ^ chh[0]));
+            hit = hit && p0 <= maxcd && s_lab[i] != clab && !fk;
+            if (!__any_sync(0xffffffffu, hit)) continue;
+            if (W1 > 1 && hit) {
+                n_full++;
+                hit = p0 + cdr3_rest<W1>(s_rl[i], s_rh[i], cl, chh) <= maxcd;
+            }
+            if (TAGS && hit) {   // the exact 64-bit tests behind the flags
+                const unsigned long long dr = s_don[i], dc = donq[sb.q0 + c];
+                const bool donors = dr != 0 && dc != 0 && dr != dc;
+                if (donors || s_dead[i] == tagq[sb.q0 + c] || deadq[sb.q0 + c] == s_tag[i]) {
+                    hit = false;
+                    tag_kills++;
+                    donor_kills += donors;
+                }
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                if (hit) myq[wq + __popc(m & lt_mask)] = make_uint2((uint32_t)(sb.q0 + r), (uint32_t)(sb.q0 + c));
+                wq += __popc(m);
+                w_band[((t.row_lo + i) >> 4) - band0] += __popc(m);
+                if (wq > S1_QCAP - 32) flush();
+            }
+        }
+    }
+    if (wq) flush();
+    if (lane == 0) {
+        if (w_band[0]) atomicAdd(&unit_cand[(size_t)t.tid * S1_WARPS + band0], w_band[0]);
+        if (w_band[1]) atomicAdd(&unit_cand[(size_t)t.tid * S1_WARPS + band0 + 1], w_band[1]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_first += __shfl_xor_sync(0xffffffffu, n_first, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+        if (TAGS) {
+            n_flag += __shfl_xor_sync(0xffffffffu, n_flag, o);
+            donor_kills += __shfl_xor_sync(0xffffffffu, donor_kills, o);
+            tag_kills += __shfl_xor_sync(0xffffffffu, tag_kills, o);
+        }
+    }
+    if (lane == 0) {
+        if (n_first) {
+            atomicAdd(&ctr->s1_first, (unsigned long long)n_first);
+            atomicAdd(&ctr->pairs_eval, (unsigned long long)n_first);   // every pair of the task's columns is looked at
+        }
+        if (n_full) atomicAdd(&ctr->s1_full, (unsigned long long)n_full);
+        if (TAGS && n_flag) atomicAdd(&ctr->n_s1_flag, (unsigned long long)n_flag);
+        if (TAGS && donor_kills) atomicAdd(&ctr->n_s1_donor, (unsigned long long)donor_kills);
+        if (TAGS && tag_kills) atomicAdd(&ctr->n_s1_kill, (unsigned long long)tag_kills);
+    }
+}
+
 }  // namespace ejb
