@@ -124,7 +124,8 @@ struct Options {
     int s1_mode = S1_RUNI | S1_TAGS;
     int no_tags = 0;
     int trace = 0;
-    int thin = 1;              // stage 1: units of at most 16 rows go to k_stage1_thin (0: always k_stage1, A/B and parity knob)
+    int thin = 16;             // stage 1: units of at most this many rows go to k_stage1_thin (0: always k_stage1; measured: 2- and 12-row
+                               // units 3-4x faster than the tile kernel, 72-row units 25 % slower)
     int quot_table = 1;        // p1: quotients from the constant table (0: three-quotient divisions, A/B and parity knob)
     int sr_host = 0;                         // build the Stirling table on the host (A/B against the device kernel)
     long long strict_div = 2048;             // strict allowance of a unit = cand_cap / strict_div candidates
@@ -821,7 +822,7 @@ int ejb_set_option(ejb_ctx* c, const char* name, long long value) {
         else if (n == "no_tags") x->opt.no_tags = value != 0;
         else if (n == "trace") x->opt.trace = value != 0;
         else if (n == "quot_table") x->opt.quot_table = value != 0;
-        else if (n == "thin") x->opt.thin = value != 0;
+        else if (n == "thin") x->opt.thin = (int)std::max(0ll, std::min(128ll, value));
         else return false;
         return true;
     };
@@ -1054,10 +1055,10 @@ int run_round(ejb_ctx* c, std::vector<Unit>& units, std::vector<RoundTimes>& tim
     const SubVec& subs = c->subs;
     // ---- tasks grouped by W1; task ids number them in launch order ----
     // groups 0 .. MAXW1: k_stage1 per CDR3 width (0: no filter); groups MAXW1+1+W1: the THIN units of that width (at most
-    // S1_THIN_ROWS rows: the first rounds of every sub-bucket), scored by k_stage1_thin
+    // opt.thin rows: the first rounds of every sub-bucket), scored by k_stage1_thin
     constexpr int NG = 2 * (MAXW1 + 1);
     auto group_of = [&](const Unit& u, const SubBucket& sb) {
-        return (c->opt.thin && sb.W1 >= 1 && u.r1 - u.r0 <= S1_THIN_ROWS) ? MAXW1 + 1 + sb.W1 : sb.W1;
+        return (sb.W1 >= 1 && u.r1 - u.r0 <= std::min(c->opt.thin, S1_THIN_ROWS)) ? MAXW1 + 1 + sb.W1 : sb.W1;
     };
     std::vector<RowTask> tasks[NG];
     std::vector<ejb_ctx::TaskMeta> metas[NG];
@@ -1356,7 +1357,27 @@ void shard_assign(SubBucket* subs, int n_subs, int rank, int world, double split
         }
     };
     for (const Item& it : big) place(it);
-    for (const Item& it : small) place(it);
+    // small items (never split): the least loaded rank keeps receiving them until it is no longer the least loaded
+    int best = 0;
+    double next_load = 0.0;
+    auto pick = [&]() {
+        best = 0;
+        for (int r = 1; r < world; r++)
+            if (load[(size_t)r] < load[(size_t)best]) best = r;
+        next_load = 1e300;
+        for (int r = 0; r < world; r++)
+            if (r != best) next_load = std::min(next_load, load[(size_t)r]);
+    };
+    pick();
+    for (const Item& it : small) {
+        if (load[(size_t)best] > next_load) pick();
+        load[(size_t)best] += it.cost;
+        if (best == rank) {
+            subs[it.sub].r_beg = it.lo;
+            subs[it.sub].n_act = it.hi;
+            subs[it.sub].owner = rank;
+        }
+    }
 }
 
 // ---- prepare: bucket scan, sub-bucket table, bucketer.  ONE read-back (the run header + the sub-bucket table). ----

@@ -102,13 +102,24 @@ __device__ __forceinline__ dd_t p1_term(const dd_t* __restrict__ sr, const doubl
     dd_t z = sr[(size_t)k * (k + 1) / 2 + u];
     const dd_t f = dd_div(dd_make((double)u), dd_make((double)n));
     for (int i = 0; i < k; i++) z = dd_mul(z, f);
+    // the quotients do not depend on z: the next four are loaded while the chain consumes the current four
+    constexpr int QB = 4;
+    dd_t q[QB], qn[QB];
     int v = 1;
-    for (; v + 3 <= u; v += 4) {   // the quotients do not depend on z: four loads in flight per step of the chain
-        const dd_t q0 = p1_quot(qt, n, u, v), q1 = p1_quot(qt, n, u, v + 1), q2 = p1_quot(qt, n, u, v + 2), q3 = p1_quot(qt, n, u, v + 3);
-        z = dd_mul(z, q0);
-        z = dd_mul(z, q1);
-        z = dd_mul(z, q2);
-        z = dd_mul(z, q3);
+    if (u >= QB) {
+#pragma unroll
+        for (int i = 0; i < QB; i++) q[i] = p1_quot(qt, n, u, v + i);
+        for (; v + 2 * QB - 1 <= u; v += QB) {
+#pragma unroll
+            for (int i = 0; i < QB; i++) qn[i] = p1_quot(qt, n, u, v + QB + i);
+#pragma unroll
+            for (int i = 0; i < QB; i++) z = dd_mul(z, q[i]);
+#pragma unroll
+            for (int i = 0; i < QB; i++) q[i] = qn[i];
+        }
+#pragma unroll
+        for (int i = 0; i < QB; i++) z = dd_mul(z, q[i]);
+        v += QB;
     }
     for (; v <= u; v++) z = dd_mul(z, p1_quot(qt, n, u, v));
     return z;
@@ -222,7 +233,7 @@ __global__ void k_p1_expand(P1Groups G, Counters* ctr) {
         if (lane == 0) G.ghave[h] = want;
     }
 }
-__global__ void __launch_bounds__(256) k_p1_terms(P1Groups G, const dd_t* __restrict__ sr, const double2* __restrict__ qt, Counters* ctr) {
+__global__ void __launch_bounds__(256, 3) k_p1_terms(P1Groups G, const dd_t* __restrict__ sr, const double2* __restrict__ qt, Counters* ctr) {
     const unsigned long long n = min(ctr->p1_desc, G.desc_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&ctr->p1_terms, n);
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {

@@ -397,14 +397,14 @@ __global__ void __launch_bounds__(S1_THREADS, (W1 <= 2) ? S1_MINB2 : ((W1 <= 3) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage 1 for THIN tasks: at most 16 rows of a row block (the first units of every sub-bucket: 2 rows, then 12) against
+// Stage 1 for THIN units: at most `thin_rows` rows (the first units of every sub-bucket: 2 rows, then 12, then 72) against
 // every column to their right.  k_stage1 stages 128-column tiles for 128 rows, so a thin task pays the whole tile pipeline
-// for 1/64 .. 1/8 of a tile of pairs; here the roles are swapped: the rows (planes, labels, flags, tags) sit in shared memory,
+// for a fraction of a tile of pairs; here the roles are swapped: the rows (planes, labels, flags, tags) sit in shared memory,
 // a THREAD owns a column (coalesced loads of the plane-major CDR3 words, labels and flags) and walks the rows.  Same
 // predicates, in the same order, as k_stage1: first word, class labels, row flags, remaining words, the exact 64-bit tag tests.
 // One CTA = `strip` column blocks of the task (the CTA -> task map of k_expand_tasks is shared with k_stage1).
 // ------------------------------------------------------------------------------------------------
-constexpr int S1_THIN_ROWS = 16;
+constexpr int S1_THIN_ROWS = TILE;   // a thin task never exceeds its row block
 template <int W1, bool TAGS>
 __global__ void __launch_bounds__(S1_THREADS) k_stage1_thin(const SubBucket* __restrict__ subs, const RowTask* __restrict__ tasks, const uint32_t* __restrict__ cdr3w,
                                                             const int32_t* __restrict__ labq, uint2* __restrict__ cand, unsigned long long cand_cap,
@@ -447,8 +447,9 @@ __global__ void __launch_bounds__(S1_THREADS) k_stage1_thin(const SubBucket* __r
     uint2* const myq = s_q[warp];
     const unsigned int lt_mask = (1u << lane) - 1u;
     unsigned int wq = 0;
-    unsigned long long w_band[2] = {0, 0};   // warp-uniform: candidates per 16-row band (a thin task touches at most two)
-    const int band0 = t.row_lo >> 4;
+    __shared__ unsigned int s_band[S1_WARPS];   // candidates per 16-row band of the row block
+    if (tid < S1_WARPS) s_band[tid] = 0u;
+    __syncthreads();
     unsigned int n_first = 0, n_full = 0, n_flag = 0, donor_kills = 0, tag_kills = 0;
     auto flush = [&]() {   // all lanes
         __syncwarp();
@@ -512,16 +513,14 @@ __global__ void __launch_bounds__(S1_THREADS) k_stage1_thin(const SubBucket* __r
             if (m) {
                 if (hit) myq[wq + __popc(m & lt_mask)] = make_uint2((uint32_t)(sb.q0 + r), (uint32_t)(sb.q0 + c));
                 wq += __popc(m);
-                w_band[((t.row_lo + i) >> 4) - band0] += __popc(m);
+                if (lane == 0) atomicAdd(&s_band[(t.row_lo + i) >> 4], (unsigned int)__popc(m));
                 if (wq > S1_QCAP - 32) flush();
             }
         }
     }
     if (wq) flush();
-    if (lane == 0) {
-        if (w_band[0]) atomicAdd(&unit_cand[(size_t)t.tid * S1_WARPS + band0], w_band[0]);
-        if (w_band[1]) atomicAdd(&unit_cand[(size_t)t.tid * S1_WARPS + band0 + 1], w_band[1]);
-    }
+    __syncthreads();
+    if (tid < S1_WARPS && s_band[tid]) atomicAdd(&unit_cand[(size_t)t.tid * S1_WARPS + tid], (unsigned long long)s_band[tid]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_first += __shfl_xor_sync(0xffffffffu, n_first, o);

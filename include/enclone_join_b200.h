@@ -277,8 +277,8 @@ typedef struct ejb_ctx ejb_ctx;
  * collective on the data path), gathers the per-device forests and merges them; the caller sees one result.      */
 int ejb_create(ejb_ctx** out, const int* device_ids, int n_devices);
 /* Developer / test knobs (none is needed in production).  Names: "first_unit", "growth" (unit schedule), "s1_mode"
- * (bit 0 uniform-label vote, bit 1 tags), "no_tags", "trace", "p1_keep" (1: keep the memo of p1(n, k, d) values
- * across the joins of this context; default 0 — every join evaluates what it needs).  The EJB_* environment variables of the same meaning are
+ * (bit 0 uniform-label vote, bit 1 tags), "no_tags", "trace", "thin" (largest unit, in rows, scored by the thread-per-column kernel; 0: always the tile kernel),
+ * "quot_table" (0: p1 with three-quotient divisions instead of the constant quotient table).  The EJB_* environment variables of the same meaning are
  * read ONCE, in ejb_create; this call overrides them for the following joins.  Unknown name: EJB_ERR_INVALID.     */
 int ejb_set_option(ejb_ctx* ctx, const char* name, long long value);
 /* Milliseconds ejb_create spent building + uploading the Stirling ratio table (device build: start.rs:50-99).   */

@@ -289,6 +289,23 @@ def test_reference_set_tags_do_not_change_the_result(gpu_ctx):
     assert off.stats["stage1_ref_kills"] == 0 and off.stats["stage1_flag_skips"] == 0
 
 
+@pytest.mark.parametrize("opt,value", [("thin", 0), ("thin", 96), ("thin", 128), ("quot_table", 0)])
+def test_kernel_variants_do_not_change_the_result(gpu_ctx, opt, value):
+    """The thin-unit stage-1 kernel (thread per column) against the tile kernel, and p1 from the constant quotient table
+    against the three-quotient divisions: every variant gives the oracle's result, bit for bit."""
+    rep = E.generate(1, n_cells=60000, seed=9)
+    p = E.default_params(True)
+    want = pyoracle.run(p, rep.c_ptr, threads=0)
+    default = {"thin": 16, "quot_table": 1}[opt]
+    gpu_ctx.set_option(opt, value)
+    try:
+        got = gpu_ctx.join(p, rep)
+    finally:
+        gpu_ctx.set_option(opt, default)
+    assert_same_result(got, want, f"{opt}={value}")
+    assert_same_result(gpu_ctx.join(p, rep.to_join_input().to_packed().to_packed_cdr3()), want, "defaults, packed input")
+
+
 def test_reference_set_tags_at_scale(gpu_ctx):
     rep = E.generate(1, n_cells=300000, seed=4)
     p = E.default_params(True)
