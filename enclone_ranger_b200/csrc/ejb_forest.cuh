@@ -215,17 +215,29 @@ __global__ void k_truncate(const UnitDesc* __restrict__ units, int n_units, cons
     double carry_cand = 0.0, carry_aj = 0.0, cand_out = 0.0, rho_last = -1.0;
     bool jumped = false;
     int r1 = u.r1, cut = 0;
-    for (int base = 0; base < n_bands && !cut; base += 32) {
-        const int bi = base + lane;
-        double cnt = 0.0;
-        int tr0 = 0, tr1 = 0;   // rows of this band that belong to the unit (empty when the band lies outside [row_lo, row_hi))
+    constexpr int PF = 4;   // chunks of 32 bands whose loads are in flight together (a 33k-row unit has 2100 bands: the walk is
+                            // bound by the latency of these dependent loads, 92 us before the batching)
+    for (int base0 = 0; base0 < n_bands && !cut; base0 += 32 * PF) {
+      double cnt_pf[PF];
+      int tr0_pf[PF], tr1_pf[PF];
+#pragma unroll
+      for (int j = 0; j < PF; j++) {
+        const int bi = base0 + 32 * j + lane;
+        cnt_pf[j] = 0.0;
+        tr0_pf[j] = tr1_pf[j] = 0;   // rows of this band that belong to the unit (empty when the band lies outside [row_lo, row_hi))
         if (bi < n_bands) {
             const RowTask rt = tasks[u.t0 + bi / S1_WARPS];
             const int b = bi % S1_WARPS;
-            tr0 = rt.rb * TILE + max(rt.row_lo, 16 * b);
-            tr1 = rt.rb * TILE + min(rt.row_hi, 16 * b + 16);
-            if (tr1 > tr0) cnt = (double)unit_cand[(size_t)rt.tid * S1_WARPS + b];
+            tr0_pf[j] = rt.rb * TILE + max(rt.row_lo, 16 * b);
+            tr1_pf[j] = rt.rb * TILE + min(rt.row_hi, 16 * b + 16);
+            if (tr1_pf[j] > tr0_pf[j]) cnt_pf[j] = (double)unit_cand[(size_t)rt.tid * S1_WARPS + b];
         }
+      }
+#pragma unroll
+      for (int j = 0; j < PF; j++) {
+        if (cut || base0 + 32 * j >= n_bands) break;
+        const double cnt = cnt_pf[j];
+        const int tr0 = tr0_pf[j], tr1 = tr1_pf[j];
         const bool valid = tr1 > tr0;
         const bool dj = valid && (u.rho_ref < 0.0 || cnt / (double)(tr1 - tr0) > 8.0 * u.rho_ref + 16.0);
         const unsigned int jm = __ballot_sync(0xffffffffu, dj);
@@ -258,6 +270,7 @@ __global__ void k_truncate(const UnitDesc* __restrict__ units, int n_units, cons
                 rho_last = __shfl_sync(0xffffffffu, cnt / (double)max(1, tr1 - tr0), L);
             }
         }
+      }
     }
     if (lane == 0) {
         qcut[u.sub] = cut ? (int32_t)(subs[u.sub].q0 + r1) : 0x7fffffff;
