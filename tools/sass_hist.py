@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "enclone_ranger_b200", "libenclone_join_b200.so")
-HOT = re.compile(r"k_stage1|k_stage2a|k_stage2b|k_pack_rows|k_forest_round|k_truncate|k_p1\b|k_sr_table")
+HOT = re.compile(r"k_stage1|k_stage2a|k_stage2b|k_pack_rows|k_forest_round|k_truncate|k_p1_|k_quot_table|k_sr_table")
 WATCH = ["POPC", "LOP3", "UBLKCP", "SYNCS", "MATCH", "REDUX", "VOTE", "SHFL", "BAR", "LDL", "STL", "ATOM", "ATOMS", "RED",
          "LDG", "STG", "LDS", "STS", "DADD", "DMUL", "DFMA", "CCTL"]
 
