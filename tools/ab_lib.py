@@ -1,4 +1,4 @@
-"""A/B of differently built join libraries (EJB_LIB) on BASELINE configs[1] (dev tool).
+"""A/B of differently built join libraries (EJB_LIB) on BASELINE configs[1] (dev tool; EJB_AB_CONFIG=4 for the 10M-cell one).
   python tools/ab_lib.py build/lib_a.so build/lib_b.so ...      ("default" = the in-tree library)"""
 import json
 import os
@@ -28,8 +28,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "--worker":
 
 import numpy as np
 import enclone_ranger_b200 as E
-rep = E.generate(1)
-inp = rep.to_join_input().to_packed()
+rep = E.generate(int(os.environ.get("EJB_AB_CONFIG", "1")))
+inp = rep.to_join_input().to_packed().to_packed_cdr3()
 rep.close()
 np.savez(PATH, **inp.a)
 for lib in sys.argv[1:] or ["default"]:

@@ -36,7 +36,8 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:16]:
     print(f"| `{k}` | {a[0]} | {a[1]:.1f} | {100 * a[1] / total:.1f}% | {a[2]:.1f} |")
 shutil.copy(launch_csv, f"profiles/launches_{tag}.csv")
 
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# a report exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv > x_raw.csv`: gpurun only brings back 64 MiB) or the report itself
+raw = open(rep, errors="replace").read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 hh = rr[0]
 ix = {n: i for i, n in enumerate(hh)}
