@@ -170,7 +170,19 @@ def run_reference_arm(args, rank):
     rep = E.generate(MAIN_CONFIG, n_cells=args.cells)
     inp = rep.to_join_input()
     rep.close()
-    sample, desc = cpu_sample(inp, row_fraction=0.02)
+    # The sample is sized so that the W + K passes together take about a minute: start from the fraction that would do so at
+    # the rate measured in round 2 (2 % of configs[4]'s rows = 40 s per pass on 16 threads), time one calibration pass, and
+    # rescale (at most three times; the sample is always a prefix of the same seeded shuffle, no bucket excluded).
+    n_pass = max(1, args.warmup + args.steps)
+    budget_s = 75.0
+    frac = 0.02 * min(1.0, budget_s / (40.0 * n_pass))
+    sample, desc = cpu_sample(inp, row_fraction=frac)
+    for _ in range(3):
+        t_cal = pyoracle.run(p, sample.c_ptr(), threads=0)["seconds_join"]
+        if t_cal * n_pass <= 1.6 * budget_s or frac <= 2e-4:
+            break
+        frac *= max(0.05, min(0.7, budget_s / (t_cal * n_pass)))
+        sample, desc = cpu_sample(inp, row_fraction=frac)
     times, pairs, threads = [], 0, 0
     for i in range(args.warmup + args.steps):
         r = pyoracle.run(p, sample.c_ptr(), threads=0)
