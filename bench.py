@@ -71,27 +71,32 @@ def algorithmic_popc(inp):
     return float((p1 * pairs).sum() / tot), float((p2 * pairs).sum() / tot), float(pairs.sum()), float(row_bytes.sum())
 
 
-def cpu_sample(inp, row_fraction, seed=0):
-    """A bounded sample of the workload for the per-step reference arm: whole lens-buckets in a seeded shuffle — NO bucket is
-    excluded for its size — until they hold `row_fraction` of the rows."""
+def cpu_sample(inp, row_fraction, seed=0, cap_rows=None):
+    """A bounded sample of the workload for the per-step reference arm: lens-buckets in a seeded shuffle — NO bucket is excluded
+    for its size — until they hold `row_fraction` of the rows.  With `cap_rows` a bucket contributes at most its first
+    `cap_rows` rows (the reference runs one thread per bucket, so one 30k-row bucket alone is 18 s per pass: a 25-pass arm can
+    only afford a prefix of it; the prefix keeps the bucket's clone structure, and `sample_bias` measures what the rule costs)."""
     bucket, lens, nch = bucket_table(inp)
     nb = int(bucket[-1]) + 1
     sizes = np.bincount(bucket, minlength=nb).astype(np.int64)
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])   # rows of a lens-bucket are contiguous (info is sorted by lens)
     two = np.zeros(nb, dtype=bool)
     two[bucket[nch == 2]] = True
     target = row_fraction * inp.n_rows
-    chosen, acc = [], 0
+    chosen, acc, capped = [], 0, 0
     for b in np.random.default_rng(seed).permutation(nb):
         if not two[b] or sizes[b] < 2:
             continue
-        chosen.append(b)
-        acc += sizes[b]
+        take = int(sizes[b]) if cap_rows is None else int(min(sizes[b], cap_rows))
+        capped += take < sizes[b]
+        chosen.append((int(b), take))
+        acc += take
         if acc >= target:
             break
-    chosen = np.sort(np.array(chosen))
-    rows = np.nonzero(np.isin(bucket, chosen))[0]
-    desc = (f"{len(chosen)} of {nb} lens-buckets (seeded shuffle, none excluded; largest {int(sizes[chosen].max()) if len(chosen) else 0} rows), "
-            f"{len(rows)} of {inp.n_rows} rows")
+    chosen.sort()
+    rows = np.concatenate([np.arange(starts[b], starts[b] + take) for b, take in chosen]) if chosen else np.zeros(0, dtype=np.int64)
+    desc = (f"{len(chosen)} of {nb} lens-buckets (seeded shuffle, none excluded; largest {max((t for _, t in chosen), default=0)} rows"
+            + (f"; {capped} truncated to their first {cap_rows} rows" if cap_rows is not None else "") + f"), {len(rows)} of {inp.n_rows} rows")
     return inp.take_rows(rows), desc
 
 
@@ -163,26 +168,29 @@ def run_reference_arm(args, rank):
     side = rep.to_join_input()
     rep.close()
     full = pyoracle.run(p, side.c_ptr(), threads=0)
-    side_sample, side_desc = cpu_sample(side, row_fraction=0.10)
-    ss = pyoracle.run(p, side_sample.c_ptr(), threads=0)
-    full_v, samp_v = full["pairs_scored"] / full["seconds_join"], ss["pairs_scored"] / ss["seconds_join"]
-    del side, side_sample
     rep = E.generate(MAIN_CONFIG, n_cells=args.cells)
     inp = rep.to_join_input()
     rep.close()
-    # The sample is sized so that the W + K passes together take about a minute: start from the fraction that would do so at
-    # the rate measured in round 2 (2 % of configs[4]'s rows = 40 s per pass on 16 threads), time one calibration pass, and
-    # rescale (at most three times; the sample is always a prefix of the same seeded shuffle, no bucket excluded).
+    # The sample is sized so that the W + K passes together take about a minute.  The reference's parallelism is one thread
+    # per lens-bucket (join.rs:582), so a pass lasts as long as its slowest bucket: a bucket contributes at most its first
+    # `cap` rows, and about one bucket per host thread is taken.  One calibration pass, then cap is rescaled with the square
+    # root of the time ratio (pairs grow with rows squared), at most three times.
     n_pass = max(1, args.warmup + args.steps)
     budget_s = 75.0
-    frac = 0.02 * min(1.0, budget_s / (40.0 * n_pass))
-    sample, desc = cpu_sample(inp, row_fraction=frac)
+    n_thr = os.cpu_count() or 8
+    cap = int(max(300, min(30000, 5500 * (budget_s / (3.0 * n_pass)) ** 0.5)))   # ~5e6 pairs/s per thread: 5500 rows = 3 s
+    sample, desc = cpu_sample(inp, row_fraction=min(0.02, n_thr * cap / max(inp.n_rows, 1)), cap_rows=cap)
     for _ in range(3):
         t_cal = pyoracle.run(p, sample.c_ptr(), threads=0)["seconds_join"]
-        if t_cal * n_pass <= 1.6 * budget_s or frac <= 2e-4:
+        if t_cal * n_pass <= 1.6 * budget_s or cap <= 300:
             break
-        frac *= max(0.05, min(0.7, budget_s / (t_cal * n_pass)))
-        sample, desc = cpu_sample(inp, row_fraction=frac)
+        cap = int(max(300, cap * max(0.2, min(0.8, (budget_s / (t_cal * n_pass)) ** 0.5))))
+        sample, desc = cpu_sample(inp, row_fraction=min(0.02, n_thr * cap / max(inp.n_rows, 1)), cap_rows=cap)
+    # the bias of THIS rule, measured where the whole workload is affordable
+    side_sample, side_desc = cpu_sample(side, row_fraction=min(0.10, 4 * n_thr * cap / max(side.n_rows, 1)), cap_rows=cap)
+    ss = pyoracle.run(p, side_sample.c_ptr(), threads=0)
+    full_v, samp_v = full["pairs_scored"] / full["seconds_join"], ss["pairs_scored"] / ss["seconds_join"]
+    del side, side_sample
     times, pairs, threads = [], 0, 0
     for i in range(args.warmup + args.steps):
         r = pyoracle.run(p, sample.c_ptr(), threads=0)
