@@ -2373,7 +2373,7 @@ int ejb_part_forest(ejb_ctx* c, int64_t* n_edges, const unsigned long long** d_e
 }
 
 // Device buffers (on the merging context) that receive the concatenated partial forests of ALL parts, `total` entries:
-// 8-byte edge weights and 24-byte tuples.  The caller fills them (NCCL gather, peer copies), then calls ejb_merge_parts.
+// 8-byte edge weights and 32-byte tuples.  The caller fills them (NCCL gather, peer copies), then calls ejb_merge_parts.
 int ejb_merge_buffers(ejb_ctx* c, int64_t total, unsigned long long** d_edges, void** d_tuples) {
     if (!c || total < 0) return EJB_ERR_INVALID;
     if (!c->have_part) return fail(c, EJB_ERR_INVALID, "ejb_merge_buffers without a sharded ejb_run on the merging context");

@@ -1,4 +1,4 @@
-// ejb_p1.cuh — p1 cache and the double-double evaluation kernel (join_one.rs:22-43).
+// ejb_p1.cuh — the per-join p1 memo, its term groups and the double-double evaluation kernels (join_one.rs:22-43).
 #pragma once
 #include "ejb_types.cuh"
 

@@ -11,7 +11,7 @@
 //                                join_one.rs:238-267, 301-440, 474-493, region diffs of :766-854
 //                   k_stage2b    barcode meet, score, JUN_SHARE, V names, FWR1/CDR12, join_one.rs:451-470,
 //                                499-567, 710-854
-//   ejb_p1.cuh      k_p1         p_at_most_m_distinct_in_sample_of_x_from_n_double, join_one.rs:22-43
+//   ejb_p1.cuh      k_p1_*       p_at_most_m_distinct_in_sample_of_x_from_n_double, join_one.rs:22-43
 //   ejb_forest.cuh  k_bor_*      lexicographic spanning forest == pot of join_core.rs:23-50
 //                   k_two_cell / k_exact_union / k_labels   join.rs:120-178, join2.rs:69-84
 #pragma once

@@ -323,7 +323,7 @@ int ejb_set_shard(ejb_ctx* ctx, int rank, int world);
 
 /* join_one for ARBITRARY pairs of rows of the input of the last completed ejb_join / ejb_run on this context: the second use the
  * reference makes of the pair predicate, define_mat's extra raw joins (enclone_process/src/define_mat.rs:172,247).  Same
- * kernels as the join (k_stage2a / k_stage2_slow / k_p1 / k_stage2b), without the same-class skip: every pair is decided on its
+ * kernels as the join (k_stage2a / k_stage2_slow / k_p1_* / k_stage2b), without the same-class skip: every pair is decided on its
  * own, in the ORDER given (join_one(k1, k2) reads a few facts from its first argument only).  pass[i] = what join_one returns
  * (the caller filters on equal lens first, as define_mat.rs does; pairs with different lens or a row without exactly two
  * chains are answered 0).  The other arrays receive the PotentialJoin members join_one would have pushed (meaningful where
